@@ -1,0 +1,81 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (build container only).
+
+    python -m oracle.make_golden
+
+For each case: seeded synthetic counts (oracle.cavi_numpy.synth_counts), `np.random.seed(1)`,
+construct the reference model with `use_factors=False` (zigap.py:55-77, base.py:15-52), copy the
+state vector out (this is the hand-off point of every parity run), then call the
+reference's own `step()` (base.py:54-56) and record the trajectory.  Also records one raw call of
+the reference's numba Z kernels (zigap.py:79-95, gap.py:67-80) and the special-function KATs of
+test/test.py:13-32.
+"""
+import os
+import numpy as np
+from oracle import refshim, cavi_numpy as cn
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+# name, model, n, p, K, steps recorded, zinb
+CASES = [
+    ('zigap_c1', 'ZIGaP', 100, 500, 2, (1, 2, 5, 50), True),     # BASELINE.json configs[0]
+    ('gap_c1', 'GaP', 100, 500, 2, (1, 2, 5, 50), True),
+    ('zigap_ragged', 'ZIGaP', 193, 331, 5, (1, 3, 10), False),   # nothing divides a tile; K odd
+    ('gap_ragged', 'GaP', 131, 257, 7, (1, 3, 10), False),
+    ('zigap_k10', 'ZIGaP', 300, 260, 10, (1, 4), True),          # K of configs[1]
+]
+
+
+def main():
+    ref = refshim.import_reference()
+    from oriana.models import ZIGaP, GaP
+    from oriana.singlecell import CountMatrix
+    from oriana import utils as rutils
+    os.makedirs(OUT, exist_ok=True)
+
+    for name, model, n, p, K, rec, zinb in CASES:
+        X = cn.synth_counts(n, p, K, seed=len(name) * 7 + n, zinb=zinb)
+        np.random.seed(1)
+        m = (ZIGaP if model == 'ZIGaP' else GaP)(CountMatrix(X), k=K, use_factors=False)
+        out = {'model': model, 'K': K, 'steps': np.asarray(rec)}
+        s0 = refshim.snapshot(m)
+        out['X'] = s0.pop('X').astype(np.int32)
+        for k, v in s0.items():
+            out['s0_' + k] = v.astype(np.float32) if k == 'p_d' else v
+        # one raw call of the numba kernel on the initial expectations
+        lU = np.ascontiguousarray(m.log_U_hat); lV = np.ascontiguousarray(m.log_V_hat)
+        X32 = m.X[:].astype(np.float32)
+        Zi = np.empty((n, K), np.float32); Zj = np.empty((p, K), np.float32)
+        if model == 'ZIGaP':
+            Z3 = np.empty((p, K), np.float32)
+            ZIGaP.compute_Z_q_expectations(Zi, Zj, Z3, lU, lV, m.D_hat, X32)
+        else:
+            GaP.compute_Z_q_expectations(Zi, Zj, lU, lV, X32)
+        out.update(z_log_U_hat=lU, z_log_V_hat=lV, z_Zi=Zi, z_Zj=Zj)
+        for t in range(1, max(rec) + 1):
+            m.step()
+            if t in rec:
+                st = refshim.snapshot(m); st.pop('X')
+                for k, v in st.items():
+                    out['s%d_%s' % (t, k)] = v.astype(np.float32) if k == 'p_d' else v
+                out['s%d_U_hat' % t] = np.asarray(m.U_hat); out['s%d_V_hat' % t] = np.asarray(m.V_hat)
+                out['s%d_log_U_hat' % t] = np.asarray(m.log_U_hat)
+                out['s%d_log_V_hat' % t] = np.asarray(m.log_V_hat)
+        np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+        print(name, 'written', {k: getattr(v, 'shape', None) for k, v in list(out.items())[:4]})
+
+    # special-function known answers, produced by the reference's own utils (utils.py:9-51)
+    x = np.concatenate([np.asarray([0.54, 6.2, 1.2, 0.3, 7.9, 4.5, 2.1]),          # test/test.py:24
+                        np.logspace(-15, 8, 70), np.asarray([1.0, 2.0, 0.5, 1e-3, 3.0, 5.999, 6.0, 6.001])])
+    y = np.concatenate([np.asarray([0.54, 6.2, 1.2, 0.3, 7.9, 4.5, 2.1]), np.linspace(-30, 12, 85)])
+    z = np.concatenate([np.asarray([-2.3, 1.5, 0.45, -0.78, 5.3, -.2, 0.]), np.linspace(-40, 40, 81)])  # test.py:14
+    q = np.concatenate([np.asarray([0.45, 0.001, 0.9987, 0.63, 0.745, 0.521, 0.32]),                    # test.py:19
+                        np.asarray([0., 1., 1e-20, 1 - 1e-17, 1e-10, 1 - 1e-10])])
+    np.savez_compressed(os.path.join(OUT, 'special.npz'),
+                        x=x, digamma=rutils.digamma(x), trigamma=rutils.digamma_prime(x),
+                        y=y, inverse_digamma=rutils.inverse_digamma(y),
+                        z=z, sigmoid=rutils.sigmoid(z), q=q, logit=rutils.logit(q))
+    print('special written')
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,54 @@
+/* oracle/zloop.c -- TEST INFRASTRUCTURE (see oracle/__init__.py).
+ *
+ * Plain-C restatement of the reference's four-deep numba loops, same loop order, same
+ * float32 arithmetic and the same SEQUENTIAL float32 accumulation:
+ *   zl_zigap_z  <- ZIGaP.compute_Z_q_expectations, oriana/models/zigap.py:79-95
+ *   zl_gap_z    <- GaP.compute_Z_q_expectations,   oriana/models/gap.py:67-80
+ * All arrays are C-contiguous float32 (the numba eager signature, zigap.py:79).
+ * `quirk` != 0 reproduces zigap.py:94 (D_hat[i, k]); 0 uses D_hat[i, j] (sparse_zigap.py:115).
+ * The third output (DZ_exp_logsum_hat, zigap.py:95) is never read by ZIGaP and is omitted.
+ * Build: make -C oracle   (gcc -O2, no -ffast-math: numba 0.41 compiled without fastmath).
+ */
+#include <math.h>
+#include <stddef.h>
+#include <string.h>
+
+#define MAXK 256
+
+void zl_zigap_z(float *Zi, float *Zj, const float *lU, const float *lV, const float *D,
+                const float *X, long n, long p, long K, int quirk)
+{
+    float e[MAXK];
+    memset(Zi, 0, sizeof(float) * (size_t)(n * K));
+    memset(Zj, 0, sizeof(float) * (size_t)(p * K));
+    for (long i = 0; i < n; ++i)
+        for (long j = 0; j < p; ++j) {
+            float den = 0.f;
+            for (long k = 0; k < K; ++k) { e[k] = expf(lU[i * K + k] + lV[j * K + k]); den += e[k]; }
+            if (!(den > 0.f)) den = 1.f;
+            for (long k = 0; k < K; ++k) {
+                float t = X[i * p + j] * e[k] / den;
+                Zi[i * K + k] += D[i * p + j] * t;
+                Zj[j * K + k] += (quirk ? D[i * p + k] : D[i * p + j]) * t;
+            }
+        }
+}
+
+void zl_gap_z(float *Zi, float *Zj, const float *lU, const float *lV, const float *X,
+              long n, long p, long K)
+{
+    float e[MAXK];
+    memset(Zi, 0, sizeof(float) * (size_t)(n * K));
+    memset(Zj, 0, sizeof(float) * (size_t)(p * K));
+    for (long i = 0; i < n; ++i)
+        for (long j = 0; j < p; ++j) {
+            float den = 0.f;
+            for (long k = 0; k < K; ++k) { e[k] = expf(lU[i * K + k] + lV[j * K + k]); den += e[k]; }
+            if (!(den > 0.f)) den = 1.f;
+            for (long k = 0; k < K; ++k) {
+                float t = X[i * p + j] * e[k] / den;
+                Zj[j * K + k] += t;
+                Zi[i * K + k] += t;
+            }
+        }
+}

@@ -1,0 +1,44 @@
+"""ctypes binding of oracle/zloop.c (TEST INFRASTRUCTURE, see oracle/__init__.py)."""
+import ctypes, os, subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, '_build', 'libzloop.so')
+
+
+def build():
+    src = os.path.join(_HERE, 'zloop.c')
+    if not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(['make', '-C', _HERE, '-s'])
+    return _SO
+
+
+def _lib():
+    lib = ctypes.CDLL(build())
+    fp = ctypes.POINTER(ctypes.c_float)
+    lib.zl_zigap_z.argtypes = [fp] * 6 + [ctypes.c_long] * 3 + [ctypes.c_int]
+    lib.zl_gap_z.argtypes = [fp] * 5 + [ctypes.c_long] * 3
+    return lib
+
+
+def _p(a):
+    assert a.dtype == np.float32 and a.flags.c_contiguous
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def zigap_z(log_U_hat, log_V_hat, D_hat, X, quirk=True):
+    """zigap.py:79-95 as a sequential float32 loop; returns (DZ_hat_i, DZ_hat_j)."""
+    n, K = log_U_hat.shape; p = log_V_hat.shape[0]
+    Zi = np.empty((n, K), np.float32); Zj = np.empty((p, K), np.float32)
+    a = [np.ascontiguousarray(x, dtype=np.float32) for x in (log_U_hat, log_V_hat, D_hat, X)]
+    _lib().zl_zigap_z(_p(Zi), _p(Zj), *[_p(x) for x in a], n, p, K, int(bool(quirk)))
+    return Zi, Zj
+
+
+def gap_z(log_U_hat, log_V_hat, X):
+    """gap.py:67-80 as a sequential float32 loop; returns (Z_hat_i, Z_hat_j)."""
+    n, K = log_U_hat.shape; p = log_V_hat.shape[0]
+    Zi = np.empty((n, K), np.float32); Zj = np.empty((p, K), np.float32)
+    a = [np.ascontiguousarray(x, dtype=np.float32) for x in (log_U_hat, log_V_hat, X)]
+    _lib().zl_gap_z(_p(Zi), _p(Zj), *[_p(x) for x in a], n, p, K)
+    return Zi, Zj

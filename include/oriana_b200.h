@@ -1,0 +1,169 @@
+/* oriana_b200.h -- C ABI of the B200-native PCMF CAVI hot path.
+ *
+ * Drop-in boundary for ONE path of AntoinePassemiers/Oriana: `FactorModel.step()`
+ * (oriana/models/base.py:54-56) for the ZIGaP and GaP models, i.e. the E-step
+ * `update_variational_parameters` (oriana/models/zigap.py:97-141, gap.py:82-115) with its numba kernel
+ * `compute_Z_q_expectations` (zigap.py:79-95, gap.py:67-80), the node expectations `Gamma.mean/meanlog`
+ * (oriana/nodes/probabilistic/gamma.py:37-61), `Bernoulli.mean` (bernoulli.py:41-48), and the M-step
+ * `update_prior_hyper_parameters` (zigap.py:143-158, gap.py:117-129) with `inverse_digamma`
+ * (oriana/utils.py:39-51).
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; every DEVICE buffer is owned by the caller (PyTorch allocates);
+ *     the library never allocates or frees device memory behind the caller's back, except inside the
+ *     `*_host` entry points, which take HOST pointers and manage their own staging buffers;
+ *   - device entry points are stream-ordered on the `stream` argument (a cudaStream_t passed as void*),
+ *     never synchronise the device and never touch the host copy of any result;
+ *   - return 0 on success, a negative ORI_E* code otherwise; `ori_last_error` gives the message;
+ *   - accumulators are zero-filled by the callee, like the reference kernels (zigap.py:81-83).
+ * There is NO CPU fallback anywhere in this library.
+ */
+#ifndef ORIANA_B200_H
+#define ORIANA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORI_OK 0
+#define ORI_EINVAL (-1)   /* bad argument (shape, alignment, null pointer)   */
+#define ORI_ECUDA (-2)    /* a CUDA runtime call or kernel launch failed      */
+#define ORI_ENODEV (-3)   /* no sm_100 device                                 */
+#define ORI_EUNSUPPORTED (-4)
+
+/* flags of ori_problem_t::flags */
+#define ORI_F_DROPOUT 1u      /* ZIGaP (zero-inflation layer D); clear = GaP                              */
+#define ORI_F_QUIRK 2u        /* reproduce zigap.py:94: Zj weighted by D_hat[i, k] instead of D_hat[i, j] */
+#define ORI_F_ELBO 4u         /* accumulate the ELBO terms inside the row pass                            */
+#define ORI_F_NO_TENSOR 8u    /* force the CUDA-core kernels (tests); default picks tcgen05 when it can   */
+
+/* modes of ori_mstep */
+#define ORI_M_STEP 0          /* regular end of iteration t+1: finalise ELBO(t), pi(t); M-step; next lp   */
+#define ORI_M_INIT 1          /* after ori_init_expectations: M-step on the initial expectations          */
+#define ORI_M_INIT_KEEP 2     /* same but keep the caller's alpha/beta (state copied from a model)        */
+#define ORI_M_FINALIZE 3      /* flush: pi(t) and ELBO(t) of the CURRENT state, nothing else changes      */
+#define ORI_M_REFRESH 4       /* after ori_init_expectations on edited (a,b): only the pending ELBO terms  */
+
+/* One rank's view of the problem.  Factor arrays are row-major with row stride KP (K padded to a
+ * multiple of 8, pad columns hold zeros).  "gen" arrays are ping-pong generations of the row factors:
+ * the gene pass needs U_hat(t) (to rebuild D_hat(t)) and U_hat(t+1) at the same time (zigap.py:124).   */
+typedef struct ori_problem {
+    int64_t n_rows;        /* cells owned by this rank                                   */
+    int64_t n_total;       /* cells over all ranks (denominator of the M-step means)     */
+    int64_t ldx;           /* row stride of X in elements (multiple of 4)                */
+    int32_t p;             /* genes                                                      */
+    int32_t K;             /* latent dimension                                           */
+    int32_t KP;            /* padded latent dimension: 8, 16, 32 or 64                   */
+    uint32_t flags;        /* ORI_F_*                                                    */
+    int32_t iter;          /* completed iterations (index into elbo_trace)               */
+    int32_t trace_cap;     /* capacity of elbo_trace                                     */
+
+    const float* X;        /* [n_rows x ldx] counts as float32 (zigap.py:112)            */
+
+    /* row side, [n_rows x KP] float32 */
+    float* a1;             /* Gamma shape of q(U)   zigap.py:115                         */
+    float* a2;             /* Gamma rate  of q(U)   zigap.py:116                         */
+    float* U_hat[2];       /* E[U]      = a1/a2             gamma.py:37-46               */
+    float* eU[2];          /* exp(E[log U]) = exp(psi(a1))/a2   gamma.py:48-61           */
+    float* eUw;            /* eU * D_hat[:, :K] (quirk operand, zigap.py:94) or NULL     */
+    float* Zi;             /* accumulator  sum_j R_ij eV_jk                              */
+    float* a2s;            /* accumulator  sum_j D_hat_ij V_hat_jk                       */
+
+    /* gene side, [p x KP] float32 (replicated on every rank) */
+    float* b1;             /* zigap.py:123 */
+    float* b2;             /* zigap.py:124 */
+    float* V_hat;
+    float* eV;
+    float* red32;          /* [2 x p x KP]: Zj partial | b2s partial -- allreduce(sum) buffer #1 */
+
+    float* lp;             /* [p] logit(pi) generating the CURRENT D_hat; -inf: D_hat=(X>0) (zigap.py:77) */
+    float* pfloor;         /* [p] 1e-10 where pi<=0 (zigap.py:133), else 0               */
+
+    /* float64 small state */
+    double* hyper;         /* [4 x K] alpha1 | alpha2 | beta1 | beta2                    */
+    double* red64;         /* [p + 2KP + 8] colsum D_hat | sum_i log U_hat | sum_i U_hat | ELBO partials
+                              -- allreduce(sum) buffer #2                                 */
+    double* gsum;          /* [2KP + 8] sum_j log V_hat | sum_j V_hat | entropy           */
+    double* pi_d;          /* [p] Bernoulli prior pi(t)  zigap.py:158                    */
+    double* scal;          /* [16] see ScalSlot in csrc/common.cuh                       */
+    double* elbo_trace;    /* [trace_cap]                                                */
+} ori_problem_t;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+int ori_version(void);
+/* Copies the last error message of the calling thread into buf; returns its length. */
+int ori_last_error(char* buf, size_t len);
+/* 0 when device `dev` is an sm_100 part, ORI_ENODEV otherwise. */
+int ori_device_check(int dev);
+
+/* ---- special functions on device arrays (oriana/utils.py:9-51; KATs test/test.py:13-32) -------- */
+/* op: 0 digamma, 1 trigamma (digamma_prime), 2 inverse_digamma, 3 sigmoid, 4 logit */
+int ori_special_f64(int op, const double* in, double* out, int64_t count, void* stream);
+
+/* ---- node expectations (gamma.py:37-61): E = a1/a2, Elog = psi(a1) - log(a2), eE = exp(Elog) ---- */
+/* any of E, Elog, eE may be NULL */
+int ori_gamma_expect_f32(const float* a1, const float* a2, float* E, float* Elog, float* eE,
+                         int64_t count, void* stream);
+
+/* ---- the CAVI iteration, device-resident state -------------------------------------------------- */
+/* Validate a problem description (shapes, alignment, null pointers). */
+int ori_problem_check(const ori_problem_t* P);
+/* Constant data statistics: sum lgamma(X+1), nnz -> scal; column sums of (X>0) -> red64[0..p). */
+int ori_count_stats(const ori_problem_t* P, void* stream);
+/* Expectations of generation `gen` from (a1,a2,b1,b2) (zigap.py:160-165) + their column sums. */
+int ori_init_expectations(const ori_problem_t* P, int gen, void* stream);
+/* Row pass ("KA"): Zi, a2s, colsum D_hat, ELBO partials from X and the state of generation gen_old. */
+int ori_pass_rows(const ori_problem_t* P, int gen_old, void* stream);
+/* U update (zigap.py:115-120) into generation 1-gen_old, plus sum_i log U_hat, sum_i U_hat. */
+int ori_row_update(const ori_problem_t* P, int gen_old, int write_state, void* stream);
+/* Gene pass ("KA'"): Zj and b2s = D_hat^T U_hat_new (zigap.py:94,124) into red32. */
+int ori_pass_genes(const ori_problem_t* P, int gen_old, void* stream);
+/* V update (zigap.py:123-128) from red32 (already summed over ranks). */
+int ori_gene_update(const ori_problem_t* P, int write_state, void* stream);
+/* M-step / finalisation (zigap.py:143-158), see ORI_M_*; reads red64 (already summed over ranks). */
+int ori_mstep(const ori_problem_t* P, int mode, void* stream);
+/* Convenience for world size 1: one full `step()` (base.py:54-56) = zero accumulators, row pass,
+ * U update, gene pass, V update, M-step.  Flips the generation: new state is in 1-gen_old. */
+int ori_cavi_step(const ori_problem_t* P, int gen_old, void* stream);
+/* First half / second half of the above around the caller's allreduce of red32 and red64. */
+int ori_cavi_step_local(const ori_problem_t* P, int gen_old, void* stream);
+int ori_cavi_step_global(const ori_problem_t* P, int gen_old, void* stream);
+/* Flush of the one-pass lag: pi(t), ELBO(t) of the current state (generation gen). Local part,
+ * then (after the caller's allreduce of red64) ori_mstep(P, ORI_M_FINALIZE). */
+int ori_finalize_local(const ori_problem_t* P, int gen, void* stream);
+
+/* Materialise D_hat = float32(p_d) (zigap.py:131-136) for rows [row0, row0+nrows) of generation gen. */
+int ori_dropout_posterior_f32(const ori_problem_t* P, int gen, float* out, int64_t ldo,
+                              int64_t row0, int64_t nrows, void* stream);
+
+/* ---- operator-level drop-ins with HOST buffers (the reference's plugin seam) -------------------- */
+/* Same argument list and semantics as `ZIGaP.compute_Z_q_expectations` (zigap.py:79-95): every array
+ * is a C-contiguous float32 HOST array; DZ_hat_i [n x K], DZ_hat_j [p x K] are overwritten.
+ * DZ_exp_logsum_hat may be NULL (never read by the reference, zigap.py:95); when given it is filled.
+ * `quirk` != 0 weights DZ_hat_j by D_hat[i, k] exactly like zigap.py:94.  Synchronous. */
+int ori_zigap_compute_Z_q_expectations_host(float* DZ_hat_i, float* DZ_hat_j, float* DZ_exp_logsum_hat,
+                                            const float* log_U_hat, const float* log_V_hat,
+                                            const float* D_hat, const float* X,
+                                            int64_t n, int64_t p, int64_t K, int quirk);
+/* `GaP.compute_Z_q_expectations` (gap.py:67-80). */
+int ori_gap_compute_Z_q_expectations_host(float* Z_hat_i, float* Z_hat_j,
+                                          const float* log_U_hat, const float* log_V_hat,
+                                          const float* X, int64_t n, int64_t p, int64_t K);
+
+/* ---- synthetic counts on device (bench only) ------------------------------- */
+/* X[i, j] = Poisson(g_ij * sum_k U*[i,k] V*[j,k]) * Bernoulli(pi_j) with U*, V* ~ Gamma(2, 1/2),
+ * g ~ Gamma(2, 1/2) (negative-binomial over-dispersion; nb = 0 gives plain Poisson) and keep
+ * probability pi_j ~ Beta(1, 1/z - 1); counter-based RNG (Philox-4x32-10) keyed by (seed, GLOBAL row,
+ * gene), so any row sharding produces the same matrix.  Rows [row0, row0+n_rows) are written.
+ * Scratch (caller-owned, device): Ustar [n_rows x K], Vstar [p x K], pi [p]. */
+int ori_synth_counts_f32(float* X, int64_t ldx, int64_t row0, int64_t n_rows, int32_t p, int32_t K,
+                         uint64_t seed, float zero_level, int nb, float* Ustar, float* Vstar, float* pi,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORIANA_B200_H */

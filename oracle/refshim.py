@@ -34,6 +34,15 @@ def import_reference():
     return oriana
 
 
+def release_reference():
+    """Undo import_reference(): drop the reference modules and its sys.path entry, so that the repo's own
+    `oriana` alias package is importable again in the same process."""
+    for k in [k for k in sys.modules if k == 'oriana' or k.startswith('oriana.')]:
+        del sys.modules[k]
+    while REFERENCE_ROOT in sys.path:
+        sys.path.remove(REFERENCE_ROOT)
+
+
 STATE_KEYS_ZIGAP = ('a1', 'a2', 'b1', 'b2', 'p_d', 'pi_d', 'alpha1', 'alpha2', 'beta1', 'beta2')
 STATE_KEYS_GAP = ('a1', 'a2', 'b1', 'b2', 'alpha1', 'alpha2', 'beta1', 'beta2')
 

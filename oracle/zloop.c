@@ -6,7 +6,7 @@
  *   zl_gap_z    <- GaP.compute_Z_q_expectations,   oriana/models/gap.py:67-80
  * All arrays are C-contiguous float32 (the numba eager signature, zigap.py:79).
  * `quirk` != 0 reproduces zigap.py:94 (D_hat[i, k]); 0 uses D_hat[i, j] (sparse_zigap.py:115).
- * The third output (DZ_exp_logsum_hat, zigap.py:95) is never read by ZIGaP and is omitted.
+ * The third output (DZ_exp_logsum_hat, zigap.py:95; never read by ZIGaP) is filled when Z3 != NULL.
  * Build: make -C oracle   (gcc -O2, no -ffast-math: numba 0.41 compiled without fastmath).
  */
 #include <math.h>
@@ -15,21 +15,23 @@
 
 #define MAXK 256
 
-void zl_zigap_z(float *Zi, float *Zj, const float *lU, const float *lV, const float *D,
+void zl_zigap_z(float *Zi, float *Zj, float *Z3, const float *lU, const float *lV, const float *D,
                 const float *X, long n, long p, long K, int quirk)
 {
-    float e[MAXK];
+    float e[MAXK], ls[MAXK];
+    if (Z3) memset(Z3, 0, sizeof(float) * (size_t)(p * K));
     memset(Zi, 0, sizeof(float) * (size_t)(n * K));
     memset(Zj, 0, sizeof(float) * (size_t)(p * K));
     for (long i = 0; i < n; ++i)
         for (long j = 0; j < p; ++j) {
             float den = 0.f;
-            for (long k = 0; k < K; ++k) { e[k] = expf(lU[i * K + k] + lV[j * K + k]); den += e[k]; }
+            for (long k = 0; k < K; ++k) { ls[k] = lU[i * K + k] + lV[j * K + k]; e[k] = expf(ls[k]); den += e[k]; }
             if (!(den > 0.f)) den = 1.f;
             for (long k = 0; k < K; ++k) {
                 float t = X[i * p + j] * e[k] / den;
                 Zi[i * K + k] += D[i * p + j] * t;
                 Zj[j * K + k] += (quirk ? D[i * p + k] : D[i * p + j]) * t;
+                if (Z3) Z3[j * K + k] += D[i * p + j] * t * ls[k];
             }
         }
 }

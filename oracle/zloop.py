@@ -16,7 +16,7 @@ def build():
 def _lib():
     lib = ctypes.CDLL(build())
     fp = ctypes.POINTER(ctypes.c_float)
-    lib.zl_zigap_z.argtypes = [fp] * 6 + [ctypes.c_long] * 3 + [ctypes.c_int]
+    lib.zl_zigap_z.argtypes = [fp] * 7 + [ctypes.c_long] * 3 + [ctypes.c_int]
     lib.zl_gap_z.argtypes = [fp] * 5 + [ctypes.c_long] * 3
     return lib
 
@@ -26,13 +26,14 @@ def _p(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
 
 
-def zigap_z(log_U_hat, log_V_hat, D_hat, X, quirk=True):
-    """zigap.py:79-95 as a sequential float32 loop; returns (DZ_hat_i, DZ_hat_j)."""
+def zigap_z(log_U_hat, log_V_hat, D_hat, X, quirk=True, third=False):
+    """zigap.py:79-95 as a sequential float32 loop; returns (DZ_hat_i, DZ_hat_j[, DZ_exp_logsum_hat])."""
     n, K = log_U_hat.shape; p = log_V_hat.shape[0]
     Zi = np.empty((n, K), np.float32); Zj = np.empty((p, K), np.float32)
+    Z3 = np.empty((p, K), np.float32) if third else None
     a = [np.ascontiguousarray(x, dtype=np.float32) for x in (log_U_hat, log_V_hat, D_hat, X)]
-    _lib().zl_zigap_z(_p(Zi), _p(Zj), *[_p(x) for x in a], n, p, K, int(bool(quirk)))
-    return Zi, Zj
+    _lib().zl_zigap_z(_p(Zi), _p(Zj), _p(Z3) if third else None, *[_p(x) for x in a], n, p, K, int(bool(quirk)))
+    return (Zi, Zj, Z3) if third else (Zi, Zj)
 
 
 def gap_z(log_U_hat, log_V_hat, X):

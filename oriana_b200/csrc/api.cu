@@ -1,0 +1,411 @@
+// api.cu -- extern "C" entry points of liboriana_b200.so (declared in include/oriana_b200.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include "common.cuh"
+#include "special.cuh"
+
+namespace ori {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_launch(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(ORI_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+    return ORI_OK;
+}
+
+#define ORI_CUDA(call)                                                                             \
+    do {                                                                                           \
+        const cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) return ori::set_error(ORI_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define ORI_TRY(call)              \
+    do {                           \
+        const int r_ = (call);     \
+        if (r_ != ORI_OK) return r_; \
+    } while (0)
+
+// ---- small elementwise kernels --------------------------------------------------------------------
+__global__ void k_special_f64(int op, const double* __restrict__ in, double* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = in[i];
+    double y;
+    switch (op) {
+        case 0: y = digamma_f64(x); break;
+        case 1: y = trigamma_f64(x); break;
+        case 2: y = inverse_digamma_f64(x); break;
+        case 3: y = sigmoid_f64(x); break;
+        default: y = logit_f64(x); break;
+    }
+    out[i] = y;
+}
+
+// gamma.py:37-61
+__global__ void k_gamma_expect(const float* __restrict__ a1, const float* __restrict__ a2,
+                               float* __restrict__ E, float* __restrict__ Elog, float* __restrict__ eE,
+                               long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float h1 = a1[i], h2 = a2[i];
+    const float l = (float)digamma_f64((double)h1) - logf(h2);
+    if (E) E[i] = (float)((double)h1 / (double)h2);
+    if (Elog) Elog[i] = l;
+    if (eE) eE[i] = expf(l);
+}
+
+// operator-level helpers: padded exp of a [rows x K] log-expectation array, optional extra weight
+__global__ void k_exp_pad(const float* __restrict__ logE, const float* __restrict__ W, long long ldw,
+                          int mul_log, float* __restrict__ out, long long rows, int K, int KP) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * KP) return;
+    const long long i = idx / KP; const int k = (int)(idx % KP);
+    float v = 0.f;
+    if (k < K) {
+        const float l = logE[i * K + k];
+        v = expf(l);
+        if (W) v *= W[i * ldw + k];
+        if (mul_log) v *= l;
+    }
+    out[idx] = v;
+}
+__global__ void k_mul(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] * b[i];
+}
+// out[i,k] (stride K) = acc[i,k] * e[i,k] (stride KP)  [+ acc2[i,k] * e[i,k] * l[i,k]]
+__global__ void k_scale_unpad(const float* __restrict__ acc, const float* __restrict__ e,
+                              const float* __restrict__ acc2, const float* __restrict__ l,
+                              float* __restrict__ out, long long rows, int K, int KP) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * K) return;
+    const long long i = idx / K; const int k = (int)(idx % K);
+    float v = acc[i * KP + k] * e[i * KP + k];
+    if (acc2) v += acc2[i * KP + k] * e[i * KP + k] * l[i * K + k];
+    out[idx] = v;
+}
+
+static int pad_k(long long K) { return K <= 8 ? 8 : K <= 16 ? 16 : K <= 32 ? 32 : K <= 64 ? 64 : -1; }
+
+}  // namespace ori
+
+using namespace ori;
+
+extern "C" {
+
+int ori_version(void) { return 100; }
+
+int ori_last_error(char* buf, size_t len) {
+    if (buf && len) { strncpy(buf, g_err, len - 1); buf[len - 1] = 0; }
+    return (int)strlen(g_err);
+}
+
+int ori_device_check(int dev) {
+    cudaDeviceProp prop;
+    ORI_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return set_error(ORI_ENODEV, "device %d is sm_%d%d, this library is sm_100a only", dev, prop.major, prop.minor);
+    return ORI_OK;
+}
+
+int ori_special_f64(int op, const double* in, double* out, int64_t count, void* stream) {
+    if (op < 0 || op > 4) return set_error(ORI_EINVAL, "ori_special_f64: bad op %d", op);
+    if (count < 0 || (count && (!in || !out))) return set_error(ORI_EINVAL, "ori_special_f64: null buffer");
+    if (count == 0) return ORI_OK;
+    k_special_f64<<<cdiv(count, 256), 256, 0, (cudaStream_t)stream>>>(op, in, out, count);
+    return check_launch("k_special_f64");
+}
+
+int ori_gamma_expect_f32(const float* a1, const float* a2, float* E, float* Elog, float* eE,
+                         int64_t count, void* stream) {
+    if (count < 0 || (count && (!a1 || !a2))) return set_error(ORI_EINVAL, "ori_gamma_expect_f32: null buffer");
+    if (count == 0) return ORI_OK;
+    k_gamma_expect<<<cdiv(count, 256), 256, 0, (cudaStream_t)stream>>>(a1, a2, E, Elog, eE, count);
+    return check_launch("k_gamma_expect");
+}
+
+int ori_problem_check(const ori_problem_t* P) {
+    if (!P) return set_error(ORI_EINVAL, "null problem");
+    if (P->n_rows < 0 || P->p <= 0 || P->K <= 0) return set_error(ORI_EINVAL, "bad shape n_rows=%lld p=%d K=%d", (long long)P->n_rows, P->p, P->K);
+    if (P->K > 64) return set_error(ORI_EUNSUPPORTED, "K=%d > 64 is not supported", P->K);
+    if (P->KP != pad_k(P->K)) return set_error(ORI_EINVAL, "KP=%d, expected %d for K=%d", P->KP, pad_k(P->K), P->K);
+    if (P->ldx < P->p || (P->ldx & 3)) return set_error(ORI_EINVAL, "ldx=%lld must be >= p and a multiple of 4", (long long)P->ldx);
+    if (P->n_total < P->n_rows || P->n_total <= 0) return set_error(ORI_EINVAL, "n_total=%lld < n_rows", (long long)P->n_total);
+    if ((P->flags & ORI_F_QUIRK) && P->p < P->K) return set_error(ORI_EINVAL, "quirk mode needs p >= K (zigap.py:94 reads D_hat[i, k])");
+    const void* need[] = {P->a1, P->a2, P->U_hat[0], P->U_hat[1], P->eU[0], P->eU[1], P->Zi, P->b1, P->b2,
+                          P->V_hat, P->eV, P->red32, P->hyper, P->red64, P->gsum, P->scal, P->elbo_trace};
+    for (size_t i = 0; i < sizeof(need) / sizeof(need[0]); ++i)
+        if (!need[i]) return set_error(ORI_EINVAL, "null buffer #%zu in ori_problem_t", i);
+    if (P->n_rows > 0 && !P->X) return set_error(ORI_EINVAL, "null X");
+    if (P->flags & ORI_F_DROPOUT)
+        if (!P->a2s || !P->lp || !P->pfloor || !P->pi_d) return set_error(ORI_EINVAL, "dropout buffers missing");
+    if ((P->flags & ORI_F_QUIRK) && !P->eUw) return set_error(ORI_EINVAL, "quirk mode needs eUw");
+    if (((uintptr_t)P->X & 15) || ((uintptr_t)P->eV & 15) || ((uintptr_t)P->V_hat & 15))
+        return set_error(ORI_EINVAL, "X, eV, V_hat must be 16-byte aligned");
+    return ORI_OK;
+}
+
+static size_t red64_bytes(const ori_problem_t* P) { return sizeof(double) * (size_t)(P->p + 2 * P->KP + R64_NSLOTS); }
+static size_t gsum_bytes(const ori_problem_t* P) { return sizeof(double) * (size_t)(2 * P->KP + 8); }
+static size_t rowf_bytes(const ori_problem_t* P) { return sizeof(float) * (size_t)P->n_rows * P->KP; }
+
+int ori_count_stats(const ori_problem_t* P, void* stream) {
+    ORI_TRY(ori_problem_check(P));
+    cudaStream_t st = (cudaStream_t)stream;
+    ORI_CUDA(cudaMemsetAsync(P->red64, 0, red64_bytes(P), st));
+    if (P->n_rows == 0) return ORI_OK;
+    return launch_count_stats(P, st);
+}
+
+int ori_init_expectations(const ori_problem_t* P, int gen, void* stream) {
+    ORI_TRY(ori_problem_check(P));
+    cudaStream_t st = (cudaStream_t)stream;
+    ORI_CUDA(cudaMemsetAsync(P->gsum, 0, gsum_bytes(P), st));
+    if (P->n_rows > 0) ORI_TRY(launch_row_update(P, gen, 2, st));
+    return launch_gene_update(P, 2, st);
+}
+
+int ori_pass_rows(const ori_problem_t* P, int gen_old, void* stream) {
+    ORI_TRY(ori_problem_check(P));
+    if (P->n_rows == 0) return ORI_OK;
+    return launch_pass_rows_simt(P, gen_old, (cudaStream_t)stream);
+}
+
+int ori_row_update(const ori_problem_t* P, int gen_old, int write_state, void* stream) {
+    ORI_TRY(ori_problem_check(P));
+    if (P->n_rows == 0) return ORI_OK;
+    return launch_row_update(P, gen_old, write_state, (cudaStream_t)stream);
+}
+
+int ori_pass_genes(const ori_problem_t* P, int gen_old, void* stream) {
+    ORI_TRY(ori_problem_check(P));
+    if (P->n_rows == 0) return ORI_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P->flags & ORI_F_QUIRK) ORI_TRY(launch_quirk_weights(P, gen_old, st));
+    return launch_pass_genes_simt(P, gen_old, st);
+}
+
+int ori_gene_update(const ori_problem_t* P, int write_state, void* stream) {
+    ORI_TRY(ori_problem_check(P));
+    cudaStream_t st = (cudaStream_t)stream;
+    ORI_CUDA(cudaMemsetAsync(P->gsum, 0, gsum_bytes(P), st));
+    return launch_gene_update(P, write_state, st);
+}
+
+int ori_mstep(const ori_problem_t* P, int mode, void* stream) {
+    ORI_TRY(ori_problem_check(P));
+    if (mode < 0 || mode > 4) return set_error(ORI_EINVAL, "ori_mstep: bad mode %d", mode);
+    return launch_mstep(P, mode, (cudaStream_t)stream);
+}
+
+static int zero_accumulators(const ori_problem_t* P, cudaStream_t st, bool genes) {
+    if (P->n_rows > 0) {
+        ORI_CUDA(cudaMemsetAsync(P->Zi, 0, rowf_bytes(P), st));
+        if (P->flags & ORI_F_DROPOUT) ORI_CUDA(cudaMemsetAsync(P->a2s, 0, rowf_bytes(P), st));
+    }
+    if (genes) ORI_CUDA(cudaMemsetAsync(P->red32, 0, sizeof(float) * 2 * (size_t)P->p * P->KP, st));
+    ORI_CUDA(cudaMemsetAsync(P->red64, 0, red64_bytes(P), st));
+    return ORI_OK;
+}
+
+int ori_cavi_step_local(const ori_problem_t* P, int gen_old, void* stream) {
+    ORI_TRY(ori_problem_check(P));
+    cudaStream_t st = (cudaStream_t)stream;
+    ORI_TRY(zero_accumulators(P, st, true));
+    if (P->n_rows == 0) return ORI_OK;
+    ORI_TRY(launch_pass_rows_simt(P, gen_old, st));
+    ORI_TRY(launch_row_update(P, gen_old, 1, st));
+    if (P->flags & ORI_F_QUIRK) ORI_TRY(launch_quirk_weights(P, gen_old, st));
+    return launch_pass_genes_simt(P, gen_old, st);
+}
+
+int ori_cavi_step_global(const ori_problem_t* P, int gen_old, void* stream) {
+    (void)gen_old;
+    ORI_TRY(ori_problem_check(P));
+    cudaStream_t st = (cudaStream_t)stream;
+    ORI_CUDA(cudaMemsetAsync(P->gsum, 0, gsum_bytes(P), st));
+    ORI_TRY(launch_gene_update(P, 1, st));
+    return launch_mstep(P, ORI_M_STEP, st);
+}
+
+int ori_cavi_step(const ori_problem_t* P, int gen_old, void* stream) {
+    ORI_TRY(ori_cavi_step_local(P, gen_old, stream));
+    return ori_cavi_step_global(P, gen_old, stream);
+}
+
+int ori_finalize_local(const ori_problem_t* P, int gen, void* stream) {
+    ORI_TRY(ori_problem_check(P));
+    cudaStream_t st = (cudaStream_t)stream;
+    ORI_TRY(zero_accumulators(P, st, false));
+    if (P->n_rows == 0) return ORI_OK;
+    ORI_TRY(launch_pass_rows_simt(P, gen, st));
+    return launch_row_update(P, gen, 0, st);
+}
+
+int ori_dropout_posterior_f32(const ori_problem_t* P, int gen, float* out, int64_t ldo,
+                              int64_t row0, int64_t nrows, void* stream) {
+    ORI_TRY(ori_problem_check(P));
+    if (!(P->flags & ORI_F_DROPOUT)) return set_error(ORI_EINVAL, "model has no dropout layer");
+    if (!out || ldo < P->p || row0 < 0 || row0 + nrows > P->n_rows) return set_error(ORI_EINVAL, "bad slab");
+    return launch_dropout_posterior(P, gen, out, ldo, row0, nrows, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+// ---- operator-level drop-in with HOST buffers ------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        const cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+        return e == cudaSuccess ? ORI_OK : set_error(ORI_ECUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    }
+    template <class T> T* as() { return (T*)p; }
+};
+
+static int z_operator_host(float* Zi_out, float* Zj_out, float* Z3_out, const float* logU, const float* logV,
+                           const float* D, const float* X, int64_t n, int64_t p, int64_t K, int quirk)
+{
+    if (n < 0 || p <= 0 || K <= 0) return set_error(ORI_EINVAL, "bad shape n=%lld p=%lld K=%lld", (long long)n, (long long)p, (long long)K);
+    if (p > 0x7fffffff) return set_error(ORI_EINVAL, "p too large");
+    if (!Zi_out || !Zj_out || !logU || !logV || !X) return set_error(ORI_EINVAL, "null array (the reference raises TypeError, zigap.py:79)");
+    const int KP = pad_k(K);
+    if (KP < 0) return set_error(ORI_EUNSUPPORTED, "K=%lld > 64 is not supported", (long long)K);
+    if (quirk && D && p < K) return set_error(ORI_EINVAL, "quirk mode needs p >= K");
+    if (n == 0) { memset(Zj_out, 0, sizeof(float) * p * K); if (Z3_out) memset(Z3_out, 0, sizeof(float) * p * K); return ORI_OK; }
+
+    cudaStream_t st = 0, st2 = 0;
+    ORI_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    ORI_CUDA(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+    struct Guard { cudaStream_t a, b; ~Guard() { cudaStreamDestroy(a); cudaStreamDestroy(b); } } guard{st, st2};
+
+    const int64_t ldx = (p + 3) & ~3ll;
+    // slab of cells sized to ~256 MB of X
+    int64_t slab = (256ll << 20) / (ldx * 4);
+    slab = slab < 128 ? 128 : (slab / 128) * 128;
+    if (slab > n) slab = n;
+    const int nbuf = n > slab ? 2 : 1;
+
+    DevBuf dX[2], dD[2], dlU, dlV, deV, dlogVraw, dZj, dZj3a, dZj3b, dOutJ;
+    DevBuf deU[2], deUw[2], deUl[2], dZi[2], dOutI[2], dlUs[2];
+    for (int b = 0; b < nbuf; ++b) {
+        ORI_TRY(dX[b].alloc(sizeof(float) * slab * ldx));
+        if (D) ORI_TRY(dD[b].alloc(sizeof(float) * slab * ldx));
+        ORI_TRY(dlUs[b].alloc(sizeof(float) * slab * K));
+        ORI_TRY(deU[b].alloc(sizeof(float) * slab * KP));
+        ORI_TRY(deUw[b].alloc(sizeof(float) * slab * KP));
+        if (Z3_out) ORI_TRY(deUl[b].alloc(sizeof(float) * slab * KP));
+        ORI_TRY(dZi[b].alloc(sizeof(float) * slab * KP));
+        ORI_TRY(dOutI[b].alloc(sizeof(float) * slab * K));
+    }
+    ORI_TRY(dlogVraw.alloc(sizeof(float) * p * K));
+    ORI_TRY(deV.alloc(sizeof(float) * p * KP));
+    ORI_TRY(dZj.alloc(sizeof(float) * 2 * p * KP));
+    ORI_TRY(dZj3a.alloc(sizeof(float) * 2 * p * KP));
+    ORI_TRY(dZj3b.alloc(sizeof(float) * 2 * p * KP));
+    ORI_TRY(dOutJ.alloc(sizeof(float) * p * K));
+    DevBuf dDummy64; ORI_TRY(dDummy64.alloc(sizeof(double) * (p + 2 * KP + R64_NSLOTS)));
+
+    ORI_CUDA(cudaMemcpyAsync(dlogVraw.p, logV, sizeof(float) * p * K, cudaMemcpyHostToDevice, st));
+    k_exp_pad<<<cdiv(p * KP, 256), 256, 0, st>>>(dlogVraw.as<float>(), nullptr, 0, 0, deV.as<float>(), p, (int)K, KP);
+    ORI_TRY(check_launch("k_exp_pad"));
+    ORI_CUDA(cudaMemsetAsync(dZj.p, 0, sizeof(float) * 2 * p * KP, st));
+    ORI_CUDA(cudaMemsetAsync(dZj3a.p, 0, sizeof(float) * 2 * p * KP, st));
+    ORI_CUDA(cudaMemsetAsync(dZj3b.p, 0, sizeof(float) * 2 * p * KP, st));
+
+    cudaEvent_t done[3];  // [0],[1]: last work on each stream; [2]: gene-side operands ready
+    for (int b = 0; b < 3; ++b) ORI_CUDA(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
+    struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 3; ++i) cudaEventDestroy(e[i]); } } evg{done};
+    ORI_CUDA(cudaEventRecord(done[2], st));
+    ORI_CUDA(cudaStreamWaitEvent(st2, done[2], 0));
+
+    ori_problem_t P;
+    memset(&P, 0, sizeof(P));
+    P.p = (int)p; P.K = (int)K; P.KP = KP; P.ldx = ldx;
+    P.eV = deV.as<float>(); P.V_hat = deV.as<float>();
+    P.red64 = dDummy64.as<double>();
+
+    int b = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += slab, b ^= (nbuf - 1)) {
+        const int64_t rows = (n - r0 < slab) ? n - r0 : slab;
+        cudaStream_t s = b ? st2 : st;
+        float* x = dX[b].as<float>();
+        ORI_CUDA(cudaMemcpy2DAsync(x, sizeof(float) * ldx, X + r0 * p, sizeof(float) * p, sizeof(float) * p, rows, cudaMemcpyHostToDevice, s));
+        if (D) ORI_CUDA(cudaMemcpy2DAsync(dD[b].p, sizeof(float) * ldx, D + r0 * p, sizeof(float) * p, sizeof(float) * p, rows, cudaMemcpyHostToDevice, s));
+        ORI_CUDA(cudaMemcpyAsync(dlUs[b].p, logU + r0 * K, sizeof(float) * rows * K, cudaMemcpyHostToDevice, s));
+        k_exp_pad<<<cdiv(rows * KP, 256), 256, 0, s>>>(dlUs[b].as<float>(), nullptr, 0, 0, deU[b].as<float>(), rows, (int)K, KP);
+        if (D && quirk)   // zigap.py:94: weight of cell i for latent k is D_hat[i, k]
+            k_exp_pad<<<cdiv(rows * KP, 256), 256, 0, s>>>(dlUs[b].as<float>(), dD[b].as<float>(), ldx, 0, deUw[b].as<float>(), rows, (int)K, KP);
+        if (Z3_out)
+            k_exp_pad<<<cdiv(rows * KP, 256), 256, 0, s>>>(dlUs[b].as<float>(), nullptr, 0, 1, deUl[b].as<float>(), rows, (int)K, KP);
+        const float* xq = x;  // X for the quirk gene sums (unweighted)
+        if (D) {              // X*D in place of X for everything weighted by D_hat[i, j]
+            if (quirk) {      // keep X: write X*D into the D buffer
+                k_mul<<<cdiv(rows * ldx, 256), 256, 0, s>>>(x, dD[b].as<float>(), dD[b].as<float>(), rows * ldx);
+                x = dD[b].as<float>();
+            } else {
+                k_mul<<<cdiv(rows * ldx, 256), 256, 0, s>>>(x, dD[b].as<float>(), x, rows * ldx);
+                xq = x;
+            }
+        }
+        ORI_TRY(check_launch("operator prologue"));
+        ORI_CUDA(cudaMemsetAsync(dZi[b].p, 0, sizeof(float) * rows * KP, s));
+        P.n_rows = rows; P.n_total = n; P.flags = 0;
+        P.eU[0] = deU[b].as<float>(); P.U_hat[0] = deU[b].as<float>(); P.U_hat[1] = deU[b].as<float>();
+        P.Zi = dZi[b].as<float>();
+        // row sums (zigap.py:93)
+        P.X = x;
+        ORI_TRY(launch_pass_rows_simt(&P, 0, s));
+        k_scale_unpad<<<cdiv(rows * K, 256), 256, 0, s>>>(dZi[b].as<float>(), deU[b].as<float>(), nullptr, nullptr, dOutI[b].as<float>(), rows, (int)K, KP);
+        ORI_CUDA(cudaMemcpyAsync(Zi_out + r0 * K, dOutI[b].p, sizeof(float) * rows * K, cudaMemcpyDeviceToHost, s));
+        // gene sums (zigap.py:94): both streams add into the same accumulators with atomics
+        if (D && quirk) { P.X = xq; P.flags = ORI_F_QUIRK; P.eUw = deUw[b].as<float>(); }
+        P.red32 = dZj.as<float>();
+        ORI_TRY(launch_pass_genes_simt(&P, 0, s));
+        if (Z3_out) {  // zigap.py:95 = eV * (R_D^T (eU*logU)) + logV * [eV * (R_D^T eU)]
+            P.X = x; P.flags = ORI_F_QUIRK; P.eUw = deUl[b].as<float>(); P.red32 = dZj3a.as<float>();
+            ORI_TRY(launch_pass_genes_simt(&P, 0, s));
+            if (D && quirk) { P.flags = 0; P.red32 = dZj3b.as<float>(); ORI_TRY(launch_pass_genes_simt(&P, 0, s)); }
+        }
+        ORI_CUDA(cudaEventRecord(done[b], s));
+    }
+    ORI_CUDA(cudaStreamWaitEvent(st, done[0], 0));
+    ORI_CUDA(cudaStreamWaitEvent(st, done[1 % nbuf], 0));
+    k_scale_unpad<<<cdiv(p * K, 256), 256, 0, st>>>(dZj.as<float>(), deV.as<float>(), nullptr, nullptr, dOutJ.as<float>(), p, (int)K, KP);
+    ORI_CUDA(cudaMemcpyAsync(Zj_out, dOutJ.p, sizeof(float) * p * K, cudaMemcpyDeviceToHost, st));
+    if (Z3_out) {
+        const float* plain = (D && quirk) ? dZj3b.as<float>() : dZj.as<float>();
+        k_scale_unpad<<<cdiv(p * K, 256), 256, 0, st>>>(dZj3a.as<float>(), deV.as<float>(), plain, dlogVraw.as<float>(), dOutJ.as<float>(), p, (int)K, KP);
+        ORI_CUDA(cudaMemcpyAsync(Z3_out, dOutJ.p, sizeof(float) * p * K, cudaMemcpyDeviceToHost, st));
+    }
+    ORI_TRY(check_launch("operator epilogue"));
+    ORI_CUDA(cudaStreamSynchronize(st2));
+    ORI_CUDA(cudaStreamSynchronize(st));
+    return ORI_OK;
+}
+
+extern "C" {
+
+int ori_zigap_compute_Z_q_expectations_host(float* DZ_hat_i, float* DZ_hat_j, float* DZ_exp_logsum_hat,
+                                            const float* log_U_hat, const float* log_V_hat,
+                                            const float* D_hat, const float* X,
+                                            int64_t n, int64_t p, int64_t K, int quirk) {
+    if (!D_hat) return set_error(ORI_EINVAL, "D_hat is NULL");
+    return z_operator_host(DZ_hat_i, DZ_hat_j, DZ_exp_logsum_hat, log_U_hat, log_V_hat, D_hat, X, n, p, K, quirk);
+}
+
+int ori_gap_compute_Z_q_expectations_host(float* Z_hat_i, float* Z_hat_j, const float* log_U_hat,
+                                          const float* log_V_hat, const float* X, int64_t n, int64_t p, int64_t K) {
+    return z_operator_host(Z_hat_i, Z_hat_j, nullptr, log_U_hat, log_V_hat, nullptr, X, n, p, K, 0);
+}
+
+}  // extern "C"

@@ -1,0 +1,45 @@
+// common.cuh -- shared declarations of the oriana_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/oriana_b200.h"
+
+namespace ori {
+
+// error plumbing (api.cu)
+int set_error(int code, const char* fmt, ...);
+int check_launch(const char* what);
+
+// slots of ori_problem_t::red64 after the p column sums and the 2K row-side sums
+enum Red64Slot {
+    R64_XLOGDEN = 0,  // sum_{X>0} X log den
+    R64_ENT = 1,      // sum_{X==0} entropy of q(D_ij)
+    R64_PUV = 2,      // sum_ij D_hat_ij (U_hat V_hat^T)_ij
+    R64_HROW = 3,     // sum_ik entropy of q(U_ik)
+    R64_NSLOTS = 8
+};
+// slots of ori_problem_t::scal (per-model persistent scalars, float64)
+enum ScalSlot {
+    SC_LGAMX = 0,     // sum_{X>0} lgamma(X+1)      (constant, all ranks)
+    SC_NNZ = 1,       // number of non-zero entries (constant, all ranks)
+    SC_PENDING = 2,   // K-/p-/nK-sized ELBO terms of the current state
+    SC_HGENE = 3,     // sum_jk entropy of q(V_jk) of the current state
+    SC_ELBO_LAST = 4, // last finalised ELBO
+    SC_ITER = 5,      // number of completed iterations
+    SC_NSLOTS = 16
+};
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// kernels_simt.cu
+int launch_pass_rows_simt(const ori_problem_t* P, int gen_old, cudaStream_t st);
+int launch_pass_genes_simt(const ori_problem_t* P, int gen_old, cudaStream_t st);
+int launch_row_update(const ori_problem_t* P, int gen_old, int write_state, cudaStream_t st);
+int launch_gene_update(const ori_problem_t* P, int write_state, cudaStream_t st);
+int launch_mstep(const ori_problem_t* P, int mode, cudaStream_t st);
+int launch_count_stats(const ori_problem_t* P, cudaStream_t st);
+int launch_quirk_weights(const ori_problem_t* P, int gen_old, cudaStream_t st);
+int launch_dropout_posterior(const ori_problem_t* P, int gen, float* out, long long ldo,
+                             long long row0, long long nrows, cudaStream_t st);
+
+}  // namespace ori

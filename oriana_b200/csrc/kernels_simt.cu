@@ -1,0 +1,652 @@
+// kernels_simt.cu -- CUDA-core (fp32 FMA) implementation of every kernel of the CAVI iteration.
+//
+// This is the reference-exact device path: it is what the tensor-core kernels (kernels_tc.cu) are
+// validated against, and it serves the small / odd shapes they do not take.  Reference lines replaced:
+//   k_pass_rows   zigap.py:79-95 (row sums DZ_hat_i), :116 (np.dot(D_hat, V_hat)), :131-136 (D_hat,
+//                 recomputed on the fly instead of stored), :158 (column sums of p_d)
+//   k_pass_genes  zigap.py:79-95 (gene sums DZ_hat_j, incl. the D_hat[i,k] quirk of :94), :124
+//   k_factor_update  zigap.py:115-120 / :123-128, gamma.py:37-61
+//   k_mstep       zigap.py:143-158, utils.py:39-51
+#include "common.cuh"
+#include "special.cuh"
+
+namespace ori {
+
+// ------------------------------------------------------------------------------------------------
+// D_hat for an entry with X == 0 (zigap.py:131-134):  sigma(logit(pi_j) - uv), floor 1e-10 where pi_j<=0.
+// lp = -inf encodes the initial indicator state p_d = (X>0) (zigap.py:77): the result is ~1.8e-35.
+__device__ __forceinline__ float dropout_p(float uv, float lp, float fl, float& e, float& ex) {
+    e = fminf(fmaxf(uv - lp, -80.f), 80.f);
+    ex = __expf(e);
+    return fmaxf(__fdividef(1.f, 1.f + ex), fl);
+}
+
+__device__ __forceinline__ double block_reduce_sum(double v, double* sbuf) {
+    // all threads of the block call this; result valid in thread 0
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) sbuf[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x == 0) for (int i = 0; i < nw; ++i) r += sbuf[i];
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row pass.  CTA = 128 threads = 128 consecutive cells; thread r keeps its cell's eU, U_hat and the 2*KP
+// accumulators in registers and sweeps gene tiles of 32; the X tile is staged (coalesced) through smem.
+constexpr int PR_TR = 128;
+constexpr int PR_TG = 32;
+
+template <int KP, bool DROPOUT, bool ELBO>
+__global__ void __launch_bounds__(PR_TR)
+k_pass_rows(const float* __restrict__ X, long long ldx, long long n_rows, int p,
+            const float* __restrict__ eU, const float* __restrict__ Uh,
+            const float* __restrict__ eV, const float* __restrict__ Vh,
+            const float* __restrict__ lp, const float* __restrict__ pfloor,
+            float* __restrict__ Zi, float* __restrict__ a2s,
+            double* __restrict__ colsum, double* __restrict__ part64)
+{
+    __shared__ float sX[PR_TR][PR_TG + 1];
+    __shared__ __align__(16) float sV[PR_TG][KP];
+    __shared__ __align__(16) float sVh[DROPOUT ? PR_TG : 1][KP];
+    __shared__ float slp[PR_TG], sfl[PR_TG];
+    __shared__ float scs[PR_TR / 32][PR_TG];
+    __shared__ double sred[PR_TR / 32];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long row0 = (long long)blockIdx.x * PR_TR;
+    const long long row = row0 + tid;
+    const bool row_ok = row < n_rows;
+
+    float eu[KP], uh[DROPOUT ? KP : 1], zi[KP], as[DROPOUT ? KP : 1];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        eu[k] = row_ok ? eU[row * KP + k] : 0.f;
+        zi[k] = 0.f;
+        if (DROPOUT) { uh[k] = row_ok ? Uh[row * KP + k] : 0.f; as[k] = 0.f; }
+    }
+    double acc_xl = 0.0, acc_ent = 0.0;
+
+    const int ntiles = (p + PR_TG - 1) / PR_TG;
+    for (int t = blockIdx.y; t < ntiles; t += gridDim.y) {
+        const int j0 = t * PR_TG;
+        const int gcount = min(PR_TG, p - j0);
+        __syncthreads();  // previous tile fully consumed
+        // X tile: warp w loads rows w, w+4, ...; a row segment is 32 consecutive floats
+        for (int rr = warp; rr < PR_TR; rr += PR_TR / 32) {
+            const long long r = row0 + rr;
+            float v = 0.f;
+            if (r < n_rows && lane < gcount) v = __ldg(X + r * ldx + j0 + lane);
+            sX[rr][lane] = v;
+        }
+        float* sVf = &sV[0][0];
+        float* sVhf = &sVh[0][0];
+        for (int idx = tid; idx < PR_TG * KP; idx += PR_TR) {
+            const int g = idx / KP;
+            const bool ok = g < gcount;
+            sVf[idx] = ok ? eV[(long long)j0 * KP + idx] : 0.f;
+            if (DROPOUT) sVhf[idx] = ok ? Vh[(long long)j0 * KP + idx] : 0.f;
+        }
+        if (DROPOUT && tid < PR_TG) {
+            slp[tid] = tid < gcount ? lp[j0 + tid] : 0.f;
+            sfl[tid] = tid < gcount ? pfloor[j0 + tid] : 0.f;
+        }
+        __syncthreads();
+
+        float t_xl = 0.f, t_ent = 0.f;
+        for (int g = 0; g < gcount; ++g) {
+            const float x = sX[tid][g];
+            float den = 0.f, uv = 0.f;
+            const float4* v4 = reinterpret_cast<const float4*>(&sV[g][0]);
+            const float4* h4 = reinterpret_cast<const float4*>(&sVh[DROPOUT ? g : 0][0]);
+#pragma unroll
+            for (int q = 0; q < KP / 4; ++q) {
+                const float4 v = v4[q];
+                den = fmaf(eu[4 * q + 0], v.x, den); den = fmaf(eu[4 * q + 1], v.y, den);
+                den = fmaf(eu[4 * q + 2], v.z, den); den = fmaf(eu[4 * q + 3], v.w, den);
+                if (DROPOUT) {
+                    const float4 h = h4[q];
+                    uv = fmaf(uh[4 * q + 0], h.x, uv); uv = fmaf(uh[4 * q + 1], h.y, uv);
+                    uv = fmaf(uh[4 * q + 2], h.z, uv); uv = fmaf(uh[4 * q + 3], h.w, uv);
+                }
+            }
+            const bool nz = x != 0.f;
+            den = den > 0.f ? den : 1.f;                 // zigap.py:90
+            const float R = x / den;
+            float D = 1.f;
+            if (DROPOUT) {
+                float e, ex;
+                const float pz = dropout_p(uv, slp[g], sfl[g], e, ex);
+                D = nz ? 1.f : pz;                       // zigap.py:135-136: float32(1 - 1e-10) == 1
+                if (ELBO && !nz) t_ent += __logf(1.f + ex) - (1.f - pz) * e;
+                sX[tid][g] = row_ok ? D : 0.f;           // for the column sums below
+            }
+            if (ELBO && nz) t_xl = fmaf(x, logf(den), t_xl);
+#pragma unroll
+            for (int q = 0; q < KP / 4; ++q) {
+                const float4 v = v4[q];
+                zi[4 * q + 0] = fmaf(R, v.x, zi[4 * q + 0]); zi[4 * q + 1] = fmaf(R, v.y, zi[4 * q + 1]);
+                zi[4 * q + 2] = fmaf(R, v.z, zi[4 * q + 2]); zi[4 * q + 3] = fmaf(R, v.w, zi[4 * q + 3]);
+                if (DROPOUT) {
+                    const float4 h = h4[q];
+                    as[4 * q + 0] = fmaf(D, h.x, as[4 * q + 0]); as[4 * q + 1] = fmaf(D, h.y, as[4 * q + 1]);
+                    as[4 * q + 2] = fmaf(D, h.z, as[4 * q + 2]); as[4 * q + 3] = fmaf(D, h.w, as[4 * q + 3]);
+                }
+            }
+        }
+        if (ELBO) { acc_xl += (double)t_xl; acc_ent += (double)t_ent; }
+
+        if (DROPOUT) {  // column sums of D_hat over this CTA's 128 cells -> pi (zigap.py:158)
+            __syncthreads();
+            float cs = 0.f;
+            if (lane < gcount) {
+#pragma unroll 8
+                for (int rr = 0; rr < 32; ++rr) cs += sX[warp * 32 + rr][lane];
+            }
+            scs[warp][lane] = cs;
+            __syncthreads();
+            if (tid < gcount) {
+                float tot = 0.f;
+#pragma unroll
+                for (int w = 0; w < PR_TR / 32; ++w) tot += scs[w][tid];
+                atomicAdd(colsum + j0 + tid, (double)tot);
+            }
+        }
+    }
+
+    if (row_ok) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            atomicAdd(Zi + row * KP + k, zi[k]);
+            if (DROPOUT) atomicAdd(a2s + row * KP + k, as[k]);
+        }
+    }
+    if (ELBO) {
+        if (!row_ok) { acc_xl = 0.0; acc_ent = 0.0; }
+        const double s1 = block_reduce_sum(acc_xl, sred);
+        const double s2 = block_reduce_sum(acc_ent, sred);
+        if (tid == 0) { atomicAdd(part64 + R64_XLOGDEN, s1); atomicAdd(part64 + R64_ENT, s2); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gene pass.  CTA = 128 threads = 128 consecutive genes; thread keeps its gene's eV, V_hat and 2*KP
+// accumulators in registers and sweeps a chunk of cells; X is read straight from global (coalesced),
+// the row operands of 32 cells at a time are broadcast from smem.
+constexpr int PG_TG = 128;
+constexpr int PG_TR = 32;
+
+template <int KP, bool DROPOUT, bool QUIRK>
+__global__ void __launch_bounds__(PG_TG)
+k_pass_genes(const float* __restrict__ X, long long ldx, long long n_rows, int p, int rows_per_chunk,
+             const float* __restrict__ eU, const float* __restrict__ eUw, const float* __restrict__ Uh,
+             const float* __restrict__ Un,
+             const float* __restrict__ eV, const float* __restrict__ Vh,
+             const float* __restrict__ lp, const float* __restrict__ pfloor,
+             float* __restrict__ Zj, float* __restrict__ b2s)
+{
+    __shared__ __align__(16) float sU[PG_TR][KP];
+    __shared__ __align__(16) float sUw[QUIRK ? PG_TR : 1][KP];
+    __shared__ __align__(16) float sUh[DROPOUT ? PG_TR : 1][KP];
+    __shared__ __align__(16) float sUn[DROPOUT ? PG_TR : 1][KP];
+
+    const int tid = threadIdx.x;
+    const int j = blockIdx.x * PG_TG + tid;
+    const bool j_ok = j < p;
+    const long long r_begin = (long long)blockIdx.y * rows_per_chunk;
+    const long long r_end = min(n_rows, r_begin + rows_per_chunk);
+
+    float ev[KP], vh[DROPOUT ? KP : 1], zj[KP], bs[DROPOUT ? KP : 1];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        ev[k] = j_ok ? eV[(long long)j * KP + k] : 0.f;
+        zj[k] = 0.f;
+        if (DROPOUT) { vh[k] = j_ok ? Vh[(long long)j * KP + k] : 0.f; bs[k] = 0.f; }
+    }
+    const float lpj = (DROPOUT && j_ok) ? lp[j] : 0.f;
+    const float flj = (DROPOUT && j_ok) ? pfloor[j] : 0.f;
+
+    float* sUf = &sU[0][0]; float* sUwf = &sUw[0][0]; float* sUhf = &sUh[0][0]; float* sUnf = &sUn[0][0];
+    for (long long r0 = r_begin; r0 < r_end; r0 += PG_TR) {
+        const int rcount = (int)min((long long)PG_TR, r_end - r0);
+        __syncthreads();
+        // rows past rcount are zero-filled: they contribute nothing (R = 0 and U_hat_new = 0)
+        for (int idx = tid; idx < PG_TR * KP; idx += PG_TG) {
+            const bool ok = idx / KP < rcount;
+            sUf[idx] = ok ? eU[r0 * KP + idx] : 0.f;
+            if (QUIRK) sUwf[idx] = ok ? eUw[r0 * KP + idx] : 0.f;
+            if (DROPOUT) {
+                sUhf[idx] = ok ? Uh[r0 * KP + idx] : 0.f;
+                sUnf[idx] = ok ? Un[r0 * KP + idx] : 0.f;
+            }
+        }
+        __syncthreads();
+        for (int rb = 0; rb < PG_TR; rb += 8) {
+            float xs[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                xs[u] = (j_ok && rb + u < rcount) ? __ldg(X + (r0 + rb + u) * ldx + j) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int rr = rb + u;
+                const float x = xs[u];
+                float den = 0.f, uv = 0.f;
+                const float4* u4 = reinterpret_cast<const float4*>(&sU[rr][0]);
+                const float4* w4 = reinterpret_cast<const float4*>(&sUw[QUIRK ? rr : 0][0]);
+                const float4* h4 = reinterpret_cast<const float4*>(&sUh[DROPOUT ? rr : 0][0]);
+                const float4* n4 = reinterpret_cast<const float4*>(&sUn[DROPOUT ? rr : 0][0]);
+#pragma unroll
+                for (int q = 0; q < KP / 4; ++q) {
+                    const float4 uu = u4[q];
+                    den = fmaf(uu.x, ev[4 * q + 0], den); den = fmaf(uu.y, ev[4 * q + 1], den);
+                    den = fmaf(uu.z, ev[4 * q + 2], den); den = fmaf(uu.w, ev[4 * q + 3], den);
+                    if (DROPOUT) {
+                        const float4 h = h4[q];
+                        uv = fmaf(h.x, vh[4 * q + 0], uv); uv = fmaf(h.y, vh[4 * q + 1], uv);
+                        uv = fmaf(h.z, vh[4 * q + 2], uv); uv = fmaf(h.w, vh[4 * q + 3], uv);
+                    }
+                }
+                den = den > 0.f ? den : 1.f;
+                const float R = x / den;
+                float D = 1.f;
+                if (DROPOUT) {
+                    float e, ex;
+                    const float pz = dropout_p(uv, lpj, flj, e, ex);
+                    D = (x != 0.f) ? 1.f : pz;
+                }
+#pragma unroll
+                for (int q = 0; q < KP / 4; ++q) {
+                    const float4 uu = QUIRK ? w4[q] : u4[q];
+                    zj[4 * q + 0] = fmaf(R, uu.x, zj[4 * q + 0]); zj[4 * q + 1] = fmaf(R, uu.y, zj[4 * q + 1]);
+                    zj[4 * q + 2] = fmaf(R, uu.z, zj[4 * q + 2]); zj[4 * q + 3] = fmaf(R, uu.w, zj[4 * q + 3]);
+                    if (DROPOUT) {
+                        const float4 nn = n4[q];
+                        bs[4 * q + 0] = fmaf(D, nn.x, bs[4 * q + 0]); bs[4 * q + 1] = fmaf(D, nn.y, bs[4 * q + 1]);
+                        bs[4 * q + 2] = fmaf(D, nn.z, bs[4 * q + 2]); bs[4 * q + 3] = fmaf(D, nn.w, bs[4 * q + 3]);
+                    }
+                }
+            }
+        }
+    }
+    if (j_ok) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            atomicAdd(Zj + (long long)j * KP + k, zj[k]);
+            if (DROPOUT) atomicAdd(b2s + (long long)j * KP + k, bs[k]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Factor update (both sides).  One thread per (row, k):
+//   h1 = clamp(c1_k + acc1 * e_old)            zigap.py:115,117 / :123,125
+//   h2 = clamp(c2_k + acc2  [or rate_const_k]) zigap.py:116,118 / :124,126  (gap.py:98,106: column sums)
+//   E = h1/h2, Elog = psi(float32(h1)) - log(float32(h2)), eE = exp(Elog)      gamma.py:37-61
+// and the column sums the M-step needs (zigap.py:146-155) plus the ELBO terms of this factor.
+// FROM_PARAMS: h1,h2 are read instead of computed (update_expectations, zigap.py:160-165).
+template <bool FROM_PARAMS>
+__global__ void __launch_bounds__(256)
+k_factor_update(long long rows, int K, int KP,
+                const float* __restrict__ acc1, const float* __restrict__ e_old,
+                const float* __restrict__ acc2, const double* __restrict__ rate_const,
+                const double* __restrict__ c1, const double* __restrict__ c2,
+                const float* __restrict__ E_old,
+                float* __restrict__ h1_io, float* __restrict__ h2_io,
+                float* __restrict__ E_new, float* __restrict__ eE_new,
+                double* __restrict__ Slog, double* __restrict__ Shat,
+                double* __restrict__ Hsum, double* __restrict__ PUVsum, int write_state)
+{
+    __shared__ double sSlog[64], sShat[64], sH, sP;
+    if (threadIdx.x < 64) { sSlog[threadIdx.x] = 0.0; sShat[threadIdx.x] = 0.0; }
+    if (threadIdx.x == 0) { sH = 0.0; sP = 0.0; }
+    __syncthreads();
+    const long long total = rows * KP;
+    double tH = 0.0, tP = 0.0;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(idx % KP);
+        if (k >= K) {
+            if (write_state) { E_new[idx] = 0.f; eE_new[idx] = 0.f; if (!FROM_PARAMS) { h1_io[idx] = 0.f; h2_io[idx] = 0.f; } }
+            continue;
+        }
+        double h1d, h2d;
+        if (FROM_PARAMS) {
+            h1d = (double)h1_io[idx]; h2d = (double)h2_io[idx];
+        } else {
+            const double z = (double)(acc1[idx] * e_old[idx]);
+            const double rate = acc2 ? (double)acc2[idx] : rate_const[k];
+            h1d = clamp_param_f64(c1[k] + z);
+            h2d = clamp_param_f64(c2[k] + rate);
+            if (PUVsum && acc2) tP += (double)E_old[idx] * (double)acc2[idx];
+        }
+        const float h1 = (float)h1d, h2 = (float)h2d;
+        const float E = (float)(h1d / h2d);
+        const double psi = digamma_f64((double)h1);
+        const float Elog = (float)psi - logf(h2);
+        if (write_state) {
+            if (!FROM_PARAMS) { h1_io[idx] = h1; h2_io[idx] = h2; }
+            E_new[idx] = E;
+            eE_new[idx] = expf(Elog);
+        }
+        atomicAdd(&sSlog[k], (double)Elog);
+        atomicAdd(&sShat[k], (double)E);
+        tH += (double)h1 - log((double)h2) + lgamma((double)h1) + (1.0 - (double)h1) * psi;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tH += __shfl_xor_sync(0xffffffffu, tH, o);
+        tP += __shfl_xor_sync(0xffffffffu, tP, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&sH, tH); atomicAdd(&sP, tP); }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        atomicAdd(Slog + threadIdx.x, sSlog[threadIdx.x]);
+        atomicAdd(Shat + threadIdx.x, sShat[threadIdx.x]);
+    }
+    if (threadIdx.x == 0) {
+        atomicAdd(Hsum, sH);
+        if (PUVsum) atomicAdd(PUVsum, sP);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// M-step and ELBO assembly: one CTA.
+__global__ void __launch_bounds__(1024)
+k_mstep(ori_problem_t P, int mode)
+{
+    __shared__ double sbuf[32];
+    const int tid = threadIdx.x;
+    const int p = P.p, K = P.K, KP = P.KP;
+    const double n = (double)P.n_total;
+    const bool dropout = (P.flags & ORI_F_DROPOUT) != 0;
+    double* colsum = P.red64;
+    double* SlogU = P.red64 + p;
+    double* SU = P.red64 + p + KP;
+    double* part = P.red64 + p + 2 * KP;
+    double* SlogV = P.gsum;
+    double* SV = P.gsum + KP;
+    double* gpart = P.gsum + 2 * KP;
+
+    // ---- phase 1: pi(t) and ELBO(t) of the state the row pass has just swept
+    if (mode == ORI_M_STEP || mode == ORI_M_FINALIZE) {
+        double bern = 0.0;
+        if (dropout) {
+            for (int j = tid; j < p; j += blockDim.x) {
+                const double cs = colsum[j];
+                const double pi = cs / n;                                  // zigap.py:158
+                P.pi_d[j] = pi;
+                const double pc = fmin(fmax(pi, 1e-15), 1.0 - 1e-15);
+                bern += cs * log(pc) + (n - cs) * log1p(-pc);
+                if (mode == ORI_M_STEP) {                                  // generates the next D_hat
+                    P.lp[j] = pi <= 0.0 ? -INFINITY : (pi >= 1.0 ? INFINITY : (float)log(pc / (1.0 - pc)));
+                    P.pfloor[j] = pi <= 0.0 ? 1e-10f : 0.f;                // zigap.py:133
+                }
+            }
+        }
+        const double b = block_reduce_sum(bern, sbuf);
+        if (tid == 0) {
+            double e = part[R64_XLOGDEN] - P.scal[SC_LGAMX] + P.scal[SC_PENDING];
+            if (dropout) {
+                const double q = 1e-10;  // p_d of a non-zero entry is 1 - 1e-10 (zigap.py:135)
+                const double h_nz = -(1.0 - q) * log1p(-q) - q * log(q);
+                e += -part[R64_PUV] + part[R64_ENT] + P.scal[SC_NNZ] * h_nz + b;
+            } else {
+                e -= P.scal[6];  // sum_k (sum_i U_hat_ik)(sum_j V_hat_jk) of the swept state
+            }
+            P.scal[SC_ELBO_LAST] = e;
+            if (P.iter >= 0 && P.iter < P.trace_cap) P.elbo_trace[P.iter] = e;
+        }
+        __syncthreads();
+        if (mode == ORI_M_FINALIZE) return;
+    }
+
+    // ---- phase 2: M-step on the new expectations (zigap.py:143-155); alpha1 uses the OLD alpha2
+    if (mode == ORI_M_INIT || mode == ORI_M_INIT_KEEP) {
+        if (tid == 0) { P.scal[SC_LGAMX] = part[4]; P.scal[SC_NNZ] = part[5]; }
+        if (dropout)
+            for (int j = tid; j < p; j += blockDim.x) {
+                P.pi_d[j] = colsum[j] / n;        // column means of p_d = (X>0)  (base.py:52 -> zigap.py:158)
+                P.lp[j] = -INFINITY;              // D_hat(0) is the indicator (zigap.py:77)
+                P.pfloor[j] = 0.f;
+            }
+    }
+    if (mode != ORI_M_INIT_KEEP && mode != ORI_M_REFRESH && tid < K) {
+        double* a1 = P.hyper, *a2 = P.hyper + K, *b1 = P.hyper + 2 * K, *b2 = P.hyper + 3 * K;
+        const int k = tid;
+        double v = clamp_param_f64(inverse_digamma_f64(log(a2[k]) + SlogU[k] / n));
+        a1[k] = v;
+        a2[k] = clamp_param_f64(v / (SU[k] / n));
+        v = clamp_param_f64(inverse_digamma_f64(log(b2[k]) + SlogV[k] / (double)p));
+        b1[k] = v;
+        b2[k] = clamp_param_f64(v / (SV[k] / (double)p));
+    }
+    __syncthreads();
+    double pend = 0.0, uvs = 0.0;
+    if (tid < K) {
+        const double* a1 = P.hyper, *a2 = P.hyper + K, *b1 = P.hyper + 2 * K, *b2 = P.hyper + 3 * K;
+        const int k = tid;
+        pend = n * (a1[k] * log(a2[k]) - lgamma(a1[k])) + (a1[k] - 1.0) * SlogU[k] - a2[k] * SU[k]
+             + (double)p * (b1[k] * log(b2[k]) - lgamma(b1[k])) + (b1[k] - 1.0) * SlogV[k] - b2[k] * SV[k];
+        uvs = SU[k] * SV[k];
+    }
+    const double ps = block_reduce_sum(pend, sbuf);
+    const double us = block_reduce_sum(uvs, sbuf);
+    if (tid == 0) {
+        P.scal[SC_PENDING] = ps + part[R64_HROW] + gpart[0];
+        P.scal[6] = us;
+        P.scal[SC_ITER] = (double)(mode == ORI_M_STEP ? P.iter + 1 : P.iter);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Constant statistics of X: sum lgamma(X+1), nnz, column sums of (X>0).
+__global__ void __launch_bounds__(128)
+k_count_stats(const float* __restrict__ X, long long ldx, long long n_rows, int p, int rows_per_chunk,
+              double* __restrict__ colsum, double* __restrict__ part64)
+{
+    __shared__ double sred[4];
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+    const long long r1 = min(n_rows, r0 + rows_per_chunk);
+    double lg = 0.0; float cnt = 0.f;
+    if (j < p)
+        for (long long r = r0; r < r1; ++r) {
+            const float x = __ldg(X + r * ldx + j);
+            if (x > 0.f) { cnt += 1.f; lg += (double)lgammaf(x + 1.f); }
+        }
+    if (j < p && cnt != 0.f) atomicAdd(colsum + j, (double)cnt);
+    const double s1 = block_reduce_sum(lg, sred);
+    const double s2 = block_reduce_sum((double)cnt, sred);
+    if (threadIdx.x == 0) { atomicAdd(part64 + 4, s1); atomicAdd(part64 + 5, s2); }
+}
+
+// eUw[i,k] = eU[i,k] * D_hat[i, gene k]   (the operand that reproduces zigap.py:94)
+__global__ void __launch_bounds__(256)
+k_quirk_weights(const float* __restrict__ X, long long ldx, long long n_rows, int K, int KP,
+                const float* __restrict__ eU, const float* __restrict__ Uh, const float* __restrict__ Vh,
+                const float* __restrict__ lp, const float* __restrict__ pfloor, float* __restrict__ eUw)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_rows * KP) return;
+    const long long i = idx / KP; const int k = (int)(idx % KP);
+    if (k >= K) { eUw[idx] = 0.f; return; }
+    const float x = X[i * ldx + k];
+    float D = 1.f;
+    if (x == 0.f) {
+        float uv = 0.f;
+        for (int q = 0; q < K; ++q) uv = fmaf(Uh[i * KP + q], Vh[(long long)k * KP + q], uv);
+        float e, ex;
+        D = dropout_p(uv, lp[k], pfloor[k], e, ex);
+    }
+    eUw[idx] = eU[idx] * D;
+}
+
+// D_hat slab (tests / API access to model.D_hat): zigap.py:131-136
+__global__ void __launch_bounds__(256)
+k_dropout_posterior(const float* __restrict__ X, long long ldx, int p, int K, int KP,
+                    const float* __restrict__ Uh, const float* __restrict__ Vh,
+                    const float* __restrict__ lp, const float* __restrict__ pfloor,
+                    float* __restrict__ out, long long ldo, long long row0, long long nrows)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nrows * p) return;
+    const long long i = row0 + idx / p; const int j = (int)(idx % p);
+    const float x = X[i * ldx + j];
+    float D = 1.f;
+    if (x == 0.f) {
+        float uv = 0.f;
+        for (int q = 0; q < K; ++q) uv = fmaf(Uh[i * KP + q], Vh[(long long)j * KP + q], uv);
+        float e, ex;
+        D = dropout_p(uv, lp[j], pfloor[j], e, ex);
+    }
+    out[(idx / p) * ldo + j] = D;
+}
+
+// ================================================================================================
+// launchers
+template <int KP>
+static int pass_rows_kp(const ori_problem_t* P, int g, cudaStream_t st) {
+    const int bx = cdiv(P->n_rows, PR_TR);
+    const int ntiles = cdiv(P->p, PR_TG);
+    int gy = 1;  // split the gene sweep when there are too few row blocks to fill 148 SMs x 4
+    while (bx * gy < 148 * 4 && gy * 2 <= ntiles) gy *= 2;
+    dim3 grid(bx, gy);
+    const bool drop = P->flags & ORI_F_DROPOUT, elbo = P->flags & ORI_F_ELBO;
+    double* colsum = P->red64;
+    double* part = P->red64 + P->p + 2 * P->KP;
+#define ORI_LAUNCH_PR(D, E)                                                                              \
+    k_pass_rows<KP, D, E><<<grid, PR_TR, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, P->eU[g], P->U_hat[g],   \
+                                                  P->eV, P->V_hat, P->lp, P->pfloor, P->Zi, P->a2s, colsum, part)
+    if (drop && elbo) ORI_LAUNCH_PR(true, true);
+    else if (drop) ORI_LAUNCH_PR(true, false);
+    else if (elbo) ORI_LAUNCH_PR(false, true);
+    else ORI_LAUNCH_PR(false, false);
+#undef ORI_LAUNCH_PR
+    return check_launch("k_pass_rows");
+}
+
+int launch_pass_rows_simt(const ori_problem_t* P, int g, cudaStream_t st) {
+    switch (P->KP) {
+        case 8: return pass_rows_kp<8>(P, g, st);
+        case 16: return pass_rows_kp<16>(P, g, st);
+        case 32: return pass_rows_kp<32>(P, g, st);
+        case 64: return pass_rows_kp<64>(P, g, st);
+    }
+    return set_error(ORI_EINVAL, "KP must be 8, 16, 32 or 64 (got %d)", P->KP);
+}
+
+template <int KP>
+static int pass_genes_kp(const ori_problem_t* P, int g, cudaStream_t st) {
+    const int bx = cdiv(P->p, PG_TG);
+    long long chunks = 1;
+    while (bx * chunks < 148 * 4 && P->n_rows / (chunks * 2) >= 64) chunks *= 2;
+    long long rpc = (P->n_rows + chunks - 1) / chunks;
+    rpc = (rpc + PG_TR - 1) / PG_TR * PG_TR;
+    if (rpc > 8192) rpc = 8192;  // bound the fp32 running sums
+    const int gy = cdiv(P->n_rows, rpc);
+    dim3 grid(bx, gy);
+    const bool drop = P->flags & ORI_F_DROPOUT, quirk = (P->flags & ORI_F_QUIRK) != 0;
+    float* Zj = P->red32;
+    float* b2s = P->red32 + (long long)P->p * P->KP;
+#define ORI_LAUNCH_PG(D, Q)                                                                             \
+    k_pass_genes<KP, D, Q><<<grid, PG_TG, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, (int)rpc, P->eU[g],    \
+                                                   P->eUw, P->U_hat[g], P->U_hat[1 - g], P->eV, P->V_hat, \
+                                                   P->lp, P->pfloor, Zj, b2s)
+    if (drop && quirk) ORI_LAUNCH_PG(true, true);
+    else if (drop) ORI_LAUNCH_PG(true, false);
+    else if (quirk) ORI_LAUNCH_PG(false, true);
+    else ORI_LAUNCH_PG(false, false);
+#undef ORI_LAUNCH_PG
+    return check_launch("k_pass_genes");
+}
+
+int launch_pass_genes_simt(const ori_problem_t* P, int g, cudaStream_t st) {
+    switch (P->KP) {
+        case 8: return pass_genes_kp<8>(P, g, st);
+        case 16: return pass_genes_kp<16>(P, g, st);
+        case 32: return pass_genes_kp<32>(P, g, st);
+        case 64: return pass_genes_kp<64>(P, g, st);
+    }
+    return set_error(ORI_EINVAL, "KP must be 8, 16, 32 or 64 (got %d)", P->KP);
+}
+
+static int update_grid(long long total) {
+    long long b = (total + 255) / 256;
+    return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
+}
+
+// write_state: 1 = regular update into generation 1-gen_old; 0 = only the ELBO term sum D_hat*uv of
+// the swept state (finalize); 2 = expectations of generation gen_old from (a1,a2) (init).
+int launch_row_update(const ori_problem_t* P, int g, int write_state, cudaStream_t st) {
+    const int p = P->p, K = P->K, KP = P->KP;
+    double* SlogU = P->red64 + p;
+    double* SU = P->red64 + p + KP;
+    double* part = P->red64 + p + 2 * KP;
+    const bool drop = P->flags & ORI_F_DROPOUT;
+    const int grid = update_grid(P->n_rows * KP);
+    if (write_state == 2) {
+        k_factor_update<true><<<grid, 256, 0, st>>>(P->n_rows, K, KP, nullptr, nullptr, nullptr, nullptr,
+            nullptr, nullptr, nullptr, P->a1, P->a2, P->U_hat[g], P->eU[g], SlogU, SU, part + R64_HROW, nullptr, 1);
+    } else {
+        // GaP: rate = alpha2 + sum_j V_hat_jk (gap.py:98); the column sums live in gsum[KP..2KP)
+        k_factor_update<false><<<grid, 256, 0, st>>>(P->n_rows, K, KP, P->Zi, P->eU[g],
+            drop ? P->a2s : nullptr, P->gsum + KP, P->hyper, P->hyper + K, P->U_hat[g],
+            P->a1, P->a2, P->U_hat[1 - g], P->eU[1 - g], SlogU, SU, part + R64_HROW, part + R64_PUV, write_state);
+    }
+    return check_launch("k_factor_update(rows)");
+}
+
+int launch_gene_update(const ori_problem_t* P, int write_state, cudaStream_t st) {
+    const int p = P->p, K = P->K, KP = P->KP;
+    const bool drop = P->flags & ORI_F_DROPOUT;
+    double* SlogV = P->gsum; double* SV = P->gsum + KP; double* gpart = P->gsum + 2 * KP;
+    const int grid = update_grid((long long)p * KP);
+    if (write_state == 2) {
+        k_factor_update<true><<<grid, 256, 0, st>>>(p, K, KP, nullptr, nullptr, nullptr, nullptr,
+            nullptr, nullptr, nullptr, P->b1, P->b2, P->V_hat, P->eV, SlogV, SV, gpart, nullptr, 1);
+    } else {
+        // GaP: rate = beta2 + sum_i U_hat_ik (gap.py:106) with the NEW U_hat: red64[p+KP ..)
+        float* Zj = P->red32; float* b2s = P->red32 + (long long)p * KP;
+        k_factor_update<false><<<grid, 256, 0, st>>>(p, K, KP, Zj, P->eV, drop ? b2s : nullptr,
+            P->red64 + p + KP, P->hyper + 2 * K, P->hyper + 3 * K, nullptr,
+            P->b1, P->b2, P->V_hat, P->eV, SlogV, SV, gpart, nullptr, write_state);
+    }
+    return check_launch("k_factor_update(genes)");
+}
+
+int launch_mstep(const ori_problem_t* P, int mode, cudaStream_t st) {
+    k_mstep<<<1, 1024, 0, st>>>(*P, mode);
+    return check_launch("k_mstep");
+}
+
+int launch_count_stats(const ori_problem_t* P, cudaStream_t st) {
+    const int bx = cdiv(P->p, 128);
+    long long chunks = 1;
+    while (bx * chunks < 148 * 4 && P->n_rows / (chunks * 2) >= 16) chunks *= 2;
+    const long long rpc = (P->n_rows + chunks - 1) / chunks;
+    dim3 grid(bx, cdiv(P->n_rows, rpc));
+    k_count_stats<<<grid, 128, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, (int)rpc, P->red64,
+                                        P->red64 + P->p + 2 * P->KP);
+    return check_launch("k_count_stats");
+}
+
+int launch_quirk_weights(const ori_problem_t* P, int g, cudaStream_t st) {
+    const long long total = P->n_rows * P->KP;
+    k_quirk_weights<<<cdiv(total, 256), 256, 0, st>>>(P->X, P->ldx, P->n_rows, P->K, P->KP, P->eU[g],
+                                                      P->U_hat[g], P->V_hat, P->lp, P->pfloor, P->eUw);
+    return check_launch("k_quirk_weights");
+}
+
+int launch_dropout_posterior(const ori_problem_t* P, int g, float* out, long long ldo, long long row0,
+                             long long nrows, cudaStream_t st) {
+    const long long total = nrows * P->p;
+    if (total == 0) return ORI_OK;
+    k_dropout_posterior<<<cdiv(total, 256), 256, 0, st>>>(P->X, P->ldx, P->p, P->K, P->KP, P->U_hat[g],
+                                                          P->V_hat, P->lp, P->pfloor, out, ldo, row0, nrows);
+    return check_launch("k_dropout_posterior");
+}
+
+}  // namespace ori

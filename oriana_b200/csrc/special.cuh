@@ -1,0 +1,65 @@
+// special.cuh -- device special functions of the CAVI path.
+//
+// Replaces oriana/utils.py:9-51 of the reference (logit, sigmoid, digamma = scipy.special.digamma,
+// digamma_prime = scipy.special.polygamma(1, .), inverse_digamma = Minka start + 5 Newton steps).
+// digamma / trigamma: upward recurrence to x >= 10, then the asymptotic (Bernoulli) series;
+// absolute error < 1e-13 in double for x in [1e-15, 1e300].
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace ori {
+
+constexpr double kDigammaOne = -0.57721566490153286061;  // psi(1), utils.py:48
+
+__host__ __device__ inline double digamma_f64(double x) {
+    double r = 0.0;
+    while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+    const double i = 1.0 / x, i2 = i * i;
+    // ln x - 1/2x - sum B_2n / (2n x^2n)
+    double s = i2 * (1.0 / 12.0 - i2 * (1.0 / 120.0 - i2 * (1.0 / 252.0 - i2 * (1.0 / 240.0
+             - i2 * (1.0 / 132.0 - i2 * (691.0 / 32760.0 - i2 * (1.0 / 12.0)))))));
+    return r + log(x) - 0.5 * i - s;
+}
+
+__host__ __device__ inline double trigamma_f64(double x) {
+    double r = 0.0;
+    while (x < 10.0) { r += 1.0 / (x * x); x += 1.0; }
+    const double i = 1.0 / x, i2 = i * i;
+    // 1/x + 1/2x^2 + sum B_2n / x^(2n+1)
+    double s = i * (1.0 + i * 0.5 + i2 * (1.0 / 6.0 - i2 * (1.0 / 30.0 - i2 * (1.0 / 42.0
+             - i2 * (1.0 / 30.0 - i2 * (5.0 / 66.0 - i2 * (691.0 / 2730.0 - i2 * (7.0 / 6.0))))))));
+    return r + s;
+}
+
+// utils.py:39-51
+__host__ __device__ inline double inverse_digamma_f64(double y) {
+    double x = (y >= -2.22) ? exp(y) + 0.5 : -1.0 / (y - kDigammaOne);
+#pragma unroll 1
+    for (int it = 0; it < 5; ++it) x -= (digamma_f64(x) - y) / trigamma_f64(x);
+    return x;
+}
+
+// utils.py:9-11
+__host__ __device__ inline double logit_f64(double x) {
+    x = fmin(fmax(x, 1e-15), 1.0 - 1e-15);
+    return log(x / (1.0 - x));
+}
+
+// utils.py:14-15
+__host__ __device__ inline double sigmoid_f64(double x) { return 1.0 / (1.0 + exp(-x)); }
+
+// max(1e-15, nan_to_num(x)) -- zigap.py:117-118 etc.  (NaN -> 0 -> 1e-15, +inf -> DBL_MAX)
+__host__ __device__ inline double clamp_param_f64(double x) {
+    if (x != x) x = 0.0;
+    if (x > 1.7976931348623157e308) x = 1.7976931348623157e308;
+    return fmax(1e-15, x);
+}
+// float32 storage of the same clamp: +inf -> FLT_MAX
+__host__ __device__ inline float clamp_param_f32(float x) {
+    if (x != x) x = 0.f;
+    if (x > 3.402823466e38f) x = 3.402823466e38f;
+    return fmaxf(1e-15f, x);
+}
+
+}  // namespace ori

@@ -1,0 +1,98 @@
+// synth.cu -- synthetic zero-inflated negative-binomial counts generated on the device (bench only;
+// SURVEY.md section 8d).  The host cannot hold BASELINE.json's larger configurations (1M x 20k int64 is
+// 160 GB), so each rank generates its own row block from a counter-based RNG.
+#include "common.cuh"
+
+namespace ori {
+
+struct Philox {
+    uint32_t k0, k1;
+    __device__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+    __device__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+        uint32_t a = k0, b = k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+            const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+            c0 = h1 ^ c1 ^ a; c1 = l1; c2 = h0 ^ c3 ^ b; c3 = l0;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+};
+
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }  // (0,1)
+
+// Gamma(2, 1/2) = (E1 + E2) / 2
+__global__ void k_synth_factor(float* __restrict__ out, long long rows, int K, long long row0, uint64_t seed, uint32_t tag) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * K) return;
+    const long long i = row0 + idx / K; const int k = (int)(idx % K);
+    const uint4 r = Philox(seed)((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)k, tag);
+    out[idx] = -0.5f * (__logf(u01(r.x)) + __logf(u01(r.y)));
+}
+
+__global__ void k_synth_pi(float* __restrict__ pi, int p, float z, uint64_t seed) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p) return;
+    const uint4 r = Philox(seed)((uint32_t)j, 0u, 0u, 0x50u);
+    const float b = 1.f / z - 1.f;   // Beta(1, b): inverse CDF
+    pi[j] = (z >= 1.f) ? 1.f : 1.f - __powf(1.f - u01(r.x), 1.f / b);
+}
+
+__global__ void __launch_bounds__(256)
+k_synth_counts(float* __restrict__ X, long long ldx, long long row0, long long n_rows, int p, int K,
+               const float* __restrict__ Us, const float* __restrict__ Vs, const float* __restrict__ pi,
+               uint64_t seed, int nb)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_rows * ldx) return;
+    const long long il = idx / ldx; const int j = (int)(idx % ldx);
+    if (j >= p) { X[idx] = 0.f; return; }
+    const long long i = row0 + il;
+    const Philox ph(seed);
+    uint4 r = ph((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)j, 0x58u);
+    float x = 0.f;
+    if (u01(r.x) < pi[j]) {
+        float lam = 0.f;
+        for (int k = 0; k < K; ++k) lam = fmaf(Us[il * K + k], Vs[(long long)j * K + k], lam);
+        if (nb) lam *= -0.5f * (__logf(u01(r.y)) + __logf(u01(r.z)));
+        if (lam > 60.f) {   // normal approximation (Box-Muller)
+            const uint4 q = ph((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)j, 0x59u);
+            const float zn = sqrtf(-2.f * __logf(u01(q.x))) * __cosf(6.2831853f * u01(q.y));
+            x = fmaxf(0.f, rintf(lam + sqrtf(lam) * zn));
+        } else {            // Knuth's product method
+            const float L = __expf(-lam);
+            float prod = u01(r.w);
+            uint32_t ctr = 0x100u;
+            int cnt = 0;
+            while (prod > L && cnt < 400) {
+                const uint4 q = ph((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)j, ctr++);
+                const float u[4] = {u01(q.x), u01(q.y), u01(q.z), u01(q.w)};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) if (prod > L) { ++cnt; prod *= u[t]; }
+            }
+            x = (float)cnt;
+        }
+    }
+    X[idx] = x;
+}
+
+}  // namespace ori
+
+using namespace ori;
+
+extern "C" int ori_synth_counts_f32(float* X, int64_t ldx, int64_t row0, int64_t n_rows, int32_t p, int32_t K,
+                                    uint64_t seed, float zero_level, int nb, float* Ustar, float* Vstar,
+                                    float* pi, void* stream)
+{
+    if (!X || !Ustar || !Vstar || !pi || ldx < p || p <= 0 || K <= 0 || n_rows < 0 || !(zero_level > 0.f))
+        return set_error(ORI_EINVAL, "ori_synth_counts_f32: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_rows == 0) return ORI_OK;
+    k_synth_factor<<<cdiv(n_rows * K, 256), 256, 0, st>>>(Ustar, n_rows, K, row0, seed, 0x55u);
+    k_synth_factor<<<cdiv((long long)p * K, 256), 256, 0, st>>>(Vstar, p, K, 0, seed, 0x56u);
+    k_synth_pi<<<cdiv(p, 256), 256, 0, st>>>(pi, p, zero_level, seed);
+    k_synth_counts<<<cdiv(n_rows * ldx, 256), 256, 0, st>>>(X, ldx, row0, n_rows, p, K, Ustar, Vstar, pi, seed, nb);
+    return check_launch("k_synth_counts");
+}

@@ -1,0 +1,416 @@
+"""`FactorModel` -- base class of the Gamma-Poisson factor models (oriana/models/base.py:13-130).
+
+Same constructor, hooks and `step()` as the reference; the state lives in HBM and every update runs in the
+CUDA library (`include/oriana_b200.h`).  One CAVI iteration (`step()`, base.py:54-56) is
+
+    update_variational_parameters()   E-step  zigap.py:97-141 / gap.py:82-115
+        row pass  -> U update -> gene pass -> [allreduce over ranks] -> V update
+    update_prior_hyper_parameters()   M-step  zigap.py:143-158 / gap.py:117-129
+
+Differences that are visible to a caller, all forced by scale (SURVEY.md sections 7-8):
+  * D_hat / p_d (n x p) is never stored: it is recomputed inside both passes from (U_hat, V_hat, pi).
+    `model.D_hat`, `model.p_d` materialise it on request; `model.pi_d` (which the reference refreshes at the
+    end of each step from the stored p_d) is produced by the NEXT row pass, or by a flush pass when read.
+  * UV = U V^T (n x p float64) is not materialised by `step()`; call `model.UV.forward()` if you want it.
+  * the model can own a row block of a larger matrix (`sharded=True`): only the gene-side sums are
+    all-reduced (NCCL) per iteration.
+  * an ELBO trace is kept (`model.elbo_trace`, `model.elbo()`); the reference has none.
+"""
+from abc import ABCMeta, abstractmethod
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..dims import Dimensions
+from ..nodes import Einsum
+from ..parameters import Parameter
+from ..sharding import RowSharding
+from ..singlecell.cmatrix import CountMatrix
+
+
+def pad_k(K):
+    for kp in (8, 16, 32, 64):
+        if K <= kp:
+            return kp
+    raise ValueError('k=%d: the CUDA kernels support latent dimensions up to 64' % K)
+
+
+class DeviceView(Parameter):
+    """A `Parameter` whose storage is a view of the model's device state.  Reads return float64 host
+    copies (the reference keeps parameters in float64, parameters.py:11); writes go to HBM and make the
+    model re-derive its expectations before the next step."""
+
+    def __init__(self, owner, getter, on_write=True):
+        self._owner = owner
+        self._getter = getter
+        self._on_write = on_write
+
+    @property
+    def _t(self):
+        return self._getter()
+
+    @property
+    def tensor(self):
+        return self._getter()
+
+    def asarray(self):
+        return self._getter().detach().to(torch.float64).cpu().numpy()
+
+    def __setitem__(self, key, value):
+        Parameter.__setitem__(self, key, value)
+        if self._on_write:
+            self._owner._dirty = True
+
+    @property
+    def buffer(self):
+        return self.asarray()
+
+    @buffer.setter
+    def buffer(self, data):
+        self[...] = data
+
+
+class FactorModel(metaclass=ABCMeta):
+
+    _dropout = False     # ZIGaP sets this
+
+    def __init__(self, cmatrix, k=2, use_factors=True, *, state=None, compat_quirk=False, sharded=False,
+                 process_group=None, elbo=True, trace_cap=4096, force_simt=False):
+        self._dev = _lib.require_cuda()
+        self._lib = _lib.load()
+        _lib.check(self._lib.ori_device_check(self._dev.index or 0))
+        if not isinstance(cmatrix, CountMatrix):
+            cmatrix = CountMatrix(cmatrix)
+        self.cmatrix = cmatrix
+
+        # dimensions (base.py:21-24)
+        self.k = int(k)
+        self.n = int(cmatrix.shape[0])
+        self.m = self.p = int(cmatrix.shape[1])
+        self.dims = Dimensions({'n': self.n, 'm': self.m, 'p': self.p, 'k': self.k})
+        self._KP = pad_k(self.k)
+        self._shard = RowSharding(process_group if (sharded or process_group is not None) else None,
+                                  enabled=bool(sharded or process_group is not None))
+        self.n_total = self._shard.total_rows(self.n, self._dev)
+        self._flags = (_lib.ORI_F_DROPOUT if self._dropout else 0) | (_lib.ORI_F_ELBO if elbo else 0) \
+            | (_lib.ORI_F_QUIRK if (compat_quirk and self._dropout) else 0) \
+            | (_lib.ORI_F_NO_TENSOR if force_simt else 0)
+        self.compat_quirk = bool(compat_quirk and self._dropout)
+        self._trace_cap = int(trace_cap)
+        self._gen = 0
+        self._iter = 0
+        self._dirty = False
+        self._pi_stale = False
+        self._D_cache = None
+        self._started = False
+
+        self._allocate(cmatrix)
+
+        # model graph (base.py:27-31); UV is NOT forwarded here (n x p float64)
+        self.U = self.build_u_node()
+        self.V = self.build_v_node()
+        self.UV = Einsum('nk,mk->nm', self.U, self.V, name='UV')
+        self.X = self.build_x_node(self.cmatrix, self.UV)
+        self.define_variational_distribution()
+
+        self.use_factors = use_factors
+        if state is not None:
+            self.load_state(state)
+        else:
+            if use_factors:
+                self._nmf_warm_start()
+            self.initialize_parameters()
+
+    # ------------------------------------------------------------------------------------------------
+    def _allocate(self, cmatrix):
+        dev, n, p, K, KP = self._dev, self.n, self.p, self.k, self._KP
+        f32 = dict(dtype=torch.float32, device=dev)
+        f64 = dict(dtype=torch.float64, device=dev)
+        ldx = (p + 3) // 4 * 4
+        src = cmatrix.as_tensor()
+        if isinstance(src, torch.Tensor) and src.is_cuda and src.dtype == torch.float32 \
+                and src.shape[1] == p and src.stride(1) == 1 and src.stride(0) % 4 == 0 \
+                and src.stride(0) >= p and src.data_ptr() % 16 == 0:
+            self._X = src                      # adopt a resident row block without copying it
+            ldx = src.stride(0) if n > 1 else max(ldx, src.stride(0))
+            self._Xfull = None
+        else:
+            self._Xfull = torch.zeros((n, ldx), **f32)
+            if isinstance(src, torch.Tensor):
+                self._Xfull[:, :p] = src.to(device=dev, dtype=torch.float32)
+            else:
+                step = max(1, (1 << 26) // max(1, p))   # upload in slabs: no n x p float32 copy on the host
+                for r in range(0, n, step):
+                    self._Xfull[r:r + step, :p] = torch.as_tensor(
+                        np.ascontiguousarray(src[r:r + step]).astype(np.float32, copy=False), device=dev)
+            self._X = self._Xfull[:, :p]
+        self._ldx = ldx
+
+        def rowf():
+            return torch.zeros((n, KP), **f32)
+
+        def genef():
+            return torch.zeros((p, KP), **f32)
+        self._a1, self._a2 = rowf(), rowf()
+        self._Uhat = [rowf(), rowf()]
+        self._eU = [rowf(), rowf()]
+        self._Zi = rowf()
+        self._a2s = rowf() if self._dropout else None
+        self._eUw = rowf() if (self._flags & _lib.ORI_F_QUIRK) else None
+        self._b1, self._b2, self._Vhat, self._eV = genef(), genef(), genef(), genef()
+        self._red32 = torch.zeros((2, p, KP), **f32)
+        self._lp = torch.full((p,), float('-inf'), **f32) if self._dropout else None
+        self._pfloor = torch.zeros((p,), **f32) if self._dropout else None
+        self._hyper = torch.ones((4, K), **f64)
+        self._red64 = torch.zeros((p + 2 * KP + _lib.R64_NSLOTS,), **f64)
+        self._gsum = torch.zeros((2 * KP + 8,), **f64)
+        self._pi = torch.zeros((p,), **f64) if self._dropout else None
+        self._scal = torch.zeros((_lib.SCAL_SLOTS,), **f64)
+        self._trace = torch.zeros((self._trace_cap,), **f64)
+
+        P = _lib.OriProblem()
+        P.n_rows, P.n_total, P.ldx = n, self.n_total, ldx
+        P.p, P.K, P.KP, P.flags = p, K, KP, self._flags
+        P.iter, P.trace_cap = 0, self._trace_cap
+
+        def ptr(t):
+            return None if t is None else t.data_ptr()
+        P.X = ptr(self._X)
+        P.a1, P.a2 = ptr(self._a1), ptr(self._a2)
+        P.U_hat[0], P.U_hat[1] = ptr(self._Uhat[0]), ptr(self._Uhat[1])
+        P.eU[0], P.eU[1] = ptr(self._eU[0]), ptr(self._eU[1])
+        P.eUw, P.Zi, P.a2s = ptr(self._eUw), ptr(self._Zi), ptr(self._a2s)
+        P.b1, P.b2, P.V_hat, P.eV = ptr(self._b1), ptr(self._b2), ptr(self._Vhat), ptr(self._eV)
+        P.red32, P.lp, P.pfloor = ptr(self._red32), ptr(self._lp), ptr(self._pfloor)
+        P.hyper, P.red64, P.gsum = ptr(self._hyper), ptr(self._red64), ptr(self._gsum)
+        P.pi_d, P.scal, P.elbo_trace = ptr(self._pi), ptr(self._scal), ptr(self._trace)
+        self._P = P
+        _lib.check(self._lib.ori_problem_check(ctypes.byref(P)))
+
+        K_ = K
+        self.a1 = DeviceView(self, lambda: self._a1[:, :K_])
+        self.a2 = DeviceView(self, lambda: self._a2[:, :K_])
+        self.b1 = DeviceView(self, lambda: self._b1[:, :K_])
+        self.b2 = DeviceView(self, lambda: self._b2[:, :K_])
+        self.alpha1 = DeviceView(self, lambda: self._hyper[0])
+        self.alpha2 = DeviceView(self, lambda: self._hyper[1])
+        self.beta1 = DeviceView(self, lambda: self._hyper[2])
+        self.beta2 = DeviceView(self, lambda: self._hyper[3])
+
+    def _call(self, name, *args):
+        self._P.iter = self._iter
+        _lib.check(getattr(self._lib, name)(ctypes.byref(self._P), *args, _lib.stream_ptr()))
+
+    # ------------------------------------------------------------------------------------------------
+    def _nmf_warm_start(self):
+        """`use_factors=True`: the reference seeds a1, b1 with sklearn NMF factors (base.py:38-40).  That is
+        host-side initialisation outside the CAVI path; it is run like the reference
+        does, on the host, and only for matrices the host can factorise."""
+        if self._shard.enabled:
+            raise ValueError('use_factors=True needs the whole matrix on one rank; use use_factors=False')
+        if self.n * self.p > 50_000_000:
+            raise ValueError('use_factors=True runs sklearn NMF on the host (base.py:38-40); '
+                             'this matrix is too large for that -- pass use_factors=False')
+        from sklearn.decomposition import NMF
+        model = NMF(n_components=self.k)
+        X = self.cmatrix.as_array()
+        self._nmf_U = model.fit_transform(X)
+        self._nmf_V = model.components_.T
+
+    def initialize_parameters(self):
+        """base.py:43-52."""
+        self.initialize_variational_parameters()
+        self.update_expectations()
+        self.update_prior_hyper_parameters()
+
+    def _set_factor(self, dst, values):
+        K = self.k
+        v = torch.as_tensor(np.asarray(values, dtype=np.float64), device=self._dev)
+        dst.zero_()
+        dst[:, :K] = torch.clamp(torch.nan_to_num(v), min=1e-15).to(torch.float32)   # zigap.py:63,73
+
+    def _draw_factor_inits(self):
+        """zigap.py:58-75 / gap.py:49-65: a1, b1 from the NMF factors or Gamma(1) draws; a2 = b2 = 1."""
+        if self.use_factors:
+            a1, b1 = self._nmf_U, self._nmf_V
+        else:
+            a1 = np.random.gamma(1., size=(self.n, self.k))
+            b1 = np.random.gamma(1., size=(self.m, self.k))
+        self._set_factor(self._a1, a1)
+        self._set_factor(self._b1, b1)
+        self._set_factor(self._a2, np.ones((self.n, self.k)))
+        self._set_factor(self._b2, np.ones((self.m, self.k)))
+
+    # ------------------------------------------------------------------------------------------------
+    def update_expectations(self):
+        """zigap.py:160-165: U_hat, V_hat, log-expectations from (a1, a2, b1, b2), on the device."""
+        self._call('ori_count_stats') if not self._started else self._red64.zero_()
+        self._call('ori_init_expectations', self._gen)
+        self._shard.allreduce_sum(self._red64)
+        self._D_cache = None
+
+    def step(self):
+        """One CAVI iteration (base.py:54-56)."""
+        self.update_variational_parameters()   # E-step
+        self.update_prior_hyper_parameters()   # M-step
+
+    def update_variational_parameters(self):
+        """E-step (zigap.py:97-141 / gap.py:82-115)."""
+        if self._iter + 1 >= self._trace_cap:
+            raise RuntimeError('elbo trace capacity %d exhausted; build the model with a larger trace_cap'
+                               % self._trace_cap)
+        if self._dirty:
+            self._refresh()
+        self._call('ori_cavi_step_local', self._gen)
+        if self._shard.enabled:
+            self._shard.allreduce_sum(self._red32)
+            self._shard.allreduce_sum(self._red64)
+        self._call('ori_gene_update', 1)
+        self._pending_mstep = True
+
+    def update_prior_hyper_parameters(self):
+        """M-step (zigap.py:143-158 / gap.py:117-129).  At construction: on the initial expectations."""
+        if not self._started:
+            mode = _lib.ORI_M_INIT_KEEP if getattr(self, '_keep_hyper', False) else _lib.ORI_M_INIT
+            self._call('ori_mstep', mode)
+            self._started = True
+            self._pi_stale = False
+            return
+        if not getattr(self, '_pending_mstep', False):
+            raise RuntimeError('update_prior_hyper_parameters() follows update_variational_parameters()')
+        self._call('ori_mstep', _lib.ORI_M_STEP)
+        self._pending_mstep = False
+        self._gen ^= 1
+        self._iter += 1
+        self._pi_stale = self._dropout
+        self._D_cache = None
+
+    def _refresh(self):
+        """Parameters were edited through `model.a1[:] = ...`: re-derive expectations and ELBO terms."""
+        self._red64.zero_()
+        self._call('ori_init_expectations', self._gen)
+        self._shard.allreduce_sum(self._red64)
+        self._call('ori_mstep', _lib.ORI_M_REFRESH)
+        self._dirty = False
+        self._D_cache = None
+
+    def _finalize(self):
+        """Flush the one-pass lag: pi(t) and ELBO(t) of the current state (one extra sweep of X)."""
+        if self._dirty:
+            self._refresh()
+        if self._dropout and self._pi_stale:
+            self._pi_gen = self._pi.clone()
+        self._call('ori_finalize_local', self._gen)
+        self._shard.allreduce_sum(self._red64)
+        self._call('ori_mstep', _lib.ORI_M_FINALIZE)
+        self._pi_stale = False
+
+    # ------------------------------------------------------------------------------------------------
+    def elbo(self):
+        """Evidence lower bound of the current state (float64 accumulation on the device)."""
+        self._finalize()
+        return float(self._scal[4].item())
+
+    @property
+    def elbo_trace(self):
+        """ELBO after construction and after each completed step: array of length iterations + 1."""
+        self._finalize()
+        return self._trace[:self._iter + 1].cpu().numpy()
+
+    @property
+    def iterations(self):
+        return self._iter
+
+    @property
+    def U_hat(self):
+        return self._Uhat[self._gen][:, :self.k].to(torch.float64).cpu().numpy()
+
+    @property
+    def V_hat(self):
+        return self._Vhat[:, :self.k].to(torch.float64).cpu().numpy()
+
+    @property
+    def log_U_hat(self):
+        return torch.log(self._eU[self._gen][:, :self.k]).cpu().numpy()
+
+    @property
+    def log_V_hat(self):
+        return torch.log(self._eV[:, :self.k]).cpu().numpy()
+
+    def device_state(self):
+        """Zero-copy views of the device-resident state (torch CUDA tensors)."""
+        K = self.k
+        out = dict(X=self._X, a1=self._a1[:, :K], a2=self._a2[:, :K], b1=self._b1[:, :K], b2=self._b2[:, :K],
+                   U_hat=self._Uhat[self._gen][:, :K], V_hat=self._Vhat[:, :K],
+                   eU=self._eU[self._gen][:, :K], eV=self._eV[:, :K],
+                   alpha1=self._hyper[0], alpha2=self._hyper[1], beta1=self._hyper[2], beta2=self._hyper[3])
+        if self._dropout:
+            out.update(lp=self._lp, pi_d=self._pi)
+        return out
+
+    def factors(self):
+        """base.py:97-98."""
+        return self.U_hat, self.V_hat
+
+    def state_dict(self):
+        """The state vector of SURVEY.md section 8c as host float64 arrays (checkpoint / parity hand-off)."""
+        s = {k: getattr(self, k).asarray() for k in ('a1', 'a2', 'b1', 'b2', 'alpha1', 'alpha2', 'beta1', 'beta2')}
+        s['iterations'] = self._iter
+        return s
+
+    def load_state(self, state):
+        """Seed the model from a state vector copied out of a reference model (or `state_dict()`)."""
+        K = self.k
+        for name, dst in (('a1', self._a1), ('a2', self._a2), ('b1', self._b1), ('b2', self._b2)):
+            v = np.asarray(state[name], dtype=np.float64)
+            if v.shape != (dst.shape[0], K):
+                raise ValueError('%s has shape %s, expected %s' % (name, v.shape, (dst.shape[0], K)))
+            dst.zero_()
+            dst[:, :K] = torch.as_tensor(v, device=self._dev).to(torch.float32)
+        for i, name in enumerate(('alpha1', 'alpha2', 'beta1', 'beta2')):
+            self._hyper[i] = torch.as_tensor(np.asarray(state[name], dtype=np.float64), device=self._dev)
+        self._keep_hyper = True
+        self._started = False
+        self._gen = 0
+        self._iter = 0
+        self.update_expectations()
+        self.update_prior_hyper_parameters()
+        self._after_load_state(state)
+
+    def _after_load_state(self, state):
+        pass
+
+    # -- reference metrics that are out of the hot path (base.py:58-95) -------------------------------
+    def frobenius_norm(self):
+        """base.py:84-87, evaluated in row slabs on the device (no n x p float64 temporary)."""
+        tot = torch.zeros((), dtype=torch.float64, device=self._dev)
+        U = self._Uhat[self._gen][:, :self.k]; V = self._Vhat[:, :self.k]
+        step = max(1, (1 << 25) // max(1, self.p))
+        for r in range(0, self.n, step):
+            d = (U[r:r + step] @ V.T) - self._X[r:r + step]
+            tot += (d.double() ** 2).sum()
+        tot = self._shard.allreduce_sum(tot.reshape(1))[0]
+        return float(torch.sqrt(tot).item())
+
+    # ------------------------------------------------------------------------------------------------
+    @abstractmethod
+    def build_u_node(self):
+        pass
+
+    @abstractmethod
+    def build_v_node(self):
+        pass
+
+    @abstractmethod
+    def build_x_node(self, cmatrix, UV):
+        pass
+
+    @abstractmethod
+    def define_variational_distribution(self):
+        pass
+
+    @abstractmethod
+    def initialize_variational_parameters(self):
+        pass

@@ -1,0 +1,135 @@
+"""CPU: host-side mirror of the reference interface, and the C-ABI surface (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_dimensions_examples_from_reference_docstring():
+    """dims.py:91-102."""
+    from oriana_b200 import Dimensions, IncompatibleShapeException
+    d = Dimensions({'n': 10, 'm': 5, 'p': 5, 'k': 3, 'l': 4})
+    assert repr(d('m,k ~ d,s')) == 'Dimension mapping (5, 3) <-> (3, 5, 1)'
+    assert repr(d('n,k ~ s,d')) == 'Dimension mapping (10, 3) <-> (10, 3, 1)'
+    assert repr(d('n,m,k ~ d,d,d')) == 'Dimension mapping (10, 5, 3) <-> (1, 150, 1)'
+    assert repr(d('n,k,l,l ~ s,d,c,c')) == 'Dimension mapping (10, 3, 4, 4) <-> (10, 3, 16)'
+    with pytest.raises(IncompatibleShapeException):
+        d('n,k ~ s')
+    rel = d('m,k ~ d,s')
+    x = np.arange(15.).reshape(3, 5, 1)
+    y = rel.reshape_func(x)
+    assert y.shape == (5, 3) and np.array_equal(rel.inv_reshape_func(y), x)
+    assert y[4, 2] == x[2, 4, 0]
+
+
+def test_parameter_semantics():
+    """parameters.py:8-32: float64 storage, [:] get/set, shape, asarray, in-place idiom."""
+    from oriana_b200 import Parameter
+    p = Parameter([[1, 2], [3, 4]])
+    assert p.shape == (2, 2) and p[:].dtype == np.float64
+    p[:] = p[:] + 1
+    p[0, :] += 1
+    assert np.array_equal(p.asarray(), [[3., 4.], [4., 5.]])
+    assert np.array_equal(np.asarray(p), p[:])
+
+
+def test_alias_package_import_paths():
+    """The reference's import lines (test/test.py:5-7, zigap.py:5-9) work unchanged."""
+    from oriana import Dimensions, Parameter  # noqa
+    from oriana.nodes import Poisson, Gamma, Bernoulli, Multinomial, Multiply, Einsum, Transpose  # noqa
+    from oriana.utils import digamma, inverse_digamma, sigmoid, logit  # noqa
+    from oriana.models import FactorModel, GaP, ZIGaP  # noqa
+    from oriana.inference import VariationalDistribution
+    from oriana.singlecell import CountMatrix  # noqa
+    v = VariationalDistribution()
+    assert len(v) == 0
+
+
+def test_bernoulli_and_multinomial_means():
+    """test/test.py:35-57 (no special function involved: runs without a GPU)."""
+    from oriana import Dimensions, Parameter
+    from oriana.nodes import Bernoulli, Multinomial
+    dims = Dimensions({'n': 2, 'm': 2, 'k': 2})
+    p = Parameter([[0.02, 0.34], [0.62, 0.79]])
+    y = Bernoulli(p, dims('m,k ~ d,d')).mean()
+    np.testing.assert_almost_equal(np.asarray([[0.02, 0.34], [0.62, 0.79]]), y)
+    assert y.dtype == np.float32                                   # bernoulli.py:45
+    n = Parameter([[0, 1], [3, 1]])
+    q = Parameter([[[0.50, 0.50], [0.21, 0.79]], [[0.43, 0.57], [0.89, 0.11]]])
+    x = Multinomial(n, q, dims('n,m,k ~ d,d,c')).mean()
+    np.testing.assert_almost_equal(x, q.asarray() * n.asarray()[..., None])
+
+
+def test_node_forward_is_lazy():
+    """test/test.py:82-96: a deterministic node changes only when forward() is called."""
+    from oriana import Dimensions, Parameter
+    from oriana.nodes import Multinomial, Multiply
+    n = Parameter([[0, 1], [3, 1]])
+    p = Parameter([[[0.50, 0.50], [0.21, 0.79]], [[0.43, 0.57], [0.89, 0.11]]])
+    dims = Dimensions({'n': 2, 'm': 2, 'k': 2})
+    m1 = Multinomial(n, p, dims('n,m,k ~ d,d,c'))
+    m2 = Multinomial(n, Parameter(1 - p.asarray()), dims('n,m,k ~ d,d,c'))
+    prod = Multiply(m1, m2)
+    prod.forward()
+    m1.sample(); m2.sample()
+    assert not np.allclose(prod[:], m1[:] * m2[:])
+    prod.forward()
+    np.testing.assert_almost_equal(prod[:], m1[:] * m2[:])
+
+
+def test_count_matrix_types():
+    from oriana.singlecell import CountMatrix
+    from oriana import DatatypeException
+    c = CountMatrix(np.arange(6).reshape(2, 3))
+    assert c.shape == (2, 3) and c.T.shape == (3, 2)
+    with pytest.raises(DatatypeException):
+        CountMatrix([[1, 2], [3, 4]])                              # cmatrix.py:25-29
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads and exports exactly what include/oriana_b200.h declares."""
+    from oriana_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'oriana_b200.h')).read()
+    declared = sorted(set(re.findall(r'^int\s+(ori_\w+)\s*\(', header, flags=re.M)))
+    assert declared == _lib.exported_symbols()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().ori_version() >= 100
+    # struct layout agreed between the header and the ctypes mirror
+    n_ptr = len(re.findall(r'^\s+(?:const\s+)?(?:float|double)\s*\*', header.split('typedef struct ori_problem')[1].split('} ori_problem_t')[0], flags=re.M))
+    assert ctypes.sizeof(_lib.OriProblem) == 3 * 8 + 6 * 4 + 23 * 8 and n_ptr >= 19
+
+
+def test_no_cpu_fallback():
+    """Without a GPU every compute entry point raises; nothing silently runs on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from oriana_b200 import _lib
+    from oriana.models import ZIGaP
+    from oriana.utils import digamma
+    with pytest.raises(_lib.OrianaB200Error):
+        ZIGaP(np.ones((4, 5)), k=2, use_factors=False)
+    with pytest.raises(_lib.OrianaB200Error):
+        digamma(np.ones(3))
+    # the product never imports the oracle
+    import subprocess, sys
+    out = subprocess.run([sys.executable, '-c', 'import oriana, oriana.models, sys; '
+                          'print(any(m == "oracle" or m.startswith("oracle.") for m in sys.modules))'],
+                         cwd=ROOT, capture_output=True, text=True)
+    assert out.stdout.strip() == 'False', out
+
+
+def test_row_blocks_cover_all_cells():
+    from oriana_b200.sharding import RowSharding
+    for n, w in ((10, 3), (1_000_000, 8), (7, 8), (0, 2)):
+        blocks = [RowSharding.row_block(n, r, w) for r in range(w)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
+        sizes = [b - a for a, b in blocks]
+        assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,90 @@
+"""CPU: the oracle port against the golden trajectories made by the UNMODIFIED reference
+(oracle/make_golden.py), i.e. the pin of the oracle (task section 3)."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, golden_state, load_golden, relerr
+from oracle import cavi_numpy as cn, zloop, refshim
+
+PARAMS = ('a1', 'a2', 'b1', 'b2', 'alpha1', 'alpha2', 'beta1', 'beta2')
+
+
+@pytest.mark.parametrize('name', GOLDEN_CASES)
+def test_z_kernel_matches_reference_numba_kernel(name):
+    """zigap.py:79-95 / gap.py:67-80: C triple loop (same order) and the ratio form vs the numba output."""
+    g = load_golden(name)
+    s = golden_state(g, 0)
+    e = cn.expectations(s)
+    assert np.array_equal(e['log_U_hat'], g['z_log_U_hat'])      # gamma.py:48-61 is reproduced bit for bit
+    assert np.array_equal(e['log_V_hat'], g['z_log_V_hat'])
+    X32 = s['X'].astype(np.float32)
+    if 'p_d' in s:
+        Zi, Zj = zloop.zigap_z(e['log_U_hat'], e['log_V_hat'], e['D_hat'], X32, quirk=True)
+    else:
+        Zi, Zj = zloop.gap_z(e['log_U_hat'], e['log_V_hat'], X32)
+    assert relerr(Zi, g['z_Zi']) < 2e-6 and relerr(Zj, g['z_Zj']) < 2e-6
+    Zi, Zj = cn.z_expectations(e['log_U_hat'], e['log_V_hat'], s['X'], e.get('D_hat'), quirk=True)
+    assert relerr(Zi, g['z_Zi']) < 2e-5 and relerr(Zj, g['z_Zj']) < 2e-5
+
+
+@pytest.mark.parametrize('name', GOLDEN_CASES)
+def test_trajectory_matches_reference(name):
+    """base.py:54-56 stepped from the reference's own post-construction state."""
+    g = load_golden(name)
+    s = golden_state(g, 0)
+    steps = [int(t) for t in g['steps']]
+    for t in range(1, max(steps) + 1):
+        cn.step(s, quirk=True)
+        if t in steps:
+            r = golden_state(g, t)
+            for k in PARAMS + (('pi_d',) if 'pi_d' in s else ()):
+                assert relerr(s[k], r[k]) < 5e-5, (name, t, k)
+            if 'p_d' in s:
+                assert np.max(np.abs(s['p_d'].astype(np.float32) - r['p_d'])) < 1e-5
+
+
+def test_elbo_monotone_without_quirk():
+    """The ELBO (new; parity unpinned in the reference) must not decrease under the de-quirked CAVI."""
+    X = cn.synth_counts(120, 90, 4, seed=5)
+    for model in ('zigap', 'gap'):
+        s = cn.init_state(X, 4, np.random.default_rng(3), model)
+        prev = cn.elbo(s)
+        for _ in range(15):
+            cn.step(s, quirk=False, dtype=np.float64)
+            cur = cn.elbo(s)
+            assert cur >= prev - 1e-7 * abs(prev), (model, prev, cur)
+            prev = cur
+
+
+def test_special_functions_against_reference_kats():
+    g = load_golden('special')
+    assert relerr(cn.digamma(g['x']), g['digamma']) < 1e-14
+    assert relerr(cn.inverse_digamma(g['y']), g['inverse_digamma']) < 1e-12
+    assert np.allclose(cn.sigmoid(g['z']), g['sigmoid'], rtol=1e-15, atol=0)
+    assert np.allclose(cn.logit(g['q']), g['logit'], rtol=1e-15, atol=0)
+    # test/test.py:13-32
+    x = np.asarray([-2.3, 1.5, 0.45, -0.78, 5.3, -.2, 0.])
+    np.testing.assert_almost_equal(cn.logit(cn.sigmoid(x)), x)
+    x = np.asarray([0.54, 6.2, 1.2, 0.3, 7.9, 4.5, 2.1])
+    np.testing.assert_almost_equal(cn.inverse_digamma(cn.digamma(x)), x)
+    np.testing.assert_almost_equal(cn.digamma(cn.inverse_digamma(x)), x)
+
+
+@pytest.mark.skipif(not refshim.available(), reason='reference checkout only exists in the build container')
+def test_port_matches_live_reference():
+    """Container only: run the real reference next to the port on a fresh problem (not a fixture)."""
+    refshim.import_reference()
+    try:
+        from oriana.models import ZIGaP
+        from oriana.singlecell import CountMatrix
+        X = cn.synth_counts(60, 70, 3, seed=11)
+        np.random.seed(4)
+        m = ZIGaP(CountMatrix(X), k=3, use_factors=False)
+        s = refshim.snapshot(m)
+        for _ in range(3):
+            m.step(); cn.step(s, quirk=True)
+        r = refshim.snapshot(m)
+        for k in PARAMS + ('pi_d',):
+            assert relerr(s[k], r[k]) < 2e-5, k
+    finally:
+        refshim.release_reference()     # leave the repo's alias package importable for later tests

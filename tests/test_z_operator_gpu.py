@@ -1,0 +1,85 @@
+"""GPU: the operator-level drop-in (`compute_Z_q_expectations` with host buffers, zigap.py:79-95 /
+gap.py:67-80) against the reference's numba output (golden) and the sequential C loop oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, golden_state, load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def z_op(lib, lU, lV, X, D=None, quirk=True, third=False):
+    from oriana_b200 import _lib
+    n, K = lU.shape; p = lV.shape[0]
+    Zi = np.full((n, K), np.nan, np.float32); Zj = np.full((p, K), np.nan, np.float32)
+    Z3 = np.full((p, K), np.nan, np.float32) if third else None
+    arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (lU, lV, X)]
+    if D is None:
+        _lib.check(lib.ori_gap_compute_Z_q_expectations_host(_ptr(Zi), _ptr(Zj), _ptr(arrs[0]), _ptr(arrs[1]),
+                                                             _ptr(arrs[2]), n, p, K))
+    else:
+        D = np.ascontiguousarray(D, dtype=np.float32)
+        _lib.check(lib.ori_zigap_compute_Z_q_expectations_host(_ptr(Zi), _ptr(Zj), _ptr(Z3), _ptr(arrs[0]),
+                                                               _ptr(arrs[1]), _ptr(D), _ptr(arrs[2]), n, p, K,
+                                                               int(quirk)))
+    return (Zi, Zj, Z3) if third else (Zi, Zj)
+
+
+@pytest.mark.parametrize('name', GOLDEN_CASES)
+def test_against_reference_numba_kernel(cuda_lib, name):
+    from oracle import cavi_numpy as cn
+    g = load_golden(name)
+    s = golden_state(g, 0)
+    D = cn.expectations(s).get('D_hat')
+    Zi, Zj = z_op(cuda_lib, g['z_log_U_hat'], g['z_log_V_hat'], s['X'], D, quirk=True)
+    assert relerr(Zi, g['z_Zi']) < 1e-5, relerr(Zi, g['z_Zi'])
+    assert relerr(Zj, g['z_Zj']) < 1e-5, relerr(Zj, g['z_Zj'])
+
+
+@pytest.mark.parametrize('quirk', [True, False])
+@pytest.mark.parametrize('shape', [(1, 3, 1), (5, 7, 3), (129, 33, 8), (260, 517, 9), (300, 140, 17), (70, 90, 40)])
+def test_against_c_loop_with_soft_dropout(cuda_lib, shape, quirk):
+    """Arbitrary D_hat in (0,1) (not just the indicator), ragged shapes, every padded-K bucket, third output."""
+    from oracle import zloop
+    n, p, K = shape
+    if quirk and p < K:
+        pytest.skip('zigap.py:94 indexes D_hat[i, k]: needs p >= K')
+    rng = np.random.default_rng(n * 1000 + p)
+    lU = rng.normal(-0.5, 1.0, (n, K)).astype(np.float32)
+    lV = rng.normal(-0.5, 1.0, (p, K)).astype(np.float32)
+    X = (rng.poisson(3.0, (n, p)) * (rng.random((n, p)) < 0.6)).astype(np.float32)
+    D = np.where(X != 0, 1.0, rng.random((n, p))).astype(np.float32)
+    Zi, Zj, Z3 = z_op(cuda_lib, lU, lV, X, D, quirk=quirk, third=True)
+    rZi, rZj, rZ3 = zloop.zigap_z(lU, lV, D, X, quirk=quirk, third=True)
+    assert relerr(Zi, rZi) < 1e-5 and relerr(Zj, rZj) < 1e-5
+    assert relerr(Z3, rZ3, floor=1e-5) < 2e-5
+    gZi, gZj = z_op(cuda_lib, lU, lV, X)
+    rZi, rZj = zloop.gap_z(lU, lV, X)
+    assert relerr(gZi, rZi) < 1e-5 and relerr(gZj, rZj) < 1e-5
+
+
+def test_underflow_guard_and_empty(cuda_lib):
+    """zigap.py:88-90: den <= 0 -> 1 (all exp underflow); n = 0 leaves zero gene sums."""
+    from oracle import zloop
+    lU = np.full((4, 2), -200., np.float32); lV = np.full((6, 2), -200., np.float32)
+    X = np.arange(24, dtype=np.float32).reshape(4, 6)
+    Zi, Zj = z_op(cuda_lib, lU, lV, X)
+    rZi, rZj = zloop.gap_z(lU, lV, X)
+    assert np.array_equal(Zi, rZi) and np.array_equal(Zj, rZj) and not Zi.any()
+    Zi, Zj = z_op(cuda_lib, np.zeros((0, 3), np.float32), np.zeros((5, 3), np.float32), np.zeros((0, 5), np.float32))
+    assert Zi.shape == (0, 3) and not Zj.any()
+
+
+def test_bad_arguments_raise(cuda_lib):
+    from oriana_b200 import _lib
+    with pytest.raises(_lib.OrianaB200Error):
+        z_op(cuda_lib, np.zeros((2, 70), np.float32), np.zeros((80, 70), np.float32), np.zeros((2, 80), np.float32))
+    with pytest.raises(_lib.OrianaB200Error):   # quirk needs p >= K
+        z_op(cuda_lib, np.zeros((2, 5), np.float32), np.zeros((3, 5), np.float32), np.zeros((2, 3), np.float32),
+             np.ones((2, 3), np.float32), quirk=True)

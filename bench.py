@@ -1,0 +1,260 @@
+#!/usr/bin/env python
+"""bench.py -- CAVI throughput of the B200 path on BASELINE.json's headline configuration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c4] [--impl reference]
+
+A "step" is one full CAVI iteration (`model.step()`, reference base.py:54-56: E-step + M-step, ELBO terms
+included) over the synthetic zero-inflated negative-binomial count matrix of the configuration:
+    c1 100 x 500 K=2 | c2 10k x 2k K=10 | c3 100k x 20k K=20 | c4 1M x 20k K=32 (default, the metric's config)
+The matrix is generated in HBM (it is far larger than L2, so no flush is needed between steps) and is
+sharded by cells over the N ranks (strong scaling: the total problem is fixed).  `value` is whole-job
+matrix entries per second (= cells * genes * iterations / s) with everything resident in HBM; `e2e` is the
+same metric through the host-buffer entry (`HostStreamedCAVI.step()`): the count matrix and the row
+parameters are streamed from pinned host memory and the results copied back inside the timed region.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    'c1': (100, 500, 2), 'c2': (10_000, 2_000, 10), 'c3': (100_000, 20_000, 20),
+    'c4': (1_000_000, 20_000, 32), 'c5': (2_000_000, 30_000, 64),
+}
+METRIC = 'cavi_matrix_entries_per_sec'
+UNIT = 'entries/s'
+
+
+def workload_name(cfg, n, p, K):
+    return 'synthetic ZINB counts %d cells x %d genes, K=%d, ZIGaP CAVI (dropout on), config %s' % (n, p, K, cfg)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.samples, self.reasons, self.max_mhz, self._stop_evt = [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {getattr(nv, k): k for k in dir(nv) if k.startswith('nvmlClocksThrottleReason') or k.startswith('nvmlClocksEventReason')}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if isinstance(bit, int) and bit and (r & bit) and 'None' not in name and 'All' not in name:
+                        self.reasons.add(name.replace('nvmlClocksThrottleReason', '').replace('nvmlClocksEventReason', ''))
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        rs = sorted({r for r in self.reasons if r not in ('GpuIdle', 'ApplicationsClocksSetting')})
+        return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=rs, samples=len(s))
+
+
+def cpu_reference_run(n, p, K, steps, warmup, seed=0, budget_rows=2048):
+    """The oracle port of the reference's step() (oracle/cavi_numpy.py: numpy + multithreaded BLAS, float32
+    ratio form) on a bounded row slab of the same workload.  Returns (entries/s, cores, sample text)."""
+    import numpy as np
+    from oracle import cavi_numpy as cn
+    rows = int(min(n, budget_rows))
+    X = cn.synth_counts(rows, p, K, seed=seed)
+    s = cn.init_state(X, K, np.random.default_rng(seed), 'zigap')
+    for _ in range(warmup):
+        cn.step(s, quirk=False)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cn.step(s, quirk=False)
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    return rows * p / dt, os.cpu_count(), ('%d-row slab of the workload (%d x %d, K=%d), %d full CAVI steps of the '
+                                          'numpy/BLAS oracle port, %.2f s/step' % (rows, rows, p, K, steps, dt)), dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default=os.environ.get('ORIANA_BENCH_CONFIG', 'c4'), choices=sorted(CONFIGS))
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--e2e-steps', type=int, default=0)
+    args = ap.parse_args()
+    n, p, K = CONFIGS[args.config]
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    W = max(args.warmup, 0)
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        steps = max(1, args.steps)
+        val, cores, sample, dt = cpu_reference_run(n, p, K, steps, W)
+        print(json.dumps({
+            'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
+            'warmup': W, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'iters_per_sec_full_problem': val / (n * p),
+            'config': {'workload': workload_name(args.config, n, p, K), 'n': n, 'p': p, 'K': K},
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}))
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from oriana.models import ZIGaP
+    from oriana.singlecell import synth_counts_device
+    from oriana_b200.host_step import HostStreamedCAVI
+    from oriana_b200.sharding import RowSharding
+
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    W = max(W, 3)
+    K_steps = max(1, args.steps)
+    r0, r1 = RowSharding.row_block(n, rank, world)
+    rows = r1 - r0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- synthetic counts, generated in HBM by this rank for its own cells
+    X = synth_counts_device(rows, p, K, seed=1234, row0=r0)
+    np.random.seed(100 + rank)
+    model = ZIGaP(X[:, :p], k=K, use_factors=False, sharded=world > 1, trace_cap=W + K_steps + 8)
+    for _ in range(W):
+        model.step()
+    model.enable_kernel_timing()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K_steps):
+        model.step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / K_steps
+    value = n * p * K_steps / (ms_total * 1e-3)
+    kt = model.kernel_times_ms()
+    model.enable_kernel_timing(False)
+    trace = model.elbo_trace
+    elbo_ok = bool(np.isfinite(trace).all() and np.all(np.diff(trace[1:]) >= -1e-6 * np.abs(trace[1:-1])))
+
+    # ---- roofline of the dominant kernel (both X-streaming kernels read this rank's X once: 4 B/entry)
+    peak, peak_src = load_peaks()
+    alg_bytes = 4.0 * rows * p
+    kernels = []
+    for name in ('pass_rows', 'pass_genes'):
+        t = max_over_ranks(kt[name])
+        kernels.append({'kernel': name, 'ms': t, 'achieved': alg_bytes / (t * 1e-3) / 1e9})
+    dom = max(kernels, key=lambda k: k['ms'])
+    traffic = None
+    prof = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get('%s:%s' % (args.config, dom['kernel']))
+        except Exception:
+            traffic = None
+    roofline = {'bound': 'hbm', 'kernel': dom['kernel'], 'achieved': dom['achieved'], 'peak': peak, 'unit': 'GB/s',
+                'frac': dom['achieved'] / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': alg_bytes, 'kernels': kernels,
+                'step_frac': (8.0 * rows * p / (ms_step * 1e-3) / 1e9) / peak}
+
+    # ---- end to end through host buffers
+    e2e = None
+    if not args.no_e2e:
+        state = model.state_dict()
+        del model
+        Xh = torch.empty((rows, p), dtype=torch.float32, pin_memory=True)
+        Xh.copy_(X[:, :p])
+        del X
+        torch.cuda.empty_cache()
+        host = HostStreamedCAVI(Xh, K, state, dropout=True, sharded=world > 1)
+        n_e2e = args.e2e_steps or max(2, min(K_steps, 4))
+        host.step()                                       # warm-up
+        h0, d0 = host.h2d_bytes, host.d2h_bytes
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            host.step()
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        hb = torch.tensor([host.h2d_bytes - h0, host.d2h_bytes - d0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(hb)
+        e2e = {'value': n * p * n_e2e / dt, 'unit': UNIT, 'h2d_bytes_per_step': float(hb[0]) / n_e2e,
+               'd2h_bytes_per_step': float(hb[1]) / n_e2e, 'steps': n_e2e, 'ms_per_step': dt / n_e2e * 1e3,
+               'api': 'oriana_b200.host_step.HostStreamedCAVI.step (pinned host X, a1, a2, b1, b2 in; results out)'}
+
+    # ---- the reference's CPU path beside it (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        val, cores, sample, _ = cpu_reference_run(n, p, K, steps=3, warmup=1)
+        cpu = {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
+
+    if rank == 0:
+        out = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K_steps, 'warmup': W,
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'iters_per_sec': 1e3 / ms_step,
+            'config': {'workload': workload_name(args.config, n, p, K), 'n': n, 'p': p, 'K': K,
+                       'cells_per_rank': rows, 'parallelism': 'cells sharded over %d rank(s); 2 sum-allreduces/iter' % world,
+                       'l2': 'X per rank is %.1f GB, far larger than the 126 MB L2: no flush between steps' % (alg_bytes / 1e9)},
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'clocks': clocks,
+            'gpu_launches': 5 * K_steps, 'elbo_monotone': elbo_ok, 'elbo_last': float(trace[-1]),
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -115,9 +115,13 @@ int ori_problem_check(const ori_problem_t* P);
 int ori_count_stats(const ori_problem_t* P, void* stream);
 /* Expectations of generation `gen` from (a1,a2,b1,b2) (zigap.py:160-165) + their column sums. */
 int ori_init_expectations(const ori_problem_t* P, int gen, void* stream);
+/* Zero-fill the accumulators of one iteration: Zi, a2s, red64 and (genes != 0) red32 (zigap.py:81-83). */
+int ori_zero_accumulators(const ori_problem_t* P, int genes, void* stream);
 /* Row pass ("KA"): Zi, a2s, colsum D_hat, ELBO partials from X and the state of generation gen_old. */
 int ori_pass_rows(const ori_problem_t* P, int gen_old, void* stream);
-/* U update (zigap.py:115-120) into generation 1-gen_old, plus sum_i log U_hat, sum_i U_hat. */
+/* U update (zigap.py:115-120) into generation 1-gen_old, plus sum_i log U_hat, sum_i U_hat.
+ * write_state: 1 regular; 0 only the ELBO term of the swept state; 2 expectations of generation gen_old
+ * from (a1, a2) with their column sums; 3 the same without touching any sum (host-streamed slabs). */
 int ori_row_update(const ori_problem_t* P, int gen_old, int write_state, void* stream);
 /* Gene pass ("KA'"): Zj and b2s = D_hat^T U_hat_new (zigap.py:94,124) into red32. */
 int ori_pass_genes(const ori_problem_t* P, int gen_old, void* stream);

@@ -186,7 +186,7 @@ def init_state(X, K, rng, model='zigap'):
 
 
 # --------------------------------------------------------------------------- ELBO (new; parity unpinned)
-def elbo(s):
+def elbo(s, guard32=False):
     """Evidence lower bound of the mean-field family of zigap.py:39-53 for the model of
     zigap.py:21-37, in float64.  The multinomial auxiliary Z is at its
     optimum given the current q(U), q(V), which turns the Poisson term into X*log(den).
@@ -197,13 +197,22 @@ def elbo(s):
                 + a1 - log a2 + lgamma(a1) + (1-a1) psi(a1)]                          (entropy of q)
       + same for V.
     pi and p are clipped to [1e-15, 1-1e-15].  GaP: p == 1 and no Bernoulli block.
+
+    guard32=True evaluates den the way the reference's Z-step does (zigap.py:86-90): float32
+    exp(E log U) . exp(E log V)^T with `den = den if den > 0 else 1`.  The two only differ when the
+    float32 exp underflows for every k of an entry, which happens on a random Gamma(1) initial state
+    (psi(a1) ~ -1/a1) and never after the first update (a1 >= alpha1).
     """
     X = s['X'].astype(np.float64)
     a1, a2, b1, b2 = (s[k].astype(np.float64) for k in ('a1', 'a2', 'b1', 'b2'))
     U_hat, V_hat = a1 / a2, b1 / b2
     lU = sp.digamma(a1) - np.log(a2)
     lV = sp.digamma(b1) - np.log(b2)
-    den = np.exp(lU) @ np.exp(lV).T
+    if guard32:
+        den = np.exp(lU.astype(np.float32)) @ np.exp(lV.astype(np.float32)).T
+        den = np.where(den > 0, den, np.float32(1)).astype(np.float64)
+    else:
+        den = np.exp(lU) @ np.exp(lV).T
     nz = X > 0
     out = (X[nz] * np.log(den[nz]) - sp.gammaln(X[nz] + 1.)).sum()
     UV = U_hat @ V_hat.T

@@ -45,6 +45,7 @@ _SIGNATURES = {
     'ori_problem_check': ([_PP], C.c_int),
     'ori_count_stats': ([_PP, C.c_void_p], C.c_int),
     'ori_init_expectations': ([_PP, C.c_int, C.c_void_p], C.c_int),
+    'ori_zero_accumulators': ([_PP, C.c_int, C.c_void_p], C.c_int),
     'ori_pass_rows': ([_PP, C.c_int, C.c_void_p], C.c_int),
     'ori_row_update': ([_PP, C.c_int, C.c_int, C.c_void_p], C.c_int),
     'ori_pass_genes': ([_PP, C.c_int, C.c_void_p], C.c_int),

@@ -217,6 +217,11 @@ static int zero_accumulators(const ori_problem_t* P, cudaStream_t st, bool genes
     return ORI_OK;
 }
 
+int ori_zero_accumulators(const ori_problem_t* P, int genes, void* stream) {
+    ORI_TRY(ori_problem_check(P));
+    return zero_accumulators(P, (cudaStream_t)stream, genes != 0);
+}
+
 int ori_cavi_step_local(const ori_problem_t* P, int gen_old, void* stream) {
     ORI_TRY(ori_problem_check(P));
     cudaStream_t st = (cudaStream_t)stream;

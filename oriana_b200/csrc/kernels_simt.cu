@@ -14,11 +14,13 @@ namespace ori {
 
 // ------------------------------------------------------------------------------------------------
 // D_hat for an entry with X == 0 (zigap.py:131-134):  sigma(logit(pi_j) - uv), floor 1e-10 where pi_j<=0.
-// lp = -inf encodes the initial indicator state p_d = (X>0) (zigap.py:77): the result is ~1.8e-35.
+// lp = -inf encodes the initial indicator state p_d = (X>0) (zigap.py:77): the result is exactly 0.
+// e (clamped to +-87) and ex = exp(e) are returned for the entropy term of the ELBO.
 __device__ __forceinline__ float dropout_p(float uv, float lp, float fl, float& e, float& ex) {
-    e = fminf(fmaxf(uv - lp, -80.f), 80.f);
+    e = fminf(fmaxf(uv - lp, -87.f), 87.5f);
     ex = __expf(e);
-    return fmaxf(__fdividef(1.f, 1.f + ex), fl);
+    const float pz = (e > 87.f) ? 0.f : __fdividef(1.f, 1.f + ex);
+    return fmaxf(pz, fl);
 }
 
 __device__ __forceinline__ double block_reduce_sum(double v, double* sbuf) {
@@ -331,6 +333,7 @@ k_factor_update(long long rows, int K, int KP,
             E_new[idx] = E;
             eE_new[idx] = expf(Elog);
         }
+        if (!Slog) continue;
         atomicAdd(&sSlog[k], (double)Elog);
         atomicAdd(&sShat[k], (double)E);
         tH += (double)h1 - log((double)h2) + lgamma((double)h1) + (1.0 - (double)h1) * psi;
@@ -342,12 +345,12 @@ k_factor_update(long long rows, int K, int KP,
     }
     if ((threadIdx.x & 31) == 0) { atomicAdd(&sH, tH); atomicAdd(&sP, tP); }
     __syncthreads();
-    if (threadIdx.x < K) {
+    if (Slog && threadIdx.x < K) {
         atomicAdd(Slog + threadIdx.x, sSlog[threadIdx.x]);
         atomicAdd(Shat + threadIdx.x, sShat[threadIdx.x]);
     }
     if (threadIdx.x == 0) {
-        atomicAdd(Hsum, sH);
+        if (Slog) atomicAdd(Hsum, sH);
         if (PUVsum) atomicAdd(PUVsum, sP);
     }
 }
@@ -579,7 +582,8 @@ static int update_grid(long long total) {
 }
 
 // write_state: 1 = regular update into generation 1-gen_old; 0 = only the ELBO term sum D_hat*uv of
-// the swept state (finalize); 2 = expectations of generation gen_old from (a1,a2) (init).
+// the swept state (finalize); 2 = expectations of generation gen_old from (a1,a2) with their column sums
+// (init); 3 = the same expectations without touching any sum (host-streamed slabs).
 int launch_row_update(const ori_problem_t* P, int g, int write_state, cudaStream_t st) {
     const int p = P->p, K = P->K, KP = P->KP;
     double* SlogU = P->red64 + p;
@@ -587,9 +591,11 @@ int launch_row_update(const ori_problem_t* P, int g, int write_state, cudaStream
     double* part = P->red64 + p + 2 * KP;
     const bool drop = P->flags & ORI_F_DROPOUT;
     const int grid = update_grid(P->n_rows * KP);
-    if (write_state == 2) {
+    if (write_state >= 2) {
+        const bool sums = write_state == 2;
         k_factor_update<true><<<grid, 256, 0, st>>>(P->n_rows, K, KP, nullptr, nullptr, nullptr, nullptr,
-            nullptr, nullptr, nullptr, P->a1, P->a2, P->U_hat[g], P->eU[g], SlogU, SU, part + R64_HROW, nullptr, 1);
+            nullptr, nullptr, nullptr, P->a1, P->a2, P->U_hat[g], P->eU[g], sums ? SlogU : nullptr, SU,
+            part + R64_HROW, nullptr, 1);
     } else {
         // GaP: rate = alpha2 + sum_j V_hat_jk (gap.py:98); the column sums live in gsum[KP..2KP)
         k_factor_update<false><<<grid, 256, 0, st>>>(P->n_rows, K, KP, P->Zi, P->eU[g],

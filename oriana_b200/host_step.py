@@ -1,0 +1,223 @@
+"""CAVI iterations on HOST-resident data: the reference-facing call with host buffers.
+
+The reference keeps X and every parameter in host numpy arrays and its `step()` (base.py:54-56) reads and
+writes them in place.  `HostStreamedCAVI.step()` is the same contract on the B200: every step, the count
+matrix and the row-side parameters are streamed from (pinned) host memory in row slabs, the three per-slab
+kernels (row pass -> U update -> gene pass) run while the next slab is in flight on a second stream, the
+updated row parameters stream back, and the gene-side update + M-step run once at the end.  Because the row
+side of the iteration never needs another row (SURVEY.md section 8e iii), a slab is needed on the device
+only while it is processed: the device footprint is two slabs, independent of n (out-of-core in HBM).
+
+All arithmetic is in the CUDA library (C ABI, include/oriana_b200.h); torch is used for pinned memory,
+streams and the copies.  No CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .models.base import pad_k
+from .sharding import RowSharding
+
+
+class HostStreamedCAVI:
+
+    def __init__(self, X_host, k, state, dropout=True, compat_quirk=False, slab_rows=None, sharded=False,
+                 process_group=None, elbo=True, keep_hyper=True):
+        """X_host: float32 CPU tensor [n, p] (pin it for asynchronous copies).  state: host arrays a1, a2
+        [n, k], b1, b2 [p, k], alpha1, alpha2, beta1, beta2 [k] (a reference model's state vector)."""
+        self._dev = _lib.require_cuda()
+        self._lib = _lib.load()
+        assert X_host.dtype == torch.float32 and X_host.dim() == 2 and not X_host.is_cuda
+        self.X = X_host
+        self.n, self.p = int(X_host.shape[0]), int(X_host.shape[1])
+        self.k = int(k)
+        KP = self._KP = pad_k(self.k)
+        n, p, K, dev = self.n, self.p, self.k, self._dev
+        self._shard = RowSharding(process_group, enabled=bool(sharded or process_group is not None))
+        self.n_total = self._shard.total_rows(n, dev)
+        self.dropout = bool(dropout)
+        self._flags = (_lib.ORI_F_DROPOUT if dropout else 0) | (_lib.ORI_F_ELBO if elbo else 0) \
+            | (_lib.ORI_F_QUIRK if (compat_quirk and dropout) else 0)
+        ldx = self._ldx = (p + 3) // 4 * 4
+        if slab_rows is None:
+            slab_rows = max(128, min(n, (512 << 20) // (4 * ldx)) // 128 * 128)
+        self.slab = S = int(min(max(1, slab_rows), max(1, n)))
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+        pin = torch.cuda.is_available()
+
+        def host(a, dtype, shape):
+            t = torch.as_tensor(np.asarray(a), dtype=dtype).reshape(shape).contiguous()
+            return t.pin_memory() if pin else t
+        # host-resident state (what a caller reads between steps)
+        self.a1 = host(state['a1'], torch.float32, (n, K)); self.a2 = host(state['a2'], torch.float32, (n, K))
+        self.b1 = host(state['b1'], torch.float32, (p, K)); self.b2 = host(state['b2'], torch.float32, (p, K))
+        self.hyper = host(np.stack([state[q] for q in ('alpha1', 'alpha2', 'beta1', 'beta2')]), torch.float64, (4, K))
+        self.pi_d = host(np.zeros(p), torch.float64, (p,))
+        self.lp = host(np.full(p, -np.inf), torch.float32, (p,))
+        self.pfloor = host(np.zeros(p), torch.float32, (p,))
+        self.scal = host(np.zeros(_lib.SCAL_SLOTS), torch.float64, (_lib.SCAL_SLOTS,))
+        self.elbo_trace = []
+        self.iterations = 0
+
+        f32 = dict(dtype=torch.float32, device=dev); f64 = dict(dtype=torch.float64, device=dev)
+        # device: gene side + reduction buffers (small), two sets of slab buffers
+        g = self._g = dict(
+            b1=torch.zeros((p, KP), **f32), b2=torch.zeros((p, KP), **f32), V_hat=torch.zeros((p, KP), **f32),
+            eV=torch.zeros((p, KP), **f32), red32=torch.zeros((2, p, KP), **f32),
+            lp=torch.zeros((p,), **f32), pfloor=torch.zeros((p,), **f32), hyper=torch.ones((4, K), **f64),
+            red64=torch.zeros((p + 2 * KP + _lib.R64_NSLOTS,), **f64), gsum=torch.zeros((2 * KP + 8,), **f64),
+            pi=torch.zeros((p,), **f64), scal=torch.zeros((_lib.SCAL_SLOTS,), **f64), trace=torch.zeros((4,), **f64))
+        self._slabs = []
+        for _ in range(2 if n > S else 1):
+            s = dict(X=torch.zeros((S, ldx), **f32), red64=torch.zeros_like(g['red64']),
+                     acc64=torch.zeros_like(g['red64']))
+            for name in ('a1', 'a2', 'U0', 'U1', 'e0', 'e1', 'Zi', 'a2s', 'eUw'):
+                s[name] = torch.zeros((S, KP), **f32)
+            s['stage'] = torch.zeros((2, S, K), **f32)     # unpadded a1|a2 as they travel
+            self._slabs.append(s)
+        self._streams = [torch.cuda.Stream(device=dev) for _ in self._slabs]
+        self._Pg = self._problem(None, 0)
+        self._keep_hyper = keep_hyper
+        self._init_pass()
+
+    # ------------------------------------------------------------------------------------------------
+    def _problem(self, s, rows):
+        g = self._g
+        P = _lib.OriProblem()
+        P.n_rows, P.n_total, P.ldx = rows, self.n_total, self._ldx
+        P.p, P.K, P.KP, P.flags = self.p, self.k, self._KP, self._flags
+        P.iter, P.trace_cap = 0, 4
+        dummy = g['red32'].data_ptr()
+        if s is not None:
+            P.X = s['X'].data_ptr()
+            P.a1, P.a2 = s['a1'].data_ptr(), s['a2'].data_ptr()
+            P.U_hat[0], P.U_hat[1] = s['U0'].data_ptr(), s['U1'].data_ptr()
+            P.eU[0], P.eU[1] = s['e0'].data_ptr(), s['e1'].data_ptr()
+            P.Zi, P.a2s, P.eUw = s['Zi'].data_ptr(), s['a2s'].data_ptr(), s['eUw'].data_ptr()
+        else:
+            P.X = None
+            P.a1 = P.a2 = P.Zi = P.a2s = P.eUw = dummy
+            P.U_hat[0] = P.U_hat[1] = P.eU[0] = P.eU[1] = dummy
+        P.b1, P.b2, P.V_hat, P.eV = (g[q].data_ptr() for q in ('b1', 'b2', 'V_hat', 'eV'))
+        P.red32, P.lp, P.pfloor = g['red32'].data_ptr(), g['lp'].data_ptr(), g['pfloor'].data_ptr()
+        P.hyper, P.red64, P.gsum = g['hyper'].data_ptr(), g['red64'].data_ptr(), g['gsum'].data_ptr()
+        P.pi_d, P.scal, P.elbo_trace = g['pi'].data_ptr(), g['scal'].data_ptr(), g['trace'].data_ptr()
+        return P
+
+    def _call(self, name, P, *args, stream=None):
+        st = ctypes.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
+        _lib.check(getattr(self._lib, name)(ctypes.byref(P), *args, st))
+
+    def _upload_genes(self):
+        g, K = self._g, self.k
+        for name in ('b1', 'b2'):
+            g[name][:, :K].copy_(getattr(self, name), non_blocking=True)
+        g['hyper'].copy_(self.hyper, non_blocking=True)
+        g['lp'].copy_(self.lp, non_blocking=True); g['pfloor'].copy_(self.pfloor, non_blocking=True)
+        g['scal'].copy_(self.scal, non_blocking=True)
+        self.h2d_bytes += 2 * self.p * K * 4 + 4 * K * 8 + self.p * 8 + _lib.SCAL_SLOTS * 8
+
+    def _upload_slab(self, s, r0, rows):
+        K, p = self.k, self.p
+        s['X'][:rows, :p].copy_(self.X[r0:r0 + rows], non_blocking=True)
+        s['stage'][0, :rows].copy_(self.a1[r0:r0 + rows], non_blocking=True)
+        s['stage'][1, :rows].copy_(self.a2[r0:r0 + rows], non_blocking=True)
+        s['a1'][:rows, :K] = s['stage'][0, :rows]; s['a2'][:rows, :K] = s['stage'][1, :rows]
+        self.h2d_bytes += rows * p * 4 + 2 * rows * K * 4
+
+    def _slab_loop(self, body):
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event(); ready.record(main)
+        for i, r0 in enumerate(range(0, self.n, self.slab)):
+            b = i % len(self._slabs)
+            st = self._streams[b]
+            if i < len(self._slabs):
+                st.wait_event(ready)
+            rows = min(self.slab, self.n - r0)
+            with torch.cuda.stream(st):
+                self._upload_slab(self._slabs[b], r0, rows)
+                body(self._slabs[b], self._problem(self._slabs[b], rows), r0, rows, st)
+        for st in self._streams:
+            main.wait_stream(st)
+
+    def _init_pass(self):
+        """Constant statistics of X + expectations of the initial state + (optionally) the first M-step
+        (base.py:43-52), streamed once."""
+        g = self._g
+        self._upload_genes()
+        g['red64'].zero_()
+        Pg = self._Pg
+
+        def body(s, P, r0, rows, st):
+            P.red64 = s['red64'].data_ptr()
+            self._call('ori_count_stats', P, stream=st)            # zero-fills its red64, then counts
+            self._call('ori_row_update', P, 0, 2, stream=st)       # + sum_i log U_hat, sum_i U_hat, entropy
+            s['acc64'].add_(s['red64'])                            # per-stream partial (no cross-stream RMW)
+        for s in self._slabs:
+            s['acc64'].zero_()
+        self._slab_loop(body)
+        for s in self._slabs:
+            g['red64'].add_(s['acc64'])
+        self._shard.allreduce_sum(g['red64'])
+        self._call('ori_init_expectations', Pg, 0)                 # n_rows = 0: gene side only
+        self._call('ori_mstep', Pg, _lib.ORI_M_INIT_KEEP if self._keep_hyper else _lib.ORI_M_INIT)
+        self._download_genes()
+        torch.cuda.current_stream().synchronize()
+
+    def _download_genes(self):
+        g, K = self._g, self.k
+        self.hyper.copy_(g['hyper'], non_blocking=True)
+        self.scal.copy_(g['scal'], non_blocking=True)
+        self.d2h_bytes += 4 * K * 8 + _lib.SCAL_SLOTS * 8
+        if self.dropout:
+            self.pi_d.copy_(g['pi'], non_blocking=True)
+            self.lp.copy_(g['lp'], non_blocking=True); self.pfloor.copy_(g['pfloor'], non_blocking=True)
+            self.d2h_bytes += self.p * 16
+
+    # ------------------------------------------------------------------------------------------------
+    def step(self):
+        """One CAVI iteration (base.py:54-56), host buffers in, host buffers out.  Returns the ELBO of the
+        state the step started from (it falls out of the row pass)."""
+        g, K, quirk = self._g, self.k, bool(self._flags & _lib.ORI_F_QUIRK)
+        self._upload_genes()
+        Pg = self._Pg
+        self._call('ori_init_expectations', Pg, 0)                  # V_hat, eV from (b1, b2): gene side only
+        g['red32'].zero_(); g['red64'].zero_()
+
+        def body(s, P, r0, rows, st):
+            self._call('ori_row_update', P, 0, 3, stream=st)        # U_hat, eU of the incoming (a1, a2)
+            s['Zi'].zero_(); s['a2s'].zero_()
+            self._call('ori_pass_rows', P, 0, stream=st)
+            self._call('ori_row_update', P, 0, 1, stream=st)
+            self._call('ori_pass_genes', P, 0, stream=st)
+            s['stage'][0, :rows] = s['a1'][:rows, :K]; s['stage'][1, :rows] = s['a2'][:rows, :K]
+            self.a1[r0:r0 + rows].copy_(s['stage'][0, :rows], non_blocking=True)
+            self.a2[r0:r0 + rows].copy_(s['stage'][1, :rows], non_blocking=True)
+            self.d2h_bytes += 2 * rows * K * 4
+        self._slab_loop(body)
+        if self._shard.enabled:
+            self._shard.allreduce_sum(g['red32']); self._shard.allreduce_sum(g['red64'])
+        self._call('ori_gene_update', Pg, 1)
+        self._call('ori_mstep', Pg, _lib.ORI_M_STEP)
+        self.b1.copy_(g['b1'][:, :K], non_blocking=True); self.b2.copy_(g['b2'][:, :K], non_blocking=True)
+        self.d2h_bytes += 2 * self.p * K * 4
+        self._download_genes()
+        torch.cuda.current_stream().synchronize()                   # results are on the host when we return
+        self.iterations += 1
+        e = float(self.scal[4])
+        self.elbo_trace.append(e)
+        return e
+
+    def state_dict(self):
+        s = dict(a1=self.a1.numpy().astype(np.float64), a2=self.a2.numpy().astype(np.float64),
+                 b1=self.b1.numpy().astype(np.float64), b2=self.b2.numpy().astype(np.float64))
+        for i, q in enumerate(('alpha1', 'alpha2', 'beta1', 'beta2')):
+            s[q] = self.hyper[i].numpy().copy()
+        if self.dropout:
+            s['pi_prev'] = self.pi_d.numpy().copy()      # generates the current D_hat (zigap.py:131-132)
+        s['iterations'] = self.iterations
+        return s

@@ -105,6 +105,7 @@ class FactorModel(metaclass=ABCMeta):
         self._pi_stale = False
         self._D_cache = None
         self._started = False
+        self._timers = None
 
         self._allocate(cmatrix)
 
@@ -263,7 +264,15 @@ class FactorModel(metaclass=ABCMeta):
                                % self._trace_cap)
         if self._dirty:
             self._refresh()
-        self._call('ori_cavi_step_local', self._gen)
+        if self._timers is None:
+            self._call('ori_cavi_step_local', self._gen)
+        else:   # same launches, with CUDA events around the two kernels that stream X
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            self._call('ori_zero_accumulators', 1)
+            ev[0].record(); self._call('ori_pass_rows', self._gen); ev[1].record()
+            self._call('ori_row_update', self._gen, 1)
+            ev[2].record(); self._call('ori_pass_genes', self._gen); ev[3].record()
+            self._timers.append(ev)
         if self._shard.enabled:
             self._shard.allreduce_sum(self._red32)
             self._shard.allreduce_sum(self._red64)
@@ -306,6 +315,19 @@ class FactorModel(metaclass=ABCMeta):
         self._shard.allreduce_sum(self._red64)
         self._call('ori_mstep', _lib.ORI_M_FINALIZE)
         self._pi_stale = False
+
+    def enable_kernel_timing(self, on=True):
+        """Record CUDA events around the row pass and the gene pass of every following step."""
+        self._timers = [] if on else None
+
+    def kernel_times_ms(self):
+        """Mean device time of (row pass, gene pass) over the steps timed so far (synchronises)."""
+        torch.cuda.synchronize()
+        if not self._timers:
+            return None
+        rows = [e[0].elapsed_time(e[1]) for e in self._timers]
+        genes = [e[2].elapsed_time(e[3]) for e in self._timers]
+        return dict(pass_rows=sum(rows) / len(rows), pass_genes=sum(genes) / len(genes), steps=len(rows))
 
     # ------------------------------------------------------------------------------------------------
     def elbo(self):

@@ -27,7 +27,7 @@ for name in GOLDEN_CASES:
                 print(name, 't=%d' % t, line)
         ref = {k: v.copy() for k, v in s.items()}
         m = cls(s['X'], k=s['a1'].shape[1], use_factors=False, state=s, compat_quirk=False)
-        want = [cn.elbo(ref)]
+        want = [cn.elbo(ref, guard32=True)]
         for t in range(5):
             m.step(); cn.step(ref, quirk=False); want.append(cn.elbo(ref))
         got = m.elbo_trace

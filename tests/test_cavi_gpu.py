@@ -62,7 +62,7 @@ def test_dequirked_update_and_elbo_match_oracle(cuda_lib, name):
     s = golden_state(g, 0)
     m = make_model(s, quirk=False)
     ref = {k: v.copy() for k, v in s.items()}
-    e0 = cn.elbo(ref)
+    e0 = cn.elbo(ref, guard32=True)     # random Gamma(1) start: fp32 exp underflow + den guard (zigap.py:90)
     assert abs(m.elbo() - e0) <= 1e-6 * abs(e0), (m.elbo(), e0)
     want = [e0]
     for t in range(1, 9):
@@ -172,3 +172,24 @@ def test_full_size_properties_config2(cuda_lib):
     assert relerr(mb.a1.asarray(), ma.a1.asarray()[pn]) < 1e-5
     assert relerr(mb.b1.asarray(), ma.b1.asarray()) < 1e-5 and relerr(mb.pi_d.asarray(), ma.pi_d.asarray()) < 1e-6
     assert abs(ma.elbo() - mb.elbo()) < 1e-6 * abs(ma.elbo())
+
+
+@pytest.mark.parametrize('name', ['zigap_ragged', 'gap_ragged'])
+def test_host_streamed_step_matches_device_model(cuda_lib, name):
+    """The host-buffer entry (what bench.py's e2e times) gives the device model's results, slab by slab."""
+    import torch
+    from oriana_b200.host_step import HostStreamedCAVI
+    g = load_golden(name)
+    s = golden_state(g, 0)
+    m = make_model(s, quirk=False)
+    Xh = torch.as_tensor(s['X'].astype(np.float32)).pin_memory()
+    h = HostStreamedCAVI(Xh, s['a1'].shape[1], s, dropout='p_d' in s, slab_rows=64)   # 4 ragged slabs
+    elbos = []
+    for _ in range(4):
+        m.step(); elbos.append(h.step())
+    hs = h.state_dict()
+    for k in PARAMS:
+        assert relerr(hs[k], getattr(m, k).asarray()) < 2e-6, k
+    want = m.elbo_trace[:4]
+    assert np.max(np.abs(np.asarray(elbos) - want) / np.abs(want)) < 1e-9
+    assert h.h2d_bytes > 4 * s['X'].size * 4 and h.d2h_bytes > 0

@@ -353,13 +353,26 @@ class FactorModel(metaclass=ABCMeta):
     def V_hat(self):
         return self._Vhat[:, :self.k].to(torch.float64).cpu().numpy()
 
+    def _meanlog(self, h1, h2):
+        """E[log .] = psi(a) - log(b) as float32 (gamma.py:48-61).  The kernels keep exp(E[log .]) only; the
+        log-expectation itself is re-derived on request (it can be below the float32 exp underflow)."""
+        a = h1[:, :self.k].contiguous(); b = h2[:, :self.k].contiguous()
+        out = torch.empty_like(a)
+        _lib.check(self._lib.ori_gamma_expect_f32(a.data_ptr(), b.data_ptr(), None, out.data_ptr(), None,
+                                                  a.numel(), _lib.stream_ptr()))
+        return out.cpu().numpy()
+
     @property
     def log_U_hat(self):
-        return torch.log(self._eU[self._gen][:, :self.k]).cpu().numpy()
+        if self._dirty:
+            self._refresh()
+        return self._meanlog(self._a1, self._a2)
 
     @property
     def log_V_hat(self):
-        return torch.log(self._eV[:, :self.k]).cpu().numpy()
+        if self._dirty:
+            self._refresh()
+        return self._meanlog(self._b1, self._b2)
 
     def device_state(self):
         """Zero-copy views of the device-resident state (torch CUDA tensors)."""

@@ -58,7 +58,8 @@ def test_against_c_loop_with_soft_dropout(cuda_lib, shape, quirk):
     Zi, Zj, Z3 = z_op(cuda_lib, lU, lV, X, D, quirk=quirk, third=True)
     rZi, rZj, rZ3 = zloop.zigap_z(lU, lV, D, X, quirk=quirk, third=True)
     assert relerr(Zi, rZi) < 1e-5 and relerr(Zj, rZj) < 1e-5
-    assert relerr(Z3, rZ3, floor=1e-5) < 2e-5
+    # signed terms cancel in zigap.py:95: judge the absolute error against the array's scale
+    assert np.max(np.abs(Z3 - rZ3)) < 3e-6 * np.max(np.abs(rZ3))
     gZi, gZj = z_op(cuda_lib, lU, lV, X)
     rZi, rZj = zloop.gap_z(lU, lV, X)
     assert relerr(gZi, rZi) < 1e-5 and relerr(gZj, rZj) < 1e-5

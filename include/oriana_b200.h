@@ -56,7 +56,7 @@ typedef struct ori_problem {
     int64_t ldx;           /* row stride of X in elements (multiple of 4)                */
     int32_t p;             /* genes                                                      */
     int32_t K;             /* latent dimension                                           */
-    int32_t KP;            /* padded latent dimension: 8, 16, 32 or 64                   */
+    int32_t KP;            /* padded latent dimension: 8, 16, 32 or 64, >= K             */
     uint32_t flags;        /* ORI_F_*                                                    */
     int32_t iter;          /* completed iterations (index into elbo_trace)               */
     int32_t trace_cap;     /* capacity of elbo_trace                                     */
@@ -90,6 +90,12 @@ typedef struct ori_problem {
     double* pi_d;          /* [p] Bernoulli prior pi(t)  zigap.py:158                    */
     double* scal;          /* [16] see ScalSlot in csrc/common.cuh                       */
     double* elbo_trace;    /* [trace_cap]                                                */
+
+    /* tensor path (tcgen05/TMA kernels, csrc/kernels_tc.cu): caller-owned scratch of at least
+     * ori_tc_workspace_floats(n_rows, p) floats, 128-byte aligned; NULL selects the CUDA-core kernels.
+     * Needs KP == 32 (any K <= 32, zero padded). */
+    float* tc_ws;
+    int64_t tc_ws_floats;
 } ori_problem_t;
 
 /* ---- library ---------------------------------------------------------------------------------- */
@@ -109,6 +115,10 @@ int ori_gamma_expect_f32(const float* a1, const float* a2, float* E, float* Elog
                          int64_t count, void* stream);
 
 /* ---- the CAVI iteration, device-resident state -------------------------------------------------- */
+/* Scratch floats the tensor path needs for a rank owning n_rows cells of p genes. */
+int64_t ori_tc_workspace_floats(int64_t n_rows, int32_t p);
+/* 1 when the calls below will take the tensor path for this problem, 0 for the CUDA-core kernels. */
+int ori_uses_tensor_path(const ori_problem_t* P);
 /* Validate a problem description (shapes, alignment, null pointers). */
 int ori_problem_check(const ori_problem_t* P);
 /* Constant data statistics: sum lgamma(X+1), nnz -> scal; column sums of (X>0) -> red64[0..p). */

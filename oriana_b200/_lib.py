@@ -32,6 +32,7 @@ class OriProblem(C.Structure):
         ('red32', C.c_void_p), ('lp', C.c_void_p), ('pfloor', C.c_void_p),
         ('hyper', C.c_void_p), ('red64', C.c_void_p), ('gsum', C.c_void_p), ('pi_d', C.c_void_p),
         ('scal', C.c_void_p), ('elbo_trace', C.c_void_p),
+        ('tc_ws', C.c_void_p), ('tc_ws_floats', C.c_int64),
     ]
 
 
@@ -42,6 +43,8 @@ _SIGNATURES = {
     'ori_device_check': ([C.c_int], C.c_int),
     'ori_special_f64': ([C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p], C.c_int),
     'ori_gamma_expect_f32': ([C.c_void_p] * 5 + [C.c_int64, C.c_void_p], C.c_int),
+    'ori_tc_workspace_floats': ([C.c_int64, C.c_int32], C.c_int64),
+    'ori_uses_tensor_path': ([_PP], C.c_int),
     'ori_problem_check': ([_PP], C.c_int),
     'ori_count_stats': ([_PP, C.c_void_p], C.c_int),
     'ori_init_expectations': ([_PP, C.c_int, C.c_void_p], C.c_int),

@@ -137,7 +137,10 @@ int ori_problem_check(const ori_problem_t* P) {
     if (!P) return set_error(ORI_EINVAL, "null problem");
     if (P->n_rows < 0 || P->p <= 0 || P->K <= 0) return set_error(ORI_EINVAL, "bad shape n_rows=%lld p=%d K=%d", (long long)P->n_rows, P->p, P->K);
     if (P->K > 64) return set_error(ORI_EUNSUPPORTED, "K=%d > 64 is not supported", P->K);
-    if (P->KP != pad_k(P->K)) return set_error(ORI_EINVAL, "KP=%d, expected %d for K=%d", P->KP, pad_k(P->K), P->K);
+    if (P->KP < P->K || (P->KP != 8 && P->KP != 16 && P->KP != 32 && P->KP != 64))
+        return set_error(ORI_EINVAL, "KP=%d must be 8, 16, 32 or 64 and >= K=%d", P->KP, P->K);
+    if (P->tc_ws && (((uintptr_t)P->tc_ws & 127) || P->tc_ws_floats < tc_workspace_floats(P->n_rows, P->p)))
+        return set_error(ORI_EINVAL, "tc_ws must be 128-byte aligned and hold ori_tc_workspace_floats() floats");
     if (P->ldx < P->p || (P->ldx & 3)) return set_error(ORI_EINVAL, "ldx=%lld must be >= p and a multiple of 4", (long long)P->ldx);
     if (P->n_total < P->n_rows || P->n_total <= 0) return set_error(ORI_EINVAL, "n_total=%lld < n_rows", (long long)P->n_total);
     if ((P->flags & ORI_F_QUIRK) && P->p < P->K) return set_error(ORI_EINVAL, "quirk mode needs p >= K (zigap.py:94 reads D_hat[i, k])");
@@ -174,10 +177,28 @@ int ori_init_expectations(const ori_problem_t* P, int gen, void* stream) {
     return launch_gene_update(P, 2, st);
 }
 
+// row pass: tensor path = operand preparation + tcgen05 kernel (statistics come from the gene pass there)
+static int pass_rows_any(const ori_problem_t* P, int gen_old, cudaStream_t st) {
+    if (!tc_eligible(P)) return launch_pass_rows_simt(P, gen_old, st);
+    ORI_TRY(launch_tc_prep_genes(P, st));
+    ORI_TRY(launch_tc_prep_rows(P, gen_old, st));
+    return launch_pass_rows_tc(P, st);
+}
+static int pass_genes_any(const ori_problem_t* P, int gen_old, cudaStream_t st) {
+    if (P->flags & ORI_F_QUIRK) ORI_TRY(launch_quirk_weights(P, gen_old, st));
+    if (!tc_eligible(P)) return launch_pass_genes_simt(P, gen_old, st);
+    ORI_TRY(launch_tc_prep_rows_T(P, gen_old, st));
+    return launch_pass_genes_tc(P, st);
+}
+
+int64_t ori_tc_workspace_floats(int64_t n_rows, int32_t p) { return tc_workspace_floats(n_rows, p); }
+
+int ori_uses_tensor_path(const ori_problem_t* P) { return (P && tc_eligible(P)) ? 1 : 0; }
+
 int ori_pass_rows(const ori_problem_t* P, int gen_old, void* stream) {
     ORI_TRY(ori_problem_check(P));
     if (P->n_rows == 0) return ORI_OK;
-    return launch_pass_rows_simt(P, gen_old, (cudaStream_t)stream);
+    return pass_rows_any(P, gen_old, (cudaStream_t)stream);
 }
 
 int ori_row_update(const ori_problem_t* P, int gen_old, int write_state, void* stream) {
@@ -189,9 +210,7 @@ int ori_row_update(const ori_problem_t* P, int gen_old, int write_state, void* s
 int ori_pass_genes(const ori_problem_t* P, int gen_old, void* stream) {
     ORI_TRY(ori_problem_check(P));
     if (P->n_rows == 0) return ORI_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (P->flags & ORI_F_QUIRK) ORI_TRY(launch_quirk_weights(P, gen_old, st));
-    return launch_pass_genes_simt(P, gen_old, st);
+    return pass_genes_any(P, gen_old, (cudaStream_t)stream);
 }
 
 int ori_gene_update(const ori_problem_t* P, int write_state, void* stream) {
@@ -227,10 +246,9 @@ int ori_cavi_step_local(const ori_problem_t* P, int gen_old, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     ORI_TRY(zero_accumulators(P, st, true));
     if (P->n_rows == 0) return ORI_OK;
-    ORI_TRY(launch_pass_rows_simt(P, gen_old, st));
+    ORI_TRY(pass_rows_any(P, gen_old, st));
     ORI_TRY(launch_row_update(P, gen_old, 1, st));
-    if (P->flags & ORI_F_QUIRK) ORI_TRY(launch_quirk_weights(P, gen_old, st));
-    return launch_pass_genes_simt(P, gen_old, st);
+    return pass_genes_any(P, gen_old, st);
 }
 
 int ori_cavi_step_global(const ori_problem_t* P, int gen_old, void* stream) {
@@ -250,10 +268,13 @@ int ori_cavi_step(const ori_problem_t* P, int gen_old, void* stream) {
 int ori_finalize_local(const ori_problem_t* P, int gen, void* stream) {
     ORI_TRY(ori_problem_check(P));
     cudaStream_t st = (cudaStream_t)stream;
-    ORI_TRY(zero_accumulators(P, st, false));
+    const bool tc = tc_eligible(P);
+    ORI_TRY(zero_accumulators(P, st, tc));
     if (P->n_rows == 0) return ORI_OK;
-    ORI_TRY(launch_pass_rows_simt(P, gen, st));
-    return launch_row_update(P, gen, 0, st);
+    ORI_TRY(pass_rows_any(P, gen, st));
+    ORI_TRY(launch_row_update(P, gen, 0, st));
+    // tensor path: colsum D_hat and the ELBO partials come out of the gene pass (red32 is scratch here)
+    return tc ? pass_genes_any(P, gen, st) : ORI_OK;
 }
 
 int ori_dropout_posterior_f32(const ori_problem_t* P, int gen, float* out, int64_t ldo,

@@ -77,7 +77,7 @@ class FactorModel(metaclass=ABCMeta):
     _dropout = False     # ZIGaP sets this
 
     def __init__(self, cmatrix, k=2, use_factors=True, *, state=None, compat_quirk=False, sharded=False,
-                 process_group=None, elbo=True, trace_cap=4096, force_simt=False):
+                 process_group=None, elbo=True, trace_cap=4096, force_simt=False, tensor=None):
         self._dev = _lib.require_cuda()
         self._lib = _lib.load()
         _lib.check(self._lib.ori_device_check(self._dev.index or 0))
@@ -90,7 +90,14 @@ class FactorModel(metaclass=ABCMeta):
         self.n = int(cmatrix.shape[0])
         self.m = self.p = int(cmatrix.shape[1])
         self.dims = Dimensions({'n': self.n, 'm': self.m, 'p': self.p, 'k': self.k})
-        self._KP = pad_k(self.k)
+        # kernel family: the tcgen05/TMA tensor path (K <= 32, tf32 contractions with fp32 accumulation) for
+        # problems large enough to fill the machine, the CUDA-core fp32 kernels otherwise (or when forced)
+        if tensor is None:
+            tensor = (not force_simt) and self.k <= 32 and self.n * self.p >= (1 << 21)
+        if tensor and (self.k > 32 or force_simt):
+            raise ValueError('the tensor path needs k <= 32 and force_simt=False')
+        self._tensor = bool(tensor)
+        self._KP = 32 if self._tensor else pad_k(self.k)
         self._shard = RowSharding(process_group if (sharded or process_group is not None) else None,
                                   enabled=bool(sharded or process_group is not None))
         self.n_total = self._shard.total_rows(self.n, self._dev)
@@ -170,6 +177,9 @@ class FactorModel(metaclass=ABCMeta):
         self._pi = torch.zeros((p,), **f64) if self._dropout else None
         self._scal = torch.zeros((_lib.SCAL_SLOTS,), **f64)
         self._trace = torch.zeros((self._trace_cap,), **f64)
+        self._tc_ws = None
+        if self._tensor:
+            self._tc_ws = torch.empty((int(self._lib.ori_tc_workspace_floats(n, p)) + 32,), **f32)
 
         P = _lib.OriProblem()
         P.n_rows, P.n_total, P.ldx = n, self.n_total, ldx
@@ -187,8 +197,13 @@ class FactorModel(metaclass=ABCMeta):
         P.red32, P.lp, P.pfloor = ptr(self._red32), ptr(self._lp), ptr(self._pfloor)
         P.hyper, P.red64, P.gsum = ptr(self._hyper), ptr(self._red64), ptr(self._gsum)
         P.pi_d, P.scal, P.elbo_trace = ptr(self._pi), ptr(self._scal), ptr(self._trace)
+        if self._tc_ws is not None:
+            P.tc_ws, P.tc_ws_floats = self._tc_ws.data_ptr(), self._tc_ws.numel()
         self._P = P
         _lib.check(self._lib.ori_problem_check(ctypes.byref(P)))
+        self.uses_tensor_path = bool(self._lib.ori_uses_tensor_path(ctypes.byref(P)))
+        if self._tensor and not self.uses_tensor_path and n > 0:
+            raise _lib.OrianaB200Error('tensor path requested but not available on this device / driver')
 
         K_ = K
         self.a1 = DeviceView(self, lambda: self._a1[:, :K_])

@@ -1,7 +1,9 @@
 // tc_probe.cu -- building-block checks for the tensor-core path, run on a B200 before the real kernels:
 //   T1  TMA(SW128) -> tcgen05.mma kind::tf32, A and B K-major from smem           D1[128x64] = A1[128x32] . B1[64x32]^T
-//   T2  multi-chunk K-major A + MN-major B (rows of the tile are the contraction)  D2[128x32] = A2[128x64] . B2[64x32]
-//   T3  A from TMEM (tcgen05.st -> mma TS) with the MN-major B of T2               D3 == D2
+//   T2  multi-chunk K-major A and B (contraction spans two 128-byte swizzle chunks)   D2[128x32] = A2[128x64] . B2T[32x64]^T
+//   T3  A from TMEM (tcgen05.st -> mma TS) with the B of T2                          D3 == D2
+// (MN-major tf32 operands need the SWIZZLE_128B_ATOM_32B layout, which no K-major operand accepts, so the
+//  kernels keep transposed copies of the factor arrays and use K-major descriptors everywhere.)
 //   T4  what the tensor core does with fp32 inputs that are not tf32-representable (truncate or round)
 // Inputs of T1-T3 are tf32-exact, so the results must match the CPU bit for bit.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o tc_probe scripts/tc_probe.cu
@@ -24,7 +26,7 @@ __global__ void __launch_bounds__(128) k_probe(const __grid_constant__ Maps maps
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     float* sA = (float*)smem;                    // up to 2 chunks [128 x 32] = 32 KB
-    float* sB = (float*)(smem + 32768);          // [64 x 32] = 8 KB
+    float* sB = (float*)(smem + 32768);          // [64 x 32] = 8 KB, or 2 chunks [32 x 32] of B2T
     __shared__ uint64_t bar_load, bar_mma;
     __shared__ uint32_t tmem_base_s;
 
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(128) k_probe(const __grid_constant__ Maps maps
                 tma_load_2d(sA + 4096, &maps.a2, &bar_load, 32, 0);
             }
             tma_load_2d(sB, &maps.b2, &bar_load, 0, 0);
+            tma_load_2d(sB + 1024, &maps.b2, &bar_load, 32, 0);
         }
     }
     if (mode == 3) {   // every thread writes its row of A2 (64 values) into TMEM columns [64, 128)
@@ -73,9 +76,9 @@ __global__ void __launch_bounds__(128) k_probe(const __grid_constant__ Maps maps
                 mma_tf32_ss(tmem, ad, bd, idesc, k > 0);
             }
         } else {
-            const uint32_t idesc = make_idesc_tf32(128, 32, false, true);
+            const uint32_t idesc = make_idesc_tf32(128, 32, false, false);
             for (int ks = 0; ks < 8; ++ks) {
-                const uint64_t bd = make_smem_desc(smem_u32(sB) + ks * 1024, 8192, 1024);
+                const uint64_t bd = make_smem_desc(smem_u32(sB) + (ks >> 2) * 4096 + (ks & 3) * 32, 16, 1024);
                 if (mode == 2) {
                     const uint64_t ad = make_smem_desc(smem_u32(sA) + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
                     mma_tf32_ss(tmem, ad, bd, idesc, ks > 0);
@@ -123,7 +126,7 @@ int main() {
 
     Maps m, m4;
     bool ok = make_tmap_f32(&m.a1, dA1, 128, 32, 32, 32, 128) && make_tmap_f32(&m.b1, dB1, 64, 32, 32, 32, 64) &&
-              make_tmap_f32(&m.a2, dA2, 128, 64, 64, 32, 128) && make_tmap_f32(&m.b2, dB2, 64, 32, 32, 32, 64);
+              make_tmap_f32(&m.a2, dA2, 128, 64, 64, 32, 128) && make_tmap_f32(&m.b2, dB2, 32, 64, 64, 32, 32);
     m4 = m;
     ok = ok && make_tmap_f32(&m4.a1, dA4, 128, 32, 32, 32, 128) && make_tmap_f32(&m4.b1, dB4, 64, 32, 32, 32, 64);
     if (!ok) { printf("tensor map creation failed\n"); return 2; }
@@ -152,7 +155,7 @@ int main() {
     }
     std::vector<float> ref2(128 * 32);
     for (int i = 0; i < 128; ++i) for (int j = 0; j < 32; ++j) {
-        float r = 0; for (int k = 0; k < 64; ++k) r += A2[i * 64 + k] * B2[k * 32 + j];
+        float r = 0; for (int k = 0; k < 64; ++k) r += A2[i * 64 + k] * B2[j * 64 + k];
         ref2[i * 32 + j] = r;
     }
     for (int mode = 2; mode <= 3; ++mode) {
@@ -162,7 +165,7 @@ int main() {
             double d = fabs((double)ref2[i] - out[i]); if (d > maxd) maxd = d;
             if (d != 0 && bad++ < 5) printf("  T%d mismatch [%d,%d] got %g want %g\n", mode, i / 32, i % 32, out[i], ref2[i]);
         }
-        printf("T%d (%s A, MN-major B): %s  bad=%d maxdiff=%g\n", mode, mode == 2 ? "2-chunk K-major smem" : "TMEM", bad ? "FAIL" : "PASS", bad, maxd);
+        printf("T%d (%s A, 2-chunk K-major B): %s  bad=%d maxdiff=%g\n", mode, mode == 2 ? "2-chunk K-major smem" : "TMEM", bad ? "FAIL" : "PASS", bad, maxd);
         fails += bad != 0;
     }
     run(4, m4, 64);

@@ -94,7 +94,7 @@ def test_library_exports_every_declared_symbol():
     """The C-ABI library loads and exports exactly what include/oriana_b200.h declares."""
     from oriana_b200 import _lib
     header = open(os.path.join(ROOT, 'include', 'oriana_b200.h')).read()
-    declared = sorted(set(re.findall(r'^int\s+(ori_\w+)\s*\(', header, flags=re.M)))
+    declared = sorted(set(re.findall(r'^(?:int|int64_t)\s+(ori_\w+)\s*\(', header, flags=re.M)))
     assert declared == _lib.exported_symbols()
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
@@ -102,7 +102,7 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().ori_version() >= 100
     # struct layout agreed between the header and the ctypes mirror
     n_ptr = len(re.findall(r'^\s+(?:const\s+)?(?:float|double)\s*\*', header.split('typedef struct ori_problem')[1].split('} ori_problem_t')[0], flags=re.M))
-    assert ctypes.sizeof(_lib.OriProblem) == 3 * 8 + 6 * 4 + 23 * 8 and n_ptr >= 19
+    assert ctypes.sizeof(_lib.OriProblem) == 3 * 8 + 6 * 4 + 24 * 8 + 8 and n_ptr >= 20
 
 
 def test_no_cpu_fallback():

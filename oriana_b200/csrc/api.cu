@@ -181,14 +181,13 @@ int ori_init_expectations(const ori_problem_t* P, int gen, void* stream) {
 static int pass_rows_any(const ori_problem_t* P, int gen_old, cudaStream_t st) {
     if (!tc_eligible(P)) return launch_pass_rows_simt(P, gen_old, st);
     ORI_TRY(launch_tc_prep_genes(P, st));
-    ORI_TRY(launch_tc_prep_rows(P, gen_old, st));
-    return launch_pass_rows_tc(P, st);
+    return launch_pass_rows_tc(P, gen_old, st);
 }
 static int pass_genes_any(const ori_problem_t* P, int gen_old, cudaStream_t st) {
     if (P->flags & ORI_F_QUIRK) ORI_TRY(launch_quirk_weights(P, gen_old, st));
     if (!tc_eligible(P)) return launch_pass_genes_simt(P, gen_old, st);
-    ORI_TRY(launch_tc_prep_rows_T(P, gen_old, st));
-    return launch_pass_genes_tc(P, st);
+    ORI_TRY(launch_tc_prep_rows(P, gen_old, st));
+    return launch_pass_genes_tc(P, gen_old, st);
 }
 
 int64_t ori_tc_workspace_floats(int64_t n_rows, int32_t p) { return tc_workspace_floats(n_rows, p); }

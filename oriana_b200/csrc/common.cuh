@@ -47,8 +47,7 @@ long long tc_workspace_floats(long long n_rows, int p);
 bool tc_eligible(const ori_problem_t* P);
 int launch_tc_prep_genes(const ori_problem_t* P, cudaStream_t st);
 int launch_tc_prep_rows(const ori_problem_t* P, int gen_old, cudaStream_t st);
-int launch_tc_prep_rows_T(const ori_problem_t* P, int gen_old, cudaStream_t st);
-int launch_pass_rows_tc(const ori_problem_t* P, cudaStream_t st);
-int launch_pass_genes_tc(const ori_problem_t* P, cudaStream_t st);
+int launch_pass_rows_tc(const ori_problem_t* P, int gen_old, cudaStream_t st);
+int launch_pass_genes_tc(const ori_problem_t* P, int gen_old, cudaStream_t st);
 
 }  // namespace ori

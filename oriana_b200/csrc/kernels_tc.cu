@@ -1,6 +1,6 @@
 // kernels_tc.cu -- the two X-streaming passes of the CAVI iteration on the sm_100a tensor path:
 // TMA-staged tiles, tcgen05.mma kind::tf32 with fp32 accumulators in TMEM, the ratio / dropout posterior
-// computed between the two groups of contractions on the TMEM-resident tile (A operand from TMEM).
+// computed between the two groups of contractions on the TMEM-resident tile (A operands from TMEM).
 //
 // Per tile of 128 "own" x 64 "sweep" entries (own = cells in the row pass, genes in the gene pass):
 //   S:  den = eO . eS^T     (3xTF32: hi.hi + hi.lo + lo.hi)          zigap.py:86-90
@@ -9,14 +9,23 @@
 //       (written back over den / uv in TMEM, rounded to tf32 to nearest)
 //   P:  acc1 += R . S1 ; acc2 += D . S2                              zigap.py:93-94 / :116, :124
 // where S1, S2 are the transposed (K-major) copies of exp(E log .) and of the matching U_hat / V_hat.
+//
+// Data movement per CTA (one CTA per SM, persistent over work items = own tile x chunk of the sweep):
+//   own side   the 128 own rows of exp(E log .) and E[.] are read once per work item from the raw factor
+//              arrays, split hi/lo in registers and parked in TMEM (128 columns): every S contraction takes
+//              its A operand from TMEM, so shared memory only carries the streamed side;
+//   sweep side three independent TMA rings: K-major hi/lo operands (consumed by S, freed as soon as S has
+//              run), transposed operands (consumed by P) and the X tile (+ logit pi) for the element-wise
+//              warps, so that a stage is recycled as early as its own consumer allows.
 // MN-major tf32 operands would need the SWIZZLE_128B_ATOM_32B smem layout, which no K-major operand accepts,
 // hence the transposed copies (prepared by k_tc_prep_*) and K-major descriptors everywhere
 // (scripts/tc_probe.cu checks every descriptor form used here against the CPU).
 //
-// Warp roles (320 threads, 1 CTA per SM, persistent over work items):
-//   warp 0    TMA producer            (one lane)
-//   warp 1    MMA issuer + TMEM owner (one lane issues)
-//   warps 2-9 element-wise stage + epilogue; warp w owns TMEM lanes 32*(w%4).. and half of the 64 columns
+// Warp roles (64 + 32*NEW threads):
+//   warp 0       TMA producer (one lane polls the three rings)
+//   warp 1       MMA issuer + TMEM owner (one lane issues)
+//   warps 2..    NEW element-wise warps; warp w owns TMEM lanes 32*(w%4).. and 64/(NEW/4) of the 64 columns
+#include <cstdlib>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -26,34 +35,42 @@ using namespace tc;
 constexpr int TC_OWN = 128;
 constexpr int TC_SW = 64;
 constexpr int TC_KP_CONST = 32;     // latent dimension of the tensor path (K <= 32, zero padded)
-constexpr int TC_EW_WARPS = 8;
-constexpr int TC_THREADS = 64 + 32 * TC_EW_WARPS;
 
-constexpr uint32_t RES_BYTES = 4 * 16384;          // own-side K-major operands: eO_hi, eO_lo, Oh_hi, Oh_lo [128 x 32]
-constexpr uint32_t ST_K = 0;                       // sweep-side K-major operands: 4 x [64 x 32]
-constexpr uint32_t ST_T = 32768;                   // sweep-side transposed operands: 2 arrays x 2 chunks [32 x 32]
-constexpr uint32_t ST_X = 49152;                   // X tile, 32 KB
-constexpr uint32_t STAGE_BYTES = 81920;
-constexpr uint32_t LP_OFF = RES_BYTES + 2 * STAGE_BYTES;   // per stage: lp2[64] | floor[64]
-constexpr uint32_t BAR_OFF = LP_OFF + 1024;
-constexpr uint32_t TC_SMEM_BYTES = BAR_OFF + 256 + 1024;   // + barriers + alignment slack
+constexpr int KST = 2;              // ring depths
+constexpr int TST = 2;
+constexpr int XST = 3;
+constexpr uint32_t K_STAGE = 32768;   // 4 K-major arrays [64 x 32]: hi(e) lo(e) hi(E) lo(E)
+constexpr uint32_t T_STAGE = 16384;   // 2 transposed arrays x 2 chunks [32 x 32]
+constexpr uint32_t X_STAGE = 32768;   // X tile
+constexpr uint32_t LP_STAGE = 512;    // lp2[64] | floor[64]
+constexpr uint32_t OFF_K = 0;
+constexpr uint32_t OFF_T = OFF_K + KST * K_STAGE;
+constexpr uint32_t OFF_X = OFF_T + TST * T_STAGE;
+constexpr uint32_t OFF_LP = OFF_X + XST * X_STAGE;
+constexpr uint32_t OFF_BAR = OFF_LP + XST * LP_STAGE;
+constexpr uint32_t TC_SMEM_BYTES = OFF_BAR + 512 + 1024;   // + barriers + alignment slack
 
-enum { B_RES_FULL = 0, B_RES_EMPTY = 1, B_FULL = 2, B_EMPTY = 4, B_SREADY = 6, B_PREADY = 8, B_ACC_READY = 10,
-       B_ACC_FREE = 11, NBARS = 12 };
+enum { B_KFULL = 0, B_KEMPTY = B_KFULL + KST, B_TFULL = B_KEMPTY + KST, B_TEMPTY = B_TFULL + TST,
+       B_XFULL = B_TEMPTY + TST, B_XEMPTY = B_XFULL + XST, B_SREADY = B_XEMPTY + XST, B_PREADY = B_SREADY + 2,
+       B_ACC_READY = B_PREADY + 2, B_ACC_FREE, B_A_READY, NBARS };
+static_assert(NBARS * 8 + 8 <= 512, "barrier area");
 
 constexpr uint32_t TM_STAGE = 128;   // TMEM columns per stage: den/R [0,64) | uv/D [64,128)
-constexpr uint32_t TM_ACC1 = 256;    // 32 columns
-constexpr uint32_t TM_ACC2 = 288;    // 32 columns
+constexpr uint32_t TM_ACC = 256;     // acc1 [256,288) | acc2 [288,320)
+constexpr uint32_t TM_A = 320;       // own-side operands: hi(e) lo(e) hi(E) lo(E), 32 columns each
 constexpr uint32_t TM_COLS = 512;
 
-struct TcMaps { CUtensorMap ownK, swK, swT, X; };
+struct TcMaps { CUtensorMap swK, swT, X; };
 
 struct TcArgs {
     long long own_total, sw_total;   // valid extents (cells / genes)
-    long long own_pad, sw_pad;       // padded extents (multiples of 128): q-th operand array starts at row q*pad
-    int n_own_tiles, n_chunks, tiles_per_chunk, n_sw_tiles;
+    long long sw_pad;                // padded sweep extent (multiple of 128): q-th operand array starts at row q*pad
+    int n_own_tiles, n_chunks, tiles_per_chunk, n_sw_tiles, n_items;
+    const float* own_e;              // [own_total x 32] exp(E log .) of the own side (raw factor array)
+    const float* own_E;              // [own_total x 32] E[.] of the own side
     const float* lp2w;               // [genes_pad] logit(pi) * log2(e); -inf: D_hat = (X>0)
     const float* flw;                // [genes_pad] floor (1e-10 where pi <= 0)
+    const int* any_floor;            // != 0 when some gene has a floor
     float* acc1;                     // [own_total x 32]  sum_sweep R  * S1
     float* acc2;                     // [own_total x 32]  sum_sweep D  * S2
     double* colsum;                  // gene pass: [genes] += sum_i D_hat
@@ -67,31 +84,57 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// tf32 round-to-nearest (ties away) for an operand the tensor core will truncate: one integer add
+__device__ __forceinline__ uint32_t tf32_bias(float x) { return __float_as_uint(x) + 0x1000u; }
 
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
-template <bool GENES, bool DROPOUT, bool ELBO>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// Walks the tiles of the work items of this CTA: item = chunk * n_own_tiles + own_tile (chunk-major, so that
+// the CTAs running at the same time sweep the same chunk and share its operands in L2).
+struct TileIter {
+    int item, t, t_begin, t_end, own0;
+    __device__ __forceinline__ void load(const TcArgs& a) {
+        if (item < a.n_items) {
+            const int chunk = item / a.n_own_tiles, own_tile = item - chunk * a.n_own_tiles;
+            own0 = own_tile * TC_OWN;
+            t_begin = chunk * a.tiles_per_chunk;
+            t_end = min(t_begin + a.tiles_per_chunk, a.n_sw_tiles);
+            t = t_begin;
+        }
+    }
+    __device__ __forceinline__ void init(const TcArgs& a) { item = blockIdx.x; load(a); }
+    __device__ __forceinline__ bool valid(const TcArgs& a) const { return item < a.n_items; }
+    __device__ __forceinline__ bool first() const { return t == t_begin; }
+    __device__ __forceinline__ bool last() const { return t == t_end - 1; }
+    __device__ __forceinline__ void next(const TcArgs& a) {
+        if (++t >= t_end) { item += gridDim.x; load(a); }
+    }
+};
+
+template <bool GENES, bool DROPOUT, bool ELBO, int NEW>
+__global__ void __launch_bounds__(64 + 32 * NEW, 1)
 k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
 {
+    constexpr int SLICES = NEW / 4;           // element-wise warps per TMEM lane quarter
+    constexpr int CW = TC_SW / SLICES;        // tile columns per element-wise warp
+    constexpr int NQ = DROPOUT ? 4 : 2;       // K-major operand arrays in use
+    constexpr int NT = DROPOUT ? 2 : 1;       // transposed operand arrays in use
+    constexpr bool GUARD_INLINE = GENES && ELBO;   // the log of the denominator is used: guard it per element
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = (uint64_t*)(smem + BAR_OFF);
+    uint64_t* bars = (uint64_t*)(smem + OFF_BAR);
     uint32_t* tmem_slot = (uint32_t*)(bars + NBARS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        mbar_init(&bars[B_RES_FULL], 1);
-        mbar_init(&bars[B_RES_EMPTY], 1);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&bars[B_FULL + s], 1);
-            mbar_init(&bars[B_EMPTY + s], 1 + TC_EW_WARPS);
-            mbar_init(&bars[B_SREADY + s], 1);
-            mbar_init(&bars[B_PREADY + s], TC_EW_WARPS);
-        }
+        for (int s = 0; s < KST; ++s) { mbar_init(&bars[B_KFULL + s], 1); mbar_init(&bars[B_KEMPTY + s], 1); }
+        for (int s = 0; s < TST; ++s) { mbar_init(&bars[B_TFULL + s], 1); mbar_init(&bars[B_TEMPTY + s], 1); }
+        for (int s = 0; s < XST; ++s) { mbar_init(&bars[B_XFULL + s], 1); mbar_init(&bars[B_XEMPTY + s], NEW); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars[B_SREADY + s], 1); mbar_init(&bars[B_PREADY + s], NEW); }
         mbar_init(&bars[B_ACC_READY], 1);
-        mbar_init(&bars[B_ACC_FREE], TC_EW_WARPS);
+        mbar_init(&bars[B_ACC_FREE], NEW);
+        mbar_init(&bars[B_A_READY], NEW);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TM_COLS);
@@ -99,49 +142,69 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const int n_items = a.n_own_tiles * a.n_chunks;
-    constexpr int NQ = DROPOUT ? 4 : 2;       // K-major operand arrays in use
-    constexpr int NT = DROPOUT ? 2 : 1;       // transposed operand arrays in use
 
     if (warp == 0) {
         // ============================================ TMA producer ============================================
         if (lane == 0) {
-            tma_prefetch_desc(&maps.ownK); tma_prefetch_desc(&maps.swK); tma_prefetch_desc(&maps.swT); tma_prefetch_desc(&maps.X);
-            uint32_t it = 0;
-            int li = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
-                const int own_tile = item / a.n_chunks, chunk = item % a.n_chunks;
-                const int own0 = own_tile * TC_OWN;
-                const int t_begin = chunk * a.tiles_per_chunk;
-                const int t_end = min(t_begin + a.tiles_per_chunk, a.n_sw_tiles);
-                mbar_wait(&bars[B_RES_EMPTY], (li & 1) ^ 1, 10);
-                mbar_expect_tx(&bars[B_RES_FULL], NQ * 16384);
-                for (int q = 0; q < NQ; ++q)
-                    tma_load_2d(smem + q * 16384, &maps.ownK, &bars[B_RES_FULL], 0, (int)(q * a.own_pad + own0));
-                for (int t = t_begin; t < t_end; ++t, ++it) {
-                    const int s = it & 1;
-                    const uint32_t ph = (it >> 1) & 1;
-                    mbar_wait(&bars[B_EMPTY + s], ph ^ 1, 11);
-                    uint8_t* st = smem + RES_BYTES + s * STAGE_BYTES;
-                    uint64_t* bar = &bars[B_FULL + s];
-                    const int sw0 = t * TC_SW;
-                    uint32_t bytes = NQ * 8192 + NT * 8192 + 32768;
-                    if (!GENES && DROPOUT) bytes += 512;
-                    mbar_expect_tx(bar, bytes);
-                    for (int q = 0; q < NQ; ++q)
-                        tma_load_2d(st + ST_K + q * 8192, &maps.swK, bar, 0, (int)(q * a.sw_pad + sw0));
-                    for (int q = 0; q < NT; ++q)
-                        for (int c = 0; c < 2; ++c)
-                            tma_load_2d(st + ST_T + q * 8192 + c * 4096, &maps.swT, bar, sw0 + 32 * c, q * 32);
-                    if (!GENES) {
-                        for (int c = 0; c < 2; ++c) tma_load_2d(st + ST_X + c * 16384, &maps.X, bar, sw0 + 32 * c, own0);
-                        if (DROPOUT) {
-                            bulk_load(smem + LP_OFF + s * 512, a.lp2w + sw0, 256, bar);
-                            bulk_load(smem + LP_OFF + s * 512 + 256, a.flw + sw0, 256, bar);
-                        }
-                    } else {
-                        for (int c = 0; c < 4; ++c) tma_load_2d(st + ST_X + c * 8192, &maps.X, bar, own0 + 32 * c, sw0);
+            tma_prefetch_desc(&maps.swK); tma_prefetch_desc(&maps.swT); tma_prefetch_desc(&maps.X);
+            TileIter ik, it_, ix;
+            ik.init(a); it_.init(a); ix.init(a);
+            uint32_t nk = 0, nt = 0, nx = 0;
+            long long t_idle = 0;
+            while (ik.valid(a) || it_.valid(a) || ix.valid(a)) {
+                bool progress = false;
+                if (ik.valid(a)) {
+                    const uint32_t s = nk % KST;
+                    if (mbar_test_wait(&bars[B_KEMPTY + s], ((nk / KST) & 1) ^ 1)) {
+                        uint8_t* st = smem + OFF_K + s * K_STAGE;
+                        uint64_t* bar = &bars[B_KFULL + s];
+                        const int sw0 = ik.t * TC_SW;
+                        mbar_expect_tx(bar, NQ * 8192);
+                        for (int q = 0; q < NQ; ++q)
+                            tma_load_2d(st + q * 8192, &maps.swK, bar, 0, (int)(q * a.sw_pad + sw0));
+                        ++nk; ik.next(a); progress = true;
                     }
+                }
+                if (ix.valid(a)) {
+                    const uint32_t s = nx % XST;
+                    if (mbar_test_wait(&bars[B_XEMPTY + s], ((nx / XST) & 1) ^ 1)) {
+                        uint8_t* st = smem + OFF_X + s * X_STAGE;
+                        uint64_t* bar = &bars[B_XFULL + s];
+                        const int sw0 = ix.t * TC_SW;
+                        mbar_expect_tx(bar, X_STAGE + ((!GENES && DROPOUT) ? LP_STAGE : 0));
+                        if (!GENES) {
+                            for (int c = 0; c < 2; ++c) tma_load_2d(st + c * 16384, &maps.X, bar, sw0 + 32 * c, ix.own0);
+                            if (DROPOUT) {
+                                bulk_load(smem + OFF_LP + s * LP_STAGE, a.lp2w + sw0, 256, bar);
+                                bulk_load(smem + OFF_LP + s * LP_STAGE + 256, a.flw + sw0, 256, bar);
+                            }
+                        } else {
+                            for (int c = 0; c < 4; ++c) tma_load_2d(st + c * 8192, &maps.X, bar, ix.own0 + 32 * c, sw0);
+                        }
+                        ++nx; ix.next(a); progress = true;
+                    }
+                }
+                if (it_.valid(a)) {
+                    const uint32_t s = nt % TST;
+                    if (mbar_test_wait(&bars[B_TEMPTY + s], ((nt / TST) & 1) ^ 1)) {
+                        uint8_t* st = smem + OFF_T + s * T_STAGE;
+                        uint64_t* bar = &bars[B_TFULL + s];
+                        const int sw0 = it_.t * TC_SW;
+                        mbar_expect_tx(bar, NT * 8192);
+                        for (int q = 0; q < NT; ++q)
+                            for (int c = 0; c < 2; ++c)
+                                tma_load_2d(st + q * 8192 + c * 4096, &maps.swT, bar, sw0 + 32 * c, q * 32);
+                        ++nt; it_.next(a); progress = true;
+                    }
+                }
+                if (progress) t_idle = 0;
+                else {
+                    if (t_idle == 0) t_idle = clock64();
+                    else if (clock64() - t_idle > ORI_MBAR_TIMEOUT_CYCLES) {
+                        printf("oriana_b200: producer timeout block=%d nk=%u nt=%u nx=%u\n", blockIdx.x, nk, nt, nx);
+                        __trap();
+                    }
+                    __nanosleep(32);
                 }
             }
         }
@@ -150,98 +213,153 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
         if (lane == 0) {
             constexpr uint32_t idescS = make_idesc_tf32(TC_OWN, TC_SW, false, false);
             constexpr uint32_t idescP = make_idesc_tf32(TC_OWN, TC_KP_CONST, false, false);
-            const uint32_t res = smem_u32(smem);
-            auto issue_P = [&](int s, uint32_t ph, bool first, bool last, int li) {
-                mbar_wait(&bars[B_PREADY + s], ph, 20);
+            const uint32_t sbase = smem_u32(smem);
+            auto issue_P = [&](uint32_t it, bool first, bool last, int li) {
+                const uint32_t s = it & 1, ts = it % TST;
+                mbar_wait(&bars[B_PREADY + s], (it >> 1) & 1, 20);
+                mbar_wait(&bars[B_TFULL + ts], (it / TST) & 1, 24);
                 if (first) mbar_wait(&bars[B_ACC_FREE], (li & 1) ^ 1, 21);
                 tc_fence_after();
-                const uint32_t st = res + RES_BYTES + s * STAGE_BYTES + ST_T;
+                const uint32_t st = sbase + OFF_T + ts * T_STAGE;
                 for (int ks = 0; ks < 8; ++ks)
-                    mma_tf32_ts(tmem + TM_ACC1, tmem + s * TM_STAGE + ks * 8,
+                    mma_tf32_ts(tmem + TM_ACC, tmem + s * TM_STAGE + ks * 8,
                                 make_smem_desc(st + (ks >> 2) * 4096 + (ks & 3) * 32, 16, 1024), idescP, !(first && ks == 0));
                 if (DROPOUT)
                     for (int ks = 0; ks < 8; ++ks)
-                        mma_tf32_ts(tmem + TM_ACC2, tmem + s * TM_STAGE + 64 + ks * 8,
+                        mma_tf32_ts(tmem + TM_ACC + 32, tmem + s * TM_STAGE + 64 + ks * 8,
                                     make_smem_desc(st + 8192 + (ks >> 2) * 4096 + (ks & 3) * 32, 16, 1024), idescP,
                                     !(first && ks == 0));
-                tc_commit(&bars[B_EMPTY + s]);
+                tc_commit(&bars[B_TEMPTY + ts]);
                 if (last) tc_commit(&bars[B_ACC_READY]);
             };
+            TileIter ti;
+            ti.init(a);
             uint32_t it = 0;
             int li = 0;
             bool have_prev = false, prev_first = false, prev_last = false;
-            int prev_s = 0, prev_li = 0;
-            uint32_t prev_ph = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
-                const int chunk = item % a.n_chunks;
-                const int t_begin = chunk * a.tiles_per_chunk;
-                const int t_end = min(t_begin + a.tiles_per_chunk, a.n_sw_tiles);
-                for (int t = t_begin; t < t_end; ++t, ++it) {
-                    const int s = it & 1;
-                    const uint32_t ph = (it >> 1) & 1;
-                    if (t == t_begin) mbar_wait(&bars[B_RES_FULL], li & 1, 22);
-                    mbar_wait(&bars[B_FULL + s], ph, 23);
-                    tc_fence_after();
-                    const uint32_t st = res + RES_BYTES + s * STAGE_BYTES + ST_K;
-                    // den (and uv) of this tile: three tf32 products per contraction
-                    auto chain = [&](uint32_t d, int qa, int qb, bool first) {
-                        for (int kk = 0; kk < 4; ++kk)
-                            mma_tf32_ss(d, make_smem_desc(res + qa * 16384 + kk * 32, 16, 1024),
-                                        make_smem_desc(st + qb * 8192 + kk * 32, 16, 1024), idescS, !(first && kk == 0));
-                    };
-                    chain(tmem + s * TM_STAGE, 0, 0, true);
-                    chain(tmem + s * TM_STAGE, 0, 1, false);
-                    chain(tmem + s * TM_STAGE, 1, 0, false);
-                    if (DROPOUT) {
-                        chain(tmem + s * TM_STAGE + 64, 2, 2, true);
-                        chain(tmem + s * TM_STAGE + 64, 2, 3, false);
-                        chain(tmem + s * TM_STAGE + 64, 3, 2, false);
-                    }
-                    tc_commit(&bars[B_SREADY + s]);
-                    if (t == t_end - 1) tc_commit(&bars[B_RES_EMPTY]);
-                    if (have_prev) issue_P(prev_s, prev_ph, prev_first, prev_last, prev_li);
-                    have_prev = true; prev_s = s; prev_ph = ph; prev_first = (t == t_begin); prev_last = (t == t_end - 1);
-                    prev_li = li;
+            int prev_li = 0;
+            while (ti.valid(a)) {
+                const uint32_t s = it & 1, ks_ = it % KST;
+                const bool first = ti.first(), last = ti.last();
+                mbar_wait(&bars[B_KFULL + ks_], (it / KST) & 1, 23);
+                if (first) mbar_wait(&bars[B_A_READY], li & 1, 22);
+                tc_fence_after();
+                const uint32_t st = sbase + OFF_K + ks_ * K_STAGE;
+                // den (and uv) of this tile: three tf32 products per contraction, A operand from TMEM
+                auto chain = [&](uint32_t d, int qa, int qb, bool fresh) {
+                    for (int kk = 0; kk < 4; ++kk)
+                        mma_tf32_ts(d, tmem + TM_A + qa * 32 + kk * 8,
+                                    make_smem_desc(st + qb * 8192 + kk * 32, 16, 1024), idescS, !(fresh && kk == 0));
+                };
+                chain(tmem + s * TM_STAGE, 0, 0, true);
+                chain(tmem + s * TM_STAGE, 0, 1, false);
+                chain(tmem + s * TM_STAGE, 1, 0, false);
+                if (DROPOUT) {
+                    chain(tmem + s * TM_STAGE + 64, 2, 2, true);
+                    chain(tmem + s * TM_STAGE + 64, 2, 3, false);
+                    chain(tmem + s * TM_STAGE + 64, 3, 2, false);
                 }
+                tc_commit(&bars[B_SREADY + s]);
+                tc_commit(&bars[B_KEMPTY + ks_]);
+                if (have_prev) issue_P(it - 1, prev_first, prev_last, prev_li);
+                have_prev = true; prev_first = first; prev_last = last; prev_li = li;
+                if (last) ++li;
+                ++it;
+                ti.next(a);
             }
-            if (have_prev) issue_P(prev_s, prev_ph, prev_first, prev_last, prev_li);
+            if (have_prev) issue_P(it - 1, prev_first, prev_last, prev_li);
         }
     } else {
         // ======================================= element-wise stage + epilogue =================================
         const int ew = warp - 2;
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
-        const int half = ew >> 2;                     // which 32 of the 64 tile columns
+        const int slice = ew >> 2;                    // which CW of the 64 tile columns
         const int lrow = quarter * 32 + lane;         // own index inside the tile = TMEM lane
         const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
+        const bool any_floor = DROPOUT && (*a.any_floor != 0);
+
+        // own-side operands of one work item -> TMEM (this warp's 32 lanes, its share of the 4 arrays)
+        constexpr int APW = (NQ + SLICES - 1) / SLICES;           // arrays per warp
+        float av[32];
+        auto a_fetch = [&](int own0) {                            // global -> registers
+            const int q0 = slice * APW;
+            if (q0 < NQ) {
+                const long long idx = (long long)own0 + lrow;
+                const float* src = ((q0 >> 1) ? a.own_E : a.own_e) + idx * 32;
+                if (idx < a.own_total) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + c);
+                        av[4 * c] = v.x; av[4 * c + 1] = v.y; av[4 * c + 2] = v.z; av[4 * c + 3] = v.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) av[c] = 0.f;
+                }
+            }
+        };
+        auto a_store = [&]() {                                    // registers -> TMEM (hi / lo split)
+            const int q0 = slice * APW;
+#pragma unroll
+            for (int j = 0; j < APW; ++j) {
+                const int q = q0 + j;
+                if (q < NQ) {
+                    // APW == 1: array q is hi (even q) or lo (odd q) of av; APW == 2: q0 even -> hi then lo
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t w[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const float v = av[16 * h + e];
+                            const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+                            w[e] = __float_as_uint((q & 1) ? v - hi : hi);
+                        }
+                        tmem_st16(tlane + TM_A + q * 32 + 16 * h, w);
+                    }
+                }
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[B_A_READY]);
+        };
+
+        TileIter ti;
+        ti.init(a);
         uint32_t it = 0;
         int li = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
-            const int own_tile = item / a.n_chunks, chunk = item % a.n_chunks;
-            const long long own_idx = (long long)own_tile * TC_OWN + lrow;
+        if (ti.valid(a)) { a_fetch(ti.own0); a_store(); }
+        while (ti.valid(a)) {
+            const long long own_idx = (long long)ti.own0 + lrow;
             const bool own_ok = own_idx < a.own_total;
-            const int t_begin = chunk * a.tiles_per_chunk;
-            const int t_end = min(t_begin + a.tiles_per_chunk, a.n_sw_tiles);
+            const int next_item = ti.item + gridDim.x;
+            const bool has_next = next_item < a.n_items;
+            const int next_own0 = (next_item % a.n_own_tiles) * TC_OWN;
             float lp2j = 0.f, flj = 0.f;
             if (GENES && DROPOUT) { lp2j = a.lp2w[own_idx]; flj = a.flw[own_idx]; }   // padded arrays: always in range
             float cs = 0.f;
             double acc_xl = 0.0, acc_ent = 0.0;
-            for (int t = t_begin; t < t_end; ++t, ++it) {
-                const int s = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                mbar_wait(&bars[B_FULL + s], ph, 30);      // X tile (and lp) visible to this thread
-                mbar_wait(&bars[B_SREADY + s], ph, 31);    // den / uv complete in TMEM
+            const int t_end = ti.t_end;
+            for (int t = ti.t_begin; t < t_end; ++t, ++it) {
+                const uint32_t s = it & 1, xs = it % XST;
+                const bool last = (t == t_end - 1);
+                if (last && has_next) a_fetch(next_own0);
+                mbar_wait(&bars[B_XFULL + xs], (it / XST) & 1, 30);      // X tile (and lp) visible to this thread
+                mbar_wait(&bars[B_SREADY + s], (it >> 1) & 1, 31);       // den / uv complete in TMEM
                 tc_fence_after();
-                const uint8_t* Xs = smem + RES_BYTES + s * STAGE_BYTES + ST_X;
-                const float* lps = (const float*)(smem + LP_OFF + s * 512);
+                if (last && has_next) a_store();    // every S of this item has completed: A can be replaced
+                const uint8_t* Xs = smem + OFF_X + xs * X_STAGE;
+                const float* lps = (const float*)(smem + OFF_LP + xs * LP_STAGE);
                 const int valid = (int)min((long long)TC_SW, a.sw_total - (long long)t * TC_SW);   // gene pass: real cells
+                const bool full = valid == TC_SW;
                 float t_xl = 0.f, t_ent = 0.f;
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const int c0 = half * 32 + g * 16;
+                for (int g = 0; g < CW / 16; ++g) {
+                    const int c0 = slice * CW + g * 16;
                     uint32_t den_r[16], uv_r[16];
                     tmem_ld16(tlane + s * TM_STAGE + c0, den_r);
                     if (DROPOUT) tmem_ld16(tlane + s * TM_STAGE + 64 + c0, uv_r);
-                    float x[16], lp2[16], fl[16];
+                    float x[16], lp2[16];
                     if (!GENES) {
                         const uint8_t* base = Xs + (c0 >> 5) * 16384 + lrow * 128;
                         const int cb = (c0 & 31) >> 2;
@@ -254,9 +372,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 const float4 l = *reinterpret_cast<const float4*>(lps + c0 + 4 * q);
-                                const float4 f = *reinterpret_cast<const float4*>(lps + 64 + c0 + 4 * q);
                                 lp2[4 * q] = l.x; lp2[4 * q + 1] = l.y; lp2[4 * q + 2] = l.z; lp2[4 * q + 3] = l.w;
-                                fl[4 * q] = f.x; fl[4 * q + 1] = f.y; fl[4 * q + 2] = f.z; fl[4 * q + 3] = f.w;
                             }
                         }
                     } else {
@@ -270,34 +386,75 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     }
                     tmem_wait_ld();
                     uint32_t R_r[16], D_r[16];
+                    float dmin = 1.f;
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
-                        const float den = __uint_as_float(den_r[e]);
+                        float den = __uint_as_float(den_r[e]);
                         const bool nz = x[e] != 0.f;
-                        const float dg = den > 0.f ? den : 1.f;                       // zigap.py:90
-                        float tt = dg, e2 = 0.f;
+                        if (GUARD_INLINE) den = den > 0.f ? den : 1.f;                // zigap.py:90
+                        else dmin = fminf(dmin, den);                                 // (fixed up below when it fires)
+                        float tt = den, e2 = 0.f;
                         if (DROPOUT) {
                             const float uv = __uint_as_float(uv_r[e]);
-                            e2 = fminf(fmaxf(fmaf(uv, LOG2E, -(GENES ? lp2j : lp2[e])), -126.f), 127.f);
-                            tt = nz ? dg : 1.f + ex2_approx(e2);
+                            e2 = fmaf(uv, LOG2E, -(GENES ? lp2j : lp2[e]));
+                            if (GENES && ELBO) e2 = fminf(e2, 127.f);
+                            const float tz = 1.f + ex2_approx(e2);
+                            tt = nz ? den : tz;
                         }
                         const float r = rcp_approx(tt);
-                        const float R = x[e] * r;                                     // 0 where X == 0
-                        R_r[e] = __float_as_uint(to_tf32_rna(R));
+                        R_r[e] = tf32_bias(x[e] * r);                                 // 0 where X == 0
                         if (DROPOUT) {
-                            const float D = fmaxf(nz ? 1.f : r, GENES ? flj : fl[e]);  // zigap.py:133-136
-                            D_r[e] = __float_as_uint(to_tf32_rna(D));
+                            float D = nz ? 1.f : r;                                   // zigap.py:131-136
                             if (GENES) {
-                                const bool live = (c0 + e) < valid;
-                                cs += live ? D : 0.f;
-                                if (ELBO && live) {
-                                    const float l2 = lg2_approx(tt);
-                                    t_xl = fmaf(x[e], l2, t_xl);
-                                    t_ent += (nz ? 0.f : l2) - (1.f - D) * e2;
+                                D = fmaxf(D, flj);                                    // zigap.py:133
+                                if (full) {
+                                    cs += D;
+                                    if (ELBO) {
+                                        const float l2 = lg2_approx(tt);
+                                        t_xl = fmaf(x[e], l2, t_xl);
+                                        t_ent += (nz ? 0.f : l2) - (1.f - D) * e2;
+                                    }
                                 }
                             }
-                        } else if (GENES && ELBO) {
-                            if ((c0 + e) < valid) t_xl = fmaf(x[e], lg2_approx(tt), t_xl);
+                            D_r[e] = tf32_bias(D);
+                        } else if (GENES && ELBO && full) {
+                            t_xl = fmaf(x[e], lg2_approx(tt), t_xl);
+                        }
+                    }
+                    // rare fix-ups, kept out of the hot loop ------------------------------------------------
+                    if (!GUARD_INLINE && dmin <= 0.f) {      // zigap.py:90: den <= 0 -> 1 (exp underflow, pad rows)
+#pragma unroll
+                        for (int e = 0; e < 16; ++e)
+                            if (__uint_as_float(den_r[e]) <= 0.f && x[e] != 0.f) R_r[e] = tf32_bias(x[e]);
+                    }
+                    if (!GENES && DROPOUT && any_floor) {    // zigap.py:133: genes with pi <= 0
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const float D = __uint_as_float(D_r[e] - 0x1000u);
+                            D_r[e] = tf32_bias(fmaxf(D, lps[64 + c0 + e]));
+                        }
+                    }
+                    if (GENES && !full) {                    // last tile of the sweep: only the real cells count
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            if ((c0 + e) < valid) {
+                                const bool nz = x[e] != 0.f;
+                                const float den = __uint_as_float(den_r[e]);
+                                if (DROPOUT) {
+                                    const float D = __uint_as_float(D_r[e] - 0x1000u);
+                                    cs += D;
+                                    if (ELBO) {
+                                        const float uv = __uint_as_float(uv_r[e]);
+                                        const float e2 = fminf(fmaf(uv, LOG2E, -lp2j), 127.f);
+                                        const float tt = nz ? (den > 0.f ? den : 1.f) : 1.f + ex2_approx(e2);
+                                        const float l2 = lg2_approx(tt);
+                                        t_xl = fmaf(x[e], l2, t_xl);
+                                        t_ent += (nz ? 0.f : l2) - (1.f - D) * e2;
+                                    }
+                                } else if (ELBO) {
+                                    t_xl = fmaf(x[e], lg2_approx(den > 0.f ? den : 1.f), t_xl);
+                                }
+                            }
                         }
                     }
                     tmem_st16(tlane + s * TM_STAGE + c0, R_r);
@@ -307,21 +464,22 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(&bars[B_PREADY + s]); mbar_arrive(&bars[B_EMPTY + s]); }
+                if (lane == 0) { mbar_arrive(&bars[B_PREADY + s]); mbar_arrive(&bars[B_XEMPTY + xs]); }
             }
-            // ---- epilogue of the work item: accumulators -> global (atomics: items of one own-tile may be split)
+            // ---- epilogue of the work item: accumulators -> global (atomics: the sweep of one own tile is split)
             mbar_wait(&bars[B_ACC_READY], li & 1, 32);
             tc_fence_after();
-            if (half == 0 || DROPOUT) {
-                float* out = (half == 0 ? a.acc1 : a.acc2) + own_idx * 32;
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
+            for (int g = 0; g < CW / 16; ++g) {
+                const int c0 = slice * CW + g * 16;          // column of [acc1 | acc2]
+                if (c0 < 32 || DROPOUT) {
                     uint32_t v[16];
-                    tmem_ld16(tlane + (half == 0 ? TM_ACC1 : TM_ACC2) + g * 16, v);
+                    tmem_ld16(tlane + TM_ACC + c0, v);
                     tmem_wait_ld();
                     if (own_ok) {
+                        float* out = (c0 < 32 ? a.acc1 + c0 : a.acc2 + (c0 - 32)) + own_idx * 32;
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) atomicAdd(out + g * 16 + e, __uint_as_float(v[e]));
+                        for (int e = 0; e < 16; ++e) atomicAdd(out + e, __uint_as_float(v[e]));
                     }
                 }
             }
@@ -343,6 +501,9 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     }
                 }
             }
+            ++li;
+            ti.item += gridDim.x;
+            ti.load(a);
         }
     }
     tc_fence_before();
@@ -387,12 +548,14 @@ k_tc_prep_T(const float* __restrict__ src, float* __restrict__ out, long long n,
     }
 }
 __global__ void k_tc_prep_lp(const float* __restrict__ lp, const float* __restrict__ fl, float* __restrict__ lp2w,
-                             float* __restrict__ flw, int p, int pad)
+                             float* __restrict__ flw, int* __restrict__ any_floor, int p, int pad)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= pad) return;
+    const float f = j < p ? fl[j] : 0.f;
     lp2w[j] = j < p ? lp[j] * LOG2E : -INFINITY;
-    flw[j] = j < p ? fl[j] : 0.f;
+    flw[j] = f;
+    if (f != 0.f) *any_floor = 1;
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
@@ -400,10 +563,10 @@ static long long pad128(long long v) { return (v + 127) / 128 * 128; }
 
 long long tc_workspace_floats(long long n_rows, int p) {
     const long long np = pad128(n_rows), pp = pad128(p);
-    return 4 * np * 32 + 2 * 32 * np + 4 * pp * 32 + 2 * 32 * pp + 2 * pp;
+    return 4 * np * 32 + 2 * 32 * np + 4 * pp * 32 + 2 * 32 * pp + 2 * pp + 32;
 }
 
-struct TcWs { float *rowK, *rowT, *geneK, *geneT, *lp2w, *flw; long long np, pp; };
+struct TcWs { float *rowK, *rowT, *geneK, *geneT, *lp2w, *flw; int* flags; long long np, pp; };
 static TcWs tc_carve(const ori_problem_t* P) {
     TcWs w;
     w.np = pad128(P->n_rows); w.pp = pad128(P->p);
@@ -413,7 +576,8 @@ static TcWs tc_carve(const ori_problem_t* P) {
     w.geneK = f; f += 4 * w.pp * 32;
     w.geneT = f; f += 2 * 32 * w.pp;
     w.lp2w = f; f += w.pp;
-    w.flw = f;
+    w.flw = f; f += w.pp;
+    w.flags = (int*)f;
     return w;
 }
 
@@ -428,94 +592,118 @@ static int num_sms() {
     return n;
 }
 
-// gene-side operands (+ padded logit(pi)); run once per iteration before the row pass
+// gene-side operands (+ padded logit(pi)): the sweep side of the row pass; run once per iteration before it
 int launch_tc_prep_genes(const ori_problem_t* P, cudaStream_t st) {
     const TcWs w = tc_carve(P);
     const bool drop = P->flags & ORI_F_DROPOUT;
     k_tc_prep_K<<<cdiv(w.pp * 32, 256), 256, 0, st>>>(P->eV, drop ? P->V_hat : nullptr, w.geneK, P->p, w.pp);
     k_tc_prep_T<<<cdiv(w.pp, 32), dim3(32, 8), 0, st>>>(P->eV, w.geneT, P->p, w.pp);
+    cudaMemsetAsync(w.flags, 0, 32 * sizeof(int), st);
     if (drop) {
         k_tc_prep_T<<<cdiv(w.pp, 32), dim3(32, 8), 0, st>>>(P->V_hat, w.geneT + 32 * w.pp, P->p, w.pp);
-        k_tc_prep_lp<<<cdiv(w.pp, 256), 256, 0, st>>>(P->lp, P->pfloor, w.lp2w, w.flw, P->p, (int)w.pp);
+        k_tc_prep_lp<<<cdiv(w.pp, 256), 256, 0, st>>>(P->lp, P->pfloor, w.lp2w, w.flw, w.flags, P->p, (int)w.pp);
     }
     return check_launch("k_tc_prep(genes)");
 }
-// row-side operands of generation g (before the row pass)
+// row-side operands, the sweep side of the gene pass: K-major hi/lo of generation g (the state that generated
+// D_hat), transposed Zj weight (eU, or eU * D_hat[:, :K] under the quirk) and transposed NEW U_hat
+// (zigap.py:124); run after the U update
 int launch_tc_prep_rows(const ori_problem_t* P, int g, cudaStream_t st) {
     const TcWs w = tc_carve(P);
     const bool drop = P->flags & ORI_F_DROPOUT;
     k_tc_prep_K<<<cdiv(w.np * 32, 256), 256, 0, st>>>(P->eU[g], drop ? P->U_hat[g] : nullptr, w.rowK, P->n_rows, w.np);
-    return check_launch("k_tc_prep(rows)");
-}
-// transposed row operands for the gene pass: the Zj weight (eU, or eU * D_hat[:, :K] under the quirk) and the
-// NEW U_hat (zigap.py:124); run after the U update
-int launch_tc_prep_rows_T(const ori_problem_t* P, int g, cudaStream_t st) {
-    const TcWs w = tc_carve(P);
-    const bool drop = P->flags & ORI_F_DROPOUT;
     const float* wsrc = (P->flags & ORI_F_QUIRK) ? P->eUw : P->eU[g];
     k_tc_prep_T<<<cdiv(w.np, 32), dim3(32, 8), 0, st>>>(wsrc, w.rowT, P->n_rows, w.np);
     if (drop) k_tc_prep_T<<<cdiv(w.np, 32), dim3(32, 8), 0, st>>>(P->U_hat[1 - g], w.rowT + 32 * w.np, P->n_rows, w.np);
-    return check_launch("k_tc_prep(rows, transposed)");
+    return check_launch("k_tc_prep(rows)");
+}
+
+static int ew_warps() {
+    static int n = 0;
+    if (!n) {
+        const char* e = getenv("ORI_TC_EW");
+        n = (e && atoi(e) == 8) ? 8 : 16;
+    }
+    return n;
+}
+
+// Split the sweep into chunks so that (a) there are many more work items than SMs, (b) the static round-robin
+// over the SMs wastes as little of the last round as possible, (c) the gene pass keeps <= 128 tiles per item
+// (fp32 running sums of the statistics).
+static void tc_partition(TcArgs& a, bool genes, int sms) {
+    const int max_tpc = genes ? 128 : 1 << 30;
+    int best_chunks = 1; double best_eff = -1.0;
+    for (int chunks = 1; chunks <= a.n_sw_tiles; ++chunks) {
+        const int tpc = cdiv(a.n_sw_tiles, chunks);
+        if (tpc > max_tpc) continue;
+        if (tpc < 16 && chunks > 1) break;
+        const int real_chunks = cdiv(a.n_sw_tiles, tpc);
+        const long long items = (long long)real_chunks * a.n_own_tiles;
+        const long long rounds = (items + sms - 1) / sms;
+        // efficiency of the static schedule, with a mild penalty per item for its prologue / epilogue
+        const double eff = (double)items / (double)(rounds * sms) * ((double)tpc / (tpc + 2.0));
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_chunks = chunks; }
+        if (items > 64LL * sms) break;
+    }
+    a.tiles_per_chunk = cdiv(a.n_sw_tiles, best_chunks);
+    a.n_chunks = cdiv(a.n_sw_tiles, a.tiles_per_chunk);
+    a.n_items = a.n_own_tiles * a.n_chunks;
 }
 
 template <bool GENES>
-static int launch_tc_pass(const ori_problem_t* P, cudaStream_t st) {
+static int launch_tc_pass(const ori_problem_t* P, int gen_old, cudaStream_t st) {
     const TcWs w = tc_carve(P);
     const bool drop = P->flags & ORI_F_DROPOUT, elbo = P->flags & ORI_F_ELBO;
     TcMaps maps;
     TcArgs a;
     bool ok;
     if (!GENES) {
-        ok = make_tmap_f32(&maps.ownK, w.rowK, 4 * w.np, 32, 32, 32, 128) &&
-             make_tmap_f32(&maps.swK, w.geneK, 4 * w.pp, 32, 32, 32, 64) &&
+        ok = make_tmap_f32(&maps.swK, w.geneK, 4 * w.pp, 32, 32, 32, 64) &&
              make_tmap_f32(&maps.swT, w.geneT, 64, w.pp, w.pp, 32, 32) &&
              make_tmap_f32(&maps.X, P->X, P->n_rows, P->p, P->ldx, 32, 128);
-        a.own_total = P->n_rows; a.sw_total = P->p; a.own_pad = w.np; a.sw_pad = w.pp;
+        a.own_total = P->n_rows; a.sw_total = P->p; a.sw_pad = w.pp;
+        a.own_e = P->eU[gen_old]; a.own_E = P->U_hat[gen_old];
         a.acc1 = P->Zi; a.acc2 = P->a2s;
     } else {
-        ok = make_tmap_f32(&maps.ownK, w.geneK, 4 * w.pp, 32, 32, 32, 128) &&
-             make_tmap_f32(&maps.swK, w.rowK, 4 * w.np, 32, 32, 32, 64) &&
+        ok = make_tmap_f32(&maps.swK, w.rowK, 4 * w.np, 32, 32, 32, 64) &&
              make_tmap_f32(&maps.swT, w.rowT, 64, w.np, w.np, 32, 32) &&
              make_tmap_f32(&maps.X, P->X, P->n_rows, P->p, P->ldx, 32, 64);
-        a.own_total = P->p; a.sw_total = P->n_rows; a.own_pad = w.pp; a.sw_pad = w.np;
+        a.own_total = P->p; a.sw_total = P->n_rows; a.sw_pad = w.np;
+        a.own_e = P->eV; a.own_E = P->V_hat;
         a.acc1 = P->red32; a.acc2 = P->red32 + (long long)P->p * 32;
     }
     if (!ok) return set_error(ORI_ECUDA, "cuTensorMapEncodeTiled failed");
-    a.lp2w = w.lp2w; a.flw = w.flw;
+    a.lp2w = w.lp2w; a.flw = w.flw; a.any_floor = w.flags;
     a.colsum = P->red64; a.part64 = P->red64 + P->p + 2 * P->KP;
     a.n_own_tiles = cdiv(a.own_total, TC_OWN);
     a.n_sw_tiles = cdiv(a.sw_total, TC_SW);
-    // split the sweep so that there are enough work items for every SM (and bounded fp32 running sums)
     const int sms = num_sms();
-    int chunks = 1;
-    while ((long long)a.n_own_tiles * chunks < 4LL * sms && a.n_sw_tiles / (chunks * 2) >= 8) chunks *= 2;
-    int tpc = cdiv(a.n_sw_tiles, chunks);
-    if (GENES && tpc > 128) tpc = 128;          // gene pass: <= 8192 cells per item (fp32 running sums of the stats)
-    a.tiles_per_chunk = tpc;
-    a.n_chunks = cdiv(a.n_sw_tiles, tpc);
-    const int n_items = a.n_own_tiles * a.n_chunks;
-    const int grid = n_items < sms ? n_items : sms;
+    tc_partition(a, GENES, sms);
+    const int grid = a.n_items < sms ? a.n_items : sms;
+    const int nw = ew_warps();
 
-#define ORI_TC_LAUNCH(D, E)                                                                                     \
+#define ORI_TC_LAUNCH(D, E, NW)                                                                                 \
     do {                                                                                                        \
-        auto kern = k_tc_pass<GENES, D, E>;                                                                     \
+        auto kern = k_tc_pass<GENES, D, E, NW>;                                                                 \
         static bool attr_done = false;                                                                          \
         if (!attr_done) {                                                                                       \
             cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES); \
             if (e_ != cudaSuccess) return set_error(ORI_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e_)); \
             attr_done = true;                                                                                   \
         }                                                                                                       \
-        kern<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, a);                                                 \
+        kern<<<grid, 64 + 32 * NW, TC_SMEM_BYTES, st>>>(maps, a);                                               \
     } while (0)
-    if (drop && elbo) ORI_TC_LAUNCH(true, true);
-    else if (drop) ORI_TC_LAUNCH(true, false);
-    else if (elbo) ORI_TC_LAUNCH(false, true);
-    else ORI_TC_LAUNCH(false, false);
+#define ORI_TC_LAUNCH_NW(D, E) do { if (nw == 8) ORI_TC_LAUNCH(D, E, 8); else ORI_TC_LAUNCH(D, E, 16); } while (0)
+    if (drop && elbo) ORI_TC_LAUNCH_NW(true, true);
+    else if (drop) ORI_TC_LAUNCH_NW(true, false);
+    else if (elbo) ORI_TC_LAUNCH_NW(false, true);
+    else ORI_TC_LAUNCH_NW(false, false);
+#undef ORI_TC_LAUNCH_NW
 #undef ORI_TC_LAUNCH
     return check_launch(GENES ? "k_tc_pass(genes)" : "k_tc_pass(rows)");
 }
 
-int launch_pass_rows_tc(const ori_problem_t* P, cudaStream_t st) { return launch_tc_pass<false>(P, st); }
-int launch_pass_genes_tc(const ori_problem_t* P, cudaStream_t st) { return launch_tc_pass<true>(P, st); }
+int launch_pass_rows_tc(const ori_problem_t* P, int gen_old, cudaStream_t st) { return launch_tc_pass<false>(P, gen_old, st); }
+int launch_pass_genes_tc(const ori_problem_t* P, int gen_old, cudaStream_t st) { return launch_tc_pass<true>(P, gen_old, st); }
 
 }  // namespace ori

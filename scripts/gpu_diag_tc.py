@@ -45,7 +45,7 @@ if which in ('all', 'time'):
     from oriana.singlecell import synth_counts_device
     for (n, p, K) in ((10_000, 2_000, 10), (100_000, 20_000, 20), (250_000, 20_000, 32)):
         X = synth_counts_device(n, p, K, seed=1)
-        for tensor in (True, False):
+        for tensor in ((True,) if 'tconly' in sys.argv else (True, False)):
             np.random.seed(0)
             m = ZIGaP(X[:, :p], k=K, use_factors=False, tensor=tensor)
             for _ in range(2): m.step()

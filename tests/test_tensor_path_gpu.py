@@ -1,0 +1,113 @@
+"""GPU: the tcgen05/TMA tensor path (csrc/kernels_tc.cu) of the two X-streaming passes against
+
+  * the golden trajectories recorded from the UNMODIFIED reference (compat_quirk=True, zigap.py:94),
+  * the oracle port for the de-quirked update and the ELBO,
+  * the CUDA-core path of the same library at sizes where work items, chunks and ring wrap-around all occur.
+
+Stated tolerances of the tensor path.  den = eU.eV^T and U_hat.V_hat^T are 3xTF32 (fp32-grade); the two
+accumulating contractions R.eV, D.V_hat (and their transposes) take R, D and the factor operand rounded to
+TF32 (11-bit significand, round to nearest), so a sum of m terms carries a relative error of about
+2^-12 / sqrt(m) * few:
+  parameters a1,a2,b1,b2 : 3e-3 relative (floor 1e-6*max) on the 100 x 500 fixtures, 1e-3 at 3000 x 1500
+  alpha, beta, pi        : 3e-4
+  D_hat                  : 1e-3 absolute
+  ELBO                   : 1e-4 relative (north_star's bound)
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, golden_state, load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+FACTORS = ('a1', 'a2', 'b1', 'b2')
+HYPER = ('alpha1', 'alpha2', 'beta1', 'beta2')
+
+
+def make_model(s, quirk, **kw):
+    from oriana.models import GaP, ZIGaP
+    from oriana.singlecell import CountMatrix
+    cls = ZIGaP if ('p_d' in s or 'pi_d' in s) else GaP
+    K = s['a1'].shape[1]
+    return cls(CountMatrix(s['X']), k=K, use_factors=False, state=s, compat_quirk=quirk, **kw)
+
+
+@pytest.mark.parametrize('name', GOLDEN_CASES)
+def test_tensor_trajectory_matches_reference(cuda_lib, name):
+    g = load_golden(name)
+    s = golden_state(g, 0)
+    m = make_model(s, quirk=True, tensor=True)
+    assert m.uses_tensor_path
+    steps = [int(t) for t in g['steps'] if int(t) <= 10]
+    for t in range(1, max(steps) + 1):
+        m.step()
+        if t in steps:
+            r = golden_state(g, t)
+            for k in FACTORS:
+                e = relerr(getattr(m, k).asarray(), r[k])
+                assert e < 3e-3, (name, t, k, e)
+            for k in HYPER + (('pi_d',) if 'pi_d' in s else ()):
+                e = relerr(getattr(m, k).asarray(), r[k])
+                assert e < 3e-4, (name, t, k, e)
+            if 'p_d' in s:
+                assert np.max(np.abs(m.D_hat - r['p_d'])) < 1e-3, (name, t)
+
+
+@pytest.mark.parametrize('name', ['zigap_ragged', 'gap_ragged', 'zigap_k10'])
+def test_tensor_dequirked_update_and_elbo_match_oracle(cuda_lib, name):
+    from oracle import cavi_numpy as cn
+    g = load_golden(name)
+    s = golden_state(g, 0)
+    m = make_model(s, quirk=False, tensor=True)
+    ref = {k: v.copy() for k, v in s.items()}
+    want = [cn.elbo(ref, guard32=True)]
+    for t in range(1, 7):
+        m.step()
+        cn.step(ref, quirk=False)
+        want.append(cn.elbo(ref))
+    for k in FACTORS:
+        assert relerr(getattr(m, k).asarray(), ref[k]) < 3e-3, k
+    for k in HYPER + (('pi_d',) if 'pi_d' in s else ()):
+        assert relerr(getattr(m, k).asarray(), ref[k]) < 3e-4, k
+    got = m.elbo_trace
+    assert np.max(np.abs(got - np.asarray(want)) / np.abs(want)) < 1e-4, (got, want)
+
+
+@pytest.mark.parametrize('shape', [(3000, 1500, 10), (5000, 2100, 32), (1111, 777, 5), (20000, 4500, 20)])
+def test_tensor_path_matches_cuda_core_path(cuda_lib, shape):
+    """Many work items per SM, split sweeps, ragged last tiles on both axes, every ring wrapping around."""
+    from oriana.models import GaP, ZIGaP
+    from oriana.singlecell import synth_counts_device
+    n, p, K = shape
+    X = synth_counts_device(n, p, K, seed=5)
+    for cls in (ZIGaP, GaP):
+        np.random.seed(3)
+        m0 = cls(X[:, :p], k=K, use_factors=False, tensor=False)
+        st = m0.state_dict(); st['X'] = X[:, :p]
+        ms = cls(X[:, :p], k=K, use_factors=False, state=st, tensor=False)
+        mt = cls(X[:, :p], k=K, use_factors=False, state=st, tensor=True)
+        assert mt.uses_tensor_path and not ms.uses_tensor_path
+        for t in range(3):
+            mt.step(); ms.step()
+        for k in FACTORS:
+            assert relerr(getattr(mt, k).asarray(), getattr(ms, k).asarray()) < 1e-3, (cls.__name__, k)
+        for k in HYPER + (('pi_d',) if cls is ZIGaP else ()):
+            assert relerr(getattr(mt, k).asarray(), getattr(ms, k).asarray()) < 1e-4, (cls.__name__, k)
+        et, es = mt.elbo_trace, ms.elbo_trace
+        assert np.max(np.abs(et - es) / np.abs(es)) < 1e-4, (et, es)
+
+
+def test_tensor_all_zero_gene_and_cell(cuda_lib):
+    """Columns with pi = 0 take the 1e-10 override (zigap.py:133) on the tensor path too."""
+    from oracle import cavi_numpy as cn
+    X = cn.synth_counts(150, 70, 3, seed=2)
+    X[:, 5] = 0; X[:, 64] = 0; X[17, :] = 0
+    s = cn.init_state(X, 3, np.random.default_rng(0), 'zigap')
+    m = make_model(s, quirk=False, tensor=True)
+    ref = {k: v.copy() for k, v in s.items()}
+    for _ in range(4):
+        m.step(); cn.step(ref, quirk=False)
+    for k in FACTORS + HYPER + ('pi_d',):
+        got = getattr(m, k).asarray()
+        assert np.isfinite(got).all()
+        assert relerr(got, ref[k]) < 3e-3, k
+    assert abs(m.pi_d[5] - ref['pi_d'][5]) < 1e-12 and m.pi_d[5] < 1e-9

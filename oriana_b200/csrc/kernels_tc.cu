@@ -145,130 +145,156 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
 
     if (warp == 0) {
         // ============================================ TMA producer ============================================
-        if (lane == 0) {
-            tma_prefetch_desc(&maps.swK); tma_prefetch_desc(&maps.swT); tma_prefetch_desc(&maps.X);
-            TileIter ik, it_, ix;
-            ik.init(a); it_.init(a); ix.init(a);
-            uint32_t nk = 0, nt = 0, nx = 0;
-            long long t_idle = 0;
-            while (ik.valid(a) || it_.valid(a) || ix.valid(a)) {
-                bool progress = false;
-                if (ik.valid(a)) {
-                    const uint32_t s = nk % KST;
-                    if (mbar_test_wait(&bars[B_KEMPTY + s], ((nk / KST) & 1) ^ 1)) {
+        // The whole warp walks the rings (warp-uniform control flow keeps every TMA operand in uniform
+        // registers); one elected lane issues.
+        if (elect_one()) { tma_prefetch_desc(&maps.swK); tma_prefetch_desc(&maps.swT); tma_prefetch_desc(&maps.X); }
+        TileIter ik, it_, ix;
+        ik.init(a); it_.init(a); ix.init(a);
+        uint32_t nk = 0, nt = 0, nx = 0;
+        long long t_idle = 0;
+        while (ik.valid(a) || it_.valid(a) || ix.valid(a)) {
+            bool progress = false;
+            if (ik.valid(a)) {
+                const uint32_t s = nk % KST;
+                if (__all_sync(0xffffffffu, mbar_test_wait(&bars[B_KEMPTY + s], ((nk / KST) & 1) ^ 1))) {
+                    if (elect_one()) {
                         uint8_t* st = smem + OFF_K + s * K_STAGE;
                         uint64_t* bar = &bars[B_KFULL + s];
                         const int sw0 = ik.t * TC_SW;
                         mbar_expect_tx(bar, NQ * 8192);
+#pragma unroll
                         for (int q = 0; q < NQ; ++q)
                             tma_load_2d(st + q * 8192, &maps.swK, bar, 0, (int)(q * a.sw_pad + sw0));
-                        ++nk; ik.next(a); progress = true;
                     }
+                    __syncwarp();
+                    ++nk; ik.next(a); progress = true;
                 }
-                if (ix.valid(a)) {
-                    const uint32_t s = nx % XST;
-                    if (mbar_test_wait(&bars[B_XEMPTY + s], ((nx / XST) & 1) ^ 1)) {
+            }
+            if (ix.valid(a)) {
+                const uint32_t s = nx % XST;
+                if (__all_sync(0xffffffffu, mbar_test_wait(&bars[B_XEMPTY + s], ((nx / XST) & 1) ^ 1))) {
+                    if (elect_one()) {
                         uint8_t* st = smem + OFF_X + s * X_STAGE;
                         uint64_t* bar = &bars[B_XFULL + s];
                         const int sw0 = ix.t * TC_SW;
                         mbar_expect_tx(bar, X_STAGE + ((!GENES && DROPOUT) ? LP_STAGE : 0));
                         if (!GENES) {
+#pragma unroll
                             for (int c = 0; c < 2; ++c) tma_load_2d(st + c * 16384, &maps.X, bar, sw0 + 32 * c, ix.own0);
                             if (DROPOUT) {
                                 bulk_load(smem + OFF_LP + s * LP_STAGE, a.lp2w + sw0, 256, bar);
                                 bulk_load(smem + OFF_LP + s * LP_STAGE + 256, a.flw + sw0, 256, bar);
                             }
                         } else {
+#pragma unroll
                             for (int c = 0; c < 4; ++c) tma_load_2d(st + c * 8192, &maps.X, bar, ix.own0 + 32 * c, sw0);
                         }
-                        ++nx; ix.next(a); progress = true;
                     }
+                    __syncwarp();
+                    ++nx; ix.next(a); progress = true;
                 }
-                if (it_.valid(a)) {
-                    const uint32_t s = nt % TST;
-                    if (mbar_test_wait(&bars[B_TEMPTY + s], ((nt / TST) & 1) ^ 1)) {
+            }
+            if (it_.valid(a)) {
+                const uint32_t s = nt % TST;
+                if (__all_sync(0xffffffffu, mbar_test_wait(&bars[B_TEMPTY + s], ((nt / TST) & 1) ^ 1))) {
+                    if (elect_one()) {
                         uint8_t* st = smem + OFF_T + s * T_STAGE;
                         uint64_t* bar = &bars[B_TFULL + s];
                         const int sw0 = it_.t * TC_SW;
                         mbar_expect_tx(bar, NT * 8192);
+#pragma unroll
                         for (int q = 0; q < NT; ++q)
+#pragma unroll
                             for (int c = 0; c < 2; ++c)
                                 tma_load_2d(st + q * 8192 + c * 4096, &maps.swT, bar, sw0 + 32 * c, q * 32);
-                        ++nt; it_.next(a); progress = true;
                     }
+                    __syncwarp();
+                    ++nt; it_.next(a); progress = true;
                 }
-                if (progress) t_idle = 0;
-                else {
-                    if (t_idle == 0) t_idle = clock64();
-                    else if (clock64() - t_idle > ORI_MBAR_TIMEOUT_CYCLES) {
-                        printf("oriana_b200: producer timeout block=%d nk=%u nt=%u nx=%u\n", blockIdx.x, nk, nt, nx);
-                        __trap();
-                    }
-                    __nanosleep(32);
+            }
+            if (progress) t_idle = 0;
+            else {
+                if (t_idle == 0) t_idle = clock64();
+                else if (clock64() - t_idle > ORI_MBAR_TIMEOUT_CYCLES) {
+                    if (lane == 0) printf("oriana_b200: producer timeout block=%d nk=%u nt=%u nx=%u\n", blockIdx.x, nk, nt, nx);
+                    __trap();
                 }
+                __nanosleep(20);
             }
         }
     } else if (warp == 1) {
         // ============================================ MMA issuer ===============================================
-        if (lane == 0) {
-            constexpr uint32_t idescS = make_idesc_tf32(TC_OWN, TC_SW, false, false);
-            constexpr uint32_t idescP = make_idesc_tf32(TC_OWN, TC_KP_CONST, false, false);
-            const uint32_t sbase = smem_u32(smem);
-            auto issue_P = [&](uint32_t it, bool first, bool last, int li) {
-                const uint32_t s = it & 1, ts = it % TST;
-                mbar_wait(&bars[B_PREADY + s], (it >> 1) & 1, 20);
-                mbar_wait(&bars[B_TFULL + ts], (it / TST) & 1, 24);
-                if (first) mbar_wait(&bars[B_ACC_FREE], (li & 1) ^ 1, 21);
-                tc_fence_after();
-                const uint32_t st = sbase + OFF_T + ts * T_STAGE;
+        // Warp-uniform control flow, one elected lane issues: descriptors and TMEM addresses stay in uniform
+        // registers (a divergent single-lane loop makes the compiler wrap every tcgen05.mma in a
+        // register->uniform-register broadcast loop, which throttles the issue rate).
+        constexpr uint32_t idescS = make_idesc_tf32(TC_OWN, TC_SW, false, false);
+        constexpr uint32_t idescP = make_idesc_tf32(TC_OWN, TC_KP_CONST, false, false);
+        const uint32_t sbase = smem_u32(smem);
+        const uint64_t kdesc0 = make_smem_desc(sbase + OFF_K, 16, 1024);
+        const uint64_t tdesc0 = make_smem_desc(sbase + OFF_T, 16, 1024);
+        auto issue_P = [&](uint32_t it, bool first, bool last, int li) {
+            const uint32_t s = it & 1, ts = it % TST;
+            mbar_wait(&bars[B_PREADY + s], (it >> 1) & 1, 20);
+            mbar_wait(&bars[B_TFULL + ts], (it / TST) & 1, 24);
+            if (first) mbar_wait(&bars[B_ACC_FREE], (li & 1) ^ 1, 21);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t td = tdesc0 + (uint64_t)((ts * T_STAGE) >> 4);
+#pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
                     mma_tf32_ts(tmem + TM_ACC, tmem + s * TM_STAGE + ks * 8,
-                                make_smem_desc(st + (ks >> 2) * 4096 + (ks & 3) * 32, 16, 1024), idescP, !(first && ks == 0));
-                if (DROPOUT)
+                                td + (uint64_t)(((ks >> 2) * 4096 + (ks & 3) * 32) >> 4), idescP, !(first && ks == 0));
+                if (DROPOUT) {
+#pragma unroll
                     for (int ks = 0; ks < 8; ++ks)
                         mma_tf32_ts(tmem + TM_ACC + 32, tmem + s * TM_STAGE + 64 + ks * 8,
-                                    make_smem_desc(st + 8192 + (ks >> 2) * 4096 + (ks & 3) * 32, 16, 1024), idescP,
+                                    td + (uint64_t)((8192 + (ks >> 2) * 4096 + (ks & 3) * 32) >> 4), idescP,
                                     !(first && ks == 0));
+                }
                 tc_commit(&bars[B_TEMPTY + ts]);
                 if (last) tc_commit(&bars[B_ACC_READY]);
-            };
-            TileIter ti;
-            ti.init(a);
-            uint32_t it = 0;
-            int li = 0;
-            bool have_prev = false, prev_first = false, prev_last = false;
-            int prev_li = 0;
-            while (ti.valid(a)) {
-                const uint32_t s = it & 1, ks_ = it % KST;
-                const bool first = ti.first(), last = ti.last();
-                mbar_wait(&bars[B_KFULL + ks_], (it / KST) & 1, 23);
-                if (first) mbar_wait(&bars[B_A_READY], li & 1, 22);
-                tc_fence_after();
-                const uint32_t st = sbase + OFF_K + ks_ * K_STAGE;
+            }
+            __syncwarp();
+        };
+        TileIter ti;
+        ti.init(a);
+        uint32_t it = 0;
+        int li = 0;
+        bool have_prev = false, prev_first = false, prev_last = false;
+        int prev_li = 0;
+        while (ti.valid(a)) {
+            const uint32_t s = it & 1, ks_ = it % KST;
+            const bool first = ti.first(), last = ti.last();
+            mbar_wait(&bars[B_KFULL + ks_], (it / KST) & 1, 23);
+            if (first) mbar_wait(&bars[B_A_READY], li & 1, 22);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t kd = kdesc0 + (uint64_t)((ks_ * K_STAGE) >> 4);
                 // den (and uv) of this tile: three tf32 products per contraction, A operand from TMEM
-                auto chain = [&](uint32_t d, int qa, int qb, bool fresh) {
-                    for (int kk = 0; kk < 4; ++kk)
-                        mma_tf32_ts(d, tmem + TM_A + qa * 32 + kk * 8,
-                                    make_smem_desc(st + qb * 8192 + kk * 32, 16, 1024), idescS, !(fresh && kk == 0));
-                };
-                chain(tmem + s * TM_STAGE, 0, 0, true);
-                chain(tmem + s * TM_STAGE, 0, 1, false);
-                chain(tmem + s * TM_STAGE, 1, 0, false);
+#define ORI_CHAIN(D_, QA, QB, FRESH)                                                                          \
+                _Pragma("unroll") for (int kk = 0; kk < 4; ++kk)                                              \
+                    mma_tf32_ts((D_), tmem + TM_A + (QA) * 32 + kk * 8,                                       \
+                                kd + (uint64_t)(((QB) * 8192 + kk * 32) >> 4), idescS, !((FRESH) && kk == 0))
+                ORI_CHAIN(tmem + s * TM_STAGE, 0, 0, true);
+                ORI_CHAIN(tmem + s * TM_STAGE, 0, 1, false);
+                ORI_CHAIN(tmem + s * TM_STAGE, 1, 0, false);
                 if (DROPOUT) {
-                    chain(tmem + s * TM_STAGE + 64, 2, 2, true);
-                    chain(tmem + s * TM_STAGE + 64, 2, 3, false);
-                    chain(tmem + s * TM_STAGE + 64, 3, 2, false);
+                    ORI_CHAIN(tmem + s * TM_STAGE + 64, 2, 2, true);
+                    ORI_CHAIN(tmem + s * TM_STAGE + 64, 2, 3, false);
+                    ORI_CHAIN(tmem + s * TM_STAGE + 64, 3, 2, false);
                 }
+#undef ORI_CHAIN
                 tc_commit(&bars[B_SREADY + s]);
                 tc_commit(&bars[B_KEMPTY + ks_]);
-                if (have_prev) issue_P(it - 1, prev_first, prev_last, prev_li);
-                have_prev = true; prev_first = first; prev_last = last; prev_li = li;
-                if (last) ++li;
-                ++it;
-                ti.next(a);
             }
+            __syncwarp();
             if (have_prev) issue_P(it - 1, prev_first, prev_last, prev_li);
+            have_prev = true; prev_first = first; prev_last = last; prev_li = li;
+            if (last) ++li;
+            ++it;
+            ti.next(a);
         }
+        if (have_prev) issue_P(it - 1, prev_first, prev_last, prev_li);
     } else {
         // ======================================= element-wise stage + epilogue =================================
         const int ew = warp - 2;
@@ -622,7 +648,7 @@ static int ew_warps() {
     static int n = 0;
     if (!n) {
         const char* e = getenv("ORI_TC_EW");
-        n = (e && atoi(e) == 8) ? 8 : 16;
+        n = (e && atoi(e) == 16) ? 16 : 8;
     }
     return n;
 }

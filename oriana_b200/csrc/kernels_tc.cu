@@ -32,6 +32,19 @@
 namespace ori {
 using namespace tc;
 
+#ifndef ORI_TC_PREFETCH_TM
+#define ORI_TC_PREFETCH_TM 1      // issue the next group's TMEM loads before computing the current group
+#endif
+#ifndef ORI_TC_BATCH
+#define ORI_TC_BATCH 0            // 1: load every group of the tile first, then compute them as one batch
+#endif
+#ifndef ORI_TC_AFETCH_EARLY
+#define ORI_TC_AFETCH_EARLY 0     // 1: fetch the next work item's own-side rows before the last tile's barrier waits (32 live registers)
+#endif
+#ifndef ORI_TC_PREFETCH_X
+#define ORI_TC_PREFETCH_X 0       // same for its X values (costs 16 registers)
+#endif
+
 constexpr int TC_OWN = 128;
 constexpr int TC_SW = 64;
 constexpr int TC_KP_CONST = 32;     // latent dimension of the tensor path (K <= 32, zero padded)
@@ -42,7 +55,7 @@ constexpr int XST = 3;
 constexpr uint32_t K_STAGE = 32768;   // 4 K-major arrays [64 x 32]: hi(e) lo(e) hi(E) lo(E)
 constexpr uint32_t T_STAGE = 16384;   // 2 transposed arrays x 2 chunks [32 x 32]
 constexpr uint32_t X_STAGE = 32768;   // X tile
-constexpr uint32_t LP_STAGE = 512;    // lp2[64] | floor[64]
+constexpr uint32_t LP_STAGE = 768;    // lp2[64] | floor[64] | (1-pi)/pi [64]
 constexpr uint32_t OFF_K = 0;
 constexpr uint32_t OFF_T = OFF_K + KST * K_STAGE;
 constexpr uint32_t OFF_X = OFF_T + TST * T_STAGE;
@@ -70,6 +83,7 @@ struct TcArgs {
     const float* own_E;              // [own_total x 32] E[.] of the own side
     const float* lp2w;               // [genes_pad] logit(pi) * log2(e); -inf: D_hat = (X>0)
     const float* flw;                // [genes_pad] floor (1e-10 where pi <= 0)
+    const float* cw;                 // [genes_pad] exp(-logit(pi)) = (1 - pi) / pi
     const int* any_floor;            // != 0 when some gene has a floor
     float* acc1;                     // [own_total x 32]  sum_sweep R  * S1
     float* acc2;                     // [own_total x 32]  sum_sweep D  * S2
@@ -86,6 +100,42 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 }
 // tf32 round-to-nearest (ties away) for an operand the tensor core will truncate: one integer add
 __device__ __forceinline__ uint32_t tf32_bias(float x) { return __float_as_uint(x) + 0x1000u; }
+
+// ld.shared on explicit shared-window addresses (the aligned dynamic-smem pointer has lost its address space)
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+// x != 0 ? a : b, twice with differently spelled tests: each predicate dies at its select, so sixteen of them
+// never have to be parked in a bit mask across the MUFU latency
+__device__ __forceinline__ float sel_nz_a(float x, float a, float b) {
+    float d;
+    asm("{\n\t.reg .pred q;\n\tsetp.neu.f32 q, %1, 0f00000000;\n\tselp.f32 %0, %2, %3, q;\n\t}" : "=f"(d) : "f"(x), "f"(a), "f"(b));
+    return d;
+}
+__device__ __forceinline__ float sel_nz_b(float x, float a, float b) {
+    float d;
+    asm("{\n\t.reg .pred q;\n\t.reg .f32 t;\n\tabs.f32 t, %1;\n\tsetp.gtu.f32 q, t, 0f00000000;\n\tselp.f32 %0, %2, %3, q;\n\t}"
+        : "=f"(d) : "f"(x), "f"(a), "f"(b));
+    return d;
+}
+__device__ __forceinline__ float sel_pos(float w, float a) {   // w > 0 ? a : 0
+    float d;
+    asm("{\n\t.reg .pred q;\n\tsetp.gt.f32 q, %1, 0f00000000;\n\tselp.f32 %0, %2, 0f00000000, q;\n\t}" : "=f"(d) : "f"(w), "f"(a));
+    return d;
+}
+__device__ __forceinline__ void kahan_add(float& s, float& c, float v) {
+    const float y = v - c;
+    const float u = s + y;
+    c = (u - s) - y;
+    s = u;
+}
 
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
@@ -148,80 +198,71 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
         // The whole warp walks the rings (warp-uniform control flow keeps every TMA operand in uniform
         // registers); one elected lane issues.
         if (elect_one()) { tma_prefetch_desc(&maps.swK); tma_prefetch_desc(&maps.swT); tma_prefetch_desc(&maps.X); }
-        TileIter ik, it_, ix;
-        ik.init(a); it_.init(a); ix.init(a);
-        uint32_t nk = 0, nt = 0, nx = 0;
-        long long t_idle = 0;
-        while (ik.valid(a) || it_.valid(a) || ix.valid(a)) {
-            bool progress = false;
-            if (ik.valid(a)) {
+        // Issue order K(j), X(j), T(j-1): the order in which the stages are released in steady state (the K stage
+        // when S(j-2) has run, the X stage when the element-wise warps are done with tile j-3, the T stage when
+        // P(j-3) has run), so the blocking waits below never hold back a load whose stage is already free.
+        TileIter ik, it_;
+        ik.init(a); it_.init(a);
+        uint32_t nk = 0, nt = 0;
+        auto load_T = [&]() {
+            const uint32_t s = nt % TST;
+            mbar_wait(&bars[B_TEMPTY + s], ((nt / TST) & 1) ^ 1, 12);
+            if (elect_one()) {
+                uint8_t* st = smem + OFF_T + s * T_STAGE;
+                uint64_t* bar = &bars[B_TFULL + s];
+                const int sw0 = it_.t * TC_SW;
+                mbar_expect_tx(bar, NT * 8192);
+#pragma unroll
+                for (int q = 0; q < NT; ++q)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        tma_load_2d(st + q * 8192 + c * 4096, &maps.swT, bar, sw0 + 32 * c, q * 32);
+            }
+            __syncwarp();
+            ++nt; it_.next(a);
+        };
+        while (ik.valid(a)) {
+            {
                 const uint32_t s = nk % KST;
-                if (__all_sync(0xffffffffu, mbar_test_wait(&bars[B_KEMPTY + s], ((nk / KST) & 1) ^ 1))) {
-                    if (elect_one()) {
-                        uint8_t* st = smem + OFF_K + s * K_STAGE;
-                        uint64_t* bar = &bars[B_KFULL + s];
-                        const int sw0 = ik.t * TC_SW;
-                        mbar_expect_tx(bar, NQ * 8192);
+                mbar_wait(&bars[B_KEMPTY + s], ((nk / KST) & 1) ^ 1, 10);
+                if (elect_one()) {
+                    uint8_t* st = smem + OFF_K + s * K_STAGE;
+                    uint64_t* bar = &bars[B_KFULL + s];
+                    const int sw0 = ik.t * TC_SW;
+                    mbar_expect_tx(bar, NQ * 8192);
 #pragma unroll
-                        for (int q = 0; q < NQ; ++q)
-                            tma_load_2d(st + q * 8192, &maps.swK, bar, 0, (int)(q * a.sw_pad + sw0));
-                    }
-                    __syncwarp();
-                    ++nk; ik.next(a); progress = true;
+                    for (int q = 0; q < NQ; ++q)
+                        tma_load_2d(st + q * 8192, &maps.swK, bar, 0, (int)(q * a.sw_pad + sw0));
                 }
+                __syncwarp();
             }
-            if (ix.valid(a)) {
-                const uint32_t s = nx % XST;
-                if (__all_sync(0xffffffffu, mbar_test_wait(&bars[B_XEMPTY + s], ((nx / XST) & 1) ^ 1))) {
-                    if (elect_one()) {
-                        uint8_t* st = smem + OFF_X + s * X_STAGE;
-                        uint64_t* bar = &bars[B_XFULL + s];
-                        const int sw0 = ix.t * TC_SW;
-                        mbar_expect_tx(bar, X_STAGE + ((!GENES && DROPOUT) ? LP_STAGE : 0));
-                        if (!GENES) {
+            {
+                const uint32_t s = nk % XST;
+                mbar_wait(&bars[B_XEMPTY + s], ((nk / XST) & 1) ^ 1, 11);
+                if (elect_one()) {
+                    uint8_t* st = smem + OFF_X + s * X_STAGE;
+                    uint64_t* bar = &bars[B_XFULL + s];
+                    const int sw0 = ik.t * TC_SW;
+                    mbar_expect_tx(bar, X_STAGE + ((!GENES && DROPOUT) ? 768 : 0));
+                    if (!GENES) {
 #pragma unroll
-                            for (int c = 0; c < 2; ++c) tma_load_2d(st + c * 16384, &maps.X, bar, sw0 + 32 * c, ix.own0);
-                            if (DROPOUT) {
-                                bulk_load(smem + OFF_LP + s * LP_STAGE, a.lp2w + sw0, 256, bar);
-                                bulk_load(smem + OFF_LP + s * LP_STAGE + 256, a.flw + sw0, 256, bar);
-                            }
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) tma_load_2d(st + c * 8192, &maps.X, bar, ix.own0 + 32 * c, sw0);
+                        for (int c = 0; c < 2; ++c) tma_load_2d(st + c * 16384, &maps.X, bar, sw0 + 32 * c, ik.own0);
+                        if (DROPOUT) {
+                            bulk_load(smem + OFF_LP + s * LP_STAGE, a.lp2w + sw0, 256, bar);
+                            bulk_load(smem + OFF_LP + s * LP_STAGE + 256, a.flw + sw0, 256, bar);
+                            bulk_load(smem + OFF_LP + s * LP_STAGE + 512, a.cw + sw0, 256, bar);
                         }
-                    }
-                    __syncwarp();
-                    ++nx; ix.next(a); progress = true;
-                }
-            }
-            if (it_.valid(a)) {
-                const uint32_t s = nt % TST;
-                if (__all_sync(0xffffffffu, mbar_test_wait(&bars[B_TEMPTY + s], ((nt / TST) & 1) ^ 1))) {
-                    if (elect_one()) {
-                        uint8_t* st = smem + OFF_T + s * T_STAGE;
-                        uint64_t* bar = &bars[B_TFULL + s];
-                        const int sw0 = it_.t * TC_SW;
-                        mbar_expect_tx(bar, NT * 8192);
+                    } else {
 #pragma unroll
-                        for (int q = 0; q < NT; ++q)
-#pragma unroll
-                            for (int c = 0; c < 2; ++c)
-                                tma_load_2d(st + q * 8192 + c * 4096, &maps.swT, bar, sw0 + 32 * c, q * 32);
+                        for (int c = 0; c < 4; ++c) tma_load_2d(st + c * 8192, &maps.X, bar, ik.own0 + 32 * c, sw0);
                     }
-                    __syncwarp();
-                    ++nt; it_.next(a); progress = true;
                 }
+                __syncwarp();
             }
-            if (progress) t_idle = 0;
-            else {
-                if (t_idle == 0) t_idle = clock64();
-                else if (clock64() - t_idle > ORI_MBAR_TIMEOUT_CYCLES) {
-                    if (lane == 0) printf("oriana_b200: producer timeout block=%d nk=%u nt=%u nx=%u\n", blockIdx.x, nk, nt, nx);
-                    __trap();
-                }
-                __nanosleep(20);
-            }
+            if (nk > 0) load_T();
+            ++nk; ik.next(a);
         }
+        if (nk > 0) load_T();
     } else if (warp == 1) {
         // ============================================ MMA issuer ===============================================
         // Warp-uniform control flow, one elected lane issues: descriptors and TMEM addresses stay in uniform
@@ -336,7 +377,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                         uint32_t w[16];
 #pragma unroll
                         for (int e = 0; e < 16; ++e) {
-                            const float v = av[16 * h + e];
+                            const float v = (GENES && q >= 2) ? av[16 * h + e] * LOG2E : av[16 * h + e];   // uv in log2 units
                             const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
                             w[e] = __float_as_uint((q & 1) ? v - hi : hi);
                         }
@@ -350,6 +391,13 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             if (lane == 0) mbar_arrive(&bars[B_A_READY]);
         };
 
+        const uint32_t sbase = smem_u32(smem);
+        constexpr int G = CW / 16;                    // groups of 16 columns per tile for this warp
+        // gene pass: X is staged [cell][gene]; lane (gene) reads one float per cell, 128-byte swizzle undone here
+        uint32_t xoff[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xoff[k] = (uint32_t)(quarter * 8192 + ((((lane >> 2) ^ k)) << 4) + (lane & 3) * 4);
+
         TileIter ti;
         ti.init(a);
         uint32_t it = 0;
@@ -361,137 +409,205 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             const int next_item = ti.item + gridDim.x;
             const bool has_next = next_item < a.n_items;
             const int next_own0 = (next_item % a.n_own_tiles) * TC_OWN;
-            float lp2j = 0.f, flj = 0.f;
-            if (GENES && DROPOUT) { lp2j = a.lp2w[own_idx]; flj = a.flw[own_idx]; }   // padded arrays: always in range
+            float lp2j = 0.f, flj = 0.f, cj = 0.f;
+            if (GENES && DROPOUT) {                   // padded arrays: always in range
+                lp2j = a.lp2w[own_idx]; flj = a.flw[own_idx];
+                cj = ex2_approx(-lp2j);               // (1 - pi) / pi
+            }
+            // genes / columns with a floor (pi <= 0, zigap.py:133) take the general path
+            const bool slow_item = DROPOUT && (GENES ? (__any_sync(0xffffffffu, flj != 0.f) != 0) : any_floor);
             float cs = 0.f;
-            double acc_xl = 0.0, acc_ent = 0.0;
+            float xl_s = 0.f, xl_c = 0.f, ent_s = 0.f, ent_c = 0.f;     // compensated fp32 sums over the item
             const int t_end = ti.t_end;
             for (int t = ti.t_begin; t < t_end; ++t, ++it) {
                 const uint32_t s = it & 1, xs = it % XST;
                 const bool last = (t == t_end - 1);
-                if (last && has_next) a_fetch(next_own0);
+                if (ORI_TC_AFETCH_EARLY && last && has_next) a_fetch(next_own0);
                 mbar_wait(&bars[B_XFULL + xs], (it / XST) & 1, 30);      // X tile (and lp) visible to this thread
                 mbar_wait(&bars[B_SREADY + s], (it >> 1) & 1, 31);       // den / uv complete in TMEM
                 tc_fence_after();
-                if (last && has_next) a_store();    // every S of this item has completed: A can be replaced
-                const uint8_t* Xs = smem + OFF_X + xs * X_STAGE;
-                const float* lps = (const float*)(smem + OFF_LP + xs * LP_STAGE);
+                if (last && has_next) {             // every S of this item has completed: A can be replaced
+                    if (!ORI_TC_AFETCH_EARLY) a_fetch(next_own0);
+                    a_store();
+                }
+                const uint32_t xs_addr = sbase + OFF_X + xs * X_STAGE;
+                const uint32_t lp_addr = sbase + OFF_LP + xs * LP_STAGE;
                 const int valid = (int)min((long long)TC_SW, a.sw_total - (long long)t * TC_SW);   // gene pass: real cells
-                const bool full = valid == TC_SW;
+                const bool slow_tile = slow_item || (GENES && valid != TC_SW);
+                const uint32_t tden = tlane + s * TM_STAGE, tuv = tden + 64;
                 float t_xl = 0.f, t_ent = 0.f;
-#pragma unroll
-                for (int g = 0; g < CW / 16; ++g) {
+
+                uint32_t dr[G][16], ur[G][16];
+                float x[G][16];
+                auto load_x = [&](int g) {
                     const int c0 = slice * CW + g * 16;
-                    uint32_t den_r[16], uv_r[16];
-                    tmem_ld16(tlane + s * TM_STAGE + c0, den_r);
-                    if (DROPOUT) tmem_ld16(tlane + s * TM_STAGE + 64 + c0, uv_r);
-                    float x[16], lp2[16];
                     if (!GENES) {
-                        const uint8_t* base = Xs + (c0 >> 5) * 16384 + lrow * 128;
+                        const uint32_t base = xs_addr + (c0 >> 5) * 16384 + lrow * 128;
                         const int cb = (c0 & 31) >> 2;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float4 v = *reinterpret_cast<const float4*>(base + (((cb + q) ^ (lrow & 7)) << 4));
-                            x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
-                        }
-                        if (DROPOUT) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float4 l = *reinterpret_cast<const float4*>(lps + c0 + 4 * q);
-                                lp2[4 * q] = l.x; lp2[4 * q + 1] = l.y; lp2[4 * q + 2] = l.z; lp2[4 * q + 3] = l.w;
-                            }
+                            const float4 v = lds128(base + (((cb + q) ^ (lrow & 7)) << 4));
+                            x[g][4 * q] = v.x; x[g][4 * q + 1] = v.y; x[g][4 * q + 2] = v.z; x[g][4 * q + 3] = v.w;
                         }
                     } else {
-                        const uint8_t* base = Xs + quarter * 8192 + (lane & 3) * 4;
-                        const int jc = lane >> 2;
 #pragma unroll
                         for (int e = 0; e < 16; ++e) {
                             const int i = c0 + e;
-                            x[e] = *reinterpret_cast<const float*>(base + i * 128 + ((jc ^ (i & 7)) << 4));
+                            x[g][e] = lds32(xs_addr + xoff[i & 7] + i * 128);
                         }
                     }
+                };
+                // general path: den guard, floors, ragged last tile (zigap.py:90, :133); rare
+                auto slow_group = [&](int g) {
+                    const int c0 = slice * CW + g * 16;
+                    tmem_ld16(tden + c0, dr[g]);
+                    if (DROPOUT) tmem_ld16(tuv + c0, ur[g]);
                     tmem_wait_ld();
-                    uint32_t R_r[16], D_r[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const float den = __uint_as_float(dr[g][e]);
+                        const float xe = x[g][e];
+                        const bool nz = xe != 0.f;
+                        const float dg = den > 0.f ? den : 1.f;
+                        float tt = dg, e2 = 0.f, D = 1.f;
+                        if (DROPOUT) {
+                            const float lp2 = GENES ? lp2j : lds32(lp_addr + 4 * (c0 + e));
+                            const float fl = GENES ? flj : lds32(lp_addr + 256 + 4 * (c0 + e));
+                            e2 = fminf(__uint_as_float(ur[g][e]) - lp2, 127.f);
+                            tt = nz ? dg : 1.f + ex2_approx(e2);
+                            const float r = rcp_approx(tt);
+                            D = fmaxf(nz ? 1.f : r, fl);
+                            dr[g][e] = tf32_bias(xe * r);
+                            ur[g][e] = tf32_bias(D);
+                        } else {
+                            dr[g][e] = tf32_bias(xe * rcp_approx(tt));
+                        }
+                        if (GENES && (c0 + e) < valid) {
+                            if (DROPOUT) cs += D;
+                            if (ELBO) {
+                                const float l2 = lg2_approx(tt);
+                                t_xl = fmaf(xe, l2, t_xl);
+                                if (DROPOUT) t_ent += (nz ? 0.f : l2) - (1.f - D) * e2;
+                            }
+                        }
+                    }
+                };
+                // lean path: full tile, no floors; returns the smallest denominator seen
+                auto fast_group = [&](int g) -> float {
+                    const int c0 = slice * CW + g * 16;
+                    float cc[16];
+                    if (DROPOUT && !GENES) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 v = lds128(lp_addr + 512 + 4 * (c0 + 4 * q));
+                            cc[4 * q] = v.x; cc[4 * q + 1] = v.y; cc[4 * q + 2] = v.z; cc[4 * q + 3] = v.w;
+                        }
+                    }
                     float dmin = 1.f;
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
-                        float den = __uint_as_float(den_r[e]);
-                        const bool nz = x[e] != 0.f;
+                        float den = __uint_as_float(dr[g][e]);
+                        const float xe = x[g][e];
                         if (GUARD_INLINE) den = den > 0.f ? den : 1.f;                // zigap.py:90
-                        else dmin = fminf(dmin, den);                                 // (fixed up below when it fires)
-                        float tt = den, e2 = 0.f;
+                        else dmin = fminf(dmin, den);                                 // (general path when it fires)
+                        float tt = den, uvp = 0.f;
                         if (DROPOUT) {
-                            const float uv = __uint_as_float(uv_r[e]);
-                            e2 = fmaf(uv, LOG2E, -(GENES ? lp2j : lp2[e]));
-                            if (GENES && ELBO) e2 = fminf(e2, 127.f);
-                            const float tz = 1.f + ex2_approx(e2);
-                            tt = nz ? den : tz;
+                            uvp = __uint_as_float(ur[g][e]);                          // U_hat.V_hat * log2(e)
+                            float tz = fmaf(ex2_approx(uvp), GENES ? cj : cc[e], 1.f);   // 1 + exp(uv - logit pi)
+                            if (GENES && ELBO) tz = fminf(tz, 1.7014118e38f);
+                            tt = sel_nz_a(xe, den, tz);
                         }
                         const float r = rcp_approx(tt);
-                        R_r[e] = tf32_bias(x[e] * r);                                 // 0 where X == 0
+                        dr[g][e] = tf32_bias(xe * r);                                 // R = X / den; 0 where X == 0
+                        float D = 1.f;
                         if (DROPOUT) {
-                            float D = nz ? 1.f : r;                                   // zigap.py:131-136
-                            if (GENES) {
-                                D = fmaxf(D, flj);                                    // zigap.py:133
-                                if (full) {
-                                    cs += D;
-                                    if (ELBO) {
-                                        const float l2 = lg2_approx(tt);
-                                        t_xl = fmaf(x[e], l2, t_xl);
-                                        t_ent += (nz ? 0.f : l2) - (1.f - D) * e2;
-                                    }
-                                }
-                            }
-                            D_r[e] = tf32_bias(D);
-                        } else if (GENES && ELBO && full) {
-                            t_xl = fmaf(x[e], lg2_approx(tt), t_xl);
+                            D = sel_nz_b(xe, 1.f, r);                                 // zigap.py:131-136
+                            ur[g][e] = tf32_bias(D);
                         }
-                    }
-                    // rare fix-ups, kept out of the hot loop ------------------------------------------------
-                    if (!GUARD_INLINE && dmin <= 0.f) {      // zigap.py:90: den <= 0 -> 1 (exp underflow, pad rows)
-#pragma unroll
-                        for (int e = 0; e < 16; ++e)
-                            if (__uint_as_float(den_r[e]) <= 0.f && x[e] != 0.f) R_r[e] = tf32_bias(x[e]);
-                    }
-                    if (!GENES && DROPOUT && any_floor) {    // zigap.py:133: genes with pi <= 0
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            const float D = __uint_as_float(D_r[e] - 0x1000u);
-                            D_r[e] = tf32_bias(fmaxf(D, lps[64 + c0 + e]));
-                        }
-                    }
-                    if (GENES && !full) {                    // last tile of the sweep: only the real cells count
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            if ((c0 + e) < valid) {
-                                const bool nz = x[e] != 0.f;
-                                const float den = __uint_as_float(den_r[e]);
+                        if (GENES) {
+                            if (DROPOUT) cs += D;
+                            if (ELBO) {
+                                const float l2 = lg2_approx(tt);
+                                t_xl = fmaf(xe, l2, t_xl);
                                 if (DROPOUT) {
-                                    const float D = __uint_as_float(D_r[e] - 0x1000u);
-                                    cs += D;
-                                    if (ELBO) {
-                                        const float uv = __uint_as_float(uv_r[e]);
-                                        const float e2 = fminf(fmaf(uv, LOG2E, -lp2j), 127.f);
-                                        const float tt = nz ? (den > 0.f ? den : 1.f) : 1.f + ex2_approx(e2);
-                                        const float l2 = lg2_approx(tt);
-                                        t_xl = fmaf(x[e], l2, t_xl);
-                                        t_ent += (nz ? 0.f : l2) - (1.f - D) * e2;
-                                    }
-                                } else if (ELBO) {
-                                    t_xl = fmaf(x[e], lg2_approx(den > 0.f ? den : 1.f), t_xl);
+                                    const float e2 = fminf(uvp - lp2j, 127.f);
+                                    const float w = 1.f - D;                          // 0 on non-zeros
+                                    t_ent += sel_pos(w, l2);
+                                    t_ent = fmaf(-w, e2, t_ent);
                                 }
                             }
                         }
                     }
-                    tmem_st16(tlane + s * TM_STAGE + c0, R_r);
-                    if (DROPOUT) tmem_st16(tlane + s * TM_STAGE + 64 + c0, D_r);
+                    return dmin;
+                };
+
+#if ORI_TC_BATCH
+                // all groups of the tile in one batch: one load phase, one long run of independent chains
+                if (!slow_tile) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        tmem_ld16(tden + slice * CW + 16 * g, dr[g]);
+                        if (DROPOUT) tmem_ld16(tuv + slice * CW + 16 * g, ur[g]);
+                    }
                 }
-                if (GENES && ELBO) { acc_xl += (double)t_xl; acc_ent += (double)t_ent; }
+#pragma unroll
+                for (int g = 0; g < G; ++g) load_x(g);
+                if (!slow_tile) tmem_wait_ld();
+                bool redo[G];
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    redo[g] = slow_tile;
+                    if (!slow_tile) {
+                        const float dmin = fast_group(g);
+                        if (!GUARD_INLINE) redo[g] = __any_sync(0xffffffffu, dmin <= 0.f) != 0;
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const int c0 = slice * CW + g * 16;
+                    if (redo[g]) slow_group(g);
+                    tmem_st16(tden + c0, dr[g]);
+                    if (DROPOUT) tmem_st16(tuv + c0, ur[g]);
+                }
+#else
+                if (!slow_tile) {
+                    tmem_ld16(tden + slice * CW, dr[0]);
+                    if (DROPOUT) tmem_ld16(tuv + slice * CW, ur[0]);
+                }
+                load_x(0);
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const int c0 = slice * CW + g * 16;
+                    bool redo = slow_tile;
+                    if (!ORI_TC_PREFETCH_TM && !slow_tile && g > 0) {
+                        tmem_ld16(tden + c0, dr[g]);
+                        if (DROPOUT) tmem_ld16(tuv + c0, ur[g]);
+                    }
+                    if (!ORI_TC_PREFETCH_X && g > 0) load_x(g);
+                    if (!slow_tile) {
+                        tmem_wait_ld();
+                        if (ORI_TC_PREFETCH_TM && g + 1 < G) {            // next group's loads fly during this one
+                            tmem_ld16(tden + c0 + 16, dr[g + 1]);
+                            if (DROPOUT) tmem_ld16(tuv + c0 + 16, ur[g + 1]);
+                        }
+                    }
+                    if (ORI_TC_PREFETCH_X && g + 1 < G) load_x(g + 1);
+                    if (!slow_tile) {
+                        const float dmin = fast_group(g);
+                        if (!GUARD_INLINE) redo = __any_sync(0xffffffffu, dmin <= 0.f) != 0;
+                    }
+                    if (redo) slow_group(g);
+                    tmem_st16(tden + c0, dr[g]);
+                    if (DROPOUT) tmem_st16(tuv + c0, ur[g]);
+                }
+#endif
+                if (GENES && ELBO) { kahan_add(xl_s, xl_c, t_xl); if (DROPOUT) kahan_add(ent_s, ent_c, t_ent); }
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&bars[B_PREADY + s]); mbar_arrive(&bars[B_XEMPTY + xs]); }
             }
+            double acc_xl = (double)xl_s - (double)xl_c, acc_ent = (double)ent_s - (double)ent_c;
             // ---- epilogue of the work item: accumulators -> global (atomics: the sweep of one own tile is split)
             mbar_wait(&bars[B_ACC_READY], li & 1, 32);
             tc_fence_after();
@@ -541,7 +657,8 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
 // K-major operand arrays: out[q][pad][32], q = 0: hi(e) 1: lo(e) 2: hi(E) 3: lo(E); hi = tf32 round-to-nearest
 // (the tensor core truncates fp32 operands to tf32: scripts/tc_probe.cu T4), lo = x - hi.  Pad rows are zero.
 __global__ void __launch_bounds__(256)
-k_tc_prep_K(const float* __restrict__ e, const float* __restrict__ E, float* __restrict__ out, long long n, long long pad)
+k_tc_prep_K(const float* __restrict__ e, const float* __restrict__ E, float Escale, float* __restrict__ out, long long n,
+            long long pad)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= pad * 32) return;
@@ -551,7 +668,7 @@ k_tc_prep_K(const float* __restrict__ e, const float* __restrict__ E, float* __r
     out[idx] = hv;
     out[pad * 32 + idx] = v - hv;
     if (E) {
-        const float w = ok ? E[idx] : 0.f;
+        const float w = ok ? E[idx] * Escale : 0.f;
         const float hw = to_tf32_rna(w);
         out[2 * pad * 32 + idx] = hw;
         out[3 * pad * 32 + idx] = w - hw;
@@ -574,13 +691,15 @@ k_tc_prep_T(const float* __restrict__ src, float* __restrict__ out, long long n,
     }
 }
 __global__ void k_tc_prep_lp(const float* __restrict__ lp, const float* __restrict__ fl, float* __restrict__ lp2w,
-                             float* __restrict__ flw, int* __restrict__ any_floor, int p, int pad)
+                             float* __restrict__ flw, float* __restrict__ cw, int* __restrict__ any_floor, int p, int pad)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= pad) return;
     const float f = j < p ? fl[j] : 0.f;
-    lp2w[j] = j < p ? lp[j] * LOG2E : -INFINITY;
+    const float l2 = j < p ? lp[j] * LOG2E : -INFINITY;
+    lp2w[j] = l2;
     flw[j] = f;
+    cw[j] = exp2f(-l2);
     if (f != 0.f) *any_floor = 1;
 }
 
@@ -589,10 +708,10 @@ static long long pad128(long long v) { return (v + 127) / 128 * 128; }
 
 long long tc_workspace_floats(long long n_rows, int p) {
     const long long np = pad128(n_rows), pp = pad128(p);
-    return 4 * np * 32 + 2 * 32 * np + 4 * pp * 32 + 2 * 32 * pp + 2 * pp + 32;
+    return 4 * np * 32 + 2 * 32 * np + 4 * pp * 32 + 2 * 32 * pp + 3 * pp + 32;
 }
 
-struct TcWs { float *rowK, *rowT, *geneK, *geneT, *lp2w, *flw; int* flags; long long np, pp; };
+struct TcWs { float *rowK, *rowT, *geneK, *geneT, *lp2w, *flw, *cw; int* flags; long long np, pp; };
 static TcWs tc_carve(const ori_problem_t* P) {
     TcWs w;
     w.np = pad128(P->n_rows); w.pp = pad128(P->p);
@@ -603,6 +722,7 @@ static TcWs tc_carve(const ori_problem_t* P) {
     w.geneT = f; f += 2 * 32 * w.pp;
     w.lp2w = f; f += w.pp;
     w.flw = f; f += w.pp;
+    w.cw = f; f += w.pp;
     w.flags = (int*)f;
     return w;
 }
@@ -622,12 +742,12 @@ static int num_sms() {
 int launch_tc_prep_genes(const ori_problem_t* P, cudaStream_t st) {
     const TcWs w = tc_carve(P);
     const bool drop = P->flags & ORI_F_DROPOUT;
-    k_tc_prep_K<<<cdiv(w.pp * 32, 256), 256, 0, st>>>(P->eV, drop ? P->V_hat : nullptr, w.geneK, P->p, w.pp);
+    k_tc_prep_K<<<cdiv(w.pp * 32, 256), 256, 0, st>>>(P->eV, drop ? P->V_hat : nullptr, LOG2E, w.geneK, P->p, w.pp);
     k_tc_prep_T<<<cdiv(w.pp, 32), dim3(32, 8), 0, st>>>(P->eV, w.geneT, P->p, w.pp);
     cudaMemsetAsync(w.flags, 0, 32 * sizeof(int), st);
     if (drop) {
         k_tc_prep_T<<<cdiv(w.pp, 32), dim3(32, 8), 0, st>>>(P->V_hat, w.geneT + 32 * w.pp, P->p, w.pp);
-        k_tc_prep_lp<<<cdiv(w.pp, 256), 256, 0, st>>>(P->lp, P->pfloor, w.lp2w, w.flw, w.flags, P->p, (int)w.pp);
+        k_tc_prep_lp<<<cdiv(w.pp, 256), 256, 0, st>>>(P->lp, P->pfloor, w.lp2w, w.flw, w.cw, w.flags, P->p, (int)w.pp);
     }
     return check_launch("k_tc_prep(genes)");
 }
@@ -637,7 +757,7 @@ int launch_tc_prep_genes(const ori_problem_t* P, cudaStream_t st) {
 int launch_tc_prep_rows(const ori_problem_t* P, int g, cudaStream_t st) {
     const TcWs w = tc_carve(P);
     const bool drop = P->flags & ORI_F_DROPOUT;
-    k_tc_prep_K<<<cdiv(w.np * 32, 256), 256, 0, st>>>(P->eU[g], drop ? P->U_hat[g] : nullptr, w.rowK, P->n_rows, w.np);
+    k_tc_prep_K<<<cdiv(w.np * 32, 256), 256, 0, st>>>(P->eU[g], drop ? P->U_hat[g] : nullptr, 1.f, w.rowK, P->n_rows, w.np);
     const float* wsrc = (P->flags & ORI_F_QUIRK) ? P->eUw : P->eU[g];
     k_tc_prep_T<<<cdiv(w.np, 32), dim3(32, 8), 0, st>>>(wsrc, w.rowT, P->n_rows, w.np);
     if (drop) k_tc_prep_T<<<cdiv(w.np, 32), dim3(32, 8), 0, st>>>(P->U_hat[1 - g], w.rowT + 32 * w.np, P->n_rows, w.np);
@@ -699,7 +819,7 @@ static int launch_tc_pass(const ori_problem_t* P, int gen_old, cudaStream_t st) 
         a.acc1 = P->red32; a.acc2 = P->red32 + (long long)P->p * 32;
     }
     if (!ok) return set_error(ORI_ECUDA, "cuTensorMapEncodeTiled failed");
-    a.lp2w = w.lp2w; a.flw = w.flw; a.any_floor = w.flags;
+    a.lp2w = w.lp2w; a.flw = w.flw; a.cw = w.cw; a.any_floor = w.flags;
     a.colsum = P->red64; a.part64 = P->red64 + P->p + 2 * P->KP;
     a.n_own_tiles = cdiv(a.own_total, TC_OWN);
     a.n_sw_tiles = cdiv(a.sw_total, TC_SW);

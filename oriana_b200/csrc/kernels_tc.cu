@@ -170,7 +170,6 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
     constexpr int CW = TC_SW / SLICES;        // tile columns per element-wise warp
     constexpr int NQ = DROPOUT ? 4 : 2;       // K-major operand arrays in use
     constexpr int NT = DROPOUT ? 2 : 1;       // transposed operand arrays in use
-    constexpr bool GUARD_INLINE = GENES && ELBO;   // the log of the denominator is used: guard it per element
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + OFF_BAR);
@@ -400,7 +399,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
 
         TileIter ti;
         ti.init(a);
-        uint32_t it = 0;
+        uint32_t s = 0, sph = 0, xs = 0, xph = 0;     // TMEM stage / X ring stage of the current tile and their phases
         int li = 0;
         if (ti.valid(a)) { a_fetch(ti.own0); a_store(); }
         while (ti.valid(a)) {
@@ -419,12 +418,11 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             float cs = 0.f;
             float xl_s = 0.f, xl_c = 0.f, ent_s = 0.f, ent_c = 0.f;     // compensated fp32 sums over the item
             const int t_end = ti.t_end;
-            for (int t = ti.t_begin; t < t_end; ++t, ++it) {
-                const uint32_t s = it & 1, xs = it % XST;
+            for (int t = ti.t_begin; t < t_end; ++t) {
                 const bool last = (t == t_end - 1);
                 if (ORI_TC_AFETCH_EARLY && last && has_next) a_fetch(next_own0);
-                mbar_wait(&bars[B_XFULL + xs], (it / XST) & 1, 30);      // X tile (and lp) visible to this thread
-                mbar_wait(&bars[B_SREADY + s], (it >> 1) & 1, 31);       // den / uv complete in TMEM
+                mbar_wait(&bars[B_XFULL + xs], xph, 30);                 // X tile (and lp) visible to this thread
+                mbar_wait(&bars[B_SREADY + s], sph, 31);                 // den / uv complete in TMEM
                 tc_fence_after();
                 if (last && has_next) {             // every S of this item has completed: A can be replaced
                     if (!ORI_TC_AFETCH_EARLY) a_fetch(next_own0);
@@ -493,7 +491,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     }
                 };
                 // lean path: full tile, no floors; returns the smallest denominator seen
-                auto fast_group = [&](int g) -> float {
+                auto fast_group = [&](int g, float& g_cs, float& g_xl, float& g_ent) -> float {
                     const int c0 = slice * CW + g * 16;
                     float cc[16];
                     if (DROPOUT && !GENES) {
@@ -506,10 +504,9 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     float dmin = 1.f;
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
-                        float den = __uint_as_float(dr[g][e]);
+                        const float den = __uint_as_float(dr[g][e]);
                         const float xe = x[g][e];
-                        if (GUARD_INLINE) den = den > 0.f ? den : 1.f;                // zigap.py:90
-                        else dmin = fminf(dmin, den);                                 // (general path when it fires)
+                        dmin = fminf(dmin, den);                  // den <= 0 (zigap.py:90): the group is redone below
                         float tt = den, uvp = 0.f;
                         if (DROPOUT) {
                             uvp = __uint_as_float(ur[g][e]);                          // U_hat.V_hat * log2(e)
@@ -525,15 +522,15 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                             ur[g][e] = tf32_bias(D);
                         }
                         if (GENES) {
-                            if (DROPOUT) cs += D;
+                            if (DROPOUT) g_cs += D;
                             if (ELBO) {
                                 const float l2 = lg2_approx(tt);
-                                t_xl = fmaf(xe, l2, t_xl);
+                                g_xl = fmaf(xe, l2, g_xl);
                                 if (DROPOUT) {
                                     const float e2 = fminf(uvp - lp2j, 127.f);
                                     const float w = 1.f - D;                          // 0 on non-zeros
-                                    t_ent += sel_pos(w, l2);
-                                    t_ent = fmaf(-w, e2, t_ent);
+                                    g_ent += sel_pos(w, l2);
+                                    g_ent = fmaf(-w, e2, g_ent);
                                 }
                             }
                         }
@@ -558,8 +555,10 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 for (int g = 0; g < G; ++g) {
                     redo[g] = slow_tile;
                     if (!slow_tile) {
-                        const float dmin = fast_group(g);
-                        if (!GUARD_INLINE) redo[g] = __any_sync(0xffffffffu, dmin <= 0.f) != 0;
+                        float g_cs = 0.f, g_xl = 0.f, g_ent = 0.f;
+                        const float dmin = fast_group(g, g_cs, g_xl, g_ent);
+                        redo[g] = __any_sync(0xffffffffu, dmin <= 0.f) != 0;
+                        if (GENES && !redo[g]) { cs += g_cs; t_xl += g_xl; t_ent += g_ent; }
                     }
                 }
 #pragma unroll
@@ -593,8 +592,10 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     }
                     if (ORI_TC_PREFETCH_X && g + 1 < G) load_x(g + 1);
                     if (!slow_tile) {
-                        const float dmin = fast_group(g);
-                        if (!GUARD_INLINE) redo = __any_sync(0xffffffffu, dmin <= 0.f) != 0;
+                        float g_cs = 0.f, g_xl = 0.f, g_ent = 0.f;
+                        const float dmin = fast_group(g, g_cs, g_xl, g_ent);
+                        redo = __any_sync(0xffffffffu, dmin <= 0.f) != 0;
+                        if (GENES && !redo) { cs += g_cs; t_xl += g_xl; t_ent += g_ent; }
                     }
                     if (redo) slow_group(g);
                     tmem_st16(tden + c0, dr[g]);
@@ -606,6 +607,8 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&bars[B_PREADY + s]); mbar_arrive(&bars[B_XEMPTY + xs]); }
+                s ^= 1; sph ^= (s == 0);
+                if (++xs == XST) { xs = 0; xph ^= 1; }
             }
             double acc_xl = (double)xl_s - (double)xl_c, acc_ent = (double)ent_s - (double)ent_c;
             // ---- epilogue of the work item: accumulators -> global (atomics: the sweep of one own tile is split)

@@ -100,6 +100,8 @@ typedef struct ori_problem {
 
 /* ---- library ---------------------------------------------------------------------------------- */
 int ori_version(void);
+/* Number of CUDA kernels this library has launched in this process (memsets and copies not counted). */
+unsigned long long ori_kernel_launches(void);
 /* Copies the last error message of the calling thread into buf; returns its length. */
 int ori_last_error(char* buf, size_t len);
 /* 0 when device `dev` is an sm_100 part, ORI_ENODEV otherwise. */

@@ -39,6 +39,7 @@ class OriProblem(C.Structure):
 _PP = C.POINTER(OriProblem)
 _SIGNATURES = {
     'ori_version': ([], C.c_int),
+    'ori_kernel_launches': ([], C.c_uint64),
     'ori_last_error': ([C.c_char_p, C.c_size_t], C.c_int),
     'ori_device_check': ([C.c_int], C.c_int),
     'ori_special_f64': ([C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p], C.c_int),

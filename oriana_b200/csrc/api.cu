@@ -1,4 +1,5 @@
 // api.cu -- extern "C" entry points of liboriana_b200.so (declared in include/oriana_b200.h).
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -18,7 +19,10 @@ int set_error(int code, const char* fmt, ...) {
     return code;
 }
 
-int check_launch(const char* what) {
+static std::atomic<unsigned long long> g_launches{0};
+
+int check_launch(const char* what, int n_kernels) {
+    g_launches.fetch_add((unsigned long long)n_kernels, std::memory_order_relaxed);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(ORI_ECUDA, "%s: %s", what, cudaGetErrorString(e));
     return ORI_OK;
@@ -103,7 +107,9 @@ using namespace ori;
 
 extern "C" {
 
-int ori_version(void) { return 100; }
+int ori_version(void) { return 101; }
+
+unsigned long long ori_kernel_launches(void) { return ori::g_launches.load(std::memory_order_relaxed); }
 
 int ori_last_error(char* buf, size_t len) {
     if (buf && len) { strncpy(buf, g_err, len - 1); buf[len - 1] = 0; }

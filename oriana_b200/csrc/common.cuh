@@ -8,7 +8,7 @@ namespace ori {
 
 // error plumbing (api.cu)
 int set_error(int code, const char* fmt, ...);
-int check_launch(const char* what);
+int check_launch(const char* what, int n_kernels = 1);   // also counts the kernels launched (ori_kernel_launches)
 
 // slots of ori_problem_t::red64 after the p column sums and the 2K row-side sums
 enum Red64Slot {

@@ -752,7 +752,7 @@ int launch_tc_prep_genes(const ori_problem_t* P, cudaStream_t st) {
         k_tc_prep_T<<<cdiv(w.pp, 32), dim3(32, 8), 0, st>>>(P->V_hat, w.geneT + 32 * w.pp, P->p, w.pp);
         k_tc_prep_lp<<<cdiv(w.pp, 256), 256, 0, st>>>(P->lp, P->pfloor, w.lp2w, w.flw, w.cw, w.flags, P->p, (int)w.pp);
     }
-    return check_launch("k_tc_prep(genes)");
+    return check_launch("k_tc_prep(genes)", drop ? 4 : 2);
 }
 // row-side operands, the sweep side of the gene pass: K-major hi/lo of generation g (the state that generated
 // D_hat), transposed Zj weight (eU, or eU * D_hat[:, :K] under the quirk) and transposed NEW U_hat
@@ -764,7 +764,7 @@ int launch_tc_prep_rows(const ori_problem_t* P, int g, cudaStream_t st) {
     const float* wsrc = (P->flags & ORI_F_QUIRK) ? P->eUw : P->eU[g];
     k_tc_prep_T<<<cdiv(w.np, 32), dim3(32, 8), 0, st>>>(wsrc, w.rowT, P->n_rows, w.np);
     if (drop) k_tc_prep_T<<<cdiv(w.np, 32), dim3(32, 8), 0, st>>>(P->U_hat[1 - g], w.rowT + 32 * w.np, P->n_rows, w.np);
-    return check_launch("k_tc_prep(rows)");
+    return check_launch("k_tc_prep(rows)", drop ? 3 : 2);
 }
 
 static int ew_warps() {

@@ -1,4 +1,4 @@
-run() { echo "== $1 EW=$2"; ORI_TC_EW=$2 ORIANA_B200_LIB=$PWD/oriana_b200/lib/$1.so timeout 300 python scripts/gpu_diag_tc.py time tconly 2>&1 | tail -2; }
-timeout 600 python -m pytest tests/test_tensor_path_gpu.py -x -q -m gpu 2>&1 | tail -3
-( run liboriana_b200 8; run liboriana_b200 16 ) > gpurun_out/v6_variants.log 2>&1
-cat gpurun_out/v6_variants.log
+timeout 300 python scripts/gpu_time_models.py > gpurun_out/v6_models.log 2>&1
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 > gpurun_out/v6_pytest_all.log
+python __graft_entry__.py smoke > gpurun_out/v6_smoke.log 2>&1
+cat gpurun_out/v6_models.log; tail -5 gpurun_out/v6_pytest_all.log; tail -3 gpurun_out/v6_smoke.log

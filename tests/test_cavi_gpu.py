@@ -169,8 +169,11 @@ def test_full_size_properties_config2(cuda_lib):
     mb = ZIGaP(s1['X'], k=K, use_factors=False, state=s1)
     for _ in range(2):
         ma.step(); mb.step()
-    assert relerr(mb.a1.asarray(), ma.a1.asarray()[pn]) < 1e-5
-    assert relerr(mb.b1.asarray(), ma.b1.asarray()) < 1e-5 and relerr(mb.pi_d.asarray(), ma.pi_d.asarray()) < 1e-6
+    # this size takes the tensor path: the gene sums are accumulated tile by tile in a different order, and
+    # their fp32 / TF32-operand rounding feeds the second step (stated tolerance of that path: 1e-3)
+    assert ma.uses_tensor_path and mb.uses_tensor_path
+    assert relerr(mb.a1.asarray(), ma.a1.asarray()[pn]) < 2e-4
+    assert relerr(mb.b1.asarray(), ma.b1.asarray()) < 2e-4 and relerr(mb.pi_d.asarray(), ma.pi_d.asarray()) < 1e-5
     assert abs(ma.elbo() - mb.elbo()) < 1e-6 * abs(ma.elbo())
 
 

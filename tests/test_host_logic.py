@@ -94,7 +94,7 @@ def test_library_exports_every_declared_symbol():
     """The C-ABI library loads and exports exactly what include/oriana_b200.h declares."""
     from oriana_b200 import _lib
     header = open(os.path.join(ROOT, 'include', 'oriana_b200.h')).read()
-    declared = sorted(set(re.findall(r'^(?:int|int64_t)\s+(ori_\w+)\s*\(', header, flags=re.M)))
+    declared = sorted(set(re.findall(r'^(?:int|int64_t|unsigned long long)\s+(ori_\w+)\s*\(', header, flags=re.M)))
     assert declared == _lib.exported_symbols()
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:

@@ -18,7 +18,7 @@ Pinning status
   `tests/golden/`).  `tests/test_oracle.py` replays those fixtures through this port.
 * Special functions (sigmoid/logit/digamma/inverse digamma, Gamma mean/meanlog,
   Bernoulli mean): pinned by the reference's own known-answer tests
-  (`test/test.py:13-41,60-79`), restated in `tests/test_special.py`.
+  (`test/test.py:13-41,60-79`), restated in `tests/test_oracle.py::test_special_functions_against_reference_kats` and `tests/test_special_gpu.py`.
 * ELBO: the reference has NO ELBO function.  The float64 formula in `cavi_numpy.elbo`
   is derived from the model definition (`zigap.py:21-53`); for it: PARITY UNPINNED
   (the float64 oracle is the only pin; it is checked for monotonicity on the de-quirked

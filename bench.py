@@ -166,10 +166,13 @@ def main():
     X = synth_counts_device(rows, p, K, seed=1234, row0=r0)
     np.random.seed(100 + rank)
     model = ZIGaP(X[:, :p], k=K, use_factors=False, sharded=world > 1, trace_cap=W + K_steps + 8)
+    uses_tc = model.uses_tensor_path
     for _ in range(W):
         model.step()
     model.enable_kernel_timing()
     sampler = ClockSampler(local)
+    from oriana_b200 import _lib as _orilib
+    launches0 = int(_orilib.load().ori_kernel_launches())
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -178,6 +181,7 @@ def main():
         model.step()
     e1.record()
     barrier()
+    launches = int(_orilib.load().ori_kernel_launches()) - launches0      # counted inside the C ABI library
     clocks = sampler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / K_steps
@@ -248,7 +252,7 @@ def main():
                        'cells_per_rank': rows, 'parallelism': 'cells sharded over %d rank(s); 2 sum-allreduces/iter' % world,
                        'l2': 'X per rank is %.1f GB, far larger than the 126 MB L2: no flush between steps' % (alg_bytes / 1e9)},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'clocks': clocks,
-            'gpu_launches': 5 * K_steps, 'elbo_monotone': elbo_ok, 'elbo_last': float(trace[-1]),
+            'gpu_launches': launches, 'tensor_path': bool(uses_tc), 'elbo_monotone': elbo_ok, 'elbo_last': float(trace[-1]),
         }
         print(json.dumps(out))
     if world > 1:

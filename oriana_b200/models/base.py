@@ -258,6 +258,11 @@ class FactorModel(metaclass=ABCMeta):
         self._set_factor(self._b1, b1)
         self._set_factor(self._a2, np.ones((self.n, self.k)))
         self._set_factor(self._b2, np.ones((self.m, self.k)))
+        # the gene side is replicated: every rank must start from the same draws (rank 0's), whatever the
+        # state of the per-process numpy generators
+        self._shard.broadcast(self._b1)
+        self._shard.broadcast(self._b2)
+        self._shard.broadcast(self._hyper)
 
     # ------------------------------------------------------------------------------------------------
     def update_expectations(self):

@@ -29,6 +29,12 @@ class RowSharding:
             dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group)
         return tensor
 
+    def broadcast(self, tensor, src=0):
+        """Make a replicated (gene-side) tensor identical on every rank: rank `src`'s values win."""
+        if self.enabled:
+            dist.broadcast(tensor, src=src, group=self.group)
+        return tensor
+
     def total_rows(self, n_rows, device=None):
         if not self.enabled:
             return int(n_rows)

@@ -84,6 +84,8 @@ def _worker(rank, world, port, model, quirk, out):
         assert shard.world == world and shard.rank == rank and shard.enabled
         r0, r1 = RowSharding.row_block(n, rank, world)
         assert shard.total_rows(r1 - r0) == n
+        t = torch.full((3,), float(rank))
+        assert shard.broadcast(t).tolist() == [0., 0., 0.]          # replicated state: rank 0's values win
         mine = {k: (v[r0:r1].copy() if k in ('X', 'a1', 'a2', 'p_d') else v.copy()) for k, v in full.items()}
         for _ in range(4):
             cn.step(full, quirk=quirk)

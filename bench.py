@@ -110,6 +110,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=0)
+    ap.add_argument('--e2e-f32', action='store_true', help='keep the host copy of X as float32 (default: uint16 counts)')
     args = ap.parse_args()
     n, p, K = CONFIGS[args.config]
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -216,8 +217,12 @@ def main():
     if not args.no_e2e:
         state = model.state_dict()
         del model
-        Xh = torch.empty((rows, p), dtype=torch.float32, pin_memory=True)
-        Xh.copy_(X[:, :p])
+        # counts are small integers: the host keeps them as uint16 (lossless here), half the bytes per step
+        xmax = float(X.max())
+        xdt = torch.uint16 if xmax < 65536 and not args.e2e_f32 else torch.float32
+        Xh = torch.empty((rows, p), dtype=xdt, pin_memory=True)
+        for r in range(0, rows, 1 << 16):
+            Xh[r:r + (1 << 16)].copy_(X[r:r + (1 << 16), :p].to(xdt))
         del X
         torch.cuda.empty_cache()
         host = HostStreamedCAVI(Xh, K, state, dropout=True, sharded=world > 1)
@@ -235,6 +240,7 @@ def main():
             dist.all_reduce(hb)
         e2e = {'value': n * p * n_e2e / dt, 'unit': UNIT, 'h2d_bytes_per_step': float(hb[0]) / n_e2e,
                'd2h_bytes_per_step': float(hb[1]) / n_e2e, 'steps': n_e2e, 'ms_per_step': dt / n_e2e * 1e3,
+               'host_x_dtype': str(xdt).replace('torch.', ''),
                'api': 'oriana_b200.host_step.HostStreamedCAVI.step (pinned host X, a1, a2, b1, b2 in; results out)'}
 
     # ---- the reference's CPU path beside it (rank 0, N=1 only)

@@ -179,6 +179,13 @@ int ori_synth_counts_f32(float* X, int64_t ldx, int64_t row0, int64_t n_rows, in
                          uint64_t seed, float zero_level, int nb, float* Ustar, float* Vstar, float* pi,
                          void* stream);
 
+/* ---- compact count storage (count-matrix ingest, oriana/singlecell/cmatrix.py:56-61) -------------- */
+/* dst[r, c] = (float)src[r, c] for unsigned integer counts of elem_bytes = 1 or 2 (device pointers; lds, ldd in
+ * elements, ldd a multiple of 4, dst 16-byte aligned).  Lets a host keep X as uint8 / uint16 and stream a
+ * quarter / half of the bytes per step; the kernels always see the float32 matrix of zigap.py:112. */
+int ori_widen_counts_f32(const void* src, int elem_bytes, int64_t lds, float* dst, int64_t ldd,
+                         int64_t rows, int32_t p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,5 +94,44 @@ extern "C" int ori_synth_counts_f32(float* X, int64_t ldx, int64_t row0, int64_t
     k_synth_factor<<<cdiv((long long)p * K, 256), 256, 0, st>>>(Vstar, p, K, 0, seed, 0x56u);
     k_synth_pi<<<cdiv(p, 256), 256, 0, st>>>(pi, p, zero_level, seed);
     k_synth_counts<<<cdiv(n_rows * ldx, 256), 256, 0, st>>>(X, ldx, row0, n_rows, p, K, Ustar, Vstar, pi, seed, nb);
-    return check_launch("k_synth_counts");
+    return check_launch("k_synth_counts", 4);
+}
+
+// ---- compact count storage -> float32 (count-matrix ingest, oriana/singlecell/cmatrix.py:56-61 as_array) --------
+// Counts are small integers: a host that keeps X as uint16 / uint8 halves / quarters the bytes that cross PCIe
+// every step of the host-streamed iteration; the kernels still see the float32 matrix of zigap.py:112.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_widen_counts(const T* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd, long long rows, int p)
+{
+    const int p4 = (p + 3) >> 2;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * p4) return;
+    const long long r = idx / p4;
+    const int c = (int)(idx - r * p4) * 4;
+    const T* s = src + r * lds + c;
+    float* d = dst + r * ldd + c;
+    if (c + 3 < p && ((lds * sizeof(T)) % (4 * sizeof(T)) == 0) && (((uintptr_t)s) % (4 * sizeof(T)) == 0)) {
+        T v[4];
+        if (sizeof(T) == 2) *reinterpret_cast<uint2*>(v) = *reinterpret_cast<const uint2*>(s);
+        else *reinterpret_cast<uint32_t*>(v) = *reinterpret_cast<const uint32_t*>(s);
+        *reinterpret_cast<float4*>(d) = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);   // ldd % 4 == 0
+    } else {
+        for (int q = 0; q < 4 && c + q < p; ++q) d[q] = (float)s[q];
+    }
+}
+
+extern "C" int ori_widen_counts_f32(const void* src, int elem_bytes, int64_t lds, float* dst, int64_t ldd,
+                                    int64_t rows, int32_t p, void* stream)
+{
+    if (!src || !dst || lds < p || ldd < p || (ldd & 3) || ((uintptr_t)dst & 15) || p <= 0 || rows < 0 ||
+        (elem_bytes != 1 && elem_bytes != 2))
+        return set_error(ORI_EINVAL, "ori_widen_counts_f32: bad argument");
+    if (rows == 0) return ORI_OK;
+    const long long n = rows * ((p + 3) >> 2);
+    if (elem_bytes == 2)
+        k_widen_counts<uint16_t><<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)src, lds, dst, ldd, rows, p);
+    else
+        k_widen_counts<uint8_t><<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)src, lds, dst, ldd, rows, p);
+    return check_launch("k_widen_counts");
 }

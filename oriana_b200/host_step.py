@@ -25,15 +25,23 @@ class HostStreamedCAVI:
 
     def __init__(self, X_host, k, state, dropout=True, compat_quirk=False, slab_rows=None, sharded=False,
                  process_group=None, elbo=True, keep_hyper=True):
-        """X_host: float32 CPU tensor [n, p] (pin it for asynchronous copies).  state: host arrays a1, a2
-        [n, k], b1, b2 [p, k], alpha1, alpha2, beta1, beta2 [k] (a reference model's state vector)."""
+        """X_host: CPU tensor [n, p] (pin it for asynchronous copies), float32 like the array the reference
+        feeds its kernel (zigap.py:112) or the same counts kept compactly as uint16 / uint8 (half / a quarter of
+        the bytes per step over PCIe; widened to float32 on the device).  state: host arrays a1, a2 [n, k],
+        b1, b2 [p, k], alpha1, alpha2, beta1, beta2 [k] (a reference model's state vector)."""
         self._dev = _lib.require_cuda()
         self._lib = _lib.load()
-        assert X_host.dtype == torch.float32 and X_host.dim() == 2 and not X_host.is_cuda
+        assert X_host.dtype in (torch.float32, torch.uint16, torch.uint8) and X_host.dim() == 2 and not X_host.is_cuda
         self.X = X_host
+        self._xbytes = X_host.element_size()
         self.n, self.p = int(X_host.shape[0]), int(X_host.shape[1])
         self.k = int(k)
-        KP = self._KP = pad_k(self.k)
+        ldx0 = (self.p + 3) // 4 * 4
+        S0 = slab_rows if slab_rows is not None else max(128, min(self.n, (512 << 20) // (4 * ldx0)) // 128 * 128)
+        S0 = int(min(max(1, S0), max(1, self.n)))
+        # slabs large enough to fill the machine take the tcgen05/TMA kernels (K <= 32), like the device model
+        self._tensor = self.k <= 32 and S0 * self.p >= (1 << 21)
+        KP = self._KP = 32 if self._tensor else pad_k(self.k)
         n, p, K, dev = self.n, self.p, self.k, self._dev
         self._shard = RowSharding(process_group, enabled=bool(sharded or process_group is not None))
         self.n_total = self._shard.total_rows(n, dev)
@@ -77,6 +85,10 @@ class HostStreamedCAVI:
                      acc64=torch.zeros_like(g['red64']))
             for name in ('a1', 'a2', 'U0', 'U1', 'e0', 'e1', 'Zi', 'a2s', 'eUw'):
                 s[name] = torch.zeros((S, KP), **f32)
+            if self._xbytes != 4:
+                s['Xq'] = torch.zeros((S, p), dtype=X_host.dtype, device=dev)      # compact counts as they arrive
+            if self._tensor:
+                s['tc_ws'] = torch.empty((int(self._lib.ori_tc_workspace_floats(S, p)) + 32,), **f32)
             s['stage'] = torch.zeros((2, S, K), **f32)     # unpadded a1|a2 as they travel
             self._slabs.append(s)
         self._streams = [torch.cuda.Stream(device=dev) for _ in self._slabs]
@@ -98,6 +110,8 @@ class HostStreamedCAVI:
             P.U_hat[0], P.U_hat[1] = s['U0'].data_ptr(), s['U1'].data_ptr()
             P.eU[0], P.eU[1] = s['e0'].data_ptr(), s['e1'].data_ptr()
             P.Zi, P.a2s, P.eUw = s['Zi'].data_ptr(), s['a2s'].data_ptr(), s['eUw'].data_ptr()
+            if 'tc_ws' in s:
+                P.tc_ws, P.tc_ws_floats = s['tc_ws'].data_ptr(), s['tc_ws'].numel()
         else:
             P.X = None
             P.a1 = P.a2 = P.Zi = P.a2s = P.eUw = dummy
@@ -123,11 +137,16 @@ class HostStreamedCAVI:
 
     def _upload_slab(self, s, r0, rows):
         K, p = self.k, self.p
-        s['X'][:rows, :p].copy_(self.X[r0:r0 + rows], non_blocking=True)
+        if self._xbytes == 4:
+            s['X'][:rows, :p].copy_(self.X[r0:r0 + rows], non_blocking=True)
+        else:
+            s['Xq'][:rows].copy_(self.X[r0:r0 + rows], non_blocking=True)
+            _lib.check(self._lib.ori_widen_counts_f32(s['Xq'].data_ptr(), self._xbytes, p, s['X'].data_ptr(), self._ldx,
+                                                      rows, p, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
         s['stage'][0, :rows].copy_(self.a1[r0:r0 + rows], non_blocking=True)
         s['stage'][1, :rows].copy_(self.a2[r0:r0 + rows], non_blocking=True)
         s['a1'][:rows, :K] = s['stage'][0, :rows]; s['a2'][:rows, :K] = s['stage'][1, :rows]
-        self.h2d_bytes += rows * p * 4 + 2 * rows * K * 4
+        self.h2d_bytes += rows * p * self._xbytes + 2 * rows * K * 4
 
     def _slab_loop(self, body):
         main = torch.cuda.current_stream()

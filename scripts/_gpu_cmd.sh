@@ -1,2 +1,2 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 --config c3 --no-e2e --no-cpu 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','elbo_monotone','elbo_last','gpu_launches')})"
-python bench.py --steps 10 --warmup 3 --config c3 --no-e2e --no-cpu 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','elbo_monotone','elbo_last','gpu_launches')})"
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -8
+python bench.py --config c3 --steps 5 --warmup 3 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['e2e']); print(d['value'], d['cpu_baseline']['value'])"

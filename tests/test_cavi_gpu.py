@@ -196,3 +196,39 @@ def test_host_streamed_step_matches_device_model(cuda_lib, name):
     want = m.elbo_trace[:4]
     assert np.max(np.abs(np.asarray(elbos) - want) / np.abs(want)) < 1e-6
     assert h.h2d_bytes > 4 * s['X'].size * 4 and h.d2h_bytes > 0
+
+
+def test_host_streamed_step_with_compact_counts(cuda_lib):
+    """X kept on the host as uint16 / uint8 counts (widened on the device) gives the float32-host results and
+    moves half / a quarter of the bytes; the widening kernel is exact on ragged shapes."""
+    import ctypes
+    import torch
+    from oriana_b200.host_step import HostStreamedCAVI
+    g = load_golden('zigap_ragged')
+    s = golden_state(g, 0)
+    K = s['a1'].shape[1]
+    X32 = torch.as_tensor(s['X'].astype(np.float32)).pin_memory()
+    ref = HostStreamedCAVI(X32, K, s, dropout=True, slab_rows=64)
+    for _ in range(3):
+        ref.step()
+    for dt in (torch.uint16, torch.uint8):
+        assert s['X'].max() < (1 << (8 * torch.empty((), dtype=dt).element_size()))
+        Xq = torch.as_tensor(s['X'].astype(np.float32)).to(dt).pin_memory()
+        h = HostStreamedCAVI(Xq, K, s, dropout=True, slab_rows=64)
+        for _ in range(3):
+            h.step()
+        for k in PARAMS:
+            assert relerr(h.state_dict()[k], ref.state_dict()[k]) < 5e-6, (dt, k)
+        assert h.h2d_bytes < ref.h2d_bytes
+    # the kernel itself, odd sizes and strides
+    rng = np.random.default_rng(0)
+    for rows, p, lds in ((7, 13, 13), (33, 130, 131), (5, 64, 64)):
+        for dt, hi in ((np.uint16, 65535), (np.uint8, 255)):
+            a = rng.integers(0, hi + 1, size=(rows, lds)).astype(dt)
+            src = torch.as_tensor(a.view(np.int16) if dt is np.uint16 else a).cuda()
+            ldd = (p + 3) // 4 * 4
+            dst = torch.zeros((rows, ldd), dtype=torch.float32, device='cuda')
+            rc = cuda_lib.ori_widen_counts_f32(src.data_ptr(), a.itemsize, lds, dst.data_ptr(), ldd, rows, p,
+                                               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            assert rc == 0
+            assert np.array_equal(dst.cpu().numpy()[:, :p], a[:, :p].astype(np.float32))

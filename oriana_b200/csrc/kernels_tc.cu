@@ -21,9 +21,13 @@
 // hence the transposed copies (prepared by k_tc_prep_*) and K-major descriptors everywhere
 // (scripts/tc_probe.cu checks every descriptor form used here against the CPU).
 //
+// CTA pairs (PAIR, the default): two CTAs of a cluster sweep the same chunk with neighbouring own tiles; every MMA
+// is a cta_group::2 instruction of M = 256 issued by the pair's leader, each CTA stages only half of every
+// streamed operand tile and TMA credits both halves to the leader's barrier; completion is multicast back.
+//
 // Warp roles (64 + 32*NEW threads):
-//   warp 0       TMA producer (one lane polls the three rings)
-//   warp 1       MMA issuer + TMEM owner (one lane issues)
+//   warp 0       TMA producer (whole warp walks the rings, one elected lane issues)
+//   warp 1       MMA issuer + TMEM owner (warp-uniform control flow, one elected lane issues)
 //   warps 2..    NEW element-wise warps; warp w owns TMEM lanes 32*(w%4).. and 64/(NEW/4) of the 64 columns
 #include <cstdlib>
 #include "common.cuh"
@@ -49,24 +53,37 @@ constexpr int TC_OWN = 128;
 constexpr int TC_SW = 64;
 constexpr int TC_KP_CONST = 32;     // latent dimension of the tensor path (K <= 32, zero padded)
 
-constexpr int KST = 2;              // ring depths
-constexpr int TST = 2;
-constexpr int XST = 3;
-constexpr uint32_t K_STAGE = 32768;   // 4 K-major arrays [64 x 32]: hi(e) lo(e) hi(E) lo(E)
-constexpr uint32_t T_STAGE = 16384;   // 2 transposed arrays x 2 chunks [32 x 32]
-constexpr uint32_t X_STAGE = 32768;   // X tile
-constexpr uint32_t LP_STAGE = 768;    // lp2[64] | floor[64] | (1-pi)/pi [64]
-constexpr uint32_t OFF_K = 0;
-constexpr uint32_t OFF_T = OFF_K + KST * K_STAGE;
-constexpr uint32_t OFF_X = OFF_T + TST * T_STAGE;
-constexpr uint32_t OFF_LP = OFF_X + XST * X_STAGE;
-constexpr uint32_t OFF_BAR = OFF_LP + XST * LP_STAGE;
-constexpr uint32_t TC_SMEM_BYTES = OFF_BAR + 512 + 1024;   // + barriers + alignment slack
-
-enum { B_KFULL = 0, B_KEMPTY = B_KFULL + KST, B_TFULL = B_KEMPTY + KST, B_TEMPTY = B_TFULL + TST,
-       B_XFULL = B_TEMPTY + TST, B_XEMPTY = B_XFULL + XST, B_SREADY = B_XEMPTY + XST, B_PREADY = B_SREADY + 2,
-       B_ACC_READY = B_PREADY + 2, B_ACC_FREE, B_A_READY, NBARS };
-static_assert(NBARS * 8 + 8 <= 512, "barrier area");
+// Shared-memory plan.  PAIR = the CTA-pair variant (cta_group::2, M = 256 over two SMs): each CTA stages only
+// half of every streamed operand tile (the pair's MMA reads both halves), which halves the TMA fill and the
+// tensor-core operand reads per SM and leaves room for deeper rings.
+template <bool PAIR>
+struct Cfg {
+    static constexpr int NCTA = PAIR ? 2 : 1;
+    static constexpr int KST = PAIR ? 3 : 2;              // ring depths
+    static constexpr int TST = PAIR ? 3 : 2;
+    static constexpr int XST = PAIR ? 4 : 3;
+    static constexpr uint32_t K_ARR = 8192 / NCTA;        // one K-major array [64 / NCTA sweep rows x 32]
+    static constexpr uint32_t K_STAGE = 4 * K_ARR;        // hi(e) lo(e) hi(E) lo(E)
+    static constexpr uint32_t T_CHUNK = 4096 / NCTA;      // [32 / NCTA latent rows x 32 sweep columns]
+    static constexpr uint32_t T_ARR = 2 * T_CHUNK;        // two chunks = 64 sweep columns
+    static constexpr uint32_t T_STAGE = 2 * T_ARR;        // transposed e and transposed E
+    static constexpr uint32_t X_STAGE = 32768;            // X tile
+    static constexpr uint32_t LP_STAGE = 768;             // lp2[64] | floor[64] | (1-pi)/pi [64]
+    static constexpr uint32_t OFF_K = 0;
+    static constexpr uint32_t OFF_T = OFF_K + KST * K_STAGE;
+    static constexpr uint32_t OFF_X = OFF_T + TST * T_STAGE;
+    static constexpr uint32_t OFF_LP = OFF_X + XST * X_STAGE;
+    static constexpr uint32_t OFF_BAR = OFF_LP + XST * LP_STAGE;
+    static constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;   // + barriers + alignment slack
+    // mbarriers.  With PAIR, KFULL / TFULL / PREADY / ACC_FREE / A_READY are used in the leader CTA only
+    // (the peer's TMA bytes and warp arrivals are credited there); the others are per CTA.
+    static constexpr int B_KFULL = 0, B_KEMPTY = B_KFULL + KST, B_TFULL = B_KEMPTY + KST, B_TEMPTY = B_TFULL + TST,
+                         B_XFULL = B_TEMPTY + TST, B_XEMPTY = B_XFULL + XST, B_SREADY = B_XEMPTY + XST,
+                         B_PREADY = B_SREADY + 2, B_ACC_READY = B_PREADY + 2, B_ACC_FREE = B_ACC_READY + 1,
+                         B_A_READY = B_ACC_FREE + 1, NBARS = B_A_READY + 1;
+    static_assert(NBARS * 8 + 8 <= 512, "barrier area");
+    static_assert(SMEM_BYTES <= 232448, "shared memory");
+};
 
 constexpr uint32_t TM_STAGE = 128;   // TMEM columns per stage: den/R [0,64) | uv/D [64,128)
 constexpr uint32_t TM_ACC = 256;     // acc1 [256,288) | acc2 [288,320)
@@ -78,7 +95,7 @@ struct TcMaps { CUtensorMap swK, swT, X; };
 struct TcArgs {
     long long own_total, sw_total;   // valid extents (cells / genes)
     long long sw_pad;                // padded sweep extent (multiple of 128): q-th operand array starts at row q*pad
-    int n_own_tiles, n_chunks, tiles_per_chunk, n_sw_tiles, n_items;
+    int n_own_tiles, n_own_units, n_chunks, tiles_per_chunk, n_sw_tiles, n_items;   // unit = own tile (pair of own tiles with PAIR)
     const float* own_e;              // [own_total x 32] exp(E log .) of the own side (raw factor array)
     const float* own_E;              // [own_total x 32] E[.] of the own side
     const float* lp2w;               // [genes_pad] logit(pi) * log2(e); -inf: D_hat = (X>0)
@@ -140,32 +157,46 @@ __device__ __forceinline__ void kahan_add(float& s, float& c, float v) {
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
-// Walks the tiles of the work items of this CTA: item = chunk * n_own_tiles + own_tile (chunk-major, so that
-// the CTAs running at the same time sweep the same chunk and share its operands in L2).
+// Walks the tiles of the work items of this CTA (pair): item = chunk * n_own_units + own_unit (chunk-major, so
+// that the CTAs running at the same time sweep the same chunk and share its operands in L2).  With PAIR the two
+// CTAs of a cluster walk the same items; CTA `rank` owns own tile 2 * own_unit + rank.
 struct TileIter {
-    int item, t, t_begin, t_end, own0;
+    int item, stride, t, t_begin, t_end, own0, ncta, rank;
     __device__ __forceinline__ void load(const TcArgs& a) {
         if (item < a.n_items) {
-            const int chunk = item / a.n_own_tiles, own_tile = item - chunk * a.n_own_tiles;
-            own0 = own_tile * TC_OWN;
+            const int chunk = item / a.n_own_units, own_unit = item - chunk * a.n_own_units;
+            own0 = (own_unit * ncta + rank) * TC_OWN;
             t_begin = chunk * a.tiles_per_chunk;
             t_end = min(t_begin + a.tiles_per_chunk, a.n_sw_tiles);
             t = t_begin;
         }
     }
-    __device__ __forceinline__ void init(const TcArgs& a) { item = blockIdx.x; load(a); }
+    __device__ __forceinline__ void init(const TcArgs& a, int ncta_, int rank_) {
+        ncta = ncta_; rank = rank_;
+        item = blockIdx.x / ncta; stride = gridDim.x / ncta;
+        load(a);
+    }
     __device__ __forceinline__ bool valid(const TcArgs& a) const { return item < a.n_items; }
     __device__ __forceinline__ bool first() const { return t == t_begin; }
     __device__ __forceinline__ bool last() const { return t == t_end - 1; }
     __device__ __forceinline__ void next(const TcArgs& a) {
-        if (++t >= t_end) { item += gridDim.x; load(a); }
+        if (++t >= t_end) { item += stride; load(a); }
     }
 };
 
-template <bool GENES, bool DROPOUT, bool ELBO, int NEW>
+template <bool GENES, bool DROPOUT, bool ELBO, int NEW, bool PAIR>
 __global__ void __launch_bounds__(64 + 32 * NEW, 1)
 k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
 {
+    using C = Cfg<PAIR>;
+    constexpr int NCTA = C::NCTA;
+    constexpr int KST = C::KST, TST = C::TST, XST = C::XST;
+    constexpr uint32_t K_STAGE = C::K_STAGE, T_STAGE = C::T_STAGE, X_STAGE = C::X_STAGE, LP_STAGE = C::LP_STAGE;
+    constexpr uint32_t OFF_K = C::OFF_K, OFF_T = C::OFF_T, OFF_X = C::OFF_X, OFF_LP = C::OFF_LP, OFF_BAR = C::OFF_BAR;
+    constexpr int B_KFULL = C::B_KFULL, B_KEMPTY = C::B_KEMPTY, B_TFULL = C::B_TFULL, B_TEMPTY = C::B_TEMPTY,
+                  B_XFULL = C::B_XFULL, B_XEMPTY = C::B_XEMPTY, B_SREADY = C::B_SREADY, B_PREADY = C::B_PREADY,
+                  B_ACC_READY = C::B_ACC_READY, B_ACC_FREE = C::B_ACC_FREE, B_A_READY = C::B_A_READY, NBARS = C::NBARS;
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;      // CTA of the pair; rank 0 leads (issues every MMA)
     constexpr int SLICES = NEW / 4;           // element-wise warps per TMEM lane quarter
     constexpr int CW = TC_SW / SLICES;        // tile columns per element-wise warp
     constexpr int NQ = DROPOUT ? 4 : 2;       // K-major operand arrays in use
@@ -180,15 +211,16 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
         for (int s = 0; s < KST; ++s) { mbar_init(&bars[B_KFULL + s], 1); mbar_init(&bars[B_KEMPTY + s], 1); }
         for (int s = 0; s < TST; ++s) { mbar_init(&bars[B_TFULL + s], 1); mbar_init(&bars[B_TEMPTY + s], 1); }
         for (int s = 0; s < XST; ++s) { mbar_init(&bars[B_XFULL + s], 1); mbar_init(&bars[B_XEMPTY + s], NEW); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&bars[B_SREADY + s], 1); mbar_init(&bars[B_PREADY + s], NEW); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars[B_SREADY + s], 1); mbar_init(&bars[B_PREADY + s], NEW * NCTA); }
         mbar_init(&bars[B_ACC_READY], 1);
-        mbar_init(&bars[B_ACC_FREE], NEW);
-        mbar_init(&bars[B_A_READY], NEW);
+        mbar_init(&bars[B_ACC_FREE], NEW * NCTA);
+        mbar_init(&bars[B_A_READY], NEW * NCTA);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, TM_COLS);
+    if (warp == 1) { if (PAIR) tmem_alloc_pair(tmem_slot, TM_COLS); else tmem_alloc(tmem_slot, TM_COLS); }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive / TMA credit
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
@@ -201,7 +233,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
         // when S(j-2) has run, the X stage when the element-wise warps are done with tile j-3, the T stage when
         // P(j-3) has run), so the blocking waits below never hold back a load whose stage is already free.
         TileIter ik, it_;
-        ik.init(a); it_.init(a);
+        ik.init(a, NCTA, rank); it_.init(a, NCTA, rank);
         uint32_t nk = 0, nt = 0;
         auto load_T = [&]() {
             const uint32_t s = nt % TST;
@@ -210,12 +242,15 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 uint8_t* st = smem + OFF_T + s * T_STAGE;
                 uint64_t* bar = &bars[B_TFULL + s];
                 const int sw0 = it_.t * TC_SW;
-                mbar_expect_tx(bar, NT * 8192);
+                if (rank == 0) mbar_expect_tx(bar, NT * 8192);              // the whole pair's bytes land on the leader's barrier
 #pragma unroll
                 for (int q = 0; q < NT; ++q)
 #pragma unroll
-                    for (int c = 0; c < 2; ++c)
-                        tma_load_2d(st + q * 8192 + c * 4096, &maps.swT, bar, sw0 + 32 * c, q * 32);
+                    for (int c = 0; c < 2; ++c) {
+                        uint8_t* dst = st + q * C::T_ARR + c * C::T_CHUNK;
+                        if (PAIR) tma_load_2d_pair(dst, &maps.swT, bar, sw0 + 32 * c, q * 32 + 16 * rank, L2_EVICT_LAST);
+                        else tma_load_2d_hint(dst, &maps.swT, bar, sw0 + 32 * c, q * 32, L2_EVICT_LAST);
+                    }
             }
             __syncwarp();
             ++nt; it_.next(a);
@@ -228,10 +263,12 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     uint8_t* st = smem + OFF_K + s * K_STAGE;
                     uint64_t* bar = &bars[B_KFULL + s];
                     const int sw0 = ik.t * TC_SW;
-                    mbar_expect_tx(bar, NQ * 8192);
+                    if (rank == 0) mbar_expect_tx(bar, NQ * 8192);
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q)
-                        tma_load_2d(st + q * 8192, &maps.swK, bar, 0, (int)(q * a.sw_pad + sw0));
+                    for (int q = 0; q < NQ; ++q) {
+                        if (PAIR) tma_load_2d_pair(st + q * C::K_ARR, &maps.swK, bar, 0, (int)(q * a.sw_pad + sw0 + 32 * rank), L2_EVICT_LAST);
+                        else tma_load_2d_hint(st + q * C::K_ARR, &maps.swK, bar, 0, (int)(q * a.sw_pad + sw0), L2_EVICT_LAST);
+                    }
                 }
                 __syncwarp();
             }
@@ -245,7 +282,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     mbar_expect_tx(bar, X_STAGE + ((!GENES && DROPOUT) ? 768 : 0));
                     if (!GENES) {
 #pragma unroll
-                        for (int c = 0; c < 2; ++c) tma_load_2d(st + c * 16384, &maps.X, bar, sw0 + 32 * c, ik.own0);
+                        for (int c = 0; c < 2; ++c) tma_load_2d_hint(st + c * 16384, &maps.X, bar, sw0 + 32 * c, ik.own0, L2_EVICT_FIRST);
                         if (DROPOUT) {
                             bulk_load(smem + OFF_LP + s * LP_STAGE, a.lp2w + sw0, 256, bar);
                             bulk_load(smem + OFF_LP + s * LP_STAGE + 256, a.flw + sw0, 256, bar);
@@ -253,7 +290,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                         }
                     } else {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) tma_load_2d(st + c * 8192, &maps.X, bar, ik.own0 + 32 * c, sw0);
+                        for (int c = 0; c < 4; ++c) tma_load_2d_hint(st + c * 8192, &maps.X, bar, ik.own0 + 32 * c, sw0, L2_EVICT_FIRST);
                     }
                 }
                 __syncwarp();
@@ -267,37 +304,44 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
         // Warp-uniform control flow, one elected lane issues: descriptors and TMEM addresses stay in uniform
         // registers (a divergent single-lane loop makes the compiler wrap every tcgen05.mma in a
         // register->uniform-register broadcast loop, which throttles the issue rate).
-        constexpr uint32_t idescS = make_idesc_tf32(TC_OWN, TC_SW, false, false);
-        constexpr uint32_t idescP = make_idesc_tf32(TC_OWN, TC_KP_CONST, false, false);
+        // With PAIR only the leader CTA issues: cta_group::2 MMAs of M = 256 span both CTAs' TMEM and read each
+        // CTA's half of the B tile; completion is multicast to the barriers of both CTAs.
+        if (!PAIR || rank == 0) {
+        constexpr uint32_t idescS = make_idesc_tf32(TC_OWN * NCTA, TC_SW, false, false);
+        constexpr uint32_t idescP = make_idesc_tf32(TC_OWN * NCTA, TC_KP_CONST, false, false);
         const uint32_t sbase = smem_u32(smem);
         const uint64_t kdesc0 = make_smem_desc(sbase + OFF_K, 16, 1024);
         const uint64_t tdesc0 = make_smem_desc(sbase + OFF_T, 16, 1024);
+        auto mma = [&](uint32_t d, uint32_t at, uint64_t bd, uint32_t idesc, bool acc) {
+            if (PAIR) mma_tf32_ts_pair(d, at, bd, idesc, acc); else mma_tf32_ts(d, at, bd, idesc, acc);
+        };
+        auto commit = [&](uint64_t* bar) { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); };
         auto issue_P = [&](uint32_t it, bool first, bool last, int li) {
             const uint32_t s = it & 1, ts = it % TST;
-            mbar_wait(&bars[B_PREADY + s], (it >> 1) & 1, 20);
+            mbar_wait(&bars[B_PREADY + s], (it >> 1) & 1, 20, PAIR);
             mbar_wait(&bars[B_TFULL + ts], (it / TST) & 1, 24);
-            if (first) mbar_wait(&bars[B_ACC_FREE], (li & 1) ^ 1, 21);
+            if (first) mbar_wait(&bars[B_ACC_FREE], (li & 1) ^ 1, 21, PAIR);
             tc_fence_after();
             if (elect_one()) {
                 const uint64_t td = tdesc0 + (uint64_t)((ts * T_STAGE) >> 4);
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
-                    mma_tf32_ts(tmem + TM_ACC, tmem + s * TM_STAGE + ks * 8,
-                                td + (uint64_t)(((ks >> 2) * 4096 + (ks & 3) * 32) >> 4), idescP, !(first && ks == 0));
+                    mma(tmem + TM_ACC, tmem + s * TM_STAGE + ks * 8,
+                        td + (uint64_t)(((ks >> 2) * C::T_CHUNK + (ks & 3) * 32) >> 4), idescP, !(first && ks == 0));
                 if (DROPOUT) {
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks)
-                        mma_tf32_ts(tmem + TM_ACC + 32, tmem + s * TM_STAGE + 64 + ks * 8,
-                                    td + (uint64_t)((8192 + (ks >> 2) * 4096 + (ks & 3) * 32) >> 4), idescP,
-                                    !(first && ks == 0));
+                        mma(tmem + TM_ACC + 32, tmem + s * TM_STAGE + 64 + ks * 8,
+                            td + (uint64_t)((C::T_ARR + (ks >> 2) * C::T_CHUNK + (ks & 3) * 32) >> 4), idescP,
+                            !(first && ks == 0));
                 }
-                tc_commit(&bars[B_TEMPTY + ts]);
-                if (last) tc_commit(&bars[B_ACC_READY]);
+                commit(&bars[B_TEMPTY + ts]);
+                if (last) commit(&bars[B_ACC_READY]);
             }
             __syncwarp();
         };
         TileIter ti;
-        ti.init(a);
+        ti.init(a, NCTA, rank);
         uint32_t it = 0;
         int li = 0;
         bool have_prev = false, prev_first = false, prev_last = false;
@@ -306,15 +350,15 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             const uint32_t s = it & 1, ks_ = it % KST;
             const bool first = ti.first(), last = ti.last();
             mbar_wait(&bars[B_KFULL + ks_], (it / KST) & 1, 23);
-            if (first) mbar_wait(&bars[B_A_READY], li & 1, 22);
+            if (first) mbar_wait(&bars[B_A_READY], li & 1, 22, PAIR);
             tc_fence_after();
             if (elect_one()) {
                 const uint64_t kd = kdesc0 + (uint64_t)((ks_ * K_STAGE) >> 4);
                 // den (and uv) of this tile: three tf32 products per contraction, A operand from TMEM
 #define ORI_CHAIN(D_, QA, QB, FRESH)                                                                          \
                 _Pragma("unroll") for (int kk = 0; kk < 4; ++kk)                                              \
-                    mma_tf32_ts((D_), tmem + TM_A + (QA) * 32 + kk * 8,                                       \
-                                kd + (uint64_t)(((QB) * 8192 + kk * 32) >> 4), idescS, !((FRESH) && kk == 0))
+                    mma((D_), tmem + TM_A + (QA) * 32 + kk * 8,                                               \
+                        kd + (uint64_t)(((QB) * C::K_ARR + kk * 32) >> 4), idescS, !((FRESH) && kk == 0))
                 ORI_CHAIN(tmem + s * TM_STAGE, 0, 0, true);
                 ORI_CHAIN(tmem + s * TM_STAGE, 0, 1, false);
                 ORI_CHAIN(tmem + s * TM_STAGE, 1, 0, false);
@@ -324,8 +368,8 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     ORI_CHAIN(tmem + s * TM_STAGE + 64, 3, 2, false);
                 }
 #undef ORI_CHAIN
-                tc_commit(&bars[B_SREADY + s]);
-                tc_commit(&bars[B_KEMPTY + ks_]);
+                commit(&bars[B_SREADY + s]);
+                commit(&bars[B_KEMPTY + ks_]);
             }
             __syncwarp();
             if (have_prev) issue_P(it - 1, prev_first, prev_last, prev_li);
@@ -335,6 +379,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             ti.next(a);
         }
         if (have_prev) issue_P(it - 1, prev_first, prev_last, prev_li);
+        }
     } else {
         // ======================================= element-wise stage + epilogue =================================
         const int ew = warp - 2;
@@ -387,7 +432,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[B_A_READY]);
+            if (lane == 0) { if (PAIR) mbar_arrive_cluster(&bars[B_A_READY], 0); else mbar_arrive(&bars[B_A_READY]); }
         };
 
         const uint32_t sbase = smem_u32(smem);
@@ -398,16 +443,16 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
         for (int k = 0; k < 8; ++k) xoff[k] = (uint32_t)(quarter * 8192 + ((((lane >> 2) ^ k)) << 4) + (lane & 3) * 4);
 
         TileIter ti;
-        ti.init(a);
+        ti.init(a, NCTA, rank);
         uint32_t s = 0, sph = 0, xs = 0, xph = 0;     // TMEM stage / X ring stage of the current tile and their phases
         int li = 0;
         if (ti.valid(a)) { a_fetch(ti.own0); a_store(); }
         while (ti.valid(a)) {
             const long long own_idx = (long long)ti.own0 + lrow;
             const bool own_ok = own_idx < a.own_total;
-            const int next_item = ti.item + gridDim.x;
+            const int next_item = ti.item + ti.stride;
             const bool has_next = next_item < a.n_items;
-            const int next_own0 = (next_item % a.n_own_tiles) * TC_OWN;
+            const int next_own0 = ((next_item % a.n_own_units) * NCTA + rank) * TC_OWN;
             float lp2j = 0.f, flj = 0.f, cj = 0.f;
             if (GENES && DROPOUT) {                   // padded arrays: always in range
                 lp2j = a.lp2w[own_idx]; flj = a.flw[own_idx];
@@ -606,7 +651,10 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(&bars[B_PREADY + s]); mbar_arrive(&bars[B_XEMPTY + xs]); }
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_cluster(&bars[B_PREADY + s], 0); else mbar_arrive(&bars[B_PREADY + s]);
+                    mbar_arrive(&bars[B_XEMPTY + xs]);
+                }
                 s ^= 1; sph ^= (s == 0);
                 if (++xs == XST) { xs = 0; xph ^= 1; }
             }
@@ -630,7 +678,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[B_ACC_FREE]);
+            if (lane == 0) { if (PAIR) mbar_arrive_cluster(&bars[B_ACC_FREE], 0); else mbar_arrive(&bars[B_ACC_FREE]); }
             if (GENES) {
                 if (DROPOUT && own_ok) atomicAdd(a.colsum + own_idx, (double)cs);
                 if (ELBO) {
@@ -647,13 +695,14 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 }
             }
             ++li;
-            ti.item += gridDim.x;
+            ti.item += ti.stride;
             ti.load(a);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, TM_COLS);
+    if (PAIR) cluster_sync_all();          // the leader's MMAs read the peer's shared memory and TMEM until the very end
+    if (warp == 1) { if (PAIR) tmem_dealloc_pair(tmem, TM_COLS); else tmem_dealloc(tmem, TM_COLS); }
 }
 
 // ---- operand preparation -------------------------------------------------------------------------------------
@@ -767,19 +816,18 @@ int launch_tc_prep_rows(const ori_problem_t* P, int g, cudaStream_t st) {
     return check_launch("k_tc_prep(rows)", drop ? 3 : 2);
 }
 
-static int ew_warps() {
-    static int n = 0;
-    if (!n) {
-        const char* e = getenv("ORI_TC_EW");
-        n = (e && atoi(e) == 16) ? 16 : 8;
-    }
-    return n;
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
+static int ew_warps() { static int n = env_int("ORI_TC_EW", 8) == 16 ? 16 : 8; return n; }
+// CTA-pair kernels (cta_group::2) by default; ORI_TC_PAIR=0 selects the single-CTA variant (kept for A/B runs)
+static bool use_pair() { static int v = env_int("ORI_TC_PAIR", 1); return v != 0; }
 
-// Split the sweep into chunks so that (a) there are many more work items than SMs, (b) the static round-robin
-// over the SMs wastes as little of the last round as possible, (c) the gene pass keeps <= 128 tiles per item
-// (fp32 running sums of the statistics).
-static void tc_partition(TcArgs& a, bool genes, int sms) {
+// Split the sweep into chunks so that (a) there are many more work items than schedulable units (SMs, or SM
+// pairs), (b) the static round-robin wastes as little of the last round as possible, (c) the gene pass keeps
+// <= 128 tiles per item (fp32 running sums of the statistics).
+static void tc_partition(TcArgs& a, bool genes, int units) {
     const int max_tpc = genes ? 128 : 1 << 30;
     int best_chunks = 1; double best_eff = -1.0;
     for (int chunks = 1; chunks <= a.n_sw_tiles; ++chunks) {
@@ -787,35 +835,57 @@ static void tc_partition(TcArgs& a, bool genes, int sms) {
         if (tpc > max_tpc) continue;
         if (tpc < 16 && chunks > 1) break;
         const int real_chunks = cdiv(a.n_sw_tiles, tpc);
-        const long long items = (long long)real_chunks * a.n_own_tiles;
-        const long long rounds = (items + sms - 1) / sms;
+        const long long items = (long long)real_chunks * a.n_own_units;
+        const long long rounds = (items + units - 1) / units;
         // efficiency of the static schedule, with a mild penalty per item for its prologue / epilogue
-        const double eff = (double)items / (double)(rounds * sms) * ((double)tpc / (tpc + 2.0));
+        const double eff = (double)items / (double)(rounds * units) * ((double)tpc / (tpc + 2.0));
         if (eff > best_eff + 1e-9) { best_eff = eff; best_chunks = chunks; }
-        if (items > 64LL * sms) break;
+        if (items > 64LL * units) break;
     }
     a.tiles_per_chunk = cdiv(a.n_sw_tiles, best_chunks);
     a.n_chunks = cdiv(a.n_sw_tiles, a.tiles_per_chunk);
-    a.n_items = a.n_own_tiles * a.n_chunks;
+    a.n_items = a.n_own_units * a.n_chunks;
 }
 
-template <bool GENES>
-static int launch_tc_pass(const ori_problem_t* P, int gen_old, cudaStream_t st) {
+template <bool GENES, bool D, bool E, int NW, bool PAIR>
+static int launch_tc_variant(const TcMaps& maps, const TcArgs& a, int grid, cudaStream_t st) {
+    auto kern = k_tc_pass<GENES, D, E, NW, PAIR>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<PAIR>::SMEM_BYTES);
+        if (e_ != cudaSuccess) return set_error(ORI_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e_));
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * NW); cfg.dynamicSmemBytes = Cfg<PAIR>::SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e_ = cudaLaunchKernelEx(&cfg, kern, maps, a);
+    if (e_ != cudaSuccess) return set_error(ORI_ECUDA, "cudaLaunchKernelEx(k_tc_pass): %s", cudaGetErrorString(e_));
+    return ORI_OK;
+}
+
+template <bool GENES, bool PAIR>
+static int launch_tc_pass_p(const ori_problem_t* P, int gen_old, cudaStream_t st) {
     const TcWs w = tc_carve(P);
     const bool drop = P->flags & ORI_F_DROPOUT, elbo = P->flags & ORI_F_ELBO;
+    constexpr int NCTA = PAIR ? 2 : 1;
     TcMaps maps;
     TcArgs a;
     bool ok;
+    // streamed-operand boxes: a CTA of a pair stages half of the 64 sweep rows / half of the 32 latent rows
     if (!GENES) {
-        ok = make_tmap_f32(&maps.swK, w.geneK, 4 * w.pp, 32, 32, 32, 64) &&
-             make_tmap_f32(&maps.swT, w.geneT, 64, w.pp, w.pp, 32, 32) &&
+        ok = make_tmap_f32(&maps.swK, w.geneK, 4 * w.pp, 32, 32, 32, 64 / NCTA) &&
+             make_tmap_f32(&maps.swT, w.geneT, 64, w.pp, w.pp, 32, 32 / NCTA) &&
              make_tmap_f32(&maps.X, P->X, P->n_rows, P->p, P->ldx, 32, 128);
         a.own_total = P->n_rows; a.sw_total = P->p; a.sw_pad = w.pp;
         a.own_e = P->eU[gen_old]; a.own_E = P->U_hat[gen_old];
         a.acc1 = P->Zi; a.acc2 = P->a2s;
     } else {
-        ok = make_tmap_f32(&maps.swK, w.rowK, 4 * w.np, 32, 32, 32, 64) &&
-             make_tmap_f32(&maps.swT, w.rowT, 64, w.np, w.np, 32, 32) &&
+        ok = make_tmap_f32(&maps.swK, w.rowK, 4 * w.np, 32, 32, 32, 64 / NCTA) &&
+             make_tmap_f32(&maps.swT, w.rowT, 64, w.np, w.np, 32, 32 / NCTA) &&
              make_tmap_f32(&maps.X, P->X, P->n_rows, P->p, P->ldx, 32, 64);
         a.own_total = P->p; a.sw_total = P->n_rows; a.sw_pad = w.np;
         a.own_e = P->eV; a.own_E = P->V_hat;
@@ -825,31 +895,27 @@ static int launch_tc_pass(const ori_problem_t* P, int gen_old, cudaStream_t st) 
     a.lp2w = w.lp2w; a.flw = w.flw; a.cw = w.cw; a.any_floor = w.flags;
     a.colsum = P->red64; a.part64 = P->red64 + P->p + 2 * P->KP;
     a.n_own_tiles = cdiv(a.own_total, TC_OWN);
+    a.n_own_units = cdiv(a.n_own_tiles, NCTA);
     a.n_sw_tiles = cdiv(a.sw_total, TC_SW);
-    const int sms = num_sms();
-    tc_partition(a, GENES, sms);
-    const int grid = a.n_items < sms ? a.n_items : sms;
+    const int units = num_sms() / NCTA;
+    tc_partition(a, GENES, units);
+    const int grid = NCTA * (a.n_items < units ? a.n_items : units);
     const int nw = ew_warps();
-
-#define ORI_TC_LAUNCH(D, E, NW)                                                                                 \
-    do {                                                                                                        \
-        auto kern = k_tc_pass<GENES, D, E, NW>;                                                                 \
-        static bool attr_done = false;                                                                          \
-        if (!attr_done) {                                                                                       \
-            cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES); \
-            if (e_ != cudaSuccess) return set_error(ORI_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e_)); \
-            attr_done = true;                                                                                   \
-        }                                                                                                       \
-        kern<<<grid, 64 + 32 * NW, TC_SMEM_BYTES, st>>>(maps, a);                                               \
-    } while (0)
-#define ORI_TC_LAUNCH_NW(D, E) do { if (nw == 8) ORI_TC_LAUNCH(D, E, 8); else ORI_TC_LAUNCH(D, E, 16); } while (0)
-    if (drop && elbo) ORI_TC_LAUNCH_NW(true, true);
-    else if (drop) ORI_TC_LAUNCH_NW(true, false);
-    else if (elbo) ORI_TC_LAUNCH_NW(false, true);
-    else ORI_TC_LAUNCH_NW(false, false);
+    int rc;
+#define ORI_TC_LAUNCH_NW(D, E) (nw == 8 ? launch_tc_variant<GENES, D, E, 8, PAIR>(maps, a, grid, st)     \
+                                        : launch_tc_variant<GENES, D, E, 16, PAIR>(maps, a, grid, st))
+    if (drop && elbo) rc = ORI_TC_LAUNCH_NW(true, true);
+    else if (drop) rc = ORI_TC_LAUNCH_NW(true, false);
+    else if (elbo) rc = ORI_TC_LAUNCH_NW(false, true);
+    else rc = ORI_TC_LAUNCH_NW(false, false);
 #undef ORI_TC_LAUNCH_NW
-#undef ORI_TC_LAUNCH
+    if (rc != ORI_OK) return rc;
     return check_launch(GENES ? "k_tc_pass(genes)" : "k_tc_pass(rows)");
+}
+
+template <bool GENES>
+static int launch_tc_pass(const ori_problem_t* P, int gen_old, cudaStream_t st) {
+    return use_pair() ? launch_tc_pass_p<GENES, true>(P, gen_old, st) : launch_tc_pass_p<GENES, false>(P, gen_old, st);
 }
 
 int launch_pass_rows_tc(const ori_problem_t* P, int gen_old, cudaStream_t st) { return launch_tc_pass<false>(P, gen_old, st); }

@@ -1,4 +1,5 @@
-for pair in 1 0; do
-  echo "== PAIR=$pair"
-  ORI_TC_PAIR=$pair python bench.py --steps 8 --warmup 3 --no-e2e --no-cpu 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], [(k['kernel'], round(k['ms'],2), round(k['achieved'])) for k in d['roofline']['kernels']], d['clocks'])"
-done
+CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu"
+$CMD > gpurun_out/plain_c4_pair.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c4_pair.csv $CMD > gpurun_out/ncu_l.log 2>&1
+$CMD > gpurun_out/plain_c4_pair2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_tc_pass -s 6 -c 2 -o gpurun_out/prof_tc_c4_pair -f $CMD > gpurun_out/ncu_f.log 2>&1
+tail -c 300 gpurun_out/plain_c4_pair.log; wc -l gpurun_out/launches_c4_pair.csv
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3

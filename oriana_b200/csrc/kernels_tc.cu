@@ -39,8 +39,10 @@ using namespace tc;
 #ifndef ORI_TC_PREFETCH_TM
 #define ORI_TC_PREFETCH_TM 1      // issue the next group's TMEM loads before computing the current group
 #endif
-#ifndef ORI_TC_BATCH
-#define ORI_TC_BATCH 0            // 1: load every group of the tile first, then compute them as one batch
+#ifndef ORI_TC_PINGPONG
+#define ORI_TC_PINGPONG 0         // 1: the element-wise warps form two groups that take alternate tiles (one TMEM stage
+                                  //    each).  Measured slower (rows 2.19 vs 1.97 ms at 100k x 20k): one warp per
+                                  //    scheduler cannot keep the MUFU pipe busy, and the group's tile takes 2900 cycles
 #endif
 #ifndef ORI_TC_AFETCH_EARLY
 #define ORI_TC_AFETCH_EARLY 0     // 1: fetch the next work item's own-side rows before the last tile's barrier waits (32 live registers)
@@ -154,6 +156,13 @@ __device__ __forceinline__ void kahan_add(float& s, float& c, float v) {
     s = u;
 }
 
+#ifdef ORI_TC_TRACE   // per-tile clock64 stamps of CTA 0 (two element-wise warps + the MMA warp), first 64 tiles
+__device__ long long g_tc_trace[2][3][64][12];
+#define ORI_STAMP(W, K_) do { if (trace_on && trace_tile < 64) g_tc_trace[GENES ? 1 : 0][W][trace_tile][K_] = clock64(); } while (0)
+#else
+#define ORI_STAMP(W, K_) do { } while (0)
+#endif
+
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
@@ -210,8 +219,9 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
     if (threadIdx.x == 0) {
         for (int s = 0; s < KST; ++s) { mbar_init(&bars[B_KFULL + s], 1); mbar_init(&bars[B_KEMPTY + s], 1); }
         for (int s = 0; s < TST; ++s) { mbar_init(&bars[B_TFULL + s], 1); mbar_init(&bars[B_TEMPTY + s], 1); }
-        for (int s = 0; s < XST; ++s) { mbar_init(&bars[B_XFULL + s], 1); mbar_init(&bars[B_XEMPTY + s], NEW); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&bars[B_SREADY + s], 1); mbar_init(&bars[B_PREADY + s], NEW * NCTA); }
+        constexpr int TILE_WARPS = ORI_TC_PINGPONG ? NEW / 2 : NEW;     // element-wise warps working on one tile
+        for (int s = 0; s < XST; ++s) { mbar_init(&bars[B_XFULL + s], 1); mbar_init(&bars[B_XEMPTY + s], TILE_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars[B_SREADY + s], 1); mbar_init(&bars[B_PREADY + s], TILE_WARPS * NCTA); }
         mbar_init(&bars[B_ACC_READY], 1);
         mbar_init(&bars[B_ACC_FREE], NEW * NCTA);
         mbar_init(&bars[B_A_READY], NEW * NCTA);
@@ -319,7 +329,13 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
         auto issue_P = [&](uint32_t it, bool first, bool last, int li) {
             const uint32_t s = it & 1, ts = it % TST;
             mbar_wait(&bars[B_PREADY + s], (it >> 1) & 1, 20, PAIR);
+#ifdef ORI_TC_TRACE
+            if (blockIdx.x == 0 && lane == 0 && it + 1 < 64) g_tc_trace[GENES ? 1 : 0][2][it + 1][3] = clock64();
+#endif
             mbar_wait(&bars[B_TFULL + ts], (it / TST) & 1, 24);
+#ifdef ORI_TC_TRACE
+            if (blockIdx.x == 0 && lane == 0 && it + 1 < 64) g_tc_trace[GENES ? 1 : 0][2][it + 1][4] = clock64();
+#endif
             if (first) mbar_wait(&bars[B_ACC_FREE], (li & 1) ^ 1, 21, PAIR);
             tc_fence_after();
             if (elect_one()) {
@@ -349,7 +365,12 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
         while (ti.valid(a)) {
             const uint32_t s = it & 1, ks_ = it % KST;
             const bool first = ti.first(), last = ti.last();
+#ifdef ORI_TC_TRACE
+            const bool trace_on = blockIdx.x == 0 && lane == 0; const uint32_t trace_tile = it;
+#endif
+            ORI_STAMP(2, 0);
             mbar_wait(&bars[B_KFULL + ks_], (it / KST) & 1, 23);
+            ORI_STAMP(2, 1);
             if (first) mbar_wait(&bars[B_A_READY], li & 1, 22, PAIR);
             tc_fence_after();
             if (elect_one()) {
@@ -372,7 +393,9 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 commit(&bars[B_KEMPTY + ks_]);
             }
             __syncwarp();
+            ORI_STAMP(2, 2);
             if (have_prev) issue_P(it - 1, prev_first, prev_last, prev_li);
+            ORI_STAMP(2, 5);
             have_prev = true; prev_first = first; prev_last = last; prev_li = li;
             if (last) ++li;
             ++it;
@@ -436,7 +459,15 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
         };
 
         const uint32_t sbase = smem_u32(smem);
-        constexpr int G = CW / 16;                    // groups of 16 columns per tile for this warp
+        // tile work split: without ping-pong all NEW warps share every tile (CW columns each); with it the warps
+        // form two groups taking alternate tiles, and a tile's 64 columns are split over the group's NEW/8 slices
+        constexpr bool PP = ORI_TC_PINGPONG != 0;
+        constexpr int TSL = PP ? NEW / 8 : SLICES;    // column slices of one tile
+        constexpr int CWT = TC_SW / TSL;              // tile columns per warp
+        constexpr int G = CWT / 16;                   // groups of 16 columns per tile for this warp
+        const int grp = PP ? ew / (NEW / 2) : 0;      // which tiles (parity of the CTA's tile counter)
+        const int tsl = PP ? (ew % (NEW / 2)) >> 2 : slice;
+        const int colbase = tsl * CWT;
         // gene pass: X is staged [cell][gene]; lane (gene) reads one float per cell, 128-byte swizzle undone here
         uint32_t xoff[8];
 #pragma unroll
@@ -444,7 +475,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
 
         TileIter ti;
         ti.init(a, NCTA, rank);
-        uint32_t s = 0, sph = 0, xs = 0, xph = 0;     // TMEM stage / X ring stage of the current tile and their phases
+        uint32_t it = 0;                              // tiles of this CTA so far: TMEM stage it & 1, X stage it % XST
         int li = 0;
         if (ti.valid(a)) { a_fetch(ti.own0); a_store(); }
         while (ti.valid(a)) {
@@ -463,11 +494,22 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             float cs = 0.f;
             float xl_s = 0.f, xl_c = 0.f, ent_s = 0.f, ent_c = 0.f;     // compensated fp32 sums over the item
             const int t_end = ti.t_end;
-            for (int t = ti.t_begin; t < t_end; ++t) {
+            const uint32_t it_last = it + (uint32_t)(t_end - ti.t_begin) - 1;
+            for (int t = ti.t_begin; t < t_end; ++t, ++it) {
+                if (PP && (int)(it & 1) != grp) continue;                // the other group's tile
                 const bool last = (t == t_end - 1);
+                const uint32_t s = it & 1, sph = (it >> 1) & 1, xs = it % XST, xph = (it / XST) & 1;
+#ifdef ORI_TC_TRACE
+                const bool trace_on = blockIdx.x == 0 && lane == 0 && (ew == 0 || ew == 4);
+                const uint32_t trace_tile = (uint32_t)(li * 100000 + (t - ti.t_begin));   // first item only
+                const int tw = ew >> 2;
+#endif
+                ORI_STAMP(tw, 0);
                 if (ORI_TC_AFETCH_EARLY && last && has_next) a_fetch(next_own0);
-                mbar_wait(&bars[B_XFULL + xs], xph, 30);                 // X tile (and lp) visible to this thread
-                mbar_wait(&bars[B_SREADY + s], sph, 31);                 // den / uv complete in TMEM
+                // X tile (and lp) visible to this thread; den / uv complete in TMEM
+                mbar_wait2(&bars[B_XFULL + xs], xph, &bars[B_SREADY + s], sph, 30);
+                ORI_STAMP(tw, 1);
+                ORI_STAMP(tw, 2);
                 tc_fence_after();
                 if (last && has_next) {             // every S of this item has completed: A can be replaced
                     if (!ORI_TC_AFETCH_EARLY) a_fetch(next_own0);
@@ -480,50 +522,52 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 const uint32_t tden = tlane + s * TM_STAGE, tuv = tden + 64;
                 float t_xl = 0.f, t_ent = 0.f;
 
-                uint32_t dr[G][16], ur[G][16];
-                float x[G][16];
+                uint32_t dr[2][16], ur[2][16];                           // two groups in flight, indexed by g & 1
+                float x[2][16];
                 auto load_x = [&](int g) {
-                    const int c0 = slice * CW + g * 16;
+                    const int c0 = colbase + g * 16;
+                    const int b = g & 1;
                     if (!GENES) {
                         const uint32_t base = xs_addr + (c0 >> 5) * 16384 + lrow * 128;
                         const int cb = (c0 & 31) >> 2;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const float4 v = lds128(base + (((cb + q) ^ (lrow & 7)) << 4));
-                            x[g][4 * q] = v.x; x[g][4 * q + 1] = v.y; x[g][4 * q + 2] = v.z; x[g][4 * q + 3] = v.w;
+                            x[b][4 * q] = v.x; x[b][4 * q + 1] = v.y; x[b][4 * q + 2] = v.z; x[b][4 * q + 3] = v.w;
                         }
                     } else {
 #pragma unroll
                         for (int e = 0; e < 16; ++e) {
                             const int i = c0 + e;
-                            x[g][e] = lds32(xs_addr + xoff[i & 7] + i * 128);
+                            x[b][e] = lds32(xs_addr + xoff[i & 7] + i * 128);
                         }
                     }
                 };
                 // general path: den guard, floors, ragged last tile (zigap.py:90, :133); rare
                 auto slow_group = [&](int g) {
-                    const int c0 = slice * CW + g * 16;
-                    tmem_ld16(tden + c0, dr[g]);
-                    if (DROPOUT) tmem_ld16(tuv + c0, ur[g]);
+                    const int c0 = colbase + g * 16;
+                    const int b = g & 1;
+                    tmem_ld16(tden + c0, dr[b]);
+                    if (DROPOUT) tmem_ld16(tuv + c0, ur[b]);
                     tmem_wait_ld();
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
-                        const float den = __uint_as_float(dr[g][e]);
-                        const float xe = x[g][e];
+                        const float den = __uint_as_float(dr[b][e]);
+                        const float xe = x[b][e];
                         const bool nz = xe != 0.f;
                         const float dg = den > 0.f ? den : 1.f;
                         float tt = dg, e2 = 0.f, D = 1.f;
                         if (DROPOUT) {
                             const float lp2 = GENES ? lp2j : lds32(lp_addr + 4 * (c0 + e));
                             const float fl = GENES ? flj : lds32(lp_addr + 256 + 4 * (c0 + e));
-                            e2 = fminf(__uint_as_float(ur[g][e]) - lp2, 127.f);
+                            e2 = fminf(__uint_as_float(ur[b][e]) - lp2, 127.f);
                             tt = nz ? dg : 1.f + ex2_approx(e2);
                             const float r = rcp_approx(tt);
                             D = fmaxf(nz ? 1.f : r, fl);
-                            dr[g][e] = tf32_bias(xe * r);
-                            ur[g][e] = tf32_bias(D);
+                            dr[b][e] = tf32_bias(xe * r);
+                            ur[b][e] = tf32_bias(D);
                         } else {
-                            dr[g][e] = tf32_bias(xe * rcp_approx(tt));
+                            dr[b][e] = tf32_bias(xe * rcp_approx(tt));
                         }
                         if (GENES && (c0 + e) < valid) {
                             if (DROPOUT) cs += D;
@@ -537,7 +581,8 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 };
                 // lean path: full tile, no floors; returns the smallest denominator seen
                 auto fast_group = [&](int g, float& g_cs, float& g_xl, float& g_ent) -> float {
-                    const int c0 = slice * CW + g * 16;
+                    const int c0 = colbase + g * 16;
+                    const int b = g & 1;
                     float cc[16];
                     if (DROPOUT && !GENES) {
 #pragma unroll
@@ -549,22 +594,22 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     float dmin = 1.f;
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
-                        const float den = __uint_as_float(dr[g][e]);
-                        const float xe = x[g][e];
+                        const float den = __uint_as_float(dr[b][e]);
+                        const float xe = x[b][e];
                         dmin = fminf(dmin, den);                  // den <= 0 (zigap.py:90): the group is redone below
                         float tt = den, uvp = 0.f;
                         if (DROPOUT) {
-                            uvp = __uint_as_float(ur[g][e]);                          // U_hat.V_hat * log2(e)
+                            uvp = __uint_as_float(ur[b][e]);                          // U_hat.V_hat * log2(e)
                             float tz = fmaf(ex2_approx(uvp), GENES ? cj : cc[e], 1.f);   // 1 + exp(uv - logit pi)
                             if (GENES && ELBO) tz = fminf(tz, 1.7014118e38f);
                             tt = sel_nz_a(xe, den, tz);
                         }
                         const float r = rcp_approx(tt);
-                        dr[g][e] = tf32_bias(xe * r);                                 // R = X / den; 0 where X == 0
+                        dr[b][e] = tf32_bias(xe * r);                                 // R = X / den; 0 where X == 0
                         float D = 1.f;
                         if (DROPOUT) {
                             D = sel_nz_b(xe, 1.f, r);                                 // zigap.py:131-136
-                            ur[g][e] = tf32_bias(D);
+                            ur[b][e] = tf32_bias(D);
                         }
                         if (GENES) {
                             if (DROPOUT) g_cs += D;
@@ -583,56 +628,26 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     return dmin;
                 };
 
-#if ORI_TC_BATCH
-                // all groups of the tile in one batch: one load phase, one long run of independent chains
                 if (!slow_tile) {
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        tmem_ld16(tden + slice * CW + 16 * g, dr[g]);
-                        if (DROPOUT) tmem_ld16(tuv + slice * CW + 16 * g, ur[g]);
-                    }
-                }
-#pragma unroll
-                for (int g = 0; g < G; ++g) load_x(g);
-                if (!slow_tile) tmem_wait_ld();
-                bool redo[G];
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    redo[g] = slow_tile;
-                    if (!slow_tile) {
-                        float g_cs = 0.f, g_xl = 0.f, g_ent = 0.f;
-                        const float dmin = fast_group(g, g_cs, g_xl, g_ent);
-                        redo[g] = __any_sync(0xffffffffu, dmin <= 0.f) != 0;
-                        if (GENES && !redo[g]) { cs += g_cs; t_xl += g_xl; t_ent += g_ent; }
-                    }
-                }
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const int c0 = slice * CW + g * 16;
-                    if (redo[g]) slow_group(g);
-                    tmem_st16(tden + c0, dr[g]);
-                    if (DROPOUT) tmem_st16(tuv + c0, ur[g]);
-                }
-#else
-                if (!slow_tile) {
-                    tmem_ld16(tden + slice * CW, dr[0]);
-                    if (DROPOUT) tmem_ld16(tuv + slice * CW, ur[0]);
+                    tmem_ld16(tden + colbase, dr[0]);
+                    if (DROPOUT) tmem_ld16(tuv + colbase, ur[0]);
                 }
                 load_x(0);
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    const int c0 = slice * CW + g * 16;
+                    const int c0 = colbase + g * 16;
                     bool redo = slow_tile;
                     if (!ORI_TC_PREFETCH_TM && !slow_tile && g > 0) {
-                        tmem_ld16(tden + c0, dr[g]);
-                        if (DROPOUT) tmem_ld16(tuv + c0, ur[g]);
+                        tmem_ld16(tden + c0, dr[g & 1]);
+                        if (DROPOUT) tmem_ld16(tuv + c0, ur[g & 1]);
                     }
                     if (!ORI_TC_PREFETCH_X && g > 0) load_x(g);
                     if (!slow_tile) {
                         tmem_wait_ld();
+                        if (g < 2) ORI_STAMP(tw, 3 + 3 * g);
                         if (ORI_TC_PREFETCH_TM && g + 1 < G) {            // next group's loads fly during this one
-                            tmem_ld16(tden + c0 + 16, dr[g + 1]);
-                            if (DROPOUT) tmem_ld16(tuv + c0 + 16, ur[g + 1]);
+                            tmem_ld16(tden + c0 + 16, dr[(g + 1) & 1]);
+                            if (DROPOUT) tmem_ld16(tuv + c0 + 16, ur[(g + 1) & 1]);
                         }
                     }
                     if (ORI_TC_PREFETCH_X && g + 1 < G) load_x(g + 1);
@@ -643,20 +658,27 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                         if (GENES && !redo) { cs += g_cs; t_xl += g_xl; t_ent += g_ent; }
                     }
                     if (redo) slow_group(g);
-                    tmem_st16(tden + c0, dr[g]);
-                    if (DROPOUT) tmem_st16(tuv + c0, ur[g]);
+                    if (g < 2) ORI_STAMP(tw, 4 + 3 * g);
+                    tmem_st16(tden + c0, dr[g & 1]);
+                    if (DROPOUT) tmem_st16(tuv + c0, ur[g & 1]);
+                    if (g < 2) ORI_STAMP(tw, 5 + 3 * g);
                 }
-#endif
                 if (GENES && ELBO) { kahan_add(xl_s, xl_c, t_xl); if (DROPOUT) kahan_add(ent_s, ent_c, t_ent); }
                 tmem_wait_st();
+                ORI_STAMP(tw, 9);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
                     if (PAIR) mbar_arrive_cluster(&bars[B_PREADY + s], 0); else mbar_arrive(&bars[B_PREADY + s]);
                     mbar_arrive(&bars[B_XEMPTY + xs]);
                 }
-                s ^= 1; sph ^= (s == 0);
-                if (++xs == XST) { xs = 0; xph ^= 1; }
+                ORI_STAMP(tw, 10);
+            }
+            if (PP && has_next && (int)(it_last & 1) != grp) {           // the other group had the item's last tile:
+                mbar_wait(&bars[B_SREADY + (it_last & 1)], (it_last >> 1) & 1, 33);   // every S of the item has run
+                tc_fence_after();
+                a_fetch(next_own0);
+                a_store();
             }
             double acc_xl = (double)xl_s - (double)xl_c, acc_ent = (double)ent_s - (double)ent_c;
             // ---- epilogue of the work item: accumulators -> global (atomics: the sweep of one own tile is split)
@@ -917,6 +939,12 @@ template <bool GENES>
 static int launch_tc_pass(const ori_problem_t* P, int gen_old, cudaStream_t st) {
     return use_pair() ? launch_tc_pass_p<GENES, true>(P, gen_old, st) : launch_tc_pass_p<GENES, false>(P, gen_old, st);
 }
+
+#ifdef ORI_TC_TRACE
+extern "C" int ori_debug_trace(long long* out) {
+    return cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(g_tc_trace)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int launch_pass_rows_tc(const ori_problem_t* P, int gen_old, cudaStream_t st) { return launch_tc_pass<false>(P, gen_old, st); }
 int launch_pass_genes_tc(const ori_problem_t* P, int gen_old, cudaStream_t st) { return launch_tc_pass<true>(P, gen_old, st); }

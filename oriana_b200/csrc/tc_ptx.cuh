@@ -76,6 +76,23 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// Wait on two barriers whose completion latencies should overlap (both try_waits are in flight together).
+__device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t par_a, uint64_t* bar_b, uint32_t par_b, int tag = 0) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4;\n\t"
+        "and.pred p, p, q;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar_a)), "r"(par_a), "r"(smem_u32(bar_b)), "r"(par_b)
+        : "memory");
+    if (ok) return;
+    mbar_wait(bar_a, par_a, tag);
+    mbar_wait(bar_b, par_b, tag + 1);
+}
+
 // ---- TMA ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");

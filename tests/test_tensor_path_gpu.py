@@ -111,3 +111,51 @@ def test_tensor_all_zero_gene_and_cell(cuda_lib):
         assert np.isfinite(got).all()
         assert relerr(got, ref[k]) < 3e-3, k
     assert abs(m.pi_d[5] - ref['pi_d'][5]) < 1e-12 and m.pi_d[5] < 1e-9
+
+
+def test_tensor_path_config2_matches_oracle(cuda_lib):
+    """BASELINE.json configs[1] (10k x 2k, K=10) at full size: two CAVI steps of the tensor path against the
+    oracle port on the same counts and initial state."""
+    from oracle import cavi_numpy as cn
+    X = cn.synth_counts(10_000, 2_000, 10, seed=4)
+    s = cn.init_state(X, 10, np.random.default_rng(2), 'zigap')
+    m = make_model(s, quirk=False, tensor=True)
+    assert m.uses_tensor_path
+    ref = {k: v.copy() for k, v in s.items()}
+    want = [cn.elbo(ref, guard32=True)]
+    for _ in range(2):
+        m.step(); cn.step(ref, quirk=False)
+        want.append(cn.elbo(ref))
+    for k in FACTORS:
+        assert relerr(getattr(m, k).asarray(), ref[k]) < 1e-3, k
+    for k in HYPER + ('pi_d',):
+        assert relerr(getattr(m, k).asarray(), ref[k]) < 1e-4, k
+    got = m.elbo_trace
+    assert np.max(np.abs(got - np.asarray(want)) / np.abs(want)) < 1e-4, (got, want)
+
+
+def test_single_cta_variant_matches_pair_variant(cuda_lib):
+    """ORI_TC_PAIR=0 (single-CTA kernels, kept for A/B runs) against the default CTA-pair kernels: same state
+    after three steps up to accumulation order.  The switch is read once per process, hence the subprocess."""
+    import os, subprocess, sys, tempfile
+    from oriana.models import ZIGaP
+    from oriana.singlecell import synth_counts_device
+    n, p, K = 4000, 1700, 12
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from oriana.models import ZIGaP\nfrom oriana.singlecell import synth_counts_device\n"
+        "X = synth_counts_device(%d, %d, %d, seed=8)\nnp.random.seed(5)\n"
+        "m = ZIGaP(X[:, :%d], k=%d, use_factors=False, tensor=True)\n"
+        "[m.step() for _ in range(3)]\n"
+        "np.savez(sys.argv[1], **{k: v for k, v in m.state_dict().items() if k != 'iterations'}, elbo=m.elbo_trace)\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), n, p, K, p, K)
+    out = {}
+    for pair in ('1', '0'):
+        with tempfile.TemporaryDirectory() as d:
+            f = os.path.join(d, 'o.npz')
+            env = dict(os.environ, ORI_TC_PAIR=pair)
+            subprocess.run([sys.executable, '-c', code, f], check=True, env=env, timeout=300)
+            out[pair] = dict(np.load(f))
+    for k in out['1']:
+        tol = 1e-6 if k == 'elbo' else 2e-4
+        assert relerr(out['0'][k], out['1'][k]) < tol, k

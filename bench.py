@@ -121,6 +121,9 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return 0
+        # torchrun pins OMP_NUM_THREADS=1 for its workers: the CPU arm gets every host core (set before numpy loads)
+        for var in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+            os.environ[var] = str(os.cpu_count() or 1)
         steps = max(1, args.steps)
         val, cores, sample, dt = cpu_reference_run(n, p, K, steps, W)
         print(json.dumps({
@@ -255,6 +258,8 @@ def main():
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic', 'iters_per_sec': 1e3 / ms_step,
             'config': {'workload': workload_name(args.config, n, p, K), 'n': n, 'p': p, 'K': K,
+                       'arithmetic': 'fp32 state; tensor contractions 3xTF32 (denominator, U.V^T) and TF32 operands '
+                                     '(R, D_hat) with fp32 accumulation in TMEM; ELBO partial sums fp64',
                        'cells_per_rank': rows, 'parallelism': 'cells sharded over %d rank(s); 2 sum-allreduces/iter' % world,
                        'l2': 'X per rank is %.1f GB, far larger than the 126 MB L2: no flush between steps' % (alg_bytes / 1e9)},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'clocks': clocks,

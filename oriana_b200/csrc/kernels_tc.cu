@@ -149,6 +149,11 @@ __device__ __forceinline__ float sel_pos(float w, float a) {   // w > 0 ? a : 0
     asm("{\n\t.reg .pred q;\n\tsetp.gt.f32 q, %1, 0f00000000;\n\tselp.f32 %0, %2, 0f00000000, q;\n\t}" : "=f"(d) : "f"(w), "f"(a));
     return d;
 }
+__device__ __forceinline__ float is_zero_f(float x) {          // 1.0f where x == 0, else 0.0f (one FSET)
+    float d;
+    asm("set.eq.f32.f32 %0, %1, 0f00000000;" : "=f"(d) : "f"(x));
+    return d;
+}
 __device__ __forceinline__ void kahan_add(float& s, float& c, float v) {
     const float y = v - c;
     const float u = s + y;
@@ -484,13 +489,15 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             const int next_item = ti.item + ti.stride;
             const bool has_next = next_item < a.n_items;
             const int next_own0 = ((next_item % a.n_own_units) * NCTA + rank) * TC_OWN;
-            float lp2j = 0.f, flj = 0.f, cj = 0.f;
+            float lp2j = 0.f, flj = 0.f, cj = 0.f, ulim = 127.f;
             if (GENES && DROPOUT) {                   // padded arrays: always in range
                 lp2j = a.lp2w[own_idx]; flj = a.flw[own_idx];
                 cj = ex2_approx(-lp2j);               // (1 - pi) / pi
+                ulim = fminf(127.f, 127.f + lp2j);    // uv * log2(e) beyond this: D_hat = 0 either way
             }
-            // genes / columns with a floor (pi <= 0, zigap.py:133) take the general path
-            const bool slow_item = DROPOUT && (GENES ? (__any_sync(0xffffffffu, flj != 0.f) != 0) : any_floor);
+            // genes / columns with a floor (pi <= 0, zigap.py:133) or with the initial indicator state (logit pi = -inf,
+            // zigap.py:77) take the general path
+            const bool slow_item = DROPOUT && (GENES ? (__any_sync(0xffffffffu, flj != 0.f || lp2j == -INFINITY) != 0) : any_floor);
             float cs = 0.f;
             float xl_s = 0.f, xl_c = 0.f, ent_s = 0.f, ent_c = 0.f;     // compensated fp32 sums over the item
             const int t_end = ti.t_end;
@@ -600,8 +607,8 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                         float tt = den, uvp = 0.f;
                         if (DROPOUT) {
                             uvp = __uint_as_float(ur[b][e]);                          // U_hat.V_hat * log2(e)
-                            float tz = fmaf(ex2_approx(uvp), GENES ? cj : cc[e], 1.f);   // 1 + exp(uv - logit pi)
-                            if (GENES && ELBO) tz = fminf(tz, 1.7014118e38f);
+                            if (GENES && ELBO) uvp = fminf(uvp, ulim);                // keeps 2^uv, tz and e2 finite
+                            const float tz = fmaf(ex2_approx(uvp), GENES ? cj : cc[e], 1.f);   // 1 + exp(uv - logit pi)
                             tt = sel_nz_a(xe, den, tz);
                         }
                         const float r = rcp_approx(tt);
@@ -617,9 +624,9 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                                 const float l2 = lg2_approx(tt);
                                 g_xl = fmaf(xe, l2, g_xl);
                                 if (DROPOUT) {
-                                    const float e2 = fminf(uvp - lp2j, 127.f);
+                                    const float e2 = uvp - lp2j;                      // <= 127 (uvp was clamped)
                                     const float w = 1.f - D;                          // 0 on non-zeros
-                                    g_ent += sel_pos(w, l2);
+                                    g_ent = fmaf(is_zero_f(xe), l2, g_ent);           // log2(1 + 2^e2) on zeros
                                     g_ent = fmaf(-w, e2, g_ent);
                                 }
                             }

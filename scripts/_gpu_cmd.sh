@@ -1,2 +1,2 @@
-timeout 600 python -m pytest tests/test_tensor_path_gpu.py -x -q -m gpu 2>&1 | tail -4
-timeout 200 python scripts/gpu_time_models.py 2>&1 | grep "elbo=True"
+( time python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 10 --warmup 3 ) > gpurun_out/bench_c4_n8.json 2> gpurun_out/bench_c4_n8.err
+tail -c 2400 gpurun_out/bench_c4_n8.json; tail -6 gpurun_out/bench_c4_n8.err

@@ -63,6 +63,35 @@ def main():
         np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
         print(name, 'written', {k: getattr(v, 'shape', None) for k, v in list(out.items())[:4]})
 
+    # SparseZIGaP (sparse_zigap.py): trajectories + the reference's own convergence metrics (base.py:58-82)
+    from oriana.models import SparseZIGaP
+    for name, n, p, K, rec in (('sparse_k4', 120, 300, 4, (1, 2, 5)), ('sparse_ragged', 157, 203, 6, (1, 3, 8))):
+        X = cn.synth_counts(n, p, K, seed=len(name) * 5 + p)
+        np.random.seed(2)
+        m = SparseZIGaP(CountMatrix(X), k=K, use_factors=False, tau=0.5)
+        out = {'model': 'SparseZIGaP', 'K': K, 'tau': 0.5, 'steps': np.asarray(rec)}
+        s0 = refshim.snapshot(m)
+        out['X'] = s0.pop('X').astype(np.int32)
+        for k, v in s0.items():
+            out['s0_' + k] = v.astype(np.float32) if k == 'p_d' else v
+        lU = np.ascontiguousarray(m.log_U_hat); lV = np.ascontiguousarray(m.log_Vprime_hat)
+        St = (m.p_s[:] > m.tau).astype(np.float32)
+        Z1 = np.empty((n, K), np.float32); Z2 = np.empty((p, K), np.float32); Z3 = np.empty((p, K), np.float32)
+        SparseZIGaP.compute_Z_q_expectations(Z1, Z2, Z3, lU, lV, St, np.ascontiguousarray(m.S_hat), m.D_hat,
+                                             m.X[:].astype(np.float32))
+        out.update(z_log_U_hat=lU, z_log_Vp_hat=lV, z_S_tilde=St, z_S_hat=np.asarray(m.S_hat), z_DSZ=Z1, z_DZ=Z2, z_DZl=Z3)
+        for t in range(1, max(rec) + 1):
+            m.step()
+            if t in rec:
+                st = refshim.snapshot(m); st.pop('X')
+                for k, v in st.items():
+                    out['s%d_%s' % (t, k)] = v.astype(np.float32) if k == 'p_d' else v
+                dev = m.reconstruction_deviance()          # mutates node buffers only (base.py:58-69)
+                out['s%d_deviance' % t] = np.float64(dev)
+                out['s%d_explained' % t] = np.float64(m.explained_deviance())
+        np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+        print(name, 'written')
+
     # special-function known answers, produced by the reference's own utils (utils.py:9-51)
     x = np.concatenate([np.asarray([0.54, 6.2, 1.2, 0.3, 7.9, 4.5, 2.1]),          # test/test.py:24
                         np.logspace(-15, 8, 70), np.asarray([1.0, 2.0, 0.5, 1e-3, 3.0, 5.999, 6.0, 6.001])])

@@ -45,11 +45,12 @@ def release_reference():
 
 STATE_KEYS_ZIGAP = ('a1', 'a2', 'b1', 'b2', 'p_d', 'pi_d', 'alpha1', 'alpha2', 'beta1', 'beta2')
 STATE_KEYS_GAP = ('a1', 'a2', 'b1', 'b2', 'alpha1', 'alpha2', 'beta1', 'beta2')
+STATE_KEYS_SPARSE = STATE_KEYS_ZIGAP + ('p_s', 'pi_s')
 
 
 def snapshot(model):
     """Copy the state vector out of a constructed reference model."""
-    keys = STATE_KEYS_ZIGAP if hasattr(model, 'p_d') else STATE_KEYS_GAP
+    keys = STATE_KEYS_SPARSE if hasattr(model, 'p_s') else (STATE_KEYS_ZIGAP if hasattr(model, 'p_d') else STATE_KEYS_GAP)
     s = {k: np.array(getattr(model, k)[:], dtype=np.float64, copy=True) for k in keys}
     s['X'] = np.array(model.X[:], copy=True)
     return s

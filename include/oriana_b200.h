@@ -92,8 +92,8 @@ typedef struct ori_problem {
     double* elbo_trace;    /* [trace_cap]                                                */
 
     /* tensor path (tcgen05/TMA kernels, csrc/kernels_tc.cu): caller-owned scratch of at least
-     * ori_tc_workspace_floats(n_rows, p) floats, 128-byte aligned; NULL selects the CUDA-core kernels.
-     * Needs KP == 32 (any K <= 32, zero padded). */
+     * ori_tc_workspace_floats(n_rows, p, KP) floats, 128-byte aligned; NULL selects the CUDA-core kernels.
+     * Needs KP == 32 (K <= 32) or KP == 64 (K <= 64), zero padded. */
     float* tc_ws;
     int64_t tc_ws_floats;
 } ori_problem_t;
@@ -117,8 +117,8 @@ int ori_gamma_expect_f32(const float* a1, const float* a2, float* E, float* Elog
                          int64_t count, void* stream);
 
 /* ---- the CAVI iteration, device-resident state -------------------------------------------------- */
-/* Scratch floats the tensor path needs for a rank owning n_rows cells of p genes. */
-int64_t ori_tc_workspace_floats(int64_t n_rows, int32_t p);
+/* Scratch floats the tensor path needs for a rank owning n_rows cells of p genes at padded latent dimension KP. */
+int64_t ori_tc_workspace_floats(int64_t n_rows, int32_t p, int32_t KP);
 /* 1 when the calls below will take the tensor path for this problem, 0 for the CUDA-core kernels. */
 int ori_uses_tensor_path(const ori_problem_t* P);
 /* Validate a problem description (shapes, alignment, null pointers). */

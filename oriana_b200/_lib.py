@@ -44,7 +44,7 @@ _SIGNATURES = {
     'ori_device_check': ([C.c_int], C.c_int),
     'ori_special_f64': ([C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p], C.c_int),
     'ori_gamma_expect_f32': ([C.c_void_p] * 5 + [C.c_int64, C.c_void_p], C.c_int),
-    'ori_tc_workspace_floats': ([C.c_int64, C.c_int32], C.c_int64),
+    'ori_tc_workspace_floats': ([C.c_int64, C.c_int32, C.c_int32], C.c_int64),
     'ori_uses_tensor_path': ([_PP], C.c_int),
     'ori_problem_check': ([_PP], C.c_int),
     'ori_count_stats': ([_PP, C.c_void_p], C.c_int),

@@ -145,7 +145,7 @@ int ori_problem_check(const ori_problem_t* P) {
     if (P->K > 64) return set_error(ORI_EUNSUPPORTED, "K=%d > 64 is not supported", P->K);
     if (P->KP < P->K || (P->KP != 8 && P->KP != 16 && P->KP != 32 && P->KP != 64))
         return set_error(ORI_EINVAL, "KP=%d must be 8, 16, 32 or 64 and >= K=%d", P->KP, P->K);
-    if (P->tc_ws && (((uintptr_t)P->tc_ws & 127) || P->tc_ws_floats < tc_workspace_floats(P->n_rows, P->p)))
+    if (P->tc_ws && (((uintptr_t)P->tc_ws & 127) || P->tc_ws_floats < tc_workspace_floats(P->n_rows, P->p, P->KP)))
         return set_error(ORI_EINVAL, "tc_ws must be 128-byte aligned and hold ori_tc_workspace_floats() floats");
     if (P->ldx < P->p || (P->ldx & 3)) return set_error(ORI_EINVAL, "ldx=%lld must be >= p and a multiple of 4", (long long)P->ldx);
     if (P->n_total < P->n_rows || P->n_total <= 0) return set_error(ORI_EINVAL, "n_total=%lld < n_rows", (long long)P->n_total);
@@ -196,7 +196,7 @@ static int pass_genes_any(const ori_problem_t* P, int gen_old, cudaStream_t st) 
     return launch_pass_genes_tc(P, gen_old, st);
 }
 
-int64_t ori_tc_workspace_floats(int64_t n_rows, int32_t p) { return tc_workspace_floats(n_rows, p); }
+int64_t ori_tc_workspace_floats(int64_t n_rows, int32_t p, int32_t KP) { return tc_workspace_floats(n_rows, p, KP); }
 
 int ori_uses_tensor_path(const ori_problem_t* P) { return (P && tc_eligible(P)) ? 1 : 0; }
 

@@ -43,7 +43,7 @@ int launch_dropout_posterior(const ori_problem_t* P, int gen, float* out, long l
                              long long row0, long long nrows, cudaStream_t st);
 
 // kernels_tc.cu
-long long tc_workspace_floats(long long n_rows, int p);
+long long tc_workspace_floats(long long n_rows, int p, int KP);
 bool tc_eligible(const ori_problem_t* P);
 int launch_tc_prep_genes(const ori_problem_t* P, cudaStream_t st);
 int launch_tc_prep_rows(const ori_problem_t* P, int gen_old, cudaStream_t st);

@@ -2,7 +2,8 @@
 // TMA-staged tiles, tcgen05.mma kind::tf32 with fp32 accumulators in TMEM, the ratio / dropout posterior
 // computed between the two groups of contractions on the TMEM-resident tile (A operands from TMEM).
 //
-// Per tile of 128 "own" x 64 "sweep" entries (own = cells in the row pass, genes in the gene pass):
+// Per tile of 128 "own" x SW "sweep" entries (own = cells in the row pass, genes in the gene pass; SW = 64 for a
+// padded latent dimension KP = 32, SW = 32 for KP = 64, so that the tile always fits the same TMEM / smem plan):
 //   S:  den = eO . eS^T     (3xTF32: hi.hi + hi.lo + lo.hi)          zigap.py:86-90
 //       uv  = Oh . Sh^T     (3xTF32)                                 zigap.py:131 (U_hat V_hat^T)
 //   E:  R = X / den ; D = X != 0 ? 1 : max(sigmoid(lp - uv), floor)  zigap.py:91-92, :131-136
@@ -12,7 +13,7 @@
 //
 // Data movement per CTA (one CTA per SM, persistent over work items = own tile x chunk of the sweep):
 //   own side   the 128 own rows of exp(E log .) and E[.] are read once per work item from the raw factor
-//              arrays, split hi/lo in registers and parked in TMEM (128 columns): every S contraction takes
+//              arrays, split hi/lo in registers and parked in TMEM (4 * KP columns): every S contraction takes
 //              its A operand from TMEM, so shared memory only carries the streamed side;
 //   sweep side three independent TMA rings: K-major hi/lo operands (consumed by S, freed as soon as S has
 //              run), transposed operands (consumed by P) and the X tile (+ logit pi) for the element-wise
@@ -25,10 +26,10 @@
 // is a cta_group::2 instruction of M = 256 issued by the pair's leader, each CTA stages only half of every
 // streamed operand tile and TMA credits both halves to the leader's barrier; completion is multicast back.
 //
-// Warp roles (64 + 32*NEW threads):
+// Warp roles (320 threads):
 //   warp 0       TMA producer (whole warp walks the rings, one elected lane issues)
 //   warp 1       MMA issuer + TMEM owner (warp-uniform control flow, one elected lane issues)
-//   warps 2..    NEW element-wise warps; warp w owns TMEM lanes 32*(w%4).. and 64/(NEW/4) of the 64 columns
+//   warps 2..9   element-wise warps; warp w owns TMEM lanes 32*(w%4).. and half of the tile's columns
 #include <cstdlib>
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -36,47 +37,45 @@
 namespace ori {
 using namespace tc;
 
-#ifndef ORI_TC_PREFETCH_TM
-#define ORI_TC_PREFETCH_TM 1      // issue the next group's TMEM loads before computing the current group
-#endif
-#ifndef ORI_TC_PINGPONG
-#define ORI_TC_PINGPONG 0         // 1: the element-wise warps form two groups that take alternate tiles (one TMEM stage
-                                  //    each).  Measured slower (rows 2.19 vs 1.97 ms at 100k x 20k): one warp per
-                                  //    scheduler cannot keep the MUFU pipe busy, and the group's tile takes 2900 cycles
-#endif
-#ifndef ORI_TC_AFETCH_EARLY
-#define ORI_TC_AFETCH_EARLY 0     // 1: fetch the next work item's own-side rows before the last tile's barrier waits (32 live registers)
-#endif
-#ifndef ORI_TC_PREFETCH_X
-#define ORI_TC_PREFETCH_X 0       // same for its X values (costs 16 registers)
-#endif
-
 constexpr int TC_OWN = 128;
-constexpr int TC_SW = 64;
-constexpr int TC_KP_CONST = 32;     // latent dimension of the tensor path (K <= 32, zero padded)
+constexpr int NEW = 8;                // element-wise warps (more of them only get 96 registers each: measured slower)
+constexpr int SLICES = NEW / 4;       // element-wise warps per TMEM lane quarter
+constexpr int TC_THREADS = 64 + 32 * NEW;
 
-// Shared-memory plan.  PAIR = the CTA-pair variant (cta_group::2, M = 256 over two SMs): each CTA stages only
-// half of every streamed operand tile (the pair's MMA reads both halves), which halves the TMA fill and the
-// tensor-core operand reads per SM and leaves room for deeper rings.
-template <bool PAIR>
+// Plan of one kernel variant.  KP: padded latent dimension (32 or 64).  PAIR: the CTA-pair variant (cta_group::2,
+// M = 256 over two SMs): each CTA stages only half of every streamed operand tile (the pair's MMA reads both
+// halves), which halves the TMA fill and the tensor-core operand reads per SM and leaves room for deeper rings.
+template <int KP, bool PAIR>
 struct Cfg {
+    static_assert(KP == 32 || KP == 64, "tensor path: KP is 32 or 64");
     static constexpr int NCTA = PAIR ? 2 : 1;
+    static constexpr int SW = 2048 / KP;                  // sweep entries per tile: 64 (KP 32) or 32 (KP 64)
+    static constexpr int KB = KP / 32;                    // 128-byte K blocks of a K-major row
     static constexpr int KST = PAIR ? 3 : 2;              // ring depths
     static constexpr int TST = PAIR ? 3 : 2;
     static constexpr int XST = PAIR ? 4 : 3;
-    static constexpr uint32_t K_ARR = 8192 / NCTA;        // one K-major array [64 / NCTA sweep rows x 32]
+    // K-major operand array of one tile: [KB blocks][SW / NCTA sweep rows][32 floats], 128-byte swizzled
+    static constexpr uint32_t K_BLK = (SW / NCTA) * 128;
+    static constexpr uint32_t K_ARR = KB * K_BLK;         // = 8192 / NCTA for both KP
     static constexpr uint32_t K_STAGE = 4 * K_ARR;        // hi(e) lo(e) hi(E) lo(E)
-    static constexpr uint32_t T_CHUNK = 4096 / NCTA;      // [32 / NCTA latent rows x 32 sweep columns]
-    static constexpr uint32_t T_ARR = 2 * T_CHUNK;        // two chunks = 64 sweep columns
+    // transposed operand array of one tile: [SW / 32 chunks][KP / NCTA latent rows][32 sweep columns]
+    static constexpr uint32_t T_CHUNK = (KP / NCTA) * 128;
+    static constexpr uint32_t T_ARR = (SW / 32) * T_CHUNK;   // = 8192 / NCTA for both KP
     static constexpr uint32_t T_STAGE = 2 * T_ARR;        // transposed e and transposed E
-    static constexpr uint32_t X_STAGE = 32768;            // X tile
-    static constexpr uint32_t LP_STAGE = 768;             // lp2[64] | floor[64] | (1-pi)/pi [64]
+    static constexpr uint32_t X_STAGE = TC_OWN * SW * 4;  // X tile
+    static constexpr uint32_t LP_STAGE = 3 * SW * 4;      // lp2[SW] | floor[SW] | (1-pi)/pi [SW]
     static constexpr uint32_t OFF_K = 0;
     static constexpr uint32_t OFF_T = OFF_K + KST * K_STAGE;
     static constexpr uint32_t OFF_X = OFF_T + TST * T_STAGE;
     static constexpr uint32_t OFF_LP = OFF_X + XST * X_STAGE;
     static constexpr uint32_t OFF_BAR = OFF_LP + XST * LP_STAGE;
     static constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;   // + barriers + alignment slack
+    // TMEM columns: 2 stages of [den/R SW | uv/D SW], accumulators [acc1 KP | acc2 KP], own operands 4 x KP
+    static constexpr uint32_t TM_STAGE = 2 * SW;
+    static constexpr uint32_t TM_ACC = 2 * TM_STAGE;
+    static constexpr uint32_t TM_A = TM_ACC + 2 * KP;
+    static constexpr uint32_t TM_COLS = 512;
+    static_assert(TM_A + 4 * KP <= TM_COLS, "TMEM plan");
     // mbarriers.  With PAIR, KFULL / TFULL / PREADY / ACC_FREE / A_READY are used in the leader CTA only
     // (the peer's TMA bytes and warp arrivals are credited there); the others are per CTA.
     static constexpr int B_KFULL = 0, B_KEMPTY = B_KFULL + KST, B_TFULL = B_KEMPTY + KST, B_TEMPTY = B_TFULL + TST,
@@ -87,25 +86,20 @@ struct Cfg {
     static_assert(SMEM_BYTES <= 232448, "shared memory");
 };
 
-constexpr uint32_t TM_STAGE = 128;   // TMEM columns per stage: den/R [0,64) | uv/D [64,128)
-constexpr uint32_t TM_ACC = 256;     // acc1 [256,288) | acc2 [288,320)
-constexpr uint32_t TM_A = 320;       // own-side operands: hi(e) lo(e) hi(E) lo(E), 32 columns each
-constexpr uint32_t TM_COLS = 512;
-
 struct TcMaps { CUtensorMap swK, swT, X; };
 
 struct TcArgs {
     long long own_total, sw_total;   // valid extents (cells / genes)
     long long sw_pad;                // padded sweep extent (multiple of 128): q-th operand array starts at row q*pad
     int n_own_tiles, n_own_units, n_chunks, tiles_per_chunk, n_sw_tiles, n_items;   // unit = own tile (pair of own tiles with PAIR)
-    const float* own_e;              // [own_total x 32] exp(E log .) of the own side (raw factor array)
-    const float* own_E;              // [own_total x 32] E[.] of the own side
+    const float* own_e;              // [own_total x KP] exp(E log .) of the own side (raw factor array)
+    const float* own_E;              // [own_total x KP] E[.] of the own side
     const float* lp2w;               // [genes_pad] logit(pi) * log2(e); -inf: D_hat = (X>0)
     const float* flw;                // [genes_pad] floor (1e-10 where pi <= 0)
     const float* cw;                 // [genes_pad] exp(-logit(pi)) = (1 - pi) / pi
     const int* any_floor;            // != 0 when some gene has a floor
-    float* acc1;                     // [own_total x 32]  sum_sweep R  * S1
-    float* acc2;                     // [own_total x 32]  sum_sweep D  * S2
+    float* acc1;                     // [own_total x KP]  sum_sweep R  * S1
+    float* acc2;                     // [own_total x KP]  sum_sweep D  * S2
     double* colsum;                  // gene pass: [genes] += sum_i D_hat
     double* part64;                  // gene pass: ELBO partial sums
 };
@@ -144,11 +138,6 @@ __device__ __forceinline__ float sel_nz_b(float x, float a, float b) {
         : "=f"(d) : "f"(x), "f"(a), "f"(b));
     return d;
 }
-__device__ __forceinline__ float sel_pos(float w, float a) {   // w > 0 ? a : 0
-    float d;
-    asm("{\n\t.reg .pred q;\n\tsetp.gt.f32 q, %1, 0f00000000;\n\tselp.f32 %0, %2, 0f00000000, q;\n\t}" : "=f"(d) : "f"(w), "f"(a));
-    return d;
-}
 __device__ __forceinline__ float is_zero_f(float x) {          // 1.0f where x == 0, else 0.0f (one FSET)
     float d;
     asm("set.eq.f32.f32 %0, %1, 0f00000000;" : "=f"(d) : "f"(x));
@@ -160,13 +149,6 @@ __device__ __forceinline__ void kahan_add(float& s, float& c, float v) {
     c = (u - s) - y;
     s = u;
 }
-
-#ifdef ORI_TC_TRACE   // per-tile clock64 stamps of CTA 0 (two element-wise warps + the MMA warp), first 64 tiles
-__device__ long long g_tc_trace[2][3][64][12];
-#define ORI_STAMP(W, K_) do { if (trace_on && trace_tile < 64) g_tc_trace[GENES ? 1 : 0][W][trace_tile][K_] = clock64(); } while (0)
-#else
-#define ORI_STAMP(W, K_) do { } while (0)
-#endif
 
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
@@ -198,23 +180,25 @@ struct TileIter {
     }
 };
 
-template <bool GENES, bool DROPOUT, bool ELBO, int NEW, bool PAIR>
-__global__ void __launch_bounds__(64 + 32 * NEW, 1)
+template <bool GENES, bool DROPOUT, bool ELBO, bool PAIR, int KP>
+__global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
 {
-    using C = Cfg<PAIR>;
-    constexpr int NCTA = C::NCTA;
+    using C = Cfg<KP, PAIR>;
+    constexpr int NCTA = C::NCTA, SW = C::SW;
     constexpr int KST = C::KST, TST = C::TST, XST = C::XST;
     constexpr uint32_t K_STAGE = C::K_STAGE, T_STAGE = C::T_STAGE, X_STAGE = C::X_STAGE, LP_STAGE = C::LP_STAGE;
     constexpr uint32_t OFF_K = C::OFF_K, OFF_T = C::OFF_T, OFF_X = C::OFF_X, OFF_LP = C::OFF_LP, OFF_BAR = C::OFF_BAR;
+    constexpr uint32_t TM_STAGE = C::TM_STAGE, TM_ACC = C::TM_ACC, TM_A = C::TM_A, TM_COLS = C::TM_COLS;
     constexpr int B_KFULL = C::B_KFULL, B_KEMPTY = C::B_KEMPTY, B_TFULL = C::B_TFULL, B_TEMPTY = C::B_TEMPTY,
                   B_XFULL = C::B_XFULL, B_XEMPTY = C::B_XEMPTY, B_SREADY = C::B_SREADY, B_PREADY = C::B_PREADY,
                   B_ACC_READY = C::B_ACC_READY, B_ACC_FREE = C::B_ACC_FREE, B_A_READY = C::B_A_READY, NBARS = C::NBARS;
-    const int rank = PAIR ? (int)cluster_ctarank() : 0;      // CTA of the pair; rank 0 leads (issues every MMA)
-    constexpr int SLICES = NEW / 4;           // element-wise warps per TMEM lane quarter
-    constexpr int CW = TC_SW / SLICES;        // tile columns per element-wise warp
+    constexpr int CW = SW / SLICES;           // tile columns per element-wise warp: 32 or 16
+    constexpr int G = CW / 16;                // groups of 16 columns per tile for one warp
     constexpr int NQ = DROPOUT ? 4 : 2;       // K-major operand arrays in use
     constexpr int NT = DROPOUT ? 2 : 1;       // transposed operand arrays in use
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;      // CTA of the pair; rank 0 leads (issues every MMA)
+
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + OFF_BAR);
@@ -224,9 +208,8 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
     if (threadIdx.x == 0) {
         for (int s = 0; s < KST; ++s) { mbar_init(&bars[B_KFULL + s], 1); mbar_init(&bars[B_KEMPTY + s], 1); }
         for (int s = 0; s < TST; ++s) { mbar_init(&bars[B_TFULL + s], 1); mbar_init(&bars[B_TEMPTY + s], 1); }
-        constexpr int TILE_WARPS = ORI_TC_PINGPONG ? NEW / 2 : NEW;     // element-wise warps working on one tile
-        for (int s = 0; s < XST; ++s) { mbar_init(&bars[B_XFULL + s], 1); mbar_init(&bars[B_XEMPTY + s], TILE_WARPS); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&bars[B_SREADY + s], 1); mbar_init(&bars[B_PREADY + s], TILE_WARPS * NCTA); }
+        for (int s = 0; s < XST; ++s) { mbar_init(&bars[B_XFULL + s], 1); mbar_init(&bars[B_XEMPTY + s], NEW); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars[B_SREADY + s], 1); mbar_init(&bars[B_PREADY + s], NEW * NCTA); }
         mbar_init(&bars[B_ACC_READY], 1);
         mbar_init(&bars[B_ACC_FREE], NEW * NCTA);
         mbar_init(&bars[B_A_READY], NEW * NCTA);
@@ -256,15 +239,16 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             if (elect_one()) {
                 uint8_t* st = smem + OFF_T + s * T_STAGE;
                 uint64_t* bar = &bars[B_TFULL + s];
-                const int sw0 = it_.t * TC_SW;
-                if (rank == 0) mbar_expect_tx(bar, NT * 8192);              // the whole pair's bytes land on the leader's barrier
+                const int sw0 = it_.t * SW;
+                if (rank == 0) mbar_expect_tx(bar, NT * C::T_ARR * NCTA);      // the whole pair's bytes land on the leader's barrier
 #pragma unroll
                 for (int q = 0; q < NT; ++q)
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
+                    for (int c = 0; c < SW / 32; ++c) {
                         uint8_t* dst = st + q * C::T_ARR + c * C::T_CHUNK;
-                        if (PAIR) tma_load_2d_pair(dst, &maps.swT, bar, sw0 + 32 * c, q * 32 + 16 * rank, L2_EVICT_LAST);
-                        else tma_load_2d_hint(dst, &maps.swT, bar, sw0 + 32 * c, q * 32, L2_EVICT_LAST);
+                        const int row = q * KP + (KP / NCTA) * rank;            // this CTA's latent rows of array q
+                        if (PAIR) tma_load_2d_pair(dst, &maps.swT, bar, sw0 + 32 * c, row, L2_EVICT_LAST);
+                        else tma_load_2d_hint(dst, &maps.swT, bar, sw0 + 32 * c, row, L2_EVICT_LAST);
                     }
             }
             __syncwarp();
@@ -277,13 +261,17 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 if (elect_one()) {
                     uint8_t* st = smem + OFF_K + s * K_STAGE;
                     uint64_t* bar = &bars[B_KFULL + s];
-                    const int sw0 = ik.t * TC_SW;
-                    if (rank == 0) mbar_expect_tx(bar, NQ * 8192);
+                    const int sw0 = ik.t * SW;
+                    if (rank == 0) mbar_expect_tx(bar, NQ * C::K_ARR * NCTA);
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        if (PAIR) tma_load_2d_pair(st + q * C::K_ARR, &maps.swK, bar, 0, (int)(q * a.sw_pad + sw0 + 32 * rank), L2_EVICT_LAST);
-                        else tma_load_2d_hint(st + q * C::K_ARR, &maps.swK, bar, 0, (int)(q * a.sw_pad + sw0), L2_EVICT_LAST);
-                    }
+                    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                        for (int kb = 0; kb < C::KB; ++kb) {
+                            uint8_t* dst = st + q * C::K_ARR + kb * C::K_BLK;
+                            const int row = (int)(q * a.sw_pad + sw0 + (SW / NCTA) * rank);   // this CTA's sweep rows
+                            if (PAIR) tma_load_2d_pair(dst, &maps.swK, bar, 32 * kb, row, L2_EVICT_LAST);
+                            else tma_load_2d_hint(dst, &maps.swK, bar, 32 * kb, row, L2_EVICT_LAST);
+                        }
                 }
                 __syncwarp();
             }
@@ -293,19 +281,21 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 if (elect_one()) {
                     uint8_t* st = smem + OFF_X + s * X_STAGE;
                     uint64_t* bar = &bars[B_XFULL + s];
-                    const int sw0 = ik.t * TC_SW;
-                    mbar_expect_tx(bar, X_STAGE + ((!GENES && DROPOUT) ? 768 : 0));
-                    if (!GENES) {
+                    const int sw0 = ik.t * SW;
+                    mbar_expect_tx(bar, X_STAGE + ((!GENES && DROPOUT) ? LP_STAGE : 0));
+                    if (!GENES) {          // [128 cells][32 genes] boxes
 #pragma unroll
-                        for (int c = 0; c < 2; ++c) tma_load_2d_hint(st + c * 16384, &maps.X, bar, sw0 + 32 * c, ik.own0, L2_EVICT_FIRST);
+                        for (int c = 0; c < SW / 32; ++c)
+                            tma_load_2d_hint(st + c * (TC_OWN * 128), &maps.X, bar, sw0 + 32 * c, ik.own0, L2_EVICT_FIRST);
                         if (DROPOUT) {
-                            bulk_load(smem + OFF_LP + s * LP_STAGE, a.lp2w + sw0, 256, bar);
-                            bulk_load(smem + OFF_LP + s * LP_STAGE + 256, a.flw + sw0, 256, bar);
-                            bulk_load(smem + OFF_LP + s * LP_STAGE + 512, a.cw + sw0, 256, bar);
+                            bulk_load(smem + OFF_LP + s * LP_STAGE, a.lp2w + sw0, SW * 4, bar);
+                            bulk_load(smem + OFF_LP + s * LP_STAGE + SW * 4, a.flw + sw0, SW * 4, bar);
+                            bulk_load(smem + OFF_LP + s * LP_STAGE + SW * 8, a.cw + sw0, SW * 4, bar);
                         }
-                    } else {
+                    } else {               // [SW cells][32 genes] boxes, one per TMEM lane quarter
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) tma_load_2d_hint(st + c * 8192, &maps.X, bar, ik.own0 + 32 * c, sw0, L2_EVICT_FIRST);
+                        for (int c = 0; c < 4; ++c)
+                            tma_load_2d_hint(st + c * (SW * 128), &maps.X, bar, ik.own0 + 32 * c, sw0, L2_EVICT_FIRST);
                     }
                 }
                 __syncwarp();
@@ -322,167 +312,141 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
         // With PAIR only the leader CTA issues: cta_group::2 MMAs of M = 256 span both CTAs' TMEM and read each
         // CTA's half of the B tile; completion is multicast to the barriers of both CTAs.
         if (!PAIR || rank == 0) {
-        constexpr uint32_t idescS = make_idesc_tf32(TC_OWN * NCTA, TC_SW, false, false);
-        constexpr uint32_t idescP = make_idesc_tf32(TC_OWN * NCTA, TC_KP_CONST, false, false);
-        const uint32_t sbase = smem_u32(smem);
-        const uint64_t kdesc0 = make_smem_desc(sbase + OFF_K, 16, 1024);
-        const uint64_t tdesc0 = make_smem_desc(sbase + OFF_T, 16, 1024);
-        auto mma = [&](uint32_t d, uint32_t at, uint64_t bd, uint32_t idesc, bool acc) {
-            if (PAIR) mma_tf32_ts_pair(d, at, bd, idesc, acc); else mma_tf32_ts(d, at, bd, idesc, acc);
-        };
-        auto commit = [&](uint64_t* bar) { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); };
-        auto issue_P = [&](uint32_t it, bool first, bool last, int li) {
-            const uint32_t s = it & 1, ts = it % TST;
-            mbar_wait(&bars[B_PREADY + s], (it >> 1) & 1, 20, PAIR);
-#ifdef ORI_TC_TRACE
-            if (blockIdx.x == 0 && lane == 0 && it + 1 < 64) g_tc_trace[GENES ? 1 : 0][2][it + 1][3] = clock64();
-#endif
-            mbar_wait(&bars[B_TFULL + ts], (it / TST) & 1, 24);
-#ifdef ORI_TC_TRACE
-            if (blockIdx.x == 0 && lane == 0 && it + 1 < 64) g_tc_trace[GENES ? 1 : 0][2][it + 1][4] = clock64();
-#endif
-            if (first) mbar_wait(&bars[B_ACC_FREE], (li & 1) ^ 1, 21, PAIR);
-            tc_fence_after();
-            if (elect_one()) {
-                const uint64_t td = tdesc0 + (uint64_t)((ts * T_STAGE) >> 4);
+            constexpr uint32_t idescS = make_idesc_tf32(TC_OWN * NCTA, SW, false, false);
+            constexpr uint32_t idescP = make_idesc_tf32(TC_OWN * NCTA, KP, false, false);
+            const uint32_t sbase = smem_u32(smem);
+            const uint64_t kdesc0 = make_smem_desc(sbase + OFF_K, 16, 1024);
+            const uint64_t tdesc0 = make_smem_desc(sbase + OFF_T, 16, 1024);
+            auto mma = [&](uint32_t d, uint32_t at, uint64_t bd, uint32_t idesc, bool acc) {
+                if (PAIR) mma_tf32_ts_pair(d, at, bd, idesc, acc); else mma_tf32_ts(d, at, bd, idesc, acc);
+            };
+            auto commit = [&](uint64_t* bar) { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); };
+            auto issue_P = [&](uint32_t it, bool first, bool last, int li) {
+                const uint32_t s = it & 1, ts = it % TST;
+                mbar_wait(&bars[B_PREADY + s], (it >> 1) & 1, 20);
+                mbar_wait(&bars[B_TFULL + ts], (it / TST) & 1, 24);
+                if (first) mbar_wait(&bars[B_ACC_FREE], (li & 1) ^ 1, 21);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t td = tdesc0 + (uint64_t)((ts * T_STAGE) >> 4);
+                    // contraction over the SW sweep entries of the tile, 8 per MMA: chunk ks / 4, 32 bytes per step
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
-                    mma(tmem + TM_ACC, tmem + s * TM_STAGE + ks * 8,
-                        td + (uint64_t)(((ks >> 2) * C::T_CHUNK + (ks & 3) * 32) >> 4), idescP, !(first && ks == 0));
-                if (DROPOUT) {
+                    for (int ks = 0; ks < SW / 8; ++ks)
+                        mma(tmem + TM_ACC, tmem + s * TM_STAGE + ks * 8,
+                            td + (uint64_t)(((ks >> 2) * C::T_CHUNK + (ks & 3) * 32) >> 4), idescP, !(first && ks == 0));
+                    if (DROPOUT) {
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-                        mma(tmem + TM_ACC + 32, tmem + s * TM_STAGE + 64 + ks * 8,
-                            td + (uint64_t)((C::T_ARR + (ks >> 2) * C::T_CHUNK + (ks & 3) * 32) >> 4), idescP,
-                            !(first && ks == 0));
+                        for (int ks = 0; ks < SW / 8; ++ks)
+                            mma(tmem + TM_ACC + KP, tmem + s * TM_STAGE + SW + ks * 8,
+                                td + (uint64_t)((C::T_ARR + (ks >> 2) * C::T_CHUNK + (ks & 3) * 32) >> 4), idescP,
+                                !(first && ks == 0));
+                    }
+                    commit(&bars[B_TEMPTY + ts]);
+                    if (last) commit(&bars[B_ACC_READY]);
                 }
-                commit(&bars[B_TEMPTY + ts]);
-                if (last) commit(&bars[B_ACC_READY]);
-            }
-            __syncwarp();
-        };
-        TileIter ti;
-        ti.init(a, NCTA, rank);
-        uint32_t it = 0;
-        int li = 0;
-        bool have_prev = false, prev_first = false, prev_last = false;
-        int prev_li = 0;
-        while (ti.valid(a)) {
-            const uint32_t s = it & 1, ks_ = it % KST;
-            const bool first = ti.first(), last = ti.last();
-#ifdef ORI_TC_TRACE
-            const bool trace_on = blockIdx.x == 0 && lane == 0; const uint32_t trace_tile = it;
-#endif
-            ORI_STAMP(2, 0);
-            mbar_wait(&bars[B_KFULL + ks_], (it / KST) & 1, 23);
-            ORI_STAMP(2, 1);
-            if (first) mbar_wait(&bars[B_A_READY], li & 1, 22, PAIR);
-            tc_fence_after();
-            if (elect_one()) {
-                const uint64_t kd = kdesc0 + (uint64_t)((ks_ * K_STAGE) >> 4);
-                // den (and uv) of this tile: three tf32 products per contraction, A operand from TMEM
-#define ORI_CHAIN(D_, QA, QB, FRESH)                                                                          \
-                _Pragma("unroll") for (int kk = 0; kk < 4; ++kk)                                              \
-                    mma((D_), tmem + TM_A + (QA) * 32 + kk * 8,                                               \
-                        kd + (uint64_t)(((QB) * C::K_ARR + kk * 32) >> 4), idescS, !((FRESH) && kk == 0))
-                ORI_CHAIN(tmem + s * TM_STAGE, 0, 0, true);
-                ORI_CHAIN(tmem + s * TM_STAGE, 0, 1, false);
-                ORI_CHAIN(tmem + s * TM_STAGE, 1, 0, false);
-                if (DROPOUT) {
-                    ORI_CHAIN(tmem + s * TM_STAGE + 64, 2, 2, true);
-                    ORI_CHAIN(tmem + s * TM_STAGE + 64, 2, 3, false);
-                    ORI_CHAIN(tmem + s * TM_STAGE + 64, 3, 2, false);
-                }
+                __syncwarp();
+            };
+            TileIter ti;
+            ti.init(a, NCTA, rank);
+            uint32_t it = 0;
+            int li = 0;
+            bool have_prev = false, prev_first = false, prev_last = false;
+            int prev_li = 0;
+            while (ti.valid(a)) {
+                const uint32_t s = it & 1, ks_ = it % KST;
+                const bool first = ti.first(), last = ti.last();
+                mbar_wait(&bars[B_KFULL + ks_], (it / KST) & 1, 23);
+                if (first) mbar_wait(&bars[B_A_READY], li & 1, 22);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t kd = kdesc0 + (uint64_t)((ks_ * K_STAGE) >> 4);
+                    // den (and uv) of this tile: three tf32 products per contraction, A operand from TMEM;
+                    // contraction over the KP latent components, 8 per MMA: K block kk / 4, 32 bytes per step
+#define ORI_CHAIN(D_, QA, QB, FRESH)                                                                              \
+                    _Pragma("unroll") for (int kk = 0; kk < KP / 8; ++kk)                                         \
+                        mma((D_), tmem + TM_A + (QA) * KP + kk * 8,                                               \
+                            kd + (uint64_t)(((QB) * C::K_ARR + (kk >> 2) * C::K_BLK + (kk & 3) * 32) >> 4), idescS, \
+                            !((FRESH) && kk == 0))
+                    ORI_CHAIN(tmem + s * TM_STAGE, 0, 0, true);
+                    ORI_CHAIN(tmem + s * TM_STAGE, 0, 1, false);
+                    ORI_CHAIN(tmem + s * TM_STAGE, 1, 0, false);
+                    if (DROPOUT) {
+                        ORI_CHAIN(tmem + s * TM_STAGE + SW, 2, 2, true);
+                        ORI_CHAIN(tmem + s * TM_STAGE + SW, 2, 3, false);
+                        ORI_CHAIN(tmem + s * TM_STAGE + SW, 3, 2, false);
+                    }
 #undef ORI_CHAIN
-                commit(&bars[B_SREADY + s]);
-                commit(&bars[B_KEMPTY + ks_]);
+                    commit(&bars[B_SREADY + s]);
+                    commit(&bars[B_KEMPTY + ks_]);
+                }
+                __syncwarp();
+                if (have_prev) issue_P(it - 1, prev_first, prev_last, prev_li);
+                have_prev = true; prev_first = first; prev_last = last; prev_li = li;
+                if (last) ++li;
+                ++it;
+                ti.next(a);
             }
-            __syncwarp();
-            ORI_STAMP(2, 2);
             if (have_prev) issue_P(it - 1, prev_first, prev_last, prev_li);
-            ORI_STAMP(2, 5);
-            have_prev = true; prev_first = first; prev_last = last; prev_li = li;
-            if (last) ++li;
-            ++it;
-            ti.next(a);
-        }
-        if (have_prev) issue_P(it - 1, prev_first, prev_last, prev_li);
         }
     } else {
         // ======================================= element-wise stage + epilogue =================================
         const int ew = warp - 2;
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
-        const int slice = ew >> 2;                    // which CW of the 64 tile columns
+        const int slice = ew >> 2;                    // which half of the tile's columns / of the own-side arrays
         const int lrow = quarter * 32 + lane;         // own index inside the tile = TMEM lane
+        const int colbase = slice * CW;
         const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t sbase = smem_u32(smem);
         const bool any_floor = DROPOUT && (*a.any_floor != 0);
+        auto arrive_leader = [&](uint64_t* bar) { if (PAIR) mbar_arrive_cluster(bar, 0); else mbar_arrive(bar); };
 
-        // own-side operands of one work item -> TMEM (this warp's 32 lanes, its share of the 4 arrays)
-        constexpr int APW = (NQ + SLICES - 1) / SLICES;           // arrays per warp
-        float av[32];
-        auto a_fetch = [&](int own0) {                            // global -> registers
-            const int q0 = slice * APW;
-            if (q0 < NQ) {
+        // own-side operands of one work item -> TMEM: slice 0 writes hi / lo of exp(E log .), slice 1 (dropout only)
+        // hi / lo of E[.], for this warp's 32 lanes, 32 latent components at a time
+        auto a_load_store = [&](int own0) {
+            if (slice * 2 < NQ) {
                 const long long idx = (long long)own0 + lrow;
-                const float* src = ((q0 >> 1) ? a.own_E : a.own_e) + idx * 32;
-                if (idx < a.own_total) {
+                const float* src = (slice ? a.own_E : a.own_e) + idx * KP;
+                const bool ok = idx < a.own_total;
+                const bool scale = GENES && slice;                 // uv is kept in log2 units: V_hat side * log2(e)
+#pragma unroll
+                for (int kb = 0; kb < C::KB; ++kb) {
+                    float av[32];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + c);
+                        const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(src + 32 * kb) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
                         av[4 * c] = v.x; av[4 * c + 1] = v.y; av[4 * c + 2] = v.z; av[4 * c + 3] = v.w;
                     }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) av[c] = 0.f;
-                }
-            }
-        };
-        auto a_store = [&]() {                                    // registers -> TMEM (hi / lo split)
-            const int q0 = slice * APW;
-#pragma unroll
-            for (int j = 0; j < APW; ++j) {
-                const int q = q0 + j;
-                if (q < NQ) {
-                    // APW == 1: array q is hi (even q) or lo (odd q) of av; APW == 2: q0 even -> hi then lo
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        uint32_t w[16];
+                        uint32_t whi[16], wlo[16];
 #pragma unroll
                         for (int e = 0; e < 16; ++e) {
-                            const float v = (GENES && q >= 2) ? av[16 * h + e] * LOG2E : av[16 * h + e];   // uv in log2 units
+                            const float v = scale ? av[16 * h + e] * LOG2E : av[16 * h + e];
                             const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
-                            w[e] = __float_as_uint((q & 1) ? v - hi : hi);
+                            whi[e] = __float_as_uint(hi);
+                            wlo[e] = __float_as_uint(v - hi);
                         }
-                        tmem_st16(tlane + TM_A + q * 32 + 16 * h, w);
+                        tmem_st16(tlane + TM_A + (2 * slice) * KP + 32 * kb + 16 * h, whi);
+                        tmem_st16(tlane + TM_A + (2 * slice + 1) * KP + 32 * kb + 16 * h, wlo);
                     }
                 }
             }
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { if (PAIR) mbar_arrive_cluster(&bars[B_A_READY], 0); else mbar_arrive(&bars[B_A_READY]); }
+            if (lane == 0) arrive_leader(&bars[B_A_READY]);
         };
 
-        const uint32_t sbase = smem_u32(smem);
-        // tile work split: without ping-pong all NEW warps share every tile (CW columns each); with it the warps
-        // form two groups taking alternate tiles, and a tile's 64 columns are split over the group's NEW/8 slices
-        constexpr bool PP = ORI_TC_PINGPONG != 0;
-        constexpr int TSL = PP ? NEW / 8 : SLICES;    // column slices of one tile
-        constexpr int CWT = TC_SW / TSL;              // tile columns per warp
-        constexpr int G = CWT / 16;                   // groups of 16 columns per tile for this warp
-        const int grp = PP ? ew / (NEW / 2) : 0;      // which tiles (parity of the CTA's tile counter)
-        const int tsl = PP ? (ew % (NEW / 2)) >> 2 : slice;
-        const int colbase = tsl * CWT;
         // gene pass: X is staged [cell][gene]; lane (gene) reads one float per cell, 128-byte swizzle undone here
         uint32_t xoff[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) xoff[k] = (uint32_t)(quarter * 8192 + ((((lane >> 2) ^ k)) << 4) + (lane & 3) * 4);
+        for (int k = 0; k < 8; ++k) xoff[k] = (uint32_t)(quarter * (SW * 128) + ((((lane >> 2) ^ k)) << 4) + (lane & 3) * 4);
 
         TileIter ti;
         ti.init(a, NCTA, rank);
         uint32_t it = 0;                              // tiles of this CTA so far: TMEM stage it & 1, X stage it % XST
         int li = 0;
-        if (ti.valid(a)) { a_fetch(ti.own0); a_store(); }
+        if (ti.valid(a)) a_load_store(ti.own0);
         while (ti.valid(a)) {
             const long long own_idx = (long long)ti.own0 + lrow;
             const bool own_ok = own_idx < a.own_total;
@@ -501,32 +465,18 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             float cs = 0.f;
             float xl_s = 0.f, xl_c = 0.f, ent_s = 0.f, ent_c = 0.f;     // compensated fp32 sums over the item
             const int t_end = ti.t_end;
-            const uint32_t it_last = it + (uint32_t)(t_end - ti.t_begin) - 1;
             for (int t = ti.t_begin; t < t_end; ++t, ++it) {
-                if (PP && (int)(it & 1) != grp) continue;                // the other group's tile
                 const bool last = (t == t_end - 1);
                 const uint32_t s = it & 1, sph = (it >> 1) & 1, xs = it % XST, xph = (it / XST) & 1;
-#ifdef ORI_TC_TRACE
-                const bool trace_on = blockIdx.x == 0 && lane == 0 && (ew == 0 || ew == 4);
-                const uint32_t trace_tile = (uint32_t)(li * 100000 + (t - ti.t_begin));   // first item only
-                const int tw = ew >> 2;
-#endif
-                ORI_STAMP(tw, 0);
-                if (ORI_TC_AFETCH_EARLY && last && has_next) a_fetch(next_own0);
                 // X tile (and lp) visible to this thread; den / uv complete in TMEM
                 mbar_wait2(&bars[B_XFULL + xs], xph, &bars[B_SREADY + s], sph, 30);
-                ORI_STAMP(tw, 1);
-                ORI_STAMP(tw, 2);
                 tc_fence_after();
-                if (last && has_next) {             // every S of this item has completed: A can be replaced
-                    if (!ORI_TC_AFETCH_EARLY) a_fetch(next_own0);
-                    a_store();
-                }
+                if (last && has_next) a_load_store(next_own0);   // every S of this item has completed: A can be replaced
                 const uint32_t xs_addr = sbase + OFF_X + xs * X_STAGE;
                 const uint32_t lp_addr = sbase + OFF_LP + xs * LP_STAGE;
-                const int valid = (int)min((long long)TC_SW, a.sw_total - (long long)t * TC_SW);   // gene pass: real cells
-                const bool slow_tile = slow_item || (GENES && valid != TC_SW);
-                const uint32_t tden = tlane + s * TM_STAGE, tuv = tden + 64;
+                const int valid = (int)min((long long)SW, a.sw_total - (long long)t * SW);   // gene pass: real cells
+                const bool slow_tile = slow_item || (GENES && valid != SW);
+                const uint32_t tden = tlane + s * TM_STAGE, tuv = tden + SW;
                 float t_xl = 0.f, t_ent = 0.f;
 
                 uint32_t dr[2][16], ur[2][16];                           // two groups in flight, indexed by g & 1
@@ -535,7 +485,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     const int c0 = colbase + g * 16;
                     const int b = g & 1;
                     if (!GENES) {
-                        const uint32_t base = xs_addr + (c0 >> 5) * 16384 + lrow * 128;
+                        const uint32_t base = xs_addr + (c0 >> 5) * (TC_OWN * 128) + lrow * 128;
                         const int cb = (c0 & 31) >> 2;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -566,7 +516,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                         float tt = dg, e2 = 0.f, D = 1.f;
                         if (DROPOUT) {
                             const float lp2 = GENES ? lp2j : lds32(lp_addr + 4 * (c0 + e));
-                            const float fl = GENES ? flj : lds32(lp_addr + 256 + 4 * (c0 + e));
+                            const float fl = GENES ? flj : lds32(lp_addr + SW * 4 + 4 * (c0 + e));
                             e2 = fminf(__uint_as_float(ur[b][e]) - lp2, 127.f);
                             tt = nz ? dg : 1.f + ex2_approx(e2);
                             const float r = rcp_approx(tt);
@@ -594,7 +544,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     if (DROPOUT && !GENES) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float4 v = lds128(lp_addr + 512 + 4 * (c0 + 4 * q));
+                            const float4 v = lds128(lp_addr + SW * 8 + 4 * (c0 + 4 * q));
                             cc[4 * q] = v.x; cc[4 * q + 1] = v.y; cc[4 * q + 2] = v.z; cc[4 * q + 3] = v.w;
                         }
                     }
@@ -644,70 +594,52 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 for (int g = 0; g < G; ++g) {
                     const int c0 = colbase + g * 16;
                     bool redo = slow_tile;
-                    if (!ORI_TC_PREFETCH_TM && !slow_tile && g > 0) {
-                        tmem_ld16(tden + c0, dr[g & 1]);
-                        if (DROPOUT) tmem_ld16(tuv + c0, ur[g & 1]);
-                    }
-                    if (!ORI_TC_PREFETCH_X && g > 0) load_x(g);
+                    if (g > 0) load_x(g);
                     if (!slow_tile) {
                         tmem_wait_ld();
-                        if (g < 2) ORI_STAMP(tw, 3 + 3 * g);
-                        if (ORI_TC_PREFETCH_TM && g + 1 < G) {            // next group's loads fly during this one
+                        if (g + 1 < G) {                                  // next group's loads fly during this one
                             tmem_ld16(tden + c0 + 16, dr[(g + 1) & 1]);
                             if (DROPOUT) tmem_ld16(tuv + c0 + 16, ur[(g + 1) & 1]);
                         }
-                    }
-                    if (ORI_TC_PREFETCH_X && g + 1 < G) load_x(g + 1);
-                    if (!slow_tile) {
                         float g_cs = 0.f, g_xl = 0.f, g_ent = 0.f;
                         const float dmin = fast_group(g, g_cs, g_xl, g_ent);
                         redo = __any_sync(0xffffffffu, dmin <= 0.f) != 0;
                         if (GENES && !redo) { cs += g_cs; t_xl += g_xl; t_ent += g_ent; }
                     }
                     if (redo) slow_group(g);
-                    if (g < 2) ORI_STAMP(tw, 4 + 3 * g);
                     tmem_st16(tden + c0, dr[g & 1]);
                     if (DROPOUT) tmem_st16(tuv + c0, ur[g & 1]);
-                    if (g < 2) ORI_STAMP(tw, 5 + 3 * g);
                 }
                 if (GENES && ELBO) { kahan_add(xl_s, xl_c, t_xl); if (DROPOUT) kahan_add(ent_s, ent_c, t_ent); }
                 tmem_wait_st();
-                ORI_STAMP(tw, 9);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    if (PAIR) mbar_arrive_cluster(&bars[B_PREADY + s], 0); else mbar_arrive(&bars[B_PREADY + s]);
+                    arrive_leader(&bars[B_PREADY + s]);
                     mbar_arrive(&bars[B_XEMPTY + xs]);
                 }
-                ORI_STAMP(tw, 10);
-            }
-            if (PP && has_next && (int)(it_last & 1) != grp) {           // the other group had the item's last tile:
-                mbar_wait(&bars[B_SREADY + (it_last & 1)], (it_last >> 1) & 1, 33);   // every S of the item has run
-                tc_fence_after();
-                a_fetch(next_own0);
-                a_store();
             }
             double acc_xl = (double)xl_s - (double)xl_c, acc_ent = (double)ent_s - (double)ent_c;
-            // ---- epilogue of the work item: accumulators -> global (atomics: the sweep of one own tile is split)
+            // ---- epilogue of the work item: accumulators -> global (atomics: the sweep of one own tile is split);
+            //      slice 0 drains acc1, slice 1 acc2
             mbar_wait(&bars[B_ACC_READY], li & 1, 32);
             tc_fence_after();
+            if (slice == 0 || DROPOUT) {
+                float* out = (slice == 0 ? a.acc1 : a.acc2) + own_idx * KP;
 #pragma unroll
-            for (int g = 0; g < CW / 16; ++g) {
-                const int c0 = slice * CW + g * 16;          // column of [acc1 | acc2]
-                if (c0 < 32 || DROPOUT) {
+                for (int g = 0; g < KP / 16; ++g) {
                     uint32_t v[16];
-                    tmem_ld16(tlane + TM_ACC + c0, v);
+                    tmem_ld16(tlane + TM_ACC + slice * KP + g * 16, v);
                     tmem_wait_ld();
                     if (own_ok) {
-                        float* out = (c0 < 32 ? a.acc1 + c0 : a.acc2 + (c0 - 32)) + own_idx * 32;
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) atomicAdd(out + e, __uint_as_float(v[e]));
+                        for (int e = 0; e < 16; ++e) atomicAdd(out + g * 16 + e, __uint_as_float(v[e]));
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { if (PAIR) mbar_arrive_cluster(&bars[B_ACC_FREE], 0); else mbar_arrive(&bars[B_ACC_FREE]); }
+            if (lane == 0) arrive_leader(&bars[B_ACC_FREE]);
             if (GENES) {
                 if (DROPOUT && own_ok) atomicAdd(a.colsum + own_idx, (double)cs);
                 if (ELBO) {
@@ -735,40 +667,41 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
 }
 
 // ---- operand preparation -------------------------------------------------------------------------------------
-// K-major operand arrays: out[q][pad][32], q = 0: hi(e) 1: lo(e) 2: hi(E) 3: lo(E); hi = tf32 round-to-nearest
+// K-major operand arrays: out[q][pad][KP], q = 0: hi(e) 1: lo(e) 2: hi(E) 3: lo(E); hi = tf32 round-to-nearest
 // (the tensor core truncates fp32 operands to tf32: scripts/tc_probe.cu T4), lo = x - hi.  Pad rows are zero.
 __global__ void __launch_bounds__(256)
 k_tc_prep_K(const float* __restrict__ e, const float* __restrict__ E, float Escale, float* __restrict__ out, long long n,
-            long long pad)
+            long long pad, int KP)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= pad * 32) return;
-    const bool ok = idx < n * 32;
+    if (idx >= pad * KP) return;
+    const bool ok = idx < n * KP;
     const float v = ok ? e[idx] : 0.f;
     const float hv = to_tf32_rna(v);
     out[idx] = hv;
-    out[pad * 32 + idx] = v - hv;
+    out[pad * KP + idx] = v - hv;
     if (E) {
         const float w = ok ? E[idx] * Escale : 0.f;
         const float hw = to_tf32_rna(w);
-        out[2 * pad * 32 + idx] = hw;
-        out[3 * pad * 32 + idx] = w - hw;
+        out[2 * pad * KP + idx] = hw;
+        out[3 * pad * KP + idx] = w - hw;
     }
 }
-// transposed operand: out[k][i] = tf32(src[i][k]),  src [n x 32], out [32 x pad]
+// transposed operand: out[k][i] = tf32(src[i][k]),  src [n x KP], out [KP x pad]; grid (pad / 32, KP / 32)
 __global__ void __launch_bounds__(256)
-k_tc_prep_T(const float* __restrict__ src, float* __restrict__ out, long long n, long long pad)
+k_tc_prep_T(const float* __restrict__ src, float* __restrict__ out, long long n, long long pad, int KP)
 {
     __shared__ float tile[32][33];
     const long long i0 = (long long)blockIdx.x * 32;
+    const int k0 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += 8) {
         const long long i = i0 + r;
-        tile[r][threadIdx.x] = i < n ? src[i * 32 + threadIdx.x] : 0.f;
+        tile[r][threadIdx.x] = i < n ? src[i * KP + k0 + threadIdx.x] : 0.f;
     }
     __syncthreads();
     for (int k = threadIdx.y; k < 32; k += 8) {
         const long long i = i0 + threadIdx.x;
-        if (i < pad) out[(long long)k * pad + i] = to_tf32_rna(tile[threadIdx.x][k]);
+        if (i < pad) out[(long long)(k0 + k) * pad + i] = to_tf32_rna(tile[threadIdx.x][k]);
     }
 }
 __global__ void k_tc_prep_lp(const float* __restrict__ lp, const float* __restrict__ fl, float* __restrict__ lp2w,
@@ -787,20 +720,21 @@ __global__ void k_tc_prep_lp(const float* __restrict__ lp, const float* __restri
 // ---- host side ---------------------------------------------------------------------------------------------------
 static long long pad128(long long v) { return (v + 127) / 128 * 128; }
 
-long long tc_workspace_floats(long long n_rows, int p) {
+long long tc_workspace_floats(long long n_rows, int p, int KP) {
     const long long np = pad128(n_rows), pp = pad128(p);
-    return 4 * np * 32 + 2 * 32 * np + 4 * pp * 32 + 2 * 32 * pp + 3 * pp + 32;
+    return 6LL * KP * (np + pp) + 3 * pp + 32;
 }
 
 struct TcWs { float *rowK, *rowT, *geneK, *geneT, *lp2w, *flw, *cw; int* flags; long long np, pp; };
 static TcWs tc_carve(const ori_problem_t* P) {
     TcWs w;
     w.np = pad128(P->n_rows); w.pp = pad128(P->p);
+    const long long KP = P->KP;
     float* f = P->tc_ws;
-    w.rowK = f; f += 4 * w.np * 32;
-    w.rowT = f; f += 2 * 32 * w.np;
-    w.geneK = f; f += 4 * w.pp * 32;
-    w.geneT = f; f += 2 * 32 * w.pp;
+    w.rowK = f; f += 4 * w.np * KP;
+    w.rowT = f; f += 2 * KP * w.np;
+    w.geneK = f; f += 4 * w.pp * KP;
+    w.geneT = f; f += 2 * KP * w.pp;
     w.lp2w = f; f += w.pp;
     w.flw = f; f += w.pp;
     w.cw = f; f += w.pp;
@@ -809,8 +743,8 @@ static TcWs tc_carve(const ori_problem_t* P) {
 }
 
 bool tc_eligible(const ori_problem_t* P) {
-    return P->tc_ws != nullptr && P->KP == 32 && !(P->flags & ORI_F_NO_TENSOR) && P->n_rows > 0 &&
-           P->tc_ws_floats >= tc_workspace_floats(P->n_rows, P->p) && get_encode_fn() != nullptr;
+    return P->tc_ws != nullptr && (P->KP == 32 || P->KP == 64) && !(P->flags & ORI_F_NO_TENSOR) && P->n_rows > 0 &&
+           P->tc_ws_floats >= tc_workspace_floats(P->n_rows, P->p, P->KP) && get_encode_fn() != nullptr;
 }
 
 static int num_sms() {
@@ -823,11 +757,13 @@ static int num_sms() {
 int launch_tc_prep_genes(const ori_problem_t* P, cudaStream_t st) {
     const TcWs w = tc_carve(P);
     const bool drop = P->flags & ORI_F_DROPOUT;
-    k_tc_prep_K<<<cdiv(w.pp * 32, 256), 256, 0, st>>>(P->eV, drop ? P->V_hat : nullptr, LOG2E, w.geneK, P->p, w.pp);
-    k_tc_prep_T<<<cdiv(w.pp, 32), dim3(32, 8), 0, st>>>(P->eV, w.geneT, P->p, w.pp);
+    const int KP = P->KP;
+    const dim3 tg(cdiv(w.pp, 32), KP / 32);
+    k_tc_prep_K<<<cdiv(w.pp * KP, 256), 256, 0, st>>>(P->eV, drop ? P->V_hat : nullptr, LOG2E, w.geneK, P->p, w.pp, KP);
+    k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(P->eV, w.geneT, P->p, w.pp, KP);
     cudaMemsetAsync(w.flags, 0, 32 * sizeof(int), st);
     if (drop) {
-        k_tc_prep_T<<<cdiv(w.pp, 32), dim3(32, 8), 0, st>>>(P->V_hat, w.geneT + 32 * w.pp, P->p, w.pp);
+        k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(P->V_hat, w.geneT + (long long)KP * w.pp, P->p, w.pp, KP);
         k_tc_prep_lp<<<cdiv(w.pp, 256), 256, 0, st>>>(P->lp, P->pfloor, w.lp2w, w.flw, w.cw, w.flags, P->p, (int)w.pp);
     }
     return check_launch("k_tc_prep(genes)", drop ? 4 : 2);
@@ -838,10 +774,12 @@ int launch_tc_prep_genes(const ori_problem_t* P, cudaStream_t st) {
 int launch_tc_prep_rows(const ori_problem_t* P, int g, cudaStream_t st) {
     const TcWs w = tc_carve(P);
     const bool drop = P->flags & ORI_F_DROPOUT;
-    k_tc_prep_K<<<cdiv(w.np * 32, 256), 256, 0, st>>>(P->eU[g], drop ? P->U_hat[g] : nullptr, 1.f, w.rowK, P->n_rows, w.np);
+    const int KP = P->KP;
+    const dim3 tg(cdiv(w.np, 32), KP / 32);
+    k_tc_prep_K<<<cdiv(w.np * KP, 256), 256, 0, st>>>(P->eU[g], drop ? P->U_hat[g] : nullptr, 1.f, w.rowK, P->n_rows, w.np, KP);
     const float* wsrc = (P->flags & ORI_F_QUIRK) ? P->eUw : P->eU[g];
-    k_tc_prep_T<<<cdiv(w.np, 32), dim3(32, 8), 0, st>>>(wsrc, w.rowT, P->n_rows, w.np);
-    if (drop) k_tc_prep_T<<<cdiv(w.np, 32), dim3(32, 8), 0, st>>>(P->U_hat[1 - g], w.rowT + 32 * w.np, P->n_rows, w.np);
+    k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(wsrc, w.rowT, P->n_rows, w.np, KP);
+    if (drop) k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(P->U_hat[1 - g], w.rowT + (long long)KP * w.np, P->n_rows, w.np, KP);
     return check_launch("k_tc_prep(rows)", drop ? 3 : 2);
 }
 
@@ -849,25 +787,25 @@ static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
 }
-static int ew_warps() { static int n = env_int("ORI_TC_EW", 8) == 16 ? 16 : 8; return n; }
-// CTA-pair kernels (cta_group::2) by default; ORI_TC_PAIR=0 selects the single-CTA variant (kept for A/B runs)
+// CTA-pair kernels (cta_group::2) by default; ORI_TC_PAIR=0 selects the single-CTA variant (kept for A/B runs, KP 32)
 static bool use_pair() { static int v = env_int("ORI_TC_PAIR", 1); return v != 0; }
 
 // Split the sweep into chunks so that (a) there are many more work items than schedulable units (SMs, or SM
 // pairs), (b) the static round-robin wastes as little of the last round as possible, (c) the gene pass keeps
-// <= 128 tiles per item (fp32 running sums of the statistics).
-static void tc_partition(TcArgs& a, bool genes, int units) {
-    const int max_tpc = genes ? 128 : 1 << 30;
+// <= 8192 cells per item (fp32 running sums of the statistics).
+static void tc_partition(TcArgs& a, bool genes, int units, int sw) {
+    const int max_tpc = genes ? 8192 / sw : 1 << 30;
+    const int min_tpc = 1024 / sw;
     int best_chunks = 1; double best_eff = -1.0;
     for (int chunks = 1; chunks <= a.n_sw_tiles; ++chunks) {
         const int tpc = cdiv(a.n_sw_tiles, chunks);
         if (tpc > max_tpc) continue;
-        if (tpc < 16 && chunks > 1) break;
+        if (tpc < min_tpc && chunks > 1) break;
         const int real_chunks = cdiv(a.n_sw_tiles, tpc);
         const long long items = (long long)real_chunks * a.n_own_units;
         const long long rounds = (items + units - 1) / units;
         // efficiency of the static schedule, with a mild penalty per item for its prologue / epilogue
-        const double eff = (double)items / (double)(rounds * units) * ((double)tpc / (tpc + 2.0));
+        const double eff = (double)items / (double)(rounds * units) * ((double)tpc / (tpc + 128.0 / sw));
         if (eff > best_eff + 1e-9) { best_eff = eff; best_chunks = chunks; }
         if (items > 64LL * units) break;
     }
@@ -876,17 +814,17 @@ static void tc_partition(TcArgs& a, bool genes, int units) {
     a.n_items = a.n_own_units * a.n_chunks;
 }
 
-template <bool GENES, bool D, bool E, int NW, bool PAIR>
+template <bool GENES, bool D, bool E, bool PAIR, int KP>
 static int launch_tc_variant(const TcMaps& maps, const TcArgs& a, int grid, cudaStream_t st) {
-    auto kern = k_tc_pass<GENES, D, E, NW, PAIR>;
+    auto kern = k_tc_pass<GENES, D, E, PAIR, KP>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<PAIR>::SMEM_BYTES);
+        cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<KP, PAIR>::SMEM_BYTES);
         if (e_ != cudaSuccess) return set_error(ORI_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e_));
         attr_done = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * NW); cfg.dynamicSmemBytes = Cfg<PAIR>::SMEM_BYTES; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg<KP, PAIR>::SMEM_BYTES; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -896,62 +834,55 @@ static int launch_tc_variant(const TcMaps& maps, const TcArgs& a, int grid, cuda
     return ORI_OK;
 }
 
-template <bool GENES, bool PAIR>
+template <bool GENES, bool PAIR, int KP>
 static int launch_tc_pass_p(const ori_problem_t* P, int gen_old, cudaStream_t st) {
+    using C = Cfg<KP, PAIR>;
     const TcWs w = tc_carve(P);
     const bool drop = P->flags & ORI_F_DROPOUT, elbo = P->flags & ORI_F_ELBO;
-    constexpr int NCTA = PAIR ? 2 : 1;
+    constexpr int NCTA = C::NCTA, SW = C::SW;
     TcMaps maps;
     TcArgs a;
     bool ok;
-    // streamed-operand boxes: a CTA of a pair stages half of the 64 sweep rows / half of the 32 latent rows
+    // streamed-operand boxes: K-major [32 latent x SW / NCTA sweep rows] per K block, transposed
+    // [32 sweep x KP / NCTA latent rows] per chunk (a CTA of a pair stages half of the rows)
     if (!GENES) {
-        ok = make_tmap_f32(&maps.swK, w.geneK, 4 * w.pp, 32, 32, 32, 64 / NCTA) &&
-             make_tmap_f32(&maps.swT, w.geneT, 64, w.pp, w.pp, 32, 32 / NCTA) &&
-             make_tmap_f32(&maps.X, P->X, P->n_rows, P->p, P->ldx, 32, 128);
+        ok = make_tmap_f32(&maps.swK, w.geneK, 4 * w.pp, KP, KP, 32, SW / NCTA) &&
+             make_tmap_f32(&maps.swT, w.geneT, 2 * KP, w.pp, w.pp, 32, KP / NCTA) &&
+             make_tmap_f32(&maps.X, P->X, P->n_rows, P->p, P->ldx, 32, TC_OWN);
         a.own_total = P->n_rows; a.sw_total = P->p; a.sw_pad = w.pp;
         a.own_e = P->eU[gen_old]; a.own_E = P->U_hat[gen_old];
         a.acc1 = P->Zi; a.acc2 = P->a2s;
     } else {
-        ok = make_tmap_f32(&maps.swK, w.rowK, 4 * w.np, 32, 32, 32, 64 / NCTA) &&
-             make_tmap_f32(&maps.swT, w.rowT, 64, w.np, w.np, 32, 32 / NCTA) &&
-             make_tmap_f32(&maps.X, P->X, P->n_rows, P->p, P->ldx, 32, 64);
+        ok = make_tmap_f32(&maps.swK, w.rowK, 4 * w.np, KP, KP, 32, SW / NCTA) &&
+             make_tmap_f32(&maps.swT, w.rowT, 2 * KP, w.np, w.np, 32, KP / NCTA) &&
+             make_tmap_f32(&maps.X, P->X, P->n_rows, P->p, P->ldx, 32, SW);
         a.own_total = P->p; a.sw_total = P->n_rows; a.sw_pad = w.np;
         a.own_e = P->eV; a.own_E = P->V_hat;
-        a.acc1 = P->red32; a.acc2 = P->red32 + (long long)P->p * 32;
+        a.acc1 = P->red32; a.acc2 = P->red32 + (long long)P->p * KP;
     }
     if (!ok) return set_error(ORI_ECUDA, "cuTensorMapEncodeTiled failed");
     a.lp2w = w.lp2w; a.flw = w.flw; a.cw = w.cw; a.any_floor = w.flags;
     a.colsum = P->red64; a.part64 = P->red64 + P->p + 2 * P->KP;
     a.n_own_tiles = cdiv(a.own_total, TC_OWN);
     a.n_own_units = cdiv(a.n_own_tiles, NCTA);
-    a.n_sw_tiles = cdiv(a.sw_total, TC_SW);
+    a.n_sw_tiles = cdiv(a.sw_total, SW);
     const int units = num_sms() / NCTA;
-    tc_partition(a, GENES, units);
+    tc_partition(a, GENES, units, SW);
     const int grid = NCTA * (a.n_items < units ? a.n_items : units);
-    const int nw = ew_warps();
     int rc;
-#define ORI_TC_LAUNCH_NW(D, E) (nw == 8 ? launch_tc_variant<GENES, D, E, 8, PAIR>(maps, a, grid, st)     \
-                                        : launch_tc_variant<GENES, D, E, 16, PAIR>(maps, a, grid, st))
-    if (drop && elbo) rc = ORI_TC_LAUNCH_NW(true, true);
-    else if (drop) rc = ORI_TC_LAUNCH_NW(true, false);
-    else if (elbo) rc = ORI_TC_LAUNCH_NW(false, true);
-    else rc = ORI_TC_LAUNCH_NW(false, false);
-#undef ORI_TC_LAUNCH_NW
+    if (drop && elbo) rc = launch_tc_variant<GENES, true, true, PAIR, KP>(maps, a, grid, st);
+    else if (drop) rc = launch_tc_variant<GENES, true, false, PAIR, KP>(maps, a, grid, st);
+    else if (elbo) rc = launch_tc_variant<GENES, false, true, PAIR, KP>(maps, a, grid, st);
+    else rc = launch_tc_variant<GENES, false, false, PAIR, KP>(maps, a, grid, st);
     if (rc != ORI_OK) return rc;
     return check_launch(GENES ? "k_tc_pass(genes)" : "k_tc_pass(rows)");
 }
 
 template <bool GENES>
 static int launch_tc_pass(const ori_problem_t* P, int gen_old, cudaStream_t st) {
-    return use_pair() ? launch_tc_pass_p<GENES, true>(P, gen_old, st) : launch_tc_pass_p<GENES, false>(P, gen_old, st);
+    if (P->KP == 64) return launch_tc_pass_p<GENES, true, 64>(P, gen_old, st);
+    return use_pair() ? launch_tc_pass_p<GENES, true, 32>(P, gen_old, st) : launch_tc_pass_p<GENES, false, 32>(P, gen_old, st);
 }
-
-#ifdef ORI_TC_TRACE
-extern "C" int ori_debug_trace(long long* out) {
-    return cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(g_tc_trace)) == cudaSuccess ? 0 : -1;
-}
-#endif
 
 int launch_pass_rows_tc(const ori_problem_t* P, int gen_old, cudaStream_t st) { return launch_tc_pass<false>(P, gen_old, st); }
 int launch_pass_genes_tc(const ori_problem_t* P, int gen_old, cudaStream_t st) { return launch_tc_pass<true>(P, gen_old, st); }

@@ -39,9 +39,9 @@ class HostStreamedCAVI:
         ldx0 = (self.p + 3) // 4 * 4
         S0 = slab_rows if slab_rows is not None else max(128, min(self.n, (512 << 20) // (4 * ldx0)) // 128 * 128)
         S0 = int(min(max(1, S0), max(1, self.n)))
-        # slabs large enough to fill the machine take the tcgen05/TMA kernels (K <= 32), like the device model
-        self._tensor = self.k <= 32 and S0 * self.p >= (1 << 21)
-        KP = self._KP = 32 if self._tensor else pad_k(self.k)
+        # slabs large enough to fill the machine take the tcgen05/TMA kernels (K <= 64), like the device model
+        self._tensor = self.k <= 64 and S0 * self.p >= (1 << 21)
+        KP = self._KP = (32 if self.k <= 32 else 64) if self._tensor else pad_k(self.k)
         n, p, K, dev = self.n, self.p, self.k, self._dev
         self._shard = RowSharding(process_group, enabled=bool(sharded or process_group is not None))
         self.n_total = self._shard.total_rows(n, dev)
@@ -88,7 +88,7 @@ class HostStreamedCAVI:
             if self._xbytes != 4:
                 s['Xq'] = torch.zeros((S, p), dtype=X_host.dtype, device=dev)      # compact counts as they arrive
             if self._tensor:
-                s['tc_ws'] = torch.empty((int(self._lib.ori_tc_workspace_floats(S, p)) + 32,), **f32)
+                s['tc_ws'] = torch.empty((int(self._lib.ori_tc_workspace_floats(S, p, KP)) + 32,), **f32)
             s['stage'] = torch.zeros((2, S, K), **f32)     # unpadded a1|a2 as they travel
             self._slabs.append(s)
         self._streams = [torch.cuda.Stream(device=dev) for _ in self._slabs]

@@ -90,14 +90,14 @@ class FactorModel(metaclass=ABCMeta):
         self.n = int(cmatrix.shape[0])
         self.m = self.p = int(cmatrix.shape[1])
         self.dims = Dimensions({'n': self.n, 'm': self.m, 'p': self.p, 'k': self.k})
-        # kernel family: the tcgen05/TMA tensor path (K <= 32, tf32 contractions with fp32 accumulation) for
+        # kernel family: the tcgen05/TMA tensor path (K <= 64, tf32 contractions with fp32 accumulation) for
         # problems large enough to fill the machine, the CUDA-core fp32 kernels otherwise (or when forced)
         if tensor is None:
-            tensor = (not force_simt) and self.k <= 32 and self.n * self.p >= (1 << 21)
-        if tensor and (self.k > 32 or force_simt):
-            raise ValueError('the tensor path needs k <= 32 and force_simt=False')
+            tensor = (not force_simt) and self.k <= 64 and self.n * self.p >= (1 << 21)
+        if tensor and (self.k > 64 or force_simt):
+            raise ValueError('the tensor path needs k <= 64 and force_simt=False')
         self._tensor = bool(tensor)
-        self._KP = 32 if self._tensor else pad_k(self.k)
+        self._KP = (32 if self.k <= 32 else 64) if self._tensor else pad_k(self.k)
         self._shard = RowSharding(process_group if (sharded or process_group is not None) else None,
                                   enabled=bool(sharded or process_group is not None))
         self.n_total = self._shard.total_rows(self.n, self._dev)
@@ -179,7 +179,7 @@ class FactorModel(metaclass=ABCMeta):
         self._trace = torch.zeros((self._trace_cap,), **f64)
         self._tc_ws = None
         if self._tensor:
-            self._tc_ws = torch.empty((int(self._lib.ori_tc_workspace_floats(n, p)) + 32,), **f32)
+            self._tc_ws = torch.empty((int(self._lib.ori_tc_workspace_floats(n, p, KP)) + 32,), **f32)
 
         P = _lib.OriProblem()
         P.n_rows, P.n_total, P.ldx = n, self.n_total, ldx

@@ -6,6 +6,8 @@ import numpy as np, torch
 from oriana.models import GaP, ZIGaP
 from oriana.singlecell import synth_counts_device
 sizes = [(100_000, 20_000, 20), (250_000, 20_000, 32)]
+if 'k64' in sys.argv:
+    sizes = [(100_000, 20_000, 48), (100_000, 20_000, 64)]
 for (n, p, K) in sizes:
     X = synth_counts_device(n, p, K, seed=1)
     for cls in (ZIGaP, GaP):

@@ -8,7 +8,7 @@ Stated tolerances of the tensor path.  den = eU.eV^T and U_hat.V_hat^T are 3xTF3
 accumulating contractions R.eV, D.V_hat (and their transposes) take R, D and the factor operand rounded to
 TF32 (11-bit significand, round to nearest), so a sum of m terms carries a relative error of about
 2^-12 / sqrt(m) * few:
-  parameters a1,a2,b1,b2 : 3e-3 relative (floor 1e-6*max) on the 100 x 500 fixtures, 1e-3 at 3000 x 1500
+  parameters a1,a2,b1,b2 : 3e-3 relative (floor 1e-6*max) on the 100 x 500 fixtures, 1e-3 at 3000 x 1500 (2e-3 for K > 32)
   alpha, beta, pi        : 3e-4
   D_hat                  : 1e-3 absolute
   ELBO                   : 1e-4 relative (north_star's bound)
@@ -72,7 +72,8 @@ def test_tensor_dequirked_update_and_elbo_match_oracle(cuda_lib, name):
     assert np.max(np.abs(got - np.asarray(want)) / np.abs(want)) < 1e-4, (got, want)
 
 
-@pytest.mark.parametrize('shape', [(3000, 1500, 10), (5000, 2100, 32), (1111, 777, 5), (20000, 4500, 20)])
+@pytest.mark.parametrize('shape', [(3000, 1500, 10), (5000, 2100, 32), (1111, 777, 5), (20000, 4500, 20),
+                                   (2500, 1900, 40), (3100, 1301, 64)])      # K > 32: the KP = 64 plan (32-wide sweep tiles)
 def test_tensor_path_matches_cuda_core_path(cuda_lib, shape):
     """Many work items per SM, split sweeps, ragged last tiles on both axes, every ring wrapping around."""
     from oriana.models import GaP, ZIGaP
@@ -88,8 +89,9 @@ def test_tensor_path_matches_cuda_core_path(cuda_lib, shape):
         assert mt.uses_tensor_path and not ms.uses_tensor_path
         for t in range(3):
             mt.step(); ms.step()
+        ftol = 1e-3 if K <= 32 else 2e-3     # more components: fewer counts per (gene, component) sum, same TF32 noise
         for k in FACTORS:
-            assert relerr(getattr(mt, k).asarray(), getattr(ms, k).asarray()) < 1e-3, (cls.__name__, k)
+            assert relerr(getattr(mt, k).asarray(), getattr(ms, k).asarray()) < ftol, (cls.__name__, k)
         for k in HYPER + (('pi_d',) if cls is ZIGaP else ()):
             assert relerr(getattr(mt, k).asarray(), getattr(ms, k).asarray()) < 1e-4, (cls.__name__, k)
         et, es = mt.elbo_trace, ms.elbo_trace

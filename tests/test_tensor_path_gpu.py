@@ -161,3 +161,30 @@ def test_single_cta_variant_matches_pair_variant(cuda_lib):
     for k in out['1']:
         tol = 1e-6 if k == 'elbo' else 2e-4
         assert relerr(out['0'][k], out['1'][k]) < tol, k
+
+
+def test_host_streamed_step_on_the_tensor_path(cuda_lib):
+    """`HostStreamedCAVI` (what bench.py reports as e2e) with slabs large enough for the tcgen05 kernels, host counts
+    kept as uint16: same results as the device-resident model, slab by slab (3 ragged slabs)."""
+    import torch
+    from oriana.models import ZIGaP
+    from oriana.singlecell import synth_counts_device
+    from oriana_b200.host_step import HostStreamedCAVI
+    n, p, K = 5000, 2300, 12
+    X = synth_counts_device(n, p, K, seed=6)
+    np.random.seed(4)
+    m = ZIGaP(X[:, :p], k=K, use_factors=False, tensor=True)
+    s = m.state_dict()
+    Xh = X[:, :p].to(torch.uint16).cpu().pin_memory()
+    h = HostStreamedCAVI(Xh, K, s, dropout=True, slab_rows=2048)
+    assert h._tensor and m.uses_tensor_path
+    elbos = []
+    for _ in range(3):
+        m.step(); elbos.append(h.step())
+    hs = h.state_dict()
+    for k in FACTORS:
+        assert relerr(hs[k], getattr(m, k).asarray()) < 1e-3, k
+    for k in HYPER:
+        assert relerr(hs[k], getattr(m, k).asarray()) < 1e-4, k
+    want = m.elbo_trace[:3]
+    assert np.max(np.abs(np.asarray(elbos) - want) / np.abs(want)) < 1e-5

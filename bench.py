@@ -195,6 +195,21 @@ def main():
     trace = model.elbo_trace
     elbo_ok = bool(np.isfinite(trace).all() and np.all(np.diff(trace[1:]) >= -1e-6 * np.abs(trace[1:-1])))
 
+    # ---- the same steps without the ELBO terms (reported beside the contract number, not instead)
+    state0 = model.state_dict(); state0['X'] = X[:, :p]
+    lean = ZIGaP(X[:, :p], k=K, use_factors=False, sharded=world > 1, state=state0, elbo=False, trace_cap=W + K_steps + 8)
+    for _ in range(W):
+        lean.step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(K_steps):
+        lean.step()
+    f1.record()
+    barrier()
+    ms_step_lean = max_over_ranks(f0.elapsed_time(f1)) / K_steps
+    del lean, state0
+
     # ---- roofline of the dominant kernel (both X-streaming kernels read this rank's X once: 4 B/entry)
     peak, peak_src = load_peaks()
     alg_bytes = 4.0 * rows * p
@@ -257,6 +272,8 @@ def main():
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K_steps, 'warmup': W,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic', 'iters_per_sec': 1e3 / ms_step,
+            'without_elbo': {'ms_per_step': ms_step_lean, 'iters_per_sec': 1e3 / ms_step_lean,
+                             'value': n * p / (ms_step_lean * 1e-3)},
             'config': {'workload': workload_name(args.config, n, p, K), 'n': n, 'p': p, 'K': K,
                        'arithmetic': 'fp32 state; tensor contractions 3xTF32 (denominator, U.V^T) and TF32 operands '
                                      '(R, D_hat) with fp32 accumulation in TMEM; ELBO partial sums fp64',

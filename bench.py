@@ -110,7 +110,8 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=0)
-    ap.add_argument('--e2e-f32', action='store_true', help='keep the host copy of X as float32 (default: uint16 counts)')
+    ap.add_argument('--e2e-x', default='u8esc', choices=['u8esc', 'u16', 'f32'],
+                    help='how the host holds X for the e2e leg: saturating uint8 + escapes (default), uint16, float32')
     args = ap.parse_args()
     n, p, K = CONFIGS[args.config]
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -197,7 +198,8 @@ def main():
 
     # ---- the same steps without the ELBO terms (reported beside the contract number, not instead)
     state0 = model.state_dict(); state0['X'] = X[:, :p]
-    lean = ZIGaP(X[:, :p], k=K, use_factors=False, sharded=world > 1, state=state0, elbo=False, trace_cap=W + K_steps + 8)
+    lean = ZIGaP(X[:, :p], k=K, use_factors=False, sharded=world > 1, state=state0, elbo=False,
+                 trace_cap=2 * (W + K_steps) + 16)      # continues the iteration count of the snapshot
     for _ in range(W):
         lean.step()
     barrier()
@@ -235,12 +237,18 @@ def main():
     if not args.no_e2e:
         state = model.state_dict()
         del model
-        # counts are small integers: the host keeps them as uint16 (lossless here), half the bytes per step
-        xmax = float(X.max())
-        xdt = torch.uint16 if xmax < 65536 and not args.e2e_f32 else torch.float32
-        Xh = torch.empty((rows, p), dtype=xdt, pin_memory=True)
-        for r in range(0, rows, 1 << 16):
-            Xh[r:r + (1 << 16)].copy_(X[r:r + (1 << 16), :p].to(xdt))
+        # counts are small integers: by default the host keeps them as saturating uint8 + an escape list for the
+        # counts >= 255 (lossless, oriana_b200.host_step.CompactCounts): one byte per entry crosses PCIe per step
+        from oriana_b200.host_step import CompactCounts
+        if args.e2e_x == 'u8esc':
+            Xh = CompactCounts.from_tensor(X[:, :p])
+            xdesc = 'uint8 + %d escapes (counts >= 255)' % Xh.row.numel()
+        else:
+            xdt = torch.uint16 if (args.e2e_x == 'u16' and float(X.max()) < 65536) else torch.float32
+            Xh = torch.empty((rows, p), dtype=xdt, pin_memory=True)
+            for r in range(0, rows, 1 << 16):
+                Xh[r:r + (1 << 16)].copy_(X[r:r + (1 << 16), :p].to(xdt))
+            xdesc = str(xdt).replace('torch.', '')
         del X
         torch.cuda.empty_cache()
         host = HostStreamedCAVI(Xh, K, state, dropout=True, sharded=world > 1)
@@ -258,7 +266,7 @@ def main():
             dist.all_reduce(hb)
         e2e = {'value': n * p * n_e2e / dt, 'unit': UNIT, 'h2d_bytes_per_step': float(hb[0]) / n_e2e,
                'd2h_bytes_per_step': float(hb[1]) / n_e2e, 'steps': n_e2e, 'ms_per_step': dt / n_e2e * 1e3,
-               'host_x_dtype': str(xdt).replace('torch.', ''),
+               'host_x_dtype': xdesc,
                'api': 'oriana_b200.host_step.HostStreamedCAVI.step (pinned host X, a1, a2, b1, b2 in; results out)'}
 
     # ---- the reference's CPU path beside it (rank 0, N=1 only)

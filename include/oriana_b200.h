@@ -186,6 +186,11 @@ int ori_synth_counts_f32(float* X, int64_t ldx, int64_t row0, int64_t n_rows, in
 int ori_widen_counts_f32(const void* src, int elem_bytes, int64_t lds, float* dst, int64_t ldd,
                          int64_t rows, int32_t p, void* stream);
 
+/* Escapes of the saturating uint8 encoding: X[row[e] - row0, col[e]] = val[e] (device pointers; row = global
+ * cell index, row0 = first cell of the slab held in X).  Entries outside the slab are ignored. */
+int ori_scatter_counts_f32(float* X, int64_t ldx, int64_t row0, int64_t rows, int32_t p, const int32_t* row,
+                           const int32_t* col, const float* val, int64_t count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -135,3 +135,26 @@ extern "C" int ori_widen_counts_f32(const void* src, int elem_bytes, int64_t lds
         k_widen_counts<uint8_t><<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)src, lds, dst, ldd, rows, p);
     return check_launch("k_widen_counts");
 }
+
+// Escapes of the saturating uint8 encoding: X[row[e] - row0, col[e]] = val[e] for the entries whose count does not
+// fit a byte (stored as 255 in the compact matrix).  row is the GLOBAL cell index, row0 the first cell of the slab.
+__global__ void __launch_bounds__(256)
+k_scatter_counts(float* __restrict__ X, long long ldx, long long row0, long long rows, int p,
+                 const int* __restrict__ row, const int* __restrict__ col, const float* __restrict__ val, long long count)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    const long long r = (long long)row[e] - row0;
+    const int c = col[e];
+    if (r >= 0 && r < rows && c >= 0 && c < p) X[r * ldx + c] = val[e];
+}
+
+extern "C" int ori_scatter_counts_f32(float* X, int64_t ldx, int64_t row0, int64_t rows, int32_t p, const int32_t* row,
+                                      const int32_t* col, const float* val, int64_t count, void* stream)
+{
+    if (!X || ldx < p || p <= 0 || rows < 0 || count < 0 || (count && (!row || !col || !val)))
+        return set_error(ORI_EINVAL, "ori_scatter_counts_f32: bad argument");
+    if (count == 0 || rows == 0) return ORI_OK;
+    k_scatter_counts<<<cdiv(count, 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, row0, rows, p, row, col, val, count);
+    return check_launch("k_scatter_counts");
+}

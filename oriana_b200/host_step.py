@@ -21,16 +21,73 @@ from .models.base import pad_k
 from .sharding import RowSharding
 
 
+class CompactCounts:
+    """A count matrix held on the host as saturating uint8 plus an escape list for the (rare) counts >= 255:
+    one byte per entry crosses PCIe per step instead of four.  Lossless: `dense()` gives the counts back.
+
+        u8    [n, p] uint8, min(X, 255)              (pinned)
+        row, col, val  escapes sorted by row: X[row, col] = val  (int32, int32, float32; pinned)
+    """
+
+    def __init__(self, u8, row, col, val):
+        assert u8.dtype == torch.uint8 and u8.dim() == 2 and not u8.is_cuda
+        assert row.dtype == torch.int32 and col.dtype == torch.int32 and val.dtype == torch.float32
+        assert row.numel() == col.numel() == val.numel()
+        self.u8, self.row, self.col, self.val = u8, row, col, val
+        self.shape = tuple(u8.shape)
+        # escapes of slab [r0, r1) = [bounds(r0), bounds(r1)) in the row-sorted list
+        self._row_np = row.numpy()
+        assert (np.diff(self._row_np) >= 0).all(), 'escape list must be sorted by row'
+
+    @classmethod
+    def from_tensor(cls, X, chunk_rows=1 << 15, pin=True):
+        """Encode a [n, p] count tensor (any real dtype, host or device; non-negative integers)."""
+        n, p = X.shape
+        u8 = torch.empty((n, p), dtype=torch.uint8, pin_memory=pin and torch.cuda.is_available())
+        rows, cols, vals = [], [], []
+        for r in range(0, n, chunk_rows):
+            blk = X[r:r + chunk_rows]
+            big = blk >= 255
+            u8[r:r + chunk_rows].copy_(torch.clamp(blk, max=255).to(torch.uint8))
+            idx = big.nonzero(as_tuple=False)
+            if idx.numel():
+                rows.append((idx[:, 0] + r).to(torch.int32).cpu()); cols.append(idx[:, 1].to(torch.int32).cpu())
+                vals.append(blk[big].to(torch.float32).cpu())
+
+        def cat(parts, dt):
+            t = torch.cat(parts) if parts else torch.empty((0,), dtype=dt)
+            return t.pin_memory() if (pin and torch.cuda.is_available() and t.numel()) else t
+        return cls(u8, cat(rows, torch.int32), cat(cols, torch.int32), cat(vals, torch.float32))
+
+    def escapes(self, r0, r1):
+        lo = int(np.searchsorted(self._row_np, r0, side='left')); hi = int(np.searchsorted(self._row_np, r1, side='left'))
+        return lo, hi
+
+    def dense(self):
+        X = self.u8.to(torch.float32)
+        if self.row.numel():
+            X[self.row.long(), self.col.long()] = self.val
+        return X
+
+    @property
+    def nbytes(self):
+        return self.u8.numel() + 12 * self.row.numel()
+
+
 class HostStreamedCAVI:
 
     def __init__(self, X_host, k, state, dropout=True, compat_quirk=False, slab_rows=None, sharded=False,
                  process_group=None, elbo=True, keep_hyper=True):
         """X_host: CPU tensor [n, p] (pin it for asynchronous copies), float32 like the array the reference
         feeds its kernel (zigap.py:112) or the same counts kept compactly as uint16 / uint8 (half / a quarter of
-        the bytes per step over PCIe; widened to float32 on the device).  state: host arrays a1, a2 [n, k],
+        the bytes per step over PCIe; widened to float32 on the device), or a `CompactCounts` (saturating uint8
+        plus an escape list for counts >= 255).  state: host arrays a1, a2 [n, k],
         b1, b2 [p, k], alpha1, alpha2, beta1, beta2 [k] (a reference model's state vector)."""
         self._dev = _lib.require_cuda()
         self._lib = _lib.load()
+        self._compact = X_host if isinstance(X_host, CompactCounts) else None
+        if self._compact is not None:
+            X_host = self._compact.u8                  # saturating bytes; the escapes follow each slab
         assert X_host.dtype in (torch.float32, torch.uint16, torch.uint8) and X_host.dim() == 2 and not X_host.is_cuda
         self.X = X_host
         self._xbytes = X_host.element_size()
@@ -87,6 +144,10 @@ class HostStreamedCAVI:
                 s[name] = torch.zeros((S, KP), **f32)
             if self._xbytes != 4:
                 s['Xq'] = torch.zeros((S, p), dtype=X_host.dtype, device=dev)      # compact counts as they arrive
+            if self._compact is not None:
+                cap = max(1024, int(4 * self._compact.row.numel() * S / max(1, n)) + 1024)
+                s['esc'] = [torch.zeros((cap,), dtype=torch.int32, device=dev), torch.zeros((cap,), dtype=torch.int32, device=dev),
+                            torch.zeros((cap,), dtype=torch.float32, device=dev)]
             if self._tensor:
                 s['tc_ws'] = torch.empty((int(self._lib.ori_tc_workspace_floats(S, p, KP)) + 32,), **f32)
             s['stage'] = torch.zeros((2, S, K), **f32)     # unpadded a1|a2 as they travel
@@ -141,8 +202,20 @@ class HostStreamedCAVI:
             s['X'][:rows, :p].copy_(self.X[r0:r0 + rows], non_blocking=True)
         else:
             s['Xq'][:rows].copy_(self.X[r0:r0 + rows], non_blocking=True)
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
             _lib.check(self._lib.ori_widen_counts_f32(s['Xq'].data_ptr(), self._xbytes, p, s['X'].data_ptr(), self._ldx,
-                                                      rows, p, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                                                      rows, p, st))
+            if self._compact is not None:
+                lo, hi = self._compact.escapes(r0, r0 + rows)
+                cnt = hi - lo
+                if cnt:
+                    if cnt > s['esc'][0].numel():          # a slab with unusually many large counts: grow its buffers
+                        s['esc'] = [torch.zeros((2 * cnt,), dtype=t.dtype, device=t.device) for t in s['esc']]
+                    for dst, src in zip(s['esc'], (self._compact.row, self._compact.col, self._compact.val)):
+                        dst[:cnt].copy_(src[lo:hi], non_blocking=True)
+                    _lib.check(self._lib.ori_scatter_counts_f32(s['X'].data_ptr(), self._ldx, r0, rows, p, s['esc'][0].data_ptr(),
+                                                                s['esc'][1].data_ptr(), s['esc'][2].data_ptr(), cnt, st))
+                    self.h2d_bytes += 12 * cnt
         s['stage'][0, :rows].copy_(self.a1[r0:r0 + rows], non_blocking=True)
         s['stage'][1, :rows].copy_(self.a2[r0:r0 + rows], non_blocking=True)
         s['a1'][:rows, :K] = s['stage'][0, :rows]; s['a2'][:rows, :K] = s['stage'][1, :rows]

@@ -220,6 +220,19 @@ def test_host_streamed_step_with_compact_counts(cuda_lib):
         for k in PARAMS:
             assert relerr(h.state_dict()[k], ref.state_dict()[k]) < 5e-6, (dt, k)
         assert h.h2d_bytes < ref.h2d_bytes
+    # saturating uint8 + escapes: counts >= 255 survive
+    from oriana_b200.host_step import CompactCounts
+    s2 = dict(s); X2 = s['X'].copy(); X2[3, 7] = 255; X2[100, 330] = 70000; X2[192, 0] = 256; s2['X'] = X2
+    X2f = torch.as_tensor(X2.astype(np.float32))
+    cc = CompactCounts.from_tensor(X2f, chunk_rows=50)
+    assert cc.row.numel() == 3 and torch.equal(cc.dense(), X2f)
+    ref2 = HostStreamedCAVI(X2f.pin_memory(), K, s2, dropout=True, slab_rows=64)
+    h2 = HostStreamedCAVI(cc, K, s2, dropout=True, slab_rows=64)
+    for _ in range(2):
+        ref2.step(); h2.step()
+    for k in PARAMS:
+        assert relerr(h2.state_dict()[k], ref2.state_dict()[k]) < 5e-6, ('u8esc', k)
+    assert h2.h2d_bytes < 0.5 * ref2.h2d_bytes       # X: 1 byte instead of 4 per entry (+ a1, a2, escapes)
     # the kernel itself, odd sizes and strides
     rng = np.random.default_rng(0)
     for rows, p, lds in ((7, 13, 13), (33, 130, 131), (5, 64, 64)):

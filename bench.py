@@ -283,8 +283,8 @@ def main():
             'without_elbo': {'ms_per_step': ms_step_lean, 'iters_per_sec': 1e3 / ms_step_lean,
                              'value': n * p / (ms_step_lean * 1e-3)},
             'config': {'workload': workload_name(args.config, n, p, K), 'n': n, 'p': p, 'K': K,
-                       'arithmetic': 'fp32 state; tensor contractions 3xTF32 (denominator, U.V^T) and TF32 operands '
-                                     '(R, D_hat) with fp32 accumulation in TMEM; ELBO partial sums fp64',
+                       'arithmetic': 'fp32 state; denominator and U.V^T split-precision on the tensor cores (tf32 hi.hi + bf16 cross '
+                                     'terms, ~2^-21); R and D_hat as TF32 operands, fp32 accumulation in TMEM; ELBO partial sums fp64',
                        'cells_per_rank': rows, 'parallelism': 'cells sharded over %d rank(s); 2 sum-allreduces/iter' % world,
                        'l2': 'X per rank is %.1f GB, far larger than the 126 MB L2: no flush between steps' % (alg_bytes / 1e9)},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'clocks': clocks,

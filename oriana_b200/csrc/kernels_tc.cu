@@ -4,8 +4,8 @@
 //
 // Per tile of 128 "own" x SW "sweep" entries (own = cells in the row pass, genes in the gene pass; SW = 64 for a
 // padded latent dimension KP = 32, SW = 32 for KP = 64, so that the tile always fits the same TMEM / smem plan):
-//   S:  den = eO . eS^T     (3xTF32: hi.hi + hi.lo + lo.hi)          zigap.py:86-90
-//       uv  = Oh . Sh^T     (3xTF32)                                 zigap.py:131 (U_hat V_hat^T)
+//   S:  den = eO . eS^T     (hi.hi in tf32 + hi.lo + lo.hi in bf16)  zigap.py:86-90
+//       uv  = Oh . Sh^T     (same split)                             zigap.py:131 (U_hat V_hat^T)
 //   E:  R = X / den ; D = X != 0 ? 1 : max(sigmoid(lp - uv), floor)  zigap.py:91-92, :131-136
 //       (written back over den / uv in TMEM, rounded to tf32 to nearest)
 //   P:  acc1 += R . S1 ; acc2 += D . S2                              zigap.py:93-94 / :116, :124
@@ -36,6 +36,11 @@
 
 namespace ori {
 using namespace tc;
+
+#ifndef ORI_TC_BF16X
+#define ORI_TC_BF16X 1     // 1: the two cross terms hi.lo + lo.hi of every 3xTF32 contraction run as ONE bf16 chain over
+                           //    [hi | lo] . [lo | hi] (error 2^-9 of a 2^-12 term): 4 instead of 6 MMA chains per tile
+#endif
 
 constexpr int TC_OWN = 128;
 constexpr int NEW = 8;                // element-wise warps (more of them only get 96 registers each: measured slower)
@@ -320,6 +325,11 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             auto mma = [&](uint32_t d, uint32_t at, uint64_t bd, uint32_t idesc, bool acc) {
                 if (PAIR) mma_tf32_ts_pair(d, at, bd, idesc, acc); else mma_tf32_ts(d, at, bd, idesc, acc);
             };
+            auto mma16 = [&](uint32_t d, uint32_t at, uint64_t bd, uint32_t idesc, bool acc) {
+                if (PAIR) mma_bf16_ts_pair(d, at, bd, idesc, acc); else mma_bf16_ts(d, at, bd, idesc, acc);
+            };
+            constexpr uint32_t idescS16 = make_idesc_bf16(TC_OWN * NCTA, SW);
+            (void)idescS16; (void)mma16;
             auto commit = [&](uint64_t* bar) { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); };
             auto issue_P = [&](uint32_t it, bool first, bool last, int li) {
                 const uint32_t s = it & 1, ts = it % TST;
@@ -367,6 +377,21 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                         mma((D_), tmem + TM_A + (QA) * KP + kk * 8,                                               \
                             kd + (uint64_t)(((QB) * C::K_ARR + (kk >> 2) * C::K_BLK + (kk & 3) * 32) >> 4), idescS, \
                             !((FRESH) && kk == 0))
+#if ORI_TC_BF16X
+                    // arrays 1 and 3 hold bf16 pairs: own side [hi | lo], sweep side [lo | hi] (2 KP elements, the
+                    // same bytes and the same 8-column / 32-byte steps as a tf32 array)
+#define ORI_CHAIN16(D_, Q)                                                                                        \
+                    _Pragma("unroll") for (int kk = 0; kk < KP / 8; ++kk)                                         \
+                        mma16((D_), tmem + TM_A + (Q) * KP + kk * 8,                                              \
+                              kd + (uint64_t)(((Q) * C::K_ARR + (kk >> 2) * C::K_BLK + (kk & 3) * 32) >> 4), idescS16, true)
+                    ORI_CHAIN(tmem + s * TM_STAGE, 0, 0, true);
+                    ORI_CHAIN16(tmem + s * TM_STAGE, 1);
+                    if (DROPOUT) {
+                        ORI_CHAIN(tmem + s * TM_STAGE + SW, 2, 2, true);
+                        ORI_CHAIN16(tmem + s * TM_STAGE + SW, 3);
+                    }
+#undef ORI_CHAIN16
+#else
                     ORI_CHAIN(tmem + s * TM_STAGE, 0, 0, true);
                     ORI_CHAIN(tmem + s * TM_STAGE, 0, 1, false);
                     ORI_CHAIN(tmem + s * TM_STAGE, 1, 0, false);
@@ -375,6 +400,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                         ORI_CHAIN(tmem + s * TM_STAGE + SW, 2, 3, false);
                         ORI_CHAIN(tmem + s * TM_STAGE + SW, 3, 2, false);
                     }
+#endif
 #undef ORI_CHAIN
                     commit(&bars[B_SREADY + s]);
                     commit(&bars[B_KEMPTY + ks_]);
@@ -427,7 +453,19 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                             wlo[e] = __float_as_uint(v - hi);
                         }
                         tmem_st16(tlane + TM_A + (2 * slice) * KP + 32 * kb + 16 * h, whi);
+#if ORI_TC_BF16X
+                        // cross-term operand [hi | lo] as bf16 pairs: these 16 components -> 8 + 8 columns
+                        uint32_t phi[8], plo[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            phi[e] = pack_bf16x2(__uint_as_float(whi[2 * e]), __uint_as_float(whi[2 * e + 1]));
+                            plo[e] = pack_bf16x2(__uint_as_float(wlo[2 * e]), __uint_as_float(wlo[2 * e + 1]));
+                        }
+                        tmem_st8(tlane + TM_A + (2 * slice + 1) * KP + 16 * kb + 8 * h, phi);
+                        tmem_st8(tlane + TM_A + (2 * slice + 1) * KP + KP / 2 + 16 * kb + 8 * h, plo);
+#else
                         tmem_st16(tlane + TM_A + (2 * slice + 1) * KP + 32 * kb + 16 * h, wlo);
+#endif
                     }
                 }
             }
@@ -679,6 +717,23 @@ k_tc_prep_K(const float* __restrict__ e, const float* __restrict__ E, float Esca
     const float v = ok ? e[idx] : 0.f;
     const float hv = to_tf32_rna(v);
     out[idx] = hv;
+#if ORI_TC_BF16X
+    // arrays 1 and 3: row i = 2 KP bf16 [lo(0..KP-1) | hi(0..KP-1)], i.e. KP 32-bit words; this thread writes word w
+    const long long i = idx / KP;
+    const int w = (int)(idx - i * KP), half = KP / 2;
+    const int k0 = 2 * (w < half ? w : w - half);
+    auto word = [&](const float* src, float scale) -> uint32_t {
+        const float a = ok ? src[i * KP + k0] * scale : 0.f, b = ok ? src[i * KP + k0 + 1] * scale : 0.f;
+        const float ha = to_tf32_rna(a), hb = to_tf32_rna(b);
+        return w < half ? pack_bf16x2(a - ha, b - hb) : pack_bf16x2(ha, hb);
+    };
+    reinterpret_cast<uint32_t*>(out)[pad * KP + idx] = word(e, 1.f);
+    if (E) {
+        const float x = ok ? E[idx] * Escale : 0.f;
+        out[2 * pad * KP + idx] = to_tf32_rna(x);
+        reinterpret_cast<uint32_t*>(out)[3 * pad * KP + idx] = word(E, Escale);
+    }
+#else
     out[pad * KP + idx] = v - hv;
     if (E) {
         const float w = ok ? E[idx] * Escale : 0.f;
@@ -686,6 +741,7 @@ k_tc_prep_K(const float* __restrict__ e, const float* __restrict__ E, float Esca
         out[2 * pad * KP + idx] = hw;
         out[3 * pad * KP + idx] = w - hw;
     }
+#endif
 }
 // transposed operand: out[k][i] = tf32(src[i][k]),  src [n x KP], out [KP x pad]; grid (pad / 32, KP / 32)
 __global__ void __launch_bounds__(256)

@@ -4,7 +4,8 @@
   * the oracle port for the de-quirked update and the ELBO,
   * the CUDA-core path of the same library at sizes where work items, chunks and ring wrap-around all occur.
 
-Stated tolerances of the tensor path.  den = eU.eV^T and U_hat.V_hat^T are 3xTF32 (fp32-grade); the two
+Stated tolerances of the tensor path.  den = eU.eV^T and U_hat.V_hat^T are split-precision (hi.hi in TF32 plus the two
+cross terms in one bf16 chain: relative error about 2^-21, fp32-grade); the two
 accumulating contractions R.eV, D.V_hat (and their transposes) take R, D and the factor operand rounded to
 TF32 (11-bit significand, round to nearest), so a sum of m terms carries a relative error of about
 2^-12 / sqrt(m) * few:
@@ -138,7 +139,8 @@ def test_tensor_path_config2_matches_oracle(cuda_lib):
 
 def test_single_cta_variant_matches_pair_variant(cuda_lib):
     """ORI_TC_PAIR=0 (single-CTA kernels, kept for A/B runs) against the default CTA-pair kernels: same state
-    after three steps up to accumulation order.  The switch is read once per process, hence the subprocess."""
+    after three steps up to accumulation order (two runs of the SAME variant differ by up to 1.2e-4 in b2 here, from the
+    order of the float atomics: scripts/gpu_stress_repeat.py).  The switch is read once per process, hence the subprocess."""
     import os, subprocess, sys, tempfile
     from oriana.models import ZIGaP
     from oriana.singlecell import synth_counts_device
@@ -159,7 +161,7 @@ def test_single_cta_variant_matches_pair_variant(cuda_lib):
             subprocess.run([sys.executable, '-c', code, f], check=True, env=env, timeout=300)
             out[pair] = dict(np.load(f))
     for k in out['1']:
-        tol = 1e-6 if k == 'elbo' else 2e-4
+        tol = 1e-5 if k == 'elbo' else 5e-4
         assert relerr(out['0'][k], out['1'][k]) < tol, k
 
 

@@ -39,6 +39,8 @@ extern "C" {
 #define ORI_F_QUIRK 2u        /* reproduce zigap.py:94: Zj weighted by D_hat[i, k] instead of D_hat[i, j] */
 #define ORI_F_ELBO 4u         /* accumulate the ELBO terms inside the row pass                            */
 #define ORI_F_NO_TENSOR 8u    /* force the CUDA-core kernels (tests); default picks tcgen05 when it can   */
+#define ORI_F_SPARSE 16u      /* SparseZIGaP: spike-and-slab layer S on V (sparse_zigap.py:100-204); needs
+                                 ORI_F_DROPOUT, the `sparse` block below, K <= 32; CUDA-core kernels, no ELBO */
 
 /* modes of ori_mstep */
 #define ORI_M_STEP 0          /* regular end of iteration t+1: finalise ELBO(t), pi(t); M-step; next lp   */
@@ -96,6 +98,20 @@ typedef struct ori_problem {
      * Needs KP == 32 (K <= 32) or KP == 64 (K <= 64), zero padded. */
     float* tc_ws;
     int64_t tc_ws_floats;
+
+    /* SparseZIGaP (ORI_F_SPARSE).  With this flag b1, b2 parametrise V' (sparse_zigap.py:24-28), eV holds
+     * exp(E[log V']) without the mask, V_hat holds the EFFECTIVE factor S_hat * V'_hat (:140) and red32 is
+     * [3 x p x KP]: Zj | b2s | Zl, the third block being sum_i R_ij eU_ik E[log U_ik] (:116).
+     * Gene-side arrays are [p x KP] float32. */
+    float* p_s;            /* Bernoulli parameter of q(S) = S_hat (float32(p_s), bernoulli.py:45)          */
+    float* logV;           /* E[log V'] (read by :116 and :157)                                            */
+    float* eVd;            /* eV * (p_s > tau): denominator operand (:103-104, :134)                       */
+    float* eVz;            /* eVd * S_hat: operand of the row sums (:114)                                  */
+    float* Vh_old;         /* S_hat * V'_hat of the PREVIOUS iteration: generates the current D_hat
+                              (:166 multiplies the new U_hat with the V_hat local of :140)                 */
+    float* eUl[2];         /* row side, per generation: eU * E[log U] (operand of :116)                    */
+    double* pi_s;          /* [p] prior of S, row means of p_s (:196), float64                             */
+    double tau;            /* threshold of S_tilde (:134)                                                  */
 } ori_problem_t;
 
 /* ---- library ---------------------------------------------------------------------------------- */
@@ -154,6 +170,18 @@ int ori_finalize_local(const ori_problem_t* P, int gen, void* stream);
 /* Materialise D_hat = float32(p_d) (zigap.py:131-136) for rows [row0, row0+nrows) of generation gen. */
 int ori_dropout_posterior_f32(const ori_problem_t* P, int gen, float* out, int64_t ldo,
                               int64_t row0, int64_t nrows, void* stream);
+
+/* ---- convergence metrics of the reference's drivers (base.py:58-82, sparse_zigap.py:44-51) ------- */
+/* out[c] = sum_i X[i, c] over this rank's rows, float64 (device pointers). */
+int ori_column_sums_f64(const float* X, int64_t ldx, int64_t n_rows, int32_t p, double* out, void* stream);
+/* The three zero-inflated Poisson log-likelihood sums behind reconstruction_deviance / explained_deviance for
+ * this rank's rows: rate = U_hat V_hat^T masked where round(D_hat) == 0 (base.py:64-67), rate = X (saturated,
+ * :68), rate = column means of X (:76; col_mean [p] float64, all ranks).  pi [p] float64 = the finalised pi_d.
+ * out_int[3]: every entry's term truncated toward zero to int64 before a wrapping sum, exactly what the
+ * reference's integer output buffer does (sparse_zigap.py:45; -inf / NaN become INT64_MIN); out_f64[3]: the
+ * plain float64 sums.  Both are ACCUMULATED into (caller zero-fills). */
+int ori_deviance_sums(const ori_problem_t* P, int gen, const double* pi, const double* col_mean,
+                      long long* out_int, double* out_f64, void* stream);
 
 /* ---- operator-level drop-ins with HOST buffers (the reference's plugin seam) -------------------- */
 /* Same argument list and semantics as `ZIGaP.compute_Z_q_expectations` (zigap.py:79-95): every array

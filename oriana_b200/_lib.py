@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('ORIANA_B200_LIB') or os.path.join(_HERE, 'lib', 'liboriana_b200.so')   # override: kernel A/B runs
 
-ORI_F_DROPOUT, ORI_F_QUIRK, ORI_F_ELBO, ORI_F_NO_TENSOR = 1, 2, 4, 8
+ORI_F_DROPOUT, ORI_F_QUIRK, ORI_F_ELBO, ORI_F_NO_TENSOR, ORI_F_SPARSE = 1, 2, 4, 8, 16
 ORI_M_STEP, ORI_M_INIT, ORI_M_INIT_KEEP, ORI_M_FINALIZE, ORI_M_REFRESH = 0, 1, 2, 3, 4
 R64_NSLOTS = 8
 SCAL_SLOTS = 16
@@ -33,6 +33,8 @@ class OriProblem(C.Structure):
         ('hyper', C.c_void_p), ('red64', C.c_void_p), ('gsum', C.c_void_p), ('pi_d', C.c_void_p),
         ('scal', C.c_void_p), ('elbo_trace', C.c_void_p),
         ('tc_ws', C.c_void_p), ('tc_ws_floats', C.c_int64),
+        ('p_s', C.c_void_p), ('logV', C.c_void_p), ('eVd', C.c_void_p), ('eVz', C.c_void_p), ('Vh_old', C.c_void_p),
+        ('eUl', C.c_void_p * 2), ('pi_s', C.c_void_p), ('tau', C.c_double),
     ]
 
 
@@ -60,6 +62,8 @@ _SIGNATURES = {
     'ori_cavi_step_global': ([_PP, C.c_int, C.c_void_p], C.c_int),
     'ori_finalize_local': ([_PP, C.c_int, C.c_void_p], C.c_int),
     'ori_dropout_posterior_f32': ([_PP, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p], C.c_int),
+    'ori_column_sums_f64': ([C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
+    'ori_deviance_sums': ([_PP, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
     'ori_zigap_compute_Z_q_expectations_host': ([C.c_void_p] * 7 + [C.c_int64] * 3 + [C.c_int], C.c_int),
     'ori_gap_compute_Z_q_expectations_host': ([C.c_void_p] * 5 + [C.c_int64] * 3, C.c_int),
     'ori_widen_counts_f32': ([C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p], C.c_int),

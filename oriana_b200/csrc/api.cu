@@ -158,6 +158,15 @@ int ori_problem_check(const ori_problem_t* P) {
     if (P->flags & ORI_F_DROPOUT)
         if (!P->a2s || !P->lp || !P->pfloor || !P->pi_d) return set_error(ORI_EINVAL, "dropout buffers missing");
     if ((P->flags & ORI_F_QUIRK) && !P->eUw) return set_error(ORI_EINVAL, "quirk mode needs eUw");
+    if (P->flags & ORI_F_SPARSE) {
+        if (!(P->flags & ORI_F_DROPOUT) || (P->flags & (ORI_F_QUIRK | ORI_F_ELBO)))
+            return set_error(ORI_EINVAL, "ORI_F_SPARSE needs ORI_F_DROPOUT and excludes ORI_F_QUIRK / ORI_F_ELBO");
+        if (P->KP > 32) return set_error(ORI_EUNSUPPORTED, "the sparse model needs K <= 32 (got %d)", P->K);
+        if (!P->p_s || !P->logV || !P->eVd || !P->eVz || !P->Vh_old || !P->eUl[0] || !P->eUl[1] || !P->pi_s)
+            return set_error(ORI_EINVAL, "sparse buffers missing");
+        if (((uintptr_t)P->eVd & 15) || ((uintptr_t)P->eVz & 15) || ((uintptr_t)P->Vh_old & 15))
+            return set_error(ORI_EINVAL, "eVd, eVz, Vh_old must be 16-byte aligned");
+    }
     if (((uintptr_t)P->X & 15) || ((uintptr_t)P->eV & 15) || ((uintptr_t)P->V_hat & 15))
         return set_error(ORI_EINVAL, "X, eV, V_hat must be 16-byte aligned");
     return ORI_OK;
@@ -236,7 +245,7 @@ static int zero_accumulators(const ori_problem_t* P, cudaStream_t st, bool genes
         ORI_CUDA(cudaMemsetAsync(P->Zi, 0, rowf_bytes(P), st));
         if (P->flags & ORI_F_DROPOUT) ORI_CUDA(cudaMemsetAsync(P->a2s, 0, rowf_bytes(P), st));
     }
-    if (genes) ORI_CUDA(cudaMemsetAsync(P->red32, 0, sizeof(float) * 2 * (size_t)P->p * P->KP, st));
+    if (genes) ORI_CUDA(cudaMemsetAsync(P->red32, 0, sizeof(float) * ((P->flags & ORI_F_SPARSE) ? 3 : 2) * (size_t)P->p * P->KP, st));
     ORI_CUDA(cudaMemsetAsync(P->red64, 0, red64_bytes(P), st));
     return ORI_OK;
 }
@@ -288,6 +297,21 @@ int ori_dropout_posterior_f32(const ori_problem_t* P, int gen, float* out, int64
     if (!(P->flags & ORI_F_DROPOUT)) return set_error(ORI_EINVAL, "model has no dropout layer");
     if (!out || ldo < P->p || row0 < 0 || row0 + nrows > P->n_rows) return set_error(ORI_EINVAL, "bad slab");
     return launch_dropout_posterior(P, gen, out, ldo, row0, nrows, (cudaStream_t)stream);
+}
+
+int ori_column_sums_f64(const float* X, int64_t ldx, int64_t n_rows, int32_t p, double* out, void* stream) {
+    if (n_rows < 0 || p <= 0 || ldx < p || !out || (n_rows > 0 && !X)) return set_error(ORI_EINVAL, "ori_column_sums_f64: bad argument");
+    ORI_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)p, (cudaStream_t)stream));
+    return launch_col_sums(X, ldx, n_rows, p, out, (cudaStream_t)stream);
+}
+
+int ori_deviance_sums(const ori_problem_t* P, int gen, const double* pi, const double* col_mean,
+                      long long* out_int, double* out_f64, void* stream) {
+    ORI_TRY(ori_problem_check(P));
+    if (!(P->flags & ORI_F_DROPOUT)) return set_error(ORI_EINVAL, "the deviance metrics need the dropout layer (sparse_zigap.py:44-51)");
+    if (!pi || !col_mean || !out_int || !out_f64 || gen < 0 || gen > 1) return set_error(ORI_EINVAL, "ori_deviance_sums: bad argument");
+    if (P->n_rows == 0) return ORI_OK;
+    return launch_deviance(P, gen, pi, col_mean, out_int, out_f64, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -42,11 +42,15 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* sbuf) {
 constexpr int PR_TR = 128;
 constexpr int PR_TG = 32;
 
-template <int KP, bool DROPOUT, bool ELBO>
+// SPARSE (sparse_zigap.py:100-116, :140-142, :166): the denominator operand eV carries the mask S_tilde, the row
+// sums contract with eVz = eV * S_hat, D_hat is rebuilt from Vh = the PREVIOUS effective V_hat and the rate sums
+// contract with Vc = the current one.  Otherwise eVz == eV and Vc == Vh (not read).
+template <int KP, bool DROPOUT, bool ELBO, bool SPARSE>
 __global__ void __launch_bounds__(PR_TR)
 k_pass_rows(const float* __restrict__ X, long long ldx, long long n_rows, int p,
             const float* __restrict__ eU, const float* __restrict__ Uh,
             const float* __restrict__ eV, const float* __restrict__ Vh,
+            const float* __restrict__ eVz, const float* __restrict__ Vc,
             const float* __restrict__ lp, const float* __restrict__ pfloor,
             float* __restrict__ Zi, float* __restrict__ a2s,
             double* __restrict__ colsum, double* __restrict__ part64)
@@ -54,6 +58,8 @@ k_pass_rows(const float* __restrict__ X, long long ldx, long long n_rows, int p,
     __shared__ float sX[PR_TR][PR_TG + 1];
     __shared__ __align__(16) float sV[PR_TG][KP];
     __shared__ __align__(16) float sVh[DROPOUT ? PR_TG : 1][KP];
+    __shared__ __align__(16) float sVz[SPARSE ? PR_TG : 1][KP];
+    __shared__ __align__(16) float sVc[SPARSE ? PR_TG : 1][KP];
     __shared__ float slp[PR_TG], sfl[PR_TG];
     __shared__ float scs[PR_TR / 32][PR_TG];
     __shared__ double sred[PR_TR / 32];
@@ -86,11 +92,17 @@ k_pass_rows(const float* __restrict__ X, long long ldx, long long n_rows, int p,
         }
         float* sVf = &sV[0][0];
         float* sVhf = &sVh[0][0];
+        float* sVzf = &sVz[0][0];
+        float* sVcf = &sVc[0][0];
         for (int idx = tid; idx < PR_TG * KP; idx += PR_TR) {
             const int g = idx / KP;
             const bool ok = g < gcount;
             sVf[idx] = ok ? eV[(long long)j0 * KP + idx] : 0.f;
             if (DROPOUT) sVhf[idx] = ok ? Vh[(long long)j0 * KP + idx] : 0.f;
+            if (SPARSE) {
+                sVzf[idx] = ok ? eVz[(long long)j0 * KP + idx] : 0.f;
+                sVcf[idx] = ok ? Vc[(long long)j0 * KP + idx] : 0.f;
+            }
         }
         if (DROPOUT && tid < PR_TG) {
             slp[tid] = tid < gcount ? lp[j0 + tid] : 0.f;
@@ -127,13 +139,15 @@ k_pass_rows(const float* __restrict__ X, long long ldx, long long n_rows, int p,
                 sX[tid][g] = row_ok ? D : 0.f;           // for the column sums below
             }
             if (ELBO && nz) t_xl = fmaf(x, logf(den), t_xl);
+            const float4* z4 = SPARSE ? reinterpret_cast<const float4*>(&sVz[SPARSE ? g : 0][0]) : v4;
+            const float4* c4 = SPARSE ? reinterpret_cast<const float4*>(&sVc[SPARSE ? g : 0][0]) : h4;
 #pragma unroll
             for (int q = 0; q < KP / 4; ++q) {
-                const float4 v = v4[q];
+                const float4 v = z4[q];
                 zi[4 * q + 0] = fmaf(R, v.x, zi[4 * q + 0]); zi[4 * q + 1] = fmaf(R, v.y, zi[4 * q + 1]);
                 zi[4 * q + 2] = fmaf(R, v.z, zi[4 * q + 2]); zi[4 * q + 3] = fmaf(R, v.w, zi[4 * q + 3]);
                 if (DROPOUT) {
-                    const float4 h = h4[q];
+                    const float4 h = c4[q];
                     as[4 * q + 0] = fmaf(D, h.x, as[4 * q + 0]); as[4 * q + 1] = fmaf(D, h.y, as[4 * q + 1]);
                     as[4 * q + 2] = fmaf(D, h.z, as[4 * q + 2]); as[4 * q + 3] = fmaf(D, h.w, as[4 * q + 3]);
                 }
@@ -181,15 +195,18 @@ k_pass_rows(const float* __restrict__ X, long long ldx, long long n_rows, int p,
 constexpr int PG_TG = 128;
 constexpr int PG_TR = 32;
 
-template <int KP, bool DROPOUT, bool QUIRK>
+// SPARSE: eV = the masked denominator operand, Vh = the previous effective V_hat (see k_pass_rows), and a third
+// sum Zl[j,k] = sum_i R_ij eU_ik E[log U_ik] (sparse_zigap.py:116) with the sweep operand eUl = eU * E[log U].
+template <int KP, bool DROPOUT, bool QUIRK, bool SPARSE>
 __global__ void __launch_bounds__(PG_TG)
 k_pass_genes(const float* __restrict__ X, long long ldx, long long n_rows, int p, int rows_per_chunk,
              const float* __restrict__ eU, const float* __restrict__ eUw, const float* __restrict__ Uh,
-             const float* __restrict__ Un,
+             const float* __restrict__ Un, const float* __restrict__ eUl,
              const float* __restrict__ eV, const float* __restrict__ Vh,
              const float* __restrict__ lp, const float* __restrict__ pfloor,
-             float* __restrict__ Zj, float* __restrict__ b2s)
+             float* __restrict__ Zj, float* __restrict__ b2s, float* __restrict__ Zl)
 {
+    __shared__ __align__(16) float sUl[SPARSE ? PG_TR : 1][KP];
     __shared__ __align__(16) float sU[PG_TR][KP];
     __shared__ __align__(16) float sUw[QUIRK ? PG_TR : 1][KP];
     __shared__ __align__(16) float sUh[DROPOUT ? PG_TR : 1][KP];
@@ -201,17 +218,19 @@ k_pass_genes(const float* __restrict__ X, long long ldx, long long n_rows, int p
     const long long r_begin = (long long)blockIdx.y * rows_per_chunk;
     const long long r_end = min(n_rows, r_begin + rows_per_chunk);
 
-    float ev[KP], vh[DROPOUT ? KP : 1], zj[KP], bs[DROPOUT ? KP : 1];
+    float ev[KP], vh[DROPOUT ? KP : 1], zj[KP], bs[DROPOUT ? KP : 1], zl[SPARSE ? KP : 1];
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
         ev[k] = j_ok ? eV[(long long)j * KP + k] : 0.f;
         zj[k] = 0.f;
+        if (SPARSE) zl[k] = 0.f;
         if (DROPOUT) { vh[k] = j_ok ? Vh[(long long)j * KP + k] : 0.f; bs[k] = 0.f; }
     }
     const float lpj = (DROPOUT && j_ok) ? lp[j] : 0.f;
     const float flj = (DROPOUT && j_ok) ? pfloor[j] : 0.f;
 
     float* sUf = &sU[0][0]; float* sUwf = &sUw[0][0]; float* sUhf = &sUh[0][0]; float* sUnf = &sUn[0][0];
+    float* sUlf = &sUl[0][0];
     for (long long r0 = r_begin; r0 < r_end; r0 += PG_TR) {
         const int rcount = (int)min((long long)PG_TR, r_end - r0);
         __syncthreads();
@@ -220,6 +239,7 @@ k_pass_genes(const float* __restrict__ X, long long ldx, long long n_rows, int p
             const bool ok = idx / KP < rcount;
             sUf[idx] = ok ? eU[r0 * KP + idx] : 0.f;
             if (QUIRK) sUwf[idx] = ok ? eUw[r0 * KP + idx] : 0.f;
+            if (SPARSE) sUlf[idx] = ok ? eUl[r0 * KP + idx] : 0.f;
             if (DROPOUT) {
                 sUhf[idx] = ok ? Uh[r0 * KP + idx] : 0.f;
                 sUnf[idx] = ok ? Un[r0 * KP + idx] : 0.f;
@@ -240,6 +260,7 @@ k_pass_genes(const float* __restrict__ X, long long ldx, long long n_rows, int p
                 const float4* w4 = reinterpret_cast<const float4*>(&sUw[QUIRK ? rr : 0][0]);
                 const float4* h4 = reinterpret_cast<const float4*>(&sUh[DROPOUT ? rr : 0][0]);
                 const float4* n4 = reinterpret_cast<const float4*>(&sUn[DROPOUT ? rr : 0][0]);
+                const float4* l4 = reinterpret_cast<const float4*>(&sUl[SPARSE ? rr : 0][0]);
 #pragma unroll
                 for (int q = 0; q < KP / 4; ++q) {
                     const float4 uu = u4[q];
@@ -269,6 +290,11 @@ k_pass_genes(const float* __restrict__ X, long long ldx, long long n_rows, int p
                         bs[4 * q + 0] = fmaf(D, nn.x, bs[4 * q + 0]); bs[4 * q + 1] = fmaf(D, nn.y, bs[4 * q + 1]);
                         bs[4 * q + 2] = fmaf(D, nn.z, bs[4 * q + 2]); bs[4 * q + 3] = fmaf(D, nn.w, bs[4 * q + 3]);
                     }
+                    if (SPARSE) {
+                        const float4 ll = l4[q];
+                        zl[4 * q + 0] = fmaf(R, ll.x, zl[4 * q + 0]); zl[4 * q + 1] = fmaf(R, ll.y, zl[4 * q + 1]);
+                        zl[4 * q + 2] = fmaf(R, ll.z, zl[4 * q + 2]); zl[4 * q + 3] = fmaf(R, ll.w, zl[4 * q + 3]);
+                    }
                 }
             }
         }
@@ -278,6 +304,7 @@ k_pass_genes(const float* __restrict__ X, long long ldx, long long n_rows, int p
         for (int k = 0; k < KP; ++k) {
             atomicAdd(Zj + (long long)j * KP + k, zj[k]);
             if (DROPOUT) atomicAdd(b2s + (long long)j * KP + k, bs[k]);
+            if (SPARSE) atomicAdd(Zl + (long long)j * KP + k, zl[k]);
         }
     }
 }
@@ -297,7 +324,7 @@ k_factor_update(long long rows, int K, int KP,
                 const double* __restrict__ c1, const double* __restrict__ c2,
                 const float* __restrict__ E_old,
                 float* __restrict__ h1_io, float* __restrict__ h2_io,
-                float* __restrict__ E_new, float* __restrict__ eE_new,
+                float* __restrict__ E_new, float* __restrict__ eE_new, float* __restrict__ eEl_new,
                 double* __restrict__ Slog, double* __restrict__ Shat,
                 double* __restrict__ Hsum, double* __restrict__ PUVsum, int write_state)
 {
@@ -311,7 +338,11 @@ k_factor_update(long long rows, int K, int KP,
          idx += (long long)gridDim.x * blockDim.x) {
         const int k = (int)(idx % KP);
         if (k >= K) {
-            if (write_state) { E_new[idx] = 0.f; eE_new[idx] = 0.f; if (!FROM_PARAMS) { h1_io[idx] = 0.f; h2_io[idx] = 0.f; } }
+            if (write_state) {
+                E_new[idx] = 0.f; eE_new[idx] = 0.f;
+                if (eEl_new) eEl_new[idx] = 0.f;
+                if (!FROM_PARAMS) { h1_io[idx] = 0.f; h2_io[idx] = 0.f; }
+            }
             continue;
         }
         double h1d, h2d;
@@ -331,7 +362,9 @@ k_factor_update(long long rows, int K, int KP,
         if (write_state) {
             if (!FROM_PARAMS) { h1_io[idx] = h1; h2_io[idx] = h2; }
             E_new[idx] = E;
-            eE_new[idx] = expf(Elog);
+            const float eE = expf(Elog);
+            eE_new[idx] = eE;
+            if (eEl_new) eEl_new[idx] = eE != 0.f ? eE * Elog : 0.f;     // sparse_zigap.py:116 operand
         }
         if (!Slog) continue;
         atomicAdd(&sSlog[k], (double)Elog);
@@ -508,6 +541,211 @@ k_dropout_posterior(const float* __restrict__ X, long long ldx, int p, int K, in
     out[(idx / p) * ldo + j] = D;
 }
 
+// ------------------------------------------------------------------------------------------------
+// SparseZIGaP gene side (sparse_zigap.py:144-163, :198-204, :196): V' update, S update, expectations and the masked
+// operands of the next iteration.  One thread per gene (the K components of a gene share logit(pi_s_j) and feed
+// pi_s_j).  FROM_PARAMS: expectations from (b1, b2, p_s) as they are (update_expectations); pi_s is left alone.
+__device__ __forceinline__ double nan_to_num_f64(double x) {
+    if (x != x) return 0.0;
+    if (x > 1.7976931348623157e308) return 1.7976931348623157e308;
+    if (x < -1.7976931348623157e308) return -1.7976931348623157e308;
+    return x;
+}
+
+template <bool FROM_PARAMS>
+__global__ void __launch_bounds__(128)
+k_sparse_gene_update(ori_problem_t P)
+{
+    __shared__ double sSlog[64], sShat[64];
+    if (threadIdx.x < 64) { sSlog[threadIdx.x] = 0.0; sShat[threadIdx.x] = 0.0; }
+    __syncthreads();
+    const int p = P.p, K = P.K, KP = P.KP;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < p) {
+        const float* Zj = P.red32;
+        const float* b2s = P.red32 + (long long)p * KP;
+        const float* Zl = P.red32 + 2ll * p * KP;
+        const double* beta1 = P.hyper + 2 * K, *beta2 = P.hyper + 3 * K;
+        const double pis = P.pi_s[j];
+        const double lps = logit_f64(pis);
+        double ssum = 0.0;
+        for (int k = 0; k < KP; ++k) {
+            const long long idx = (long long)j * KP + k;
+            if (k >= K) {
+                P.b1[idx] = 0.f; P.b2[idx] = 0.f; P.p_s[idx] = 0.f; P.logV[idx] = 0.f; P.eV[idx] = 0.f;
+                P.eVd[idx] = 0.f; P.eVz[idx] = 0.f; P.Vh_old[idx] = 0.f; P.V_hat[idx] = 0.f;
+                continue;
+            }
+            double h1d, h2d, ps;
+            if (FROM_PARAMS) {
+                h1d = (double)P.b1[idx]; h2d = (double)P.b2[idx]; ps = (double)P.p_s[idx];
+            } else {
+                const float S = P.p_s[idx];                       // S_hat of the iteration's start (:139)
+                const float ed = P.eVd[idx], lV = P.logV[idx];
+                const float RtU = Zj[idx], DtU = b2s[idx];
+                const float DZ = RtU * ed;                        // :115
+                const float DZl = fmaf(lV, RtU, Zl[idx]) * ed;    // :116
+                h1d = clamp_param_f64(beta1[k] + (double)(S * DZ));            // :149, :151
+                h2d = clamp_param_f64(beta2[k] + (double)S * (double)DtU);     // :150, :152
+                const double Vp = h1d / h2d;
+                const double tmp = -(double)DZl + nan_to_num_f64((double)DtU * Vp);   // :157-158
+                ps = nan_to_num_f64(sigmoid_f64(lps - tmp));                           // :159-160
+                if (pis <= 0.0) ps = 1e-10;                                            // :161
+                if (pis >= 1.0) ps = 1.0 - 1e-10;                                      // :162
+                P.b1[idx] = (float)h1d; P.b2[idx] = (float)h2d;
+            }
+            const float h1 = (float)h1d, h2 = (float)h2d;
+            const float E = (float)(h1d / h2d);
+            const float Elog = (float)digamma_f64((double)h1) - logf(h2);     // gamma.py:48-61
+            const float eE = expf(Elog);
+            const float Sn = (float)ps;                                       // bernoulli.py:45
+            const float ed_new = ps > P.tau ? eE : 0.f;                       // :134, :103
+            const float veff = Sn * E;                                        // :140
+            P.Vh_old[idx] = FROM_PARAMS ? veff : P.V_hat[idx];
+            P.p_s[idx] = Sn; P.logV[idx] = Elog; P.eV[idx] = eE;
+            P.eVd[idx] = ed_new; P.eVz[idx] = ed_new * Sn; P.V_hat[idx] = veff;
+            atomicAdd(&sSlog[k], (double)Elog);
+            atomicAdd(&sShat[k], (double)E);
+            ssum += ps;
+        }
+        if (!FROM_PARAMS) P.pi_s[j] = ssum / (double)K;                       // :196
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        atomicAdd(P.gsum + threadIdx.x, sSlog[threadIdx.x]);
+        atomicAdd(P.gsum + KP + threadIdx.x, sShat[threadIdx.x]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column sums of X in float64 (column means for explained_deviance, base.py:76).
+__global__ void __launch_bounds__(128)
+k_col_sums(const float* __restrict__ X, long long ldx, long long n_rows, int p, int rows_per_chunk,
+           double* __restrict__ out)
+{
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    if (j >= p) return;
+    const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+    const long long r1 = min(n_rows, r0 + rows_per_chunk);
+    double s = 0.0;
+    for (long long r = r0; r < r1; ++r) s += (double)__ldg(X + r * ldx + j);
+    if (s != 0.0) atomicAdd(out + j, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Zero-inflated Poisson log-likelihood sums behind reconstruction_deviance / explained_deviance (base.py:58-82,
+// sparse_zigap.py:44-51).  Same tiling as the row pass.  A float64 value assigned into the reference's int64
+// buffer (sparse_zigap.py:45) is truncated toward zero; NaN / inf / out of range become INT64_MIN (x86 cvttsd2si).
+__device__ __forceinline__ long long trunc_like_numpy(double v) {
+    if (!(fabs(v) < 9.2233720368547758e18)) return (long long)0x8000000000000000ull;
+    return (long long)v;
+}
+
+template <int KP>
+__global__ void __launch_bounds__(PR_TR)
+k_deviance(const float* __restrict__ X, long long ldx, long long n_rows, int p,
+           const float* __restrict__ Uh, const float* __restrict__ b1, const float* __restrict__ b2,
+           const float* __restrict__ Sh, const float* __restrict__ Vo,
+           const float* __restrict__ lp, const float* __restrict__ pfloor,
+           const double* __restrict__ pi, const double* __restrict__ cmean,
+           unsigned long long* __restrict__ out_int, double* __restrict__ out_f64)
+{
+    __shared__ float sX[PR_TR][PR_TG + 1];
+    // the rate is accumulated in float64 from V' = b1 / b2 and S_hat: the reference's float64 product (base.py:63-66)
+    // stays positive where a float32 S_hat * V'_hat underflows, and log(0) would turn the metric into INT64_MIN
+    __shared__ __align__(16) double sVc[PR_TG][KP];
+    __shared__ __align__(16) float sVo[PR_TG][KP];
+    __shared__ float slp[PR_TG], sfl[PR_TG];
+    __shared__ double spi[PR_TG], scm[PR_TG];
+    __shared__ double sred[PR_TR / 32];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long row0 = (long long)blockIdx.x * PR_TR;
+    const long long row = row0 + tid;
+    const bool row_ok = row < n_rows;
+    float uh[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) uh[k] = row_ok ? Uh[row * KP + k] : 0.f;
+
+    unsigned long long ti[3] = {0ull, 0ull, 0ull};
+    double tf[3] = {0.0, 0.0, 0.0};
+    const int ntiles = (p + PR_TG - 1) / PR_TG;
+    for (int t = blockIdx.y; t < ntiles; t += gridDim.y) {
+        const int j0 = t * PR_TG;
+        const int gcount = min(PR_TG, p - j0);
+        __syncthreads();
+        for (int rr = warp; rr < PR_TR; rr += PR_TR / 32) {
+            const long long r = row0 + rr;
+            float v = 0.f;
+            if (r < n_rows && lane < gcount) v = __ldg(X + r * ldx + j0 + lane);
+            sX[rr][lane] = v;
+        }
+        double* sVcf = &sVc[0][0];
+        float* sVof = &sVo[0][0];
+        for (int idx = tid; idx < PR_TG * KP; idx += PR_TR) {
+            const bool ok = idx / KP < gcount;
+            const long long gi = (long long)j0 * KP + idx;
+            double v = 0.0;
+            if (ok && b2[gi] != 0.f) v = (double)b1[gi] / (double)b2[gi] * (Sh ? (double)Sh[gi] : 1.0);   // pad columns: 0
+            sVcf[idx] = v;
+            sVof[idx] = ok ? Vo[gi] : 0.f;
+        }
+        if (tid < PR_TG) {
+            const bool ok = tid < gcount;
+            slp[tid] = ok ? lp[j0 + tid] : 0.f;
+            sfl[tid] = ok ? pfloor[j0 + tid] : 0.f;
+            spi[tid] = ok ? pi[j0 + tid] : 0.5;
+            scm[tid] = ok ? cmean[j0 + tid] : 0.0;
+        }
+        __syncthreads();
+        if (!row_ok) continue;
+        for (int g = 0; g < gcount; ++g) {
+            const float x = sX[tid][g];
+            double lam = 0.0;
+            float uv = 0.f;
+            const double2* c2 = reinterpret_cast<const double2*>(&sVc[g][0]);
+            const float4* o4 = reinterpret_cast<const float4*>(&sVo[g][0]);
+#pragma unroll
+            for (int q = 0; q < KP / 4; ++q) {
+                const double2 ca = c2[2 * q], cb = c2[2 * q + 1];
+                const float4 o = o4[q];
+                lam = fma((double)uh[4 * q + 0], ca.x, lam); lam = fma((double)uh[4 * q + 1], ca.y, lam);
+                lam = fma((double)uh[4 * q + 2], cb.x, lam); lam = fma((double)uh[4 * q + 3], cb.y, lam);
+                uv = fmaf(uh[4 * q + 0], o.x, uv); uv = fmaf(uh[4 * q + 1], o.y, uv);
+                uv = fmaf(uh[4 * q + 2], o.z, uv); uv = fmaf(uh[4 * q + 3], o.w, uv);
+            }
+            const bool nz = x != 0.f;
+            float D = 1.f;
+            if (!nz) { float e, ex; D = dropout_p(uv, slp[g], sfl[g], e, ex); }
+            const double L = (D > 0.5f) ? lam : 0.0;               // base.py:67: UV[round(D_hat) == 0] = 0
+            const double pj = spi[g], cm = scm[g], xd = (double)x;
+            double l_uv, l_sat, l_mean;
+            if (!nz) {                                            // sparse_zigap.py:49
+                l_uv = log(pj * exp(-L) + (1.0 - pj));
+                l_sat = log(pj + (1.0 - pj));
+                l_mean = log(pj * exp(-cm) + (1.0 - pj));
+            } else {                                              // sparse_zigap.py:50
+                const double lpi = log(pj);
+                l_uv = lpi - L + xd * log(L);
+                l_sat = lpi - xd + xd * log(xd);
+                l_mean = lpi - cm + xd * log(cm);
+            }
+            ti[0] += (unsigned long long)trunc_like_numpy(l_uv);
+            ti[1] += (unsigned long long)trunc_like_numpy(l_sat);
+            ti[2] += (unsigned long long)trunc_like_numpy(l_mean);
+            tf[0] += l_uv; tf[1] += l_sat; tf[2] += l_mean;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ti[c] += __shfl_xor_sync(0xffffffffu, ti[c], o);
+        if (lane == 0 && ti[c]) atomicAdd(out_int + c, ti[c]);
+        const double r = block_reduce_sum(tf[c], sred);
+        if (tid == 0) atomicAdd(out_f64 + c, r);
+    }
+}
+
 // ================================================================================================
 // launchers
 template <int KP>
@@ -520,9 +758,18 @@ static int pass_rows_kp(const ori_problem_t* P, int g, cudaStream_t st) {
     const bool drop = P->flags & ORI_F_DROPOUT, elbo = P->flags & ORI_F_ELBO;
     double* colsum = P->red64;
     double* part = P->red64 + P->p + 2 * P->KP;
+    if (P->flags & ORI_F_SPARSE) {
+        if constexpr (KP <= 32) {
+            k_pass_rows<KP, true, false, true><<<grid, PR_TR, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, P->eU[g],
+                P->U_hat[g], P->eVd, P->Vh_old, P->eVz, P->V_hat, P->lp, P->pfloor, P->Zi, P->a2s, colsum, part);
+            return check_launch("k_pass_rows(sparse)");
+        } else {
+            return set_error(ORI_EUNSUPPORTED, "the sparse model needs K <= 32");
+        }
+    }
 #define ORI_LAUNCH_PR(D, E)                                                                              \
-    k_pass_rows<KP, D, E><<<grid, PR_TR, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, P->eU[g], P->U_hat[g],   \
-                                                  P->eV, P->V_hat, P->lp, P->pfloor, P->Zi, P->a2s, colsum, part)
+    k_pass_rows<KP, D, E, false><<<grid, PR_TR, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, P->eU[g], P->U_hat[g], \
+                                                  P->eV, P->V_hat, P->eV, P->V_hat, P->lp, P->pfloor, P->Zi, P->a2s, colsum, part)
     if (drop && elbo) ORI_LAUNCH_PR(true, true);
     else if (drop) ORI_LAUNCH_PR(true, false);
     else if (elbo) ORI_LAUNCH_PR(false, true);
@@ -554,10 +801,20 @@ static int pass_genes_kp(const ori_problem_t* P, int g, cudaStream_t st) {
     const bool drop = P->flags & ORI_F_DROPOUT, quirk = (P->flags & ORI_F_QUIRK) != 0;
     float* Zj = P->red32;
     float* b2s = P->red32 + (long long)P->p * P->KP;
+    if (P->flags & ORI_F_SPARSE) {
+        if constexpr (KP <= 32) {
+            k_pass_genes<KP, true, false, true><<<grid, PG_TG, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, (int)rpc,
+                P->eU[g], nullptr, P->U_hat[g], P->U_hat[1 - g], P->eUl[g], P->eVd, P->Vh_old, P->lp, P->pfloor,
+                Zj, b2s, P->red32 + 2ll * P->p * P->KP);
+            return check_launch("k_pass_genes(sparse)");
+        } else {
+            return set_error(ORI_EUNSUPPORTED, "the sparse model needs K <= 32");
+        }
+    }
 #define ORI_LAUNCH_PG(D, Q)                                                                             \
-    k_pass_genes<KP, D, Q><<<grid, PG_TG, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, (int)rpc, P->eU[g],    \
-                                                   P->eUw, P->U_hat[g], P->U_hat[1 - g], P->eV, P->V_hat, \
-                                                   P->lp, P->pfloor, Zj, b2s)
+    k_pass_genes<KP, D, Q, false><<<grid, PG_TG, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, (int)rpc, P->eU[g], \
+                                                   P->eUw, P->U_hat[g], P->U_hat[1 - g], nullptr, P->eV, P->V_hat, \
+                                                   P->lp, P->pfloor, Zj, b2s, nullptr)
     if (drop && quirk) ORI_LAUNCH_PG(true, true);
     else if (drop) ORI_LAUNCH_PG(true, false);
     else if (quirk) ORI_LAUNCH_PG(false, true);
@@ -589,18 +846,19 @@ int launch_row_update(const ori_problem_t* P, int g, int write_state, cudaStream
     double* SlogU = P->red64 + p;
     double* SU = P->red64 + p + KP;
     double* part = P->red64 + p + 2 * KP;
-    const bool drop = P->flags & ORI_F_DROPOUT;
+    const bool drop = P->flags & ORI_F_DROPOUT, sparse = P->flags & ORI_F_SPARSE;
     const int grid = update_grid(P->n_rows * KP);
     if (write_state >= 2) {
         const bool sums = write_state == 2;
         k_factor_update<true><<<grid, 256, 0, st>>>(P->n_rows, K, KP, nullptr, nullptr, nullptr, nullptr,
-            nullptr, nullptr, nullptr, P->a1, P->a2, P->U_hat[g], P->eU[g], sums ? SlogU : nullptr, SU,
-            part + R64_HROW, nullptr, 1);
+            nullptr, nullptr, nullptr, P->a1, P->a2, P->U_hat[g], P->eU[g], sparse ? P->eUl[g] : nullptr,
+            sums ? SlogU : nullptr, SU, part + R64_HROW, nullptr, 1);
     } else {
         // GaP: rate = alpha2 + sum_j V_hat_jk (gap.py:98); the column sums live in gsum[KP..2KP)
         k_factor_update<false><<<grid, 256, 0, st>>>(P->n_rows, K, KP, P->Zi, P->eU[g],
             drop ? P->a2s : nullptr, P->gsum + KP, P->hyper, P->hyper + K, P->U_hat[g],
-            P->a1, P->a2, P->U_hat[1 - g], P->eU[1 - g], SlogU, SU, part + R64_HROW, part + R64_PUV, write_state);
+            P->a1, P->a2, P->U_hat[1 - g], P->eU[1 - g], sparse ? P->eUl[1 - g] : nullptr, SlogU, SU,
+            part + R64_HROW, part + R64_PUV, write_state);
     }
     return check_launch("k_factor_update(rows)");
 }
@@ -610,15 +868,21 @@ int launch_gene_update(const ori_problem_t* P, int write_state, cudaStream_t st)
     const bool drop = P->flags & ORI_F_DROPOUT;
     double* SlogV = P->gsum; double* SV = P->gsum + KP; double* gpart = P->gsum + 2 * KP;
     const int grid = update_grid((long long)p * KP);
+    if (P->flags & ORI_F_SPARSE) {
+        const int gs = cdiv(p, 128);
+        if (write_state == 2) k_sparse_gene_update<true><<<gs, 128, 0, st>>>(*P);
+        else k_sparse_gene_update<false><<<gs, 128, 0, st>>>(*P);
+        return check_launch("k_sparse_gene_update");
+    }
     if (write_state == 2) {
         k_factor_update<true><<<grid, 256, 0, st>>>(p, K, KP, nullptr, nullptr, nullptr, nullptr,
-            nullptr, nullptr, nullptr, P->b1, P->b2, P->V_hat, P->eV, SlogV, SV, gpart, nullptr, 1);
+            nullptr, nullptr, nullptr, P->b1, P->b2, P->V_hat, P->eV, nullptr, SlogV, SV, gpart, nullptr, 1);
     } else {
         // GaP: rate = beta2 + sum_i U_hat_ik (gap.py:106) with the NEW U_hat: red64[p+KP ..)
         float* Zj = P->red32; float* b2s = P->red32 + (long long)p * KP;
         k_factor_update<false><<<grid, 256, 0, st>>>(p, K, KP, Zj, P->eV, drop ? b2s : nullptr,
             P->red64 + p + KP, P->hyper + 2 * K, P->hyper + 3 * K, nullptr,
-            P->b1, P->b2, P->V_hat, P->eV, SlogV, SV, gpart, nullptr, write_state);
+            P->b1, P->b2, P->V_hat, P->eV, nullptr, SlogV, SV, gpart, nullptr, write_state);
     }
     return check_launch("k_factor_update(genes)");
 }
@@ -651,8 +915,45 @@ int launch_dropout_posterior(const ori_problem_t* P, int g, float* out, long lon
     const long long total = nrows * P->p;
     if (total == 0) return ORI_OK;
     k_dropout_posterior<<<cdiv(total, 256), 256, 0, st>>>(P->X, P->ldx, P->p, P->K, P->KP, P->U_hat[g],
-                                                          P->V_hat, P->lp, P->pfloor, out, ldo, row0, nrows);
+                                                          (P->flags & ORI_F_SPARSE) ? P->Vh_old : P->V_hat, P->lp,
+                                                          P->pfloor, out, ldo, row0, nrows);
     return check_launch("k_dropout_posterior");
+}
+
+int launch_col_sums(const float* X, long long ldx, long long n_rows, int p, double* out, cudaStream_t st) {
+    if (n_rows == 0) return ORI_OK;
+    const int bx = cdiv(p, 128);
+    long long chunks = 1;
+    while (bx * chunks < 148 * 4 && n_rows / (chunks * 2) >= 16) chunks *= 2;
+    const long long rpc = (n_rows + chunks - 1) / chunks;
+    dim3 grid(bx, cdiv(n_rows, rpc));
+    k_col_sums<<<grid, 128, 0, st>>>(X, ldx, n_rows, p, (int)rpc, out);
+    return check_launch("k_col_sums");
+}
+
+template <int KP>
+static int deviance_kp(const ori_problem_t* P, int g, const double* pi, const double* cmean, long long* out_int,
+                       double* out_f64, cudaStream_t st) {
+    const int bx = cdiv(P->n_rows, PR_TR);
+    const int ntiles = cdiv(P->p, PR_TG);
+    int gy = 1;
+    while (bx * gy < 148 * 4 && gy * 2 <= ntiles) gy *= 2;
+    const bool sparse = P->flags & ORI_F_SPARSE;
+    k_deviance<KP><<<dim3(bx, gy), PR_TR, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, P->U_hat[g], P->b1, P->b2,
+        sparse ? P->p_s : nullptr, sparse ? P->Vh_old : P->V_hat, P->lp, P->pfloor, pi, cmean,
+        (unsigned long long*)out_int, out_f64);
+    return check_launch("k_deviance");
+}
+
+int launch_deviance(const ori_problem_t* P, int g, const double* pi, const double* cmean, long long* out_int,
+                    double* out_f64, cudaStream_t st) {
+    switch (P->KP) {
+        case 8: return deviance_kp<8>(P, g, pi, cmean, out_int, out_f64, st);
+        case 16: return deviance_kp<16>(P, g, pi, cmean, out_int, out_f64, st);
+        case 32: return deviance_kp<32>(P, g, pi, cmean, out_int, out_f64, st);
+        case 64: return deviance_kp<64>(P, g, pi, cmean, out_int, out_f64, st);
+    }
+    return set_error(ORI_EINVAL, "KP must be 8, 16, 32 or 64 (got %d)", P->KP);
 }
 
 }  // namespace ori

@@ -799,7 +799,7 @@ static TcWs tc_carve(const ori_problem_t* P) {
 }
 
 bool tc_eligible(const ori_problem_t* P) {
-    return P->tc_ws != nullptr && (P->KP == 32 || P->KP == 64) && !(P->flags & ORI_F_NO_TENSOR) && P->n_rows > 0 &&
+    return P->tc_ws != nullptr && (P->KP == 32 || P->KP == 64) && !(P->flags & (ORI_F_NO_TENSOR | ORI_F_SPARSE)) && P->n_rows > 0 &&
            P->tc_ws_floats >= tc_workspace_floats(P->n_rows, P->p, P->KP) && get_encode_fn() != nullptr;
 }
 

@@ -1,7 +1,9 @@
-"""Factor models (oriana/models/__init__.py).  ZIGaP and GaP are the models of the accelerated CAVI path;
-the sparse variants (sparse_zigap.py, sparse_gap.py) are the next row of SURVEY.md section 8f."""
+"""Factor models (oriana/models/__init__.py).  ZIGaP and GaP are the models of the accelerated CAVI path (tensor
+kernels); SparseZIGaP runs the same iteration with the sparsity layer on the CUDA-core
+kernels.  SparseGaP.step() raises NameError in the reference (sparse_gap.py:127) and is not provided."""
 from .base import FactorModel
 from .gap import GaP
 from .zigap import ZIGaP
+from .sparse_zigap import SparseZIGaP
 
-__all__ = ['FactorModel', 'GaP', 'ZIGaP']
+__all__ = ['FactorModel', 'GaP', 'ZIGaP', 'SparseZIGaP']

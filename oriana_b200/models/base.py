@@ -75,6 +75,7 @@ class DeviceView(Parameter):
 class FactorModel(metaclass=ABCMeta):
 
     _dropout = False     # ZIGaP sets this
+    _sparse = False      # SparseZIGaP sets this
 
     def __init__(self, cmatrix, k=2, use_factors=True, *, state=None, compat_quirk=False, sharded=False,
                  process_group=None, elbo=True, trace_cap=4096, force_simt=False, tensor=None):
@@ -103,7 +104,7 @@ class FactorModel(metaclass=ABCMeta):
         self.n_total = self._shard.total_rows(self.n, self._dev)
         self._flags = (_lib.ORI_F_DROPOUT if self._dropout else 0) | (_lib.ORI_F_ELBO if elbo else 0) \
             | (_lib.ORI_F_QUIRK if (compat_quirk and self._dropout) else 0) \
-            | (_lib.ORI_F_NO_TENSOR if force_simt else 0)
+            | (_lib.ORI_F_NO_TENSOR if force_simt else 0) | (_lib.ORI_F_SPARSE if self._sparse else 0)
         self.compat_quirk = bool(compat_quirk and self._dropout)
         self._trace_cap = int(trace_cap)
         self._gen = 0
@@ -168,7 +169,7 @@ class FactorModel(metaclass=ABCMeta):
         self._a2s = rowf() if self._dropout else None
         self._eUw = rowf() if (self._flags & _lib.ORI_F_QUIRK) else None
         self._b1, self._b2, self._Vhat, self._eV = genef(), genef(), genef(), genef()
-        self._red32 = torch.zeros((2, p, KP), **f32)
+        self._red32 = torch.zeros((3 if self._sparse else 2, p, KP), **f32)
         self._lp = torch.full((p,), float('-inf'), **f32) if self._dropout else None
         self._pfloor = torch.zeros((p,), **f32) if self._dropout else None
         self._hyper = torch.ones((4, K), **f64)
@@ -199,6 +200,7 @@ class FactorModel(metaclass=ABCMeta):
         P.pi_d, P.scal, P.elbo_trace = ptr(self._pi), ptr(self._scal), ptr(self._trace)
         if self._tc_ws is not None:
             P.tc_ws, P.tc_ws_floats = self._tc_ws.data_ptr(), self._tc_ws.numel()
+        self._bind_extra(P, rowf, genef, ptr)
         self._P = P
         _lib.check(self._lib.ori_problem_check(ctypes.byref(P)))
         self.uses_tensor_path = bool(self._lib.ori_uses_tensor_path(ctypes.byref(P)))
@@ -214,6 +216,9 @@ class FactorModel(metaclass=ABCMeta):
         self.alpha2 = DeviceView(self, lambda: self._hyper[1])
         self.beta1 = DeviceView(self, lambda: self._hyper[2])
         self.beta2 = DeviceView(self, lambda: self._hyper[3])
+
+    def _bind_extra(self, P, rowf, genef, ptr):
+        """Hook for model-specific device state (SparseZIGaP)."""
 
     def _call(self, name, *args):
         self._P.iter = self._iter

@@ -1,0 +1,108 @@
+"""GPU: SparseZIGaP on the device against
+
+  * trajectories and deviance values recorded from the UNMODIFIED reference (`sparse_*` fixtures of
+    oracle/make_golden.py: sparse_zigap.py:118-196, base.py:58-82),
+  * the oracle restatement (oracle/sparse_numpy.py) on fresh seeded problems, including the float64 deviance.
+
+Tolerances: as in tests/test_oracle_sparse.py -- the S-step is a sigmoid of a difference of two large sums, so p_s
+amplifies float32 accumulation-order differences: 2e-5 after one step, 5e-3 later (relative, floor 1e-6 of the
+array's scale); the deviance metrics 1e-4 relative (they are sums of integers, see quirk Q10 in oracle/sparse_numpy.py).
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import golden_state, load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+KEYS = ('a1', 'a2', 'b1', 'b2', 'p_s', 'pi_s', 'pi_d', 'alpha1', 'alpha2', 'beta1', 'beta2')
+
+
+def _close(got, want, rtol=1e-4):
+    """Relative comparison; a log(0) entry makes both sides the same infinity (or the same INT64_MIN-sized number)."""
+    if not np.isfinite(want):
+        return got == want
+    return abs(got - want) <= rtol * abs(want)
+
+
+def _state(g, t):
+    s = golden_state(g, t)
+    for k in ('deviance', 'explained'):
+        s.pop(k, None)
+    return s
+
+
+def make_model(s, tau):
+    from oriana.models import SparseZIGaP
+    from oriana.singlecell import CountMatrix
+    return SparseZIGaP(CountMatrix(s['X']), k=s['a1'].shape[1], use_factors=False, state=s, tau=tau)
+
+
+@pytest.mark.parametrize('name', ['sparse_k4', 'sparse_ragged'])
+def test_sparse_trajectory_and_deviance_match_reference(cuda_lib, name):
+    g = load_golden(name)
+    m = make_model(_state(g, 0), float(g['tau']))
+    assert not m.uses_tensor_path
+    steps = [int(t) for t in g['steps']]
+    for t in range(1, max(steps) + 1):
+        m.step()
+        if t not in steps:
+            continue
+        want = _state(g, t)
+        tol = 2e-5 if t == 1 else 5e-3
+        for k in KEYS:
+            assert relerr(getattr(m, k).asarray(), want[k]) < tol, (name, t, k)
+        assert np.max(np.abs(m.D_hat - want['p_d'])) < (1e-5 if t == 1 else 2e-3), (name, t)
+        dev_ref, expl_ref = float(g['s%d_deviance' % t]), float(g['s%d_explained' % t])
+        if abs(dev_ref) < 1e15:        # beyond: a -inf entry was cast to INT64_MIN (quirk Q10), meaningless
+            assert abs(m.reconstruction_deviance() - dev_ref) <= 1e-4 * abs(dev_ref), (name, t)
+            assert abs(m.explained_deviance() - expl_ref) <= 1e-4 * abs(expl_ref), (name, t)
+
+
+@pytest.mark.parametrize('shape', [(700, 450, 6), (257, 1031, 20), (1500, 90, 32)])
+def test_sparse_fresh_problem_matches_oracle(cuda_lib, shape):
+    from oracle import cavi_numpy as cn, sparse_numpy as sn
+    n, p, K = shape
+    X = cn.synth_counts(n, p, K, seed=11)
+    s = sn.init_state(X, K, np.random.default_rng(5))
+    m = make_model({k: np.array(v, copy=True) for k, v in s.items()}, 0.5)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for t in range(1, 4):
+            m.step(); sn.step(s, tau=0.5)
+            tol = 2e-5 if t == 1 else 5e-3
+            for k in KEYS:
+                assert relerr(getattr(m, k).asarray(), s[k]) < tol, (shape, t, k)
+        # the masks agree entry for entry (no p_s within rounding of tau in these problems)
+        assert ((m.p_s.asarray() > 0.5) == (s['p_s'] > 0.5)).all()
+        for quirk in (True, False):
+            want = sn.reconstruction_deviance(s, int_quirk=quirk)
+            assert _close(m.reconstruction_deviance(int_quirk=quirk), want), (shape, quirk)
+            want = sn.explained_deviance(s, int_quirk=quirk)
+            got = m.explained_deviance(int_quirk=quirk)
+            assert _close(got, want) or (np.isnan(want) and np.isnan(got)), (shape, quirk)
+
+
+def test_sparse_constructor_path_and_snapshot(cuda_lib):
+    """`use_factors=False` construction (sparse_zigap.py:74-98, base.py:43-52), a few steps, then a mid-run snapshot
+    reloaded into a second model continues identically."""
+    from oracle import cavi_numpy as cn
+    from oriana.models import SparseZIGaP
+    from oriana.singlecell import CountMatrix
+    X = cn.synth_counts(300, 200, 4, seed=2)
+    np.random.seed(7)
+    m = SparseZIGaP(CountMatrix(X), k=4, use_factors=False)
+    assert np.all(m.pi_s.asarray() == 1.) and np.all(m.p_s.asarray() == 1.)
+    assert np.allclose(m.pi_d.asarray(), (X > 0).mean(axis=0))
+    for _ in range(3):
+        m.step()
+    ps = m.p_s.asarray()
+    assert np.isfinite(ps).all() and ((ps >= 0) & (ps <= 1)).all()
+    snap = m.state_dict(); snap['X'] = X
+    m2 = SparseZIGaP(CountMatrix(X), k=4, use_factors=False, state=snap)
+    m.step(); m2.step()
+    for k in KEYS:
+        assert relerr(getattr(m2, k).asarray(), getattr(m, k).asarray()) < 1e-5, k
+    with pytest.raises(ValueError):
+        SparseZIGaP(CountMatrix(X), k=40, use_factors=False)

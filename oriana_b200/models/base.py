@@ -146,15 +146,10 @@ class FactorModel(metaclass=ABCMeta):
             ldx = src.stride(0) if n > 1 else max(ldx, src.stride(0))
             self._Xfull = None
         else:
-            self._Xfull = torch.zeros((n, ldx), **f32)
-            if isinstance(src, torch.Tensor):
-                self._Xfull[:, :p] = src.to(device=dev, dtype=torch.float32)
-            else:
-                step = max(1, (1 << 26) // max(1, p))   # upload in slabs: no n x p float32 copy on the host
-                for r in range(0, n, step):
-                    self._Xfull[r:r + step, :p] = torch.as_tensor(
-                        np.ascontiguousarray(src[r:r + step]).astype(np.float32, copy=False), device=dev)
-            self._X = self._Xfull[:, :p]
+            # ingest (cmatrix.py -> HBM): slabs cross PCIe in the narrowest integer type that holds the counts and are
+            # widened on the device; no n x p float32 copy on the host
+            self._X = cmatrix.to_device(dev)
+            self._Xfull = self._X
         self._ldx = ldx
 
         def rowf():

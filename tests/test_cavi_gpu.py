@@ -245,3 +245,23 @@ def test_host_streamed_step_with_compact_counts(cuda_lib):
                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
             assert rc == 0
             assert np.array_equal(dst.cpu().numpy()[:, :p], a[:, :p].astype(np.float32))
+
+
+def test_count_matrix_to_device_narrow_upload(cuda_lib):
+    """CountMatrix.to_device: uint8 / uint16 / float32 uploads give the same float32 matrix in HBM, with the 16-byte
+    row pitch the kernels need (ragged p), uploaded in several slabs."""
+    import torch
+    from oriana.singlecell import CountMatrix
+    rng = np.random.default_rng(3)
+    X = rng.poisson(2., size=(301, 77)).astype(np.int64)
+    for top, dt in ((None, torch.uint8), (300, torch.uint16), (70000, None)):
+        Y = X.copy()
+        if top:
+            Y[17, 5] = top
+        c = CountMatrix(Y)
+        assert c.narrow_dtype() == dt
+        d = c.to_device('cuda', slab_rows=64)
+        assert d.shape == (301, 77) and d.dtype == torch.float32 and d.stride(0) == 80 and d.data_ptr() % 16 == 0
+        np.testing.assert_array_equal(d.cpu().numpy(), Y.astype(np.float32))
+    Z = torch.as_tensor(X, device='cuda')
+    np.testing.assert_array_equal(CountMatrix(Z).to_device().cpu().numpy(), X.astype(np.float32))

@@ -90,6 +90,56 @@ def test_count_matrix_types():
         CountMatrix([[1, 2], [3, 4]])                              # cmatrix.py:25-29
 
 
+def test_count_matrix_reference_interface(tmp_path):
+    """cmatrix.py:39-121: csv ingest, labels, label-based column access, row filtering, sparse export."""
+    import pandas as pd
+    from oriana.singlecell import CountMatrix
+    df = pd.DataFrame(np.arange(12).reshape(4, 3), index=['c0', 'c1', 'c2', 'c3'], columns=['gA', 'gB', 'gC'])
+    path = tmp_path / 'counts.csv'
+    df.to_csv(path)
+    c = CountMatrix.from_csv(str(path))
+    assert c.shape == (4, 3)
+    assert list(c.row_names) == ['c0', 'c1', 'c2', 'c3'] and list(c.col_names) == ['gA', 'gB', 'gC']
+    np.testing.assert_array_equal(c.as_array(), df.values)
+    np.testing.assert_array_equal(c['gB'], df['gB'].values)
+    c['gB'] = np.array([7, 7, 7, 7])
+    assert (c.as_array()[:, 1] == 7).all()
+    sub = c.filter_rows(['c3', 'c1'], inplace=False)
+    assert sub.shape == (2, 3) and list(sub.row_names) == ['c3', 'c1'] and c.shape == (4, 3)
+    np.testing.assert_array_equal(sub.as_array()[:, 0], [9, 3])
+    assert c.filter_rows(['c0', 'c2']) is c and c.shape == (2, 3)
+    t = c.T
+    assert t.shape == (3, 2) and list(t.row_names) == ['gA', 'gB', 'gC']
+    assert c.as_sparse_matrix().shape == (2, 3) and c.as_sparse_matrix('csr').format == 'csr'
+    with pytest.raises(KeyError):
+        c['nope']
+    plain = CountMatrix(np.zeros((2, 5), dtype=np.int64))
+    assert list(plain.col_names) == [0, 1, 2, 3, 4] and list(plain.row_names) == [0, 1]
+
+
+def test_count_matrix_ingest_helpers():
+    """Row blocks of a sharded matrix tile it exactly; the narrow storage type follows the largest count."""
+    import torch
+    from oriana.singlecell import CountMatrix
+    X = np.random.default_rng(0).poisson(3., size=(103, 7))
+    c = CountMatrix(X)
+    for world in (1, 2, 3, 8):
+        blocks = [c.row_block(r, world) for r in range(world)]
+        assert sum(b.shape[0] for b in blocks) == 103
+        assert max(b.shape[0] for b in blocks) - min(b.shape[0] for b in blocks) <= 1
+        np.testing.assert_array_equal(np.concatenate([b.as_array() for b in blocks]), X)
+    assert CountMatrix.row_range(10, 3, 4) == (8, 10)
+    assert c.narrow_dtype() == torch.uint8
+    Y = X.copy(); Y[5, 2] = 300
+    assert CountMatrix(Y).narrow_dtype() == torch.uint16
+    Y[5, 2] = 70000
+    assert CountMatrix(Y).narrow_dtype() is None
+    assert CountMatrix(X + 0.5).narrow_dtype() is None
+    cc = CountMatrix(np.minimum(Y, 1000)).to_compact(pin=False)
+    np.testing.assert_array_equal(cc.dense().numpy(), np.minimum(Y, 1000))
+    assert cc.row.numel() == 1
+
+
 def test_library_exports_every_declared_symbol():
     """The C-ABI library loads and exports exactly what include/oriana_b200.h declares."""
     from oriana_b200 import _lib

@@ -112,6 +112,13 @@ typedef struct ori_problem {
     float* eUl[2];         /* row side, per generation: eU * E[log U] (operand of :116)                    */
     double* pi_s;          /* [p] prior of S, row means of p_s (:196), float64                             */
     double tau;            /* threshold of S_tilde (:134)                                                  */
+
+    /* eU / eV hold exp(E[log .]) of each cell / gene rescaled by exp(30 - max_k E[log .]) (the multinomial step only
+     * uses ratios, zigap.py:86-92; see csrc/special.cuh).  The ELBO term sum_ij X_ij log den_ij takes the scales back
+     * through the row sums of this rank's X and the column sums of the WHOLE X (ori_row_sums_f32,
+     * ori_column_sums_f64 + all-reduce, as float32); required with ORI_F_ELBO, NULL otherwise. */
+    const float* xrow;     /* [n_rows] */
+    const float* xcol;     /* [p]      */
 } ori_problem_t;
 
 /* ---- library ---------------------------------------------------------------------------------- */
@@ -172,6 +179,8 @@ int ori_dropout_posterior_f32(const ori_problem_t* P, int gen, float* out, int64
                               int64_t row0, int64_t nrows, void* stream);
 
 /* ---- convergence metrics of the reference's drivers (base.py:58-82, sparse_zigap.py:44-51) ------- */
+/* out[r] = sum_j X[r, j], float32 (device pointers). */
+int ori_row_sums_f32(const float* X, int64_t ldx, int64_t n_rows, int32_t p, float* out, void* stream);
 /* out[c] = sum_i X[i, c] over this rank's rows, float64 (device pointers). */
 int ori_column_sums_f64(const float* X, int64_t ldx, int64_t n_rows, int32_t p, double* out, void* stream);
 /* The three zero-inflated Poisson log-likelihood sums behind reconstruction_deviance / explained_deviance for

@@ -85,6 +85,22 @@ def expectations(s, dtype=np.float32):
 
 
 # --------------------------------------------------------------------------- multinomial latent-count step
+EXP_CENTER_LOG2, EXP_FLUSH, EXP_DEAD = 58, -104., -1e4
+
+
+def centred_exp(log_hat, dtype=np.float32):
+    """exp(l - max_k l) * 2^58 per row (2^58 = e^40.2; a power of two keeps every row's leading operand exactly
+    representable in tf32 on the device), 0 for components more than e^-104 below their row's largest (the reference's
+    float32 exp(lU + lV) underflows below -103.3) and for rows whose largest log-expectation is below -1e4.
+    Operands stay in [e^-64, e^40.2]: no product, ratio or accumulated sum leaves float32."""
+    l = log_hat.astype(dtype)
+    m = l.max(axis=1, keepdims=True)
+    with np.errstate(over='ignore', invalid='ignore'):
+        rel = l - m
+        e = np.ldexp(np.exp(rel), EXP_CENTER_LOG2).astype(dtype)
+    return np.where((m > EXP_DEAD) & (rel >= EXP_FLUSH), e, dtype(0)).astype(dtype)
+
+
 def z_expectations(log_U_hat, log_V_hat, X, D_hat=None, quirk=True, dtype=np.float32):
     """Ratio-form restatement of the numba triple loops zigap.py:79-95 / gap.py:67-80.
 
@@ -94,10 +110,12 @@ def z_expectations(log_U_hat, log_V_hat, X, D_hat=None, quirk=True, dtype=np.flo
         Zj = (R^T . (eU * D[:, :K])) * eV     when quirk         zigap.py:94 (D_hat[i, k] -- sic)
            = ((R*D)^T . eU) * eV              when not quirk     sparse_zigap.py:115 (correct index)
     GaP (D_hat is None): D == 1 (gap.py:78-80).  The never-read third output
-    (zigap.py:95) is not computed.  exp(lu+lv) is evaluated as exp(lu)*exp(lv).
+    (zigap.py:95) is not computed.  exp(lu+lv) is evaluated as exp(lu)*exp(lv), each factor rescaled per row
+    (`centred_exp`): the ratios the reference forms are invariant to that, and the product stays inside float32 where
+    the reference's exp of the SUM does (NMF-initialised factors, base.py:38-40: psi(a1) ~ -1/a1 ~ -100).
     """
-    eU = np.exp(log_U_hat.astype(dtype))
-    eV = np.exp(log_V_hat.astype(dtype))
+    eU = centred_exp(log_U_hat, dtype)
+    eV = centred_exp(log_V_hat, dtype)
     X = X.astype(dtype)
     den = eU @ eV.T
     den = np.where(den > 0, den, dtype(1))

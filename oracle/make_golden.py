@@ -10,6 +10,7 @@ the reference's numba Z kernels (zigap.py:79-95, gap.py:67-80) and the special-f
 test/test.py:13-32.
 """
 import os
+import sys
 import numpy as np
 from oracle import refshim, cavi_numpy as cn
 
@@ -25,7 +26,56 @@ CASES = [
 ]
 
 
+GENERATOR_CASES = [((30, 50, 4), {}), ((17, 23, 7), dict(n_groups=3, sparsity_degree_in_v=0.3, zero_inflation_level=0.7)),
+                   ((100, 500, 2), {})]    # the last one is the call of experiments/clustering.py:47 at configs[0] size
+
+
+def write_generator_fixture():
+    """The reference's synthetic-data generator (singlecell/generation.py:68-86) under a fixed seed."""
+    refshim.import_reference()
+    from oriana.singlecell import generate_factor_matrices
+    out = {}
+    for i, (args, kw) in enumerate(GENERATOR_CASES):
+        np.random.seed(100 + i)
+        X, U, V, labels = generate_factor_matrices(*args, **kw)
+        out.update({'c%d_X' % i: X.astype(np.int64), 'c%d_U' % i: U, 'c%d_V' % i: V, 'c%d_labels' % i: labels.astype(np.int64)})
+    np.savez_compressed(os.path.join(OUT, 'generator.npz'), **out)
+    refshim.release_reference()
+    print('generator written')
+
+
+def write_nmf_fixture():
+    """The reference's DEFAULT construction path, `use_factors=True` (base.py:38-40: a1, b1 seeded with sklearn NMF
+    factors, many of them tiny or exactly 0, so E[log U] reaches -100 ... -1e15 and exp(E log U) underflows float32 on
+    its own while the reference's exp(lU + lV) does not).  Post-construction state + trajectory."""
+    refshim.import_reference()
+    from oriana.models import ZIGaP
+    from oriana.singlecell import CountMatrix
+    n, p, K, rec = 400, 300, 5, (1, 2, 4)
+    X = cn.synth_counts(n, p, K, seed=9)
+    np.random.seed(0)
+    m = ZIGaP(CountMatrix(X), k=K, use_factors=True)
+    out = {'model': 'ZIGaP', 'K': K, 'steps': np.asarray(rec)}
+    s0 = refshim.snapshot(m)
+    out['X'] = s0.pop('X').astype(np.int32)
+    for k, v in s0.items():
+        out['s0_' + k] = v.astype(np.float32) if k == 'p_d' else v
+    for t in range(1, max(rec) + 1):
+        m.step()
+        if t in rec:
+            st = refshim.snapshot(m); st.pop('X')
+            for k, v in st.items():
+                out['s%d_%s' % (t, k)] = v.astype(np.float32) if k == 'p_d' else v
+    np.savez_compressed(os.path.join(OUT, 'zigap_nmf.npz'), **out)
+    refshim.release_reference()
+    print('zigap_nmf written')
+
+
 def main():
+    if sys.argv[1:] == ['generator']:
+        return write_generator_fixture()
+    if sys.argv[1:] == ['nmf']:
+        return write_nmf_fixture()
     ref = refshim.import_reference()
     from oriana.models import ZIGaP, GaP
     from oriana.singlecell import CountMatrix
@@ -104,6 +154,8 @@ def main():
                         y=y, inverse_digamma=rutils.inverse_digamma(y),
                         z=z, sigmoid=rutils.sigmoid(z), q=q, logit=rutils.logit(q))
     print('special written')
+    write_generator_fixture()
+    write_nmf_fixture()
 
 
 if __name__ == '__main__':

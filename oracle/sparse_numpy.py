@@ -28,8 +28,8 @@ def z_expectations(log_U_hat, log_Vp_hat, S_tilde, S_hat, D_hat, X, dtype=np.flo
         DZ_exp_logsum_hat[j,k] = eV_jk * (sum_i R_ij eU_ik logU_ik + logV'_jk sum_i R_ij eU_ik)   :116
     """
     lU = log_U_hat.astype(dtype); lV = log_Vp_hat.astype(dtype)
-    eU = np.exp(lU)
-    eV = np.exp(lV) * S_tilde.astype(dtype)
+    eU = cn.centred_exp(lU, dtype)                     # per-row rescaling: every output is a ratio (cavi_numpy.py)
+    eV = cn.centred_exp(lV, dtype) * S_tilde.astype(dtype)
     den = eU @ eV.T
     den = np.where(den > 0, den, dtype(1))
     R = X.astype(dtype) * D_hat.astype(dtype) / den

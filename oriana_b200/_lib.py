@@ -35,6 +35,7 @@ class OriProblem(C.Structure):
         ('tc_ws', C.c_void_p), ('tc_ws_floats', C.c_int64),
         ('p_s', C.c_void_p), ('logV', C.c_void_p), ('eVd', C.c_void_p), ('eVz', C.c_void_p), ('Vh_old', C.c_void_p),
         ('eUl', C.c_void_p * 2), ('pi_s', C.c_void_p), ('tau', C.c_double),
+        ('xrow', C.c_void_p), ('xcol', C.c_void_p),
     ]
 
 
@@ -62,6 +63,7 @@ _SIGNATURES = {
     'ori_cavi_step_global': ([_PP, C.c_int, C.c_void_p], C.c_int),
     'ori_finalize_local': ([_PP, C.c_int, C.c_void_p], C.c_int),
     'ori_dropout_posterior_f32': ([_PP, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p], C.c_int),
+    'ori_row_sums_f32': ([C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
     'ori_column_sums_f64': ([C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
     'ori_deviance_sums': ([_PP, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
     'ori_zigap_compute_Z_q_expectations_host': ([C.c_void_p] * 7 + [C.c_int64] * 3 + [C.c_int], C.c_int),

@@ -76,10 +76,12 @@ __global__ void k_exp_pad(const float* __restrict__ logE, const float* __restric
     const long long i = idx / KP; const int k = (int)(idx % KP);
     float v = 0.f;
     if (k < K) {
+        float m = -INFINITY;                       // centred exponent of the row (special.cuh): outputs are ratios
+        for (int q = 0; q < K; ++q) m = fmaxf(m, logE[i * K + q]);
         const float l = logE[i * K + k];
-        v = expf(l);
+        v = centred_exp_f32(l, m);
         if (W) v *= W[i * ldw + k];
-        if (mul_log) v *= l;
+        if (mul_log && v != 0.f) v *= l;
     }
     out[idx] = v;
 }
@@ -158,6 +160,8 @@ int ori_problem_check(const ori_problem_t* P) {
     if (P->flags & ORI_F_DROPOUT)
         if (!P->a2s || !P->lp || !P->pfloor || !P->pi_d) return set_error(ORI_EINVAL, "dropout buffers missing");
     if ((P->flags & ORI_F_QUIRK) && !P->eUw) return set_error(ORI_EINVAL, "quirk mode needs eUw");
+    if ((P->flags & ORI_F_ELBO) && (!P->xcol || (P->n_rows > 0 && !P->xrow)))
+        return set_error(ORI_EINVAL, "ORI_F_ELBO needs xrow / xcol (row and column sums of X)");
     if (P->flags & ORI_F_SPARSE) {
         if (!(P->flags & ORI_F_DROPOUT) || (P->flags & (ORI_F_QUIRK | ORI_F_ELBO)))
             return set_error(ORI_EINVAL, "ORI_F_SPARSE needs ORI_F_DROPOUT and excludes ORI_F_QUIRK / ORI_F_ELBO");
@@ -297,6 +301,11 @@ int ori_dropout_posterior_f32(const ori_problem_t* P, int gen, float* out, int64
     if (!(P->flags & ORI_F_DROPOUT)) return set_error(ORI_EINVAL, "model has no dropout layer");
     if (!out || ldo < P->p || row0 < 0 || row0 + nrows > P->n_rows) return set_error(ORI_EINVAL, "bad slab");
     return launch_dropout_posterior(P, gen, out, ldo, row0, nrows, (cudaStream_t)stream);
+}
+
+int ori_row_sums_f32(const float* X, int64_t ldx, int64_t n_rows, int32_t p, float* out, void* stream) {
+    if (n_rows < 0 || p <= 0 || ldx < p || (n_rows > 0 && (!X || !out))) return set_error(ORI_EINVAL, "ori_row_sums_f32: bad argument");
+    return launch_row_sums(X, ldx, n_rows, p, out, (cudaStream_t)stream);
 }
 
 int ori_column_sums_f64(const float* X, int64_t ldx, int64_t n_rows, int32_t p, double* out, void* stream) {

@@ -41,6 +41,7 @@ int launch_count_stats(const ori_problem_t* P, cudaStream_t st);
 int launch_quirk_weights(const ori_problem_t* P, int gen_old, cudaStream_t st);
 int launch_dropout_posterior(const ori_problem_t* P, int gen, float* out, long long ldo,
                              long long row0, long long nrows, cudaStream_t st);
+int launch_row_sums(const float* X, long long ldx, long long n_rows, int p, float* out, cudaStream_t st);
 int launch_col_sums(const float* X, long long ldx, long long n_rows, int p, double* out, cudaStream_t st);
 int launch_deviance(const ori_problem_t* P, int gen, const double* pi, const double* col_mean, long long* out_int,
                     double* out_f64, cudaStream_t st);

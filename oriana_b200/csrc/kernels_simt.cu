@@ -325,51 +325,76 @@ k_factor_update(long long rows, int K, int KP,
                 const float* __restrict__ E_old,
                 float* __restrict__ h1_io, float* __restrict__ h2_io,
                 float* __restrict__ E_new, float* __restrict__ eE_new, float* __restrict__ eEl_new,
+                const float* __restrict__ xsum,
                 double* __restrict__ Slog, double* __restrict__ Shat,
                 double* __restrict__ Hsum, double* __restrict__ PUVsum, int write_state)
 {
     __shared__ double sSlog[64], sShat[64], sH, sP;
+    __shared__ float smax[8];
     if (threadIdx.x < 64) { sSlog[threadIdx.x] = 0.0; sShat[threadIdx.x] = 0.0; }
     if (threadIdx.x == 0) { sH = 0.0; sP = 0.0; }
     __syncthreads();
     const long long total = rows * KP;
+    const int warp = threadIdx.x >> 5;
     double tH = 0.0, tP = 0.0;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(idx % KP);
-        if (k >= K) {
-            if (write_state) {
+    // a row occupies KP consecutive threads (KP divides 256); the trip count is uniform over the block
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {
+        const long long idx = base + threadIdx.x;
+        const bool in = idx < total;
+        const int k = in ? (int)(idx % KP) : KP;
+        const bool live = in && k < K;
+        float h1 = 0.f, h2 = 0.f, E = 0.f, Elog = -INFINITY;
+        if (live) {
+            double h1d, h2d;
+            if (FROM_PARAMS) {
+                h1d = (double)h1_io[idx]; h2d = (double)h2_io[idx];
+            } else {
+                const double z = (double)(acc1[idx] * e_old[idx]);
+                const double rate = acc2 ? (double)acc2[idx] : rate_const[k];
+                h1d = clamp_param_f64(c1[k] + z);
+                h2d = clamp_param_f64(c2[k] + rate);
+                if (PUVsum && acc2) tP += (double)E_old[idx] * (double)acc2[idx];
+            }
+            h1 = (float)h1d; h2 = (float)h2d;
+            E = (float)(h1d / h2d);
+            Elog = (float)digamma_f64((double)h1) - logf(h2);
+        }
+        // largest log-expectation of the row -> centred exponent (special.cuh)
+        float m = Elog;
+        for (int o = (KP < 32 ? KP : 32) >> 1; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (KP == 64) {
+            smax[warp] = m;
+            __syncthreads();
+            m = fmaxf(smax[warp], smax[warp ^ 1]);
+            __syncthreads();
+        }
+        const bool dead = !(m > EXP_DEAD);
+        const double shift = dead ? 0.0 : EXP_CENTER - (double)m;
+        if (!live) {
+            if (in && write_state) {
                 E_new[idx] = 0.f; eE_new[idx] = 0.f;
                 if (eEl_new) eEl_new[idx] = 0.f;
                 if (!FROM_PARAMS) { h1_io[idx] = 0.f; h2_io[idx] = 0.f; }
             }
             continue;
         }
-        double h1d, h2d;
-        if (FROM_PARAMS) {
-            h1d = (double)h1_io[idx]; h2d = (double)h2_io[idx];
-        } else {
-            const double z = (double)(acc1[idx] * e_old[idx]);
-            const double rate = acc2 ? (double)acc2[idx] : rate_const[k];
-            h1d = clamp_param_f64(c1[k] + z);
-            h2d = clamp_param_f64(c2[k] + rate);
-            if (PUVsum && acc2) tP += (double)E_old[idx] * (double)acc2[idx];
-        }
-        const float h1 = (float)h1d, h2 = (float)h2d;
-        const float E = (float)(h1d / h2d);
-        const double psi = digamma_f64((double)h1);
-        const float Elog = (float)psi - logf(h2);
         if (write_state) {
             if (!FROM_PARAMS) { h1_io[idx] = h1; h2_io[idx] = h2; }
             E_new[idx] = E;
-            const float eE = expf(Elog);
+            const float eE = centred_exp_f32(Elog, m);
             eE_new[idx] = eE;
             if (eEl_new) eEl_new[idx] = eE != 0.f ? eE * Elog : 0.f;     // sparse_zigap.py:116 operand
         }
         if (!Slog) continue;
         atomicAdd(&sSlog[k], (double)Elog);
         atomicAdd(&sShat[k], (double)E);
-        tH += (double)h1 - log((double)h2) + lgamma((double)h1) + (1.0 - (double)h1) * psi;
+        // entropy of q: a - log b + lgamma(a) + (1 - a) psi(a), with psi(a) taken as Elog + log b from the float32
+        // Elog that also enters the prior term (alpha1 - 1) sum Elog: when a ~ 1e-15 (zero NMF factors, base.py:38-40)
+        // psi ~ -1e15 and the two terms only cancel if they carry the same rounding
+        const double lb = log((double)h2);
+        tH += (double)h1 - lb + lgamma((double)h1) + (1.0 - (double)h1) * ((double)Elog + lb);
+        // the passes will see den * exp(shift_i + shift_j): sum_ij X_ij log den_ij gets back  - shift_i * sum_j X_ij
+        if (k == 0 && xsum) tH -= shift * (double)xsum[idx / KP];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -569,6 +594,7 @@ k_sparse_gene_update(ori_problem_t P)
         const double pis = P.pi_s[j];
         const double lps = logit_f64(pis);
         double ssum = 0.0;
+        float m = -INFINITY;
         for (int k = 0; k < KP; ++k) {
             const long long idx = (long long)j * KP + k;
             if (k >= K) {
@@ -597,16 +623,22 @@ k_sparse_gene_update(ori_problem_t P)
             const float h1 = (float)h1d, h2 = (float)h2d;
             const float E = (float)(h1d / h2d);
             const float Elog = (float)digamma_f64((double)h1) - logf(h2);     // gamma.py:48-61
-            const float eE = expf(Elog);
             const float Sn = (float)ps;                                       // bernoulli.py:45
-            const float ed_new = ps > P.tau ? eE : 0.f;                       // :134, :103
             const float veff = Sn * E;                                        // :140
             P.Vh_old[idx] = FROM_PARAMS ? veff : P.V_hat[idx];
-            P.p_s[idx] = Sn; P.logV[idx] = Elog; P.eV[idx] = eE;
-            P.eVd[idx] = ed_new; P.eVz[idx] = ed_new * Sn; P.V_hat[idx] = veff;
+            P.p_s[idx] = Sn; P.logV[idx] = Elog; P.V_hat[idx] = veff;
+            P.eVd[idx] = ps > P.tau ? 1.f : 0.f;                              // S_tilde (:134), scaled below
+            m = fmaxf(m, Elog);
             atomicAdd(&sSlog[k], (double)Elog);
             atomicAdd(&sShat[k], (double)E);
             ssum += ps;
+        }
+        // centred exponentials of this gene (special.cuh) and the masked operands of the next iteration
+        for (int k = 0; k < K; ++k) {
+            const long long idx = (long long)j * KP + k;
+            const float eE = centred_exp_f32(P.logV[idx], m);
+            const float ed_new = P.eVd[idx] * eE;                             // :103-104
+            P.eV[idx] = eE; P.eVd[idx] = ed_new; P.eVz[idx] = ed_new * P.p_s[idx];
         }
         if (!FROM_PARAMS) P.pi_s[j] = ssum / (double)K;                       // :196
     }
@@ -630,6 +662,20 @@ k_col_sums(const float* __restrict__ X, long long ldx, long long n_rows, int p, 
     double s = 0.0;
     for (long long r = r0; r < r1; ++r) s += (double)__ldg(X + r * ldx + j);
     if (s != 0.0) atomicAdd(out + j, s);
+}
+
+// Row sums of X (float32): one warp per cell.
+__global__ void __launch_bounds__(256)
+k_row_sums(const float* __restrict__ X, long long ldx, long long n_rows, int p, float* __restrict__ out)
+{
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    float s = 0.f;
+    for (int j = lane; j < p; j += 32) s += __ldg(X + row * ldx + j);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[row] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -851,13 +897,13 @@ int launch_row_update(const ori_problem_t* P, int g, int write_state, cudaStream
     if (write_state >= 2) {
         const bool sums = write_state == 2;
         k_factor_update<true><<<grid, 256, 0, st>>>(P->n_rows, K, KP, nullptr, nullptr, nullptr, nullptr,
-            nullptr, nullptr, nullptr, P->a1, P->a2, P->U_hat[g], P->eU[g], sparse ? P->eUl[g] : nullptr,
+            nullptr, nullptr, nullptr, P->a1, P->a2, P->U_hat[g], P->eU[g], sparse ? P->eUl[g] : nullptr, P->xrow,
             sums ? SlogU : nullptr, SU, part + R64_HROW, nullptr, 1);
     } else {
         // GaP: rate = alpha2 + sum_j V_hat_jk (gap.py:98); the column sums live in gsum[KP..2KP)
         k_factor_update<false><<<grid, 256, 0, st>>>(P->n_rows, K, KP, P->Zi, P->eU[g],
             drop ? P->a2s : nullptr, P->gsum + KP, P->hyper, P->hyper + K, P->U_hat[g],
-            P->a1, P->a2, P->U_hat[1 - g], P->eU[1 - g], sparse ? P->eUl[1 - g] : nullptr, SlogU, SU,
+            P->a1, P->a2, P->U_hat[1 - g], P->eU[1 - g], sparse ? P->eUl[1 - g] : nullptr, P->xrow, SlogU, SU,
             part + R64_HROW, part + R64_PUV, write_state);
     }
     return check_launch("k_factor_update(rows)");
@@ -876,13 +922,13 @@ int launch_gene_update(const ori_problem_t* P, int write_state, cudaStream_t st)
     }
     if (write_state == 2) {
         k_factor_update<true><<<grid, 256, 0, st>>>(p, K, KP, nullptr, nullptr, nullptr, nullptr,
-            nullptr, nullptr, nullptr, P->b1, P->b2, P->V_hat, P->eV, nullptr, SlogV, SV, gpart, nullptr, 1);
+            nullptr, nullptr, nullptr, P->b1, P->b2, P->V_hat, P->eV, nullptr, P->xcol, SlogV, SV, gpart, nullptr, 1);
     } else {
         // GaP: rate = beta2 + sum_i U_hat_ik (gap.py:106) with the NEW U_hat: red64[p+KP ..)
         float* Zj = P->red32; float* b2s = P->red32 + (long long)p * KP;
         k_factor_update<false><<<grid, 256, 0, st>>>(p, K, KP, Zj, P->eV, drop ? b2s : nullptr,
             P->red64 + p + KP, P->hyper + 2 * K, P->hyper + 3 * K, nullptr,
-            P->b1, P->b2, P->V_hat, P->eV, nullptr, SlogV, SV, gpart, nullptr, write_state);
+            P->b1, P->b2, P->V_hat, P->eV, nullptr, P->xcol, SlogV, SV, gpart, nullptr, write_state);
     }
     return check_launch("k_factor_update(genes)");
 }
@@ -929,6 +975,12 @@ int launch_col_sums(const float* X, long long ldx, long long n_rows, int p, doub
     dim3 grid(bx, cdiv(n_rows, rpc));
     k_col_sums<<<grid, 128, 0, st>>>(X, ldx, n_rows, p, (int)rpc, out);
     return check_launch("k_col_sums");
+}
+
+int launch_row_sums(const float* X, long long ldx, long long n_rows, int p, float* out, cudaStream_t st) {
+    if (n_rows == 0) return ORI_OK;
+    k_row_sums<<<cdiv(n_rows, 8), 256, 0, st>>>(X, ldx, n_rows, p, out);
+    return check_launch("k_row_sums");
 }
 
 template <int KP>

@@ -62,4 +62,27 @@ __host__ __device__ inline float clamp_param_f32(float x) {
     return fmaxf(1e-15f, x);
 }
 
+
+// exp(E[log .]) is kept per row (cell or gene) as exp(Elog - max_k Elog + EXP_CENTER): the multinomial step only uses
+// ratios exp(lU_ik + lV_jk) / sum_k'(...) (zigap.py:86-92), which do not change when a row of either factor is
+// rescaled, and the centred operands stay inside float32 where exp(lU) * exp(lV) would under- or overflow although
+// exp(lU + lV) -- what the reference evaluates -- does not (NMF-initialised factors, base.py:38-40, live there).
+// Range plan: operands in [e^-64, e^40.2] (components more than e^-104 below their row's largest are flushed to 0: the
+// reference's float32 exp(lU + lV) underflows below -103.3, so with log-expectations of order 1 on the other side
+// those terms are 0 there too); denominators <= K e^80; accumulators of R * operand <= (sum of X) * e^64.
+// The scale is a power of two, 2^58 = e^40.2: the largest component of every row becomes exactly 2^58, which tf32
+// represents exactly -- a scale like e^40 would give every row's leading operand the SAME tf32 rounding error, a bias
+// the sums over cells / genes do not average out (measured: +50 % error of the tensor path against the fp32 path).
+constexpr int EXP_CENTER_LOG2 = 58;
+constexpr double EXP_CENTER = 58.0 * 0.69314718055994530942;     // in natural-log units (ELBO bookkeeping)
+constexpr float EXP_FLUSH = -104.f;
+// rows whose largest log-expectation is below this carry no representable ratio information in float32 (the log itself
+// has lost its fractional bits): all their components are treated as 0, as the reference's float32 exp would make them
+constexpr float EXP_DEAD = -1e4f;
+
+__host__ __device__ inline float centred_exp_f32(float elog, float row_max) {
+    const float rel = elog - row_max;
+    return (row_max > EXP_DEAD && rel >= EXP_FLUSH) ? (float)ldexp(exp((double)rel), EXP_CENTER_LOG2) : 0.f;
+}
+
 }  // namespace ori

@@ -135,11 +135,13 @@ class HostStreamedCAVI:
             eV=torch.zeros((p, KP), **f32), red32=torch.zeros((2, p, KP), **f32),
             lp=torch.zeros((p,), **f32), pfloor=torch.zeros((p,), **f32), hyper=torch.ones((4, K), **f64),
             red64=torch.zeros((p + 2 * KP + _lib.R64_NSLOTS,), **f64), gsum=torch.zeros((2 * KP + 8,), **f64),
-            pi=torch.zeros((p,), **f64), scal=torch.zeros((_lib.SCAL_SLOTS,), **f64), trace=torch.zeros((4,), **f64))
+            pi=torch.zeros((p,), **f64), scal=torch.zeros((_lib.SCAL_SLOTS,), **f64), trace=torch.zeros((4,), **f64),
+            xcol=torch.zeros((p,), **f32))
         self._slabs = []
         for _ in range(2 if n > S else 1):
             s = dict(X=torch.zeros((S, ldx), **f32), red64=torch.zeros_like(g['red64']),
-                     acc64=torch.zeros_like(g['red64']))
+                     acc64=torch.zeros_like(g['red64']), xrow=torch.zeros((S,), **f32),
+                     cs64=torch.zeros((p,), **f64), csacc=torch.zeros((p,), **f64))
             for name in ('a1', 'a2', 'U0', 'U1', 'e0', 'e1', 'Zi', 'a2s', 'eUw'):
                 s[name] = torch.zeros((S, KP), **f32)
             if self._xbytes != 4:
@@ -173,6 +175,7 @@ class HostStreamedCAVI:
             P.Zi, P.a2s, P.eUw = s['Zi'].data_ptr(), s['a2s'].data_ptr(), s['eUw'].data_ptr()
             if 'tc_ws' in s:
                 P.tc_ws, P.tc_ws_floats = s['tc_ws'].data_ptr(), s['tc_ws'].numel()
+            P.xrow = s['xrow'].data_ptr()
         else:
             P.X = None
             P.a1 = P.a2 = P.Zi = P.a2s = P.eUw = dummy
@@ -181,6 +184,7 @@ class HostStreamedCAVI:
         P.red32, P.lp, P.pfloor = g['red32'].data_ptr(), g['lp'].data_ptr(), g['pfloor'].data_ptr()
         P.hyper, P.red64, P.gsum = g['hyper'].data_ptr(), g['red64'].data_ptr(), g['gsum'].data_ptr()
         P.pi_d, P.scal, P.elbo_trace = g['pi'].data_ptr(), g['scal'].data_ptr(), g['trace'].data_ptr()
+        P.xcol = g['xcol'].data_ptr()
         return P
 
     def _call(self, name, P, *args, stream=None):
@@ -216,6 +220,9 @@ class HostStreamedCAVI:
                     _lib.check(self._lib.ori_scatter_counts_f32(s['X'].data_ptr(), self._ldx, r0, rows, p, s['esc'][0].data_ptr(),
                                                                 s['esc'][1].data_ptr(), s['esc'][2].data_ptr(), cnt, st))
                     self.h2d_bytes += 12 * cnt
+        # row sums of the slab (ELBO scale term, include/oriana_b200.h xrow): X is in HBM anyway
+        _lib.check(self._lib.ori_row_sums_f32(s['X'].data_ptr(), self._ldx, rows, p, s['xrow'].data_ptr(),
+                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
         s['stage'][0, :rows].copy_(self.a1[r0:r0 + rows], non_blocking=True)
         s['stage'][1, :rows].copy_(self.a2[r0:r0 + rows], non_blocking=True)
         s['a1'][:rows, :K] = s['stage'][0, :rows]; s['a2'][:rows, :K] = s['stage'][1, :rows]
@@ -249,12 +256,17 @@ class HostStreamedCAVI:
             self._call('ori_count_stats', P, stream=st)            # zero-fills its red64, then counts
             self._call('ori_row_update', P, 0, 2, stream=st)       # + sum_i log U_hat, sum_i U_hat, entropy
             s['acc64'].add_(s['red64'])                            # per-stream partial (no cross-stream RMW)
+            _lib.check(self._lib.ori_column_sums_f64(s['X'].data_ptr(), self._ldx, rows, self.p, s['cs64'].data_ptr(),
+                                                     ctypes.c_void_p(st.cuda_stream)))
+            s['csacc'].add_(s['cs64'])
         for s in self._slabs:
-            s['acc64'].zero_()
+            s['acc64'].zero_(); s['csacc'].zero_()
         self._slab_loop(body)
+        cs = torch.zeros((self.p,), dtype=torch.float64, device=self._dev)
         for s in self._slabs:
-            g['red64'].add_(s['acc64'])
+            g['red64'].add_(s['acc64']); cs.add_(s['csacc'])
         self._shard.allreduce_sum(g['red64'])
+        g['xcol'].copy_(self._shard.allreduce_sum(cs).to(torch.float32))
         self._call('ori_init_expectations', Pg, 0)                 # n_rows = 0: gene side only
         self._call('ori_mstep', Pg, _lib.ORI_M_INIT_KEEP if self._keep_hyper else _lib.ORI_M_INIT)
         self._download_genes()

@@ -78,7 +78,7 @@ class FactorModel(metaclass=ABCMeta):
     _sparse = False      # SparseZIGaP sets this
 
     def __init__(self, cmatrix, k=2, use_factors=True, *, state=None, compat_quirk=False, sharded=False,
-                 process_group=None, elbo=True, trace_cap=4096, force_simt=False, tensor=None):
+                 process_group=None, elbo=True, trace_cap=4096, force_simt=False, tensor=None, nmf=None):
         self._dev = _lib.require_cuda()
         self._lib = _lib.load()
         _lib.check(self._lib.ori_device_check(self._dev.index or 0))
@@ -107,6 +107,9 @@ class FactorModel(metaclass=ABCMeta):
             | (_lib.ORI_F_NO_TENSOR if force_simt else 0) | (_lib.ORI_F_SPARSE if self._sparse else 0)
         self.compat_quirk = bool(compat_quirk and self._dropout)
         self._trace_cap = int(trace_cap)
+        if nmf not in (None, 'host', 'device'):
+            raise ValueError("nmf must be None, 'host' or 'device'")
+        self._nmf_mode = nmf
         self._gen = 0
         self._iter = 0
         self._dirty = False
@@ -173,6 +176,15 @@ class FactorModel(metaclass=ABCMeta):
         self._pi = torch.zeros((p,), **f64) if self._dropout else None
         self._scal = torch.zeros((_lib.SCAL_SLOTS,), **f64)
         self._trace = torch.zeros((self._trace_cap,), **f64)
+        # row sums of this rank's X and column sums of the whole X: the ELBO takes the per-row / per-gene scales of
+        # the exp(E[log .]) operands back through them (include/oriana_b200.h, xrow / xcol)
+        self._xrow = self._xcol = None
+        if self._flags & _lib.ORI_F_ELBO:
+            self._xrow = torch.zeros((max(n, 1),), **f32)
+            cs = torch.zeros((p,), **f64)
+            _lib.check(self._lib.ori_row_sums_f32(self._X.data_ptr(), ldx, n, p, self._xrow.data_ptr(), _lib.stream_ptr()))
+            _lib.check(self._lib.ori_column_sums_f64(self._X.data_ptr(), ldx, n, p, cs.data_ptr(), _lib.stream_ptr()))
+            self._xcol = self._shard.allreduce_sum(cs).to(torch.float32)
         self._tc_ws = None
         if self._tensor:
             self._tc_ws = torch.empty((int(self._lib.ori_tc_workspace_floats(n, p, KP)) + 32,), **f32)
@@ -195,6 +207,7 @@ class FactorModel(metaclass=ABCMeta):
         P.pi_d, P.scal, P.elbo_trace = ptr(self._pi), ptr(self._scal), ptr(self._trace)
         if self._tc_ws is not None:
             P.tc_ws, P.tc_ws_floats = self._tc_ws.data_ptr(), self._tc_ws.numel()
+        P.xrow, P.xcol = ptr(self._xrow), ptr(self._xcol)
         self._bind_extra(P, rowf, genef, ptr)
         self._P = P
         _lib.check(self._lib.ori_problem_check(ctypes.byref(P)))
@@ -221,19 +234,44 @@ class FactorModel(metaclass=ABCMeta):
 
     # ------------------------------------------------------------------------------------------------
     def _nmf_warm_start(self):
-        """`use_factors=True`: the reference seeds a1, b1 with sklearn NMF factors (base.py:38-40).  That is
-        host-side initialisation outside the CAVI path; it is run like the reference
-        does, on the host, and only for matrices the host can factorise."""
-        if self._shard.enabled:
-            raise ValueError('use_factors=True needs the whole matrix on one rank; use use_factors=False')
-        if self.n * self.p > 50_000_000:
-            raise ValueError('use_factors=True runs sklearn NMF on the host (base.py:38-40); '
-                             'this matrix is too large for that -- pass use_factors=False')
-        from sklearn.decomposition import NMF
-        model = NMF(n_components=self.k)
-        X = self.cmatrix.as_array()
-        self._nmf_U = model.fit_transform(X)
-        self._nmf_V = model.components_.T
+        """`use_factors=True`: the reference seeds a1, b1 with sklearn NMF factors of X (base.py:38-40).  Matrices the
+        host can factorise on one rank go through sklearn exactly like the reference; larger or row-sharded ones
+        (where the reference cannot run at all) are factorised in HBM (`_nmf_device`)."""
+        mode = self._nmf_mode
+        if mode is None:
+            mode = 'device' if (self._shard.enabled or self.n * self.p > 50_000_000) else 'host'
+        if mode == 'host':
+            if self._shard.enabled:
+                raise ValueError("nmf='host' needs the whole matrix on one rank")
+            from sklearn.decomposition import NMF
+            model = NMF(n_components=self.k)
+            X = self.cmatrix.as_array()
+            self._nmf_U = model.fit_transform(X)
+            self._nmf_V = model.components_.T
+        else:
+            self._nmf_U, self._nmf_V = self._nmf_device()
+
+    def _nmf_device(self, iters=100, eps=1e-9):
+        """Non-negative factorisation X ~ U V^T (Frobenius) by Lee-Seung multiplicative updates on the resident row
+        block: two library GEMMs per sweep (X V and X^T U; torch.matmul, fp32), the p x k and k x k products summed
+        over ranks.  Initialisation as sklearn's `init='random'`: sqrt(mean(X) / k) * |N(0, 1)|, seeded from
+        `np.random` (rank 0's gene factors are broadcast).  Initialisation only: not part of the CAVI iteration."""
+        dev, k = self._dev, self.k
+        X = self._X
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(int(np.random.randint(0, 2 ** 31 - 1)))
+        tot = self._shard.allreduce_sum(X.sum(dtype=torch.float64).reshape(1))[0]
+        scale = float(torch.sqrt(tot / (float(self.n_total) * self.p * k)).item()) or 1.0
+        U = scale * torch.randn((self.n, k), device=dev, generator=gen).abs_()
+        V = scale * torch.randn((self.p, k), device=dev, generator=gen).abs_()
+        self._shard.broadcast(V)
+        for _ in range(iters):
+            VtV = V.T @ V
+            U *= (X @ V) / (U @ VtV + eps)
+            XtU = self._shard.allreduce_sum(X.T @ U)
+            UtU = self._shard.allreduce_sum(U.T @ U)
+            V *= XtU / (V @ UtU + eps)
+        return U, V
 
     def initialize_parameters(self):
         """base.py:43-52."""
@@ -243,7 +281,10 @@ class FactorModel(metaclass=ABCMeta):
 
     def _set_factor(self, dst, values):
         K = self.k
-        v = torch.as_tensor(np.asarray(values, dtype=np.float64), device=self._dev)
+        if isinstance(values, torch.Tensor):
+            v = values.to(device=self._dev, dtype=torch.float64)
+        else:
+            v = torch.as_tensor(np.asarray(values, dtype=np.float64), device=self._dev)
         dst.zero_()
         dst[:, :K] = torch.clamp(torch.nan_to_num(v), min=1e-15).to(torch.float32)   # zigap.py:63,73
 

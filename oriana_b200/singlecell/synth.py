@@ -2,7 +2,8 @@
 
 The host cannot hold BASELINE.json's larger configurations, so each rank generates its row block with the
 library's counter-based generator (`ori_synth_counts_f32`, csrc/synth.cu).  The reference's own generator
-(oriana/singlecell/generation.py) is out of scope.
+(oriana/singlecell/generation.py) is provided in `generation.py`; its counts are not Poisson draws (SURVEY.md
+section 2 #13), so the bench does not use it.
 """
 import torch
 

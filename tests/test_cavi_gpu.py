@@ -265,3 +265,60 @@ def test_count_matrix_to_device_narrow_upload(cuda_lib):
         np.testing.assert_array_equal(d.cpu().numpy(), Y.astype(np.float32))
     Z = torch.as_tensor(X, device='cuda')
     np.testing.assert_array_equal(CountMatrix(Z).to_device().cpu().numpy(), X.astype(np.float32))
+
+
+def test_nmf_warm_start_on_device(cuda_lib):
+    """`use_factors=True` (base.py:38-40) with the factorisation done in HBM: the factors are non-negative, reconstruct
+    X about as well as sklearn's NMF does, seed a1 / b1 exactly like the host path, and the CAVI steps run from them."""
+    from oracle import cavi_numpy as cn
+    from oriana.models import ZIGaP
+    from oriana.singlecell import CountMatrix
+    from sklearn.decomposition import NMF
+    X = cn.synth_counts(400, 300, 5, seed=9)
+    np.random.seed(0)
+    m = ZIGaP(CountMatrix(X), k=5, use_factors=True, nmf='device')
+    U, V = m._nmf_U.cpu().numpy().astype(np.float64), m._nmf_V.cpu().numpy().astype(np.float64)
+    assert (U >= 0).all() and (V >= 0).all()
+    err_dev = np.linalg.norm(X - U @ V.T)
+    sk = NMF(n_components=5, max_iter=400)
+    W = sk.fit_transform(X.astype(np.float64))
+    err_host = np.linalg.norm(X - W @ sk.components_)
+    assert err_dev < 1.05 * err_host, (err_dev, err_host)
+    assert relerr(m.a1.asarray(), np.maximum(U, 1e-15)) < 1e-6 and relerr(m.b1.asarray(), np.maximum(V, 1e-15)) < 1e-6
+    for _ in range(3):
+        m.step()
+    tr = m.elbo_trace
+    assert np.isfinite(tr).all() and (np.diff(tr) > -1e-6 * np.abs(tr[:-1])).all()
+    np.random.seed(0)
+    mh = ZIGaP(CountMatrix(X), k=5, use_factors=True, nmf='host')      # the reference's own route (sklearn)
+    mh.step()
+    assert np.isfinite(mh.elbo_trace).all()
+
+
+@pytest.mark.parametrize('tensor', [False, True])
+def test_nmf_initialised_trajectory_matches_reference(cuda_lib, tensor):
+    """The reference's default construction path (`use_factors=True`, base.py:38-40) from its recorded
+    post-construction state (tests/golden/zigap_nmf.npz): E[log U], E[log V] between -100 and -1e15, where
+    exp(lU) * exp(lV) leaves float32 although the reference's exp(lU + lV) does not.  Both kernel families stay finite
+    and on the reference's trajectory (per-row centred exponentials, csrc/special.cuh)."""
+    from oriana.models import ZIGaP
+    from oriana.singlecell import CountMatrix
+    g = load_golden('zigap_nmf')
+    s = golden_state(g, 0)
+    m = ZIGaP(CountMatrix(s['X']), k=s['a1'].shape[1], use_factors=False, state=s, compat_quirk=True, tensor=tensor)
+    assert m.uses_tensor_path == tensor
+    steps = [int(t) for t in g['steps']]
+    # tensor path: TF32 operand rounding is amplified by the near-dead components of this regime
+    ftol, htol, dtol = (1e-2, 3e-4, 1e-3) if tensor else (3e-4, 1e-5, 2e-5)
+    for t in range(1, max(steps) + 1):
+        m.step()
+        if t in steps:
+            r = golden_state(g, t)
+            for k in ('a1', 'a2', 'b1', 'b2'):
+                got = getattr(m, k).asarray()
+                assert np.isfinite(got).all(), (t, k)
+                assert relerr(got, r[k]) < ftol, (t, k)
+            for k in ('alpha1', 'alpha2', 'beta1', 'beta2', 'pi_d'):
+                assert relerr(getattr(m, k).asarray(), r[k]) < htol, (t, k)
+            assert np.max(np.abs(m.D_hat - r['p_d'])) < dtol, t
+    assert np.isfinite(m.elbo_trace).all()

@@ -117,6 +117,24 @@ def test_count_matrix_reference_interface(tmp_path):
     assert list(plain.col_names) == [0, 1, 2, 3, 4] and list(plain.row_names) == [0, 1]
 
 
+def test_block_generator_matches_reference_fixture():
+    """singlecell/generation.py:68-86 under fixed seeds, against matrices recorded from the reference
+    (oracle/make_golden.py generator): same draws in the same order, bit for bit."""
+    from conftest import load_golden
+    from oracle.make_golden import GENERATOR_CASES
+    from oriana.singlecell import generate_factor_matrices
+    g = load_golden('generator')
+    for i, (args, kw) in enumerate(GENERATOR_CASES):
+        np.random.seed(100 + i)
+        X, U, V, labels = generate_factor_matrices(*args, **kw)
+        np.testing.assert_array_equal(X, g['c%d_X' % i])
+        np.testing.assert_array_equal(U, g['c%d_U' % i])
+        np.testing.assert_array_equal(V, g['c%d_V' % i])
+        np.testing.assert_array_equal(labels, g['c%d_labels' % i])
+    with pytest.raises(ValueError):
+        generate_factor_matrices(10, 10, 2, n_groups=3)      # fewer components than groups: the reference raises too
+
+
 def test_count_matrix_ingest_helpers():
     """Row blocks of a sharded matrix tile it exactly; the narrow storage type follows the largest count."""
     import torch
@@ -152,7 +170,7 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().ori_version() >= 100
     # struct layout agreed between the header and the ctypes mirror
     n_ptr = len(re.findall(r'^\s+(?:const\s+)?(?:float|double)\s*\*', header.split('typedef struct ori_problem')[1].split('} ori_problem_t')[0], flags=re.M))
-    assert ctypes.sizeof(_lib.OriProblem) == 3 * 8 + 6 * 4 + 24 * 8 + 8 + 9 * 8 and n_ptr >= 20   # + the sparse block
+    assert ctypes.sizeof(_lib.OriProblem) == 3 * 8 + 6 * 4 + 24 * 8 + 8 + 9 * 8 + 2 * 8 and n_ptr >= 20   # + the sparse block + xrow, xcol
 
 
 def test_no_cpu_fallback():

@@ -88,3 +88,21 @@ def test_port_matches_live_reference():
             assert relerr(s[k], r[k]) < 2e-5, k
     finally:
         refshim.release_reference()     # leave the repo's alias package importable for later tests
+
+
+def test_nmf_initialised_trajectory_matches_reference():
+    """The reference's default construction path (`use_factors=True`, base.py:38-40): NMF factors with tiny and exactly
+    zero entries put E[log U], E[log V] at -100 ... -1e15.  The ratio form only survives there because each factor is
+    rescaled per row (`cn.centred_exp`); without it a1, b1 overflow in the first step."""
+    g = load_golden('zigap_nmf')
+    s = golden_state(g, 0)
+    assert (s['a1'] <= 1e-15).any() and (s['b1'] <= 1e-15).any()          # exact zeros of the NMF factors, clamped
+    steps = [int(t) for t in g['steps']]
+    for t in range(1, max(steps) + 1):
+        cn.step(s, quirk=True)
+        if t in steps:
+            r = golden_state(g, t)
+            for k in PARAMS + ('pi_d',):
+                assert np.isfinite(s[k]).all(), (t, k)
+                assert relerr(s[k], r[k]) < 2e-4, (t, k)
+            assert np.max(np.abs(s['p_d'] - r['p_d'])) < 1e-5, t

@@ -44,6 +44,37 @@ def write_generator_fixture():
     print('generator written')
 
 
+def write_sparse_generator_fixture():
+    """The reference's own experiment (experiments/clustering.py:18-57): SparseZIGaP, use_factors=False, on a matrix from
+    its block generator (counts up to ~1e5) -- trajectory and the deviance trace its driver prints."""
+    refshim.import_reference()
+    from oriana.models import SparseZIGaP
+    from oriana.singlecell import CountMatrix, generate_factor_matrices
+    np.random.seed(3)
+    X, _, _, _ = generate_factor_matrices(100, 800, 2, sparsity_degree_in_v=0.9, beta=80, theta=0.5, n_groups=2,
+                                          zero_inflation_level=0.5)
+    rec = (1, 3, 6)
+    np.random.seed(1)
+    m = SparseZIGaP(CountMatrix(X), k=2, use_factors=False)
+    out = {'model': 'SparseZIGaP', 'K': 2, 'tau': 0.5, 'steps': np.asarray(rec)}
+    s0 = refshim.snapshot(m)
+    out['X'] = s0.pop('X').astype(np.int32)
+    for k, v in s0.items():
+        out['s0_' + k] = v.astype(np.float32) if k == 'p_d' else v
+    out['s0_deviance'] = np.float64(m.reconstruction_deviance())       # clustering.py:20, before any step
+    for t in range(1, max(rec) + 1):
+        m.step()
+        if t in rec:
+            st = refshim.snapshot(m); st.pop('X')
+            for k, v in st.items():
+                out['s%d_%s' % (t, k)] = v.astype(np.float32) if k == 'p_d' else v
+            out['s%d_deviance' % t] = np.float64(m.reconstruction_deviance())
+            out['s%d_explained' % t] = np.float64(m.explained_deviance())
+    np.savez_compressed(os.path.join(OUT, 'sparse_gen.npz'), **out)
+    refshim.release_reference()
+    print('sparse_gen written')
+
+
 def write_nmf_fixture():
     """The reference's DEFAULT construction path, `use_factors=True` (base.py:38-40: a1, b1 seeded with sklearn NMF
     factors, many of them tiny or exactly 0, so E[log U] reaches -100 ... -1e15 and exp(E log U) underflows float32 on
@@ -76,6 +107,8 @@ def main():
         return write_generator_fixture()
     if sys.argv[1:] == ['nmf']:
         return write_nmf_fixture()
+    if sys.argv[1:] == ['sparse_gen']:
+        return write_sparse_generator_fixture()
     ref = refshim.import_reference()
     from oriana.models import ZIGaP, GaP
     from oriana.singlecell import CountMatrix
@@ -156,6 +189,7 @@ def main():
     print('special written')
     write_generator_fixture()
     write_nmf_fixture()
+    write_sparse_generator_fixture()
 
 
 if __name__ == '__main__':

@@ -16,7 +16,7 @@ from conftest import load_golden, relerr
 
 def _state(g, t):
     pre = 's%d_' % t
-    skip = ('deviance', 'explained')
+    skip = ('deviance', 'explained')       # sparse_gen: the reference's own experiment data (clustering.py:47)
     s = {k[len(pre):]: np.array(g[k], dtype=np.float64) for k in g.files if k.startswith(pre) and k[len(pre):] not in skip}
     s['X'] = g['X'].astype(np.int64)
     return s
@@ -33,7 +33,7 @@ def test_sparse_z_kernel_matches_reference_numba_kernel(name):
         assert relerr(a, g[key]) < tol, key
 
 
-@pytest.mark.parametrize('name', ['sparse_k4', 'sparse_ragged'])
+@pytest.mark.parametrize('name', ['sparse_k4', 'sparse_ragged', 'sparse_gen'])
 def test_sparse_trajectory_and_deviance_match_reference(name):
     from oracle import sparse_numpy as sn
     g = load_golden(name)

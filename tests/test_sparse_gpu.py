@@ -39,11 +39,13 @@ def make_model(s, tau):
     return SparseZIGaP(CountMatrix(s['X']), k=s['a1'].shape[1], use_factors=False, state=s, tau=tau)
 
 
-@pytest.mark.parametrize('name', ['sparse_k4', 'sparse_ragged'])
+@pytest.mark.parametrize('name', ['sparse_k4', 'sparse_ragged', 'sparse_gen'])
 def test_sparse_trajectory_and_deviance_match_reference(cuda_lib, name):
     g = load_golden(name)
     m = make_model(_state(g, 0), float(g['tau']))
     assert not m.uses_tensor_path
+    if 's0_deviance' in g.files:             # the driver's first print, before any step (clustering.py:20)
+        assert abs(m.reconstruction_deviance() - float(g['s0_deviance'])) <= 1e-4 * abs(float(g['s0_deviance']))
     steps = [int(t) for t in g['steps']]
     for t in range(1, max(steps) + 1):
         m.step()

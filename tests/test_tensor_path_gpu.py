@@ -190,3 +190,30 @@ def test_host_streamed_step_on_the_tensor_path(cuda_lib):
         assert relerr(hs[k], getattr(m, k).asarray()) < 1e-4, k
     want = m.elbo_trace[:3]
     assert np.max(np.abs(np.asarray(elbos) - want) / np.abs(want)) < 1e-5
+
+
+def test_config5_slab_tensor_path_matches_cuda_core_path(cuda_lib):
+    """BASELINE.json configs[4] (2M x 30k, K = 64, ~90 % zeros, 8 GPUs) at one slab of its cells: full gene axis and
+    latent dimension (the KP = 64 plan with 32-wide sweep tiles), the sparsity of that configuration."""
+    import torch
+    from oriana.models import ZIGaP
+    from oriana.singlecell import synth_counts_device
+    n, p, K = 3072, 30_000, 64
+    X = synth_counts_device(n, p, K, seed=12, zero_level=0.12)
+    zeros = float((X[:, :p] == 0).float().mean())
+    assert 0.85 < zeros < 0.95, zeros
+    np.random.seed(6)
+    m0 = ZIGaP(X[:, :p], k=K, use_factors=False, tensor=False)
+    st = m0.state_dict(); st['X'] = X[:, :p]
+    ms = ZIGaP(X[:, :p], k=K, use_factors=False, state=st, tensor=False)
+    mt = ZIGaP(X[:, :p], k=K, use_factors=False, state=st, tensor=True)
+    assert mt.uses_tensor_path and mt._KP == 64
+    for _ in range(2):
+        mt.step(); ms.step()
+    for k in FACTORS:
+        assert relerr(getattr(mt, k).asarray(), getattr(ms, k).asarray()) < 2e-3, k
+    for k in HYPER + ('pi_d',):
+        assert relerr(getattr(mt, k).asarray(), getattr(ms, k).asarray()) < 1e-4, k
+    et, es = mt.elbo_trace, ms.elbo_trace
+    assert np.max(np.abs(et - es) / np.abs(es)) < 1e-4, (et, es)
+    assert (np.diff(et) > 0).all()

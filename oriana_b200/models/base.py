@@ -436,7 +436,8 @@ class FactorModel(metaclass=ABCMeta):
         return self._meanlog(self._b1, self._b2)
 
     def device_state(self):
-        """Zero-copy views of the device-resident state (torch CUDA tensors)."""
+        """Zero-copy views of the device-resident state (torch CUDA tensors).  `eU` / `eV` are exp(E[log .]) rescaled per
+        cell / gene by 2^58 / max_k exp(E[log .]) (csrc/special.cuh): only their ratios within a row are meaningful."""
         K = self.k
         out = dict(X=self._X, a1=self._a1[:, :K], a2=self._a2[:, :K], b1=self._b1[:, :K], b2=self._b2[:, :K],
                    U_hat=self._Uhat[self._gen][:, :K], V_hat=self._Vhat[:, :K],

@@ -177,6 +177,64 @@ def test_full_size_properties_config2(cuda_lib):
     assert abs(ma.elbo() - mb.elbo()) < 1e-6 * abs(ma.elbo())
 
 
+def test_full_size_properties_config3(cuda_lib):
+    """BASELINE.json configs[2] (100k x 20k, K=20, dropout on; 8 GB of counts) at full size on the tensor path:
+    monotone ELBO, pi bounds, sum-preservation of the latent counts, and the two-block property -- the gene-side
+    sums of the whole matrix equal the sums of its two halves (what row sharding over ranks relies on)."""
+    import ctypes
+    import torch
+    from oriana.models import ZIGaP
+    from oriana.singlecell import synth_counts_device
+    from oriana_b200 import _lib
+    n, p, K = 100_000, 20_000, 20
+    X = synth_counts_device(n, p, K, seed=3)
+    np.random.seed(0)
+    m = ZIGaP(X[:, :p], k=K, use_factors=False)
+    assert m.uses_tensor_path
+    # one step by hand: the latent counts of every cell / gene add up to its counts (sum_k r_ijk = 1, zigap.py:91-94)
+    m._call('ori_zero_accumulators', 1)
+    m._call('ori_pass_rows', m._gen)
+    Zi = (m._Zi * m._eU[m._gen]).sum(1)
+    rows = X[:, :p].sum(1)
+    assert float(((Zi - rows).abs() / rows.clamp(min=1)).max()) < 2e-3
+    m._call('ori_row_update', m._gen, 1)
+    m._call('ori_pass_genes', m._gen)
+    whole = m._red32.clone()
+    Zj = (whole[0] * m._eV).sum(1)
+    cols = X[:, :p].sum(0)
+    assert float(((Zj - cols).abs() / cols.clamp(min=1)).max()) < 2e-3
+    # the same gene-side sums from two row blocks, each through its own problem description
+    halves = torch.zeros_like(whole)
+    for r0, r1 in ((0, n // 2 + 64), (n // 2 + 64, n)):
+        P = _lib.OriProblem.from_buffer_copy(m._P)
+        P.n_rows = r1 - r0
+        P.X = m._X[r0:r1].data_ptr()
+        for name in ('a1', 'a2', 'Zi', 'a2s'):
+            setattr(P, name, getattr(m, '_' + name)[r0:r1].data_ptr())
+        for g in (0, 1):
+            P.U_hat[g] = m._Uhat[g][r0:r1].data_ptr(); P.eU[g] = m._eU[g][r0:r1].data_ptr()
+        P.xrow = m._xrow[r0:r1].data_ptr()
+        part = torch.zeros_like(whole)
+        scratch64 = torch.zeros_like(m._red64)
+        P.red32, P.red64 = part.data_ptr(), scratch64.data_ptr()
+        # the block's own local half-step (the tensor path lays its workspace out per problem size)
+        m._Zi[r0:r1].zero_(); m._a2s[r0:r1].zero_()
+        for call, args in (('ori_pass_rows', (m._gen,)), ('ori_row_update', (m._gen, 1)), ('ori_pass_genes', (m._gen,))):
+            _lib.check(getattr(m._lib, call)(ctypes.byref(P), *args, _lib.stream_ptr()))
+        halves += part
+    scale = whole.abs().amax(dim=(1, 2), keepdim=True)
+    assert float(((halves - whole).abs() / scale).max()) < 1e-4        # fp32 sums over 100k cells in a different order
+    m._call('ori_gene_update', 1); m._pending_mstep = True
+    m.update_prior_hyper_parameters()
+    for _ in range(3):
+        m.step()
+    tr = m.elbo_trace
+    assert np.isfinite(tr).all() and np.all(np.diff(tr) >= -1e-6 * np.abs(tr[:-1]))
+    pi = m.pi_d.asarray()
+    nzfrac = (X[:, :p] != 0).double().mean(0).cpu().numpy()
+    assert np.all(pi >= nzfrac - 1e-9) and np.all(pi <= 1 + 1e-12)
+
+
 @pytest.mark.parametrize('name', ['zigap_ragged', 'gap_ragged'])
 def test_host_streamed_step_matches_device_model(cuda_lib, name):
     """The host-buffer entry (what bench.py's e2e times) gives the device model's results, slab by slab."""

@@ -43,8 +43,12 @@ using namespace tc;
 #endif
 
 constexpr int TC_OWN = 128;
-constexpr int NEW = 8;                // element-wise warps (more of them only get 96 registers each: measured slower)
+#ifndef ORI_TC_NEW
+#define ORI_TC_NEW 8
+#endif
+constexpr int NEW = ORI_TC_NEW;       // element-wise warps: 8 (168 registers each) or 16 (96 registers, one column group per tile)
 constexpr int SLICES = NEW / 4;       // element-wise warps per TMEM lane quarter
+constexpr int ASUBS = SLICES / 2;     // warps sharing one own-side array / one accumulator
 constexpr int TC_THREADS = 64 + 32 * NEW;
 
 // Plan of one kernel variant.  KP: padded latent dimension (32 or 64).  PAIR: the CTA-pair variant (cta_group::2,
@@ -186,7 +190,11 @@ struct TileIter {
 };
 
 template <bool GENES, bool DROPOUT, bool ELBO, bool PAIR, int KP>
+#if ORI_TC_NEW == 16
+__global__ void __maxnreg__(96)
+#else
 __global__ void __launch_bounds__(TC_THREADS, 1)
+#endif
 k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
 {
     using C = Cfg<KP, PAIR>;
@@ -428,45 +436,44 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
 
         // own-side operands of one work item -> TMEM: slice 0 writes hi / lo of exp(E log .), slice 1 (dropout only)
         // hi / lo of E[.], for this warp's 32 lanes, 32 latent components at a time
+        const int aside = slice / ASUBS;              // 0: exp(E log .) and accumulator 1; 1: E[.] and accumulator 2
+        const int asub = slice % ASUBS;
         auto a_load_store = [&](int own0) {
-            if (slice * 2 < NQ) {
+            if (aside * 2 < NQ) {
                 const long long idx = (long long)own0 + lrow;
-                const float* src = (slice ? a.own_E : a.own_e) + idx * KP;
+                const float* src = (aside ? a.own_E : a.own_e) + idx * KP;
                 const bool ok = idx < a.own_total;
-                const bool scale = GENES && slice;                 // uv is kept in log2 units: V_hat side * log2(e)
+                const bool scale = GENES && aside;                 // uv is kept in log2 units: V_hat side * log2(e)
 #pragma unroll
-                for (int kb = 0; kb < C::KB; ++kb) {
-                    float av[32];
+                for (int c16 = asub; c16 < KP / 16; c16 += ASUBS) {        // 16 latent components at a time
+                    float av[16];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(src + 32 * kb) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(src + 16 * c16) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
                         av[4 * c] = v.x; av[4 * c + 1] = v.y; av[4 * c + 2] = v.z; av[4 * c + 3] = v.w;
                     }
+                    uint32_t whi[16], wlo[16];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint32_t whi[16], wlo[16];
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            const float v = scale ? av[16 * h + e] * LOG2E : av[16 * h + e];
-                            const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
-                            whi[e] = __float_as_uint(hi);
-                            wlo[e] = __float_as_uint(v - hi);
-                        }
-                        tmem_st16(tlane + TM_A + (2 * slice) * KP + 32 * kb + 16 * h, whi);
-#if ORI_TC_BF16X
-                        // cross-term operand [hi | lo] as bf16 pairs: these 16 components -> 8 + 8 columns
-                        uint32_t phi[8], plo[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            phi[e] = pack_bf16x2(__uint_as_float(whi[2 * e]), __uint_as_float(whi[2 * e + 1]));
-                            plo[e] = pack_bf16x2(__uint_as_float(wlo[2 * e]), __uint_as_float(wlo[2 * e + 1]));
-                        }
-                        tmem_st8(tlane + TM_A + (2 * slice + 1) * KP + 16 * kb + 8 * h, phi);
-                        tmem_st8(tlane + TM_A + (2 * slice + 1) * KP + KP / 2 + 16 * kb + 8 * h, plo);
-#else
-                        tmem_st16(tlane + TM_A + (2 * slice + 1) * KP + 32 * kb + 16 * h, wlo);
-#endif
+                    for (int e = 0; e < 16; ++e) {
+                        const float v = scale ? av[e] * LOG2E : av[e];
+                        const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+                        whi[e] = __float_as_uint(hi);
+                        wlo[e] = __float_as_uint(v - hi);
                     }
+                    tmem_st16(tlane + TM_A + (2 * aside) * KP + 16 * c16, whi);
+#if ORI_TC_BF16X
+                    // cross-term operand [hi | lo] as bf16 pairs: these 16 components -> 8 + 8 columns
+                    uint32_t phi[8], plo[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        phi[e] = pack_bf16x2(__uint_as_float(whi[2 * e]), __uint_as_float(whi[2 * e + 1]));
+                        plo[e] = pack_bf16x2(__uint_as_float(wlo[2 * e]), __uint_as_float(wlo[2 * e + 1]));
+                    }
+                    tmem_st8(tlane + TM_A + (2 * aside + 1) * KP + 8 * c16, phi);
+                    tmem_st8(tlane + TM_A + (2 * aside + 1) * KP + KP / 2 + 8 * c16, plo);
+#else
+                    tmem_st16(tlane + TM_A + (2 * aside + 1) * KP + 16 * c16, wlo);
+#endif
                 }
             }
             tmem_wait_st();
@@ -662,12 +669,12 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             //      slice 0 drains acc1, slice 1 acc2
             mbar_wait(&bars[B_ACC_READY], li & 1, 32);
             tc_fence_after();
-            if (slice == 0 || DROPOUT) {
-                float* out = (slice == 0 ? a.acc1 : a.acc2) + own_idx * KP;
+            if (aside == 0 || DROPOUT) {
+                float* out = (aside == 0 ? a.acc1 : a.acc2) + own_idx * KP;
 #pragma unroll
-                for (int g = 0; g < KP / 16; ++g) {
+                for (int g = asub; g < KP / 16; g += ASUBS) {
                     uint32_t v[16];
-                    tmem_ld16(tlane + TM_ACC + slice * KP + g * 16, v);
+                    tmem_ld16(tlane + TM_ACC + aside * KP + g * 16, v);
                     tmem_wait_ld();
                     if (own_ok) {
 #pragma unroll
@@ -936,7 +943,11 @@ static int launch_tc_pass_p(const ori_problem_t* P, int gen_old, cudaStream_t st
 
 template <bool GENES>
 static int launch_tc_pass(const ori_problem_t* P, int gen_old, cudaStream_t st) {
+#if ORI_TC_NEW == 8
     if (P->KP == 64) return launch_tc_pass_p<GENES, true, 64>(P, gen_old, st);
+#else
+    if (P->KP == 64) return set_error(ORI_EUNSUPPORTED, "this build (ORI_TC_NEW != 8) has no KP = 64 plan");
+#endif
     return use_pair() ? launch_tc_pass_p<GENES, true, 32>(P, gen_old, st) : launch_tc_pass_p<GENES, false, 32>(P, gen_old, st);
 }
 

@@ -71,6 +71,94 @@ def sharded_step(s, shard, n_total, quirk):
     return s
 
 
+def sharded_sparse_step(s, shard, n_total, tau):
+    """One SparseZIGaP iteration on this rank's row block (reference order sparse_zigap.py:118-196): the device path
+    reduces red32 = [R^T eU | D_hat^T U_hat | R^T (eU log U)] and red64 = [colsum p_d | sum log U_hat | sum U_hat];
+    the S update, pi_s and the V' side are recomputed on every rank from the reduced sums."""
+    from oracle import cavi_numpy as cn, sparse_numpy as sn
+    dt = np.float32
+    e = sn.expectations(s)
+    X = s['X'].astype(dt); D = e['D_hat'].astype(dt); S_hat = e['S_hat'].astype(dt)
+    lU = e['log_U_hat'].astype(dt); lV = e['log_Vprime_hat'].astype(dt)
+    eU = cn.centred_exp(lU, dt)
+    eV = cn.centred_exp(lV, dt) * (s['p_s'] > tau).astype(dt)
+    den = eU @ eV.T
+    R = X * D / np.where(den > 0, den, dt(1))
+    V_eff = S_hat * e['Vprime_hat']
+    s['a1'] = cn.clamp(s['alpha1'][None, :] + (R @ (eV * S_hat)) * eU)              # row side: local
+    s['a2'] = cn.clamp(s['alpha2'] + e['D_hat'] @ V_eff)
+    U_hat = cn.gamma_mean(s['a1'], s['a2'])
+    red32 = torch.as_tensor(np.stack([(R.T @ eU).astype(np.float64), np.asarray(e['D_hat'].T @ U_hat, dtype=np.float64),
+                                      (R.T @ (eU * lU)).astype(np.float64)]))
+    shard.allreduce_sum(red32)                                                       # allreduce #1 (three blocks)
+    RtU, DtU, Zl = (red32[i].numpy() for i in range(3))
+    DZ = (RtU.astype(dt) * eV); DZl = ((Zl.astype(dt) + lV * RtU.astype(dt)) * eV)
+    s['b1'] = cn.clamp(s['beta1'][None, :] + S_hat * DZ)
+    s['b2'] = cn.clamp(s['beta2'] + S_hat * DtU)
+    Vp = cn.gamma_mean(s['b1'], s['b2'])
+    pi_s = s['pi_s']
+    p_s = np.nan_to_num(cn.sigmoid(cn.logit(pi_s)[:, None] - (-DZl + np.nan_to_num(DtU * Vp))))
+    p_s[pi_s <= 0] = 1e-10; p_s[pi_s >= 1] = 1. - 1e-10
+    s['p_s'] = p_s
+    pi = s['pi_d']
+    p_d = cn.sigmoid(cn.logit(pi)[None, :] - U_hat @ V_eff.T)                        # OLD effective V_hat, NEW U_hat
+    p_d[:, pi <= 0] = 1e-10; p_d[:, pi >= 1] = 1. - 1e-10; p_d[s['X'] != 0] = 1. - 1e-10
+    s['p_d'] = p_d
+    e = sn.expectations(s)
+    p, K = s['b1'].shape
+    red64 = torch.as_tensor(np.concatenate([p_d.sum(axis=0), e['log_U_hat'].astype(np.float64).sum(axis=0),
+                                            e['U_hat'].sum(axis=0)]))
+    shard.allreduce_sum(red64)                                                       # allreduce #2
+    r = red64.numpy()
+    s['alpha1'] = cn.clamp(cn.inverse_digamma(np.log(s['alpha2']) + r[p:p + K] / n_total))
+    s['alpha2'] = cn.clamp(s['alpha1'] / (r[p + K:p + 2 * K] / n_total))
+    s['beta1'] = cn.clamp(cn.inverse_digamma(np.log(s['beta2']) + np.mean(e['log_Vprime_hat'], axis=0)))
+    s['beta2'] = cn.clamp(s['beta1'] / np.mean(e['Vprime_hat'], axis=0))
+    s['pi_d'] = r[:p] / n_total
+    s['pi_s'] = np.mean(s['p_s'], axis=1)
+    return s
+
+
+def _sparse_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import warnings
+        from oracle import cavi_numpy as cn, sparse_numpy as sn
+        from oriana_b200.sharding import RowSharding
+        n, p, K = 61, 40, 3
+        X = cn.synth_counts(n, p, K, seed=11)
+        full = sn.init_state(X, K, np.random.default_rng(5))
+        shard = RowSharding(enabled=True)
+        r0, r1 = RowSharding.row_block(n, rank, world)
+        mine = {k: (v[r0:r1].copy() if k in ('X', 'a1', 'a2', 'p_d') else v.copy()) for k, v in full.items()}
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            for _ in range(3):
+                sn.step(full, tau=0.5)
+                sharded_sparse_step(mine, shard, n, 0.5)
+        err = {}
+        for k in ('a1', 'a2'):
+            err[k] = float(np.max(np.abs(mine[k] - full[k][r0:r1]) / (np.abs(full[k][r0:r1]) + 1e-9)))
+        for k in ('b1', 'b2', 'alpha1', 'alpha2', 'beta1', 'beta2', 'pi_d', 'pi_s'):
+            err[k] = float(np.max(np.abs(mine[k] - full[k]) / (np.abs(full[k]) + 1e-9)))
+        err['p_s'] = float(np.max(np.abs(mine['p_s'] - full['p_s']) / (np.abs(full['p_s']) + 1e-6)))
+        out[rank] = err
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_row_sharding_of_the_sparse_model():
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_sparse_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        assert sorted(out.keys()) == [0, 1]
+        for rank in (0, 1):
+            for k, e in out[rank].items():
+                assert e < (2e-3 if k in ('p_s', 'pi_s') else 2e-5), (rank, k, e)   # the S-step amplifies summation order
+
+
 def _worker(rank, world, port, model, quirk, out):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)

@@ -458,7 +458,8 @@ k_mstep(ori_problem_t P, int mode)
                 e -= P.scal[6];  // sum_k (sum_i U_hat_ik)(sum_j V_hat_jk) of the swept state
             }
             P.scal[SC_ELBO_LAST] = e;
-            if (P.iter >= 0 && P.iter < P.trace_cap) P.elbo_trace[P.iter] = e;
+            const int it = (P.flags & ORI_F_DEVICE_ITER) ? (int)P.scal[SC_ITER] : P.iter;
+            if (it >= 0 && it < P.trace_cap) P.elbo_trace[it] = e;
         }
         __syncthreads();
         if (mode == ORI_M_FINALIZE) return;
@@ -498,7 +499,8 @@ k_mstep(ori_problem_t P, int mode)
     if (tid == 0) {
         P.scal[SC_PENDING] = ps + part[R64_HROW] + gpart[0];
         P.scal[6] = us;
-        P.scal[SC_ITER] = (double)(mode == ORI_M_STEP ? P.iter + 1 : P.iter);
+        const int it = (P.flags & ORI_F_DEVICE_ITER) ? (int)P.scal[SC_ITER] : P.iter;
+        P.scal[SC_ITER] = (double)(mode == ORI_M_STEP ? it + 1 : it);
     }
 }
 

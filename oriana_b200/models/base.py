@@ -78,7 +78,7 @@ class FactorModel(metaclass=ABCMeta):
     _sparse = False      # SparseZIGaP sets this
 
     def __init__(self, cmatrix, k=2, use_factors=True, *, state=None, compat_quirk=False, sharded=False,
-                 process_group=None, elbo=True, trace_cap=4096, force_simt=False, tensor=None, nmf=None):
+                 process_group=None, elbo=True, trace_cap=4096, force_simt=False, tensor=None, nmf=None, graphs=False):
         self._dev = _lib.require_cuda()
         self._lib = _lib.load()
         _lib.check(self._lib.ori_device_check(self._dev.index or 0))
@@ -104,7 +104,11 @@ class FactorModel(metaclass=ABCMeta):
         self.n_total = self._shard.total_rows(self.n, self._dev)
         self._flags = (_lib.ORI_F_DROPOUT if self._dropout else 0) | (_lib.ORI_F_ELBO if elbo else 0) \
             | (_lib.ORI_F_QUIRK if (compat_quirk and self._dropout) else 0) \
-            | (_lib.ORI_F_NO_TENSOR if force_simt else 0) | (_lib.ORI_F_SPARSE if self._sparse else 0)
+            | (_lib.ORI_F_NO_TENSOR if force_simt else 0) | (_lib.ORI_F_SPARSE if self._sparse else 0) \
+            | (_lib.ORI_F_DEVICE_ITER if graphs else 0)
+        # graphs=True: step() replays one captured CUDA graph per generation parity (every launch of the iteration,
+        # the memsets and, when sharded, the two NCCL all-reduces) instead of ~15 separate launches
+        self._graphs = {} if graphs else None
         self.compat_quirk = bool(compat_quirk and self._dropout)
         self._trace_cap = int(trace_cap)
         if nmf not in (None, 'host', 'device'):
@@ -315,8 +319,52 @@ class FactorModel(metaclass=ABCMeta):
 
     def step(self):
         """One CAVI iteration (base.py:54-56)."""
+        if self._graphs is not None and self._timers is None and not self._dirty:
+            return self._step_graph()
         self.update_variational_parameters()   # E-step
         self.update_prior_hyper_parameters()   # M-step
+
+    def _step_graph(self):
+        """step() as the replay of a CUDA graph.  Two graphs are captured lazily, one per parity of the row-factor
+        generation (the kernels receive the ping-pong index as an argument); the iteration count lives on the device
+        (ORI_F_DEVICE_ITER).  The first step of each parity runs eagerly once (lazy one-time initialisation inside the
+        library must not happen under capture)."""
+        if self._iter + 1 >= self._trace_cap:
+            raise RuntimeError('elbo trace capacity %d exhausted; build the model with a larger trace_cap'
+                               % self._trace_cap)
+        key = self._gen
+        g = self._graphs.get(key)
+        if g is None:
+            self._graphs[key] = 'warm'                    # this parity has now run eagerly once
+            self.update_variational_parameters()
+            self.update_prior_hyper_parameters()
+            return
+        if g == 'warm':
+            self._scal[5] = float(self._iter)             # SC_ITER: the device-side count the captured kernels read
+            torch.cuda.synchronize()
+            before = int(self._lib.ori_kernel_launches())
+            g = torch.cuda.CUDAGraph()
+            gen0, it0 = self._gen, self._iter
+            with torch.cuda.graph(g):
+                self.update_variational_parameters()
+                self.update_prior_hyper_parameters()
+            self._gen, self._iter = gen0, it0             # capture executed nothing: undo the host-side bookkeeping
+            self._graphs[key] = g
+            self._graph_kernels = int(self._lib.ori_kernel_launches()) - before
+            self.graph_replays = getattr(self, 'graph_replays', 0)
+        g.replay()
+        self.graph_replays += 1
+        self._pending_mstep = False
+        self._gen ^= 1
+        self._iter += 1
+        self._pi_stale = self._dropout
+        self._D_cache = None
+
+    @property
+    def graph_kernel_launches(self):
+        """Kernels of this library launched through graph replays so far (ori_kernel_launches() counts launch calls,
+        i.e. a captured step only once)."""
+        return getattr(self, 'graph_replays', 0) * getattr(self, '_graph_kernels', 0)
 
     def update_variational_parameters(self):
         """E-step (zigap.py:97-141 / gap.py:82-115)."""

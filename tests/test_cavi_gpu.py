@@ -380,3 +380,43 @@ def test_nmf_initialised_trajectory_matches_reference(cuda_lib, tensor):
                 assert relerr(getattr(m, k).asarray(), r[k]) < htol, (t, k)
             assert np.max(np.abs(m.D_hat - r['p_d'])) < dtol, t
     assert np.isfinite(m.elbo_trace).all()
+
+
+@pytest.mark.parametrize('case', ['zigap_simt', 'gap_simt', 'zigap_tensor', 'sparse'])
+def test_graph_replayed_steps_match_eager_steps(cuda_lib, case):
+    """`graphs=True`: step() replays a captured CUDA graph (one per generation parity, iteration count on the device).
+    Same states and the same ELBO trace as separate launches, up to the order of the float atomics."""
+    from oracle import cavi_numpy as cn, sparse_numpy as sn
+    from oriana.models import GaP, SparseZIGaP, ZIGaP
+    from oriana.singlecell import CountMatrix
+    if case == 'sparse':
+        X = cn.synth_counts(300, 260, 5, seed=4)
+        s = sn.init_state(X, 5, np.random.default_rng(1))
+        mk = lambda **kw: SparseZIGaP(CountMatrix(X), k=5, use_factors=False, state={k: np.array(v) for k, v in s.items()}, **kw)
+        keys = ('a1', 'a2', 'b1', 'b2', 'p_s', 'pi_s', 'pi_d', 'alpha1', 'beta2')
+    else:
+        n, p, K = (4000, 1800, 12) if case == 'zigap_tensor' else (300, 260, 5)
+        X = cn.synth_counts(n, p, K, seed=4)
+        kind = 'gap' if case.startswith('gap') else 'zigap'
+        s = cn.init_state(X, K, np.random.default_rng(1), kind)
+        cls = GaP if kind == 'gap' else ZIGaP
+        mk = lambda **kw: cls(CountMatrix(X), k=K, use_factors=False, state={k: np.array(v) for k, v in s.items()},
+                              tensor=(case == 'zigap_tensor'), **kw)
+        keys = ('a1', 'a2', 'b1', 'b2', 'alpha1', 'beta2') + (('pi_d',) if kind == 'zigap' else ())
+    me, mg = mk(), mk(graphs=True)
+    for _ in range(7):
+        me.step(); mg.step()
+    assert mg.graph_replays == 5 and mg.graph_kernel_launches > 0 and mg.iterations == me.iterations == 7
+    tol = 2e-3 if case == 'sparse' else (5e-4 if case == 'zigap_tensor' else 1e-5)
+    for k in keys:
+        assert relerr(getattr(mg, k).asarray(), getattr(me, k).asarray()) < tol, (case, k)
+    if case != 'sparse':
+        te, tg = me.elbo_trace, mg.elbo_trace
+        assert te.shape == tg.shape == (8,) and np.max(np.abs(te - tg) / np.abs(te)) < 1e-5
+    else:
+        assert abs(mg.reconstruction_deviance() - me.reconstruction_deviance()) <= 1e-5 * abs(me.reconstruction_deviance())
+    # an edit of the parameters falls back to eager launches for that step and the graphs stay valid afterwards
+    mg.a1[:] = mg.a1.asarray(); me.a1[:] = me.a1.asarray()
+    for _ in range(2):
+        me.step(); mg.step()
+    assert relerr(mg.b1.asarray(), me.b1.asarray()) < tol

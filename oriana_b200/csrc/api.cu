@@ -206,7 +206,11 @@ static int pass_genes_any(const ori_problem_t* P, int gen_old, cudaStream_t st) 
     if (P->flags & ORI_F_QUIRK) ORI_TRY(launch_quirk_weights(P, gen_old, st));
     if (!tc_eligible(P)) return launch_pass_genes_simt(P, gen_old, st);
     ORI_TRY(launch_tc_prep_rows(P, gen_old, st));
-    return launch_pass_genes_tc(P, gen_old, st);
+    ORI_TRY(launch_pass_genes_tc(P, gen_old, st));
+    if (!(P->flags & ORI_F_SPARSE)) return ORI_OK;
+    // sparse model: second, dropout-free sweep for sum_i R_ij eU_ik E[log U_ik] (sparse_zigap.py:116)
+    ORI_TRY(launch_tc_prep_rows_logsum(P, gen_old, st));
+    return launch_pass_genes_logsum_tc(P, gen_old, st);
 }
 
 int64_t ori_tc_workspace_floats(int64_t n_rows, int32_t p, int32_t KP) { return tc_workspace_floats(n_rows, p, KP); }

@@ -53,5 +53,7 @@ int launch_tc_prep_genes(const ori_problem_t* P, cudaStream_t st);
 int launch_tc_prep_rows(const ori_problem_t* P, int gen_old, cudaStream_t st);
 int launch_pass_rows_tc(const ori_problem_t* P, int gen_old, cudaStream_t st);
 int launch_pass_genes_tc(const ori_problem_t* P, int gen_old, cudaStream_t st);
+int launch_tc_prep_rows_logsum(const ori_problem_t* P, int gen_old, cudaStream_t st);
+int launch_pass_genes_logsum_tc(const ori_problem_t* P, int gen_old, cudaStream_t st);
 
 }  // namespace ori

@@ -806,7 +806,8 @@ static TcWs tc_carve(const ori_problem_t* P) {
 }
 
 bool tc_eligible(const ori_problem_t* P) {
-    return P->tc_ws != nullptr && (P->KP == 32 || P->KP == 64) && !(P->flags & (ORI_F_NO_TENSOR | ORI_F_SPARSE)) && P->n_rows > 0 &&
+    if ((P->flags & ORI_F_SPARSE) && P->KP != 32) return false;
+    return P->tc_ws != nullptr && (P->KP == 32 || P->KP == 64) && !(P->flags & ORI_F_NO_TENSOR) && P->n_rows > 0 &&
            P->tc_ws_floats >= tc_workspace_floats(P->n_rows, P->p, P->KP) && get_encode_fn() != nullptr;
 }
 
@@ -819,11 +820,16 @@ static int num_sms() {
 // gene-side operands (+ padded logit(pi)): the sweep side of the row pass; run once per iteration before it
 int launch_tc_prep_genes(const ori_problem_t* P, cudaStream_t st) {
     const TcWs w = tc_carve(P);
-    const bool drop = P->flags & ORI_F_DROPOUT;
+    const bool drop = P->flags & ORI_F_DROPOUT, sparse = P->flags & ORI_F_SPARSE;
     const int KP = P->KP;
     const dim3 tg(cdiv(w.pp, 32), KP / 32);
-    k_tc_prep_K<<<cdiv(w.pp * KP, 256), 256, 0, st>>>(P->eV, drop ? P->V_hat : nullptr, LOG2E, w.geneK, P->p, w.pp, KP);
-    k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(P->eV, w.geneT, P->p, w.pp, KP);
+    // sparse model (sparse_zigap.py:100-116, :140-142, :166): the denominator operand carries the mask, the row sums
+    // contract with eVz, D_hat is rebuilt from the PREVIOUS effective V_hat, the rate sums contract with the current one
+    const float* e_den = sparse ? P->eVd : P->eV;
+    const float* e_acc = sparse ? P->eVz : P->eV;
+    const float* E_uv = sparse ? P->Vh_old : P->V_hat;
+    k_tc_prep_K<<<cdiv(w.pp * KP, 256), 256, 0, st>>>(e_den, drop ? E_uv : nullptr, LOG2E, w.geneK, P->p, w.pp, KP);
+    k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(e_acc, w.geneT, P->p, w.pp, KP);
     cudaMemsetAsync(w.flags, 0, 32 * sizeof(int), st);
     if (drop) {
         k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(P->V_hat, w.geneT + (long long)KP * w.pp, P->p, w.pp, KP);
@@ -844,6 +850,14 @@ int launch_tc_prep_rows(const ori_problem_t* P, int g, cudaStream_t st) {
     k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(wsrc, w.rowT, P->n_rows, w.np, KP);
     if (drop) k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(P->U_hat[1 - g], w.rowT + (long long)KP * w.np, P->n_rows, w.np, KP);
     return check_launch("k_tc_prep(rows)", drop ? 3 : 2);
+}
+
+// sparse model, third gene-side sum (sparse_zigap.py:116): the transposed operand of accumulator 1 becomes eU * E[log U]
+int launch_tc_prep_rows_logsum(const ori_problem_t* P, int g, cudaStream_t st) {
+    const TcWs w = tc_carve(P);
+    const dim3 tg(cdiv(w.np, 32), P->KP / 32);
+    k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(P->eUl[g], w.rowT, P->n_rows, w.np, P->KP);
+    return check_launch("k_tc_prep(rows, logsum)");
 }
 
 static int env_int(const char* name, int dflt) {
@@ -897,11 +911,13 @@ static int launch_tc_variant(const TcMaps& maps, const TcArgs& a, int grid, cuda
     return ORI_OK;
 }
 
+// logsum: the dropout-free sweep of the sparse model's third gene-side sum into red32 block 2
 template <bool GENES, bool PAIR, int KP>
-static int launch_tc_pass_p(const ori_problem_t* P, int gen_old, cudaStream_t st) {
+static int launch_tc_pass_p(const ori_problem_t* P, int gen_old, cudaStream_t st, bool logsum = false) {
     using C = Cfg<KP, PAIR>;
     const TcWs w = tc_carve(P);
-    const bool drop = P->flags & ORI_F_DROPOUT, elbo = P->flags & ORI_F_ELBO;
+    const bool sparse = P->flags & ORI_F_SPARSE;
+    const bool drop = (P->flags & ORI_F_DROPOUT) && !logsum, elbo = (P->flags & ORI_F_ELBO) && !logsum;
     constexpr int NCTA = C::NCTA, SW = C::SW;
     TcMaps maps;
     TcArgs a;
@@ -920,8 +936,8 @@ static int launch_tc_pass_p(const ori_problem_t* P, int gen_old, cudaStream_t st
              make_tmap_f32(&maps.swT, w.rowT, 2 * KP, w.np, w.np, 32, KP / NCTA) &&
              make_tmap_f32(&maps.X, P->X, P->n_rows, P->p, P->ldx, 32, SW);
         a.own_total = P->p; a.sw_total = P->n_rows; a.sw_pad = w.np;
-        a.own_e = P->eV; a.own_E = P->V_hat;
-        a.acc1 = P->red32; a.acc2 = P->red32 + (long long)P->p * KP;
+        a.own_e = sparse ? P->eVd : P->eV; a.own_E = sparse ? P->Vh_old : P->V_hat;
+        a.acc1 = P->red32 + (logsum ? 2ll * P->p * KP : 0ll); a.acc2 = P->red32 + (long long)P->p * KP;
     }
     if (!ok) return set_error(ORI_ECUDA, "cuTensorMapEncodeTiled failed");
     a.lp2w = w.lp2w; a.flw = w.flw; a.cw = w.cw; a.any_floor = w.flags;
@@ -942,16 +958,17 @@ static int launch_tc_pass_p(const ori_problem_t* P, int gen_old, cudaStream_t st
 }
 
 template <bool GENES>
-static int launch_tc_pass(const ori_problem_t* P, int gen_old, cudaStream_t st) {
+static int launch_tc_pass(const ori_problem_t* P, int gen_old, cudaStream_t st, bool logsum = false) {
 #if ORI_TC_NEW == 8
-    if (P->KP == 64) return launch_tc_pass_p<GENES, true, 64>(P, gen_old, st);
+    if (P->KP == 64) return launch_tc_pass_p<GENES, true, 64>(P, gen_old, st, logsum);
 #else
     if (P->KP == 64) return set_error(ORI_EUNSUPPORTED, "this build (ORI_TC_NEW != 8) has no KP = 64 plan");
 #endif
-    return use_pair() ? launch_tc_pass_p<GENES, true, 32>(P, gen_old, st) : launch_tc_pass_p<GENES, false, 32>(P, gen_old, st);
+    return use_pair() ? launch_tc_pass_p<GENES, true, 32>(P, gen_old, st, logsum) : launch_tc_pass_p<GENES, false, 32>(P, gen_old, st, logsum);
 }
 
 int launch_pass_rows_tc(const ori_problem_t* P, int gen_old, cudaStream_t st) { return launch_tc_pass<false>(P, gen_old, st); }
 int launch_pass_genes_tc(const ori_problem_t* P, int gen_old, cudaStream_t st) { return launch_tc_pass<true>(P, gen_old, st); }
+int launch_pass_genes_logsum_tc(const ori_problem_t* P, int gen_old, cudaStream_t st) { return launch_tc_pass<true>(P, gen_old, st, true); }
 
 }  // namespace ori

@@ -7,7 +7,7 @@ import numpy as np, torch
 from oriana.models import SparseZIGaP
 from oriana.singlecell import synth_counts_device
 
-for (n, p, K) in [(10_000, 2_000, 10), (100_000, 20_000, 20)]:
+for (n, p, K) in [(10_000, 2_000, 10), (100_000, 20_000, 20), (250_000, 20_000, 32)]:
     X = synth_counts_device(n, p, K, seed=1)
     np.random.seed(0)
     m = SparseZIGaP(X[:, :p], k=K, use_factors=False)
@@ -36,5 +36,22 @@ for (n, p, K) in [(10_000, 2_000, 10), (100_000, 20_000, 20)]:
             t0 = time.perf_counter(); sn.step(s); t1 = time.perf_counter()
         print('  numpy oracle step at the same size: %.2f s = %.3g entries/s (%d host threads)'
               % (t1 - t0, n * p / (t1 - t0), os.cpu_count()), flush=True)
-    del m, X
+    # the opt-in tensor path: time, and agreement with the CUDA-core path after 3 steps from the same state
+    np.random.seed(0)
+    ma = SparseZIGaP(X[:, :p], k=K, use_factors=False)
+    st = ma.state_dict(); st['X'] = X[:, :p]
+    mt = SparseZIGaP(X[:, :p], k=K, use_factors=False, state=st, tensor=True)
+    mb = SparseZIGaP(X[:, :p], k=K, use_factors=False, state=st)
+    for _ in range(3): mt.step(); mb.step()
+    ps_t, ps_s = mt.p_s.asarray(), mb.p_s.asarray()
+    rel = lambda a, b: float(np.max(np.abs(a - b) / (np.abs(b) + 1e-6 * np.abs(b).max())))
+    print('  tensor vs CUDA-core after 3 steps: a1 %.1e b1(median) %.1e pi_d %.1e | masks differ %.2e, |dp_s|>0.05: %.2e'
+          % (rel(mt.a1.asarray(), mb.a1.asarray()), float(np.median(np.abs(mt.b1.asarray() - mb.b1.asarray()) / (np.abs(mb.b1.asarray()) + 1e-12))),
+             rel(mt.pi_d.asarray(), mb.pi_d.asarray()), np.mean((ps_t > 0.5) != (ps_s > 0.5)), np.mean(np.abs(ps_t - ps_s) > 0.05)), flush=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(steps): mt.step()
+    e1.record(); torch.cuda.synchronize()
+    mst = e0.elapsed_time(e1) / steps
+    print('  tensor path: %.2f ms/step = %.3g entries/s (%.1fx)' % (mst, n * p / mst * 1e3, ms / mst), flush=True)
+    del m, ma, mt, mb, X
     torch.cuda.empty_cache()

@@ -108,3 +108,31 @@ def test_sparse_constructor_path_and_snapshot(cuda_lib):
         assert relerr(getattr(m2, k).asarray(), getattr(m, k).asarray()) < 1e-5, k
     with pytest.raises(ValueError):
         SparseZIGaP(CountMatrix(X), k=40, use_factors=False)
+
+
+def test_sparse_tensor_path_tracks_the_cuda_core_path(cuda_lib):
+    """`tensor=True` (opt-in): the tcgen05 kernels with the masked operands and a second gene sweep for the third sum.
+    Not bit-comparable with the fp32 path (the S update amplifies the TF32 rounding of the gene-side sums), so the
+    check is statistical: factors and priors close, masks S_tilde almost everywhere equal, same deviance."""
+    from oriana.models import SparseZIGaP
+    from oriana.singlecell import synth_counts_device
+    n, p, K = 20_000, 3_000, 8
+    X = synth_counts_device(n, p, K, seed=9)
+    np.random.seed(3)
+    m0 = SparseZIGaP(X[:, :p], k=K, use_factors=False)
+    st = m0.state_dict(); st['X'] = X[:, :p]
+    ms = SparseZIGaP(X[:, :p], k=K, use_factors=False, state=st)
+    mt = SparseZIGaP(X[:, :p], k=K, use_factors=False, state=st, tensor=True)
+    assert mt.uses_tensor_path and not ms.uses_tensor_path
+    for _ in range(3):
+        ms.step(); mt.step()
+    for k in ('a1', 'a2', 'alpha1', 'alpha2', 'beta1', 'beta2', 'pi_d'):
+        assert relerr(getattr(mt, k).asarray(), getattr(ms, k).asarray()) < 5e-3, k
+    ps_s, ps_t = ms.p_s.asarray(), mt.p_s.asarray()
+    assert np.mean((ps_s > 0.5) != (ps_t > 0.5)) < 5e-3
+    assert np.mean(np.abs(ps_s - ps_t) > 0.05) < 2e-2
+    same = (ps_s > 0.5) == (ps_t > 0.5)
+    b1s, b1t = ms.b1.asarray(), mt.b1.asarray()
+    assert np.median(np.abs(b1t - b1s)[same] / (np.abs(b1s)[same] + 1e-12)) < 1e-3
+    ds, dt = ms.reconstruction_deviance(int_quirk=False), mt.reconstruction_deviance(int_quirk=False)
+    assert abs(dt - ds) <= 5e-3 * abs(ds) or not np.isfinite(ds)

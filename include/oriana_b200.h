@@ -191,7 +191,8 @@ int ori_column_sums_f64(const float* X, int64_t ldx, int64_t n_rows, int32_t p, 
  * :68), rate = column means of X (:76; col_mean [p] float64, all ranks).  pi [p] float64 = the finalised pi_d.
  * out_int[3]: every entry's term truncated toward zero to int64 before a wrapping sum, exactly what the
  * reference's integer output buffer does (sparse_zigap.py:45; -inf / NaN become INT64_MIN); out_f64[3]: the
- * plain float64 sums.  Both are ACCUMULATED into (caller zero-fills). */
+ * plain float64 sums, or NULL (then zero entries of genes with 1 - pi >= 1/e, whose terms all truncate to 0, are
+ * skipped).  Both are ACCUMULATED into (caller zero-fills). */
 int ori_deviance_sums(const ori_problem_t* P, int gen, const double* pi, const double* col_mean,
                       long long* out_int, double* out_f64, void* stream);
 

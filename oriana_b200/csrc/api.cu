@@ -322,7 +322,7 @@ int ori_deviance_sums(const ori_problem_t* P, int gen, const double* pi, const d
                       long long* out_int, double* out_f64, void* stream) {
     ORI_TRY(ori_problem_check(P));
     if (!(P->flags & ORI_F_DROPOUT)) return set_error(ORI_EINVAL, "the deviance metrics need the dropout layer (sparse_zigap.py:44-51)");
-    if (!pi || !col_mean || !out_int || !out_f64 || gen < 0 || gen > 1) return set_error(ORI_EINVAL, "ori_deviance_sums: bad argument");
+    if (!pi || !col_mean || !out_int || gen < 0 || gen > 1) return set_error(ORI_EINVAL, "ori_deviance_sums: bad argument");
     if (P->n_rows == 0) return ORI_OK;
     return launch_deviance(P, gen, pi, col_mean, out_int, out_f64, (cudaStream_t)stream);
 }

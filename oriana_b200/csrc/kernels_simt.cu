@@ -698,13 +698,14 @@ k_deviance(const float* __restrict__ X, long long ldx, long long n_rows, int p,
            const double* __restrict__ pi, const double* __restrict__ cmean,
            unsigned long long* __restrict__ out_int, double* __restrict__ out_f64)
 {
+    const bool want_f64 = out_f64 != nullptr;
     __shared__ float sX[PR_TR][PR_TG + 1];
     // the rate is accumulated in float64 from V' = b1 / b2 and S_hat: the reference's float64 product (base.py:63-66)
     // stays positive where a float32 S_hat * V'_hat underflows, and log(0) would turn the metric into INT64_MIN
     __shared__ __align__(16) double sVc[PR_TG][KP];
     __shared__ __align__(16) float sVo[PR_TG][KP];
     __shared__ float slp[PR_TG], sfl[PR_TG];
-    __shared__ double spi[PR_TG], scm[PR_TG];
+    __shared__ double spi[PR_TG], scm[PR_TG], slpi[PR_TG], slcm[PR_TG];
     __shared__ double sred[PR_TR / 32];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -744,39 +745,51 @@ k_deviance(const float* __restrict__ X, long long ldx, long long n_rows, int p,
             sfl[tid] = ok ? pfloor[j0 + tid] : 0.f;
             spi[tid] = ok ? pi[j0 + tid] : 0.5;
             scm[tid] = ok ? cmean[j0 + tid] : 0.0;
+            slpi[tid] = log(spi[tid]);                            // per-gene logarithms of the non-zero branch
+            slcm[tid] = log(scm[tid]);
         }
         __syncthreads();
         if (!row_ok) continue;
         for (int g = 0; g < gcount; ++g) {
             const float x = sX[tid][g];
-            double lam = 0.0;
-            float uv = 0.f;
-            const double2* c2 = reinterpret_cast<const double2*>(&sVc[g][0]);
-            const float4* o4 = reinterpret_cast<const float4*>(&sVo[g][0]);
-#pragma unroll
-            for (int q = 0; q < KP / 4; ++q) {
-                const double2 ca = c2[2 * q], cb = c2[2 * q + 1];
-                const float4 o = o4[q];
-                lam = fma((double)uh[4 * q + 0], ca.x, lam); lam = fma((double)uh[4 * q + 1], ca.y, lam);
-                lam = fma((double)uh[4 * q + 2], cb.x, lam); lam = fma((double)uh[4 * q + 3], cb.y, lam);
-                uv = fmaf(uh[4 * q + 0], o.x, uv); uv = fmaf(uh[4 * q + 1], o.y, uv);
-                uv = fmaf(uh[4 * q + 2], o.z, uv); uv = fmaf(uh[4 * q + 3], o.w, uv);
-            }
             const bool nz = x != 0.f;
-            float D = 1.f;
-            if (!nz) { float e, ex; D = dropout_p(uv, slp[g], sfl[g], e, ex); }
-            const double L = (D > 0.5f) ? lam : 0.0;               // base.py:67: UV[round(D_hat) == 0] = 0
             const double pj = spi[g], cm = scm[g], xd = (double)x;
+            // integer-only mode: a zero entry's terms lie in (log(1 - pi_j), 0], so they all truncate to 0 when
+            // 1 - pi_j >= 1/e -- no work at all for those genes' zeros
+            if (!nz && !want_f64 && (1.0 - pj) >= 0.36787944117144233) continue;
+            float D = 1.f;
+            if (!nz) {                                            // D_hat only matters on zeros (zigap.py:135-136)
+                float uv = 0.f;
+                const float4* o4 = reinterpret_cast<const float4*>(&sVo[g][0]);
+#pragma unroll
+                for (int q = 0; q < KP / 4; ++q) {
+                    const float4 o = o4[q];
+                    uv = fmaf(uh[4 * q + 0], o.x, uv); uv = fmaf(uh[4 * q + 1], o.y, uv);
+                    uv = fmaf(uh[4 * q + 2], o.z, uv); uv = fmaf(uh[4 * q + 3], o.w, uv);
+                }
+                float e, ex;
+                D = dropout_p(uv, slp[g], sfl[g], e, ex);
+            }
+            double L = 0.0;                                       // base.py:67: UV[round(D_hat) == 0] = 0
+            if (D > 0.5f) {
+                const double2* c2 = reinterpret_cast<const double2*>(&sVc[g][0]);
+#pragma unroll
+                for (int q = 0; q < KP / 4; ++q) {
+                    const double2 ca = c2[2 * q], cb = c2[2 * q + 1];
+                    L = fma((double)uh[4 * q + 0], ca.x, L); L = fma((double)uh[4 * q + 1], ca.y, L);
+                    L = fma((double)uh[4 * q + 2], cb.x, L); L = fma((double)uh[4 * q + 3], cb.y, L);
+                }
+            }
             double l_uv, l_sat, l_mean;
             if (!nz) {                                            // sparse_zigap.py:49
                 l_uv = log(pj * exp(-L) + (1.0 - pj));
                 l_sat = log(pj + (1.0 - pj));
                 l_mean = log(pj * exp(-cm) + (1.0 - pj));
             } else {                                              // sparse_zigap.py:50
-                const double lpi = log(pj);
+                const double lpi = slpi[g];
                 l_uv = lpi - L + xd * log(L);
                 l_sat = lpi - xd + xd * log(xd);
-                l_mean = lpi - cm + xd * log(cm);
+                l_mean = lpi - cm + xd * slcm[g];
             }
             ti[0] += (unsigned long long)trunc_like_numpy(l_uv);
             ti[1] += (unsigned long long)trunc_like_numpy(l_sat);
@@ -790,7 +803,7 @@ k_deviance(const float* __restrict__ X, long long ldx, long long n_rows, int p,
         for (int o = 16; o > 0; o >>= 1) ti[c] += __shfl_xor_sync(0xffffffffu, ti[c], o);
         if (lane == 0 && ti[c]) atomicAdd(out_int + c, ti[c]);
         const double r = block_reduce_sum(tf[c], sred);
-        if (tid == 0) atomicAdd(out_f64 + c, r);
+        if (tid == 0 && want_f64) atomicAdd(out_f64 + c, r);
     }
 }
 

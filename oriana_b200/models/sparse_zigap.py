@@ -129,7 +129,7 @@ class SparseZIGaP(ZIGaP):
             self._Vh_old[:, :self.k] = torch.as_tensor(np.asarray(state['V_eff_prev']), device=self._dev).to(torch.float32)
 
     # -- the reference's convergence metrics (base.py:58-82, sparse_zigap.py:44-51) ------------------------
-    def _loglikelihood_sums(self):
+    def _loglikelihood_sums(self, want_f64=True):
         """(int64-truncated, float64) sums of the zero-inflated Poisson log-likelihood at the three rates:
         masked U_hat V_hat^T, X itself, column means of X."""
         if self._dirty:
@@ -145,7 +145,7 @@ class SparseZIGaP(ZIGaP):
         out_i = torch.zeros((3,), dtype=torch.int64, device=dev)
         out_f = torch.zeros((3,), dtype=torch.float64, device=dev)
         self._call('ori_deviance_sums', self._gen, pi.data_ptr(), self._col_mean.data_ptr(), out_i.data_ptr(),
-                   out_f.data_ptr())
+                   out_f.data_ptr() if want_f64 else None)
         self._shard.allreduce_sum(out_i)
         self._shard.allreduce_sum(out_f)
         return out_i.cpu().numpy(), out_f.cpu().numpy()
@@ -153,12 +153,12 @@ class SparseZIGaP(ZIGaP):
     def reconstruction_deviance(self, int_quirk=True):
         """base.py:58-69.  `int_quirk=True` reproduces the reference's integer log-likelihood buffer
         (sparse_zigap.py:45: every entry truncated toward zero before the sum); False gives the float64 sum."""
-        li, lf = self._loglikelihood_sums()
+        li, lf = self._loglikelihood_sums(want_f64=not int_quirk)
         ll = li.astype(np.float64) if int_quirk else lf
         return float(-2. * (ll[0] - ll[1]))
 
     def explained_deviance(self, int_quirk=True):
         """base.py:71-82 (with the rate mask of the current state, i.e. right after reconstruction_deviance())."""
-        li, lf = self._loglikelihood_sums()
+        li, lf = self._loglikelihood_sums(want_f64=not int_quirk)
         ll = li.astype(np.float64) if int_quirk else lf
         return float((ll[0] - ll[2]) / (ll[1] - ll[2]))

@@ -106,8 +106,11 @@ class FactorModel(metaclass=ABCMeta):
             | (_lib.ORI_F_QUIRK if (compat_quirk and self._dropout) else 0) \
             | (_lib.ORI_F_NO_TENSOR if force_simt else 0) | (_lib.ORI_F_SPARSE if self._sparse else 0) \
             | (_lib.ORI_F_DEVICE_ITER if graphs else 0)
-        # graphs=True: step() replays one captured CUDA graph per generation parity (every launch of the iteration,
-        # the memsets and, when sharded, the two NCCL all-reduces) instead of ~15 separate launches
+        # graphs=True: step() replays one captured CUDA graph per generation parity (every launch of the iteration and
+        # the memsets) instead of ~15 separate launches; single rank only
+        if graphs and (sharded or process_group is not None):
+            raise ValueError('graphs=True is a single-rank feature: capturing the NCCL all-reduces of a sharded step '
+                             'is not supported')
         self._graphs = {} if graphs else None
         self.compat_quirk = bool(compat_quirk and self._dropout)
         self._trace_cap = int(trace_cap)

@@ -69,6 +69,13 @@ def _worker(rank, world, port, out):
             if fz is not None:
                 fz.step()
         tr = mz.elbo_trace
+        # graph replay is a single-rank feature (capturing the NCCL all-reduces hung on this stack): refused up front
+        try:
+            ZIGaP(CountMatrix(mine['X']), k=K, use_factors=False, state=mine, sharded=True, tensor=True, graphs=True)
+            refused = False
+        except ValueError:
+            refused = True
+        assert refused
         if rank == 0:
             for k in ('b1', 'b2', 'pi_d', 'alpha1', 'beta2'):
                 a, b = getattr(mz, k).asarray(), getattr(fz, k).asarray()

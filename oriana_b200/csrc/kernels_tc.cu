@@ -830,7 +830,10 @@ int launch_tc_prep_genes(const ori_problem_t* P, cudaStream_t st) {
     const float* E_uv = sparse ? P->Vh_old : P->V_hat;
     k_tc_prep_K<<<cdiv(w.pp * KP, 256), 256, 0, st>>>(e_den, drop ? E_uv : nullptr, LOG2E, w.geneK, P->p, w.pp, KP);
     k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(e_acc, w.geneT, P->p, w.pp, KP);
-    cudaMemsetAsync(w.flags, 0, 32 * sizeof(int), st);
+    {
+        const cudaError_t e_ = cudaMemsetAsync(w.flags, 0, 32 * sizeof(int), st);
+        if (e_ != cudaSuccess) return set_error(ORI_ECUDA, "cudaMemsetAsync(tc flags): %s", cudaGetErrorString(e_));
+    }
     if (drop) {
         k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(P->V_hat, w.geneT + (long long)KP * w.pp, P->p, w.pp, KP);
         k_tc_prep_lp<<<cdiv(w.pp, 256), 256, 0, st>>>(P->lp, P->pfloor, w.lp2w, w.flw, w.cw, w.flags, P->p, (int)w.pp);

@@ -112,6 +112,8 @@ class FactorModel(metaclass=ABCMeta):
             raise ValueError('graphs=True is a single-rank feature: capturing the NCCL all-reduces of a sharded step '
                              'is not supported')
         self._graphs = {} if graphs else None
+        self.graph_replays = 0
+        self._graph_kernels = 0
         self.compat_quirk = bool(compat_quirk and self._dropout)
         self._trace_cap = int(trace_cap)
         if nmf not in (None, 'host', 'device'):
@@ -354,7 +356,6 @@ class FactorModel(metaclass=ABCMeta):
             self._gen, self._iter = gen0, it0             # capture executed nothing: undo the host-side bookkeeping
             self._graphs[key] = g
             self._graph_kernels = int(self._lib.ori_kernel_launches()) - before
-            self.graph_replays = getattr(self, 'graph_replays', 0)
         g.replay()
         self.graph_replays += 1
         self._pending_mstep = False
@@ -367,7 +368,7 @@ class FactorModel(metaclass=ABCMeta):
     def graph_kernel_launches(self):
         """Kernels of this library launched through graph replays so far (ori_kernel_launches() counts launch calls,
         i.e. a captured step only once)."""
-        return getattr(self, 'graph_replays', 0) * getattr(self, '_graph_kernels', 0)
+        return self.graph_replays * self._graph_kernels
 
     def update_variational_parameters(self):
         """E-step (zigap.py:97-141 / gap.py:82-115)."""

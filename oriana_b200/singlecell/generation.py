@@ -1,7 +1,7 @@
 """The reference's block-structured synthetic data (oriana/singlecell/generation.py:8-86), used by its drivers
 (`main.py`, `experiments/clustering.py:47`).  Host numpy, global `np.random` stream consumed in the reference's order,
-so a seeded call reproduces the reference's matrices (checked against the live reference in the build container,
-tests/test_oracle.py).  Bench inputs do NOT come from here (these counts are D * floor(U V^T)
+so a seeded call reproduces the reference's matrices bit for bit (tests/golden/generator.npz, recorded from the
+reference; tests/test_host_logic.py).  Bench inputs do NOT come from here (these counts are D * floor(U V^T)
 with rates in the thousands, not Poisson draws); see `synth_counts_device`.
 """
 import numpy as np

@@ -1,7 +1,8 @@
 /* oriana_b200.h -- C ABI of the B200-native PCMF CAVI hot path.
  *
  * Drop-in boundary for ONE path of AntoinePassemiers/Oriana: `FactorModel.step()`
- * (oriana/models/base.py:54-56) for the ZIGaP and GaP models, i.e. the E-step
+ * (oriana/models/base.py:54-56) for the ZIGaP and GaP models (and, behind ORI_F_SPARSE, SparseZIGaP,
+ * oriana/models/sparse_zigap.py:100-204, with the deviance metrics of base.py:58-82), i.e. the E-step
  * `update_variational_parameters` (oriana/models/zigap.py:97-141, gap.py:82-115) with its numba kernel
  * `compute_Z_q_expectations` (zigap.py:79-95, gap.py:67-80), the node expectations `Gamma.mean/meanlog`
  * (oriana/nodes/probabilistic/gamma.py:37-61), `Bernoulli.mean` (bernoulli.py:41-48), and the M-step

@@ -158,6 +158,21 @@ def test_count_matrix_ingest_helpers():
     assert cc.row.numel() == 1
 
 
+def test_header_is_plain_c(tmp_path):
+    """include/oriana_b200.h is the drop-in boundary: it must compile as C99 (no C++ / torch types), and the struct
+    mirrored by ctypes must have the size the C compiler gives it."""
+    import subprocess
+    src = tmp_path / 'hdr.c'
+    src.write_text('#include <stdio.h>\n#include "oriana_b200.h"\n'
+                   'int main(void) { printf("%zu\\n", sizeof(ori_problem_t)); return 0; }\n')
+    exe = tmp_path / 'hdr'
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-I', os.path.join(ROOT, 'include'),
+                    str(src), '-o', str(exe)], check=True)
+    size = int(subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout)
+    from oriana_b200 import _lib
+    assert size == ctypes.sizeof(_lib.OriProblem)
+
+
 def test_library_exports_every_declared_symbol():
     """The C-ABI library loads and exports exactly what include/oriana_b200.h declares."""
     from oriana_b200 import _lib

@@ -75,6 +75,35 @@ def write_sparse_generator_fixture():
     print('sparse_gen written')
 
 
+def write_sparse_nmf_fixture():
+    """main.py:29 exactly: SparseZIGaP(counts, k, use_factors=True) -- NMF-seeded factors with exact zeros -- with the
+    deviance its loop prints (main.py:30, :42)."""
+    refshim.import_reference()
+    from oriana.models import SparseZIGaP
+    from oriana.singlecell import CountMatrix
+    X = cn.synth_counts(300, 400, 4, seed=13)
+    rec = (1, 2, 4)
+    np.random.seed(2)
+    m = SparseZIGaP(CountMatrix(X), k=4, use_factors=True)
+    out = {'model': 'SparseZIGaP', 'K': 4, 'tau': 0.5, 'steps': np.asarray(rec)}
+    s0 = refshim.snapshot(m)
+    out['X'] = s0.pop('X').astype(np.int32)
+    for k, v in s0.items():
+        out['s0_' + k] = v.astype(np.float32) if k == 'p_d' else v
+    out['s0_deviance'] = np.float64(m.reconstruction_deviance())
+    for t in range(1, max(rec) + 1):
+        m.step()
+        if t in rec:
+            st = refshim.snapshot(m); st.pop('X')
+            for k, v in st.items():
+                out['s%d_%s' % (t, k)] = v.astype(np.float32) if k == 'p_d' else v
+            out['s%d_deviance' % t] = np.float64(m.reconstruction_deviance())
+            out['s%d_explained' % t] = np.float64(m.explained_deviance())
+    np.savez_compressed(os.path.join(OUT, 'sparse_nmf.npz'), **out)
+    refshim.release_reference()
+    print('sparse_nmf written')
+
+
 def write_nmf_fixture():
     """The reference's DEFAULT construction path, `use_factors=True` (base.py:38-40: a1, b1 seeded with sklearn NMF
     factors, many of them tiny or exactly 0, so E[log U] reaches -100 ... -1e15 and exp(E log U) underflows float32 on
@@ -109,6 +138,8 @@ def main():
         return write_nmf_fixture()
     if sys.argv[1:] == ['sparse_gen']:
         return write_sparse_generator_fixture()
+    if sys.argv[1:] == ['sparse_nmf']:
+        return write_sparse_nmf_fixture()
     ref = refshim.import_reference()
     from oriana.models import ZIGaP, GaP
     from oriana.singlecell import CountMatrix
@@ -190,6 +221,7 @@ def main():
     write_generator_fixture()
     write_nmf_fixture()
     write_sparse_generator_fixture()
+    write_sparse_nmf_fixture()
 
 
 if __name__ == '__main__':

@@ -33,7 +33,7 @@ def test_sparse_z_kernel_matches_reference_numba_kernel(name):
         assert relerr(a, g[key]) < tol, key
 
 
-@pytest.mark.parametrize('name', ['sparse_k4', 'sparse_ragged', 'sparse_gen'])
+@pytest.mark.parametrize('name', ['sparse_k4', 'sparse_ragged', 'sparse_gen', 'sparse_nmf'])
 def test_sparse_trajectory_and_deviance_match_reference(name):
     from oracle import sparse_numpy as sn
     g = load_golden(name)
@@ -48,7 +48,9 @@ def test_sparse_trajectory_and_deviance_match_reference(name):
             want = _state(g, t)
             for k in want:
                 if k != 'X':
-                    assert relerr(s[k], want[k]) < (1e-5 if t == 1 else 5e-3), (name, t, k)
+                    late = 1.5e-2 if name == 'sparse_nmf' else 5e-3      # sparse_nmf = main.py:29 (NMF-seeded: near-dead components)
+                    first = 2e-4 if name == 'sparse_nmf' else 1e-5       # beta1 ~ 1e-14 there: psi^-1 of a float32 mean near -1e13
+                    assert relerr(s[k], want[k]) < (first if t == 1 else late), (name, t, k)
             dev_ref, expl_ref = float(g['s%d_deviance' % t]), float(g['s%d_explained' % t])
             if abs(dev_ref) < 1e15:            # beyond: a -inf entry was cast to INT64_MIN (quirk Q10), meaningless
                 assert abs(sn.reconstruction_deviance(s) - dev_ref) <= 1e-4 * abs(dev_ref), (name, t)

@@ -39,7 +39,7 @@ def make_model(s, tau):
     return SparseZIGaP(CountMatrix(s['X']), k=s['a1'].shape[1], use_factors=False, state=s, tau=tau)
 
 
-@pytest.mark.parametrize('name', ['sparse_k4', 'sparse_ragged', 'sparse_gen'])
+@pytest.mark.parametrize('name', ['sparse_k4', 'sparse_ragged', 'sparse_gen', 'sparse_nmf'])
 def test_sparse_trajectory_and_deviance_match_reference(cuda_lib, name):
     g = load_golden(name)
     m = make_model(_state(g, 0), float(g['tau']))
@@ -52,7 +52,8 @@ def test_sparse_trajectory_and_deviance_match_reference(cuda_lib, name):
         if t not in steps:
             continue
         want = _state(g, t)
-        tol = 2e-5 if t == 1 else 5e-3
+        # sparse_nmf = main.py:29 (NMF-seeded factors with near-dead components): wider late envelope, as for the oracle
+        tol = (2e-4 if name == 'sparse_nmf' else 2e-5) if t == 1 else (1.5e-2 if name == 'sparse_nmf' else 5e-3)
         for k in KEYS:
             assert relerr(getattr(m, k).asarray(), want[k]) < tol, (name, t, k)
         assert np.max(np.abs(m.D_hat - want['p_d'])) < (1e-5 if t == 1 else 2e-3), (name, t)

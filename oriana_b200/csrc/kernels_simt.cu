@@ -689,7 +689,13 @@ __device__ __forceinline__ long long trunc_like_numpy(double v) {
     return (long long)v;
 }
 
-template <int KP>
+// EXACT: float64 throughout (the float64 sums are wanted).  Otherwise (integer sums only) the rate is a float32 dot
+// product with a float64 fallback where it could underflow, the logarithms are float32 (an error of 1e-7 moves a term
+// across an integer boundary with probability ~1e-7: invisible in sums of ~1e9), log(x) of small counts comes from a
+// table, and zero entries whose terms all truncate to 0 are skipped.
+constexpr int DEV_LOGX = 1024;
+
+template <int KP, bool EXACT>
 __global__ void __launch_bounds__(PR_TR)
 k_deviance(const float* __restrict__ X, long long ldx, long long n_rows, int p,
            const float* __restrict__ Uh, const float* __restrict__ b1, const float* __restrict__ b2,
@@ -698,14 +704,17 @@ k_deviance(const float* __restrict__ X, long long ldx, long long n_rows, int p,
            const double* __restrict__ pi, const double* __restrict__ cmean,
            unsigned long long* __restrict__ out_int, double* __restrict__ out_f64)
 {
-    const bool want_f64 = out_f64 != nullptr;
     __shared__ float sX[PR_TR][PR_TG + 1];
-    // the rate is accumulated in float64 from V' = b1 / b2 and S_hat: the reference's float64 product (base.py:63-66)
-    // stays positive where a float32 S_hat * V'_hat underflows, and log(0) would turn the metric into INT64_MIN
-    __shared__ __align__(16) double sVc[PR_TG][KP];
+    // EXACT: the rate is accumulated in float64 from V' = b1 / b2 and S_hat -- the reference's float64 product
+    // (base.py:63-66) stays positive where a float32 S_hat * V'_hat underflows, and log(0) would turn the metric into
+    // INT64_MIN; the fast path keeps a float32 copy and falls back to float64 (from global memory) below 1e-30
+    __shared__ __align__(16) double sVc[EXACT ? PR_TG : 1][KP];
+    __shared__ __align__(16) float sVf[EXACT ? 1 : PR_TG][KP];
     __shared__ __align__(16) float sVo[PR_TG][KP];
     __shared__ float slp[PR_TG], sfl[PR_TG];
     __shared__ double spi[PR_TG], scm[PR_TG], slpi[PR_TG], slcm[PR_TG];
+    __shared__ float slogx[EXACT ? 1 : DEV_LOGX];
+    __shared__ float sgf[EXACT ? 1 : PR_TG][6];               // fast path: pi, 1 - pi, log pi, mean, log mean, exp(-mean)
     __shared__ double sred[PR_TR / 32];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -715,6 +724,8 @@ k_deviance(const float* __restrict__ X, long long ldx, long long n_rows, int p,
     float uh[KP];
 #pragma unroll
     for (int k = 0; k < KP; ++k) uh[k] = row_ok ? Uh[row * KP + k] : 0.f;
+    if (!EXACT)
+        for (int i = tid; i < DEV_LOGX; i += PR_TR) slogx[i] = i ? (float)log((double)i) : 0.f;
 
     unsigned long long ti[3] = {0ull, 0ull, 0ull};
     double tf[3] = {0.0, 0.0, 0.0};
@@ -729,14 +740,13 @@ k_deviance(const float* __restrict__ X, long long ldx, long long n_rows, int p,
             if (r < n_rows && lane < gcount) v = __ldg(X + r * ldx + j0 + lane);
             sX[rr][lane] = v;
         }
-        double* sVcf = &sVc[0][0];
         float* sVof = &sVo[0][0];
         for (int idx = tid; idx < PR_TG * KP; idx += PR_TR) {
             const bool ok = idx / KP < gcount;
             const long long gi = (long long)j0 * KP + idx;
             double v = 0.0;
             if (ok && b2[gi] != 0.f) v = (double)b1[gi] / (double)b2[gi] * (Sh ? (double)Sh[gi] : 1.0);   // pad columns: 0
-            sVcf[idx] = v;
+            if (EXACT) (&sVc[0][0])[idx] = v; else (&sVf[0][0])[idx] = (float)v;
             sVof[idx] = ok ? Vo[gi] : 0.f;
         }
         if (tid < PR_TG) {
@@ -747,6 +757,11 @@ k_deviance(const float* __restrict__ X, long long ldx, long long n_rows, int p,
             scm[tid] = ok ? cmean[j0 + tid] : 0.0;
             slpi[tid] = log(spi[tid]);                            // per-gene logarithms of the non-zero branch
             slcm[tid] = log(scm[tid]);
+            if (!EXACT) {
+                float* gf = &sgf[EXACT ? 0 : tid][0];
+                gf[0] = (float)spi[tid]; gf[1] = (float)(1.0 - spi[tid]); gf[2] = (float)slpi[tid];
+                gf[3] = (float)scm[tid]; gf[4] = (float)slcm[tid]; gf[5] = (float)exp(-scm[tid]);
+            }
         }
         __syncthreads();
         if (!row_ok) continue;
@@ -756,45 +771,108 @@ k_deviance(const float* __restrict__ X, long long ldx, long long n_rows, int p,
             const double pj = spi[g], cm = scm[g], xd = (double)x;
             // integer-only mode: a zero entry's terms lie in (log(1 - pi_j), 0], so they all truncate to 0 when
             // 1 - pi_j >= 1/e -- no work at all for those genes' zeros
-            if (!nz && !want_f64 && (1.0 - pj) >= 0.36787944117144233) continue;
-            float D = 1.f;
-            if (!nz) {                                            // D_hat only matters on zeros (zigap.py:135-136)
-                float uv = 0.f;
+            if (!nz && !EXACT && (1.0 - pj) >= 0.36787944117144233) continue;
+            // both contractions for every lane, four partial sums each: one serial chain of 32 dependent FMAs per
+            // branch made this kernel latency-bound (3 warps per scheduler): 64 ms -> see DESIGN.md 4.4
+            float uv = 0.f, Lfast = 0.f;
+            {
+                float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f, l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
                 const float4* o4 = reinterpret_cast<const float4*>(&sVo[g][0]);
+                const float4* c4 = reinterpret_cast<const float4*>(&sVf[EXACT ? 0 : g][0]);
 #pragma unroll
                 for (int q = 0; q < KP / 4; ++q) {
                     const float4 o = o4[q];
-                    uv = fmaf(uh[4 * q + 0], o.x, uv); uv = fmaf(uh[4 * q + 1], o.y, uv);
-                    uv = fmaf(uh[4 * q + 2], o.z, uv); uv = fmaf(uh[4 * q + 3], o.w, uv);
+                    u0 = fmaf(uh[4 * q + 0], o.x, u0); u1 = fmaf(uh[4 * q + 1], o.y, u1);
+                    u2 = fmaf(uh[4 * q + 2], o.z, u2); u3 = fmaf(uh[4 * q + 3], o.w, u3);
+                    if (!EXACT) {
+                        const float4 c = c4[q];
+                        l0 = fmaf(uh[4 * q + 0], c.x, l0); l1 = fmaf(uh[4 * q + 1], c.y, l1);
+                        l2 = fmaf(uh[4 * q + 2], c.z, l2); l3 = fmaf(uh[4 * q + 3], c.w, l3);
+                    }
                 }
+                uv = (u0 + u1) + (u2 + u3);
+                Lfast = (l0 + l1) + (l2 + l3);
+            }
+            float D = 1.f;
+            if (!nz) {                                            // D_hat only matters on zeros (zigap.py:135-136)
                 float e, ex;
                 D = dropout_p(uv, slp[g], sfl[g], e, ex);
             }
-            double L = 0.0;                                       // base.py:67: UV[round(D_hat) == 0] = 0
-            if (D > 0.5f) {
-                const double2* c2 = reinterpret_cast<const double2*>(&sVc[g][0]);
+            const bool masked = !(D > 0.5f);                      // base.py:67: UV[round(D_hat) == 0] = 0
+            if (!EXACT && masked && !nz) {                        // rate 0 on a zero entry: l_uv = l_sat = log(1) = 0
+                const float* gf = &sgf[EXACT ? 0 : g][0];
+                ti[2] += (unsigned long long)(long long)(int)__logf(fmaf(gf[0], gf[5], gf[1]));
+                continue;
+            }
+            double L = 0.0, logL = -INFINITY;
+            if (!masked) {
+                if (EXACT) {
+                    const double2* c2 = reinterpret_cast<const double2*>(&sVc[EXACT ? g : 0][0]);
 #pragma unroll
-                for (int q = 0; q < KP / 4; ++q) {
-                    const double2 ca = c2[2 * q], cb = c2[2 * q + 1];
-                    L = fma((double)uh[4 * q + 0], ca.x, L); L = fma((double)uh[4 * q + 1], ca.y, L);
-                    L = fma((double)uh[4 * q + 2], cb.x, L); L = fma((double)uh[4 * q + 3], cb.y, L);
+                    for (int q = 0; q < KP / 4; ++q) {
+                        const double2 ca = c2[2 * q], cb = c2[2 * q + 1];
+                        L = fma((double)uh[4 * q + 0], ca.x, L); L = fma((double)uh[4 * q + 1], ca.y, L);
+                        L = fma((double)uh[4 * q + 2], cb.x, L); L = fma((double)uh[4 * q + 3], cb.y, L);
+                    }
+                    logL = log(L);
+                } else {
+                    const float Lf = Lfast;
+                    if (Lf >= 1e-30f) {
+                        // everything in float32: terms below 2^23 in magnitude are truncated exactly like their float64
+                        // twins except within ~1e-2 of an integer (a +-1 on a term of 1e3 ... 1e5, unbiased)
+                        const float* gf = &sgf[EXACT ? 0 : g][0];
+                        float f_uv, f_sat, f_mean;
+                        if (!nz) {
+                            f_uv = __logf(fmaf(gf[0], __expf(-Lf), gf[1]));
+                            f_sat = 0.f;
+                            f_mean = __logf(fmaf(gf[0], gf[5], gf[1]));
+                        } else {
+                            const int xi = (int)x;
+                            const float logx = (x < (float)DEV_LOGX && (float)xi == x) ? slogx[EXACT ? 0 : xi] : logf(x);
+                            f_uv = fmaf(x, __logf(Lf), gf[2] - Lf);
+                            f_sat = fmaf(x, logx, gf[2] - x);
+                            f_mean = fmaf(x, gf[4], gf[2] - gf[3]);
+                        }
+                        if (fabsf(f_uv) < 8e6f && fabsf(f_sat) < 8e6f && fabsf(f_mean) < 8e6f) {
+                            ti[0] += (unsigned long long)(long long)(int)f_uv;
+                            ti[1] += (unsigned long long)(long long)(int)f_sat;
+                            ti[2] += (unsigned long long)(long long)(int)f_mean;
+                            continue;
+                        }
+                        L = (double)Lf; logL = log(L);            // huge or non-finite term: the float64 path below
+                    } else {                                      // rare: redo in float64 from the parameters
+                        const long long gj = (long long)(j0 + g) * KP;
+#pragma unroll
+                        for (int k = 0; k < KP; ++k)
+                            if (b2[gj + k] != 0.f)
+                                L = fma((double)uh[k], (double)b1[gj + k] / (double)b2[gj + k] * (Sh ? (double)Sh[gj + k] : 1.0), L);
+                        logL = log(L);
+                    }
                 }
             }
             double l_uv, l_sat, l_mean;
             if (!nz) {                                            // sparse_zigap.py:49
-                l_uv = log(pj * exp(-L) + (1.0 - pj));
-                l_sat = log(pj + (1.0 - pj));
-                l_mean = log(pj * exp(-cm) + (1.0 - pj));
+                if (EXACT) {
+                    l_uv = log(pj * exp(-L) + (1.0 - pj));
+                    l_sat = log(pj + (1.0 - pj));
+                    l_mean = log(pj * exp(-cm) + (1.0 - pj));
+                } else {
+                    const float pf = (float)pj, qf = (float)(1.0 - pj);
+                    l_uv = (double)logf(fmaf(pf, expf(-(float)L), qf));
+                    l_sat = 0.0;
+                    l_mean = (double)logf(fmaf(pf, expf(-(float)cm), qf));
+                }
             } else {                                              // sparse_zigap.py:50
                 const double lpi = slpi[g];
-                l_uv = lpi - L + xd * log(L);
-                l_sat = lpi - xd + xd * log(xd);
+                const double logx = log(xd);
+                l_uv = lpi - L + xd * logL;
+                l_sat = lpi - xd + xd * logx;
                 l_mean = lpi - cm + xd * slcm[g];
             }
             ti[0] += (unsigned long long)trunc_like_numpy(l_uv);
             ti[1] += (unsigned long long)trunc_like_numpy(l_sat);
             ti[2] += (unsigned long long)trunc_like_numpy(l_mean);
-            tf[0] += l_uv; tf[1] += l_sat; tf[2] += l_mean;
+            if (EXACT) { tf[0] += l_uv; tf[1] += l_sat; tf[2] += l_mean; }
         }
     }
 #pragma unroll
@@ -802,8 +880,10 @@ k_deviance(const float* __restrict__ X, long long ldx, long long n_rows, int p,
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ti[c] += __shfl_xor_sync(0xffffffffu, ti[c], o);
         if (lane == 0 && ti[c]) atomicAdd(out_int + c, ti[c]);
-        const double r = block_reduce_sum(tf[c], sred);
-        if (tid == 0 && want_f64) atomicAdd(out_f64 + c, r);
+        if (EXACT) {
+            const double r = block_reduce_sum(tf[c], sred);
+            if (tid == 0) atomicAdd(out_f64 + c, r);
+        }
     }
 }
 
@@ -1006,9 +1086,14 @@ static int deviance_kp(const ori_problem_t* P, int g, const double* pi, const do
     int gy = 1;
     while (bx * gy < 148 * 4 && gy * 2 <= ntiles) gy *= 2;
     const bool sparse = P->flags & ORI_F_SPARSE;
-    k_deviance<KP><<<dim3(bx, gy), PR_TR, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, P->U_hat[g], P->b1, P->b2,
-        sparse ? P->p_s : nullptr, sparse ? P->Vh_old : P->V_hat, P->lp, P->pfloor, pi, cmean,
-        (unsigned long long*)out_int, out_f64);
+    if (out_f64)
+        k_deviance<KP, true><<<dim3(bx, gy), PR_TR, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, P->U_hat[g], P->b1, P->b2,
+            sparse ? P->p_s : nullptr, sparse ? P->Vh_old : P->V_hat, P->lp, P->pfloor, pi, cmean,
+            (unsigned long long*)out_int, out_f64);
+    else
+        k_deviance<KP, false><<<dim3(bx, gy), PR_TR, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, P->U_hat[g], P->b1, P->b2,
+            sparse ? P->p_s : nullptr, sparse ? P->Vh_old : P->V_hat, P->lp, P->pfloor, pi, cmean,
+            (unsigned long long*)out_int, nullptr);
     return check_launch("k_deviance");
 }
 

@@ -893,8 +893,8 @@ template <int KP>
 static int pass_rows_kp(const ori_problem_t* P, int g, cudaStream_t st) {
     const int bx = cdiv(P->n_rows, PR_TR);
     const int ntiles = cdiv(P->p, PR_TG);
-    int gy = 1;  // split the gene sweep when there are too few row blocks to fill 148 SMs x 4
-    while (bx * gy < 148 * 4 && gy * 2 <= ntiles) gy *= 2;
+    int gy = 1;  // split the gene sweep until there are several waves of CTAs (3 resident per SM): a 1.8-wave grid idles
+    while (bx * gy < 148 * 3 * 6 && gy * 2 <= ntiles) gy *= 2;   // most of the machine during its last wave
     dim3 grid(bx, gy);
     const bool drop = P->flags & ORI_F_DROPOUT, elbo = P->flags & ORI_F_ELBO;
     double* colsum = P->red64;
@@ -1083,8 +1083,10 @@ static int deviance_kp(const ori_problem_t* P, int g, const double* pi, const do
                        double* out_f64, cudaStream_t st) {
     const int bx = cdiv(P->n_rows, PR_TR);
     const int ntiles = cdiv(P->p, PR_TG);
+    // the gene sweep is split so that there are >= 8 waves of CTAs (4 resident per SM): the per-tile global loads are
+    // exposed, so resident warps are what hides them, and a 1.3-wave grid leaves two thirds of the machine idle at the end
     int gy = 1;
-    while (bx * gy < 148 * 4 && gy * 2 <= ntiles) gy *= 2;
+    while (bx * gy < 148 * 4 * 8 && gy * 2 <= ntiles) gy *= 2;
     const bool sparse = P->flags & ORI_F_SPARSE;
     if (out_f64)
         k_deviance<KP, true><<<dim3(bx, gy), PR_TR, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, P->U_hat[g], P->b1, P->b2,

@@ -158,6 +158,25 @@ def test_count_matrix_ingest_helpers():
     assert cc.row.numel() == 1
 
 
+def test_reference_driver_imports_resolve():
+    """Every `from oriana... import ...` line of the reference's drivers and tests (main.py:5-6,
+    experiments/clustering.py:5-6, test/test.py:5-7) resolves against the alias package."""
+    import importlib
+    wanted = {'oriana.models': ['GaP', 'SparseGaP', 'ZIGaP', 'SparseZIGaP', 'FactorModel'],
+              'oriana.singlecell': ['CountMatrix', 'generate_factor_matrices', 'generate_u', 'generate_v'],
+              'oriana': ['Dimensions', 'Parameter', 'DatatypeException', 'IncompatibleShapeException'],
+              'oriana.nodes': ['Poisson', 'Gamma', 'Bernoulli', 'Multinomial', 'Multiply', 'Einsum', 'Transpose'],
+              'oriana.utils': ['digamma', 'inverse_digamma', 'sigmoid', 'logit'],
+              'oriana.inference': ['VariationalDistribution']}
+    for mod, names in wanted.items():
+        m = importlib.import_module(mod)
+        for name in names:
+            assert hasattr(m, name), (mod, name)
+    from oriana.models import SparseGaP
+    with pytest.raises(NotImplementedError):
+        SparseGaP(None)
+
+
 def test_header_is_plain_c(tmp_path):
     """include/oriana_b200.h is the drop-in boundary: it must compile as C99 (no C++ / torch types), and the struct
     mirrored by ctypes must have the size the C compiler gives it."""

@@ -75,6 +75,45 @@ def write_sparse_generator_fixture():
     print('sparse_gen written')
 
 
+def write_large_k_fixtures():
+    """Latent dimensions of BASELINE.json configs[3] and configs[4] (K = 32, 64) at small n, p: the reference's own
+    trajectories for the padded-K plans of the device kernels (KP = 32 with 64-wide sweep tiles, KP = 64 with 32-wide)."""
+    refshim.import_reference()
+    from oriana.models import ZIGaP, GaP
+    from oriana.singlecell import CountMatrix
+    for name, cls, n, p, K, rec in (('zigap_k32', ZIGaP, 150, 210, 32, (1, 3)), ('zigap_k64', ZIGaP, 130, 170, 64, (1, 3)),
+                                    ('gap_k40', GaP, 140, 190, 40, (1, 3))):
+        X = cn.synth_counts(n, p, K, seed=len(name) * 3 + K)
+        np.random.seed(1)
+        m = cls(CountMatrix(X), k=K, use_factors=False)
+        out = {'model': cls.__name__, 'K': K, 'steps': np.asarray(rec)}
+        s0 = refshim.snapshot(m)
+        out['X'] = s0.pop('X').astype(np.int32)
+        for k, v in s0.items():
+            out['s0_' + k] = v.astype(np.float32) if k == 'p_d' else v
+        # one raw call of the numba kernel on the initial expectations
+        lU = np.ascontiguousarray(m.log_U_hat); lV = np.ascontiguousarray(m.log_V_hat)
+        X32 = m.X[:].astype(np.float32)
+        Zi = np.empty((n, K), np.float32); Zj = np.empty((p, K), np.float32)
+        if cls is ZIGaP:
+            ZIGaP.compute_Z_q_expectations(Zi, Zj, np.empty((p, K), np.float32), lU, lV, m.D_hat, X32)
+        else:
+            GaP.compute_Z_q_expectations(Zi, Zj, lU, lV, X32)
+        out.update(z_log_U_hat=lU, z_log_V_hat=lV, z_Zi=Zi, z_Zj=Zj)
+        for t in range(1, max(rec) + 1):
+            m.step()
+            if t in rec:
+                st = refshim.snapshot(m); st.pop('X')
+                for k, v in st.items():
+                    out['s%d_%s' % (t, k)] = v.astype(np.float32) if k == 'p_d' else v
+                out['s%d_U_hat' % t] = np.asarray(m.U_hat); out['s%d_V_hat' % t] = np.asarray(m.V_hat)
+                out['s%d_log_U_hat' % t] = np.asarray(m.log_U_hat)
+                out['s%d_log_V_hat' % t] = np.asarray(m.log_V_hat)
+        np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+        print(name, 'written')
+    refshim.release_reference()
+
+
 def write_sparse_nmf_fixture():
     """main.py:29 exactly: SparseZIGaP(counts, k, use_factors=True) -- NMF-seeded factors with exact zeros -- with the
     deviance its loop prints (main.py:30, :42)."""
@@ -140,6 +179,8 @@ def main():
         return write_sparse_generator_fixture()
     if sys.argv[1:] == ['sparse_nmf']:
         return write_sparse_nmf_fixture()
+    if sys.argv[1:] == ['large_k']:
+        return write_large_k_fixtures()
     ref = refshim.import_reference()
     from oriana.models import ZIGaP, GaP
     from oriana.singlecell import CountMatrix
@@ -222,6 +263,7 @@ def main():
     write_nmf_fixture()
     write_sparse_generator_fixture()
     write_sparse_nmf_fixture()
+    write_large_k_fixtures()
 
 
 if __name__ == '__main__':

@@ -38,7 +38,8 @@ def relerr(a, b, floor=1e-6):
     return float(np.max(np.abs(a - b) / (np.abs(b) + floor * np.max(np.abs(b)) + 1e-300)))
 
 
-GOLDEN_CASES = ['zigap_c1', 'gap_c1', 'zigap_ragged', 'gap_ragged', 'zigap_k10']
+GOLDEN_CASES = ['zigap_c1', 'gap_c1', 'zigap_ragged', 'gap_ragged', 'zigap_k10',
+                'zigap_k32', 'zigap_k64', 'gap_k40']      # the last three: K of configs[3] / configs[4], padded-K plans
 
 
 @pytest.fixture(scope='session')

@@ -10,7 +10,7 @@ accumulating contractions R.eV, D.V_hat (and their transposes) take R, D and the
 TF32 (11-bit significand, round to nearest), so a sum of m terms carries a relative error of about
 2^-12 / sqrt(m) * few:
   parameters a1,a2,b1,b2 : 3e-3 relative (floor 1e-6*max) on the 100 x 500 fixtures, 1e-3 at 3000 x 1500 (2e-3 for K > 32)
-  alpha, beta, pi        : 3e-4
+  alpha, beta, pi        : 3e-4 (5e-4 for K > 32)
   D_hat                  : 1e-3 absolute
   ELBO                   : 1e-4 relative (north_star's bound)
 """
@@ -46,9 +46,10 @@ def test_tensor_trajectory_matches_reference(cuda_lib, name):
             for k in FACTORS:
                 e = relerr(getattr(m, k).asarray(), r[k])
                 assert e < 3e-3, (name, t, k, e)
+            htol = 3e-4 if s['a1'].shape[1] <= 32 else 5e-4       # K > 32: fewer counts per (row, component) sum
             for k in HYPER + (('pi_d',) if 'pi_d' in s else ()):
                 e = relerr(getattr(m, k).asarray(), r[k])
-                assert e < 3e-4, (name, t, k, e)
+                assert e < htol, (name, t, k, e)
             if 'p_d' in s:
                 assert np.max(np.abs(m.D_hat - r['p_d'])) < 1e-3, (name, t)
 

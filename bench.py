@@ -83,9 +83,10 @@ class ClockSampler(threading.Thread):
         return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=rs, samples=len(s))
 
 
-def cpu_reference_run(n, p, K, steps, warmup, seed=0, budget_rows=2048):
+def cpu_port_run(n, p, K, steps, warmup, seed=0, budget_rows=2048):
     """The oracle port of the reference's step() (oracle/cavi_numpy.py: numpy + multithreaded BLAS, float32
-    ratio form) on a bounded row slab of the same workload.  Returns (entries/s, cores, sample text)."""
+    ratio form) on a bounded row slab of the same workload: the "fair multi-core numpy" number of BASELINE.md
+    section 3.  Returns (entries/s, cores, sample text, s/step)."""
     import numpy as np
     from oracle import cavi_numpy as cn
     rows = int(min(n, budget_rows))
@@ -99,6 +100,76 @@ def cpu_reference_run(n, p, K, steps, warmup, seed=0, budget_rows=2048):
     dt = (time.perf_counter() - t0) / max(1, steps)
     return rows * p / dt, os.cpu_count(), ('%d-row slab of the workload (%d x %d, K=%d), %d full CAVI steps of the '
                                           'numpy/BLAS oracle port, %.2f s/step' % (rows, rows, p, K, steps, dt)), dt
+
+
+def cpu_reference_run(n, p, K, steps, warmup, seed=0, budget_s=150.0):
+    """The UNMODIFIED reference (`oriana.models.ZIGaP.step()`, zigap.py:97-158: numba triple loop + numpy) installed
+    under baseline/_ref by `__graft_entry__.build()`, on a bounded row slab of the same workload, through its own
+    public API.  The slab is sized so that warmup + steps fit the time budget (the per-entry cost is flat in the
+    number of rows).  Returns None when the install did not travel."""
+    import warnings
+    import numpy as np
+    from oracle import refshim, cavi_numpy as cn
+    if not refshim.available():
+        return None
+    ns_per_entry = 25.0 * K                                 # BASELINE.md section 2: 776 ns at K = 32, 271 ns at K = 10
+    rows = int(budget_s / max(1, steps + warmup) / (ns_per_entry * 1e-9) / p)
+    rows = max(16, min(n, 256, rows))
+    X = cn.synth_counts(rows, p, K, seed=seed)
+    try:
+        refshim.import_reference()
+        from oriana.models import ZIGaP
+        from oriana.singlecell import CountMatrix
+        np.random.seed(1)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            m = ZIGaP(CountMatrix(X), k=K, use_factors=False)
+            for _ in range(warmup):
+                m.step()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                m.step()
+            dt = (time.perf_counter() - t0) / max(1, steps)
+        ok = bool(np.isfinite(m.a1[:]).all() and np.isfinite(m.b1[:]).all())
+    finally:
+        refshim.release_reference()
+    sample = ('%d-row slab of the workload (%d x %d, K=%d), %d steps of the unmodified reference ZIGaP.step() '
+              '(baseline/_ref; numba Z-loop on ONE thread by construction = ~80 %% of the step, the two np.dot on %d BLAS '
+              'threads), %.2f s/step, state finite: %s' % (rows, rows, p, K, steps, os.cpu_count() or 1, dt, ok))
+    return rows * p / dt, 1, sample, dt
+
+
+def initial_state(n, p, K, r0, r1, seed=4321, block=8192):
+    """The `use_factors=False` initialisation of the reference (zigap.py:58-75: a1, b1 ~ Gamma(1), a2 = b2 = 1; prior
+    shapes ~ Gamma(2), rates 1, zigap.py:22-27) drawn from counter-based streams keyed by the GLOBAL row block, so rows
+    [r0, r1) get the same values under any sharding.  D_hat starts as the indicator (X > 0), zigap.py:77."""
+    import numpy as np
+
+    def stream(tag, idx):
+        return np.random.Generator(np.random.Philox(key=[seed, tag], counter=[idx, 0, 0, 0]))
+    a1 = np.empty((r1 - r0, K))
+    for b in range(r0 // block, (r1 + block - 1) // block):
+        lo, hi = b * block, min(n, (b + 1) * block)
+        blk = stream(1, b).gamma(1., size=(hi - lo, K))
+        s0, s1 = max(lo, r0), min(hi, r1)
+        a1[s0 - r0:s1 - r0] = blk[s0 - lo:s1 - lo]
+    g = stream(2, 0)
+    return dict(a1=a1, a2=np.ones((r1 - r0, K)), b1=g.gamma(1., size=(p, K)), b2=np.ones((p, K)),
+                alpha1=g.gamma(2., size=K), alpha2=np.ones(K), beta1=g.gamma(2., size=K), beta2=np.ones(K))
+
+
+def elbo_vs_n1(cfg, warmup, steps, world, elbo_last):
+    """Relative difference between this run's final ELBO and the one a single GPU reaches after the same number of
+    steps from the same (sharding-invariant) initial state: profiles/elbo_ref.json holds the N = 1 values this repo
+    measured, keyed "<config>:<warmup + steps>"; a N = 1 run with no entry reports 0 against itself, others null."""
+    path = os.path.join(ROOT, 'profiles', 'elbo_ref.json')
+    try:
+        ref = json.load(open(path)).get('%s:%d' % (cfg, warmup + steps))
+    except Exception:
+        ref = None
+    if ref is None:
+        return 0.0 if world == 1 else None
+    return abs(elbo_last - ref) / abs(ref)
 
 
 def main():
@@ -124,16 +195,26 @@ def main():
         if rank != 0:
             return 0
         # torchrun pins OMP_NUM_THREADS=1 for its workers: the CPU arm gets every host core (set before numpy loads)
-        for var in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        for var in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS', 'NUMBA_NUM_THREADS'):
             os.environ[var] = str(os.cpu_count() or 1)
         steps = max(1, args.steps)
-        val, cores, sample, dt = cpu_reference_run(n, p, K, steps, W)
+        pval, pcores, psample, pdt = cpu_port_run(n, p, K, min(steps, 5), min(W, 1))
+        port = {'value': pval, 'unit': UNIT, 'cores': pcores, 'kind': 'port', 'sample': psample}
+        ref = cpu_reference_run(n, p, K, steps, W)
+        if ref is not None:
+            val, cores, sample, dt = ref
+            kind = 'reference'
+        else:   # the install did not travel (baseline/_ref missing): the port is what is left
+            val, cores, sample, dt = cpu_port_run(n, p, K, steps, W)
+            kind = 'port'
         print(json.dumps({
             'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
             'warmup': W, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic', 'iters_per_sec_full_problem': val / (n * p),
+            'dtype': 'f32/f64 (reference: float32 Z loop, float64 parameters)', 'data': 'synthetic',
+            'iters_per_sec_full_problem': val / (n * p),
             'config': {'workload': workload_name(args.config, n, p, K), 'n': n, 'p': p, 'K': K},
-            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
+            'fair_multicore_port': port,
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}))
         return 0
@@ -170,8 +251,13 @@ def main():
 
     # ---- synthetic counts, generated in HBM by this rank for its own cells
     X = synth_counts_device(rows, p, K, seed=1234, row0=r0, zero_level=ZERO_LEVEL.get(args.config, 0.5))
-    np.random.seed(100 + rank)
-    model = ZIGaP(X[:, :p], k=K, use_factors=False, sharded=world > 1, trace_cap=W + K_steps + 8)
+    # initial state keyed by the GLOBAL row (like the counts): the same model whatever the number of ranks, so that the
+    # ELBO after the timed steps is a sharding check across N = 1/2/4/8 (it differs only by summation order)
+    state0 = initial_state(n, p, K, r0, r1)
+    state0['X'] = X[:, :p]
+    model = ZIGaP(X[:, :p], k=K, use_factors=False, sharded=world > 1, state=state0, keep_hyper=False,
+                  trace_cap=W + K_steps + 8)
+    del state0
     uses_tc = model.uses_tensor_path
     for _ in range(W):
         model.step()
@@ -221,11 +307,13 @@ def main():
         t = max_over_ranks(kt[name])
         kernels.append({'kernel': name, 'ms': t, 'achieved': alg_bytes / (t * 1e-3) / 1e9})
     dom = max(kernels, key=lambda k: k['ms'])
+    # DRAM bytes per launch of the dominant kernel from an `ncu --set full` capture of THIS configuration and world
+    # size (profiles/traffic.json, key "<config>:n<world>:<kernel>"); null when no such capture exists
     traffic = None
     prof = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get('%s:%s' % (args.config, dom['kernel']))
+            traffic = json.load(open(prof)).get('%s:n%d:%s' % (args.config, world, dom['kernel']))
         except Exception:
             traffic = None
     roofline = {'bound': 'hbm', 'kernel': dom['kernel'], 'achieved': dom['achieved'], 'peak': peak, 'unit': 'GB/s',
@@ -254,7 +342,7 @@ def main():
         torch.cuda.empty_cache()
         host = HostStreamedCAVI(Xh, K, state, dropout=True, sharded=world > 1)
         n_e2e = args.e2e_steps or max(2, min(K_steps, 4))
-        host.step()                                       # warm-up
+        e_first = host.step()                             # warm-up; returns the ELBO of the state it started from
         h0, d0 = host.h2d_bytes, host.d2h_bytes
         barrier()
         t0 = time.perf_counter()
@@ -268,19 +356,31 @@ def main():
         e2e = {'value': n * p * n_e2e / dt, 'unit': UNIT, 'h2d_bytes_per_step': float(hb[0]) / n_e2e,
                'd2h_bytes_per_step': float(hb[1]) / n_e2e, 'steps': n_e2e, 'ms_per_step': dt / n_e2e * 1e3,
                'host_x_dtype': xdesc,
+               # the host-streamed run continues the device run: its first step reports the ELBO of the device model's
+               # last state
+               'elbo_first_vs_device': abs(e_first - float(trace[-1])) / abs(float(trace[-1])),
                'api': 'oriana_b200.host_step.HostStreamedCAVI.step (pinned host X, a1, a2, b1, b2 in; results out)'}
 
-    # ---- the reference's CPU path beside it (rank 0, N=1 only)
+    # ---- the reference's CPU path beside it (rank 0, N=1 only): the unmodified reference on a bounded slab, and the
+    #      multi-core numpy/BLAS port of the same step as the fair comparison
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        val, cores, sample, _ = cpu_reference_run(n, p, K, steps=3, warmup=1)
-        cpu = {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
+        for var in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+            os.environ.setdefault(var, str(os.cpu_count() or 1))
+        pval, pcores, psample, _ = cpu_port_run(n, p, K, steps=3, warmup=1)
+        port = {'value': pval, 'unit': UNIT, 'cores': pcores, 'kind': 'port', 'sample': psample}
+        ref = cpu_reference_run(n, p, K, steps=3, warmup=1, budget_s=12.0)
+        if ref is not None:
+            cpu = {'value': ref[0], 'unit': UNIT, 'cores': ref[1], 'kind': 'reference', 'sample': ref[2], 'port': port}
+        else:
+            cpu = port
 
     if rank == 0:
         out = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K_steps, 'warmup': W,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic', 'iters_per_sec': 1e3 / ms_step,
+            'dtype': 'tf32 operands / f32 accumulate (f32 state, f64 ELBO sums)' if uses_tc else 'f32', 'data': 'synthetic',
+            'iters_per_sec': 1e3 / ms_step,
             'without_elbo': {'ms_per_step': ms_step_lean, 'iters_per_sec': 1e3 / ms_step_lean,
                              'value': n * p / (ms_step_lean * 1e-3)},
             'config': {'workload': workload_name(args.config, n, p, K), 'n': n, 'p': p, 'K': K,
@@ -290,6 +390,7 @@ def main():
                        'l2': 'X per rank is %.1f GB, far larger than the 126 MB L2: no flush between steps' % (alg_bytes / 1e9)},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'clocks': clocks,
             'gpu_launches': launches, 'tensor_path': bool(uses_tc), 'elbo_monotone': elbo_ok, 'elbo_last': float(trace[-1]),
+            'elbo_vs_n1': elbo_vs_n1(args.config, W, K_steps, world, float(trace[-1])),
         }
         print(json.dumps(out))
     if world > 1:

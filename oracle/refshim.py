@@ -1,26 +1,71 @@
-"""Import the UNMODIFIED reference in the build container (TEST INFRASTRUCTURE).
+"""Import the UNMODIFIED reference (TEST / BASELINE INFRASTRUCTURE, never on the product path).
 
-`/root/reference` exists only in the build container, never on the GPU box: nothing that runs
-under `pytest -m gpu`, `smoke()` or `bench.py` may import this module.  It is used by
-`oracle/make_golden.py` to produce the fixtures under `tests/golden/` and by the optional
-container-only test `tests/test_oracle.py::test_port_matches_live_reference`.
+Two places hold it:
+  * `/root/reference` -- the read-only checkout, present in the build container only; `oracle/make_golden.py` records
+    the fixtures under `tests/golden/` from it;
+  * `baseline/_ref/`  -- the reference INSTALLED from that checkout by `install()` below (the base contract's recipe:
+    `pip install --no-index --no-build-isolation --no-deps --target baseline/_ref <copy of /root/reference>`; run by
+    `__graft_entry__.build()` whenever the checkout is visible).  The directory is git-ignored (not product source) but
+    travels to the GPU box with the snapshot, so `bench.py --impl reference`, `bench.py`'s `cpu_baseline` leg and
+    `tests/test_reference_seam_gpu.py` can run the reference's own `ZIGaP.step()` there.  Nothing on the GPU box reads
+    `/root/reference`.
 
-The reference pins numpy 1.13 and uses `np.float` / `np.int` (`oriana/parameters.py:11`), removed
-in numpy >= 1.24; the two-line alias below is the only change needed.
+The reference pins numpy 1.13 and uses `np.float` / `np.int` (`oriana/parameters.py:11`), removed in numpy >= 1.24; the
+two-line alias below is the only change needed -- the installed files are byte-identical to the
+checkout's.
 """
-import os, sys
+import os, shutil, subprocess, sys, tempfile
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get('ORIANA_REFERENCE_ROOT', '/root/reference')
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CHECKOUT = '/root/reference'
+INSTALLED = os.path.join(_REPO, 'baseline', '_ref')
+
+
+def _root():
+    env = os.environ.get('ORIANA_REFERENCE_ROOT')
+    if env:
+        return env
+    if os.path.isdir(os.path.join(INSTALLED, 'oriana', 'models')):
+        return INSTALLED                      # the install (byte-identical files) wins: same path here and on the GPU box
+    if os.path.isdir(os.path.join(CHECKOUT, 'oriana')):
+        return CHECKOUT
+    return INSTALLED
+
+
+REFERENCE_ROOT = _root()
 
 
 def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, 'oriana'))
 
 
+def install(force=False):
+    """Install the reference from the read-only checkout into baseline/_ref (no-op when the checkout is absent, e.g. on
+    the GPU box, or when the install is already there).  pip builds a wheel in the source tree, hence the /tmp copy."""
+    if not os.path.isdir(os.path.join(CHECKOUT, 'oriana')):
+        return os.path.isdir(os.path.join(INSTALLED, 'oriana'))
+    if os.path.isdir(os.path.join(INSTALLED, 'oriana', 'models')) and not force:
+        return True
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, 'reference')
+        shutil.copytree(CHECKOUT, src)
+        for d, _, files in os.walk(src):
+            os.chmod(d, 0o755)
+            for f in files:
+                os.chmod(os.path.join(d, f), 0o644)
+        shutil.rmtree(INSTALLED, ignore_errors=True)
+        os.makedirs(os.path.dirname(INSTALLED), exist_ok=True)
+        r = subprocess.run([sys.executable, '-m', 'pip', 'install', '--no-index', '--no-build-isolation', '--no-deps',
+                            '--find-links', '/opt/wheelhouse', '--target', INSTALLED, src], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('pip install of the reference failed:\n' + r.stdout + r.stderr)
+    return True
+
+
 def import_reference():
     if not available():
-        raise ImportError('reference checkout not present at %s' % REFERENCE_ROOT)
+        raise ImportError('reference not present at %s (neither the checkout nor baseline/_ref)' % REFERENCE_ROOT)
     np.float = float  # noqa: alias shim
     np.int = int
     sys.dont_write_bytecode = True  # the reference tree is read-only

@@ -37,6 +37,28 @@
 namespace ori {
 using namespace tc;
 
+#ifndef ORI_TC_XPREF
+#define ORI_TC_XPREF 1     // 1: fetch the first group of the next tile during the last group of this one (two groups per tile)
+#endif
+// knock-out switches of the element-wise stage: timing experiments only (WRONG results), never set in the product build
+#ifndef ORI_KO_DMIN
+#define ORI_KO_DMIN 0
+#endif
+#ifndef ORI_KO_ULIM
+#define ORI_KO_ULIM 0
+#endif
+#ifndef ORI_KO_BIAS
+#define ORI_KO_BIAS 0
+#endif
+#ifndef ORI_KO_CS
+#define ORI_KO_CS 0
+#endif
+#ifndef ORI_KO_LG2
+#define ORI_KO_LG2 0
+#endif
+#ifndef ORI_KO_ENT2
+#define ORI_KO_ENT2 0
+#endif
 #ifndef ORI_TC_BF16X
 #define ORI_TC_BF16X 1     // 1: the two cross terms hi.lo + lo.hi of every 3xTF32 contraction run as ONE bf16 chain over
                            //    [hi | lo] . [lo | hi] (error 2^-9 of a 2^-12 term): 4 instead of 6 MMA chains per tile
@@ -510,159 +532,197 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             float cs = 0.f;
             float xl_s = 0.f, xl_c = 0.f, ent_s = 0.f, ent_c = 0.f;     // compensated fp32 sums over the item
             const int t_end = ti.t_end;
-            for (int t = ti.t_begin; t < t_end; ++t, ++it) {
-                const bool last = (t == t_end - 1);
-                const uint32_t s = it & 1, sph = (it >> 1) & 1, xs = it % XST, xph = (it / XST) & 1;
-                // X tile (and lp) visible to this thread; den / uv complete in TMEM
+            // ---- tiles of the item.  Two register buffers of 16 columns are in flight per warp.  With XPREF (two groups
+            //      per warp and tile) the first group of tile t+1 -- barrier wait, tcgen05.ld, X -- is fetched while the
+            //      second group of tile t is computed, so the hand-off between tiles leaves no pipe idle.
+            uint32_t dr[2][16], ur[2][16];
+            float x[2][16];
+            struct Tile { uint32_t xs_addr, lp_addr, tden, s, xs; int valid; bool slow; };
+            auto tile_of = [&](uint32_t it_, int t_) {
+                Tile c;
+                c.s = it_ & 1; c.xs = it_ % XST;
+                c.xs_addr = sbase + OFF_X + c.xs * X_STAGE;
+                c.lp_addr = sbase + OFF_LP + c.xs * LP_STAGE;
+                c.valid = (int)min((long long)SW, a.sw_total - (long long)t_ * SW);   // gene pass: real cells
+                c.slow = slow_item || (GENES && c.valid != SW);
+                c.tden = tlane + c.s * TM_STAGE;                                      // uv / D_hat: + SW
+                return c;
+            };
+            // X tile (and lp) visible to this thread; den / uv complete in TMEM
+            auto wait_tile = [&](uint32_t it_) {
+                const uint32_t s = it_ & 1, sph = (it_ >> 1) & 1, xs = it_ % XST, xph = (it_ / XST) & 1;
                 mbar_wait2(&bars[B_XFULL + xs], xph, &bars[B_SREADY + s], sph, 30);
                 tc_fence_after();
-                if (last && has_next) a_load_store(next_own0);   // every S of this item has completed: A can be replaced
-                const uint32_t xs_addr = sbase + OFF_X + xs * X_STAGE;
-                const uint32_t lp_addr = sbase + OFF_LP + xs * LP_STAGE;
-                const int valid = (int)min((long long)SW, a.sw_total - (long long)t * SW);   // gene pass: real cells
-                const bool slow_tile = slow_item || (GENES && valid != SW);
-                const uint32_t tden = tlane + s * TM_STAGE, tuv = tden + SW;
-                float t_xl = 0.f, t_ent = 0.f;
-
-                uint32_t dr[2][16], ur[2][16];                           // two groups in flight, indexed by g & 1
-                float x[2][16];
-                auto load_x = [&](int g) {
-                    const int c0 = colbase + g * 16;
-                    const int b = g & 1;
-                    if (!GENES) {
-                        const uint32_t base = xs_addr + (c0 >> 5) * (TC_OWN * 128) + lrow * 128;
-                        const int cb = (c0 & 31) >> 2;
+            };
+            auto ld_group = [&](const Tile& c, int g, int b) {
+                tmem_ld16(c.tden + colbase + g * 16, dr[b]);
+                if (DROPOUT) tmem_ld16(c.tden + SW + colbase + g * 16, ur[b]);
+            };
+            auto load_x = [&](const Tile& c, int g, int b) {
+                const int c0 = colbase + g * 16;
+                if (!GENES) {
+                    const uint32_t base = c.xs_addr + (c0 >> 5) * (TC_OWN * 128) + lrow * 128;
+                    const int cb = (c0 & 31) >> 2;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 v = lds128(base + (((cb + q) ^ (lrow & 7)) << 4));
-                            x[b][4 * q] = v.x; x[b][4 * q + 1] = v.y; x[b][4 * q + 2] = v.z; x[b][4 * q + 3] = v.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            const int i = c0 + e;
-                            x[b][e] = lds32(xs_addr + xoff[i & 7] + i * 128);
-                        }
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 v = lds128(base + (((cb + q) ^ (lrow & 7)) << 4));
+                        x[b][4 * q] = v.x; x[b][4 * q + 1] = v.y; x[b][4 * q + 2] = v.z; x[b][4 * q + 3] = v.w;
                     }
-                };
-                // general path: den guard, floors, ragged last tile (zigap.py:90, :133); rare
-                auto slow_group = [&](int g) {
-                    const int c0 = colbase + g * 16;
-                    const int b = g & 1;
-                    tmem_ld16(tden + c0, dr[b]);
-                    if (DROPOUT) tmem_ld16(tuv + c0, ur[b]);
-                    tmem_wait_ld();
+                } else {
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
-                        const float den = __uint_as_float(dr[b][e]);
-                        const float xe = x[b][e];
-                        const bool nz = xe != 0.f;
-                        const float dg = den > 0.f ? den : 1.f;
-                        float tt = dg, e2 = 0.f, D = 1.f;
-                        if (DROPOUT) {
-                            const float lp2 = GENES ? lp2j : lds32(lp_addr + 4 * (c0 + e));
-                            const float fl = GENES ? flj : lds32(lp_addr + SW * 4 + 4 * (c0 + e));
-                            e2 = fminf(__uint_as_float(ur[b][e]) - lp2, 127.f);
-                            tt = nz ? dg : 1.f + ex2_approx(e2);
-                            const float r = rcp_approx(tt);
-                            D = fmaxf(nz ? 1.f : r, fl);
-                            dr[b][e] = tf32_bias(xe * r);
-                            ur[b][e] = tf32_bias(D);
-                        } else {
-                            dr[b][e] = tf32_bias(xe * rcp_approx(tt));
-                        }
-                        if (GENES && (c0 + e) < valid) {
-                            if (DROPOUT) cs += D;
-                            if (ELBO) {
-                                const float l2 = lg2_approx(tt);
-                                t_xl = fmaf(xe, l2, t_xl);
-                                if (DROPOUT) t_ent += (nz ? 0.f : l2) - (1.f - D) * e2;
-                            }
-                        }
+                        const int i = c0 + e;
+                        x[b][e] = lds32(c.xs_addr + xoff[i & 7] + i * 128);
                     }
-                };
-                // lean path: full tile, no floors; returns the smallest denominator seen
-                auto fast_group = [&](int g, float& g_cs, float& g_xl, float& g_ent) -> float {
-                    const int c0 = colbase + g * 16;
-                    const int b = g & 1;
-                    float cc[16];
-                    if (DROPOUT && !GENES) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 v = lds128(lp_addr + SW * 8 + 4 * (c0 + 4 * q));
-                            cc[4 * q] = v.x; cc[4 * q + 1] = v.y; cc[4 * q + 2] = v.z; cc[4 * q + 3] = v.w;
-                        }
-                    }
-                    float dmin = 1.f;
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const float den = __uint_as_float(dr[b][e]);
-                        const float xe = x[b][e];
-                        dmin = fminf(dmin, den);                  // den <= 0 (zigap.py:90): the group is redone below
-                        float tt = den, uvp = 0.f;
-                        if (DROPOUT) {
-                            uvp = __uint_as_float(ur[b][e]);                          // U_hat.V_hat * log2(e)
-                            if (GENES && ELBO) uvp = fminf(uvp, ulim);                // keeps 2^uv, tz and e2 finite
-                            const float tz = fmaf(ex2_approx(uvp), GENES ? cj : cc[e], 1.f);   // 1 + exp(uv - logit pi)
-                            tt = sel_nz_a(xe, den, tz);
-                        }
-                        const float r = rcp_approx(tt);
-                        dr[b][e] = tf32_bias(xe * r);                                 // R = X / den; 0 where X == 0
-                        float D = 1.f;
-                        if (DROPOUT) {
-                            D = sel_nz_b(xe, 1.f, r);                                 // zigap.py:131-136
-                            ur[b][e] = tf32_bias(D);
-                        }
-                        if (GENES) {
-                            if (DROPOUT) g_cs += D;
-                            if (ELBO) {
-                                const float l2 = lg2_approx(tt);
-                                g_xl = fmaf(xe, l2, g_xl);
-                                if (DROPOUT) {
-                                    const float e2 = uvp - lp2j;                      // <= 127 (uvp was clamped)
-                                    const float w = 1.f - D;                          // 0 on non-zeros
-                                    g_ent = fmaf(is_zero_f(xe), l2, g_ent);           // log2(1 + 2^e2) on zeros
-                                    g_ent = fmaf(-w, e2, g_ent);
-                                }
-                            }
-                        }
-                    }
-                    return dmin;
-                };
-
-                if (!slow_tile) {
-                    tmem_ld16(tden + colbase, dr[0]);
-                    if (DROPOUT) tmem_ld16(tuv + colbase, ur[0]);
                 }
-                load_x(0);
+            };
+            // general path: den guard, floors, ragged last tile (zigap.py:90, :133); rare
+            auto slow_group = [&](const Tile& c, int g, int b, float& t_xl, float& t_ent) {
+                const int c0 = colbase + g * 16;
+                tmem_ld16(c.tden + c0, dr[b]);
+                if (DROPOUT) tmem_ld16(c.tden + SW + c0, ur[b]);
+                tmem_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const float den = __uint_as_float(dr[b][e]);
+                    const float xe = x[b][e];
+                    const bool nz = xe != 0.f;
+                    const float dg = den > 0.f ? den : 1.f;
+                    float tt = dg, e2 = 0.f, D = 1.f;
+                    if (DROPOUT) {
+                        const float lp2 = GENES ? lp2j : lds32(c.lp_addr + 4 * (c0 + e));
+                        const float fl = GENES ? flj : lds32(c.lp_addr + SW * 4 + 4 * (c0 + e));
+                        e2 = fminf(__uint_as_float(ur[b][e]) - lp2, 127.f);
+                        tt = nz ? dg : 1.f + ex2_approx(e2);
+                        const float r = rcp_approx(tt);
+                        D = fmaxf(nz ? 1.f : r, fl);
+                        dr[b][e] = tf32_bias(xe * r);
+                        ur[b][e] = tf32_bias(D);
+                    } else {
+                        dr[b][e] = tf32_bias(xe * rcp_approx(tt));
+                    }
+                    if (GENES && (c0 + e) < c.valid) {
+                        if (DROPOUT) cs += D;
+                        if (ELBO) {
+                            const float l2 = lg2_approx(tt);
+                            t_xl = fmaf(xe, l2, t_xl);
+                            if (DROPOUT) t_ent += (nz ? 0.f : l2) - (1.f - D) * e2;
+                        }
+                    }
+                }
+            };
+            // lean path: full tile, no floors; returns the smallest denominator seen
+            auto fast_group = [&](const Tile& c, int g, int b, float& g_cs, float& g_xl, float& g_ent) -> float {
+                const int c0 = colbase + g * 16;
+                float cc[16];
+                if (DROPOUT && !GENES) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 v = lds128(c.lp_addr + SW * 8 + 4 * (c0 + 4 * q));
+                        cc[4 * q] = v.x; cc[4 * q + 1] = v.y; cc[4 * q + 2] = v.z; cc[4 * q + 3] = v.w;
+                    }
+                }
+                float dmin = 1.f;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const float den = __uint_as_float(dr[b][e]);
+                    const float xe = x[b][e];
+#if !ORI_KO_DMIN
+                    dmin = fminf(dmin, den);                  // den <= 0 (zigap.py:90): the group is redone below
+#endif
+                    float tt = den, uvp = 0.f;
+                    if (DROPOUT) {
+                        uvp = __uint_as_float(ur[b][e]);                          // U_hat.V_hat * log2(e)
+#if !ORI_KO_ULIM
+                        if (GENES && ELBO) uvp = fminf(uvp, ulim);                // keeps 2^uv, tz and e2 finite
+#endif
+                        const float tz = fmaf(ex2_approx(uvp), GENES ? cj : cc[e], 1.f);   // 1 + exp(uv - logit pi)
+                        tt = sel_nz_a(xe, den, tz);
+                    }
+                    const float r = rcp_approx(tt);
+#if ORI_KO_BIAS
+                    dr[b][e] = __float_as_uint(xe * r);
+#else
+                    dr[b][e] = tf32_bias(xe * r);                                 // R = X / den; 0 where X == 0
+#endif
+                    float D = 1.f;
+                    if (DROPOUT) {
+                        D = sel_nz_b(xe, 1.f, r);                                 // zigap.py:131-136
+#if ORI_KO_BIAS
+                        ur[b][e] = __float_as_uint(D);
+#else
+                        ur[b][e] = tf32_bias(D);
+#endif
+                    }
+                    if (GENES) {
+#if !ORI_KO_CS
+                        if (DROPOUT) g_cs += D;
+#endif
+                        if (ELBO) {
+#if ORI_KO_LG2
+                            const float l2 = tt;
+#else
+                            const float l2 = lg2_approx(tt);
+#endif
+                            g_xl = fmaf(xe, l2, g_xl);
+                            if (DROPOUT) {
+                                g_ent = fmaf(is_zero_f(xe), l2, g_ent);           // log2(1 + 2^e2) on zeros
+#if !ORI_KO_ENT2
+                                const float e2 = uvp - lp2j;                      // <= 127 (uvp was clamped)
+                                const float w = 1.f - D;                          // 0 on non-zeros
+                                g_ent = fmaf(-w, e2, g_ent);
+#endif
+                            }
+                        }
+                    }
+                }
+                return dmin;
+            };
+
+            constexpr bool XPREF = (ORI_TC_XPREF != 0) && (G == 2);
+            bool pref = false;                        // group 0 of this tile is already in flight (fetched by the last one)
+            for (int t = ti.t_begin; t < t_end; ++t, ++it) {
+                const bool last = (t == t_end - 1);
+                const Tile c = tile_of(it, t);
+                if (!pref) {
+                    wait_tile(it);
+                    if (!c.slow) ld_group(c, 0, 0);
+                    load_x(c, 0, 0);
+                }
+                if (last && has_next) a_load_store(next_own0);   // every S of this item has completed: A can be replaced
+                const bool pref_next = XPREF && !last;
+                const Tile nc = tile_of(it + 1, t + 1);
+                float t_xl = 0.f, t_ent = 0.f;
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    const int c0 = colbase + g * 16;
-                    bool redo = slow_tile;
-                    if (g > 0) load_x(g);
-                    if (!slow_tile) {
-                        tmem_wait_ld();
-                        if (g + 1 < G) {                                  // next group's loads fly during this one
-                            tmem_ld16(tden + c0 + 16, dr[(g + 1) & 1]);
-                            if (DROPOUT) tmem_ld16(tuv + c0 + 16, ur[(g + 1) & 1]);
-                        }
+                    const int b = g & 1;
+                    const bool tail = (g == G - 1);
+                    bool redo = c.slow;
+                    if (!tail) load_x(c, g + 1, b ^ 1);
+                    else if (pref_next) wait_tile(it + 1);            // S(t+1) was issued before P(t-1): long complete
+                    if (!c.slow) tmem_wait_ld();
+                    // the next group's loads fly during this one
+                    if (!tail) { if (!c.slow) ld_group(c, g + 1, b ^ 1); }
+                    else if (pref_next) { ld_group(nc, 0, b ^ 1); load_x(nc, 0, b ^ 1); }
+                    if (!c.slow) {
                         float g_cs = 0.f, g_xl = 0.f, g_ent = 0.f;
-                        const float dmin = fast_group(g, g_cs, g_xl, g_ent);
+                        const float dmin = fast_group(c, g, b, g_cs, g_xl, g_ent);
                         redo = __any_sync(0xffffffffu, dmin <= 0.f) != 0;
                         if (GENES && !redo) { cs += g_cs; t_xl += g_xl; t_ent += g_ent; }
                     }
-                    if (redo) slow_group(g);
-                    tmem_st16(tden + c0, dr[g & 1]);
-                    if (DROPOUT) tmem_st16(tuv + c0, ur[g & 1]);
+                    if (redo) slow_group(c, g, b, t_xl, t_ent);
+                    tmem_st16(c.tden + colbase + g * 16, dr[b]);
+                    if (DROPOUT) tmem_st16(c.tden + SW + colbase + g * 16, ur[b]);
                 }
                 if (GENES && ELBO) { kahan_add(xl_s, xl_c, t_xl); if (DROPOUT) kahan_add(ent_s, ent_c, t_ent); }
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    arrive_leader(&bars[B_PREADY + s]);
-                    mbar_arrive(&bars[B_XEMPTY + xs]);
+                    arrive_leader(&bars[B_PREADY + c.s]);
+                    mbar_arrive(&bars[B_XEMPTY + c.xs]);
                 }
+                pref = pref_next;
             }
             double acc_xl = (double)xl_s - (double)xl_c, acc_ent = (double)ent_s - (double)ent_c;
             // ---- epilogue of the work item: accumulators -> global (atomics: the sweep of one own tile is split);

@@ -158,6 +158,24 @@ class HostStreamedCAVI:
         self._Pg = self._problem(None, 0)
         self._keep_hyper = keep_hyper
         self._init_pass()
+        # mid-run state (e.g. this class's own state_dict(), or a device model's): D_hat of the first step is the sigmoid
+        # generated by pi_prev (zigap.py:131-132), not the indicator of a freshly constructed model (zigap.py:77)
+        it0 = int(state.get('iterations', 0) or 0)
+        if self.dropout and state.get('pi_prev') is not None:
+            pi = np.asarray(state['pi_prev'], dtype=np.float64).reshape(p)
+            pc = np.clip(pi, 1e-15, 1. - 1e-15)
+            with np.errstate(divide='ignore'):
+                lp = np.log(pc / (1. - pc))
+            lp = np.where(pi <= 0, -np.inf, np.where(pi >= 1, np.inf, lp))
+            self.lp.copy_(torch.as_tensor(lp.astype(np.float32)))
+            self.pfloor.copy_(torch.as_tensor(np.where(pi <= 0, 1e-10, 0.).astype(np.float32)))
+            self.pi_d.copy_(torch.as_tensor(pi))
+            self.iterations = it0
+        elif self.dropout and it0 > 0:
+            raise ValueError('a mid-run state (iterations=%d) must carry "pi_prev", the Bernoulli prior that generated its '
+                             'dropout posterior (SURVEY.md section 8c)' % it0)
+        else:
+            self.iterations = it0
 
     # ------------------------------------------------------------------------------------------------
     def _problem(self, s, rows):

@@ -78,7 +78,8 @@ class FactorModel(metaclass=ABCMeta):
     _sparse = False      # SparseZIGaP sets this
 
     def __init__(self, cmatrix, k=2, use_factors=True, *, state=None, compat_quirk=False, sharded=False,
-                 process_group=None, elbo=True, trace_cap=4096, force_simt=False, tensor=None, nmf=None, graphs=False):
+                 process_group=None, elbo=True, trace_cap=4096, force_simt=False, tensor=None, nmf=None, graphs=False,
+                 keep_hyper=True):
         self._dev = _lib.require_cuda()
         self._lib = _lib.load()
         _lib.check(self._lib.ori_device_check(self._dev.index or 0))
@@ -119,6 +120,9 @@ class FactorModel(metaclass=ABCMeta):
         if nmf not in (None, 'host', 'device'):
             raise ValueError("nmf must be None, 'host' or 'device'")
         self._nmf_mode = nmf
+        # with state=: keep the state's alpha / beta (a model copied mid-run or out of a reference model, whose constructor
+        # has already run its M-step) or, keep_hyper=False, run the constructor's M-step on the expectations (base.py:52)
+        self._keep_hyper_arg = bool(keep_hyper)
         self._gen = 0
         self._iter = 0
         self._dirty = False
@@ -334,9 +338,7 @@ class FactorModel(metaclass=ABCMeta):
         generation (the kernels receive the ping-pong index as an argument); the iteration count lives on the device
         (ORI_F_DEVICE_ITER).  The first step of each parity runs eagerly once (lazy one-time initialisation inside the
         library must not happen under capture)."""
-        if self._iter + 1 >= self._trace_cap:
-            raise RuntimeError('elbo trace capacity %d exhausted; build the model with a larger trace_cap'
-                               % self._trace_cap)
+        self._check_trace_room()
         key = self._gen
         g = self._graphs.get(key)
         if g is None:
@@ -372,9 +374,7 @@ class FactorModel(metaclass=ABCMeta):
 
     def update_variational_parameters(self):
         """E-step (zigap.py:97-141 / gap.py:82-115)."""
-        if self._iter + 1 >= self._trace_cap:
-            raise RuntimeError('elbo trace capacity %d exhausted; build the model with a larger trace_cap'
-                               % self._trace_cap)
+        self._check_trace_room()
         if self._dirty:
             self._refresh()
         if self._timers is None:
@@ -408,6 +408,14 @@ class FactorModel(metaclass=ABCMeta):
         self._iter += 1
         self._pi_stale = self._dropout
         self._D_cache = None
+
+    def _check_trace_room(self):
+        """The ELBO trace is a fixed device buffer: a model that records it refuses to run past its capacity (build it
+        with a larger `trace_cap`); models without the ELBO terms (elbo=False, SparseZIGaP) have no iteration limit,
+        like the reference."""
+        if (self._flags & _lib.ORI_F_ELBO) and self._iter + 1 >= self._trace_cap:
+            raise RuntimeError('elbo trace capacity %d exhausted; build the model with a larger trace_cap'
+                               % self._trace_cap)
 
     def _refresh(self):
         """Parameters were edited through `model.a1[:] = ...`: re-derive expectations and ELBO terms."""
@@ -520,13 +528,19 @@ class FactorModel(metaclass=ABCMeta):
             dst[:, :K] = torch.as_tensor(v, device=self._dev).to(torch.float32)
         for i, name in enumerate(('alpha1', 'alpha2', 'beta1', 'beta2')):
             self._hyper[i] = torch.as_tensor(np.asarray(state[name], dtype=np.float64), device=self._dev)
-        self._keep_hyper = True
+        self._keep_hyper = self._keep_hyper_arg
         self._started = False
         self._gen = 0
         self._iter = 0
         self.update_expectations()
         self.update_prior_hyper_parameters()
         self._after_load_state(state)
+        # the device-side iteration count (ORI_F_DEVICE_ITER: index of the next ELBO trace entry under graph replay) and
+        # the trace follow the host-side count of the loaded state
+        self._scal[5] = float(self._iter)
+        self._trace.zero_()
+        if self._graphs is not None:
+            self._graphs.clear()
 
     def _after_load_state(self, state):
         pass

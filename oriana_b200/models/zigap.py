@@ -94,6 +94,9 @@ class ZIGaP(FactorModel):
         self._lp.copy_(lp.to(torch.float32))
         self._pfloor.copy_(torch.where(pi <= 0, 1e-10, 0.).to(torch.float32))
         self._pi_gen = pi.clone()
+        # `_finalize()` snapshots `_pi` as the generating pi before it refreshes it: keep the two in step, so that a
+        # state_dict() taken right after a load (no step in between) carries the same pi_prev it was loaded with
+        self._pi.copy_(pi)
         self._pi_stale = True
         self._D_cache = None
 

@@ -10,10 +10,13 @@ if 'k64' in sys.argv:
     sizes = [(100_000, 20_000, 48), (100_000, 20_000, 64)]
 if 'c5' in sys.argv:       # one rank's share of BASELINE configs[4] over 8 GPUs
     sizes = [(250_000, 30_000, 64)]
+quick = 'quick' in sys.argv   # ZIGaP with the ELBO at 250k x 20k, K = 32 only (kernel A/B runs)
+if quick:
+    sizes = [(250_000, 20_000, 32)]
 for (n, p, K) in sizes:
     X = synth_counts_device(n, p, K, seed=1)
-    for cls in ((ZIGaP,) if 'c5' in sys.argv else (ZIGaP, GaP)):
-        for elbo in (True, False):
+    for cls in ((ZIGaP,) if ('c5' in sys.argv or quick) else (ZIGaP, GaP)):
+        for elbo in ((True,) if quick else (True, False)):
             np.random.seed(0)
             m = cls(X[:, :p], k=K, use_factors=False, tensor=True, elbo=elbo)
             for _ in range(2): m.step()

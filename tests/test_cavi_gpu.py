@@ -99,6 +99,58 @@ def test_split_step_equals_step_and_state_roundtrip(cuda_lib):
         make_model(bad, quirk=False)
 
 
+def test_state_roundtrip_without_a_step_in_between(cuda_lib):
+    """load -> state_dict() -> load with no step in between keeps the generating pi (pi_prev): the checkpoint of a freshly
+    resumed model continues like the model it was saved from."""
+    g = load_golden('zigap_k10')
+    s = golden_state(g, 0)
+    a = make_model(s, quirk=False)
+    for _ in range(3):
+        a.step()
+    snap = a.state_dict(); snap['X'] = s['X']
+    b = make_model(snap, quirk=False)
+    snap2 = b.state_dict(); snap2['X'] = s['X']             # no step between load and save
+    assert np.array_equal(snap2['pi_prev'], snap['pi_prev'])
+    assert snap2['iterations'] == snap['iterations'] == 3
+    c = make_model(snap2, quirk=False)
+    a.step(); c.step()
+    for k in PARAMS + ('pi_d',):
+        assert relerr(c.state_dict()[k], a.state_dict()[k]) < 5e-6, k
+
+
+def test_host_streamed_resume_from_mid_run_state(cuda_lib):
+    """`HostStreamedCAVI` resumed from its own state_dict() (or a device model's) follows the run it was saved from: the
+    first step rebuilds D_hat from pi_prev, not from the indicator of a fresh model."""
+    import torch
+    from oriana_b200.host_step import HostStreamedCAVI
+    g = load_golden('zigap_ragged')
+    s = golden_state(g, 0)
+    K = s['a1'].shape[1]
+    Xh = torch.as_tensor(s['X'].astype(np.float32)).pin_memory()
+    h = HostStreamedCAVI(Xh, K, s, dropout=True, slab_rows=64)
+    for _ in range(3):
+        h.step()
+    snap = h.state_dict()
+    h2 = HostStreamedCAVI(Xh, K, snap, dropout=True, slab_rows=96)
+    assert h2.iterations == 3
+    e1, e2 = h.step(), h2.step()
+    assert abs(e1 - e2) < 1e-6 * abs(e1)
+    a, b = h.state_dict(), h2.state_dict()
+    for k in PARAMS:
+        assert relerr(b[k], a[k]) < 5e-6, k
+    m = make_model(s, quirk=False)                           # the device model's snapshot seeds the host-streamed run too
+    for _ in range(3):
+        m.step()
+    h3 = HostStreamedCAVI(Xh, K, m.state_dict(), dropout=True, slab_rows=64)
+    h3.step()
+    c = h3.state_dict()
+    for k in PARAMS:
+        assert relerr(c[k], a[k]) < 2e-5, k
+    bad = dict(snap); bad.pop('pi_prev')
+    with pytest.raises(ValueError):
+        HostStreamedCAVI(Xh, K, bad, dropout=True)
+
+
 def test_all_zero_gene_and_cell(cuda_lib):
     """Columns with pi = 0 take the 1e-10 override (zigap.py:133); all-zero rows and genes stay finite."""
     from oracle import cavi_numpy as cn

@@ -75,7 +75,12 @@ def test_node_forward_is_lazy():
     m2 = Multinomial(n, Parameter(1 - p.asarray()), dims('n,m,k ~ d,d,c'))
     prod = Multiply(m1, m2)
     prod.forward()
-    m1.sample(); m2.sample()
+    before = np.array(prod[:], copy=True)
+    for _ in range(50):                      # the draws are random: resample until the inputs' product has moved
+        m1.sample(); m2.sample()
+        if not np.allclose(before, m1[:] * m2[:]):
+            break
+    assert np.array_equal(prod[:], before)   # untouched until forward() is called
     assert not np.allclose(prod[:], m1[:] * m2[:])
     prod.forward()
     np.testing.assert_almost_equal(prod[:], m1[:] * m2[:])

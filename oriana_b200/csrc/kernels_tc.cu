@@ -38,7 +38,9 @@ namespace ori {
 using namespace tc;
 
 #ifndef ORI_TC_XPREF
-#define ORI_TC_XPREF 1     // 1: fetch the first group of the next tile during the last group of this one (two groups per tile)
+#define ORI_TC_XPREF 0     // fetch the first group of the next tile early (two groups per tile): 1 = during the last group of this
+                           // tile -- measured SLOWER (rows 6.57 vs 4.89 ms: S(t+1) is only issued after P(t-1), i.e. when tile t
+                           // starts, and lands on the critical path); 2 = under the stores / hand-off of this tile
 #endif
 // knock-out switches of the element-wise stage: timing experiments only (WRONG results), never set in the product build
 #ifndef ORI_KO_DMIN
@@ -58,6 +60,15 @@ using namespace tc;
 #endif
 #ifndef ORI_KO_ENT2
 #define ORI_KO_ENT2 0
+#endif
+#ifndef ORI_KO_LDUV
+#define ORI_KO_LDUV 0      // skip the tcgen05.ld of the uv tile
+#endif
+#ifndef ORI_KO_STD
+#define ORI_KO_STD 0       // skip the tcgen05.st of the D_hat tile
+#endif
+#ifndef ORI_KO_MATH
+#define ORI_KO_MATH 0      // no element-wise math at all: den / uv go back as they came
 #endif
 #ifndef ORI_TC_BF16X
 #define ORI_TC_BF16X 1     // 1: the two cross terms hi.lo + lo.hi of every 3xTF32 contraction run as ONE bf16 chain over
@@ -526,6 +537,9 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 cj = ex2_approx(-lp2j);               // (1 - pi) / pi
                 ulim = fminf(127.f, 127.f + lp2j);    // uv * log2(e) beyond this: D_hat = 0 either way
             }
+            // pi_j = 1 (a gene without a single zero, logit = +inf): every entry has D_hat = 1 and contributes
+            // (1 - D) * e2 = 0 * -inf to the entropy sum; a finite stand-in keeps that product at 0
+            const float lp2f = fminf(lp2j, 3.0e38f);
             // genes / columns with a floor (pi <= 0, zigap.py:133) or with the initial indicator state (logit pi = -inf,
             // zigap.py:77) take the general path
             const bool slow_item = DROPOUT && (GENES ? (__any_sync(0xffffffffu, flj != 0.f || lp2j == -INFINITY) != 0) : any_floor);
@@ -556,7 +570,9 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             };
             auto ld_group = [&](const Tile& c, int g, int b) {
                 tmem_ld16(c.tden + colbase + g * 16, dr[b]);
+#if !ORI_KO_LDUV
                 if (DROPOUT) tmem_ld16(c.tden + SW + colbase + g * 16, ur[b]);
+#endif
             };
             auto load_x = [&](const Tile& c, int g, int b) {
                 const int c0 = colbase + g * 16;
@@ -606,7 +622,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                         if (ELBO) {
                             const float l2 = lg2_approx(tt);
                             t_xl = fmaf(xe, l2, t_xl);
-                            if (DROPOUT) t_ent += (nz ? 0.f : l2) - (1.f - D) * e2;
+                            if (DROPOUT && !nz) t_ent += l2 - (1.f - D) * e2;      // non-zeros: D_hat = 1, no entropy
                         }
                     }
                 }
@@ -623,6 +639,10 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     }
                 }
                 float dmin = 1.f;
+#if ORI_KO_MATH
+                g_cs += x[b][0] + ((DROPOUT && !GENES) ? cc[0] : 0.f);
+                return dmin;
+#endif
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
                     const float den = __uint_as_float(dr[b][e]);
@@ -632,7 +652,11 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
 #endif
                     float tt = den, uvp = 0.f;
                     if (DROPOUT) {
+#if ORI_KO_LDUV
+                        uvp = den * 1e-30f;
+#else
                         uvp = __uint_as_float(ur[b][e]);                          // U_hat.V_hat * log2(e)
+#endif
 #if !ORI_KO_ULIM
                         if (GENES && ELBO) uvp = fminf(uvp, ulim);                // keeps 2^uv, tz and e2 finite
 #endif
@@ -668,7 +692,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                             if (DROPOUT) {
                                 g_ent = fmaf(is_zero_f(xe), l2, g_ent);           // log2(1 + 2^e2) on zeros
 #if !ORI_KO_ENT2
-                                const float e2 = uvp - lp2j;                      // <= 127 (uvp was clamped)
+                                const float e2 = uvp - lp2f;                      // <= 127 (uvp was clamped)
                                 const float w = 1.f - D;                          // 0 on non-zeros
                                 g_ent = fmaf(-w, e2, g_ent);
 #endif
@@ -699,11 +723,11 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     const bool tail = (g == G - 1);
                     bool redo = c.slow;
                     if (!tail) load_x(c, g + 1, b ^ 1);
-                    else if (pref_next) wait_tile(it + 1);            // S(t+1) was issued before P(t-1): long complete
+                    else if (pref_next && ORI_TC_XPREF == 1) wait_tile(it + 1);
                     if (!c.slow) tmem_wait_ld();
                     // the next group's loads fly during this one
                     if (!tail) { if (!c.slow) ld_group(c, g + 1, b ^ 1); }
-                    else if (pref_next) { ld_group(nc, 0, b ^ 1); load_x(nc, 0, b ^ 1); }
+                    else if (pref_next && ORI_TC_XPREF == 1) { ld_group(nc, 0, b ^ 1); load_x(nc, 0, b ^ 1); }
                     if (!c.slow) {
                         float g_cs = 0.f, g_xl = 0.f, g_ent = 0.f;
                         const float dmin = fast_group(c, g, b, g_cs, g_xl, g_ent);
@@ -712,7 +736,12 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     }
                     if (redo) slow_group(c, g, b, t_xl, t_ent);
                     tmem_st16(c.tden + colbase + g * 16, dr[b]);
+#if !ORI_KO_STD
                     if (DROPOUT) tmem_st16(c.tden + SW + colbase + g * 16, ur[b]);
+#endif
+                    // XPREF == 2: S(t+1) has long completed when the last group of tile t is done (it was issued right after
+                    // P(t-1)); its first group is fetched under the stores and the hand-off of this tile
+                    if (tail && pref_next && ORI_TC_XPREF == 2) { wait_tile(it + 1); ld_group(nc, 0, b ^ 1); load_x(nc, 0, b ^ 1); }
                 }
                 if (GENES && ELBO) { kahan_add(xl_s, xl_c, t_xl); if (DROPOUT) kahan_add(ent_s, ent_c, t_ent); }
                 tmem_wait_st();

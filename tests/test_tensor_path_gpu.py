@@ -11,8 +11,9 @@ TF32 (11-bit significand, round to nearest), so a sum of m terms carries a relat
 2^-12 / sqrt(m) * few:
   parameters a1,a2,b1,b2 : 3e-3 relative (floor 1e-6*max) on the 100 x 500 fixtures, 1e-3 at 3000 x 1500 (2e-3 for K > 32)
   alpha, beta, pi        : 3e-4 (5e-4 for K > 32)
-  D_hat                  : 1e-3 absolute
-  ELBO                   : 1e-4 relative (north_star's bound)
+  D_hat                  : 3e-4 absolute (measured <= 1.3e-4 on the fixtures, 2e-5 on the benchmark slabs)
+  ELBO                   : 1e-4 relative (north_star's bound; measured <= 1.6e-5 everywhere, 6e-6 on the benchmark slabs)
+Measured values per fixture and step: `scripts/gpu_parity_report.py` (log kept under profiles/).
 """
 import numpy as np
 import pytest
@@ -34,11 +35,16 @@ def make_model(s, quirk, **kw):
 
 @pytest.mark.parametrize('name', GOLDEN_CASES)
 def test_tensor_trajectory_matches_reference(cuda_lib, name):
+    """Every recorded step of every fixture (up to 50 steps on the config-1 fixtures), not only the early ones: the
+    parameters stay inside the stated TF32 envelope -- measured drift at t = 50 (scripts/gpu_parity_report.py): a1..b2
+    3.6e-4 / 4.2e-4, alpha / beta / pi 1.9e-4 / 1.2e-4, D_hat 3.5e-5 (zigap_c1 / gap_c1) -- and the ELBO of the device
+    model follows the float64 ELBO of the reference's own recorded states to 1e-4 (measured <= 1.6e-5)."""
+    from oracle import cavi_numpy as cn
     g = load_golden(name)
     s = golden_state(g, 0)
-    m = make_model(s, quirk=True, tensor=True)
+    steps = [int(t) for t in g['steps']]
+    m = make_model(s, quirk=True, tensor=True, trace_cap=max(steps) + 8)
     assert m.uses_tensor_path
-    steps = [int(t) for t in g['steps'] if int(t) <= 10]
     for t in range(1, max(steps) + 1):
         m.step()
         if t in steps:
@@ -51,7 +57,61 @@ def test_tensor_trajectory_matches_reference(cuda_lib, name):
                 e = relerr(getattr(m, k).asarray(), r[k])
                 assert e < htol, (name, t, k, e)
             if 'p_d' in s:
-                assert np.max(np.abs(m.D_hat - r['p_d'])) < 1e-3, (name, t)
+                assert np.max(np.abs(m.D_hat - r['p_d'])) < 3e-4, (name, t)
+            want = cn.elbo(r)
+            got = m.elbo()
+            assert abs(got - want) < 1e-4 * abs(want), (name, t, got, want)
+
+
+@pytest.mark.parametrize('cfg,shape,z', [('c3', (2048, 20000, 20), 0.5), ('c4', (2048, 20000, 32), 0.5),
+                                         ('c5', (2048, 30000, 64), 0.12)])
+def test_tensor_path_on_the_benchmark_workloads_matches_oracle(cuda_lib, cfg, shape, z):
+    """BASELINE.json configs[2], [3] (the bench's own workload: exactly the 2048-row slab `bench.py` feeds the oracle for
+    `cpu_baseline`) and [4] (K = 64, ~90 % zeros) at a row slab with the full gene axis and latent dimension: six steps of
+    the tensor path against the oracle port -- factors, hyper-parameters, pi, D_hat and the whole ELBO trace.
+    Measured (scripts/gpu_parity_report.py): a1..b2 2.2e-3 / 1.8e-3 / 2.7e-3 after six steps, alpha, beta, pi 6e-5,
+    D_hat 2e-5, ELBO trace 6e-6; the CUDA-core kernels on the same slabs: 8e-6, 5e-6, 1e-6, 6e-7."""
+    from oracle import cavi_numpy as cn
+    n, p, K = shape
+    X = cn.synth_counts(n, p, K, seed=0, z=z)
+    if cfg == 'c5':
+        assert 0.85 < float((X == 0).mean()) < 0.95
+    s = cn.init_state(X, K, np.random.default_rng(0), 'zigap')
+    m = make_model(s, quirk=False, tensor=True)
+    assert m.uses_tensor_path and m._KP == (32 if K <= 32 else 64)
+    ref = {k: v.copy() for k, v in s.items()}
+    want = [cn.elbo(ref, guard32=True)]
+    for _ in range(6):
+        m.step(); cn.step(ref, quirk=False)
+        want.append(cn.elbo(ref))
+    for k in FACTORS:
+        assert relerr(getattr(m, k).asarray(), ref[k]) < 4e-3, (cfg, k)
+    for k in HYPER + ('pi_d',):
+        assert relerr(getattr(m, k).asarray(), ref[k]) < 2e-4, (cfg, k)
+    assert np.max(np.abs(m.D_hat.astype(np.float64) - ref['p_d'])) < 1e-4, cfg
+    got = m.elbo_trace
+    assert np.max(np.abs(got - np.asarray(want)) / np.abs(want)) < 2e-5, (got, want)
+    assert (np.diff(got) > 0).all()
+
+
+def test_tensor_path_gene_without_zeros(cuda_lib):
+    """A gene every cell expresses has pi = 1 (logit = +inf) after the first step: its entropy terms are exact zeros, not
+    0 * inf (the ELBO of the tensor path used to come back NaN from such a column)."""
+    from oracle import cavi_numpy as cn
+    X = cn.synth_counts(2100, 1100, 6, seed=21)
+    X[:, 7] = np.maximum(X[:, 7], 1); X[:, 300] = np.maximum(X[:, 300], 2)
+    s = cn.init_state(X, 6, np.random.default_rng(3), 'zigap')
+    m = make_model(s, quirk=False, tensor=True)
+    assert m.uses_tensor_path
+    ref = {k: v.copy() for k, v in s.items()}
+    want = [cn.elbo(ref, guard32=True)]
+    for _ in range(4):
+        m.step(); cn.step(ref, quirk=False)
+        want.append(cn.elbo(ref))
+    got = m.elbo_trace
+    assert np.isfinite(got).all()
+    assert np.max(np.abs(got - np.asarray(want)) / np.abs(want)) < 1e-4, (got, want)
+    assert m.pi_d.asarray()[7] > 1 - 1e-9
 
 
 @pytest.mark.parametrize('name', ['zigap_ragged', 'gap_ragged', 'zigap_k10'])

@@ -31,17 +31,13 @@
 //   warp 1       MMA issuer + TMEM owner (warp-uniform control flow, one elected lane issues)
 //   warps 2..9   element-wise warps; warp w owns TMEM lanes 32*(w%4).. and half of the tile's columns
 #include <cstdlib>
+#include <type_traits>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
 namespace ori {
 using namespace tc;
 
-#ifndef ORI_TC_XPREF
-#define ORI_TC_XPREF 0     // fetch the first group of the next tile early (two groups per tile): 1 = during the last group of this
-                           // tile -- measured SLOWER (rows 6.57 vs 4.89 ms: S(t+1) is only issued after P(t-1), i.e. when tile t
-                           // starts, and lands on the critical path); 2 = under the stores / hand-off of this tile
-#endif
 // knock-out switches of the element-wise stage: timing experiments only (WRONG results), never set in the product build
 #ifndef ORI_KO_DMIN
 #define ORI_KO_DMIN 0
@@ -67,6 +63,9 @@ using namespace tc;
 #ifndef ORI_KO_STD
 #define ORI_KO_STD 0       // skip the tcgen05.st of the D_hat tile
 #endif
+#ifndef ORI_KO_TMA
+#define ORI_KO_TMA 0       // the producer issues one K box, one T box and no logit(pi) loads per tile (is it the floor?)
+#endif
 #ifndef ORI_KO_MATH
 #define ORI_KO_MATH 0      // no element-wise math at all: den / uv go back as they came
 #endif
@@ -82,27 +81,45 @@ constexpr int TC_OWN = 128;
 constexpr int NEW = ORI_TC_NEW;       // element-wise warps: 8 (168 registers each) or 16 (96 registers, one column group per tile)
 constexpr int SLICES = NEW / 4;       // element-wise warps per TMEM lane quarter
 constexpr int ASUBS = SLICES / 2;     // warps sharing one own-side array / one accumulator
-constexpr int TC_THREADS = 64 + 32 * NEW;
+#ifndef ORI_TC_ISSUERS
+#define ORI_TC_ISSUERS 1   // MMA-issuing warps.  2 = the den -> acc1 chain and the uv -> acc2 chain of a ZIGaP tile are issued by
+                           // two warps (disjoint TMEM columns, no ordering needed between them).  Measured SLOWER (250k x 20k,
+                           // K = 32: rows 5.24 vs 4.91 ms, no-math floor 4.13 vs 3.80 ms): kept as an experiment switch.
+#endif
+constexpr int NISS = ORI_TC_ISSUERS;
+constexpr int ISS2_WARP = 2 + NEW;    // the second issuer sits after the element-wise warps (quarter = warp & 3 stays valid)
+constexpr int TC_THREADS = 64 + 32 * NEW + (NISS == 2 ? 32 : 0);
 
 // Plan of one kernel variant.  KP: padded latent dimension (32 or 64).  PAIR: the CTA-pair variant (cta_group::2,
 // M = 256 over two SMs): each CTA stages only half of every streamed operand tile (the pair's MMA reads both
 // halves), which halves the TMA fill and the tensor-core operand reads per SM and leaves room for deeper rings.
+#ifndef ORI_TC_DEEP
+#define ORI_TC_DEEP 0      // 1: KP = 32 runs 32-wide sweep tiles on a 4-deep TMEM pipeline (S three tiles ahead of the
+                           //    element-wise warps, which prefetch the next tile and defer their hand-off by one tile: no
+                           //    hand-off latency is exposed).  Measured SLOWER (250k x 20k, K = 32: rows 6.54 vs 4.89 ms, genes
+                           //    8.48 vs 6.86 ms; without any element-wise math 5.64 vs 3.80 ms): a tcgen05.mma of N <= 64 costs
+                           //    ~45 cycles of issue whatever its N, and 32-wide tiles need 48 instead of 32 of them per 64
+                           //    sweep entries.  0 (default): 64-wide tiles, 2 TMEM stages, two groups per warp and tile.
+#endif
+
 template <int KP, bool PAIR>
 struct Cfg {
     static_assert(KP == 32 || KP == 64, "tensor path: KP is 32 or 64");
     static constexpr int NCTA = PAIR ? 2 : 1;
-    static constexpr int SW = 2048 / KP;                  // sweep entries per tile: 64 (KP 32) or 32 (KP 64)
+    static constexpr bool DEEP = (ORI_TC_DEEP != 0) && KP == 32;
+    static constexpr int SW = DEEP ? 32 : 2048 / KP;      // sweep entries per tile: 32 (deep plan, KP 64) or 64 (KP 32, round-1 plan)
+    static constexpr int NS = DEEP ? 4 : 2;               // TMEM stages of [den/R | uv/D]
     static constexpr int KB = KP / 32;                    // 128-byte K blocks of a K-major row
-    static constexpr int KST = PAIR ? 3 : 2;              // ring depths
-    static constexpr int TST = PAIR ? 3 : 2;
-    static constexpr int XST = PAIR ? 4 : 3;
+    static constexpr int KST = DEEP ? 4 : (PAIR ? 3 : 2); // ring depths
+    static constexpr int TST = DEEP ? 4 : (PAIR ? 3 : 2);
+    static constexpr int XST = DEEP ? (PAIR ? 8 : 6) : (PAIR ? 4 : 3);
     // K-major operand array of one tile: [KB blocks][SW / NCTA sweep rows][32 floats], 128-byte swizzled
     static constexpr uint32_t K_BLK = (SW / NCTA) * 128;
-    static constexpr uint32_t K_ARR = KB * K_BLK;         // = 8192 / NCTA for both KP
+    static constexpr uint32_t K_ARR = KB * K_BLK;
     static constexpr uint32_t K_STAGE = 4 * K_ARR;        // hi(e) lo(e) hi(E) lo(E)
     // transposed operand array of one tile: [SW / 32 chunks][KP / NCTA latent rows][32 sweep columns]
     static constexpr uint32_t T_CHUNK = (KP / NCTA) * 128;
-    static constexpr uint32_t T_ARR = (SW / 32) * T_CHUNK;   // = 8192 / NCTA for both KP
+    static constexpr uint32_t T_ARR = (SW / 32) * T_CHUNK;
     static constexpr uint32_t T_STAGE = 2 * T_ARR;        // transposed e and transposed E
     static constexpr uint32_t X_STAGE = TC_OWN * SW * 4;  // X tile
     static constexpr uint32_t LP_STAGE = 3 * SW * 4;      // lp2[SW] | floor[SW] | (1-pi)/pi [SW]
@@ -112,9 +129,9 @@ struct Cfg {
     static constexpr uint32_t OFF_LP = OFF_X + XST * X_STAGE;
     static constexpr uint32_t OFF_BAR = OFF_LP + XST * LP_STAGE;
     static constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;   // + barriers + alignment slack
-    // TMEM columns: 2 stages of [den/R SW | uv/D SW], accumulators [acc1 KP | acc2 KP], own operands 4 x KP
+    // TMEM columns: NS stages of [den/R SW | uv/D SW], accumulators [acc1 KP | acc2 KP], own operands 4 x KP
     static constexpr uint32_t TM_STAGE = 2 * SW;
-    static constexpr uint32_t TM_ACC = 2 * TM_STAGE;
+    static constexpr uint32_t TM_ACC = NS * TM_STAGE;
     static constexpr uint32_t TM_A = TM_ACC + 2 * KP;
     static constexpr uint32_t TM_COLS = 512;
     static_assert(TM_A + 4 * KP <= TM_COLS, "TMEM plan");
@@ -122,7 +139,7 @@ struct Cfg {
     // (the peer's TMA bytes and warp arrivals are credited there); the others are per CTA.
     static constexpr int B_KFULL = 0, B_KEMPTY = B_KFULL + KST, B_TFULL = B_KEMPTY + KST, B_TEMPTY = B_TFULL + TST,
                          B_XFULL = B_TEMPTY + TST, B_XEMPTY = B_XFULL + XST, B_SREADY = B_XEMPTY + XST,
-                         B_PREADY = B_SREADY + 2, B_ACC_READY = B_PREADY + 2, B_ACC_FREE = B_ACC_READY + 1,
+                         B_PREADY = B_SREADY + NS, B_ACC_READY = B_PREADY + NS, B_ACC_FREE = B_ACC_READY + 1,
                          B_A_READY = B_ACC_FREE + 1, NBARS = B_A_READY + 1;
     static_assert(NBARS * 8 + 8 <= 512, "barrier area");
     static_assert(SMEM_BYTES <= 232448, "shared memory");
@@ -231,7 +248,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
 {
     using C = Cfg<KP, PAIR>;
-    constexpr int NCTA = C::NCTA, SW = C::SW;
+    constexpr int NCTA = C::NCTA, SW = C::SW, NS = C::NS;
     constexpr int KST = C::KST, TST = C::TST, XST = C::XST;
     constexpr uint32_t K_STAGE = C::K_STAGE, T_STAGE = C::T_STAGE, X_STAGE = C::X_STAGE, LP_STAGE = C::LP_STAGE;
     constexpr uint32_t OFF_K = C::OFF_K, OFF_T = C::OFF_T, OFF_X = C::OFF_X, OFF_LP = C::OFF_LP, OFF_BAR = C::OFF_BAR;
@@ -252,11 +269,12 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < KST; ++s) { mbar_init(&bars[B_KFULL + s], 1); mbar_init(&bars[B_KEMPTY + s], 1); }
-        for (int s = 0; s < TST; ++s) { mbar_init(&bars[B_TFULL + s], 1); mbar_init(&bars[B_TEMPTY + s], 1); }
+        constexpr int NI = (NISS == 2 && DROPOUT) ? 2 : 1;      // issuers at work: each commits once per stage
+        for (int s = 0; s < KST; ++s) { mbar_init(&bars[B_KFULL + s], 1); mbar_init(&bars[B_KEMPTY + s], NI); }
+        for (int s = 0; s < TST; ++s) { mbar_init(&bars[B_TFULL + s], 1); mbar_init(&bars[B_TEMPTY + s], NI); }
         for (int s = 0; s < XST; ++s) { mbar_init(&bars[B_XFULL + s], 1); mbar_init(&bars[B_XEMPTY + s], NEW); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&bars[B_SREADY + s], 1); mbar_init(&bars[B_PREADY + s], NEW * NCTA); }
-        mbar_init(&bars[B_ACC_READY], 1);
+        for (int s = 0; s < NS; ++s) { mbar_init(&bars[B_SREADY + s], NI); mbar_init(&bars[B_PREADY + s], NEW * NCTA); }
+        mbar_init(&bars[B_ACC_READY], NI);
         mbar_init(&bars[B_ACC_FREE], NEW * NCTA);
         mbar_init(&bars[B_A_READY], NEW * NCTA);
         fence_barrier_init();
@@ -286,9 +304,10 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 uint8_t* st = smem + OFF_T + s * T_STAGE;
                 uint64_t* bar = &bars[B_TFULL + s];
                 const int sw0 = it_.t * SW;
-                if (rank == 0) mbar_expect_tx(bar, NT * C::T_ARR * NCTA);      // the whole pair's bytes land on the leader's barrier
+                constexpr int NTL = ORI_KO_TMA ? 1 : NT;
+                if (rank == 0) mbar_expect_tx(bar, NTL * C::T_ARR * NCTA);      // the whole pair's bytes land on the leader's barrier
 #pragma unroll
-                for (int q = 0; q < NT; ++q)
+                for (int q = 0; q < NTL; ++q)
 #pragma unroll
                     for (int c = 0; c < SW / 32; ++c) {
                         uint8_t* dst = st + q * C::T_ARR + c * C::T_CHUNK;
@@ -308,9 +327,10 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     uint8_t* st = smem + OFF_K + s * K_STAGE;
                     uint64_t* bar = &bars[B_KFULL + s];
                     const int sw0 = ik.t * SW;
-                    if (rank == 0) mbar_expect_tx(bar, NQ * C::K_ARR * NCTA);
+                    constexpr int NQL = ORI_KO_TMA ? 1 : NQ;
+                    if (rank == 0) mbar_expect_tx(bar, NQL * C::K_ARR * NCTA);
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q)
+                    for (int q = 0; q < NQL; ++q)
 #pragma unroll
                         for (int kb = 0; kb < C::KB; ++kb) {
                             uint8_t* dst = st + q * C::K_ARR + kb * C::K_BLK;
@@ -328,12 +348,12 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     uint8_t* st = smem + OFF_X + s * X_STAGE;
                     uint64_t* bar = &bars[B_XFULL + s];
                     const int sw0 = ik.t * SW;
-                    mbar_expect_tx(bar, X_STAGE + ((!GENES && DROPOUT) ? LP_STAGE : 0));
+                    mbar_expect_tx(bar, X_STAGE + ((!GENES && DROPOUT && !ORI_KO_TMA) ? LP_STAGE : 0));
                     if (!GENES) {          // [128 cells][32 genes] boxes
 #pragma unroll
                         for (int c = 0; c < SW / 32; ++c)
                             tma_load_2d_hint(st + c * (TC_OWN * 128), &maps.X, bar, sw0 + 32 * c, ik.own0, L2_EVICT_FIRST);
-                        if (DROPOUT) {
+                        if (DROPOUT && !ORI_KO_TMA) {
                             bulk_load(smem + OFF_LP + s * LP_STAGE, a.lp2w + sw0, SW * 4, bar);
                             bulk_load(smem + OFF_LP + s * LP_STAGE + SW * 4, a.flw + sw0, SW * 4, bar);
                             bulk_load(smem + OFF_LP + s * LP_STAGE + SW * 8, a.cw + sw0, SW * 4, bar);
@@ -350,14 +370,19 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             ++nk; ik.next(a);
         }
         if (nk > 0) load_T();
-    } else if (warp == 1) {
-        // ============================================ MMA issuer ===============================================
+    } else if (warp == 1 || (NISS == 2 && warp == ISS2_WARP)) {
+        // ============================================ MMA issuer(s) ============================================
+        // Two issuers (ZIGaP): warp 1 issues the den chains and the R . S1 accumulation, the second issuer the uv chains
+        // and the D . S2 accumulation -- disjoint TMEM columns, so the two streams need no ordering between them.
         // Warp-uniform control flow, one elected lane issues: descriptors and TMEM addresses stay in uniform
         // registers (a divergent single-lane loop makes the compiler wrap every tcgen05.mma in a
         // register->uniform-register broadcast loop, which throttles the issue rate).
         // With PAIR only the leader CTA issues: cta_group::2 MMAs of M = 256 span both CTAs' TMEM and read each
         // CTA's half of the B tile; completion is multicast to the barriers of both CTAs.
-        if (!PAIR || rank == 0) {
+        const bool two = (NISS == 2) && DROPOUT;
+        const int iss = (warp == 1) ? 0 : 1;
+        const bool do_den = !two || iss == 0, do_uv = DROPOUT && (!two || iss == 1);
+        if ((!PAIR || rank == 0) && (iss == 0 || two)) {
             constexpr uint32_t idescS = make_idesc_tf32(TC_OWN * NCTA, SW, false, false);
             constexpr uint32_t idescP = make_idesc_tf32(TC_OWN * NCTA, KP, false, false);
             const uint32_t sbase = smem_u32(smem);
@@ -373,21 +398,23 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             (void)idescS16; (void)mma16;
             auto commit = [&](uint64_t* bar) { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); };
             auto issue_P = [&](uint32_t it, bool first, bool last, int li) {
-                const uint32_t s = it & 1, ts = it % TST;
-                mbar_wait(&bars[B_PREADY + s], (it >> 1) & 1, 20);
+                const uint32_t s = it % NS, ts = it % TST;
+                mbar_wait(&bars[B_PREADY + s], (it / NS) & 1, 20);
                 mbar_wait(&bars[B_TFULL + ts], (it / TST) & 1, 24);
                 if (first) mbar_wait(&bars[B_ACC_FREE], (li & 1) ^ 1, 21);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t td = tdesc0 + (uint64_t)((ts * T_STAGE) >> 4);
                     // contraction over the SW sweep entries of the tile, 8 per MMA: chunk ks / 4, 32 bytes per step
+                    // the two accumulators are independent chains: issued alternately, so that an MMA never has to wait
+                    // for the write-back of the one just before it (dependent MMAs of N <= 64 cost their latency, not
+                    // their throughput)
 #pragma unroll
-                    for (int ks = 0; ks < SW / 8; ++ks)
-                        mma(tmem + TM_ACC, tmem + s * TM_STAGE + ks * 8,
-                            td + (uint64_t)(((ks >> 2) * C::T_CHUNK + (ks & 3) * 32) >> 4), idescP, !(first && ks == 0));
-                    if (DROPOUT) {
-#pragma unroll
-                        for (int ks = 0; ks < SW / 8; ++ks)
+                    for (int ks = 0; ks < SW / 8; ++ks) {
+                        if (do_den)
+                            mma(tmem + TM_ACC, tmem + s * TM_STAGE + ks * 8,
+                                td + (uint64_t)(((ks >> 2) * C::T_CHUNK + (ks & 3) * 32) >> 4), idescP, !(first && ks == 0));
+                        if (do_uv)
                             mma(tmem + TM_ACC + KP, tmem + s * TM_STAGE + SW + ks * 8,
                                 td + (uint64_t)((C::T_ARR + (ks >> 2) * C::T_CHUNK + (ks & 3) * 32) >> 4), idescP,
                                 !(first && ks == 0));
@@ -397,14 +424,20 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 }
                 __syncwarp();
             };
-            TileIter ti;
-            ti.init(a, NCTA, rank);
-            uint32_t it = 0;
-            int li = 0;
-            bool have_prev = false, prev_first = false, prev_last = false;
-            int prev_li = 0;
+            // S runs NS - 1 tiles ahead of P: S(it) overwrites the TMEM stage P(it - NS) has read (the tensor pipe executes in
+            // issue order), so each loop iteration issues S(it) and then P(it - (NS - 1)); `tp` trails `ti` for the latter
+            TileIter ti, tp;
+            ti.init(a, NCTA, rank); tp.init(a, NCTA, rank);
+            uint32_t it = 0, itp = 0;
+            int li = 0, lip = 0;
+            auto trail_P = [&]() {
+                const bool pl = tp.last();
+                issue_P(itp, tp.first(), pl, lip);
+                if (pl) ++lip;
+                ++itp; tp.next(a);
+            };
             while (ti.valid(a)) {
-                const uint32_t s = it & 1, ks_ = it % KST;
+                const uint32_t s = it % NS, ks_ = it % KST;
                 const bool first = ti.first(), last = ti.last();
                 mbar_wait(&bars[B_KFULL + ks_], (it / KST) & 1, 23);
                 if (first) mbar_wait(&bars[B_A_READY], li & 1, 22);
@@ -425,18 +458,22 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     _Pragma("unroll") for (int kk = 0; kk < KP / 8; ++kk)                                         \
                         mma16((D_), tmem + TM_A + (Q) * KP + kk * 8,                                              \
                               kd + (uint64_t)(((Q) * C::K_ARR + (kk >> 2) * C::K_BLK + (kk & 3) * 32) >> 4), idescS16, true)
-                    ORI_CHAIN(tmem + s * TM_STAGE, 0, 0, true);
-                    ORI_CHAIN16(tmem + s * TM_STAGE, 1);
-                    if (DROPOUT) {
+                    if (do_den) {
+                        ORI_CHAIN(tmem + s * TM_STAGE, 0, 0, true);
+                        ORI_CHAIN16(tmem + s * TM_STAGE, 1);
+                    }
+                    if (do_uv) {
                         ORI_CHAIN(tmem + s * TM_STAGE + SW, 2, 2, true);
                         ORI_CHAIN16(tmem + s * TM_STAGE + SW, 3);
                     }
 #undef ORI_CHAIN16
 #else
-                    ORI_CHAIN(tmem + s * TM_STAGE, 0, 0, true);
-                    ORI_CHAIN(tmem + s * TM_STAGE, 0, 1, false);
-                    ORI_CHAIN(tmem + s * TM_STAGE, 1, 0, false);
-                    if (DROPOUT) {
+                    if (do_den) {
+                        ORI_CHAIN(tmem + s * TM_STAGE, 0, 0, true);
+                        ORI_CHAIN(tmem + s * TM_STAGE, 0, 1, false);
+                        ORI_CHAIN(tmem + s * TM_STAGE, 1, 0, false);
+                    }
+                    if (do_uv) {
                         ORI_CHAIN(tmem + s * TM_STAGE + SW, 2, 2, true);
                         ORI_CHAIN(tmem + s * TM_STAGE + SW, 2, 3, false);
                         ORI_CHAIN(tmem + s * TM_STAGE + SW, 3, 2, false);
@@ -447,13 +484,12 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     commit(&bars[B_KEMPTY + ks_]);
                 }
                 __syncwarp();
-                if (have_prev) issue_P(it - 1, prev_first, prev_last, prev_li);
-                have_prev = true; prev_first = first; prev_last = last; prev_li = li;
+                if (it >= (uint32_t)(NS - 1)) trail_P();
                 if (last) ++li;
                 ++it;
                 ti.next(a);
             }
-            if (have_prev) issue_P(it - 1, prev_first, prev_last, prev_li);
+            while (itp < it) trail_P();
         }
     } else {
         // ======================================= element-wise stage + epilogue =================================
@@ -546,15 +582,13 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             float cs = 0.f;
             float xl_s = 0.f, xl_c = 0.f, ent_s = 0.f, ent_c = 0.f;     // compensated fp32 sums over the item
             const int t_end = ti.t_end;
-            // ---- tiles of the item.  Two register buffers of 16 columns are in flight per warp.  With XPREF (two groups
-            //      per warp and tile) the first group of tile t+1 -- barrier wait, tcgen05.ld, X -- is fetched while the
-            //      second group of tile t is computed, so the hand-off between tiles leaves no pipe idle.
+            // ---- tiles of the item.  Two register buffers of 16 columns are in flight per warp.
             uint32_t dr[2][16], ur[2][16];
             float x[2][16];
             struct Tile { uint32_t xs_addr, lp_addr, tden, s, xs; int valid; bool slow; };
             auto tile_of = [&](uint32_t it_, int t_) {
                 Tile c;
-                c.s = it_ & 1; c.xs = it_ % XST;
+                c.s = it_ % NS; c.xs = it_ % XST;
                 c.xs_addr = sbase + OFF_X + c.xs * X_STAGE;
                 c.lp_addr = sbase + OFF_LP + c.xs * LP_STAGE;
                 c.valid = (int)min((long long)SW, a.sw_total - (long long)t_ * SW);   // gene pass: real cells
@@ -564,7 +598,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             };
             // X tile (and lp) visible to this thread; den / uv complete in TMEM
             auto wait_tile = [&](uint32_t it_) {
-                const uint32_t s = it_ & 1, sph = (it_ >> 1) & 1, xs = it_ % XST, xph = (it_ / XST) & 1;
+                const uint32_t s = it_ % NS, sph = (it_ / NS) & 1, xs = it_ % XST, xph = (it_ / XST) & 1;
                 mbar_wait2(&bars[B_XFULL + xs], xph, &bars[B_SREADY + s], sph, 30);
                 tc_fence_after();
             };
@@ -703,55 +737,98 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 return dmin;
             };
 
-            constexpr bool XPREF = (ORI_TC_XPREF != 0) && (G == 2);
-            bool pref = false;                        // group 0 of this tile is already in flight (fetched by the last one)
-            for (int t = ti.t_begin; t < t_end; ++t, ++it) {
-                const bool last = (t == t_end - 1);
-                const Tile c = tile_of(it, t);
-                if (!pref) {
-                    wait_tile(it);
-                    if (!c.slow) ld_group(c, 0, 0);
-                    load_x(c, 0, 0);
-                }
-                if (last && has_next) a_load_store(next_own0);   // every S of this item has completed: A can be replaced
-                const bool pref_next = XPREF && !last;
-                const Tile nc = tile_of(it + 1, t + 1);
-                float t_xl = 0.f, t_ent = 0.f;
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const int b = g & 1;
-                    const bool tail = (g == G - 1);
-                    bool redo = c.slow;
-                    if (!tail) load_x(c, g + 1, b ^ 1);
-                    else if (pref_next && ORI_TC_XPREF == 1) wait_tile(it + 1);
-                    if (!c.slow) tmem_wait_ld();
-                    // the next group's loads fly during this one
-                    if (!tail) { if (!c.slow) ld_group(c, g + 1, b ^ 1); }
-                    else if (pref_next && ORI_TC_XPREF == 1) { ld_group(nc, 0, b ^ 1); load_x(nc, 0, b ^ 1); }
-                    if (!c.slow) {
-                        float g_cs = 0.f, g_xl = 0.f, g_ent = 0.f;
-                        const float dmin = fast_group(c, g, b, g_cs, g_xl, g_ent);
-                        redo = __any_sync(0xffffffffu, dmin <= 0.f) != 0;
-                        if (GENES && !redo) { cs += g_cs; t_xl += g_xl; t_ent += g_ent; }
-                    }
-                    if (redo) slow_group(c, g, b, t_xl, t_ent);
-                    tmem_st16(c.tden + colbase + g * 16, dr[b]);
+            auto st_group = [&](const Tile& c, int g, int b) {
+                tmem_st16(c.tden + colbase + g * 16, dr[b]);
 #if !ORI_KO_STD
-                    if (DROPOUT) tmem_st16(c.tden + SW + colbase + g * 16, ur[b]);
+                if (DROPOUT) tmem_st16(c.tden + SW + colbase + g * 16, ur[b]);
 #endif
-                    // XPREF == 2: S(t+1) has long completed when the last group of tile t is done (it was issued right after
-                    // P(t-1)); its first group is fetched under the stores and the hand-off of this tile
-                    if (tail && pref_next && ORI_TC_XPREF == 2) { wait_tile(it + 1); ld_group(nc, 0, b ^ 1); load_x(nc, 0, b ^ 1); }
-                }
-                if (GENES && ELBO) { kahan_add(xl_s, xl_c, t_xl); if (DROPOUT) kahan_add(ent_s, ent_c, t_ent); }
-                tmem_wait_st();
+            };
+            // R / D_hat of the tile are in TMEM (after tcgen05.wait::st): P may run; the X stage may be refilled
+            auto hand_off = [&](const Tile& c) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
                     arrive_leader(&bars[B_PREADY + c.s]);
                     mbar_arrive(&bars[B_XEMPTY + c.xs]);
                 }
-                pref = pref_next;
+            };
+            if constexpr (!C::DEEP) {
+                // ---- round-1 plan: every warp owns G groups of the tile; the next group's loads fly during the current one;
+                //      the tile is handed to the MMA warp as soon as its last group is stored
+                for (int t = ti.t_begin; t < t_end; ++t, ++it) {
+                    const bool last = (t == t_end - 1);
+                    const Tile c = tile_of(it, t);
+                    wait_tile(it);
+                    if (last && has_next) a_load_store(next_own0);   // every S of this item has completed: A can be replaced
+                    if (!c.slow) ld_group(c, 0, 0);
+                    load_x(c, 0, 0);
+                    float t_xl = 0.f, t_ent = 0.f;
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const int b = g & 1;
+                        bool redo = c.slow;
+                        if (g + 1 < G) load_x(c, g + 1, b ^ 1);
+                        if (!c.slow) {
+                            tmem_wait_ld();
+                            if (g + 1 < G) ld_group(c, g + 1, b ^ 1);
+                            float g_cs = 0.f, g_xl = 0.f, g_ent = 0.f;
+                            const float dmin = fast_group(c, g, b, g_cs, g_xl, g_ent);
+                            redo = __any_sync(0xffffffffu, dmin <= 0.f) != 0;
+                            if (GENES && !redo) { cs += g_cs; t_xl += g_xl; t_ent += g_ent; }
+                        }
+                        if (redo) slow_group(c, g, b, t_xl, t_ent);
+                        st_group(c, g, b);
+                    }
+                    if (GENES && ELBO) { kahan_add(xl_s, xl_c, t_xl); if (DROPOUT) kahan_add(ent_s, ent_c, t_ent); }
+                    tmem_wait_st();
+                    hand_off(c);
+                }
+            } else {
+                // ---- deep plan (one 16-column group per warp and tile, S three tiles ahead): while tile t is computed the
+                //      loads of tile t+1 (barrier wait, tcgen05.ld, X) are in flight in the other register buffer, and tile
+                //      t-1 is handed to the MMA warp only now -- its tcgen05.st has had a whole tile to complete -- so no
+                //      latency of the hand-off chain is exposed.  Buffer parity is a compile-time constant: the loop body is
+                //      instantiated for even and odd tiles of the item.
+                static_assert(G == 1, "deep plan: one group per warp and tile");
+                Tile pend = tile_of(0, 0);
+                bool have_pend = false;
+                auto tile_step = [&](auto PAR_, int t) {
+                    constexpr int b = decltype(PAR_)::value;
+                    const bool last = (t == t_end - 1);
+                    const Tile c = tile_of(it, t);
+                    if (t == ti.t_begin) {                       // nothing was prefetched across the item boundary
+                        wait_tile(it);
+                        ld_group(c, 0, b);
+                        load_x(c, 0, b);
+                    }
+                    if (last && has_next) a_load_store(next_own0);   // every S of this item has completed: A can be replaced
+                    bool redo = c.slow;
+                    float t_xl = 0.f, t_ent = 0.f;
+                    tmem_wait_ld();
+                    if (!last) {
+                        const Tile nc = tile_of(it + 1, t + 1);
+                        wait_tile(it + 1);                       // S(t+1) was issued NS - 1 tiles ago
+                        ld_group(nc, 0, b ^ 1);
+                        load_x(nc, 0, b ^ 1);
+                    }
+                    if (!c.slow) {
+                        float g_cs = 0.f, g_xl = 0.f, g_ent = 0.f;
+                        const float dmin = fast_group(c, 0, b, g_cs, g_xl, g_ent);
+                        redo = __any_sync(0xffffffffu, dmin <= 0.f) != 0;
+                        if (GENES && !redo) { cs += g_cs; t_xl += g_xl; t_ent += g_ent; }
+                    }
+                    if (redo) slow_group(c, 0, b, t_xl, t_ent);
+                    if (GENES && ELBO) { kahan_add(xl_s, xl_c, t_xl); if (DROPOUT) kahan_add(ent_s, ent_c, t_ent); }
+                    if (have_pend) { tmem_wait_st(); hand_off(pend); }
+                    st_group(c, 0, b);
+                    pend = c; have_pend = true;
+                    ++it;
+                };
+                for (int t = ti.t_begin; t < t_end; t += 2) {
+                    tile_step(std::integral_constant<int, 0>{}, t);
+                    if (t + 1 < t_end) tile_step(std::integral_constant<int, 1>{}, t + 1);
+                }
+                if (have_pend) { tmem_wait_st(); hand_off(pend); }
             }
             double acc_xl = (double)xl_s - (double)xl_c, acc_ent = (double)ent_s - (double)ent_c;
             // ---- epilogue of the work item: accumulators -> global (atomics: the sweep of one own tile is split);

@@ -28,6 +28,9 @@ CONFIGS = {
     'c4': (1_000_000, 20_000, 32), 'c5': (2_000_000, 30_000, 64),
 }
 ZERO_LEVEL = {'c5': 0.12}          # keep-probability mean: ~90 % zeros for BASELINE configs[4], 0.5 elsewhere
+# torch.matmul fp32 with TF32 tensor cores, 8192^3, sustained for 4 s on this pool's B200 (scripts/gpu_peaks.py, measured in
+# round 2 the way MEASURED_PEAKS.json measured bf16: 700.0 TF burst, 614.7 TF sustained; profiles/r2_peaks.json)
+TF32_PEAK_TFLOPS = 614.7
 METRIC = 'cavi_matrix_entries_per_sec'
 UNIT = 'entries/s'
 
@@ -172,6 +175,84 @@ def elbo_vs_n1(cfg, warmup, steps, world, elbo_last):
     return abs(elbo_last - ref) / abs(ref)
 
 
+def secondary_device_run(cfg, world, rank, dev, steps=5, warmup=3):
+    """A short device-resident run of another BASELINE configuration in the same job (no e2e / CPU legs): used for config 5
+    (2M x 30k, K = 64, ~90 % zeros), which BASELINE.json defines at 8 GPUs only, so that the driver's 8-GPU run records it."""
+    import torch
+    import torch.distributed as dist
+    from oriana.models import ZIGaP
+    from oriana.singlecell import synth_counts_device
+    from oriana_b200.sharding import RowSharding
+    n, p, K = CONFIGS[cfg]
+    r0, r1 = RowSharding.row_block(n, rank, world)
+    rows = r1 - r0
+    X = synth_counts_device(rows, p, K, seed=1234, row0=r0, zero_level=ZERO_LEVEL.get(cfg, 0.5))
+    zeros = float((X[: min(rows, 4096), :p] == 0).float().mean())
+    st = initial_state(n, p, K, r0, r1)
+    st['X'] = X[:, :p]
+    m = ZIGaP(X[:, :p], k=K, use_factors=False, sharded=world > 1, state=st, keep_hyper=False, trace_cap=warmup + steps + 8)
+    del st
+    for _ in range(warmup):
+        m.step()
+    m.enable_kernel_timing()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        m.step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    kt = m.kernel_times_ms()
+    trace = m.elbo_trace
+    peak, _ = load_peaks()
+    alg = 4.0 * rows * p
+    flops = 12.0 * K * rows * p          # SURVEY.md 8d: algorithmic flops per entry and iteration with dropout
+    out = {'workload': workload_name(cfg, n, p, K), 'n_gpus': world, 'steps': steps, 'warmup': warmup, 'ms_per_step': ms,
+           'iters_per_sec': 1e3 / ms, 'value': n * p / (ms * 1e-3), 'unit': UNIT, 'zero_fraction_sample': zeros,
+           'KP_plan': 32 if K <= 32 else 64,
+           'kernels': [{'kernel': k, 'ms': kt[k], 'hbm_gbs': alg / (kt[k] * 1e-3) / 1e9, 'hbm_frac': alg / (kt[k] * 1e-3) / 1e9 / peak}
+                       for k in ('pass_rows', 'pass_genes')],
+           'algorithmic_tflops_per_rank': flops / (ms * 1e-3) / 1e12,
+           'tf32_peak_tflops': TF32_PEAK_TFLOPS, 'tensor_frac_of_tf32_peak': flops / (ms * 1e-3) / 1e12 / TF32_PEAK_TFLOPS,
+           'elbo_monotone': bool((trace[2:] >= trace[1:-1] - 1e-6 * abs(trace[1:-1])).all()), 'elbo_last': float(trace[-1])}
+    del m, X
+    torch.cuda.empty_cache()
+    return out
+
+
+def operator_seam_rates(lib):
+    """The reference's plug-in point (`ZIGaP.compute_Z_q_expectations`, zigap.py:79-95) through its C-ABI replacement with
+    HOST numpy arrays in and out, at config 2 and at a row slab of config 3: entries / s of the whole call (copies in)."""
+    import ctypes
+    import numpy as np
+    out = []
+    fp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for name, (n, p, K) in (('c2 10000 x 2000, K=10', (10_000, 2_000, 10)), ('c3 slab 8192 x 20000, K=20', (8192, 20_000, 20))):
+        rng = np.random.default_rng(0)
+        lU = rng.normal(-0.5, 1.0, (n, K)).astype(np.float32); lV = rng.normal(-0.5, 1.0, (p, K)).astype(np.float32)
+        X = (rng.poisson(3.0, (n, p)) * (rng.random((n, p)) < 0.5)).astype(np.float32)
+        D = np.where(X != 0, np.float32(1), rng.random((n, p), dtype=np.float32)).astype(np.float32)
+        Zi = np.empty((n, K), np.float32); Zj = np.empty((p, K), np.float32)
+        call = lambda: lib.ori_zigap_compute_Z_q_expectations_host(fp(Zi), fp(Zj), None, fp(lU), fp(lV), fp(D), fp(X), n, p, K, 1)
+        assert call() == 0
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            assert call() == 0
+        dt = (time.perf_counter() - t0) / reps
+        out.append({'shape': name, 'ms_per_call': dt * 1e3, 'entries_per_s': n * p / dt,
+                    'host_bytes_in_per_call': int(X.nbytes + D.nbytes + lU.nbytes + lV.nbytes)})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -181,6 +262,7 @@ def main():
     ap.add_argument('--config', default=os.environ.get('ORIANA_BENCH_CONFIG', 'c4'), choices=sorted(CONFIGS))
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the secondary measurements (operator seam, config 5 at 8 GPUs)')
     ap.add_argument('--e2e-steps', type=int, default=0)
     ap.add_argument('--e2e-x', default='u8esc', choices=['u8esc', 'u16', 'f32'],
                     help='how the host holds X for the e2e leg: saturating uint8 + escapes (default), uint16, float32')
@@ -375,6 +457,20 @@ def main():
         else:
             cpu = port
 
+    # ---- secondary measurements in the same job
+    extra = {}
+    if not args.no_extra:
+        try:
+            del host, Xh
+        except NameError:
+            pass
+        import gc
+        gc.collect(); torch.cuda.empty_cache()
+        if world == 1 and rank == 0:
+            extra['operator_seam'] = operator_seam_rates(_orilib.load())
+        if world == 8 and args.config == 'c4':
+            extra['config5'] = secondary_device_run('c5', world, rank, dev)
+
     if rank == 0:
         out = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K_steps, 'warmup': W,
@@ -391,7 +487,9 @@ def main():
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'clocks': clocks,
             'gpu_launches': launches, 'tensor_path': bool(uses_tc), 'elbo_monotone': elbo_ok, 'elbo_last': float(trace[-1]),
             'elbo_vs_n1': elbo_vs_n1(args.config, W, K_steps, world, float(trace[-1])),
+            'tensor_frac_of_tf32_peak': (12.0 * K * rows * p / (ms_step * 1e-3) / 1e12) / TF32_PEAK_TFLOPS,
         }
+        out.update(extra)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

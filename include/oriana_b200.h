@@ -12,7 +12,8 @@
  * Conventions:
  *   - plain pointers and sizes only; every DEVICE buffer is owned by the caller (PyTorch allocates);
  *     the library never allocates or frees device memory behind the caller's back, except inside the
- *     `*_host` entry points, which take HOST pointers and manage their own staging buffers;
+ *     `*_host` / `*_ctx` operator entry points, which take HOST pointers and keep their staging buffers in a
+ *     context (ori_ctx_t) between calls;
  *   - device entry points are stream-ordered on the `stream` argument (a cudaStream_t passed as void*),
  *     never synchronise the device and never touch the host copy of any result;
  *   - return 0 on success, a negative ORI_E* code otherwise; `ori_last_error` gives the message;
@@ -117,7 +118,7 @@ typedef struct ori_problem {
     double* pi_s;          /* [p] prior of S, row means of p_s (:196), float64                             */
     double tau;            /* threshold of S_tilde (:134)                                                  */
 
-    /* eU / eV hold exp(E[log .]) of each cell / gene rescaled by exp(30 - max_k E[log .]) (the multinomial step only
+    /* eU / eV hold exp(E[log .]) of each cell / gene rescaled by 2^58 / max_k exp(E[log .]) (the multinomial step only
      * uses ratios, zigap.py:86-92; see csrc/special.cuh).  The ELBO term sum_ij X_ij log den_ij takes the scales back
      * through the row sums of this rank's X and the column sums of the WHOLE X (ori_row_sums_f32,
      * ori_column_sums_f64 + all-reduce, as float32); required with ORI_F_ELBO, NULL otherwise. */
@@ -197,7 +198,21 @@ int ori_column_sums_f64(const float* X, int64_t ldx, int64_t n_rows, int32_t p, 
 int ori_deviance_sums(const ori_problem_t* P, int gen, const double* pi, const double* col_mean,
                       long long* out_int, double* out_f64, void* stream);
 
-/* ---- operator-level drop-ins with HOST buffers (the reference's plugin seam) -------------------- */
+/* ---- operator-level drop-ins with HOST buffers (the reference's plugin seam) --------------------
+ * A context keeps the device side of these calls between invocations: two streams, the events, the slab staging
+ * buffers and the tensor-path workspaces (grow-only: sized by the largest call so far).  After the first call of a
+ * given shape a call creates no stream or event and allocates no device memory.  Row slabs of >= 2^21 entries run the
+ * tcgen05 / TMA passes (D_hat is an explicit input of this seam, so it is folded into X and the GaP-shaped kernels are
+ * used), smaller problems the CUDA-core kernels.  One call at a time per context (internally serialised).
+ * slab_rows: cells per slab (rounded to a multiple of 128), 0 = ~256 MB of X per slab. */
+typedef struct ori_ctx ori_ctx_t;
+int ori_ctx_create(ori_ctx_t** out, int64_t slab_rows);
+int ori_ctx_destroy(ori_ctx_t* ctx);
+/* Counters of a context (NULL: the default context used by the *_host entry points): calls served, cudaMalloc calls
+ * made, slabs processed by the tensor / the CUDA-core kernels.  Any output pointer may be NULL. */
+int ori_ctx_stats(ori_ctx_t* ctx, unsigned long long* calls, unsigned long long* device_allocations,
+                  unsigned long long* tensor_slabs, unsigned long long* simt_slabs);
+
 /* Same argument list and semantics as `ZIGaP.compute_Z_q_expectations` (zigap.py:79-95): every array
  * is a C-contiguous float32 HOST array; DZ_hat_i [n x K], DZ_hat_j [p x K] are overwritten.
  * DZ_exp_logsum_hat may be NULL (never read by the reference, zigap.py:95); when given it is filled.
@@ -210,6 +225,14 @@ int ori_zigap_compute_Z_q_expectations_host(float* DZ_hat_i, float* DZ_hat_j, fl
 int ori_gap_compute_Z_q_expectations_host(float* Z_hat_i, float* Z_hat_j,
                                           const float* log_U_hat, const float* log_V_hat,
                                           const float* X, int64_t n, int64_t p, int64_t K);
+/* The same two operators on an explicit context (the *_host forms use a process-wide default context). */
+int ori_zigap_compute_Z_q_expectations_ctx(ori_ctx_t* ctx, float* DZ_hat_i, float* DZ_hat_j, float* DZ_exp_logsum_hat,
+                                           const float* log_U_hat, const float* log_V_hat,
+                                           const float* D_hat, const float* X,
+                                           int64_t n, int64_t p, int64_t K, int quirk);
+int ori_gap_compute_Z_q_expectations_ctx(ori_ctx_t* ctx, float* Z_hat_i, float* Z_hat_j,
+                                         const float* log_U_hat, const float* log_V_hat,
+                                         const float* X, int64_t n, int64_t p, int64_t K);
 
 /* ---- synthetic counts on device (bench only) ------------------------------- */
 /* X[i, j] = Poisson(g_ij * sum_k U*[i,k] V*[j,k]) * Bernoulli(pi_j) with U*, V* ~ Gamma(2, 1/2),

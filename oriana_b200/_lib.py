@@ -68,6 +68,11 @@ _SIGNATURES = {
     'ori_deviance_sums': ([_PP, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
     'ori_zigap_compute_Z_q_expectations_host': ([C.c_void_p] * 7 + [C.c_int64] * 3 + [C.c_int], C.c_int),
     'ori_gap_compute_Z_q_expectations_host': ([C.c_void_p] * 5 + [C.c_int64] * 3, C.c_int),
+    'ori_ctx_create': ([C.POINTER(C.c_void_p), C.c_int64], C.c_int),
+    'ori_ctx_destroy': ([C.c_void_p], C.c_int),
+    'ori_ctx_stats': ([C.c_void_p] + [C.POINTER(C.c_uint64)] * 4, C.c_int),
+    'ori_zigap_compute_Z_q_expectations_ctx': ([C.c_void_p] * 8 + [C.c_int64] * 3 + [C.c_int], C.c_int),
+    'ori_gap_compute_Z_q_expectations_ctx': ([C.c_void_p] * 6 + [C.c_int64] * 3, C.c_int),
     'ori_widen_counts_f32': ([C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p], C.c_int),
     'ori_scatter_counts_f32': ([C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int64, C.c_void_p], C.c_int),

@@ -330,130 +330,191 @@ int ori_deviance_sums(const ori_problem_t* P, int gen, const double* pi, const d
 }  // extern "C"
 
 // ---- operator-level drop-in with HOST buffers ------------------------------------------------------
-struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int alloc(size_t bytes) {
-        const cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
-        return e == cudaSuccess ? ORI_OK : set_error(ORI_ECUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+// A context owns everything a call needs on the device -- two streams, the events, the slab staging buffers, the
+// tensor-path workspaces -- and keeps it between calls: after the first call of a given shape no cudaMalloc, no stream
+// or event is created (ori_ctx_stats counts them).  The *_host entry points without a context argument use one
+// process-wide default context behind a mutex.
+#include <mutex>
+
+struct ori_ctx {
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    struct Buf { void* p = nullptr; size_t cap = 0; };
+    enum { X0, X1, D0, D1, LUS0, LUS1, EU0, EU1, EUW0, EUW1, EUL0, EUL1, ZI0, ZI1, OI0, OI1, WS0, WS1,
+           LVRAW, EV, ZJ, ZJ3A, ZJ3B, OUTJ, D64, NBUF };
+    Buf buf[NBUF];
+    unsigned long long allocs = 0, calls = 0, tensor_slabs = 0, simt_slabs = 0;
+    int64_t slab_rows = 0;     // 0: ~256 MB of X per slab
+    std::mutex mu;
+
+    int init() {
+        for (int i = 0; i < 2; ++i) {
+            const cudaError_t e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+            if (e != cudaSuccess) return set_error(ORI_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        }
+        for (int i = 0; i < 3; ++i) {
+            const cudaError_t e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) return set_error(ORI_ECUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
+        }
+        return ORI_OK;
     }
-    template <class T> T* as() { return (T*)p; }
+    void release() {
+        for (auto& b : buf) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+        for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+        for (auto& s : st) { if (s) cudaStreamDestroy(s); s = nullptr; }
+    }
+    // grow-only: a buffer is reallocated only when a call needs more than any call before it
+    int need(int id, size_t bytes) {
+        Buf& b = buf[id];
+        if (bytes <= b.cap && b.p) return ORI_OK;
+        if (b.p) { cudaStreamSynchronize(st[0]); cudaStreamSynchronize(st[1]); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+        const size_t cap = bytes < 256 ? 256 : bytes;
+        const cudaError_t e = cudaMalloc(&b.p, cap);
+        if (e != cudaSuccess) return set_error(ORI_ECUDA, "cudaMalloc(%zu): %s", cap, cudaGetErrorString(e));
+        b.cap = cap; ++allocs;
+        return ORI_OK;
+    }
+    template <class T> T* as(int id) { return (T*)buf[id].p; }
 };
 
-static int z_operator_host(float* Zi_out, float* Zj_out, float* Z3_out, const float* logU, const float* logV,
-                           const float* D, const float* X, int64_t n, int64_t p, int64_t K, int quirk)
+static int z_operator_ctx(ori_ctx* C, float* Zi_out, float* Zj_out, float* Z3_out, const float* logU, const float* logV,
+                          const float* D, const float* X, int64_t n, int64_t p, int64_t K, int quirk)
 {
+    if (!C) return set_error(ORI_EINVAL, "null context");
     if (n < 0 || p <= 0 || K <= 0) return set_error(ORI_EINVAL, "bad shape n=%lld p=%lld K=%lld", (long long)n, (long long)p, (long long)K);
     if (p > 0x7fffffff) return set_error(ORI_EINVAL, "p too large");
     if (!Zi_out || !Zj_out || !logU || !logV || !X) return set_error(ORI_EINVAL, "null array (the reference raises TypeError, zigap.py:79)");
-    const int KP = pad_k(K);
-    if (KP < 0) return set_error(ORI_EUNSUPPORTED, "K=%lld > 64 is not supported", (long long)K);
+    if (pad_k(K) < 0) return set_error(ORI_EUNSUPPORTED, "K=%lld > 64 is not supported", (long long)K);
     if (quirk && D && p < K) return set_error(ORI_EINVAL, "quirk mode needs p >= K");
     if (n == 0) { memset(Zj_out, 0, sizeof(float) * p * K); if (Z3_out) memset(Z3_out, 0, sizeof(float) * p * K); return ORI_OK; }
-
-    cudaStream_t st = 0, st2 = 0;
-    ORI_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    ORI_CUDA(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
-    struct Guard { cudaStream_t a, b; ~Guard() { cudaStreamDestroy(a); cudaStreamDestroy(b); } } guard{st, st2};
+    std::lock_guard<std::mutex> lock(C->mu);
+    ++C->calls;
+    cudaStream_t st = C->st[0], st2 = C->st[1];
 
     const int64_t ldx = (p + 3) & ~3ll;
-    // slab of cells sized to ~256 MB of X
-    int64_t slab = (256ll << 20) / (ldx * 4);
+    // slab of cells sized to ~256 MB of X (or the context's setting), a multiple of 128
+    int64_t slab = C->slab_rows > 0 ? C->slab_rows : (256ll << 20) / (ldx * 4);
     slab = slab < 128 ? 128 : (slab / 128) * 128;
     if (slab > n) slab = n;
     const int nbuf = n > slab ? 2 : 1;
+    // kernel family: slabs that fill the machine take the tcgen05 / TMA passes (GaP-shaped: D_hat is an explicit input
+    // here, folded into X), smaller ones the CUDA-core kernels -- the same rule as the device models
+    const bool tensor = slab * p >= (1ll << 21);
+    const int KP = tensor ? (K <= 32 ? 32 : 64) : pad_k(K);
+    const size_t ws_floats = tensor ? (size_t)tc_workspace_floats(slab, (int)p, KP) + 32 : 0;
 
-    DevBuf dX[2], dD[2], dlU, dlV, deV, dlogVraw, dZj, dZj3a, dZj3b, dOutJ;
-    DevBuf deU[2], deUw[2], deUl[2], dZi[2], dOutI[2], dlUs[2];
+    typedef ori_ctx B;
     for (int b = 0; b < nbuf; ++b) {
-        ORI_TRY(dX[b].alloc(sizeof(float) * slab * ldx));
-        if (D) ORI_TRY(dD[b].alloc(sizeof(float) * slab * ldx));
-        ORI_TRY(dlUs[b].alloc(sizeof(float) * slab * K));
-        ORI_TRY(deU[b].alloc(sizeof(float) * slab * KP));
-        ORI_TRY(deUw[b].alloc(sizeof(float) * slab * KP));
-        if (Z3_out) ORI_TRY(deUl[b].alloc(sizeof(float) * slab * KP));
-        ORI_TRY(dZi[b].alloc(sizeof(float) * slab * KP));
-        ORI_TRY(dOutI[b].alloc(sizeof(float) * slab * K));
+        ORI_TRY(C->need(B::X0 + b, sizeof(float) * slab * ldx));
+        if (D) ORI_TRY(C->need(B::D0 + b, sizeof(float) * slab * ldx));
+        ORI_TRY(C->need(B::LUS0 + b, sizeof(float) * slab * K));
+        ORI_TRY(C->need(B::EU0 + b, sizeof(float) * slab * KP));
+        ORI_TRY(C->need(B::EUW0 + b, sizeof(float) * slab * KP));
+        if (Z3_out) ORI_TRY(C->need(B::EUL0 + b, sizeof(float) * slab * KP));
+        ORI_TRY(C->need(B::ZI0 + b, sizeof(float) * slab * KP));
+        ORI_TRY(C->need(B::OI0 + b, sizeof(float) * slab * K));
+        if (tensor) ORI_TRY(C->need(B::WS0 + b, sizeof(float) * ws_floats));
     }
-    ORI_TRY(dlogVraw.alloc(sizeof(float) * p * K));
-    ORI_TRY(deV.alloc(sizeof(float) * p * KP));
-    ORI_TRY(dZj.alloc(sizeof(float) * 2 * p * KP));
-    ORI_TRY(dZj3a.alloc(sizeof(float) * 2 * p * KP));
-    ORI_TRY(dZj3b.alloc(sizeof(float) * 2 * p * KP));
-    ORI_TRY(dOutJ.alloc(sizeof(float) * p * K));
-    DevBuf dDummy64; ORI_TRY(dDummy64.alloc(sizeof(double) * (p + 2 * KP + R64_NSLOTS)));
+    ORI_TRY(C->need(B::LVRAW, sizeof(float) * p * K));
+    ORI_TRY(C->need(B::EV, sizeof(float) * p * KP));
+    ORI_TRY(C->need(B::ZJ, sizeof(float) * 2 * p * KP));
+    ORI_TRY(C->need(B::ZJ3A, sizeof(float) * 2 * p * KP));
+    ORI_TRY(C->need(B::ZJ3B, sizeof(float) * 2 * p * KP));
+    ORI_TRY(C->need(B::OUTJ, sizeof(float) * p * K));
+    ORI_TRY(C->need(B::D64, sizeof(double) * (p + 2 * KP + R64_NSLOTS)));
 
-    ORI_CUDA(cudaMemcpyAsync(dlogVraw.p, logV, sizeof(float) * p * K, cudaMemcpyHostToDevice, st));
-    k_exp_pad<<<cdiv(p * KP, 256), 256, 0, st>>>(dlogVraw.as<float>(), nullptr, 0, 0, deV.as<float>(), p, (int)K, KP);
+    float* dlogVraw = C->as<float>(B::LVRAW);
+    float* deV = C->as<float>(B::EV);
+    float* dZj = C->as<float>(B::ZJ); float* dZj3a = C->as<float>(B::ZJ3A); float* dZj3b = C->as<float>(B::ZJ3B);
+    float* dOutJ = C->as<float>(B::OUTJ);
+
+    ORI_CUDA(cudaMemcpyAsync(dlogVraw, logV, sizeof(float) * p * K, cudaMemcpyHostToDevice, st));
+    k_exp_pad<<<cdiv(p * KP, 256), 256, 0, st>>>(dlogVraw, nullptr, 0, 0, deV, p, (int)K, KP);
     ORI_TRY(check_launch("k_exp_pad"));
-    ORI_CUDA(cudaMemsetAsync(dZj.p, 0, sizeof(float) * 2 * p * KP, st));
-    ORI_CUDA(cudaMemsetAsync(dZj3a.p, 0, sizeof(float) * 2 * p * KP, st));
-    ORI_CUDA(cudaMemsetAsync(dZj3b.p, 0, sizeof(float) * 2 * p * KP, st));
-
-    cudaEvent_t done[3];  // [0],[1]: last work on each stream; [2]: gene-side operands ready
-    for (int b = 0; b < 3; ++b) ORI_CUDA(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
-    struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 3; ++i) cudaEventDestroy(e[i]); } } evg{done};
-    ORI_CUDA(cudaEventRecord(done[2], st));
-    ORI_CUDA(cudaStreamWaitEvent(st2, done[2], 0));
+    ORI_CUDA(cudaMemsetAsync(dZj, 0, sizeof(float) * 2 * p * KP, st));
+    ORI_CUDA(cudaMemsetAsync(dZj3a, 0, sizeof(float) * 2 * p * KP, st));
+    ORI_CUDA(cudaMemsetAsync(dZj3b, 0, sizeof(float) * 2 * p * KP, st));
+    // [0],[1]: last work on each stream; [2]: gene-side operands ready
+    ORI_CUDA(cudaEventRecord(C->ev[2], st));
+    ORI_CUDA(cudaStreamWaitEvent(st2, C->ev[2], 0));
 
     ori_problem_t P;
     memset(&P, 0, sizeof(P));
     P.p = (int)p; P.K = (int)K; P.KP = KP; P.ldx = ldx;
-    P.eV = deV.as<float>(); P.V_hat = deV.as<float>();
-    P.red64 = dDummy64.as<double>();
+    P.eV = deV; P.V_hat = deV;
+    P.red64 = C->as<double>(B::D64);
+
+    // gene sums of one slab (zigap.py:94): both streams add into the same accumulators with atomics
+    auto genes = [&](cudaStream_t s) -> int {
+        if (!tc_eligible(&P)) return launch_pass_genes_simt(&P, 0, s);
+        ORI_TRY(launch_tc_prep_rows(&P, 0, s));
+        return launch_pass_genes_tc(&P, 0, s);
+    };
+    auto rows = [&](cudaStream_t s) -> int {
+        if (!tc_eligible(&P)) return launch_pass_rows_simt(&P, 0, s);
+        ORI_TRY(launch_tc_prep_genes(&P, s));
+        return launch_pass_rows_tc(&P, 0, s);
+    };
 
     int b = 0;
     for (int64_t r0 = 0; r0 < n; r0 += slab, b ^= (nbuf - 1)) {
-        const int64_t rows = (n - r0 < slab) ? n - r0 : slab;
+        const int64_t nr = (n - r0 < slab) ? n - r0 : slab;
         cudaStream_t s = b ? st2 : st;
-        float* x = dX[b].as<float>();
-        ORI_CUDA(cudaMemcpy2DAsync(x, sizeof(float) * ldx, X + r0 * p, sizeof(float) * p, sizeof(float) * p, rows, cudaMemcpyHostToDevice, s));
-        if (D) ORI_CUDA(cudaMemcpy2DAsync(dD[b].p, sizeof(float) * ldx, D + r0 * p, sizeof(float) * p, sizeof(float) * p, rows, cudaMemcpyHostToDevice, s));
-        ORI_CUDA(cudaMemcpyAsync(dlUs[b].p, logU + r0 * K, sizeof(float) * rows * K, cudaMemcpyHostToDevice, s));
-        k_exp_pad<<<cdiv(rows * KP, 256), 256, 0, s>>>(dlUs[b].as<float>(), nullptr, 0, 0, deU[b].as<float>(), rows, (int)K, KP);
+        float* x = C->as<float>(B::X0 + b);
+        float* dD = D ? C->as<float>(B::D0 + b) : nullptr;
+        float* dlUs = C->as<float>(B::LUS0 + b);
+        float* deU = C->as<float>(B::EU0 + b); float* deUw = C->as<float>(B::EUW0 + b); float* deUl = C->as<float>(B::EUL0 + b);
+        float* dZi = C->as<float>(B::ZI0 + b); float* dOutI = C->as<float>(B::OI0 + b);
+        ORI_CUDA(cudaMemcpy2DAsync(x, sizeof(float) * ldx, X + r0 * p, sizeof(float) * p, sizeof(float) * p, nr, cudaMemcpyHostToDevice, s));
+        if (D) ORI_CUDA(cudaMemcpy2DAsync(dD, sizeof(float) * ldx, D + r0 * p, sizeof(float) * p, sizeof(float) * p, nr, cudaMemcpyHostToDevice, s));
+        ORI_CUDA(cudaMemcpyAsync(dlUs, logU + r0 * K, sizeof(float) * nr * K, cudaMemcpyHostToDevice, s));
+        k_exp_pad<<<cdiv(nr * KP, 256), 256, 0, s>>>(dlUs, nullptr, 0, 0, deU, nr, (int)K, KP);
         if (D && quirk)   // zigap.py:94: weight of cell i for latent k is D_hat[i, k]
-            k_exp_pad<<<cdiv(rows * KP, 256), 256, 0, s>>>(dlUs[b].as<float>(), dD[b].as<float>(), ldx, 0, deUw[b].as<float>(), rows, (int)K, KP);
+            k_exp_pad<<<cdiv(nr * KP, 256), 256, 0, s>>>(dlUs, dD, ldx, 0, deUw, nr, (int)K, KP);
         if (Z3_out)
-            k_exp_pad<<<cdiv(rows * KP, 256), 256, 0, s>>>(dlUs[b].as<float>(), nullptr, 0, 1, deUl[b].as<float>(), rows, (int)K, KP);
+            k_exp_pad<<<cdiv(nr * KP, 256), 256, 0, s>>>(dlUs, nullptr, 0, 1, deUl, nr, (int)K, KP);
         const float* xq = x;  // X for the quirk gene sums (unweighted)
         if (D) {              // X*D in place of X for everything weighted by D_hat[i, j]
             if (quirk) {      // keep X: write X*D into the D buffer
-                k_mul<<<cdiv(rows * ldx, 256), 256, 0, s>>>(x, dD[b].as<float>(), dD[b].as<float>(), rows * ldx);
-                x = dD[b].as<float>();
+                k_mul<<<cdiv(nr * ldx, 256), 256, 0, s>>>(x, dD, dD, nr * ldx);
+                x = dD;
             } else {
-                k_mul<<<cdiv(rows * ldx, 256), 256, 0, s>>>(x, dD[b].as<float>(), x, rows * ldx);
+                k_mul<<<cdiv(nr * ldx, 256), 256, 0, s>>>(x, dD, x, nr * ldx);
                 xq = x;
             }
         }
         ORI_TRY(check_launch("operator prologue"));
-        ORI_CUDA(cudaMemsetAsync(dZi[b].p, 0, sizeof(float) * rows * KP, s));
-        P.n_rows = rows; P.n_total = n; P.flags = 0;
-        P.eU[0] = deU[b].as<float>(); P.U_hat[0] = deU[b].as<float>(); P.U_hat[1] = deU[b].as<float>();
-        P.Zi = dZi[b].as<float>();
+        ORI_CUDA(cudaMemsetAsync(dZi, 0, sizeof(float) * nr * KP, s));
+        P.n_rows = nr; P.n_total = n; P.flags = 0;
+        P.eU[0] = deU; P.U_hat[0] = deU; P.U_hat[1] = deU;
+        P.Zi = dZi;
+        P.tc_ws = tensor ? C->as<float>(B::WS0 + b) : nullptr;
+        P.tc_ws_floats = tensor ? (int64_t)ws_floats : 0;
         // row sums (zigap.py:93)
         P.X = x;
-        ORI_TRY(launch_pass_rows_simt(&P, 0, s));
-        k_scale_unpad<<<cdiv(rows * K, 256), 256, 0, s>>>(dZi[b].as<float>(), deU[b].as<float>(), nullptr, nullptr, dOutI[b].as<float>(), rows, (int)K, KP);
-        ORI_CUDA(cudaMemcpyAsync(Zi_out + r0 * K, dOutI[b].p, sizeof(float) * rows * K, cudaMemcpyDeviceToHost, s));
-        // gene sums (zigap.py:94): both streams add into the same accumulators with atomics
-        if (D && quirk) { P.X = xq; P.flags = ORI_F_QUIRK; P.eUw = deUw[b].as<float>(); }
-        P.red32 = dZj.as<float>();
-        ORI_TRY(launch_pass_genes_simt(&P, 0, s));
+        (tc_eligible(&P) ? C->tensor_slabs : C->simt_slabs) += 1;
+        ORI_TRY(rows(s));
+        k_scale_unpad<<<cdiv(nr * K, 256), 256, 0, s>>>(dZi, deU, nullptr, nullptr, dOutI, nr, (int)K, KP);
+        ORI_CUDA(cudaMemcpyAsync(Zi_out + r0 * K, dOutI, sizeof(float) * nr * K, cudaMemcpyDeviceToHost, s));
+        // gene sums (zigap.py:94)
+        if (D && quirk) { P.X = xq; P.flags = ORI_F_QUIRK; P.eUw = deUw; }
+        P.red32 = dZj;
+        ORI_TRY(genes(s));
         if (Z3_out) {  // zigap.py:95 = eV * (R_D^T (eU*logU)) + logV * [eV * (R_D^T eU)]
-            P.X = x; P.flags = ORI_F_QUIRK; P.eUw = deUl[b].as<float>(); P.red32 = dZj3a.as<float>();
-            ORI_TRY(launch_pass_genes_simt(&P, 0, s));
-            if (D && quirk) { P.flags = 0; P.red32 = dZj3b.as<float>(); ORI_TRY(launch_pass_genes_simt(&P, 0, s)); }
+            P.X = x; P.flags = ORI_F_QUIRK; P.eUw = deUl; P.red32 = dZj3a;
+            ORI_TRY(genes(s));
+            if (D && quirk) { P.flags = 0; P.red32 = dZj3b; ORI_TRY(genes(s)); }
         }
-        ORI_CUDA(cudaEventRecord(done[b], s));
+        ORI_CUDA(cudaEventRecord(C->ev[b], s));
     }
-    ORI_CUDA(cudaStreamWaitEvent(st, done[0], 0));
-    ORI_CUDA(cudaStreamWaitEvent(st, done[1 % nbuf], 0));
-    k_scale_unpad<<<cdiv(p * K, 256), 256, 0, st>>>(dZj.as<float>(), deV.as<float>(), nullptr, nullptr, dOutJ.as<float>(), p, (int)K, KP);
-    ORI_CUDA(cudaMemcpyAsync(Zj_out, dOutJ.p, sizeof(float) * p * K, cudaMemcpyDeviceToHost, st));
+    ORI_CUDA(cudaStreamWaitEvent(st, C->ev[0], 0));
+    ORI_CUDA(cudaStreamWaitEvent(st, C->ev[1 % nbuf], 0));
+    k_scale_unpad<<<cdiv(p * K, 256), 256, 0, st>>>(dZj, deV, nullptr, nullptr, dOutJ, p, (int)K, KP);
+    ORI_CUDA(cudaMemcpyAsync(Zj_out, dOutJ, sizeof(float) * p * K, cudaMemcpyDeviceToHost, st));
     if (Z3_out) {
-        const float* plain = (D && quirk) ? dZj3b.as<float>() : dZj.as<float>();
-        k_scale_unpad<<<cdiv(p * K, 256), 256, 0, st>>>(dZj3a.as<float>(), deV.as<float>(), plain, dlogVraw.as<float>(), dOutJ.as<float>(), p, (int)K, KP);
-        ORI_CUDA(cudaMemcpyAsync(Z3_out, dOutJ.p, sizeof(float) * p * K, cudaMemcpyDeviceToHost, st));
+        const float* plain = (D && quirk) ? dZj3b : dZj;
+        k_scale_unpad<<<cdiv(p * K, 256), 256, 0, st>>>(dZj3a, deV, plain, dlogVraw, dOutJ, p, (int)K, KP);
+        ORI_CUDA(cudaMemcpyAsync(Z3_out, dOutJ, sizeof(float) * p * K, cudaMemcpyDeviceToHost, st));
     }
     ORI_TRY(check_launch("operator epilogue"));
     ORI_CUDA(cudaStreamSynchronize(st2));
@@ -461,19 +522,81 @@ static int z_operator_host(float* Zi_out, float* Zj_out, float* Z3_out, const fl
     return ORI_OK;
 }
 
+static ori_ctx* default_ctx(int* rc) {
+    static std::mutex mu;
+    static ori_ctx* ctx = nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    *rc = ORI_OK;
+    if (!ctx) {
+        ctx = new ori_ctx();
+        *rc = ctx->init();
+        if (*rc != ORI_OK) { ctx->release(); delete ctx; ctx = nullptr; }
+    }
+    return ctx;
+}
+
 extern "C" {
+
+int ori_ctx_create(ori_ctx_t** out, int64_t slab_rows) {
+    if (!out || slab_rows < 0) return set_error(ORI_EINVAL, "ori_ctx_create: bad argument");
+    ori_ctx* c = new ori_ctx();
+    const int rc = c->init();
+    if (rc != ORI_OK) { c->release(); delete c; *out = nullptr; return rc; }
+    c->slab_rows = slab_rows;
+    *out = c;
+    return ORI_OK;
+}
+
+int ori_ctx_destroy(ori_ctx_t* ctx) {
+    if (!ctx) return ORI_OK;
+    ctx->release();
+    delete ctx;
+    return ORI_OK;
+}
+
+int ori_ctx_stats(ori_ctx_t* ctx, unsigned long long* calls, unsigned long long* device_allocations,
+                  unsigned long long* tensor_slabs, unsigned long long* simt_slabs) {
+    int rc = ORI_OK;
+    ori_ctx* c = ctx ? ctx : default_ctx(&rc);
+    if (!c) return rc;
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (calls) *calls = c->calls;
+    if (device_allocations) *device_allocations = c->allocs;
+    if (tensor_slabs) *tensor_slabs = c->tensor_slabs;
+    if (simt_slabs) *simt_slabs = c->simt_slabs;
+    return ORI_OK;
+}
+
+int ori_zigap_compute_Z_q_expectations_ctx(ori_ctx_t* ctx, float* DZ_hat_i, float* DZ_hat_j, float* DZ_exp_logsum_hat,
+                                           const float* log_U_hat, const float* log_V_hat,
+                                           const float* D_hat, const float* X,
+                                           int64_t n, int64_t p, int64_t K, int quirk) {
+    if (!D_hat) return set_error(ORI_EINVAL, "D_hat is NULL");
+    return z_operator_ctx(ctx, DZ_hat_i, DZ_hat_j, DZ_exp_logsum_hat, log_U_hat, log_V_hat, D_hat, X, n, p, K, quirk);
+}
+
+int ori_gap_compute_Z_q_expectations_ctx(ori_ctx_t* ctx, float* Z_hat_i, float* Z_hat_j, const float* log_U_hat,
+                                         const float* log_V_hat, const float* X, int64_t n, int64_t p, int64_t K) {
+    return z_operator_ctx(ctx, Z_hat_i, Z_hat_j, nullptr, log_U_hat, log_V_hat, nullptr, X, n, p, K, 0);
+}
 
 int ori_zigap_compute_Z_q_expectations_host(float* DZ_hat_i, float* DZ_hat_j, float* DZ_exp_logsum_hat,
                                             const float* log_U_hat, const float* log_V_hat,
                                             const float* D_hat, const float* X,
                                             int64_t n, int64_t p, int64_t K, int quirk) {
     if (!D_hat) return set_error(ORI_EINVAL, "D_hat is NULL");
-    return z_operator_host(DZ_hat_i, DZ_hat_j, DZ_exp_logsum_hat, log_U_hat, log_V_hat, D_hat, X, n, p, K, quirk);
+    int rc;
+    ori_ctx* c = default_ctx(&rc);
+    if (!c) return rc;
+    return z_operator_ctx(c, DZ_hat_i, DZ_hat_j, DZ_exp_logsum_hat, log_U_hat, log_V_hat, D_hat, X, n, p, K, quirk);
 }
 
 int ori_gap_compute_Z_q_expectations_host(float* Z_hat_i, float* Z_hat_j, const float* log_U_hat,
                                           const float* log_V_hat, const float* X, int64_t n, int64_t p, int64_t K) {
-    return z_operator_host(Z_hat_i, Z_hat_j, nullptr, log_U_hat, log_V_hat, nullptr, X, n, p, K, 0);
+    int rc;
+    ori_ctx* c = default_ctx(&rc);
+    if (!c) return rc;
+    return z_operator_ctx(c, Z_hat_i, Z_hat_j, nullptr, log_U_hat, log_V_hat, nullptr, X, n, p, K, 0);
 }
 
 }  // extern "C"

@@ -142,7 +142,8 @@ def test_host_streamed_resume_from_mid_run_state(cuda_lib):
     for _ in range(3):
         m.step()
     h3 = HostStreamedCAVI(Xh, K, m.state_dict(), dropout=True, slab_rows=64)
-    h3.step()
+    e3 = h3.step()                                           # = the ELBO of the state it started from
+    assert abs(e3 - m.elbo()) < 2e-6 * abs(e3), (e3, m.elbo())
     c = h3.state_dict()
     for k in PARAMS:
         assert relerr(c[k], a[k]) < 2e-5, k

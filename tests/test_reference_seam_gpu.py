@@ -8,7 +8,8 @@ arrays with the O(n p K) loop on the B200, and is stepped against its un-patched
 constructed state.
 
 Tolerance: the reference accumulates the latent-count sums sequentially in float32; the device sums them in tiles.
-Over 5 steps the parameters agree to 2e-4 relative (floor 1e-6 max), D_hat to 2e-5 absolute.
+Over 5 steps the parameters agree to 2e-4 relative (floor 1e-6 max), D_hat to 2e-5 absolute on the CUDA-core kernels
+(small problems); a slab of >= 2^21 entries runs the tcgen05 kernels with TF32 operands: 2e-3 / 2e-4 after 2 steps.
 """
 import ctypes
 import warnings
@@ -24,9 +25,17 @@ pytestmark = pytest.mark.gpu
 def _stubs(lib):
     fp = ctypes.c_void_p
 
-    def ptr(a):
-        if a.dtype != np.float32 or not a.flags.c_contiguous:      # the numba signature raises TypeError too
-            raise TypeError('C-contiguous float32 array expected (zigap.py:79)')
+    keep = []
+
+    def ptr(a, out=False):
+        if a.dtype != np.float32 or a.ndim != 2:                   # the numba signature f4[:, :] raises TypeError too
+            raise TypeError('2-D float32 array expected (zigap.py:79)')
+        if not a.flags.c_contiguous:
+            # f4[:, :] accepts any layout, and the reference does pass one: X[:] comes out of a DataFrame column-major
+            # (cmatrix.py:31-37) and .astype keeps that order (zigap.py:112).  The C ABI takes row-major arrays.
+            assert not out, 'outputs are np.empty arrays (zigap.py:102-104): always C-contiguous'
+            a = np.ascontiguousarray(a)
+            keep.append(a)
         return fp(a.ctypes.data)
 
     def check(rc):
@@ -42,15 +51,17 @@ def _stubs(lib):
         K = log_U_hat.shape[1]
         calls['zigap'] += 1
         check(lib.ori_zigap_compute_Z_q_expectations_host(
-            ptr(DZ_hat_i), ptr(DZ_hat_j), ptr(DZ_exp_logsum_hat), ptr(log_U_hat), ptr(log_V_hat), ptr(D_hat), ptr(X),
-            n, p, K, 1))            # 1 = keep the D_hat[i, k] indexing of zigap.py:94
+            ptr(DZ_hat_i, True), ptr(DZ_hat_j, True), ptr(DZ_exp_logsum_hat, True), ptr(log_U_hat), ptr(log_V_hat),
+            ptr(D_hat), ptr(X), n, p, K, 1))            # 1 = keep the D_hat[i, k] indexing of zigap.py:94
+        keep.clear()
 
     def gap_z(Z_hat_i, Z_hat_j, log_U_hat, log_V_hat, X):                                  # gap.py:68
         n, p = X.shape
         K = log_U_hat.shape[1]
         calls['gap'] += 1
-        check(lib.ori_gap_compute_Z_q_expectations_host(ptr(Z_hat_i), ptr(Z_hat_j), ptr(log_U_hat), ptr(log_V_hat),
-                                                        ptr(X), n, p, K))
+        check(lib.ori_gap_compute_Z_q_expectations_host(ptr(Z_hat_i, True), ptr(Z_hat_j, True), ptr(log_U_hat),
+                                                        ptr(log_V_hat), ptr(X), n, p, K))
+        keep.clear()
     return zigap_z, gap_z, calls
 
 
@@ -88,10 +99,11 @@ def test_reference_step_with_the_b200_operator(cuda_lib, model_name, shape):
                 cls.compute_Z_q_expectations = original
         assert calls['zigap' if model_name == 'ZIGaP' else 'gap'] == steps
         names = ('a1', 'a2', 'b1', 'b2', 'alpha1', 'alpha2', 'beta1', 'beta2') + (('pi_d',) if model_name == 'ZIGaP' else ())
+        tensor = n * p >= (1 << 21)          # slabs of this size run the tcgen05 kernels: TF32 operands (measured 3.5e-4)
         for k in names:
             e = relerr(getattr(ours, k)[:], getattr(twin, k)[:])
-            assert e < 2e-4, (model_name, k, e)
+            assert e < (2e-3 if tensor else 2e-4), (model_name, k, e)
         if model_name == 'ZIGaP':
-            assert np.max(np.abs(ours.D_hat - twin.D_hat)) < 2e-5
+            assert np.max(np.abs(ours.D_hat - twin.D_hat)) < (2e-4 if tensor else 2e-5)
     finally:
         refshim.release_reference()

@@ -102,3 +102,68 @@ def test_bad_arguments_raise(cuda_lib):
     with pytest.raises(_lib.OrianaB200Error):   # quirk needs p >= K
         z_op(cuda_lib, np.zeros((2, 5), np.float32), np.zeros((3, 5), np.float32), np.zeros((2, 3), np.float32),
              np.ones((2, 3), np.float32), quirk=True)
+
+
+def _stats(lib, ctx=None):
+    c = [ctypes.c_uint64(0) for _ in range(4)]
+    from oriana_b200 import _lib
+    _lib.check(lib.ori_ctx_stats(ctx, *[ctypes.byref(x) for x in c]))
+    return dict(zip(('calls', 'allocs', 'tensor_slabs', 'simt_slabs'), (int(x.value) for x in c)))
+
+
+@pytest.mark.parametrize('quirk', [True, False])
+def test_tensor_sized_slabs_take_the_tcgen05_passes(cuda_lib, quirk):
+    """Slabs of >= 2^21 entries go through the tcgen05 / TMA kernels (TF32 operands: 1e-3 against the sequential float32
+    loop of the reference, restated in C), through an explicit context with three ragged slabs; a second call of the
+    same shape allocates nothing and gives the same answer up to the order of the float atomics."""
+    from oracle import zloop
+    from oriana_b200 import _lib
+    n, p, K = 2900, 1500, 10
+    rng = np.random.default_rng(5)
+    lU = rng.normal(-0.5, 1.0, (n, K)).astype(np.float32)
+    lV = rng.normal(-0.5, 1.0, (p, K)).astype(np.float32)
+    X = (rng.poisson(3.0, (n, p)) * (rng.random((n, p)) < 0.6)).astype(np.float32)
+    D = np.where(X != 0, 1.0, rng.random((n, p))).astype(np.float32)
+    ctx = ctypes.c_void_p()
+    _lib.check(cuda_lib.ori_ctx_create(ctypes.byref(ctx), 1408))          # 1408 x 1500 = 2.1e6 entries per slab
+    try:
+        outs = []
+        for rep in range(2):
+            Zi = np.full((n, K), np.nan, np.float32); Zj = np.full((p, K), np.nan, np.float32)
+            Z3 = np.full((p, K), np.nan, np.float32)
+            _lib.check(cuda_lib.ori_zigap_compute_Z_q_expectations_ctx(ctx, _ptr(Zi), _ptr(Zj), _ptr(Z3), _ptr(lU), _ptr(lV),
+                                                                       _ptr(D), _ptr(X), n, p, K, int(quirk)))
+            outs.append((Zi, Zj, Z3))
+            st = _stats(cuda_lib, ctx)
+            if rep == 0:
+                first = st
+        assert first['tensor_slabs'] == 3 and first['simt_slabs'] == 0 and first['allocs'] > 0
+        assert st['allocs'] == first['allocs'] and st['calls'] == 2 and st['tensor_slabs'] == 6   # nothing allocated again
+        rZi, rZj, rZ3 = zloop.zigap_z(lU, lV, D, X, quirk=quirk, third=True)
+        Zi, Zj, Z3 = outs[1]
+        assert relerr(Zi, rZi) < 1e-3 and relerr(Zj, rZj) < 1e-3, (relerr(Zi, rZi), relerr(Zj, rZj))
+        assert np.max(np.abs(Z3 - rZ3)) < 1e-3 * np.max(np.abs(rZ3))
+        for a, b in zip(outs[0], outs[1]):
+            assert relerr(a, b) < 1e-5
+        gZi = np.full((n, K), np.nan, np.float32); gZj = np.full((p, K), np.nan, np.float32)
+        _lib.check(cuda_lib.ori_gap_compute_Z_q_expectations_ctx(ctx, _ptr(gZi), _ptr(gZj), _ptr(lU), _ptr(lV), _ptr(X), n, p, K))
+        rZi, rZj = zloop.gap_z(lU, lV, X)
+        assert relerr(gZi, rZi) < 1e-3 and relerr(gZj, rZj) < 1e-3
+        assert _stats(cuda_lib, ctx)['allocs'] == first['allocs']                  # GaP needs a subset of the buffers
+    finally:
+        _lib.check(cuda_lib.ori_ctx_destroy(ctx))
+
+
+def test_default_context_allocates_once(cuda_lib):
+    """The *_host entry points (what INTEGRATION.md binds) keep one process-wide context: repeated calls of a shape no
+    larger than any before allocate no device memory and create no streams."""
+    rng = np.random.default_rng(1)
+    n, p, K = 300, 200, 5
+    lU = rng.normal(-0.5, 1.0, (n, K)).astype(np.float32); lV = rng.normal(-0.5, 1.0, (p, K)).astype(np.float32)
+    X = rng.poisson(2.0, (n, p)).astype(np.float32)
+    z_op(cuda_lib, lU, lV, X)
+    a0 = _stats(cuda_lib)
+    for _ in range(3):
+        z_op(cuda_lib, lU, lV, X)
+    a1 = _stats(cuda_lib)
+    assert a1['allocs'] == a0['allocs'] and a1['calls'] == a0['calls'] + 3

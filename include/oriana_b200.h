@@ -47,6 +47,11 @@ extern "C" {
                                  instead of ori_problem_t::iter, so that one captured CUDA graph of a whole
                                  step can be replayed for every iteration                                   */
 
+#define ORI_F_PRECISE 64u     /* tensor path only (K <= 32): the accumulating contractions R.eV, D.V_hat and their transposes
+                                 take R, D_hat and the factor operands split hi/lo (tf32 + one bf16 chain for the cross terms)
+                                 like den and U.V^T: every sum fp32-grade (~2^-21) instead of TF32-grade; about half the rate.
+                                 K > 32 with this flag runs the CUDA-core kernels                                           */
+
 /* modes of ori_mstep */
 #define ORI_M_STEP 0          /* regular end of iteration t+1: finalise ELBO(t), pi(t); M-step; next lp   */
 #define ORI_M_INIT 1          /* after ori_init_expectations: M-step on the initial expectations          */

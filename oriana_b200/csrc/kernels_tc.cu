@@ -102,17 +102,23 @@ constexpr int TC_THREADS = 64 + 32 * NEW + (NISS == 2 ? 32 : 0);
                            //    sweep entries.  0 (default): 64-wide tiles, 2 TMEM stages, two groups per warp and tile.
 #endif
 
-template <int KP, bool PAIR>
+// PRECISE (KP = 32): the accumulating contractions R . S1 and D . S2 are split-precision too -- R, D and the factor operands
+// as tf32 hi plus a bf16 [hi | lo] . [lo | hi] chain for the two cross terms, like den / uv -- so every sum is fp32-grade
+// (~2^-21) instead of TF32-grade (~2^-12 per term).  The tile keeps R16 / D16 (the packed bf16 pairs) beside R / D in TMEM,
+// which halves the sweep width (32) to stay inside 512 columns.
+template <int KP, bool PAIR, bool PRECISE = false>
 struct Cfg {
     static_assert(KP == 32 || KP == 64, "tensor path: KP is 32 or 64");
+    static_assert(!PRECISE || KP == 32, "the fp32-grade plan exists for KP = 32");
     static constexpr int NCTA = PAIR ? 2 : 1;
-    static constexpr bool DEEP = (ORI_TC_DEEP != 0) && KP == 32;
-    static constexpr int SW = DEEP ? 32 : 2048 / KP;      // sweep entries per tile: 32 (deep plan, KP 64) or 64 (KP 32, round-1 plan)
+    static constexpr bool DEEP = (ORI_TC_DEEP != 0) && KP == 32 && !PRECISE;
+    static constexpr int SW = (DEEP || PRECISE) ? 32 : 2048 / KP;   // sweep entries per tile
     static constexpr int NS = DEEP ? 4 : 2;               // TMEM stages of [den/R | uv/D]
     static constexpr int KB = KP / 32;                    // 128-byte K blocks of a K-major row
     static constexpr int KST = DEEP ? 4 : (PAIR ? 3 : 2); // ring depths
     static constexpr int TST = DEEP ? 4 : (PAIR ? 3 : 2);
     static constexpr int XST = DEEP ? (PAIR ? 8 : 6) : (PAIR ? 4 : 3);
+    static constexpr int NTA = PRECISE ? 4 : 2;           // transposed operand arrays per stage: e, E [, bf16 pairs of e, of E]
     // K-major operand array of one tile: [KB blocks][SW / NCTA sweep rows][32 floats], 128-byte swizzled
     static constexpr uint32_t K_BLK = (SW / NCTA) * 128;
     static constexpr uint32_t K_ARR = KB * K_BLK;
@@ -120,7 +126,7 @@ struct Cfg {
     // transposed operand array of one tile: [SW / 32 chunks][KP / NCTA latent rows][32 sweep columns]
     static constexpr uint32_t T_CHUNK = (KP / NCTA) * 128;
     static constexpr uint32_t T_ARR = (SW / 32) * T_CHUNK;
-    static constexpr uint32_t T_STAGE = 2 * T_ARR;        // transposed e and transposed E
+    static constexpr uint32_t T_STAGE = NTA * T_ARR;      // transposed e and transposed E (+ their bf16 [lo | hi] pairs)
     static constexpr uint32_t X_STAGE = TC_OWN * SW * 4;  // X tile
     static constexpr uint32_t LP_STAGE = 3 * SW * 4;      // lp2[SW] | floor[SW] | (1-pi)/pi [SW]
     static constexpr uint32_t OFF_K = 0;
@@ -130,7 +136,9 @@ struct Cfg {
     static constexpr uint32_t OFF_BAR = OFF_LP + XST * LP_STAGE;
     static constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;   // + barriers + alignment slack
     // TMEM columns: NS stages of [den/R SW | uv/D SW], accumulators [acc1 KP | acc2 KP], own operands 4 x KP
-    static constexpr uint32_t TM_STAGE = 2 * SW;
+    // stage: [den/R SW | uv/D SW], or with PRECISE [den/R SW | R16 SW | uv/D SW | D16 SW]
+    static constexpr uint32_t TM_UV = PRECISE ? 2 * SW : SW;
+    static constexpr uint32_t TM_STAGE = PRECISE ? 4 * SW : 2 * SW;
     static constexpr uint32_t TM_ACC = NS * TM_STAGE;
     static constexpr uint32_t TM_A = TM_ACC + 2 * KP;
     static constexpr uint32_t TM_COLS = 512;
@@ -239,7 +247,7 @@ struct TileIter {
     }
 };
 
-template <bool GENES, bool DROPOUT, bool ELBO, bool PAIR, int KP>
+template <bool GENES, bool DROPOUT, bool ELBO, bool PAIR, int KP, bool PRECISE>
 #if ORI_TC_NEW == 16
 __global__ void __maxnreg__(96)
 #else
@@ -247,8 +255,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #endif
 k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
 {
-    using C = Cfg<KP, PAIR>;
+    using C = Cfg<KP, PAIR, PRECISE>;
     constexpr int NCTA = C::NCTA, SW = C::SW, NS = C::NS;
+    constexpr uint32_t TM_UV = C::TM_UV;
     constexpr int KST = C::KST, TST = C::TST, XST = C::XST;
     constexpr uint32_t K_STAGE = C::K_STAGE, T_STAGE = C::T_STAGE, X_STAGE = C::X_STAGE, LP_STAGE = C::LP_STAGE;
     constexpr uint32_t OFF_K = C::OFF_K, OFF_T = C::OFF_T, OFF_X = C::OFF_X, OFF_LP = C::OFF_LP, OFF_BAR = C::OFF_BAR;
@@ -305,16 +314,20 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 uint64_t* bar = &bars[B_TFULL + s];
                 const int sw0 = it_.t * SW;
                 constexpr int NTL = ORI_KO_TMA ? 1 : NT;
-                if (rank == 0) mbar_expect_tx(bar, NTL * C::T_ARR * NCTA);      // the whole pair's bytes land on the leader's barrier
+                constexpr int NTP = PRECISE ? 2 : 1;                            // + the bf16 [lo | hi] pairs of each array
+                if (rank == 0) mbar_expect_tx(bar, NTP * NTL * C::T_ARR * NCTA);      // the whole pair's bytes land on the leader's barrier
 #pragma unroll
-                for (int q = 0; q < NTL; ++q)
+                for (int h = 0; h < NTP; ++h)
 #pragma unroll
-                    for (int c = 0; c < SW / 32; ++c) {
-                        uint8_t* dst = st + q * C::T_ARR + c * C::T_CHUNK;
-                        const int row = q * KP + (KP / NCTA) * rank;            // this CTA's latent rows of array q
-                        if (PAIR) tma_load_2d_pair(dst, &maps.swT, bar, sw0 + 32 * c, row, L2_EVICT_LAST);
-                        else tma_load_2d_hint(dst, &maps.swT, bar, sw0 + 32 * c, row, L2_EVICT_LAST);
-                    }
+                    for (int q0 = 0; q0 < NTL; ++q0)
+#pragma unroll
+                        for (int c = 0; c < SW / 32; ++c) {
+                            const int q = 2 * h + q0;                               // slot in the stage = array in global memory
+                            uint8_t* dst = st + q * C::T_ARR + c * C::T_CHUNK;
+                            const int row = q * KP + (KP / NCTA) * rank;            // this CTA's latent rows of array q
+                            if (PAIR) tma_load_2d_pair(dst, &maps.swT, bar, sw0 + 32 * c, row, L2_EVICT_LAST);
+                            else tma_load_2d_hint(dst, &maps.swT, bar, sw0 + 32 * c, row, L2_EVICT_LAST);
+                        }
             }
             __syncwarp();
             ++nt; it_.next(a);
@@ -415,9 +428,23 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                             mma(tmem + TM_ACC, tmem + s * TM_STAGE + ks * 8,
                                 td + (uint64_t)(((ks >> 2) * C::T_CHUNK + (ks & 3) * 32) >> 4), idescP, !(first && ks == 0));
                         if (do_uv)
-                            mma(tmem + TM_ACC + KP, tmem + s * TM_STAGE + SW + ks * 8,
+                            mma(tmem + TM_ACC + KP, tmem + s * TM_STAGE + TM_UV + ks * 8,
                                 td + (uint64_t)((C::T_ARR + (ks >> 2) * C::T_CHUNK + (ks & 3) * 32) >> 4), idescP,
                                 !(first && ks == 0));
+                    }
+                    if (PRECISE) {
+                        // cross terms hi.lo + lo.hi of both accumulations: A = the bf16 pairs [hi | lo] of R / D beside them in
+                        // TMEM (SW words = 2 SW bf16), B = the bf16 pairs [lo | hi] of the transposed operands (slots 2, 3)
+                        constexpr uint32_t idescP16 = make_idesc_bf16(TC_OWN * NCTA, KP);
+#pragma unroll
+                        for (int ks = 0; ks < SW / 8; ++ks) {
+                            if (do_den)
+                                mma16(tmem + TM_ACC, tmem + s * TM_STAGE + SW + ks * 8,
+                                      td + (uint64_t)((2 * C::T_ARR + (ks >> 2) * C::T_CHUNK + (ks & 3) * 32) >> 4), idescP16, true);
+                            if (do_uv)
+                                mma16(tmem + TM_ACC + KP, tmem + s * TM_STAGE + TM_UV + SW + ks * 8,
+                                      td + (uint64_t)((3 * C::T_ARR + (ks >> 2) * C::T_CHUNK + (ks & 3) * 32) >> 4), idescP16, true);
+                        }
                     }
                     commit(&bars[B_TEMPTY + ts]);
                     if (last) commit(&bars[B_ACC_READY]);
@@ -463,8 +490,8 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                         ORI_CHAIN16(tmem + s * TM_STAGE, 1);
                     }
                     if (do_uv) {
-                        ORI_CHAIN(tmem + s * TM_STAGE + SW, 2, 2, true);
-                        ORI_CHAIN16(tmem + s * TM_STAGE + SW, 3);
+                        ORI_CHAIN(tmem + s * TM_STAGE + TM_UV, 2, 2, true);
+                        ORI_CHAIN16(tmem + s * TM_STAGE + TM_UV, 3);
                     }
 #undef ORI_CHAIN16
 #else
@@ -474,9 +501,9 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                         ORI_CHAIN(tmem + s * TM_STAGE, 1, 0, false);
                     }
                     if (do_uv) {
-                        ORI_CHAIN(tmem + s * TM_STAGE + SW, 2, 2, true);
-                        ORI_CHAIN(tmem + s * TM_STAGE + SW, 2, 3, false);
-                        ORI_CHAIN(tmem + s * TM_STAGE + SW, 3, 2, false);
+                        ORI_CHAIN(tmem + s * TM_STAGE + TM_UV, 2, 2, true);
+                        ORI_CHAIN(tmem + s * TM_STAGE + TM_UV, 2, 3, false);
+                        ORI_CHAIN(tmem + s * TM_STAGE + TM_UV, 3, 2, false);
                     }
 #endif
 #undef ORI_CHAIN
@@ -593,7 +620,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 c.lp_addr = sbase + OFF_LP + c.xs * LP_STAGE;
                 c.valid = (int)min((long long)SW, a.sw_total - (long long)t_ * SW);   // gene pass: real cells
                 c.slow = slow_item || (GENES && c.valid != SW);
-                c.tden = tlane + c.s * TM_STAGE;                                      // uv / D_hat: + SW
+                c.tden = tlane + c.s * TM_STAGE;                                      // uv / D_hat: + TM_UV
                 return c;
             };
             // X tile (and lp) visible to this thread; den / uv complete in TMEM
@@ -605,8 +632,21 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             auto ld_group = [&](const Tile& c, int g, int b) {
                 tmem_ld16(c.tden + colbase + g * 16, dr[b]);
 #if !ORI_KO_LDUV
-                if (DROPOUT) tmem_ld16(c.tden + SW + colbase + g * 16, ur[b]);
+                if (DROPOUT) tmem_ld16(c.tden + TM_UV + colbase + g * 16, ur[b]);
 #endif
+            };
+            // PRECISE: v -> tf32 hi (written where the MMA reads R / D) and the bf16 pairs of (hi, lo) of two neighbouring
+            // entries (written beside them): words 0..7 of a group = hi pairs, pk[8..15] = lo pairs
+            uint32_t pkr_h[8], pkr_l[8], pkd_h[8], pkd_l[8];
+            auto split_store = [&](uint32_t (&w)[16], uint32_t (&ph)[8], uint32_t (&pl)[8]) {
+#pragma unroll
+                for (int e = 0; e < 16; e += 2) {
+                    const float v0 = __uint_as_float(w[e]), v1 = __uint_as_float(w[e + 1]);
+                    const float h0 = __uint_as_float((w[e] + 0x1000u) & 0xffffe000u), h1 = __uint_as_float((w[e + 1] + 0x1000u) & 0xffffe000u);
+                    w[e] = __float_as_uint(h0); w[e + 1] = __float_as_uint(h1);
+                    ph[e >> 1] = pack_bf16x2(h0, h1);
+                    pl[e >> 1] = pack_bf16x2(v0 - h0, v1 - h1);
+                }
             };
             auto load_x = [&](const Tile& c, int g, int b) {
                 const int c0 = colbase + g * 16;
@@ -630,7 +670,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             auto slow_group = [&](const Tile& c, int g, int b, float& t_xl, float& t_ent) {
                 const int c0 = colbase + g * 16;
                 tmem_ld16(c.tden + c0, dr[b]);
-                if (DROPOUT) tmem_ld16(c.tden + SW + c0, ur[b]);
+                if (DROPOUT) tmem_ld16(c.tden + TM_UV + c0, ur[b]);
                 tmem_wait_ld();
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
@@ -646,10 +686,11 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                         tt = nz ? dg : 1.f + ex2_approx(e2);
                         const float r = rcp_approx(tt);
                         D = fmaxf(nz ? 1.f : r, fl);
-                        dr[b][e] = tf32_bias(xe * r);
-                        ur[b][e] = tf32_bias(D);
+                        dr[b][e] = PRECISE ? __float_as_uint(xe * r) : tf32_bias(xe * r);
+                        ur[b][e] = PRECISE ? __float_as_uint(D) : tf32_bias(D);
                     } else {
-                        dr[b][e] = tf32_bias(xe * rcp_approx(tt));
+                        const float R = xe * rcp_approx(tt);
+                        dr[b][e] = PRECISE ? __float_as_uint(R) : tf32_bias(R);
                     }
                     if (GENES && (c0 + e) < c.valid) {
                         if (DROPOUT) cs += D;
@@ -701,7 +742,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
 #if ORI_KO_BIAS
                     dr[b][e] = __float_as_uint(xe * r);
 #else
-                    dr[b][e] = tf32_bias(xe * r);                                 // R = X / den; 0 where X == 0
+                    dr[b][e] = PRECISE ? __float_as_uint(xe * r) : tf32_bias(xe * r);   // R = X / den; 0 where X == 0
 #endif
                     float D = 1.f;
                     if (DROPOUT) {
@@ -709,7 +750,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
 #if ORI_KO_BIAS
                         ur[b][e] = __float_as_uint(D);
 #else
-                        ur[b][e] = tf32_bias(D);
+                        ur[b][e] = PRECISE ? __float_as_uint(D) : tf32_bias(D);
 #endif
                     }
                     if (GENES) {
@@ -738,9 +779,20 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             };
 
             auto st_group = [&](const Tile& c, int g, int b) {
-                tmem_st16(c.tden + colbase + g * 16, dr[b]);
+                const int c0 = colbase + g * 16;
+                if (PRECISE) {
+                    split_store(dr[b], pkr_h, pkr_l);
+                    tmem_st8(c.tden + SW + (c0 >> 1), pkr_h);
+                    tmem_st8(c.tden + SW + SW / 2 + (c0 >> 1), pkr_l);
+                    if (DROPOUT) {
+                        split_store(ur[b], pkd_h, pkd_l);
+                        tmem_st8(c.tden + TM_UV + SW + (c0 >> 1), pkd_h);
+                        tmem_st8(c.tden + TM_UV + SW + SW / 2 + (c0 >> 1), pkd_l);
+                    }
+                }
+                tmem_st16(c.tden + c0, dr[b]);
 #if !ORI_KO_STD
-                if (DROPOUT) tmem_st16(c.tden + SW + colbase + g * 16, ur[b]);
+                if (DROPOUT) tmem_st16(c.tden + TM_UV + c0, ur[b]);
 #endif
             };
             // R / D_hat of the tile are in TMEM (after tcgen05.wait::st): P may run; the X stage may be refilled
@@ -916,9 +968,11 @@ k_tc_prep_K(const float* __restrict__ e, const float* __restrict__ E, float Esca
     }
 #endif
 }
-// transposed operand: out[k][i] = tf32(src[i][k]),  src [n x KP], out [KP x pad]; grid (pad / 32, KP / 32)
+// transposed operand: out[k][i] = tf32(src[i][k]),  src [n x KP], out [KP x pad]; grid (pad / 32, KP / 32).
+// out16 (PRECISE, else NULL): the bf16 pairs [lo | hi] of the same values, 32 words per block of 32 sweep entries:
+// word w < 16 = (lo[2w], lo[2w+1]), word w >= 16 = (hi[2(w-16)], hi[2(w-16)+1]); hi = tf32 round-to-nearest, lo = v - hi
 __global__ void __launch_bounds__(256)
-k_tc_prep_T(const float* __restrict__ src, float* __restrict__ out, long long n, long long pad, int KP)
+k_tc_prep_T(const float* __restrict__ src, float* __restrict__ out, uint32_t* __restrict__ out16, long long n, long long pad, int KP)
 {
     __shared__ float tile[32][33];
     const long long i0 = (long long)blockIdx.x * 32;
@@ -930,7 +984,15 @@ k_tc_prep_T(const float* __restrict__ src, float* __restrict__ out, long long n,
     __syncthreads();
     for (int k = threadIdx.y; k < 32; k += 8) {
         const long long i = i0 + threadIdx.x;
-        if (i < pad) out[(long long)(k0 + k) * pad + i] = to_tf32_rna(tile[threadIdx.x][k]);
+        if (i < pad) {
+            out[(long long)(k0 + k) * pad + i] = to_tf32_rna(tile[threadIdx.x][k]);
+            if (out16) {
+                const int w = threadIdx.x, e = 2 * (w & 15);
+                const float a = tile[e][k], b = tile[e + 1][k];
+                const float ha = to_tf32_rna(a), hb = to_tf32_rna(b);
+                out16[(long long)(k0 + k) * pad + i] = w < 16 ? pack_bf16x2(a - ha, b - hb) : pack_bf16x2(ha, hb);
+            }
+        }
     }
 }
 __global__ void k_tc_prep_lp(const float* __restrict__ lp, const float* __restrict__ fl, float* __restrict__ lp2w,
@@ -951,7 +1013,7 @@ static long long pad128(long long v) { return (v + 127) / 128 * 128; }
 
 long long tc_workspace_floats(long long n_rows, int p, int KP) {
     const long long np = pad128(n_rows), pp = pad128(p);
-    return 6LL * KP * (np + pp) + 3 * pp + 32;
+    return 8LL * KP * (np + pp) + 3 * pp + 32;      // K-major 4 arrays + transposed 2 tf32 + 2 bf16-pair arrays per side
 }
 
 struct TcWs { float *rowK, *rowT, *geneK, *geneT, *lp2w, *flw, *cw; int* flags; long long np, pp; };
@@ -961,9 +1023,9 @@ static TcWs tc_carve(const ori_problem_t* P) {
     const long long KP = P->KP;
     float* f = P->tc_ws;
     w.rowK = f; f += 4 * w.np * KP;
-    w.rowT = f; f += 2 * KP * w.np;
+    w.rowT = f; f += 4 * KP * w.np;        // [e | E] tf32, then [e | E] bf16 pairs (PRECISE)
     w.geneK = f; f += 4 * w.pp * KP;
-    w.geneT = f; f += 2 * KP * w.pp;
+    w.geneT = f; f += 4 * KP * w.pp;
     w.lp2w = f; f += w.pp;
     w.flw = f; f += w.pp;
     w.cw = f; f += w.pp;
@@ -972,7 +1034,7 @@ static TcWs tc_carve(const ori_problem_t* P) {
 }
 
 bool tc_eligible(const ori_problem_t* P) {
-    if ((P->flags & ORI_F_SPARSE) && P->KP != 32) return false;
+    if ((P->flags & (ORI_F_SPARSE | ORI_F_PRECISE)) && P->KP != 32) return false;
     return P->tc_ws != nullptr && (P->KP == 32 || P->KP == 64) && !(P->flags & ORI_F_NO_TENSOR) && P->n_rows > 0 &&
            P->tc_ws_floats >= tc_workspace_floats(P->n_rows, P->p, P->KP) && get_encode_fn() != nullptr;
 }
@@ -995,13 +1057,17 @@ int launch_tc_prep_genes(const ori_problem_t* P, cudaStream_t st) {
     const float* e_acc = sparse ? P->eVz : P->eV;
     const float* E_uv = sparse ? P->Vh_old : P->V_hat;
     k_tc_prep_K<<<cdiv(w.pp * KP, 256), 256, 0, st>>>(e_den, drop ? E_uv : nullptr, LOG2E, w.geneK, P->p, w.pp, KP);
-    k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(e_acc, w.geneT, P->p, w.pp, KP);
+    const bool precise = (P->flags & ORI_F_PRECISE) != 0;
+    auto t16 = [&](float* base, long long pad, int q) -> uint32_t* {      // bf16-pair twin of transposed array q (PRECISE)
+        return precise ? reinterpret_cast<uint32_t*>(base + (long long)(2 + q) * KP * pad) : nullptr;
+    };
+    k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(e_acc, w.geneT, t16(w.geneT, w.pp, 0), P->p, w.pp, KP);
     {
         const cudaError_t e_ = cudaMemsetAsync(w.flags, 0, 32 * sizeof(int), st);
         if (e_ != cudaSuccess) return set_error(ORI_ECUDA, "cudaMemsetAsync(tc flags): %s", cudaGetErrorString(e_));
     }
     if (drop) {
-        k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(P->V_hat, w.geneT + (long long)KP * w.pp, P->p, w.pp, KP);
+        k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(P->V_hat, w.geneT + (long long)KP * w.pp, t16(w.geneT, w.pp, 1), P->p, w.pp, KP);
         k_tc_prep_lp<<<cdiv(w.pp, 256), 256, 0, st>>>(P->lp, P->pfloor, w.lp2w, w.flw, w.cw, w.flags, P->p, (int)w.pp);
     }
     return check_launch("k_tc_prep(genes)", drop ? 4 : 2);
@@ -1016,8 +1082,11 @@ int launch_tc_prep_rows(const ori_problem_t* P, int g, cudaStream_t st) {
     const dim3 tg(cdiv(w.np, 32), KP / 32);
     k_tc_prep_K<<<cdiv(w.np * KP, 256), 256, 0, st>>>(P->eU[g], drop ? P->U_hat[g] : nullptr, 1.f, w.rowK, P->n_rows, w.np, KP);
     const float* wsrc = (P->flags & ORI_F_QUIRK) ? P->eUw : P->eU[g];
-    k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(wsrc, w.rowT, P->n_rows, w.np, KP);
-    if (drop) k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(P->U_hat[1 - g], w.rowT + (long long)KP * w.np, P->n_rows, w.np, KP);
+    const bool precise = (P->flags & ORI_F_PRECISE) != 0;
+    uint32_t* r16 = precise ? reinterpret_cast<uint32_t*>(w.rowT + 2ll * KP * w.np) : nullptr;
+    k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(wsrc, w.rowT, r16, P->n_rows, w.np, KP);
+    if (drop) k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(P->U_hat[1 - g], w.rowT + (long long)KP * w.np,
+                                                      precise ? r16 + (long long)KP * w.np : nullptr, P->n_rows, w.np, KP);
     return check_launch("k_tc_prep(rows)", drop ? 3 : 2);
 }
 
@@ -1025,7 +1094,9 @@ int launch_tc_prep_rows(const ori_problem_t* P, int g, cudaStream_t st) {
 int launch_tc_prep_rows_logsum(const ori_problem_t* P, int g, cudaStream_t st) {
     const TcWs w = tc_carve(P);
     const dim3 tg(cdiv(w.np, 32), P->KP / 32);
-    k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(P->eUl[g], w.rowT, P->n_rows, w.np, P->KP);
+    const bool precise = (P->flags & ORI_F_PRECISE) != 0;
+    k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(P->eUl[g], w.rowT, precise ? reinterpret_cast<uint32_t*>(w.rowT + 2ll * P->KP * w.np) : nullptr,
+                                            P->n_rows, w.np, P->KP);
     return check_launch("k_tc_prep(rows, logsum)");
 }
 
@@ -1060,17 +1131,17 @@ static void tc_partition(TcArgs& a, bool genes, int units, int sw) {
     a.n_items = a.n_own_units * a.n_chunks;
 }
 
-template <bool GENES, bool D, bool E, bool PAIR, int KP>
+template <bool GENES, bool D, bool E, bool PAIR, int KP, bool PRECISE>
 static int launch_tc_variant(const TcMaps& maps, const TcArgs& a, int grid, cudaStream_t st) {
-    auto kern = k_tc_pass<GENES, D, E, PAIR, KP>;
+    auto kern = k_tc_pass<GENES, D, E, PAIR, KP, PRECISE>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<KP, PAIR>::SMEM_BYTES);
+        cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<KP, PAIR, PRECISE>::SMEM_BYTES);
         if (e_ != cudaSuccess) return set_error(ORI_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e_));
         attr_done = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg<KP, PAIR>::SMEM_BYTES; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg<KP, PAIR, PRECISE>::SMEM_BYTES; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -1081,9 +1152,9 @@ static int launch_tc_variant(const TcMaps& maps, const TcArgs& a, int grid, cuda
 }
 
 // logsum: the dropout-free sweep of the sparse model's third gene-side sum into red32 block 2
-template <bool GENES, bool PAIR, int KP>
+template <bool GENES, bool PAIR, int KP, bool PRECISE>
 static int launch_tc_pass_p(const ori_problem_t* P, int gen_old, cudaStream_t st, bool logsum = false) {
-    using C = Cfg<KP, PAIR>;
+    using C = Cfg<KP, PAIR, PRECISE>;
     const TcWs w = tc_carve(P);
     const bool sparse = P->flags & ORI_F_SPARSE;
     const bool drop = (P->flags & ORI_F_DROPOUT) && !logsum, elbo = (P->flags & ORI_F_ELBO) && !logsum;
@@ -1095,14 +1166,14 @@ static int launch_tc_pass_p(const ori_problem_t* P, int gen_old, cudaStream_t st
     // [32 sweep x KP / NCTA latent rows] per chunk (a CTA of a pair stages half of the rows)
     if (!GENES) {
         ok = make_tmap_f32(&maps.swK, w.geneK, 4 * w.pp, KP, KP, 32, SW / NCTA) &&
-             make_tmap_f32(&maps.swT, w.geneT, 2 * KP, w.pp, w.pp, 32, KP / NCTA) &&
+             make_tmap_f32(&maps.swT, w.geneT, C::NTA * KP, w.pp, w.pp, 32, KP / NCTA) &&
              make_tmap_f32(&maps.X, P->X, P->n_rows, P->p, P->ldx, 32, TC_OWN);
         a.own_total = P->n_rows; a.sw_total = P->p; a.sw_pad = w.pp;
         a.own_e = P->eU[gen_old]; a.own_E = P->U_hat[gen_old];
         a.acc1 = P->Zi; a.acc2 = P->a2s;
     } else {
         ok = make_tmap_f32(&maps.swK, w.rowK, 4 * w.np, KP, KP, 32, SW / NCTA) &&
-             make_tmap_f32(&maps.swT, w.rowT, 2 * KP, w.np, w.np, 32, KP / NCTA) &&
+             make_tmap_f32(&maps.swT, w.rowT, C::NTA * KP, w.np, w.np, 32, KP / NCTA) &&
              make_tmap_f32(&maps.X, P->X, P->n_rows, P->p, P->ldx, 32, SW);
         a.own_total = P->p; a.sw_total = P->n_rows; a.sw_pad = w.np;
         a.own_e = sparse ? P->eVd : P->eV; a.own_E = sparse ? P->Vh_old : P->V_hat;
@@ -1118,22 +1189,30 @@ static int launch_tc_pass_p(const ori_problem_t* P, int gen_old, cudaStream_t st
     tc_partition(a, GENES, units, SW);
     const int grid = NCTA * (a.n_items < units ? a.n_items : units);
     int rc;
-    if (drop && elbo) rc = launch_tc_variant<GENES, true, true, PAIR, KP>(maps, a, grid, st);
-    else if (drop) rc = launch_tc_variant<GENES, true, false, PAIR, KP>(maps, a, grid, st);
-    else if (elbo) rc = launch_tc_variant<GENES, false, true, PAIR, KP>(maps, a, grid, st);
-    else rc = launch_tc_variant<GENES, false, false, PAIR, KP>(maps, a, grid, st);
+    if (drop && elbo) rc = launch_tc_variant<GENES, true, true, PAIR, KP, PRECISE>(maps, a, grid, st);
+    else if (drop) rc = launch_tc_variant<GENES, true, false, PAIR, KP, PRECISE>(maps, a, grid, st);
+    else if (elbo) rc = launch_tc_variant<GENES, false, true, PAIR, KP, PRECISE>(maps, a, grid, st);
+    else rc = launch_tc_variant<GENES, false, false, PAIR, KP, PRECISE>(maps, a, grid, st);
     if (rc != ORI_OK) return rc;
     return check_launch(GENES ? "k_tc_pass(genes)" : "k_tc_pass(rows)");
 }
 
 template <bool GENES>
 static int launch_tc_pass(const ori_problem_t* P, int gen_old, cudaStream_t st, bool logsum = false) {
+    if (P->flags & ORI_F_PRECISE) {      // fp32-grade contractions: KP = 32 plan with 32-wide sweep tiles (tc_eligible checks KP)
 #if ORI_TC_NEW == 8
-    if (P->KP == 64) return launch_tc_pass_p<GENES, true, 64>(P, gen_old, st, logsum);
+        return launch_tc_pass_p<GENES, true, 32, true>(P, gen_old, st, logsum);
+#else
+        return set_error(ORI_EUNSUPPORTED, "this build (ORI_TC_NEW != 8) has no fp32-grade plan");
+#endif
+    }
+#if ORI_TC_NEW == 8
+    if (P->KP == 64) return launch_tc_pass_p<GENES, true, 64, false>(P, gen_old, st, logsum);
 #else
     if (P->KP == 64) return set_error(ORI_EUNSUPPORTED, "this build (ORI_TC_NEW != 8) has no KP = 64 plan");
 #endif
-    return use_pair() ? launch_tc_pass_p<GENES, true, 32>(P, gen_old, st, logsum) : launch_tc_pass_p<GENES, false, 32>(P, gen_old, st, logsum);
+    return use_pair() ? launch_tc_pass_p<GENES, true, 32, false>(P, gen_old, st, logsum)
+                      : launch_tc_pass_p<GENES, false, 32, false>(P, gen_old, st, logsum);
 }
 
 int launch_pass_rows_tc(const ori_problem_t* P, int gen_old, cudaStream_t st) { return launch_tc_pass<false>(P, gen_old, st); }

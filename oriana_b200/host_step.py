@@ -77,7 +77,7 @@ class CompactCounts:
 class HostStreamedCAVI:
 
     def __init__(self, X_host, k, state, dropout=True, compat_quirk=False, slab_rows=None, sharded=False,
-                 process_group=None, elbo=True, keep_hyper=True):
+                 process_group=None, elbo=True, keep_hyper=True, precise=False):
         """X_host: CPU tensor [n, p] (pin it for asynchronous copies), float32 like the array the reference
         feeds its kernel (zigap.py:112) or the same counts kept compactly as uint16 / uint8 (half / a quarter of
         the bytes per step over PCIe; widened to float32 on the device), or a `CompactCounts` (saturating uint8
@@ -97,14 +97,15 @@ class HostStreamedCAVI:
         S0 = slab_rows if slab_rows is not None else max(128, min(self.n, (512 << 20) // (4 * ldx0)) // 128 * 128)
         S0 = int(min(max(1, S0), max(1, self.n)))
         # slabs large enough to fill the machine take the tcgen05/TMA kernels (K <= 64), like the device model
-        self._tensor = self.k <= 64 and S0 * self.p >= (1 << 21)
+        self._tensor = self.k <= (32 if precise else 64) and S0 * self.p >= (1 << 21)
         KP = self._KP = (32 if self.k <= 32 else 64) if self._tensor else pad_k(self.k)
         n, p, K, dev = self.n, self.p, self.k, self._dev
         self._shard = RowSharding(process_group, enabled=bool(sharded or process_group is not None))
         self.n_total = self._shard.total_rows(n, dev)
         self.dropout = bool(dropout)
         self._flags = (_lib.ORI_F_DROPOUT if dropout else 0) | (_lib.ORI_F_ELBO if elbo else 0) \
-            | (_lib.ORI_F_QUIRK if (compat_quirk and dropout) else 0)
+            | (_lib.ORI_F_QUIRK if (compat_quirk and dropout) else 0) \
+            | (_lib.ORI_F_PRECISE if (precise and self._tensor and self.k <= 32) else 0)
         ldx = self._ldx = (p + 3) // 4 * 4
         if slab_rows is None:
             slab_rows = max(128, min(n, (512 << 20) // (4 * ldx)) // 128 * 128)

@@ -79,7 +79,7 @@ class FactorModel(metaclass=ABCMeta):
 
     def __init__(self, cmatrix, k=2, use_factors=True, *, state=None, compat_quirk=False, sharded=False,
                  process_group=None, elbo=True, trace_cap=4096, force_simt=False, tensor=None, nmf=None, graphs=False,
-                 keep_hyper=True):
+                 keep_hyper=True, precise=False):
         self._dev = _lib.require_cuda()
         self._lib = _lib.load()
         _lib.check(self._lib.ori_device_check(self._dev.index or 0))
@@ -98,6 +98,12 @@ class FactorModel(metaclass=ABCMeta):
             tensor = (not force_simt) and self.k <= 64 and self.n * self.p >= (1 << 21)
         if tensor and (self.k > 64 or force_simt):
             raise ValueError('the tensor path needs k <= 64 and force_simt=False')
+        # precise=True: fp32-grade arithmetic everywhere.  On the tensor path (k <= 32) R, D_hat and the factor operands of
+        # the accumulating contractions are split hi/lo like the denominator (ORI_F_PRECISE, about half the rate of the
+        # default TF32-operand kernels); for k > 32 the CUDA-core kernels are used.
+        self.precise = bool(precise)
+        if self.precise and tensor and self.k > 32:
+            tensor = False
         self._tensor = bool(tensor)
         self._KP = (32 if self.k <= 32 else 64) if self._tensor else pad_k(self.k)
         self._shard = RowSharding(process_group if (sharded or process_group is not None) else None,
@@ -106,7 +112,7 @@ class FactorModel(metaclass=ABCMeta):
         self._flags = (_lib.ORI_F_DROPOUT if self._dropout else 0) | (_lib.ORI_F_ELBO if elbo else 0) \
             | (_lib.ORI_F_QUIRK if (compat_quirk and self._dropout) else 0) \
             | (_lib.ORI_F_NO_TENSOR if force_simt else 0) | (_lib.ORI_F_SPARSE if self._sparse else 0) \
-            | (_lib.ORI_F_DEVICE_ITER if graphs else 0)
+            | (_lib.ORI_F_DEVICE_ITER if graphs else 0) | (_lib.ORI_F_PRECISE if (self.precise and self._tensor) else 0)
         # graphs=True: step() replays one captured CUDA graph per generation parity (every launch of the iteration and
         # the memsets) instead of ~15 separate launches; single rank only
         if graphs and (sharded or process_group is not None):

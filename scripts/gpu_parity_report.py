@@ -30,8 +30,10 @@ def golden():
         g = load_golden(name)
         s = golden_state(g, 0)
         steps = sorted(int(t) for t in g['steps'])
-        for tensor in (True, False):
-            m = make_model(s, quirk=True, tensor=tensor, trace_cap=max(steps) + 8)
+        for tensor in ('precise', True, False):
+            if tensor == 'precise' and s['a1'].shape[1] > 32:
+                continue
+            m = make_model(s, quirk=True, tensor=bool(tensor), precise=(tensor == 'precise'), trace_cap=max(steps) + 8)
             rows = []
             for t in range(1, max(steps) + 1):
                 m.step()
@@ -42,7 +44,7 @@ def golden():
                     ed = float(np.max(np.abs(m.D_hat - r['p_d']))) if 'p_d' in s else 0.0
                     ee = abs(m.elbo() - cn.elbo(r)) / abs(cn.elbo(r))
                     rows.append((t, ef, eh, ed, ee))
-            print('%-13s %-6s ' % (name, 'tensor' if tensor else 'simt') +
+            print('%-13s %-7s ' % (name, 'precise' if tensor == 'precise' else ('tensor' if tensor else 'simt')) +
                   ' | '.join('t=%d f %.1e h %.1e D %.1e E %.1e' % r for r in rows), flush=True)
 
 
@@ -50,8 +52,10 @@ def slabs():
     for cfg, (n, p, K, z) in (('c3', (2048, 20000, 20, 0.5)), ('c4', (2048, 20000, 32, 0.5)), ('c5', (2048, 30000, 64, 0.12))):
         X = cn.synth_counts(n, p, K, seed=0, z=z)
         s = cn.init_state(X, K, np.random.default_rng(0), 'zigap')
-        for tensor in (True, False):
-            m = make_model(s, quirk=False, tensor=tensor)
+        for tensor in ('precise', True, False):
+            if tensor == 'precise' and K > 32:
+                continue
+            m = make_model(s, quirk=False, tensor=bool(tensor), precise=(tensor == 'precise'))
             ref = {k: v.copy() for k, v in s.items()}
             want = [cn.elbo(ref, guard32=True)]
             t0 = time.time()
@@ -65,8 +69,9 @@ def slabs():
             ed = float(np.max(np.abs(m.D_hat.astype(np.float64) - ref['p_d'])))
             got = m.elbo_trace
             ee = float(np.max(np.abs(got - np.asarray(want)) / np.abs(want)))
-            print('%s slab %dx%d K=%d zeros %.2f %-6s %s | D %.1e ELBO trace %.1e (%.0f s)' % (
-                cfg, n, p, K, float((X == 0).mean()), 'tensor' if tensor else 'simt', ' | '.join(out), ed, ee, time.time() - t0),
+            print('%s slab %dx%d K=%d zeros %.2f %-7s %s | D %.1e ELBO trace %.1e (%.0f s)' % (
+                cfg, n, p, K, float((X == 0).mean()), 'precise' if tensor == 'precise' else ('tensor' if tensor else 'simt'), ' | '.join(out), ed, ee,
+                time.time() - t0),
                 flush=True)
             del m
 

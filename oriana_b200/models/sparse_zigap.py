@@ -11,12 +11,14 @@ One CAVI iteration is the ZIGaP iteration with three changes (sparse_zigap.py:11
 K <= 32; no ELBO (the reference's convergence trace for this model is the deviance, `reconstruction_deviance()` /
 `explained_deviance()`, base.py:58-82, evaluated on the device).
 
-Kernel family.  Default: the CUDA-core kernels (csrc/kernels_simt.cu, fp32 FMA) -- the S update is a sigmoid of the
-difference of two large gene-side sums (:157-160), so p_s amplifies ABSOLUTE errors of those sums exponentially, and
-parity with the reference is only defined on the fp32 path.  `tensor=True` opts into the tcgen05 kernels (the same two
-passes with the masked operands, plus a second, dropout-free gene sweep for the third sum): ~5x faster at scale; the
-TF32 rounding of R and D_hat perturbs each gene-side sum by about 2^-12 / sqrt(cells), which at 1e5 cells is below
-the noise of the reference's own sequential float32 accumulation but is not bit-comparable with it.
+Kernel family.  The S update is a sigmoid of the difference of two large gene-side sums (:157-160), so p_s amplifies
+ABSOLUTE errors of those sums exponentially: parity with the reference needs fp32-grade sums.  Problems large enough to
+fill the machine (>= 2^21 entries) therefore run the tcgen05 kernels in their fp32-grade mode (`precise=True`, the
+default here: R, D_hat and the factor operands of the gene- and row-side sums split hi/lo, csrc/kernels_tc.cu PRECISE)
+-- the same two passes with the masked operands plus a second, dropout-free gene sweep for the third sum; smaller ones
+run the CUDA-core kernels (csrc/kernels_simt.cu, fp32 FMA).  Both are checked against the reference's recorded
+trajectories at the same tolerances (tests/test_sparse_gpu.py).  `precise=False` opts into the TF32-operand kernels
+(~1.4x faster, 2^-12 / sqrt(cells) noise on each gene-side sum: not comparable step by step).
 """
 import numpy as np
 import torch
@@ -37,7 +39,7 @@ class SparseZIGaP(ZIGaP):
         if kwargs.get('k', args[1] if len(args) > 1 else 2) > 32:
             raise ValueError('SparseZIGaP supports k <= 32')
         kwargs['elbo'] = False
-        kwargs['tensor'] = bool(kwargs.get('tensor', False))      # opt-in only (see the module docstring)
+        kwargs.setdefault('precise', True)                        # fp32-grade sums (see the module docstring)
         self._col_mean = None
         ZIGaP.__init__(self, *args, tau=tau, **kwargs)
 

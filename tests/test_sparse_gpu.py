@@ -33,17 +33,21 @@ def _state(g, t):
     return s
 
 
-def make_model(s, tau):
+def make_model(s, tau, **kw):
     from oriana.models import SparseZIGaP
     from oriana.singlecell import CountMatrix
-    return SparseZIGaP(CountMatrix(s['X']), k=s['a1'].shape[1], use_factors=False, state=s, tau=tau)
+    return SparseZIGaP(CountMatrix(s['X']), k=s['a1'].shape[1], use_factors=False, state=s, tau=tau, **kw)
 
 
+@pytest.mark.parametrize('path', ['cuda_core', 'tensor_fp32_grade'])
 @pytest.mark.parametrize('name', ['sparse_k4', 'sparse_ragged', 'sparse_gen', 'sparse_nmf'])
-def test_sparse_trajectory_and_deviance_match_reference(cuda_lib, name):
+def test_sparse_trajectory_and_deviance_match_reference(cuda_lib, name, path):
+    """Both kernel families against the reference's recorded trajectories at the SAME tolerances: the CUDA-core kernels
+    (what fixtures of this size run by default) and the tcgen05 kernels in their fp32-grade mode (the default from 2^21
+    entries on, forced here)."""
     g = load_golden(name)
-    m = make_model(_state(g, 0), float(g['tau']))
-    assert not m.uses_tensor_path
+    m = make_model(_state(g, 0), float(g['tau']), tensor=(path != 'cuda_core'))
+    assert m.uses_tensor_path == (path != 'cuda_core') and (path == 'cuda_core' or m.precise)
     if 's0_deviance' in g.files:             # the driver's first print, before any step (clustering.py:20)
         assert abs(m.reconstruction_deviance() - float(g['s0_deviance'])) <= 1e-4 * abs(float(g['s0_deviance']))
     steps = [int(t) for t in g['steps']]
@@ -111,25 +115,41 @@ def test_sparse_constructor_path_and_snapshot(cuda_lib):
         SparseZIGaP(CountMatrix(X), k=40, use_factors=False)
 
 
-def test_sparse_tensor_path_tracks_the_cuda_core_path(cuda_lib):
-    """`tensor=True` (opt-in): the tcgen05 kernels with the masked operands and a second gene sweep for the third sum.
-    Not bit-comparable with the fp32 path (the S update amplifies the TF32 rounding of the gene-side sums), so the
-    check is statistical: factors and priors close, masks S_tilde almost everywhere equal, same deviance."""
+def test_sparse_tensor_paths_track_the_cuda_core_path(cuda_lib):
+    """At a size where the tensor kernels are the default: the fp32-grade mode (default) follows the CUDA-core path like
+    the CUDA-core path follows the reference (same envelope, masks S_tilde equal almost everywhere); the TF32-operand mode
+    (`precise=False`, opt-in) is not comparable step by step (the S update amplifies the TF32 rounding of the gene-side
+    sums), so its check is statistical: factors and priors close, masks almost everywhere equal, same deviance."""
     from oriana.models import SparseZIGaP
     from oriana.singlecell import synth_counts_device
     n, p, K = 20_000, 3_000, 8
     X = synth_counts_device(n, p, K, seed=9)
     np.random.seed(3)
-    m0 = SparseZIGaP(X[:, :p], k=K, use_factors=False)
+    m0 = SparseZIGaP(X[:, :p], k=K, use_factors=False, tensor=False)
     st = m0.state_dict(); st['X'] = X[:, :p]
-    ms = SparseZIGaP(X[:, :p], k=K, use_factors=False, state=st)
-    mt = SparseZIGaP(X[:, :p], k=K, use_factors=False, state=st, tensor=True)
-    assert mt.uses_tensor_path and not ms.uses_tensor_path
+    ms = SparseZIGaP(X[:, :p], k=K, use_factors=False, state=st, tensor=False)
+    mp = SparseZIGaP(X[:, :p], k=K, use_factors=False, state=st)                       # default: tensor, fp32-grade
+    mt = SparseZIGaP(X[:, :p], k=K, use_factors=False, state=st, precise=False)        # TF32 operands
+    assert mp.uses_tensor_path and mp.precise and mt.uses_tensor_path and not mt.precise and not ms.uses_tensor_path
     for _ in range(3):
-        ms.step(); mt.step()
+        ms.step(); mt.step(); mp.step()
+    ps_s, ps_t, ps_p = ms.p_s.asarray(), mt.p_s.asarray(), mp.p_s.asarray()
+    # fp32-grade mode.  At this size a handful of (gene, component) pairs sit on the edge of the S update's sigmoid, where ANY
+    # change of summation order flips them (measured: |dp_s| > 0.05 on ~1e-5 of the pairs for both tensor modes), and a
+    # flipped pair moves the cells it loads on: medians, not maxima
+    med = lambda a, b: float(np.median(np.abs(a - b) / (np.abs(b) + 1e-12)))
+    for k in ('a1', 'a2', 'b1', 'b2'):
+        assert med(getattr(mp, k).asarray(), getattr(ms, k).asarray()) < 1e-5, k
+    for k in ('alpha1', 'alpha2', 'beta1', 'beta2', 'pi_s'):
+        assert relerr(getattr(mp, k).asarray(), getattr(ms, k).asarray()) < 5e-3, k
+    assert med(mp.pi_d.asarray(), ms.pi_d.asarray()) < 1e-5
+    assert np.mean((ps_s > 0.5) != (ps_p > 0.5)) < 1e-4
+    assert np.mean(np.abs(ps_s - ps_p) > 0.05) < 5e-4
+    dsq, dpq = ms.reconstruction_deviance(), mp.reconstruction_deviance()
+    assert abs(dpq - dsq) <= 1e-3 * abs(dsq) or not np.isfinite(dsq)
+    # TF32-operand mode
     for k in ('a1', 'a2', 'alpha1', 'alpha2', 'beta1', 'beta2', 'pi_d'):
         assert relerr(getattr(mt, k).asarray(), getattr(ms, k).asarray()) < 5e-3, k
-    ps_s, ps_t = ms.p_s.asarray(), mt.p_s.asarray()
     assert np.mean((ps_s > 0.5) != (ps_t > 0.5)) < 5e-3
     assert np.mean(np.abs(ps_s - ps_t) > 0.05) < 2e-2
     same = (ps_s > 0.5) == (ps_t > 0.5)

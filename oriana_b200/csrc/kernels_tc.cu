@@ -1107,26 +1107,28 @@ static int env_int(const char* name, int dflt) {
 // CTA-pair kernels (cta_group::2) by default; ORI_TC_PAIR=0 selects the single-CTA variant (kept for A/B runs, KP 32)
 static bool use_pair() { static int v = env_int("ORI_TC_PAIR", 1); return v != 0; }
 
-// Split the sweep into chunks so that (a) there are many more work items than schedulable units (SMs, or SM
-// pairs), (b) the static round-robin wastes as little of the last round as possible, (c) the gene pass keeps
-// <= 8192 cells per item (fp32 running sums of the statistics).
-static void tc_partition(TcArgs& a, bool genes, int units, int sw) {
-    const int max_tpc = genes ? 8192 / sw : 1 << 30;
-    const int min_tpc = 1024 / sw;
-    int best_chunks = 1; double best_eff = -1.0;
-    for (int chunks = 1; chunks <= a.n_sw_tiles; ++chunks) {
-        const int tpc = cdiv(a.n_sw_tiles, chunks);
-        if (tpc > max_tpc) continue;
-        if (tpc < min_tpc && chunks > 1) break;
-        const int real_chunks = cdiv(a.n_sw_tiles, tpc);
-        const long long items = (long long)real_chunks * a.n_own_units;
-        const long long rounds = (items + units - 1) / units;
-        // efficiency of the static schedule, with a mild penalty per item for its prologue / epilogue
-        const double eff = (double)items / (double)(rounds * units) * ((double)tpc / (tpc + 128.0 / sw));
-        if (eff > best_eff + 1e-9) { best_eff = eff; best_chunks = chunks; }
-        if (items > 64LL * units) break;
-    }
-    a.tiles_per_chunk = cdiv(a.n_sw_tiles, best_chunks);
+// Split the sweep into chunks of a FIXED length: the accumulators of a work item live in TMEM, and the tensor core's fp32
+// accumulation truncates -- a chain of S accumulating MMAs comes out about S * 3e-8 low (measured: sum_ij D_ij (U V^T)_ij
+// at 100k x 20k differed by 8e-6 between a 2504-step and an 830-step chaining of the same state, and with it the ELBO by
+// 2e-5).  Items therefore hand their partial sums to global memory (round-to-nearest float atomics) every ORI_TC_CHUNK
+// sweep entries -- 512 accumulating steps per accumulator -- and, because the chunk length depends on nothing but the kernel
+// plan, every cell and gene sees the same chaining whatever the number of ranks or slabs the matrix is split into: the same
+// state evaluated by the device model and by host-streamed slabs now gives the same ELBO to 1e-8.  Measured cost at
+// 250k x 20k, K = 32 (rows / genes, ms): one chunk per row 4.91 / 7.11 (8192-cell gene chunks), 4096: 5.05 / 7.09,
+// 2048: 5.56 / 7.57, 1024: 6.63 / 8.49 (every item boundary drains the pipeline and reloads the own-side operands).
+// Problems too small to give every SM (pair) an item are split further.  (The gene pass also needs <= 8192 cells per item
+// for its fp32 running sums.)
+#ifndef ORI_TC_CHUNK
+#define ORI_TC_CHUNK 4096
+#endif
+static void tc_partition(TcArgs& a, bool genes, int units, int sw, bool precise) {
+    (void)genes;
+    int tpc = (precise ? ORI_TC_CHUNK / 2 : ORI_TC_CHUNK) / sw;     // precise: two MMAs per 8 sweep entries and accumulator
+    if (tpc < 1) tpc = 1;
+    if (tpc > a.n_sw_tiles) tpc = a.n_sw_tiles;
+    const int min_tpc = (128 / sw) > 1 ? 128 / sw : 1;
+    while ((long long)a.n_own_units * cdiv(a.n_sw_tiles, tpc) < units && tpc > min_tpc) tpc = (tpc + 1) / 2;
+    a.tiles_per_chunk = tpc;
     a.n_chunks = cdiv(a.n_sw_tiles, a.tiles_per_chunk);
     a.n_items = a.n_own_units * a.n_chunks;
 }
@@ -1186,7 +1188,7 @@ static int launch_tc_pass_p(const ori_problem_t* P, int gen_old, cudaStream_t st
     a.n_own_units = cdiv(a.n_own_tiles, NCTA);
     a.n_sw_tiles = cdiv(a.sw_total, SW);
     const int units = num_sms() / NCTA;
-    tc_partition(a, GENES, units, SW);
+    tc_partition(a, GENES, units, SW, PRECISE);
     const int grid = NCTA * (a.n_items < units ? a.n_items : units);
     int rc;
     if (drop && elbo) rc = launch_tc_variant<GENES, true, true, PAIR, KP, PRECISE>(maps, a, grid, st);

@@ -1,31 +1,43 @@
-"""Run the same three CAVI steps many times and report the spread between runs (atomics order only => ~1e-6).
-An outlier means a race.  Usage: python scripts/gpu_stress_repeat.py [reps] [n p K]"""
+"""Run the same CAVI steps several times from one state and report, per step count, the spread between runs: the only
+source of run-to-run variation is the order of the floating-point atomics (the kernels themselves are deterministic), and the
+iteration amplifies it step by step.  An outlier against the trend would mean a race.
+Usage: python scripts/gpu_stress_repeat.py [reps] [n p K] [simt|precise]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from oriana.models import ZIGaP
 from oriana.singlecell import synth_counts_device
 
-reps = int(sys.argv[1]) if len(sys.argv) > 1 else 30
-n, p, K = (int(a) for a in sys.argv[2:5]) if len(sys.argv) > 4 else (4000, 1700, 12)
+args = [a for a in sys.argv[1:] if a not in ('simt', 'precise')]
+reps = int(args[0]) if len(args) > 0 else 6
+n, p, K = (int(a) for a in args[1:4]) if len(args) > 3 else (4000, 1700, 12)
+kw = dict(tensor=('simt' not in sys.argv), precise=('precise' in sys.argv))
 X = synth_counts_device(n, p, K, seed=8)
 np.random.seed(5)
-m0 = ZIGaP(X[:, :p], k=K, use_factors=False, tensor=True)
+m0 = ZIGaP(X[:, :p], k=K, use_factors=False, **kw)
 st = m0.state_dict(); st['X'] = X[:, :p]
+del m0
+checkpoints = (1, 2, 3, 5, 8)
 base = None
 worst = {}
 for r in range(reps):
-    m = ZIGaP(X[:, :p], k=K, use_factors=False, state=st, tensor=True)
-    for _ in range(3):
+    m = ZIGaP(X[:, :p], k=K, use_factors=False, state=st, **kw)
+    snaps = {}
+    for t in range(1, max(checkpoints) + 1):
         m.step()
-    s = {k: np.asarray(v, dtype=np.float64) for k, v in m.state_dict().items() if k not in ('iterations', 'X')}
-    s['elbo'] = np.asarray(m.elbo_trace)
+        if t in checkpoints:
+            snaps[t] = {k: getattr(m, k).asarray() for k in ('a1', 'b1', 'b2', 'alpha1')}
+    tr = np.asarray(m.elbo_trace)
+    for t in checkpoints:
+        snaps[t]['elbo'] = tr[t:t + 1]
     if base is None:
-        base = s; continue
-    for k in s:
-        d = np.abs(s[k] - base[k]); sc = np.maximum(np.abs(base[k]), 1e-6 * np.abs(base[k]).max())
-        e = float((d / sc).max())
-        if e > worst.get(k, (0, 0))[0]:
-            worst[k] = (e, r)
-print('PAIR=%s reps=%d shape=%s' % (os.environ.get('ORI_TC_PAIR', '1'), reps, (n, p, K)))
-print('  '.join('%s=%.1e@%d' % (k, v[0], v[1]) for k, v in worst.items()))
+        base = snaps; del m; continue
+    for t in checkpoints:
+        for k in snaps[t]:
+            d = np.abs(snaps[t][k] - base[t][k]); sc = np.maximum(np.abs(base[t][k]), 1e-6 * np.abs(base[t][k]).max())
+            e = float((d / sc).max())
+            worst[(t, k)] = max(worst.get((t, k), 0.0), e)
+    del m
+print('%s reps=%d shape=%s' % (kw, reps, (n, p, K)))
+for t in checkpoints:
+    print('  after %d steps: ' % t + '  '.join('%s=%.1e' % (k, worst[(t, k)]) for k in ('a1', 'b1', 'b2', 'alpha1', 'elbo')))

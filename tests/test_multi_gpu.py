@@ -98,8 +98,10 @@ def test_two_gpu_sharded_models_match_unsharded(cuda_lib):
     assert res, 'rank 0 reported nothing'
     print(res)
     for k, e in res.items():
-        if k in ('zigap_elbo', 'sparse_deviance', 'sparse_explained'):
+        if k == 'zigap_elbo':
             tol = 1e-5
+        elif k in ('sparse_deviance', 'sparse_explained'):     # integer-truncated sums masked by round(D_hat): they inherit
+            tol = 2e-4                                         # the p_s differences below (measured 4e-7 ... 6e-5 between runs)
         elif k.startswith('sparse'):      # the S update amplifies the order of the float32 sums; b1, b2, a1 inherit S_hat
             tol = 5e-3 if k in ('sparse_p_s', 'sparse_pi_s') else 2e-3
         else:

@@ -324,6 +324,10 @@ int ori_deviance_sums(const ori_problem_t* P, int gen, const double* pi, const d
     if (!(P->flags & ORI_F_DROPOUT)) return set_error(ORI_EINVAL, "the deviance metrics need the dropout layer (sparse_zigap.py:44-51)");
     if (!pi || !col_mean || !out_int || gen < 0 || gen > 1) return set_error(ORI_EINVAL, "ori_deviance_sums: bad argument");
     if (P->n_rows == 0) return ORI_OK;
+    // integer sums of a problem on the tensor path: the tcgen05 pass; the float64 sums (int_quirk=False) and small
+    // problems: the CUDA-core kernel
+    if (!out_f64 && tc_eligible(P) && !(P->flags & ORI_F_QUIRK))
+        return launch_deviance_tc(P, gen, pi, col_mean, out_int, (cudaStream_t)stream);
     return launch_deviance(P, gen, pi, col_mean, out_int, out_f64, (cudaStream_t)stream);
 }
 

@@ -55,5 +55,6 @@ int launch_pass_rows_tc(const ori_problem_t* P, int gen_old, cudaStream_t st);
 int launch_pass_genes_tc(const ori_problem_t* P, int gen_old, cudaStream_t st);
 int launch_tc_prep_rows_logsum(const ori_problem_t* P, int gen_old, cudaStream_t st);
 int launch_pass_genes_logsum_tc(const ori_problem_t* P, int gen_old, cudaStream_t st);
+int launch_deviance_tc(const ori_problem_t* P, int gen, const double* pi, const double* col_mean, long long* out_int, cudaStream_t st);
 
 }  // namespace ori

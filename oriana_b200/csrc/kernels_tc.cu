@@ -31,6 +31,7 @@
 //   warp 1       MMA issuer + TMEM owner (warp-uniform control flow, one elected lane issues)
 //   warps 2..9   element-wise warps; warp w owns TMEM lanes 32*(w%4).. and half of the tile's columns
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -106,7 +107,7 @@ constexpr int TC_THREADS = 64 + 32 * NEW + (NISS == 2 ? 32 : 0);
 // as tf32 hi plus a bf16 [hi | lo] . [lo | hi] chain for the two cross terms, like den / uv -- so every sum is fp32-grade
 // (~2^-21) instead of TF32-grade (~2^-12 per term).  The tile keeps R16 / D16 (the packed bf16 pairs) beside R / D in TMEM,
 // which halves the sweep width (32) to stay inside 512 columns.
-template <int KP, bool PAIR, bool PRECISE = false>
+template <int KP, bool PAIR, bool PRECISE = false, bool DEVI = false>
 struct Cfg {
     static_assert(KP == 32 || KP == 64, "tensor path: KP is 32 or 64");
     static_assert(!PRECISE || KP == 32, "the fp32-grade plan exists for KP = 32");
@@ -128,7 +129,8 @@ struct Cfg {
     static constexpr uint32_t T_ARR = (SW / 32) * T_CHUNK;
     static constexpr uint32_t T_STAGE = NTA * T_ARR;      // transposed e and transposed E (+ their bf16 [lo | hi] pairs)
     static constexpr uint32_t X_STAGE = TC_OWN * SW * 4;  // X tile
-    static constexpr uint32_t LP_STAGE = 3 * SW * 4;      // lp2[SW] | floor[SW] | (1-pi)/pi [SW]
+    // per-gene constants of a tile: lp2[SW] | floor[SW] | (1-pi)/pi [SW]; deviance pass: 8 arrays (k_tc_prep_dev)
+    static constexpr uint32_t LP_STAGE = (DEVI ? 8 : 3) * SW * 4;
     static constexpr uint32_t OFF_K = 0;
     static constexpr uint32_t OFF_T = OFF_K + KST * K_STAGE;
     static constexpr uint32_t OFF_X = OFF_T + TST * T_STAGE;
@@ -169,6 +171,10 @@ struct TcArgs {
     float* acc2;                     // [own_total x KP]  sum_sweep D  * S2
     double* colsum;                  // gene pass: [genes] += sum_i D_hat
     double* part64;                  // gene pass: ELBO partial sums
+    // deviance pass (DEVI): per-gene constants, tile-major [n_sw_tiles][8][SW]; float64 fallback operands; int64 sums
+    const float* devlp;
+    const float* dev_b1; const float* dev_b2; const float* dev_ps;     // V' = b1 / b2 (* S_hat) [genes x KP]
+    unsigned long long* dev_out;     // [3] truncated log-likelihood sums at the rates U V^T (masked), X, column means
 };
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -247,7 +253,7 @@ struct TileIter {
     }
 };
 
-template <bool GENES, bool DROPOUT, bool ELBO, bool PAIR, int KP, bool PRECISE>
+template <bool GENES, bool DROPOUT, bool ELBO, bool PAIR, int KP, bool PRECISE, bool DEVI = false>
 #if ORI_TC_NEW == 16
 __global__ void __maxnreg__(96)
 #else
@@ -255,7 +261,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #endif
 k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
 {
-    using C = Cfg<KP, PAIR, PRECISE>;
+    using C = Cfg<KP, PAIR, PRECISE, DEVI>;
+    static_assert(!DEVI || (!GENES && DROPOUT && !ELBO && !PRECISE), "deviance pass: row orientation, two contractions");
     constexpr int NCTA = C::NCTA, SW = C::SW, NS = C::NS;
     constexpr uint32_t TM_UV = C::TM_UV;
     constexpr int KST = C::KST, TST = C::TST, XST = C::XST;
@@ -307,6 +314,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
         ik.init(a, NCTA, rank); it_.init(a, NCTA, rank);
         uint32_t nk = 0, nt = 0;
         auto load_T = [&]() {
+            if (DEVI) { ++nt; it_.next(a); return; }       // no accumulating contraction: no transposed operands
             const uint32_t s = nt % TST;
             mbar_wait(&bars[B_TEMPTY + s], ((nt / TST) & 1) ^ 1, 12);
             if (elect_one()) {
@@ -362,11 +370,12 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     uint64_t* bar = &bars[B_XFULL + s];
                     const int sw0 = ik.t * SW;
                     mbar_expect_tx(bar, X_STAGE + ((!GENES && DROPOUT && !ORI_KO_TMA) ? LP_STAGE : 0));
+                    if (DEVI) bulk_load(smem + OFF_LP + s * LP_STAGE, a.devlp + (long long)ik.t * (8 * SW), LP_STAGE, bar);
                     if (!GENES) {          // [128 cells][32 genes] boxes
 #pragma unroll
                         for (int c = 0; c < SW / 32; ++c)
                             tma_load_2d_hint(st + c * (TC_OWN * 128), &maps.X, bar, sw0 + 32 * c, ik.own0, L2_EVICT_FIRST);
-                        if (DROPOUT && !ORI_KO_TMA) {
+                        if (DROPOUT && !ORI_KO_TMA && !DEVI) {
                             bulk_load(smem + OFF_LP + s * LP_STAGE, a.lp2w + sw0, SW * 4, bar);
                             bulk_load(smem + OFF_LP + s * LP_STAGE + SW * 4, a.flw + sw0, SW * 4, bar);
                             bulk_load(smem + OFF_LP + s * LP_STAGE + SW * 8, a.cw + sw0, SW * 4, bar);
@@ -459,6 +468,9 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             int li = 0, lip = 0;
             auto trail_P = [&]() {
                 const bool pl = tp.last();
+                if (DEVI) {     // nothing to accumulate: only wait until the element-wise warps have read the stage S will reuse
+                    mbar_wait(&bars[B_PREADY + itp % NS], (itp / NS) & 1, 20);
+                } else
                 issue_P(itp, tp.first(), pl, lip);
                 if (pl) ++lip;
                 ++itp; tp.next(a);
@@ -804,7 +816,94 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     mbar_arrive(&bars[B_XEMPTY + c.xs]);
                 }
             };
-            if constexpr (!C::DEEP) {
+            long long dv0 = 0, dv1 = 0, dv2 = 0;      // deviance pass: truncated log-likelihood sums of this thread and item
+            if constexpr (DEVI) {
+                // ---- deviance pass (base.py:58-82, sparse_zigap.py:44-51): "den" = the rate L = U_hat . V_hat^T, "uv" = the
+                //      contraction that generates D_hat (log2 units).  Per entry, like k_deviance's integer mode:
+                //        zero, round(D_hat) = 0 (uv >= logit pi):  l_uv = 0
+                //        zero, kept:   l_uv = log(pi e^-L + 1 - pi);     l_sat = 0;   l_mean = log(pi e^-mean + 1 - pi)
+                //        non-zero:     l = log pi - rate + x log rate    at the rates L, x, mean
+                //      every term truncated toward zero before it is summed (sparse_zigap.py:45).  float32 with a float64
+                //      redo of the entries whose rate underflows or whose terms leave the exact range; nothing is written back.
+                for (int t = ti.t_begin; t < t_end; ++t, ++it) {
+                    const bool last = (t == t_end - 1);
+                    const Tile c = tile_of(it, t);
+                    wait_tile(it);
+                    if (last && has_next) a_load_store(next_own0);
+                    ld_group(c, 0, 0);
+                    load_x(c, 0, 0);
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const int b = g & 1;
+                        const int c0 = colbase + g * 16;
+                        if (g + 1 < G) load_x(c, g + 1, b ^ 1);
+                        tmem_wait_ld();
+                        if (g + 1 < G) ld_group(c, g + 1, b ^ 1);
+                        int s0 = 0, s1 = 0, s2 = 0;       // <= 16 terms of magnitude < 8e6 each
+                        uint32_t bad = 0;                 // entries that need the float64 redo (kept out of the unrolled code)
+                        const int nvalid = (int)min((long long)16, a.sw_total - ((long long)t * SW + c0));
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const uint32_t ca = c.lp_addr + 32 * (c0 + e);        // 8 constants per gene (k_tc_prep_dev)
+                            const float L = __uint_as_float(dr[b][e]), uvp = __uint_as_float(ur[b][e]), xe = x[b][e];
+                            const float4 ga = lds128(ca), gb = lds128(ca + 16);
+                            const float lp2 = ga.x, pj = ga.y, qj = ga.z, lpi = ga.w, mj = gb.x, lmj = gb.y, lm0 = gb.z;
+                            const bool nz = xe != 0.f;
+                            const bool kept = uvp < lp2;                           // round(D_hat) = 1 on a zero entry
+                            // both branches for every lane, selected afterwards: 4 MUFU per entry, no divergence
+                            const float lnL = lg2_approx(L) * LN2, lnx = lg2_approx(xe) * LN2;
+                            const float z0 = lg2_approx(fmaf(pj, ex2_approx(-L * LOG2E), qj)) * LN2;
+                            const float f0 = nz ? fmaf(xe, lnL, lpi - L) : (kept ? z0 : 0.f);
+                            const float f1 = nz ? fmaf(xe, lnx, lpi - xe) : 0.f;
+                            const float f2 = nz ? fmaf(xe, lmj, lpi - mj) : lm0;
+                            const bool ok = (!nz || L >= 1e-30f) && fmaxf(fmaxf(fabsf(f0), fabsf(f1)), fabsf(f2)) < 8e6f;
+                            const bool live = own_ok && e < nvalid;
+                            if (live && ok) { s0 += (int)f0; s1 += (int)f1; s2 += (int)f2; }
+                            if (live && !ok) bad |= 1u << e;
+                        }
+                        if (__any_sync(0xffffffffu, bad != 0)) {
+                            // rare: the float32 rate underflowed under an observed count (the reference's float64 product does
+                            // not), or a term is huge / not finite: float64 from the parameters, numpy's cast rules
+                            float xs_[16], us_[16];
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) { xs_[e] = x[b][e]; us_[e] = __uint_as_float(ur[b][e]); }
+#pragma unroll 1
+                            for (int e = 0; e < 16; ++e) {
+                                if (!((bad >> e) & 1u)) continue;
+                                const long long j = (long long)t * SW + c0 + e;
+                                const uint32_t ca = c.lp_addr + 32 * (c0 + e);
+                                const float4 ga = lds128(ca), gb = lds128(ca + 16);
+                                const float xe = xs_[e], uvp = us_[e];
+                                const bool nz = xe != 0.f, kept = uvp < ga.x;
+                                double Ld = 0.0;
+                                const float* uh = a.own_E + own_idx * KP;
+                                for (int k = 0; k < KP; ++k) {
+                                    const long long gk = j * KP + k;
+                                    if (a.dev_b2[gk] != 0.f)
+                                        Ld = fma((double)uh[k], (double)a.dev_b1[gk] / (double)a.dev_b2[gk] * (a.dev_ps ? (double)a.dev_ps[gk] : 1.0), Ld);
+                                }
+                                const double xd = (double)xe;
+                                double l0, l1, l2;
+                                if (nz) {
+                                    l0 = (double)ga.w - Ld + xd * log(Ld);
+                                    l1 = (double)ga.w - xd + xd * log(xd);
+                                    l2 = (double)ga.w - (double)gb.x + xd * (double)gb.y;
+                                } else {
+                                    l0 = kept ? (double)logf(fmaf(ga.y, expf(-(float)Ld), ga.z)) : 0.0;
+                                    l1 = 0.0;
+                                    l2 = (double)gb.z;
+                                }
+                                auto trunc64 = [](double v) -> long long {
+                                    return (fabs(v) < 9.2233720368547758e18) ? (long long)v : (long long)0x8000000000000000ull;
+                                };
+                                dv0 += trunc64(l0); dv1 += trunc64(l1); dv2 += trunc64(l2);
+                            }
+                        }
+                        dv0 += s0; dv1 += s1; dv2 += s2;
+                    }
+                    hand_off(c);
+                }
+            } else if constexpr (!C::DEEP) {
                 // ---- round-1 plan: every warp owns G groups of the tile; the next group's loads fly during the current one;
                 //      the tile is handed to the MMA warp as soon as its last group is stored
                 for (int t = ti.t_begin; t < t_end; ++t, ++it) {
@@ -881,6 +980,23 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     if (t + 1 < t_end) tile_step(std::integral_constant<int, 1>{}, t + 1);
                 }
                 if (have_pend) { tmem_wait_st(); hand_off(pend); }
+            }
+            if constexpr (DEVI) {
+                unsigned long long r0 = (unsigned long long)dv0, r1 = (unsigned long long)dv1, r2 = (unsigned long long)dv2;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    r0 += __shfl_xor_sync(0xffffffffu, r0, o); r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+                    r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+                }
+                if (lane == 0) {
+                    if (r0) atomicAdd(a.dev_out, r0);
+                    if (r1) atomicAdd(a.dev_out + 1, r1);
+                    if (r2) atomicAdd(a.dev_out + 2, r2);
+                }
+                ++li;
+                ti.item += ti.stride;
+                ti.load(a);
+                continue;
             }
             double acc_xl = (double)xl_s - (double)xl_c, acc_ent = (double)ent_s - (double)ent_c;
             // ---- epilogue of the work item: accumulators -> global (atomics: the sweep of one own tile is split);
@@ -1006,6 +1122,26 @@ __global__ void k_tc_prep_lp(const float* __restrict__ lp, const float* __restri
     flw[j] = f;
     cw[j] = exp2f(-l2);
     if (f != 0.f) *any_floor = 1;
+}
+
+// deviance pass: 8 constants per gene, tile-major [tile][SW][8]:
+//   logit(pi_gen) * log2(e) | pi | 1 - pi | log pi | mean | log mean | trunc(log(pi e^-mean + 1 - pi)) | 0
+// pi = the finalised Bernoulli prior, pi_gen (through lp) the one that generated D_hat, mean = column mean of X
+__global__ void k_tc_prep_dev(const float* __restrict__ lp, const double* __restrict__ pi, const double* __restrict__ cmean,
+                              float* __restrict__ out, int p, int pad)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= pad) return;
+    float4 a = make_float4(-INFINITY, 0.5f, 0.5f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < p) {
+        const double pj = pi[j], mj = cmean[j];
+        a.x = lp[j] * LOG2E; a.y = (float)pj; a.z = (float)(1.0 - pj); a.w = (float)log(pj);
+        b.x = (float)mj; b.y = (float)log(mj);
+        const float lm = logf(fmaf((float)pj, (float)exp(-mj), (float)(1.0 - pj)));     // as k_deviance's integer mode
+        b.z = (float)(int)lm;
+    }
+    reinterpret_cast<float4*>(out)[2 * (long long)j] = a;
+    reinterpret_cast<float4*>(out)[2 * (long long)j + 1] = b;
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
@@ -1215,6 +1351,76 @@ static int launch_tc_pass(const ori_problem_t* P, int gen_old, cudaStream_t st, 
 #endif
     return use_pair() ? launch_tc_pass_p<GENES, true, 32, false>(P, gen_old, st, logsum)
                       : launch_tc_pass_p<GENES, false, 32, false>(P, gen_old, st, logsum);
+}
+
+// The three truncated log-likelihood sums behind reconstruction_deviance / explained_deviance (base.py:58-82) on the
+// tensor path: a row-oriented pass whose two contractions are the rate U_hat . V_hat^T and the one that generates D_hat.
+template <int KP>
+static int launch_deviance_tc_kp(const ori_problem_t* P, int g, const double* pi, const double* cmean, long long* out_int,
+                                 cudaStream_t st) {
+    using C = Cfg<KP, true, false, true>;
+    constexpr int NCTA = C::NCTA, SW = C::SW;
+    const TcWs w = tc_carve(P);
+    const bool sparse = P->flags & ORI_F_SPARSE;
+    // gene-side K-major operands: [hi | lo] of the effective V_hat (rate) and of the V_hat that generates D_hat (log2 units)
+    k_tc_prep_K<<<cdiv(w.pp * KP, 256), 256, 0, st>>>(P->V_hat, sparse ? P->Vh_old : P->V_hat, LOG2E, w.geneK, P->p, w.pp, KP);
+    float* devlp = w.geneT;                 // the transposed-operand area is free here (no accumulating contraction)
+    k_tc_prep_dev<<<cdiv(w.pp, 256), 256, 0, st>>>(P->lp, pi, cmean, devlp, P->p, (int)w.pp);
+    {
+        const cudaError_t e_ = cudaMemsetAsync(w.flags, 0, 32 * sizeof(int), st);
+        if (e_ != cudaSuccess) return set_error(ORI_ECUDA, "cudaMemsetAsync(tc flags): %s", cudaGetErrorString(e_));
+    }
+    if (check_launch("k_tc_prep(deviance)", 2) != ORI_OK) return ORI_ECUDA;
+    TcMaps maps;
+    TcArgs a;
+    memset(&a, 0, sizeof(a));
+    const bool ok = make_tmap_f32(&maps.swK, w.geneK, 4 * w.pp, KP, KP, 32, SW / NCTA) &&
+                    make_tmap_f32(&maps.swT, w.geneT, C::NTA * KP, w.pp, w.pp, 32, KP / NCTA) &&
+                    make_tmap_f32(&maps.X, P->X, P->n_rows, P->p, P->ldx, 32, TC_OWN);
+    if (!ok) return set_error(ORI_ECUDA, "cuTensorMapEncodeTiled failed");
+    a.own_total = P->n_rows; a.sw_total = P->p; a.sw_pad = w.pp;
+    a.own_e = P->U_hat[g]; a.own_E = P->U_hat[g];
+    a.lp2w = w.lp2w; a.flw = w.flw; a.cw = w.cw; a.any_floor = w.flags;
+    a.devlp = devlp;
+    a.dev_b1 = P->b1; a.dev_b2 = P->b2; a.dev_ps = sparse ? P->p_s : nullptr;
+    a.dev_out = (unsigned long long*)out_int;
+    a.n_own_tiles = cdiv(a.own_total, TC_OWN);
+    a.n_own_units = cdiv(a.n_own_tiles, NCTA);
+    a.n_sw_tiles = cdiv(a.sw_total, SW);
+    const int units = num_sms() / NCTA;
+    // one chunk per row block where that fills the machine: nothing accumulates in TMEM here
+    a.tiles_per_chunk = a.n_sw_tiles;
+    while ((long long)a.n_own_units * cdiv(a.n_sw_tiles, a.tiles_per_chunk) < 2LL * units && a.tiles_per_chunk > 4)
+        a.tiles_per_chunk = (a.tiles_per_chunk + 1) / 2;
+    a.n_chunks = cdiv(a.n_sw_tiles, a.tiles_per_chunk);
+    a.n_items = a.n_own_units * a.n_chunks;
+    const int grid = NCTA * (a.n_items < units ? a.n_items : units);
+    auto kern = k_tc_pass<false, true, false, true, KP, false, true>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e_ != cudaSuccess) return set_error(ORI_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e_));
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e_ = cudaLaunchKernelEx(&cfg, kern, maps, a);
+    if (e_ != cudaSuccess) return set_error(ORI_ECUDA, "cudaLaunchKernelEx(k_tc_pass deviance): %s", cudaGetErrorString(e_));
+    return check_launch("k_tc_pass(deviance)");
+}
+
+// integer sums only (the float64 sums stay on the CUDA-core kernel); `pi`, `cmean` as for launch_deviance
+int launch_deviance_tc(const ori_problem_t* P, int g, const double* pi, const double* cmean, long long* out_int, cudaStream_t st) {
+#if ORI_TC_NEW == 8
+    if (P->KP == 64) return launch_deviance_tc_kp<64>(P, g, pi, cmean, out_int, st);
+    return launch_deviance_tc_kp<32>(P, g, pi, cmean, out_int, st);
+#else
+    return set_error(ORI_EUNSUPPORTED, "this build (ORI_TC_NEW != 8) has no deviance pass on the tensor path");
+#endif
 }
 
 int launch_pass_rows_tc(const ori_problem_t* P, int gen_old, cudaStream_t st) { return launch_tc_pass<false>(P, gen_old, st); }

@@ -431,6 +431,7 @@ class FactorModel(metaclass=ABCMeta):
         self._call('ori_mstep', _lib.ORI_M_REFRESH)
         self._dirty = False
         self._D_cache = None
+        self._ll_cache = None
 
     def _finalize(self):
         """Flush the one-pass lag: pi(t) and ELBO(t) of the current state (one extra sweep of X)."""
@@ -535,6 +536,7 @@ class FactorModel(metaclass=ABCMeta):
         for i, name in enumerate(('alpha1', 'alpha2', 'beta1', 'beta2')):
             self._hyper[i] = torch.as_tensor(np.asarray(state[name], dtype=np.float64), device=self._dev)
         self._keep_hyper = self._keep_hyper_arg
+        self._ll_cache = None
         self._started = False
         self._gen = 0
         self._iter = 0

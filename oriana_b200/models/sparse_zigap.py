@@ -136,6 +136,11 @@ class SparseZIGaP(ZIGaP):
         masked U_hat V_hat^T, X itself, column means of X."""
         if self._dirty:
             self._refresh()
+        # the reference's drivers print both metrics every iteration (main.py:37-44): one sweep of X serves both calls
+        key = (self._iter, self._gen, bool(want_f64))
+        cached = getattr(self, '_ll_cache', None)
+        if cached is not None and cached[0] == key and self._D_cache_valid_for_ll():
+            return cached[1]
         pi = self._current_pi()
         dev = self._dev
         if self._col_mean is None:
@@ -150,7 +155,17 @@ class SparseZIGaP(ZIGaP):
                    out_f.data_ptr() if want_f64 else None)
         self._shard.allreduce_sum(out_i)
         self._shard.allreduce_sum(out_f)
-        return out_i.cpu().numpy(), out_f.cpu().numpy()
+        res = (out_i.cpu().numpy(), out_f.cpu().numpy())
+        self._ll_cache = (key, res)
+        self._ll_epoch = self._state_epoch()
+        return res
+
+    def _state_epoch(self):
+        # changes whenever the state the metrics are computed from may have changed: steps, reloads, parameter edits
+        return (self._iter, self._gen, self._started, id(self._graphs) if self._graphs is not None else 0, self.graph_replays)
+
+    def _D_cache_valid_for_ll(self):
+        return getattr(self, '_ll_epoch', None) == self._state_epoch() and not self._dirty
 
     def reconstruction_deviance(self, int_quirk=True):
         """base.py:58-69.  `int_quirk=True` reproduces the reference's integer log-likelihood buffer

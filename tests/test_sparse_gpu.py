@@ -140,9 +140,10 @@ def test_sparse_tensor_paths_track_the_cuda_core_path(cuda_lib):
     med = lambda a, b: float(np.median(np.abs(a - b) / (np.abs(b) + 1e-12)))
     for k in ('a1', 'a2', 'b1', 'b2'):
         assert med(getattr(mp, k).asarray(), getattr(ms, k).asarray()) < 1e-5, k
-    for k in ('alpha1', 'alpha2', 'beta1', 'beta2', 'pi_s'):
+    for k in ('alpha1', 'alpha2', 'beta1', 'beta2'):
         assert relerr(getattr(mp, k).asarray(), getattr(ms, k).asarray()) < 5e-3, k
     assert med(mp.pi_d.asarray(), ms.pi_d.asarray()) < 1e-5
+    assert np.quantile(np.abs(mp.pi_s.asarray() - ms.pi_s.asarray()), 0.999) < 1e-3     # pi_s_j = mean_k p_s[j, k]
     assert np.mean((ps_s > 0.5) != (ps_p > 0.5)) < 1e-4
     assert np.mean(np.abs(ps_s - ps_p) > 0.05) < 5e-4
     dsq, dpq = ms.reconstruction_deviance(), mp.reconstruction_deviance()

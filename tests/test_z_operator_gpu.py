@@ -143,8 +143,9 @@ def test_tensor_sized_slabs_take_the_tcgen05_passes(cuda_lib, quirk):
         Zi, Zj, Z3 = outs[1]
         assert relerr(Zi, rZi) < 1e-3 and relerr(Zj, rZj) < 1e-3, (relerr(Zi, rZi), relerr(Zj, rZj))
         assert np.max(np.abs(Z3 - rZ3)) < 1e-3 * np.max(np.abs(rZ3))
-        for a, b in zip(outs[0], outs[1]):
+        for a, b in zip(outs[0][:2], outs[1][:2]):
             assert relerr(a, b) < 1e-5
+        assert np.max(np.abs(outs[0][2] - outs[1][2])) < 1e-5 * np.max(np.abs(outs[1][2]))     # signed terms cancel (zigap.py:95)
         gZi = np.full((n, K), np.nan, np.float32); gZj = np.full((p, K), np.nan, np.float32)
         _lib.check(cuda_lib.ori_gap_compute_Z_q_expectations_ctx(ctx, _ptr(gZi), _ptr(gZj), _ptr(lU), _ptr(lV), _ptr(X), n, p, K))
         rZi, rZj = zloop.gap_z(lU, lV, X)

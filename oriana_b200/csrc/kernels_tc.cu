@@ -1247,19 +1247,25 @@ static bool use_pair() { static int v = env_int("ORI_TC_PAIR", 1); return v != 0
 // accumulation truncates -- a chain of S accumulating MMAs comes out about S * 3e-8 low (measured: sum_ij D_ij (U V^T)_ij
 // at 100k x 20k differed by 8e-6 between a 2504-step and an 830-step chaining of the same state, and with it the ELBO by
 // 2e-5).  Items therefore hand their partial sums to global memory (round-to-nearest float atomics) every ORI_TC_CHUNK
-// sweep entries -- 512 accumulating steps per accumulator -- and, because the chunk length depends on nothing but the kernel
-// plan, every cell and gene sees the same chaining whatever the number of ranks or slabs the matrix is split into: the same
-// state evaluated by the device model and by host-streamed slabs now gives the same ELBO to 1e-8.  Measured cost at
-// 250k x 20k, K = 32 (rows / genes, ms): one chunk per row 4.91 / 7.11 (8192-cell gene chunks), 4096: 5.05 / 7.09,
-// 2048: 5.56 / 7.57, 1024: 6.63 / 8.49 (every item boundary drains the pipeline and reloads the own-side operands).
-// Problems too small to give every SM (pair) an item are split further.  (The gene pass also needs <= 8192 cells per item
-// for its fp32 running sums.)
+// sweep entries and, because the chunk length depends on nothing but the kernel plan, every cell and gene sees the same
+// chaining whatever the number of ranks or slabs the matrix is split into: the same state evaluated by the device model
+// and by host-streamed slabs gives the same ELBO to 1e-8 (it differed by 2e-5 ... 1e-4 when the chunking followed the
+// load balance).  Every item boundary drains the pipeline and reloads the own-side operands; measured at config 4
+// (1M x 20k, K = 32, one GPU, ms per step / row pass / gene pass): 4096: 53.9 / 21.0 / 31.5, 8192: 52.8 / 20.5 / 30.9,
+// 16384: 51.9 / 20.2 / 30.3.  The TF32-operand mode takes 16384 (2048 accumulating steps: a bias of ~3e-5, an order of
+// magnitude below its operand rounding); the fp32-grade mode 2048 (256 + 256 steps, ~4e-6).  Cutting the chain inside an
+// item instead (two accumulator sets in TMEM, the element-wise warps flushing one while the other accumulates) was built
+// and measured: 60.2 / 24.3 / 34.4 ms -- the flush code in the element-wise loop costs more than the drains it saves.
+// Problems too small to give every SM (pair) an item are split further.
 #ifndef ORI_TC_CHUNK
-#define ORI_TC_CHUNK 4096
+#define ORI_TC_CHUNK 16384
+#endif
+#ifndef ORI_TC_CHUNK_PRECISE
+#define ORI_TC_CHUNK_PRECISE 2048
 #endif
 static void tc_partition(TcArgs& a, bool genes, int units, int sw, bool precise) {
     (void)genes;
-    int tpc = (precise ? ORI_TC_CHUNK / 2 : ORI_TC_CHUNK) / sw;     // precise: two MMAs per 8 sweep entries and accumulator
+    int tpc = (precise ? ORI_TC_CHUNK_PRECISE : ORI_TC_CHUNK) / sw;
     if (tpc < 1) tpc = 1;
     if (tpc > a.n_sw_tiles) tpc = a.n_sw_tiles;
     const int min_tpc = (128 / sw) > 1 ? 128 / sw : 1;

@@ -76,6 +76,16 @@ class CompactCounts:
 
 class HostStreamedCAVI:
 
+    @staticmethod
+    def _default_slab(n, ldx):
+        """Cells per slab: up to ~1.5 GB of float32 X, a multiple of the tensor kernels' accumulation chunk (16384 sweep
+        entries, csrc/kernels_tc.cu ORI_TC_CHUNK) where the matrix is that long -- the gene-side sums of a slab are then chained
+        exactly like those of a device-resident matrix, so both give the same numbers -- else a multiple of 128."""
+        rows = min(n, (1536 << 20) // (4 * ldx))
+        if rows >= 16384:
+            return rows // 16384 * 16384
+        return max(128, rows // 128 * 128)
+
     def __init__(self, X_host, k, state, dropout=True, compat_quirk=False, slab_rows=None, sharded=False,
                  process_group=None, elbo=True, keep_hyper=True, precise=False):
         """X_host: CPU tensor [n, p] (pin it for asynchronous copies), float32 like the array the reference
@@ -94,7 +104,7 @@ class HostStreamedCAVI:
         self.n, self.p = int(X_host.shape[0]), int(X_host.shape[1])
         self.k = int(k)
         ldx0 = (self.p + 3) // 4 * 4
-        S0 = slab_rows if slab_rows is not None else max(128, min(self.n, (512 << 20) // (4 * ldx0)) // 128 * 128)
+        S0 = slab_rows if slab_rows is not None else self._default_slab(self.n, ldx0)
         S0 = int(min(max(1, S0), max(1, self.n)))
         # slabs large enough to fill the machine take the tcgen05/TMA kernels (K <= 64), like the device model
         self._tensor = self.k <= (32 if precise else 64) and S0 * self.p >= (1 << 21)
@@ -108,7 +118,7 @@ class HostStreamedCAVI:
             | (_lib.ORI_F_PRECISE if (precise and self._tensor and self.k <= 32) else 0)
         ldx = self._ldx = (p + 3) // 4 * 4
         if slab_rows is None:
-            slab_rows = max(128, min(n, (512 << 20) // (4 * ldx)) // 128 * 128)
+            slab_rows = self._default_slab(n, ldx)
         self.slab = S = int(min(max(1, slab_rows), max(1, n)))
         self.h2d_bytes = 0
         self.d2h_bytes = 0

@@ -410,7 +410,10 @@ def main():
         del model
         # counts are small integers: by default the host keeps them as saturating uint8 + an escape list for the
         # counts >= 255 (lossless, oriana_b200.host_step.CompactCounts): one byte per entry crosses PCIe per step
-        from oriana_b200.host_step import CompactCounts
+        from oriana_b200.host_step import CompactCounts, bind_host_thread_to_gpu
+        # pinned host buffers next to this rank's GPU: allocate them from the cores NVML calls local to it
+        all_cores = os.sched_getaffinity(0)
+        numa_cores = bind_host_thread_to_gpu(local)
         if args.e2e_x == 'u8esc':
             Xh = CompactCounts.from_tensor(X[:, :p])
             xdesc = 'uint8 + %d escapes (counts >= 255)' % Xh.row.numel()
@@ -437,11 +440,12 @@ def main():
             dist.all_reduce(hb)
         e2e = {'value': n * p * n_e2e / dt, 'unit': UNIT, 'h2d_bytes_per_step': float(hb[0]) / n_e2e,
                'd2h_bytes_per_step': float(hb[1]) / n_e2e, 'steps': n_e2e, 'ms_per_step': dt / n_e2e * 1e3,
-               'host_x_dtype': xdesc,
+               'host_x_dtype': xdesc, 'host_cores_bound': (None if numa_cores is None else '%d cores: %d-%d' % (len(numa_cores), numa_cores[0], numa_cores[-1])),
                # the host-streamed run continues the device run: its first step reports the ELBO of the device model's
                # last state
                'elbo_first_vs_device': abs(e_first - float(trace[-1])) / abs(float(trace[-1])),
                'api': 'oriana_b200.host_step.HostStreamedCAVI.step (pinned host X, a1, a2, b1, b2 in; results out)'}
+        os.sched_setaffinity(0, all_cores)          # the CPU arm below gets every host core again
 
     # ---- the reference's CPU path beside it (rank 0, N=1 only): the unmodified reference on a bounded slab, and the
     #      multi-core numpy/BLAS port of the same step as the fair comparison

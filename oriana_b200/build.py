@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'liboriana_b200.so')
-SOURCES = ['api.cu', 'kernels_simt.cu', 'synth.cu', 'kernels_tc.cu', 'host_step.cu']
+SOURCES = ['api.cu', 'kernels_simt.cu', 'synth.cu', 'kernels_tc.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 

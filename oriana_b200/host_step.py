@@ -21,6 +21,28 @@ from .models.base import pad_k
 from .sharding import RowSharding
 
 
+def bind_host_thread_to_gpu(device_index):
+    """Pin the calling process to the CPU cores NVML names as local to GPU `device_index` (its NUMA node), so that the
+    pinned buffers allocated afterwards are first-touched -- i.e. placed -- on that node and the copy threads run next to
+    them.  Returns the core list, or None when NVML / the affinity call is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = [64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cores = sorted(c for c in cores if c in allowed)
+        if not cores:
+            return None
+        os.sched_setaffinity(0, cores)
+        return cores
+    except Exception:
+        return None
+
+
 class CompactCounts:
     """A count matrix held on the host as saturating uint8 plus an escape list for the (rare) counts >= 255:
     one byte per entry crosses PCIe per step instead of four.  Lossless: `dense()` gives the counts back.

@@ -240,3 +240,50 @@ def test_row_blocks_cover_all_cells():
         assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
         sizes = [b - a for a, b in blocks]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_bench_initial_state_does_not_depend_on_the_sharding():
+    """bench.py starts every world size from the same model: the row-side draws are keyed by the GLOBAL row block."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    n, p, K = 30_000, 50, 4
+    whole = bench.initial_state(n, p, K, 0, n)
+    for world in (2, 3, 8):
+        parts = []
+        for r in range(world):
+            r0, r1 = n * r // world, n * (r + 1) // world
+            s = bench.initial_state(n, p, K, r0, r1)
+            parts.append(s['a1'])
+            for k in ('b1', 'alpha1', 'beta1'):
+                assert np.array_equal(s[k], whole[k])
+        assert np.array_equal(np.concatenate(parts), whole['a1'])
+    assert bench.elbo_vs_n1('no-such-config', 1, 1, 1, -5.0) == 0.0 and bench.elbo_vs_n1('no-such-config', 1, 1, 2, -5.0) is None
+
+
+def test_reference_install_is_importable_and_steps():
+    """The reference arm of bench.py and tests/test_reference_seam_gpu.py run the UNMODIFIED reference from baseline/_ref
+    (installed by __graft_entry__.build(), oracle/refshim.py): it imports under the alias shim and steps."""
+    import warnings
+    from oracle import refshim, cavi_numpy as cn
+    if not refshim.available():
+        pytest.skip('no reference install and no checkout here')
+    X = cn.synth_counts(40, 30, 3, seed=1)
+    refshim.import_reference()
+    try:
+        from oriana.models import ZIGaP
+        from oriana.singlecell import CountMatrix
+        import oriana
+        assert 'baseline' in oriana.__file__ or 'reference' in oriana.__file__
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            np.random.seed(0)
+            m = ZIGaP(CountMatrix(X), k=3, use_factors=False)
+            m.step()
+        assert np.isfinite(m.a1[:]).all() and m.a1[:].shape == (40, 3)
+    finally:
+        refshim.release_reference()
+    import oriana as ours                        # the repo's alias package is importable again
+    assert hasattr(ours, 'models') and 'oriana_b200' in ours.models.__name__

@@ -308,7 +308,13 @@ class FactorModel(metaclass=ABCMeta):
         dst[:, :K] = torch.clamp(torch.nan_to_num(v), min=1e-15).to(torch.float32)   # zigap.py:63,73
 
     def _draw_factor_inits(self):
-        """zigap.py:58-75 / gap.py:49-65: a1, b1 from the NMF factors or Gamma(1) draws; a2 = b2 = 1."""
+        """zigap.py:58-75 / gap.py:49-65: a1, b1 from the NMF factors or Gamma(1) draws; a2 = b2 = 1.
+
+        RNG stream: the reference's constructor ALWAYS runs sklearn's NMF (base.py:37-40), whose default initialisation
+        draws from the global `np.random` state, before it reaches these Gamma(1) draws; with `use_factors=False` this
+        class skips the factorisation (it is discarded by the reference in that case), so after `np.random.seed(s)` the
+        draws below are NOT the reference's.  Parity runs therefore copy the state vector out of a constructed reference
+        model (`state=`) instead of re-deriving it from a seed."""
         if self.use_factors:
             a1, b1 = self._nmf_U, self._nmf_V
         else:

@@ -51,6 +51,9 @@ extern "C" {
                                  take R, D_hat and the factor operands split hi/lo (tf32 + one bf16 chain for the cross terms)
                                  like den and U.V^T: every sum fp32-grade (~2^-21) instead of TF32-grade; about half the rate.
                                  K > 32 with this flag runs the CUDA-core kernels                                           */
+#define ORI_F_FIXED_CHAIN 128u /* this problem is a row slab of a larger matrix (host-streamed steps): keep the tensor kernels'
+                                 accumulation chunks at their nominal length even when the slab is too small to fill the
+                                 machine, so that its sums are chained -- and rounded -- like the resident matrix's          */
 
 /* modes of ori_mstep */
 #define ORI_M_STEP 0          /* regular end of iteration t+1: finalise ELBO(t), pi(t); M-step; next lp   */

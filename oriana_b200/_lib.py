@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('ORIANA_B200_LIB') or os.path.join(_HERE, 'lib', 'liboriana_b200.so')   # override: kernel A/B runs
 
 ORI_F_DROPOUT, ORI_F_QUIRK, ORI_F_ELBO, ORI_F_NO_TENSOR, ORI_F_SPARSE, ORI_F_DEVICE_ITER, ORI_F_PRECISE = 1, 2, 4, 8, 16, 32, 64
+ORI_F_FIXED_CHAIN = 128
 ORI_M_STEP, ORI_M_INIT, ORI_M_INIT_KEEP, ORI_M_FINALIZE, ORI_M_REFRESH = 0, 1, 2, 3, 4
 R64_NSLOTS = 8
 SCAL_SLOTS = 16

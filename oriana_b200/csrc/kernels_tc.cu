@@ -1263,13 +1263,17 @@ static bool use_pair() { static int v = env_int("ORI_TC_PAIR", 1); return v != 0
 #ifndef ORI_TC_CHUNK_PRECISE
 #define ORI_TC_CHUNK_PRECISE 2048
 #endif
-static void tc_partition(TcArgs& a, bool genes, int units, int sw, bool precise) {
-    (void)genes;
-    int tpc = (precise ? ORI_TC_CHUNK_PRECISE : ORI_TC_CHUNK) / sw;
+static void tc_partition(TcArgs& a, bool genes, int units, int sw, bool precise, bool fixed_chain) {
+    // the row pass sweeps the genes: its chaining depends on p only (not on the sharding / slabbing of the cells), so its
+    // chunks may be twice as long -- one item per row block up to p = 32768 -- at the same accumulation bias
+    int tpc = (precise ? ORI_TC_CHUNK_PRECISE : (genes ? ORI_TC_CHUNK : 2 * ORI_TC_CHUNK)) / sw;
     if (tpc < 1) tpc = 1;
     if (tpc > a.n_sw_tiles) tpc = a.n_sw_tiles;
     const int min_tpc = (128 / sw) > 1 ? 128 / sw : 1;
-    while ((long long)a.n_own_units * cdiv(a.n_sw_tiles, tpc) < units && tpc > min_tpc) tpc = (tpc + 1) / 2;
+    // small problems: split further, but only when fewer than half of the units would get an item -- a 16384-row slab
+    // (64 row-block pairs) keeps the chaining of a large matrix
+    // (never for a slab of a larger matrix -- ORI_F_FIXED_CHAIN -- whose sums must be chained like the resident matrix's)
+    while (!fixed_chain && (long long)a.n_own_units * cdiv(a.n_sw_tiles, tpc) < units / 2 && tpc > min_tpc) tpc = (tpc + 1) / 2;
     a.tiles_per_chunk = tpc;
     a.n_chunks = cdiv(a.n_sw_tiles, a.tiles_per_chunk);
     a.n_items = a.n_own_units * a.n_chunks;
@@ -1330,7 +1334,7 @@ static int launch_tc_pass_p(const ori_problem_t* P, int gen_old, cudaStream_t st
     a.n_own_units = cdiv(a.n_own_tiles, NCTA);
     a.n_sw_tiles = cdiv(a.sw_total, SW);
     const int units = num_sms() / NCTA;
-    tc_partition(a, GENES, units, SW, PRECISE);
+    tc_partition(a, GENES, units, SW, PRECISE, (P->flags & ORI_F_FIXED_CHAIN) != 0);
     const int grid = NCTA * (a.n_items < units ? a.n_items : units);
     int rc;
     if (drop && elbo) rc = launch_tc_variant<GENES, true, true, PAIR, KP, PRECISE>(maps, a, grid, st);

@@ -100,12 +100,12 @@ class HostStreamedCAVI:
 
     @staticmethod
     def _default_slab(n, ldx):
-        """Cells per slab: up to ~1.5 GB of float32 X, a multiple of the tensor kernels' accumulation chunk (16384 sweep
+        """Cells per slab: up to 32768 cells / 4 GB of float32 X, a multiple of the tensor kernels' accumulation chunk (16384 sweep
         entries, csrc/kernels_tc.cu ORI_TC_CHUNK) where the matrix is that long -- the gene-side sums of a slab are then chained
         exactly like those of a device-resident matrix, so both give the same numbers -- else a multiple of 128."""
-        rows = min(n, (1536 << 20) // (4 * ldx))
+        rows = min(n, (4 << 30) // (4 * ldx))
         if rows >= 16384:
-            return rows // 16384 * 16384
+            return min(rows // 16384 * 16384, 32768)
         return max(128, rows // 128 * 128)
 
     def __init__(self, X_host, k, state, dropout=True, compat_quirk=False, slab_rows=None, sharded=False,
@@ -137,7 +137,8 @@ class HostStreamedCAVI:
         self.dropout = bool(dropout)
         self._flags = (_lib.ORI_F_DROPOUT if dropout else 0) | (_lib.ORI_F_ELBO if elbo else 0) \
             | (_lib.ORI_F_QUIRK if (compat_quirk and dropout) else 0) \
-            | (_lib.ORI_F_PRECISE if (precise and self._tensor and self.k <= 32) else 0)
+            | (_lib.ORI_F_PRECISE if (precise and self._tensor and self.k <= 32) else 0) \
+            | (_lib.ORI_F_FIXED_CHAIN if self.n > S0 else 0)
         ldx = self._ldx = (p + 3) // 4 * 4
         if slab_rows is None:
             slab_rows = self._default_slab(n, ldx)

@@ -251,6 +251,12 @@ def test_host_streamed_step_on_the_tensor_path(cuda_lib):
         assert relerr(hs[k], getattr(m, k).asarray()) < 1e-4, k
     want = m.elbo_trace[:3]
     assert np.max(np.abs(np.asarray(elbos) - want) / np.abs(want)) < 1e-5
+    # a host-streamed run resumed from the device model's mid-run state reports, with its first step, the ELBO of that state
+    # (slabs shorter than the kernels' accumulation chunk are chained differently from the resident matrix: 2e-5; slabs that
+    # are multiples of the chunk -- the default -- agree to 1e-7, bench.py `elbo_first_vs_device`)
+    h2 = HostStreamedCAVI(Xh, K, m.state_dict(), dropout=True, slab_rows=2048)
+    e2 = h2.step()
+    assert abs(e2 - m.elbo()) < 2e-5 * abs(e2), (e2, m.elbo())
 
 
 def test_config5_slab_tensor_path_matches_cuda_core_path(cuda_lib):

@@ -143,6 +143,52 @@ def write_sparse_nmf_fixture():
     print('sparse_nmf written')
 
 
+def write_loglik_fixture():
+    """FactorModel.loglikelihood() (base.py:89-95) of the reference's GaP along the trajectories of the gap_* cases
+    above (same seeds, so the states are the recorded ones).  ZIGaP has no such value: its X node is a Multiply node
+    without `loglikelihood` (AttributeError in the reference), which the fixture records as a flag."""
+    refshim.import_reference()
+    from oriana.models import ZIGaP, GaP
+    from oriana.singlecell import CountMatrix
+    out = {}
+    for name, model, n, p, K, rec, zinb in CASES:
+        if model != 'GaP':
+            continue
+        X = cn.synth_counts(n, p, K, seed=len(name) * 7 + n, zinb=zinb)
+        np.random.seed(1)
+        m = GaP(CountMatrix(X), k=K, use_factors=False)
+        for t in range(1, max(rec) + 1):
+            m.step()
+            if t in rec:
+                out['%s_s%d' % (name, t)] = np.float64(m.loglikelihood())
+    X = cn.synth_counts(20, 30, 2, seed=3)
+    np.random.seed(1)
+    z = ZIGaP(CountMatrix(X), k=2, use_factors=False)
+    try:
+        z.loglikelihood(); out['zigap_raises'] = np.bool_(False)
+    except AttributeError:
+        out['zigap_raises'] = np.bool_(True)
+    # node-level logp() with the reference's own broadcasting (gamma.py:63-68, bernoulli.py:50-52, poisson.py:64-73)
+    from oriana import Dimensions, Parameter
+    from oriana.nodes import Gamma, Bernoulli, Poisson
+    rng = np.random.default_rng(11)
+    dims = Dimensions({'n': 6, 'k': 3, 'm': 4})
+    al, be = rng.uniform(0.5, 4., 3), rng.uniform(0.5, 3., 3)
+    g = Gamma(Parameter(al), Parameter(be), dims('n,k ~ s,d'))
+    gs = rng.gamma(2., size=(6, 3)); g.buffer = gs
+    out.update(node_gamma_alpha=al, node_gamma_beta=be, node_gamma_samples=gs, node_gamma_logp=g.logp())
+    pi = rng.uniform(0.05, 0.95, 4)
+    b = Bernoulli(Parameter(pi), dims('n,m ~ s,d'))
+    bs = (rng.uniform(size=(6, 4)) < 0.5).astype(np.float64); b.buffer = bs
+    out.update(node_bern_pi=pi, node_bern_samples=bs, node_bern_logp=b.logp())
+    lam = rng.gamma(2., size=(6, 4)); lam[0, 0] = 0.; lam[1, 2] = 0.
+    po = Poisson(Parameter(lam), dims('n,m ~ d,d'))
+    ps = rng.poisson(2., size=(6, 4)).astype(np.float64); ps[0, 0] = 0.; ps[1, 2] = 3.; po.buffer = ps
+    out.update(node_pois_lambda=lam, node_pois_samples=ps, node_pois_logp=po.logp())
+    np.savez_compressed(os.path.join(OUT, 'loglik.npz'), **out)
+    print('loglik written', {k: (float(v) if np.ndim(v) == 0 else np.shape(v)) for k, v in out.items()})
+
+
 def write_nmf_fixture():
     """The reference's DEFAULT construction path, `use_factors=True` (base.py:38-40: a1, b1 seeded with sklearn NMF
     factors, many of them tiny or exactly 0, so E[log U] reaches -100 ... -1e15 and exp(E log U) underflows float32 on
@@ -176,6 +222,8 @@ def main():
         return write_generator_fixture()
     if sys.argv[1:] == ['nmf']:
         return write_nmf_fixture()
+    if sys.argv[1:] == ['loglik']:
+        return write_loglik_fixture()
     if sys.argv[1:] == ['sparse_gen']:
         return write_sparse_generator_fixture()
     if sys.argv[1:] == ['sparse_nmf']:

@@ -571,6 +571,24 @@ class FactorModel(metaclass=ABCMeta):
         tot = self._shard.allreduce_sum(tot.reshape(1))[0]
         return float(torch.sqrt(tot).item())
 
+    def loglikelihood(self):
+        """base.py:89-95: log p(U) + log p(V) + log p(X | U V^T) at the current expectations, summed by the graph nodes
+        themselves (the reference's own per-node formulas).  Like the reference this materialises U V^T as an n x p
+        float64 array (here on the device, released before returning), so it is for small problems; and like the
+        reference it only exists where the X node is probabilistic (GaP): ZIGaP's X is a `Multiply` node, which has no
+        `loglikelihood` (AttributeError in the reference too).  The node formulas are the reference's, quirks included:
+        Gamma terms summed over every (factor column, parameter column) pair, Poisson terms without log x! and
+        truncated to integers when the count matrix came in an integer dtype (tests/golden/loglik.npz)."""
+        x_ll = self.X.loglikelihood                                   # AttributeError for deterministic X, before any work
+        self.U.buffer = self._Uhat[self._gen][:, :self.k].double()
+        self.V.buffer = self._Vhat[:, :self.k].double()
+        self.UV.forward()
+        try:
+            local = torch.tensor([self.U.loglikelihood() + x_ll()], dtype=torch.float64, device=self._dev)
+        finally:
+            self.UV._t = None
+        return float(self._shard.allreduce_sum(local)[0].item()) + self.V.loglikelihood()
+
     # ------------------------------------------------------------------------------------------------
     @abstractmethod
     def build_u_node(self):

@@ -5,6 +5,7 @@ The Gamma rates are column sums (gap.py:98,106); the latent-count step is the dr
 the same CUDA kernels.
 """
 import numpy as np
+import torch
 
 from ..nodes import Gamma, Poisson
 from .base import FactorModel
@@ -28,6 +29,9 @@ class GaP(FactorModel):
     def build_x_node(self, cmatrix, UV):
         X = Poisson(UV, self.dims('n,m ~ d,d'), name='X')
         X.buffer = self._X                                              # gap.py:30 (device view, no copy)
+        src = cmatrix.as_tensor()                                       # the dtype the reference's buffer would have
+        X.integer_samples = not src.dtype.is_floating_point if isinstance(src, torch.Tensor) \
+            else bool(np.issubdtype(src.dtype, np.integer))
         return X
 
     def define_variational_distribution(self):

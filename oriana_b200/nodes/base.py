@@ -26,6 +26,7 @@ class Node:
         self.children = []
         self.fixed = False
         self._t = None
+        self.integer_samples = False
         for parent in parents:
             if isinstance(parent, Node):
                 parent.add_child(self)
@@ -62,9 +63,13 @@ class Node:
 
     @buffer.setter
     def buffer(self, data):
+        # `integer_samples`: the reference keeps the dtype of whatever was assigned, and Poisson.logp() allocates its
+        # result with it (poisson.py:68) -- per-entry log-probabilities of integer counts are truncated to integers
         if isinstance(data, torch.Tensor):
             self._t = data                       # adopt a device tensor as is (no copy, any dtype)
+            self.integer_samples = not (data.dtype.is_floating_point or data.dtype.is_complex)
         else:
+            self.integer_samples = bool(np.issubdtype(np.asarray(data).dtype, np.integer))
             dtype = self._t.dtype if self._t is not None else torch.float64
             self._t = as_tensor(data, dtype=dtype)
 

@@ -49,11 +49,14 @@ class Gamma(ProbabilisticNode):
         return draws.unsqueeze(-1)
 
     def _logp(self, samples, alpha, beta):
-        # the reference's own (unnormalised-rate) formula, gamma.py:63-68
+        # the reference's own formula AND broadcasting (gamma.py:63-68): `beta` enters as a scale, the normaliser is
+        # log(gamma(alpha)) (infinite past alpha = 171.6), and the flat parameter vectors broadcast against the
+        # (n, m, 1) samples, so the result is (n, m, m): entry [i, a, b] pairs sample (i, a) with parameters b
         a = alpha.reshape(-1).double(); b = beta.reshape(-1).double()
-        s = samples.squeeze(-1)
-        out = (a - 1.) * log(s) - s / b - a * log(b) - torch.lgamma(a)
-        return out.unsqueeze(-1)
+        s = samples.double()
+        out = (a - 1.) * log(s) - (s / b)
+        out = out + (-a * log(b) - log(torch.exp(torch.lgamma(a))))
+        return out
 
 
 class Bernoulli(ProbabilisticNode):
@@ -72,9 +75,10 @@ class Bernoulli(ProbabilisticNode):
         return torch.bernoulli(p).unsqueeze(-1)
 
     def _logp(self, samples, pi):
+        # bernoulli.py:50-52, with its broadcasting: (n, m, 1) samples against the flat (m,) parameters -> (n, m, m)
         p = pi.reshape(-1).double()
-        s = samples.squeeze(-1)
-        return (s * log(p) + (1. - s) * log(1. - p)).unsqueeze(-1)
+        s = samples.double()
+        return s * log(p) + (1. - s) * log(1. - p)
 
 
 class Poisson(ProbabilisticNode):
@@ -92,9 +96,13 @@ class Poisson(ProbabilisticNode):
         return torch.poisson(l).unsqueeze(-1)
 
     def _logp(self, samples, lam):
+        # poisson.py:64-73: flat result, no log-factorial term, 0 where both are zero, -1000 for a count at rate zero;
+        # the result array has the dtype of the samples (`np.empty_like`, :68), so integer counts truncate every entry
         l = lam.reshape(-1).double()
-        s = samples.squeeze(-1)
-        return (s * log(l) - l - torch.lgamma(s + 1.)).unsqueeze(-1)
+        s = samples.reshape(-1).double()
+        zero_rate = torch.where(s > 0, torch.full_like(s, -1000.), torch.zeros_like(s))
+        out = torch.where(l > 0, -l + s * log(l), zero_rate)
+        return torch.trunc(out) if self.integer_samples else out
 
 
 class Multinomial(ProbabilisticNode):

@@ -516,3 +516,52 @@ def test_block_generator_on_device(cuda_lib):
 def torch_equal(a, b):
     import torch
     return bool(torch.equal(a, b))
+
+
+@pytest.mark.parametrize('name', ['gap_c1', 'gap_ragged'])
+def test_model_loglikelihood_matches_reference(cuda_lib, name):
+    """FactorModel.loglikelihood() (base.py:89-95) against the values the reference's GaP printed along the recorded
+    trajectories (tests/golden/loglik.npz, oracle/make_golden.py loglik); ZIGaP has none in the reference either."""
+    import os
+    from conftest import GOLDEN
+    ll = np.load(os.path.join(GOLDEN, 'loglik.npz'))
+    g = load_golden(name)
+    s = golden_state(g, 0)
+    m = make_model(s, quirk=True)
+    steps = [int(t) for t in g['steps']]
+    for t in range(1, max(steps) + 1):
+        m.step()
+        if t in steps:
+            want = float(ll['%s_s%d' % (name, t)])
+            got = m.loglikelihood()
+            assert abs(got - want) < 2e-4 * abs(want) + 1.0, (name, t, got, want)
+    assert bool(ll['zigap_raises'])
+    z = make_model(golden_state(load_golden('zigap_ragged'), 0), quirk=True)
+    with pytest.raises(AttributeError):
+        z.loglikelihood()
+
+
+def test_node_logp_matches_reference_including_its_broadcasting(cuda_lib):
+    """Gamma / Bernoulli / Poisson `logp()` against arrays the reference's own nodes returned (tests/golden/loglik.npz):
+    same formulas (gamma.py:63-68 uses beta as a scale; poisson.py:64-73 has no log-factorial term and the -1000 rule)
+    and the same result shapes ((n, m, m) from the flat parameter broadcast; flat for Poisson)."""
+    import os
+    from conftest import GOLDEN
+    from oriana import Dimensions, Parameter
+    from oriana.nodes import Bernoulli, Gamma, Poisson
+    f = np.load(os.path.join(GOLDEN, 'loglik.npz'))
+    dims = Dimensions({'n': 6, 'k': 3, 'm': 4})
+    g = Gamma(Parameter(f['node_gamma_alpha']), Parameter(f['node_gamma_beta']), dims('n,k ~ s,d'))
+    g.buffer = f['node_gamma_samples']
+    got = g.logp()
+    assert got.shape == f['node_gamma_logp'].shape == (6, 3, 3)
+    assert np.allclose(got, f['node_gamma_logp'], rtol=1e-12, atol=1e-12)
+    assert abs(g.loglikelihood() - f['node_gamma_logp'].sum()) < 1e-9
+    b = Bernoulli(Parameter(f['node_bern_pi']), dims('n,m ~ s,d'))
+    b.buffer = f['node_bern_samples']
+    assert b.logp().shape == (6, 4, 4) and np.allclose(b.logp(), f['node_bern_logp'], rtol=1e-12, atol=1e-12)
+    po = Poisson(Parameter(f['node_pois_lambda']), dims('n,m ~ d,d'))
+    po.buffer = f['node_pois_samples']
+    got = po.logp()
+    assert got.shape == (24,) and np.allclose(got, f['node_pois_logp'], rtol=1e-12, atol=1e-12)
+    assert got[0] == 0.0 and got[1 * 4 + 2] == -1000.0

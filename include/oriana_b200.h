@@ -132,6 +132,15 @@ typedef struct ori_problem {
      * ori_column_sums_f64 + all-reduce, as float32); required with ORI_F_ELBO, NULL otherwise. */
     const float* xrow;     /* [n_rows] */
     const float* xcol;     /* [p]      */
+
+    /* Float32-underflow emulation of the reference's multinomial step (zigap.py:86-90, gap.py:73-76), optional: both
+     * NULL = off (exact ratios everywhere).  thr = 2^-17 exp(-max_k E[log .]) per cell / gene, written next to eU / eV by
+     * ori_init_expectations, ori_row_update and ori_gene_update; the passes drop every term with
+     * eU_ik eV_jk <= thrU_i thrV_j -- the terms whose float32 exp(log_U_hat + log_V_hat) is 0 in the reference -- so an
+     * entry whose terms all underflow assigns its count to no component (den = 0 -> 1, :90).  CUDA-core kernels: per
+     * term; tcgen05 kernels: per entry (den < thrU_i thrV_j).  Not with ORI_F_SPARSE. */
+    float* thrU;           /* [2 x n_rows], per generation like eU */
+    float* thrV;           /* [p]                                  */
 } ori_problem_t;
 
 /* ---- library ---------------------------------------------------------------------------------- */

@@ -36,7 +36,7 @@ class OriProblem(C.Structure):
         ('tc_ws', C.c_void_p), ('tc_ws_floats', C.c_int64),
         ('p_s', C.c_void_p), ('logV', C.c_void_p), ('eVd', C.c_void_p), ('eVz', C.c_void_p), ('Vh_old', C.c_void_p),
         ('eUl', C.c_void_p * 2), ('pi_s', C.c_void_p), ('tau', C.c_double),
-        ('xrow', C.c_void_p), ('xcol', C.c_void_p),
+        ('xrow', C.c_void_p), ('xcol', C.c_void_p), ('thrU', C.c_void_p), ('thrV', C.c_void_p),
     ]
 
 

@@ -70,7 +70,8 @@ __global__ void k_gamma_expect(const float* __restrict__ a1, const float* __rest
 
 // operator-level helpers: padded exp of a [rows x K] log-expectation array, optional extra weight
 __global__ void k_exp_pad(const float* __restrict__ logE, const float* __restrict__ W, long long ldw,
-                          int mul_log, float* __restrict__ out, long long rows, int K, int KP) {
+                          int mul_log, float* __restrict__ out, long long rows, int K, int KP,
+                          float* __restrict__ thr_out = nullptr) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * KP) return;
     const long long i = idx / KP; const int k = (int)(idx % KP);
@@ -78,6 +79,7 @@ __global__ void k_exp_pad(const float* __restrict__ logE, const float* __restric
     if (k < K) {
         float m = -INFINITY;                       // centred exponent of the row (special.cuh): outputs are ratios
         for (int q = 0; q < K; ++q) m = fmaxf(m, logE[i * K + q]);
+        if (thr_out && k == 0) thr_out[i] = underflow_thr_f32(m);   // the reference's float32 exp underflow (zigap.py:86-90)
         const float l = logE[i * K + k];
         v = centred_exp_f32(l, m);
         if (W) v *= W[i * ldw + k];
@@ -344,8 +346,8 @@ struct ori_ctx {
     cudaStream_t st[2] = {nullptr, nullptr};
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     struct Buf { void* p = nullptr; size_t cap = 0; };
-    enum { X0, X1, D0, D1, LUS0, LUS1, EU0, EU1, EUW0, EUW1, EUL0, EUL1, ZI0, ZI1, OI0, OI1, WS0, WS1,
-           LVRAW, EV, ZJ, ZJ3A, ZJ3B, OUTJ, D64, NBUF };
+    enum { X0, X1, D0, D1, LUS0, LUS1, EU0, EU1, EUW0, EUW1, EUL0, EUL1, ZI0, ZI1, OI0, OI1, WS0, WS1, THRU0, THRU1,
+           LVRAW, EV, ZJ, ZJ3A, ZJ3B, OUTJ, D64, THRV, NBUF };
     Buf buf[NBUF];
     unsigned long long allocs = 0, calls = 0, tensor_slabs = 0, simt_slabs = 0;
     int64_t slab_rows = 0;     // 0: ~256 MB of X per slab
@@ -417,6 +419,7 @@ static int z_operator_ctx(ori_ctx* C, float* Zi_out, float* Zj_out, float* Z3_ou
         if (Z3_out) ORI_TRY(C->need(B::EUL0 + b, sizeof(float) * slab * KP));
         ORI_TRY(C->need(B::ZI0 + b, sizeof(float) * slab * KP));
         ORI_TRY(C->need(B::OI0 + b, sizeof(float) * slab * K));
+        ORI_TRY(C->need(B::THRU0 + b, sizeof(float) * slab));
         if (tensor) ORI_TRY(C->need(B::WS0 + b, sizeof(float) * ws_floats));
     }
     ORI_TRY(C->need(B::LVRAW, sizeof(float) * p * K));
@@ -426,6 +429,7 @@ static int z_operator_ctx(ori_ctx* C, float* Zi_out, float* Zj_out, float* Z3_ou
     ORI_TRY(C->need(B::ZJ3B, sizeof(float) * 2 * p * KP));
     ORI_TRY(C->need(B::OUTJ, sizeof(float) * p * K));
     ORI_TRY(C->need(B::D64, sizeof(double) * (p + 2 * KP + R64_NSLOTS)));
+    ORI_TRY(C->need(B::THRV, sizeof(float) * p));
 
     float* dlogVraw = C->as<float>(B::LVRAW);
     float* deV = C->as<float>(B::EV);
@@ -433,7 +437,9 @@ static int z_operator_ctx(ori_ctx* C, float* Zi_out, float* Zj_out, float* Z3_ou
     float* dOutJ = C->as<float>(B::OUTJ);
 
     ORI_CUDA(cudaMemcpyAsync(dlogVraw, logV, sizeof(float) * p * K, cudaMemcpyHostToDevice, st));
-    k_exp_pad<<<cdiv(p * KP, 256), 256, 0, st>>>(dlogVraw, nullptr, 0, 0, deV, p, (int)K, KP);
+    // the operator IS the reference's numba loop: its float32 exp underflow (den = 0 -> 1, zigap.py:86-90) is part of
+    // the contract here, so the thresholds are always on
+    k_exp_pad<<<cdiv(p * KP, 256), 256, 0, st>>>(dlogVraw, nullptr, 0, 0, deV, p, (int)K, KP, C->as<float>(B::THRV));
     ORI_TRY(check_launch("k_exp_pad"));
     ORI_CUDA(cudaMemsetAsync(dZj, 0, sizeof(float) * 2 * p * KP, st));
     ORI_CUDA(cudaMemsetAsync(dZj3a, 0, sizeof(float) * 2 * p * KP, st));
@@ -446,6 +452,7 @@ static int z_operator_ctx(ori_ctx* C, float* Zi_out, float* Zj_out, float* Z3_ou
     memset(&P, 0, sizeof(P));
     P.p = (int)p; P.K = (int)K; P.KP = KP; P.ldx = ldx;
     P.eV = deV; P.V_hat = deV;
+    P.thrV = C->as<float>(B::THRV);
     P.red64 = C->as<double>(B::D64);
 
     // gene sums of one slab (zigap.py:94): both streams add into the same accumulators with atomics
@@ -472,7 +479,7 @@ static int z_operator_ctx(ori_ctx* C, float* Zi_out, float* Zj_out, float* Z3_ou
         ORI_CUDA(cudaMemcpy2DAsync(x, sizeof(float) * ldx, X + r0 * p, sizeof(float) * p, sizeof(float) * p, nr, cudaMemcpyHostToDevice, s));
         if (D) ORI_CUDA(cudaMemcpy2DAsync(dD, sizeof(float) * ldx, D + r0 * p, sizeof(float) * p, sizeof(float) * p, nr, cudaMemcpyHostToDevice, s));
         ORI_CUDA(cudaMemcpyAsync(dlUs, logU + r0 * K, sizeof(float) * nr * K, cudaMemcpyHostToDevice, s));
-        k_exp_pad<<<cdiv(nr * KP, 256), 256, 0, s>>>(dlUs, nullptr, 0, 0, deU, nr, (int)K, KP);
+        k_exp_pad<<<cdiv(nr * KP, 256), 256, 0, s>>>(dlUs, nullptr, 0, 0, deU, nr, (int)K, KP, C->as<float>(B::THRU0 + b));
         if (D && quirk)   // zigap.py:94: weight of cell i for latent k is D_hat[i, k]
             k_exp_pad<<<cdiv(nr * KP, 256), 256, 0, s>>>(dlUs, dD, ldx, 0, deUw, nr, (int)K, KP);
         if (Z3_out)
@@ -492,6 +499,7 @@ static int z_operator_ctx(ori_ctx* C, float* Zi_out, float* Zj_out, float* Z3_ou
         P.n_rows = nr; P.n_total = n; P.flags = 0;
         P.eU[0] = deU; P.U_hat[0] = deU; P.U_hat[1] = deU;
         P.Zi = dZi;
+        P.thrU = C->as<float>(B::THRU0 + b);
         P.tc_ws = tensor ? C->as<float>(B::WS0 + b) : nullptr;
         P.tc_ws_floats = tensor ? (int64_t)ws_floats : 0;
         // row sums (zigap.py:93)

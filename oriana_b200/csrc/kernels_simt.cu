@@ -53,9 +53,11 @@ k_pass_rows(const float* __restrict__ X, long long ldx, long long n_rows, int p,
             const float* __restrict__ eVz, const float* __restrict__ Vc,
             const float* __restrict__ lp, const float* __restrict__ pfloor,
             float* __restrict__ Zi, float* __restrict__ a2s,
-            double* __restrict__ colsum, double* __restrict__ part64)
+            double* __restrict__ colsum, double* __restrict__ part64,
+            const float* __restrict__ thrU, const float* __restrict__ thrV)
 {
     __shared__ float sX[PR_TR][PR_TG + 1];
+    __shared__ float sthr[PR_TG];
     __shared__ __align__(16) float sV[PR_TG][KP];
     __shared__ __align__(16) float sVh[DROPOUT ? PR_TG : 1][KP];
     __shared__ __align__(16) float sVz[SPARSE ? PR_TG : 1][KP];
@@ -77,6 +79,7 @@ k_pass_rows(const float* __restrict__ X, long long ldx, long long n_rows, int p,
         if (DROPOUT) { uh[k] = row_ok ? Uh[row * KP + k] : 0.f; as[k] = 0.f; }
     }
     double acc_xl = 0.0, acc_ent = 0.0;
+    const float tu = (thrU && row_ok) ? thrU[row] : 0.f;         // underflow emulation (special.cuh); 0: never triggers
 
     const int ntiles = (p + PR_TG - 1) / PR_TG;
     for (int t = blockIdx.y; t < ntiles; t += gridDim.y) {
@@ -108,6 +111,7 @@ k_pass_rows(const float* __restrict__ X, long long ldx, long long n_rows, int p,
             slp[tid] = tid < gcount ? lp[j0 + tid] : 0.f;
             sfl[tid] = tid < gcount ? pfloor[j0 + tid] : 0.f;
         }
+        if (tid < PR_TG) sthr[tid] = (thrV && tid < gcount) ? thrV[j0 + tid] : 0.f;
         __syncthreads();
 
         float t_xl = 0.f, t_ent = 0.f;
@@ -129,7 +133,19 @@ k_pass_rows(const float* __restrict__ X, long long ldx, long long n_rows, int p,
             }
             const bool nz = x != 0.f;
             den = den > 0.f ? den : 1.f;                 // zigap.py:90
-            const float R = x / den;
+            float R = x / den;
+            const float T = tu * sthr[g];
+            if (!SPARSE && nz && T > 0.f && den < T * UFL_NEAR) {
+                // some term of this entry is (or is close to) one the reference's float32 exp flushes to 0 (zigap.py:86):
+                // redo the entry from its terms, dropping those; nothing survives -> den = 1, no count assigned (:90)
+                float d2 = 0.f;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) { const float tk = eu[k] * sV[g][k]; d2 += tk > T ? tk : 0.f; }
+                const float r2 = d2 > 0.f ? x / d2 : 0.f;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) { const float vk = sV[g][k]; if (eu[k] * vk > T) zi[k] = fmaf(r2, vk, zi[k]); }
+                R = 0.f;
+            }
             float D = 1.f;
             if (DROPOUT) {
                 float e, ex;
@@ -204,8 +220,10 @@ k_pass_genes(const float* __restrict__ X, long long ldx, long long n_rows, int p
              const float* __restrict__ Un, const float* __restrict__ eUl,
              const float* __restrict__ eV, const float* __restrict__ Vh,
              const float* __restrict__ lp, const float* __restrict__ pfloor,
-             float* __restrict__ Zj, float* __restrict__ b2s, float* __restrict__ Zl)
+             float* __restrict__ Zj, float* __restrict__ b2s, float* __restrict__ Zl,
+             const float* __restrict__ thrU, const float* __restrict__ thrV)
 {
+    __shared__ float sthr[PG_TR];
     __shared__ __align__(16) float sUl[SPARSE ? PG_TR : 1][KP];
     __shared__ __align__(16) float sU[PG_TR][KP];
     __shared__ __align__(16) float sUw[QUIRK ? PG_TR : 1][KP];
@@ -228,6 +246,7 @@ k_pass_genes(const float* __restrict__ X, long long ldx, long long n_rows, int p
     }
     const float lpj = (DROPOUT && j_ok) ? lp[j] : 0.f;
     const float flj = (DROPOUT && j_ok) ? pfloor[j] : 0.f;
+    const float tv = (thrV && j_ok) ? thrV[j] : 0.f;            // underflow emulation (special.cuh); 0: never triggers
 
     float* sUf = &sU[0][0]; float* sUwf = &sUw[0][0]; float* sUhf = &sUh[0][0]; float* sUnf = &sUn[0][0];
     float* sUlf = &sUl[0][0];
@@ -245,6 +264,7 @@ k_pass_genes(const float* __restrict__ X, long long ldx, long long n_rows, int p
                 sUnf[idx] = ok ? Un[r0 * KP + idx] : 0.f;
             }
         }
+        if (tid < PG_TR) sthr[tid] = (thrU && tid < rcount) ? thrU[r0 + tid] : 0.f;
         __syncthreads();
         for (int rb = 0; rb < PG_TR; rb += 8) {
             float xs[8];
@@ -273,7 +293,18 @@ k_pass_genes(const float* __restrict__ X, long long ldx, long long n_rows, int p
                     }
                 }
                 den = den > 0.f ? den : 1.f;
-                const float R = x / den;
+                float R = x / den;
+                const float T = tv * sthr[rr];
+                if (!SPARSE && x != 0.f && T > 0.f && den < T * UFL_NEAR) {     // see k_pass_rows
+                    float d2 = 0.f;
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) { const float tk = sU[rr][k] * ev[k]; d2 += tk > T ? tk : 0.f; }
+                    const float r2 = d2 > 0.f ? x / d2 : 0.f;
+#pragma unroll
+                    for (int k = 0; k < KP; ++k)
+                        if (sU[rr][k] * ev[k] > T) zj[k] = fmaf(r2, QUIRK ? sUw[QUIRK ? rr : 0][k] : sU[rr][k], zj[k]);
+                    R = 0.f;
+                }
                 float D = 1.f;
                 if (DROPOUT) {
                     float e, ex;
@@ -327,7 +358,8 @@ k_factor_update(long long rows, int K, int KP,
                 float* __restrict__ E_new, float* __restrict__ eE_new, float* __restrict__ eEl_new,
                 const float* __restrict__ xsum,
                 double* __restrict__ Slog, double* __restrict__ Shat,
-                double* __restrict__ Hsum, double* __restrict__ PUVsum, int write_state)
+                double* __restrict__ Hsum, double* __restrict__ PUVsum, int write_state,
+                float* __restrict__ thr_out)
 {
     __shared__ double sSlog[64], sShat[64], sH, sP;
     __shared__ float smax[8];
@@ -370,6 +402,7 @@ k_factor_update(long long rows, int K, int KP,
         }
         const bool dead = !(m > EXP_DEAD);
         const double shift = dead ? 0.0 : EXP_CENTER - (double)m;
+        if (thr_out && write_state && in && k == 0) thr_out[idx / KP] = underflow_thr_f32(m);
         if (!live) {
             if (in && write_state) {
                 E_new[idx] = 0.f; eE_new[idx] = 0.f;
@@ -902,7 +935,8 @@ static int pass_rows_kp(const ori_problem_t* P, int g, cudaStream_t st) {
     if (P->flags & ORI_F_SPARSE) {
         if constexpr (KP <= 32) {
             k_pass_rows<KP, true, false, true><<<grid, PR_TR, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, P->eU[g],
-                P->U_hat[g], P->eVd, P->Vh_old, P->eVz, P->V_hat, P->lp, P->pfloor, P->Zi, P->a2s, colsum, part);
+                P->U_hat[g], P->eVd, P->Vh_old, P->eVz, P->V_hat, P->lp, P->pfloor, P->Zi, P->a2s, colsum, part,
+                nullptr, nullptr);
             return check_launch("k_pass_rows(sparse)");
         } else {
             return set_error(ORI_EUNSUPPORTED, "the sparse model needs K <= 32");
@@ -910,7 +944,9 @@ static int pass_rows_kp(const ori_problem_t* P, int g, cudaStream_t st) {
     }
 #define ORI_LAUNCH_PR(D, E)                                                                              \
     k_pass_rows<KP, D, E, false><<<grid, PR_TR, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, P->eU[g], P->U_hat[g], \
-                                                  P->eV, P->V_hat, P->eV, P->V_hat, P->lp, P->pfloor, P->Zi, P->a2s, colsum, part)
+                                                  P->eV, P->V_hat, P->eV, P->V_hat, P->lp, P->pfloor, P->Zi, P->a2s, colsum, part, \
+                                                  (P->thrU && P->thrV) ? P->thrU + (long long)g * P->n_rows : nullptr, \
+                                                  P->thrU ? P->thrV : nullptr)
     if (drop && elbo) ORI_LAUNCH_PR(true, true);
     else if (drop) ORI_LAUNCH_PR(true, false);
     else if (elbo) ORI_LAUNCH_PR(false, true);
@@ -946,7 +982,7 @@ static int pass_genes_kp(const ori_problem_t* P, int g, cudaStream_t st) {
         if constexpr (KP <= 32) {
             k_pass_genes<KP, true, false, true><<<grid, PG_TG, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, (int)rpc,
                 P->eU[g], nullptr, P->U_hat[g], P->U_hat[1 - g], P->eUl[g], P->eVd, P->Vh_old, P->lp, P->pfloor,
-                Zj, b2s, P->red32 + 2ll * P->p * P->KP);
+                Zj, b2s, P->red32 + 2ll * P->p * P->KP, nullptr, nullptr);
             return check_launch("k_pass_genes(sparse)");
         } else {
             return set_error(ORI_EUNSUPPORTED, "the sparse model needs K <= 32");
@@ -955,7 +991,9 @@ static int pass_genes_kp(const ori_problem_t* P, int g, cudaStream_t st) {
 #define ORI_LAUNCH_PG(D, Q)                                                                             \
     k_pass_genes<KP, D, Q, false><<<grid, PG_TG, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, (int)rpc, P->eU[g], \
                                                    P->eUw, P->U_hat[g], P->U_hat[1 - g], nullptr, P->eV, P->V_hat, \
-                                                   P->lp, P->pfloor, Zj, b2s, nullptr)
+                                                   P->lp, P->pfloor, Zj, b2s, nullptr, \
+                                                   (P->thrU && P->thrV) ? P->thrU + (long long)g * P->n_rows : nullptr, \
+                                                  P->thrU ? P->thrV : nullptr)
     if (drop && quirk) ORI_LAUNCH_PG(true, true);
     else if (drop) ORI_LAUNCH_PG(true, false);
     else if (quirk) ORI_LAUNCH_PG(false, true);
@@ -993,13 +1031,13 @@ int launch_row_update(const ori_problem_t* P, int g, int write_state, cudaStream
         const bool sums = write_state == 2;
         k_factor_update<true><<<grid, 256, 0, st>>>(P->n_rows, K, KP, nullptr, nullptr, nullptr, nullptr,
             nullptr, nullptr, nullptr, P->a1, P->a2, P->U_hat[g], P->eU[g], sparse ? P->eUl[g] : nullptr, P->xrow,
-            sums ? SlogU : nullptr, SU, part + R64_HROW, nullptr, 1);
+            sums ? SlogU : nullptr, SU, part + R64_HROW, nullptr, 1, P->thrU ? P->thrU + (long long)g * P->n_rows : nullptr);
     } else {
         // GaP: rate = alpha2 + sum_j V_hat_jk (gap.py:98); the column sums live in gsum[KP..2KP)
         k_factor_update<false><<<grid, 256, 0, st>>>(P->n_rows, K, KP, P->Zi, P->eU[g],
             drop ? P->a2s : nullptr, P->gsum + KP, P->hyper, P->hyper + K, P->U_hat[g],
             P->a1, P->a2, P->U_hat[1 - g], P->eU[1 - g], sparse ? P->eUl[1 - g] : nullptr, P->xrow, SlogU, SU,
-            part + R64_HROW, part + R64_PUV, write_state);
+            part + R64_HROW, part + R64_PUV, write_state, P->thrU ? P->thrU + (long long)(1 - g) * P->n_rows : nullptr);
     }
     return check_launch("k_factor_update(rows)");
 }
@@ -1017,13 +1055,13 @@ int launch_gene_update(const ori_problem_t* P, int write_state, cudaStream_t st)
     }
     if (write_state == 2) {
         k_factor_update<true><<<grid, 256, 0, st>>>(p, K, KP, nullptr, nullptr, nullptr, nullptr,
-            nullptr, nullptr, nullptr, P->b1, P->b2, P->V_hat, P->eV, nullptr, P->xcol, SlogV, SV, gpart, nullptr, 1);
+            nullptr, nullptr, nullptr, P->b1, P->b2, P->V_hat, P->eV, nullptr, P->xcol, SlogV, SV, gpart, nullptr, 1, P->thrV);
     } else {
         // GaP: rate = beta2 + sum_i U_hat_ik (gap.py:106) with the NEW U_hat: red64[p+KP ..)
         float* Zj = P->red32; float* b2s = P->red32 + (long long)p * KP;
         k_factor_update<false><<<grid, 256, 0, st>>>(p, K, KP, Zj, P->eV, drop ? b2s : nullptr,
             P->red64 + p + KP, P->hyper + 2 * K, P->hyper + 3 * K, nullptr,
-            P->b1, P->b2, P->V_hat, P->eV, nullptr, P->xcol, SlogV, SV, gpart, nullptr, write_state);
+            P->b1, P->b2, P->V_hat, P->eV, nullptr, P->xcol, SlogV, SV, gpart, nullptr, write_state, P->thrV);
     }
     return check_launch("k_factor_update(genes)");
 }

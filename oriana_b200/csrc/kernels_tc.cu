@@ -175,6 +175,12 @@ struct TcArgs {
     const float* devlp;
     const float* dev_b1; const float* dev_b2; const float* dev_ps;     // V' = b1 / b2 (* S_hat) [genes x KP]
     unsigned long long* dev_out;     // [3] truncated log-likelihood sums at the rates U V^T (masked), X, column means
+    // float32-underflow emulation (special.cuh: underflow_thr_f32; zigap.py:86-90), all NULL = off: an entry with
+    // den < thr_own * thr_sw assigns its count to no component.  The fast path only compares the smallest denominator of
+    // a group with thr_own * max(thr_sw) -- no instruction per entry -- and sends the group to the general path.
+    const float* thr_own;            // [own_total]
+    const float* thr_sw;             // [sw_total]
+    const float* thr_sw_max;         // [1] largest thr_sw
 };
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -253,7 +259,9 @@ struct TileIter {
     }
 };
 
-template <bool GENES, bool DROPOUT, bool ELBO, bool PAIR, int KP, bool PRECISE, bool DEVI = false>
+// UFL: underflow-emulation hooks (TcArgs::thr_*).  A separate instantiation: two more live registers in the element-wise
+// loop cost the plain kernels 7 % (row pass) / 3 % (gene pass) when the hooks were runtime-switched.
+template <bool GENES, bool DROPOUT, bool ELBO, bool PAIR, int KP, bool PRECISE, bool DEVI = false, bool UFL = false>
 #if ORI_TC_NEW == 16
 __global__ void __maxnreg__(96)
 #else
@@ -615,6 +623,13 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             // pi_j = 1 (a gene without a single zero, logit = +inf): every entry has D_hat = 1 and contributes
             // (1 - D) * e2 = 0 * -inf to the entropy sum; a finite stand-in keeps that product at 0
             const float lp2f = fminf(lp2j, 3.0e38f);
+            // underflow emulation: this row's threshold factor and the bound under which a denominator needs the exact test
+            float thr_o = 0.f, den_lim = 0.f;             // compile-time zeros without UFL
+            if constexpr (UFL) {
+                thr_o = own_ok ? a.thr_own[own_idx] : 0.f;
+                den_lim = thr_o * __ldg(a.thr_sw_max);
+                den_lim = den_lim == den_lim ? fminf(den_lim, 3.0e38f) : 0.f;
+            }
             // genes / columns with a floor (pi <= 0, zigap.py:133) or with the initial indicator state (logit pi = -inf,
             // zigap.py:77) take the general path
             const bool slow_item = DROPOUT && (GENES ? (__any_sync(0xffffffffu, flj != 0.f || lp2j == -INFINITY) != 0) : any_floor);
@@ -624,13 +639,14 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             // ---- tiles of the item.  Two register buffers of 16 columns are in flight per warp.
             uint32_t dr[2][16], ur[2][16];
             float x[2][16];
-            struct Tile { uint32_t xs_addr, lp_addr, tden, s, xs; int valid; bool slow; };
+            struct Tile { uint32_t xs_addr, lp_addr, tden, s, xs; int valid; bool slow; long long sw0; };
             auto tile_of = [&](uint32_t it_, int t_) {
                 Tile c;
                 c.s = it_ % NS; c.xs = it_ % XST;
                 c.xs_addr = sbase + OFF_X + c.xs * X_STAGE;
                 c.lp_addr = sbase + OFF_LP + c.xs * LP_STAGE;
                 c.valid = (int)min((long long)SW, a.sw_total - (long long)t_ * SW);   // gene pass: real cells
+                c.sw0 = (long long)t_ * SW;
                 c.slow = slow_item || (GENES && c.valid != SW);
                 c.tden = tlane + c.s * TM_STAGE;                                      // uv / D_hat: + TM_UV
                 return c;
@@ -689,6 +705,10 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     const float den = __uint_as_float(dr[b][e]);
                     const float xe = x[b][e];
                     const bool nz = xe != 0.f;
+                    // every term of the entry underflows in the reference's float32 exp: no count assigned (zigap.py:90)
+                    float xr = xe;
+                    if constexpr (UFL)
+                        if (den_lim > 0.f && nz && (c0 + e) < c.valid && den < thr_o * __ldg(a.thr_sw + c.sw0 + c0 + e)) xr = 0.f;
                     const float dg = den > 0.f ? den : 1.f;
                     float tt = dg, e2 = 0.f, D = 1.f;
                     if (DROPOUT) {
@@ -698,10 +718,10 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                         tt = nz ? dg : 1.f + ex2_approx(e2);
                         const float r = rcp_approx(tt);
                         D = fmaxf(nz ? 1.f : r, fl);
-                        dr[b][e] = PRECISE ? __float_as_uint(xe * r) : tf32_bias(xe * r);
+                        dr[b][e] = PRECISE ? __float_as_uint(xr * r) : tf32_bias(xr * r);
                         ur[b][e] = PRECISE ? __float_as_uint(D) : tf32_bias(D);
                     } else {
-                        const float R = xe * rcp_approx(tt);
+                        const float R = xr * rcp_approx(tt);
                         dr[b][e] = PRECISE ? __float_as_uint(R) : tf32_bias(R);
                     }
                     if (GENES && (c0 + e) < c.valid) {
@@ -924,7 +944,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                             if (g + 1 < G) ld_group(c, g + 1, b ^ 1);
                             float g_cs = 0.f, g_xl = 0.f, g_ent = 0.f;
                             const float dmin = fast_group(c, g, b, g_cs, g_xl, g_ent);
-                            redo = __any_sync(0xffffffffu, dmin <= 0.f) != 0;
+                            redo = __any_sync(0xffffffffu, dmin <= den_lim) != 0;
                             if (GENES && !redo) { cs += g_cs; t_xl += g_xl; t_ent += g_ent; }
                         }
                         if (redo) slow_group(c, g, b, t_xl, t_ent);
@@ -965,7 +985,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     if (!c.slow) {
                         float g_cs = 0.f, g_xl = 0.f, g_ent = 0.f;
                         const float dmin = fast_group(c, 0, b, g_cs, g_xl, g_ent);
-                        redo = __any_sync(0xffffffffu, dmin <= 0.f) != 0;
+                        redo = __any_sync(0xffffffffu, dmin <= den_lim) != 0;
                         if (GENES && !redo) { cs += g_cs; t_xl += g_xl; t_ent += g_ent; }
                     }
                     if (redo) slow_group(c, 0, b, t_xl, t_ent);
@@ -1124,6 +1144,16 @@ __global__ void k_tc_prep_lp(const float* __restrict__ lp, const float* __restri
     if (f != 0.f) *any_floor = 1;
 }
 
+// largest underflow threshold of a side (non-negative floats order like their bit patterns)
+__global__ void k_tc_thr_max(const float* __restrict__ thr, long long n, int* __restrict__ out)
+{
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, thr[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_int(m));
+}
+
 // deviance pass: 8 constants per gene, tile-major [tile][SW][8]:
 //   logit(pi_gen) * log2(e) | pi | 1 - pi | log pi | mean | log mean | trunc(log(pi e^-mean + 1 - pi)) | 0
 // pi = the finalised Bernoulli prior, pi_gen (through lp) the one that generated D_hat, mean = column mean of X
@@ -1206,7 +1236,9 @@ int launch_tc_prep_genes(const ori_problem_t* P, cudaStream_t st) {
         k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(P->V_hat, w.geneT + (long long)KP * w.pp, t16(w.geneT, w.pp, 1), P->p, w.pp, KP);
         k_tc_prep_lp<<<cdiv(w.pp, 256), 256, 0, st>>>(P->lp, P->pfloor, w.lp2w, w.flw, w.cw, w.flags, P->p, (int)w.pp);
     }
-    return check_launch("k_tc_prep(genes)", drop ? 4 : 2);
+    const bool ufl = P->thrU && P->thrV && !sparse;
+    if (ufl) k_tc_thr_max<<<(cdiv(P->p, 256) < 296 ? (int)cdiv(P->p, 256) : 296), 256, 0, st>>>(P->thrV, P->p, w.flags + 1);
+    return check_launch("k_tc_prep(genes)", (drop ? 4 : 2) + (ufl ? 1 : 0));
 }
 // row-side operands, the sweep side of the gene pass: K-major hi/lo of generation g (the state that generated
 // D_hat), transposed Zj weight (eU, or eU * D_hat[:, :K] under the quirk) and transposed NEW U_hat
@@ -1223,7 +1255,10 @@ int launch_tc_prep_rows(const ori_problem_t* P, int g, cudaStream_t st) {
     k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(wsrc, w.rowT, r16, P->n_rows, w.np, KP);
     if (drop) k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(P->U_hat[1 - g], w.rowT + (long long)KP * w.np,
                                                       precise ? r16 + (long long)KP * w.np : nullptr, P->n_rows, w.np, KP);
-    return check_launch("k_tc_prep(rows)", drop ? 3 : 2);
+    const bool ufl = P->thrU && P->thrV && !(P->flags & ORI_F_SPARSE);
+    if (ufl) k_tc_thr_max<<<(cdiv(P->n_rows, 256) < 296 ? (int)cdiv(P->n_rows, 256) : 296), 256, 0, st>>>(
+        P->thrU + (long long)g * P->n_rows, P->n_rows, w.flags + 2);
+    return check_launch("k_tc_prep(rows)", (drop ? 3 : 2) + (ufl ? 1 : 0));
 }
 
 // sparse model, third gene-side sum (sparse_zigap.py:116): the transposed operand of accumulator 1 becomes eU * E[log U]
@@ -1279,9 +1314,9 @@ static void tc_partition(TcArgs& a, bool genes, int units, int sw, bool precise,
     a.n_items = a.n_own_units * a.n_chunks;
 }
 
-template <bool GENES, bool D, bool E, bool PAIR, int KP, bool PRECISE>
+template <bool GENES, bool D, bool E, bool PAIR, int KP, bool PRECISE, bool UFL = false>
 static int launch_tc_variant(const TcMaps& maps, const TcArgs& a, int grid, cudaStream_t st) {
-    auto kern = k_tc_pass<GENES, D, E, PAIR, KP, PRECISE>;
+    auto kern = k_tc_pass<GENES, D, E, PAIR, KP, PRECISE, false, UFL>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<KP, PAIR, PRECISE>::SMEM_BYTES);
@@ -1329,6 +1364,11 @@ static int launch_tc_pass_p(const ori_problem_t* P, int gen_old, cudaStream_t st
     }
     if (!ok) return set_error(ORI_ECUDA, "cuTensorMapEncodeTiled failed");
     a.lp2w = w.lp2w; a.flw = w.flw; a.cw = w.cw; a.any_floor = w.flags;
+    const bool ufl = P->thrU && P->thrV && !sparse;          // underflow emulation (thresholds reduced by the prep launches)
+    const float* thr_rows = ufl ? P->thrU + (long long)gen_old * P->n_rows : nullptr;     // thresholds of generation gen_old
+    a.thr_own = ufl ? (GENES ? P->thrV : thr_rows) : nullptr;
+    a.thr_sw = ufl ? (GENES ? thr_rows : P->thrV) : nullptr;
+    a.thr_sw_max = ufl ? reinterpret_cast<const float*>(w.flags + (GENES ? 2 : 1)) : nullptr;
     a.colsum = P->red64; a.part64 = P->red64 + P->p + 2 * P->KP;
     a.n_own_tiles = cdiv(a.own_total, TC_OWN);
     a.n_own_units = cdiv(a.n_own_tiles, NCTA);
@@ -1337,6 +1377,16 @@ static int launch_tc_pass_p(const ori_problem_t* P, int gen_old, cudaStream_t st
     tc_partition(a, GENES, units, SW, PRECISE, (P->flags & ORI_F_FIXED_CHAIN) != 0);
     const int grid = NCTA * (a.n_items < units ? a.n_items : units);
     int rc;
+    if (ufl) {
+        if constexpr (PAIR) {
+            if (drop && elbo) rc = launch_tc_variant<GENES, true, true, PAIR, KP, PRECISE, true>(maps, a, grid, st);
+            else if (drop) rc = launch_tc_variant<GENES, true, false, PAIR, KP, PRECISE, true>(maps, a, grid, st);
+            else if (elbo) rc = launch_tc_variant<GENES, false, true, PAIR, KP, PRECISE, true>(maps, a, grid, st);
+            else rc = launch_tc_variant<GENES, false, false, PAIR, KP, PRECISE, true>(maps, a, grid, st);
+        } else {
+            return set_error(ORI_EUNSUPPORTED, "underflow emulation on the tensor path needs the CTA-pair kernels (ORI_TC_PAIR=1)");
+        }
+    } else
     if (drop && elbo) rc = launch_tc_variant<GENES, true, true, PAIR, KP, PRECISE>(maps, a, grid, st);
     else if (drop) rc = launch_tc_variant<GENES, true, false, PAIR, KP, PRECISE>(maps, a, grid, st);
     else if (elbo) rc = launch_tc_variant<GENES, false, true, PAIR, KP, PRECISE>(maps, a, grid, st);

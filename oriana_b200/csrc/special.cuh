@@ -85,4 +85,19 @@ __host__ __device__ inline float centred_exp_f32(float elog, float row_max) {
     return (row_max > EXP_DEAD && rel >= EXP_FLUSH) ? (float)ldexp(exp((double)rel), EXP_CENTER_LOG2) : 0.f;
 }
 
+// Float32-underflow emulation (zigap.py:86-90, gap.py:73-76): the reference evaluates exp(lU_ik + lV_jk) in float32,
+// which rounds to 0 below 2^-150 (log-sum <= -103.972); an entry whose every term does so keeps den = 0 -> 1 and hands
+// its count to no component.  In centred operands term_k = eU_ik * eV_jk = exp(lU + lV - m_i - m_j) 2^116, so
+//     term_k underflows in the reference  <=>  eU_ik * eV_jk <= thr_i * thr_j,   thr = 2^-17 exp(-m)
+// with m the row's largest log-expectation.  Saturates at 3e38 (rows that far down pair with nothing real) and is 3e38 for
+// the all-zero rows of EXP_DEAD.
+__host__ __device__ inline float underflow_thr_f32(float row_max) {
+    if (!(row_max > EXP_DEAD)) return 3.0e38f;
+    const double t = ldexp(exp(-(double)row_max), -17);
+    return t > 3.0e38 ? 3.0e38f : (float)t;
+}
+// an entry can only be touched by the rule when its denominator is within 2^24 of the threshold (terms 2^24 below the
+// denominator do not move a float32 sum)
+constexpr float UFL_NEAR = 16777216.f;
+
 }  // namespace ori

@@ -79,7 +79,7 @@ class FactorModel(metaclass=ABCMeta):
 
     def __init__(self, cmatrix, k=2, use_factors=True, *, state=None, compat_quirk=False, sharded=False,
                  process_group=None, elbo=True, trace_cap=4096, force_simt=False, tensor=None, nmf=None, graphs=False,
-                 keep_hyper=True, precise=False):
+                 keep_hyper=True, precise=False, emulate_underflow=False):
         self._dev = _lib.require_cuda()
         self._lib = _lib.load()
         _lib.check(self._lib.ori_device_check(self._dev.index or 0))
@@ -118,6 +118,12 @@ class FactorModel(metaclass=ABCMeta):
         if graphs and (sharded or process_group is not None):
             raise ValueError('graphs=True is a single-rank feature: capturing the NCCL all-reduces of a sharded step '
                              'is not supported')
+        # emulate_underflow=True: reproduce the reference's float32 exp underflow in the multinomial step (zigap.py:86-90,
+        # gap.py:73-76: terms with log_U_hat + log_V_hat <= -103.97 are 0 there; an entry whose terms all are assigns its
+        # count to no component).  Off by default, like the quirk: the default keeps the exact ratios.
+        self.emulate_underflow = bool(emulate_underflow)
+        if self.emulate_underflow and self._sparse:
+            raise ValueError('emulate_underflow is not available for the sparse model')
         self._graphs = {} if graphs else None
         self.graph_replays = 0
         self._graph_kernels = 0
@@ -204,6 +210,8 @@ class FactorModel(metaclass=ABCMeta):
             _lib.check(self._lib.ori_row_sums_f32(self._X.data_ptr(), ldx, n, p, self._xrow.data_ptr(), _lib.stream_ptr()))
             _lib.check(self._lib.ori_column_sums_f64(self._X.data_ptr(), ldx, n, p, cs.data_ptr(), _lib.stream_ptr()))
             self._xcol = self._shard.allreduce_sum(cs).to(torch.float32)
+        self._thrU = torch.zeros((2, max(n, 1)), **f32) if self.emulate_underflow else None
+        self._thrV = torch.zeros((p,), **f32) if self.emulate_underflow else None
         self._tc_ws = None
         if self._tensor:
             self._tc_ws = torch.empty((int(self._lib.ori_tc_workspace_floats(n, p, KP)) + 32,), **f32)
@@ -227,6 +235,7 @@ class FactorModel(metaclass=ABCMeta):
         if self._tc_ws is not None:
             P.tc_ws, P.tc_ws_floats = self._tc_ws.data_ptr(), self._tc_ws.numel()
         P.xrow, P.xcol = ptr(self._xrow), ptr(self._xcol)
+        P.thrU, P.thrV = ptr(self._thrU), ptr(self._thrV)
         self._bind_extra(P, rowf, genef, ptr)
         self._P = P
         _lib.check(self._lib.ori_problem_check(ctypes.byref(P)))

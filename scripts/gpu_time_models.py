@@ -18,7 +18,8 @@ for (n, p, K) in sizes:
     for cls in ((ZIGaP,) if ('c5' in sys.argv or quick) else (ZIGaP, GaP)):
         for elbo in ((True,) if quick else (True, False)):
             np.random.seed(0)
-            m = cls(X[:, :p], k=K, use_factors=False, tensor=True, elbo=elbo, precise='precise' in sys.argv)
+            m = cls(X[:, :p], k=K, use_factors=False, tensor=True, elbo=elbo, precise='precise' in sys.argv,
+                    emulate_underflow='underflow' in sys.argv)
             for _ in range(2): m.step()
             m.enable_kernel_timing()
             for _ in range(4): m.step()

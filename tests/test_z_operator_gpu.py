@@ -68,12 +68,9 @@ def test_against_c_loop_with_soft_dropout(cuda_lib, shape, quirk):
 def test_underflow_guard_and_empty(cuda_lib):
     """zigap.py:88-90: den <= 0 -> 1 when every exp underflows; n = 0 leaves zero gene sums.
 
-    The log-expectations are centred per row before the exp (csrc/special.cuh), so the guard is reached where a whole
-    row is below any float32 scale (E log < -1e4: psi(a) of a clamped a = 1e-15 is -1e15) -- same zeros as the
-    reference.  For rows that are merely very negative (-200) the reference's float32 exp(lU + lV) is 0 for every
-    component and it assigns the count to nobody, while the centred form still knows the ratios (here 1/2 each):
-    a documented deviation, in a regime (an observed count under a model rate below 1e-45) no fixture of the
-    reference reaches."""
+    The log-expectations are centred per row before the exp (csrc/special.cuh), so the centred denominators stay
+    positive where the reference's float32 exp(lU + lV) is 0 for every component; the operator carries the reference's
+    underflow thresholds (underflow_thr_f32) and assigns such counts to nobody, like the reference."""
     from oracle import zloop
     X = np.arange(24, dtype=np.float32).reshape(4, 6)
     lU = np.full((4, 2), -3e4, np.float32); lV = np.full((6, 2), -1.5, np.float32)
@@ -82,9 +79,18 @@ def test_underflow_guard_and_empty(cuda_lib):
     assert np.array_equal(Zi, rZi) and np.array_equal(Zj, rZj) and not Zi.any() and not Zj.any()
     lU = np.full((4, 2), -200., np.float32); lV = np.full((6, 2), -200., np.float32)
     Zi, Zj = z_op(cuda_lib, lU, lV, X)
-    np.testing.assert_allclose(Zi, np.repeat(X.sum(1, keepdims=True) / 2, 2, axis=1), rtol=1e-6)
-    np.testing.assert_allclose(Zj, np.repeat(X.sum(0)[:, None] / 2, 2, axis=1), rtol=1e-6)
     assert not zloop.gap_z(lU, lV, X)[0].any()                    # the reference: all zero
+    assert not Zi.any() and not Zj.any()
+    # -60 and -60: exp(-120) is 0 in float32 although neither factor is out of range on its own
+    lU = np.full((4, 2), -60., np.float32); lV = np.full((6, 2), -60., np.float32)
+    Zi, Zj = z_op(cuda_lib, lU, lV, X)
+    assert not zloop.gap_z(lU, lV, X)[0].any() and not Zi.any() and not Zj.any()
+    # -60 and -20: a normal float32 number (e^-80): the ratios (1/2 each) are kept
+    lV = np.full((6, 2), -20., np.float32)
+    Zi, Zj = z_op(cuda_lib, lU, lV, X)
+    rZi, rZj = zloop.gap_z(lU, lV, X)
+    np.testing.assert_allclose(Zi, rZi, rtol=1e-5); np.testing.assert_allclose(Zj, rZj, rtol=1e-5)
+    np.testing.assert_allclose(Zi, np.repeat(X.sum(1, keepdims=True) / 2, 2, axis=1), rtol=1e-5)
     # one component 150 below the other: flushed (the reference's exp underflows for it as well)
     lU = np.tile(np.asarray([[-1., -151.]], np.float32), (4, 1)); lV = np.tile(np.asarray([[-0.5, -0.5]], np.float32), (6, 1))
     Zi, Zj = z_op(cuda_lib, lU, lV, X)
@@ -168,3 +174,41 @@ def test_default_context_allocates_once(cuda_lib):
         z_op(cuda_lib, lU, lV, X)
     a1 = _stats(cuda_lib)
     assert a1['allocs'] == a0['allocs'] and a1['calls'] == a0['calls'] + 3
+
+
+def _underflow_case(n, p, K, seed):
+    """A third of the cells and of the genes live 70 below the rest: the reference's float32 exp(lU + lV) is 0 for every
+    component where both meet (-140), a normal number everywhere else (>= e^-80); no entry sits in the denormal band, where
+    the reference's own ratios are imprecise."""
+    rng = np.random.default_rng(seed)
+    lU = rng.uniform(-3., 2., (n, K)); lV = rng.uniform(-3., 2., (p, K))
+    low_i = rng.random(n) < 0.33; low_j = rng.random(p) < 0.33
+    lU[low_i] -= 70.; lV[low_j] -= 70.
+    lU[rng.random((n, K)) < 0.05] = -1e15                       # exact zeros of NMF factors (psi of a clamped 1e-15)
+    X = (rng.poisson(3.0, (n, p)) * (rng.random((n, p)) < 0.6)).astype(np.float32)
+    D = np.where(X != 0, 1.0, rng.random((n, p))).astype(np.float32)
+    return lU.astype(np.float32), lV.astype(np.float32), X, D, low_i, low_j
+
+
+@pytest.mark.parametrize('quirk', [True, False])
+@pytest.mark.parametrize('shape,tol', [((300, 260, 5), 1e-5), ((150, 90, 40), 1e-5), ((2048, 1024, 12), 2e-3)])
+def test_float32_underflow_of_the_reference_is_reproduced(cuda_lib, shape, tol, quirk):
+    """zigap.py:86-90 / gap.py:73-76 on both kernel families (the third shape takes the tcgen05 passes): counts of entries
+    whose every term underflows in the reference go to no component; everything else keeps its ratios."""
+    from oracle import zloop
+    n, p, K = shape
+    lU, lV, X, D, low_i, low_j = _underflow_case(n, p, K, seed=n + p + K)
+    rZi, rZj, rZ3 = zloop.zigap_z(lU, lV, D, X, quirk=quirk, third=True)
+    # the case does what it says: the reference drops the counts of (low cell, low gene) pairs
+    XD = X * D
+    kept = XD[np.ix_(low_i, ~low_j)].sum(1)
+    np.testing.assert_allclose(rZi[low_i].sum(1), kept, rtol=1e-4, atol=1e-3)
+    assert XD[np.ix_(low_i, low_j)].sum() > 0
+    Zi, Zj, Z3 = z_op(cuda_lib, lU, lV, X, D, quirk=quirk, third=True)
+    assert relerr(Zi, rZi) < tol, relerr(Zi, rZi)
+    assert relerr(Zj, rZj) < tol, relerr(Zj, rZj)
+    assert np.max(np.abs(Z3 - rZ3)) < max(tol, 3e-6) * np.max(np.abs(rZ3))
+    np.testing.assert_allclose(Zi[low_i].sum(1), kept, rtol=10 * tol, atol=1e-3)
+    gZi, gZj = z_op(cuda_lib, lU, lV, X)
+    rZi, rZj = zloop.gap_z(lU, lV, X)
+    assert relerr(gZi, rZi) < tol and relerr(gZj, rZj) < tol

@@ -138,7 +138,8 @@ typedef struct ori_problem {
      * ori_init_expectations, ori_row_update and ori_gene_update; the passes drop every term with
      * eU_ik eV_jk <= thrU_i thrV_j -- the terms whose float32 exp(log_U_hat + log_V_hat) is 0 in the reference -- so an
      * entry whose terms all underflow assigns its count to no component (den = 0 -> 1, :90).  CUDA-core kernels: per
-     * term; tcgen05 kernels: per entry (den < thrU_i thrV_j).  Not with ORI_F_SPARSE. */
+     * term; tcgen05 kernels: per entry (den < thrU_i thrV_j).  The sparse model's terms carry the mask S_tilde
+     * (sparse_zigap.py:109): same rule. */
     float* thrU;           /* [2 x n_rows], per generation like eU */
     float* thrV;           /* [p]                                  */
 } ori_problem_t;

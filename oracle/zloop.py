@@ -18,6 +18,7 @@ def _lib():
     fp = ctypes.POINTER(ctypes.c_float)
     lib.zl_zigap_z.argtypes = [fp] * 7 + [ctypes.c_long] * 3 + [ctypes.c_int]
     lib.zl_gap_z.argtypes = [fp] * 5 + [ctypes.c_long] * 3
+    lib.zl_sparse_z.argtypes = [fp] * 9 + [ctypes.c_long] * 3
     return lib
 
 
@@ -43,3 +44,12 @@ def gap_z(log_U_hat, log_V_hat, X):
     a = [np.ascontiguousarray(x, dtype=np.float32) for x in (log_U_hat, log_V_hat, X)]
     _lib().zl_gap_z(_p(Zi), _p(Zj), *[_p(x) for x in a], n, p, K)
     return Zi, Zj
+
+
+def sparse_z(log_U_hat, log_Vp_hat, S_tilde, S_hat, D_hat, X):
+    """sparse_zigap.py:100-116 as a sequential float32 loop; returns (DSZ_hat, DZ_hat, DZ_exp_logsum_hat)."""
+    n, K = log_U_hat.shape; p = log_Vp_hat.shape[0]
+    DSZ = np.empty((n, K), np.float32); DZ = np.empty((p, K), np.float32); DZl = np.empty((p, K), np.float32)
+    a = [np.ascontiguousarray(x, dtype=np.float32) for x in (log_U_hat, log_Vp_hat, S_tilde, S_hat, D_hat, X)]
+    _lib().zl_sparse_z(_p(DSZ), _p(DZ), _p(DZl), *[_p(x) for x in a], n, p, K)
+    return DSZ, DZ, DZl

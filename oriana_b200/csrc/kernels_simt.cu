@@ -135,15 +135,17 @@ k_pass_rows(const float* __restrict__ X, long long ldx, long long n_rows, int p,
             den = den > 0.f ? den : 1.f;                 // zigap.py:90
             float R = x / den;
             const float T = tu * sthr[g];
-            if (!SPARSE && nz && T > 0.f && den < T * UFL_NEAR) {
-                // some term of this entry is (or is close to) one the reference's float32 exp flushes to 0 (zigap.py:86):
-                // redo the entry from its terms, dropping those; nothing survives -> den = 1, no count assigned (:90)
+            if (nz && T > 0.f && den < T * UFL_NEAR) {
+                // some term of this entry is (or is close to) one the reference's float32 exp flushes to 0 (zigap.py:86,
+                // sparse_zigap.py:109): redo the entry from its terms, dropping those; nothing survives -> den = 1, no
+                // count assigned (:90).  SPARSE: sV carries the mask S_tilde, the sums contract with sVz = sV * S_hat.
                 float d2 = 0.f;
 #pragma unroll
                 for (int k = 0; k < KP; ++k) { const float tk = eu[k] * sV[g][k]; d2 += tk > T ? tk : 0.f; }
                 const float r2 = d2 > 0.f ? x / d2 : 0.f;
 #pragma unroll
-                for (int k = 0; k < KP; ++k) { const float vk = sV[g][k]; if (eu[k] * vk > T) zi[k] = fmaf(r2, vk, zi[k]); }
+                for (int k = 0; k < KP; ++k)
+                    if (eu[k] * sV[g][k] > T) zi[k] = fmaf(r2, SPARSE ? sVz[SPARSE ? g : 0][k] : sV[g][k], zi[k]);
                 R = 0.f;
             }
             float D = 1.f;
@@ -295,14 +297,17 @@ k_pass_genes(const float* __restrict__ X, long long ldx, long long n_rows, int p
                 den = den > 0.f ? den : 1.f;
                 float R = x / den;
                 const float T = tv * sthr[rr];
-                if (!SPARSE && x != 0.f && T > 0.f && den < T * UFL_NEAR) {     // see k_pass_rows
+                if (x != 0.f && T > 0.f && den < T * UFL_NEAR) {     // see k_pass_rows
                     float d2 = 0.f;
 #pragma unroll
                     for (int k = 0; k < KP; ++k) { const float tk = sU[rr][k] * ev[k]; d2 += tk > T ? tk : 0.f; }
                     const float r2 = d2 > 0.f ? x / d2 : 0.f;
 #pragma unroll
                     for (int k = 0; k < KP; ++k)
-                        if (sU[rr][k] * ev[k] > T) zj[k] = fmaf(r2, QUIRK ? sUw[QUIRK ? rr : 0][k] : sU[rr][k], zj[k]);
+                        if (sU[rr][k] * ev[k] > T) {
+                            zj[k] = fmaf(r2, QUIRK ? sUw[QUIRK ? rr : 0][k] : sU[rr][k], zj[k]);
+                            if (SPARSE) zl[k] = fmaf(r2, sUl[SPARSE ? rr : 0][k], zl[k]);
+                        }
                     R = 0.f;
                 }
                 float D = 1.f;
@@ -675,6 +680,7 @@ k_sparse_gene_update(ori_problem_t P)
             const float ed_new = P.eVd[idx] * eE;                             // :103-104
             P.eV[idx] = eE; P.eVd[idx] = ed_new; P.eVz[idx] = ed_new * P.p_s[idx];
         }
+        if (P.thrV) P.thrV[j] = underflow_thr_f32(m);
         if (!FROM_PARAMS) P.pi_s[j] = ssum / (double)K;                       // :196
     }
     __syncthreads();
@@ -936,7 +942,7 @@ static int pass_rows_kp(const ori_problem_t* P, int g, cudaStream_t st) {
         if constexpr (KP <= 32) {
             k_pass_rows<KP, true, false, true><<<grid, PR_TR, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, P->eU[g],
                 P->U_hat[g], P->eVd, P->Vh_old, P->eVz, P->V_hat, P->lp, P->pfloor, P->Zi, P->a2s, colsum, part,
-                nullptr, nullptr);
+                (P->thrU && P->thrV) ? P->thrU + (long long)g * P->n_rows : nullptr, P->thrU ? P->thrV : nullptr);
             return check_launch("k_pass_rows(sparse)");
         } else {
             return set_error(ORI_EUNSUPPORTED, "the sparse model needs K <= 32");
@@ -982,7 +988,8 @@ static int pass_genes_kp(const ori_problem_t* P, int g, cudaStream_t st) {
         if constexpr (KP <= 32) {
             k_pass_genes<KP, true, false, true><<<grid, PG_TG, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, (int)rpc,
                 P->eU[g], nullptr, P->U_hat[g], P->U_hat[1 - g], P->eUl[g], P->eVd, P->Vh_old, P->lp, P->pfloor,
-                Zj, b2s, P->red32 + 2ll * P->p * P->KP, nullptr, nullptr);
+                Zj, b2s, P->red32 + 2ll * P->p * P->KP,
+                (P->thrU && P->thrV) ? P->thrU + (long long)g * P->n_rows : nullptr, P->thrU ? P->thrV : nullptr);
             return check_launch("k_pass_genes(sparse)");
         } else {
             return set_error(ORI_EUNSUPPORTED, "the sparse model needs K <= 32");

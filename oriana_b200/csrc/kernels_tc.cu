@@ -1236,7 +1236,7 @@ int launch_tc_prep_genes(const ori_problem_t* P, cudaStream_t st) {
         k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(P->V_hat, w.geneT + (long long)KP * w.pp, t16(w.geneT, w.pp, 1), P->p, w.pp, KP);
         k_tc_prep_lp<<<cdiv(w.pp, 256), 256, 0, st>>>(P->lp, P->pfloor, w.lp2w, w.flw, w.cw, w.flags, P->p, (int)w.pp);
     }
-    const bool ufl = P->thrU && P->thrV && !sparse;
+    const bool ufl = P->thrU && P->thrV;
     if (ufl) k_tc_thr_max<<<(cdiv(P->p, 256) < 296 ? (int)cdiv(P->p, 256) : 296), 256, 0, st>>>(P->thrV, P->p, w.flags + 1);
     return check_launch("k_tc_prep(genes)", (drop ? 4 : 2) + (ufl ? 1 : 0));
 }
@@ -1255,7 +1255,7 @@ int launch_tc_prep_rows(const ori_problem_t* P, int g, cudaStream_t st) {
     k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(wsrc, w.rowT, r16, P->n_rows, w.np, KP);
     if (drop) k_tc_prep_T<<<tg, dim3(32, 8), 0, st>>>(P->U_hat[1 - g], w.rowT + (long long)KP * w.np,
                                                       precise ? r16 + (long long)KP * w.np : nullptr, P->n_rows, w.np, KP);
-    const bool ufl = P->thrU && P->thrV && !(P->flags & ORI_F_SPARSE);
+    const bool ufl = P->thrU && P->thrV;
     if (ufl) k_tc_thr_max<<<(cdiv(P->n_rows, 256) < 296 ? (int)cdiv(P->n_rows, 256) : 296), 256, 0, st>>>(
         P->thrU + (long long)g * P->n_rows, P->n_rows, w.flags + 2);
     return check_launch("k_tc_prep(rows)", (drop ? 3 : 2) + (ufl ? 1 : 0));
@@ -1364,7 +1364,7 @@ static int launch_tc_pass_p(const ori_problem_t* P, int gen_old, cudaStream_t st
     }
     if (!ok) return set_error(ORI_ECUDA, "cuTensorMapEncodeTiled failed");
     a.lp2w = w.lp2w; a.flw = w.flw; a.cw = w.cw; a.any_floor = w.flags;
-    const bool ufl = P->thrU && P->thrV && !sparse;          // underflow emulation (thresholds reduced by the prep launches)
+    const bool ufl = P->thrU && P->thrV;          // underflow emulation (thresholds reduced by the prep launches)
     const float* thr_rows = ufl ? P->thrU + (long long)gen_old * P->n_rows : nullptr;     // thresholds of generation gen_old
     a.thr_own = ufl ? (GENES ? P->thrV : thr_rows) : nullptr;
     a.thr_sw = ufl ? (GENES ? thr_rows : P->thrV) : nullptr;

@@ -122,8 +122,6 @@ class FactorModel(metaclass=ABCMeta):
         # gap.py:73-76: terms with log_U_hat + log_V_hat <= -103.97 are 0 there; an entry whose terms all are assigns its
         # count to no component).  Off by default, like the quirk: the default keeps the exact ratios.
         self.emulate_underflow = bool(emulate_underflow)
-        if self.emulate_underflow and self._sparse:
-            raise ValueError('emulate_underflow is not available for the sparse model')
         self._graphs = {} if graphs else None
         self.graph_replays = 0
         self._graph_kernels = 0

@@ -33,6 +33,21 @@ def test_sparse_z_kernel_matches_reference_numba_kernel(name):
         assert relerr(a, g[key]) < tol, key
 
 
+@pytest.mark.parametrize('name', ['sparse_k4', 'sparse_ragged'])
+def test_sequential_c_loop_matches_reference_numba_kernel(name):
+    """oracle/zloop.c: zl_sparse_z -- same loop order and float32 arithmetic as sparse_zigap.py:100-116 -- against the raw
+    kernel call recorded from the reference (the checker of the underflow-emulation tests)."""
+    from oracle import zloop
+    g = load_golden(name)
+    s = _state(g, 0)
+    got = zloop.sparse_z(g['z_log_U_hat'], g['z_log_Vp_hat'], g['z_S_tilde'], g['z_S_hat'], s['p_d'].astype(np.float32),
+                         s['X'].astype(np.float32))
+    for a, key in zip(got[:2], ('z_DSZ', 'z_DZ')):
+        assert relerr(a, g[key]) < 2e-6, (key, relerr(a, g[key]))
+    # signed terms cancel in sparse_zigap.py:116 (expf of gcc's libm vs numba's differs in the last bit): absolute error
+    assert np.max(np.abs(got[2] - g['z_DZl'])) < 3e-6 * np.max(np.abs(g['z_DZl']))
+
+
 @pytest.mark.parametrize('name', ['sparse_k4', 'sparse_ragged', 'sparse_gen', 'sparse_nmf'])
 def test_sparse_trajectory_and_deviance_match_reference(name):
     from oracle import sparse_numpy as sn

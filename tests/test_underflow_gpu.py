@@ -78,8 +78,39 @@ def test_thresholds_do_not_touch_ordinary_states(cuda_lib):
         assert relerr(getattr(a, k).asarray(), getattr(b, k).asarray()) < 1e-6, k
 
 
-def test_sparse_model_refuses(cuda_lib):
+def _literal_sparse_z(lU, lV, S_tilde, S_hat, D_hat, X, dtype=np.float32):
+    from oracle import zloop
+    return zloop.sparse_z(lU, lV, S_tilde, S_hat, D_hat, X.astype(np.float32))
+
+
+@pytest.mark.parametrize('shape,tensor,tol', [((260, 330, 6), False, 5e-5), ((2048, 1024, 10), True, 5e-4)])
+def test_sparse_model_step_reproduces_the_reference_underflow(cuda_lib, monkeypatch, shape, tensor, tol):
+    """SparseZIGaP (sparse_zigap.py:100-116: the same float32 exp, times the mask S_tilde) on the CUDA-core kernels and on
+    the tcgen05 kernels (fp32-grade mode, the sparse model's default) against the oracle step with the sequential loop."""
+    from oracle import cavi_numpy as cn, sparse_numpy as sn
     from oriana.models import SparseZIGaP
     from oriana.singlecell import CountMatrix
-    with pytest.raises(ValueError):
-        SparseZIGaP(CountMatrix(np.ones((8, 8))), k=2, use_factors=False, emulate_underflow=True)
+    n, p, K = shape
+    X = cn.synth_counts(n, p, K, seed=n + K)
+    s = sn.init_state(X, K, np.random.default_rng(n))
+    rng = np.random.default_rng(n + 1)
+    low_i = rng.random(n) < 0.4; low_j = rng.random(p) < 0.4
+    s['a1'][low_i] = 0.0143; s['b1'][low_j] = 0.0143
+    kw = dict(k=K, use_factors=False, state=s, tau=0.5, tensor=tensor)
+    m = SparseZIGaP(CountMatrix(X), emulate_underflow=True, **kw)
+    plain = SparseZIGaP(CountMatrix(X), **kw)
+    assert m.uses_tensor_path == tensor
+    ref = {k: v.copy() for k, v in s.items()}
+    monkeypatch.setattr(sn, 'z_expectations', _literal_sparse_z)
+    alpha1 = ref['alpha1'].copy()
+    m.step(); plain.step(); sn.step(ref, tau=0.5)
+    got = (m.a1.asarray() - alpha1[None, :]).sum(1)
+    want = (ref['a1'] - alpha1[None, :]).sum(1)
+    np.testing.assert_allclose(got[low_i], want[low_i], rtol=20 * tol, atol=1e-3)
+    off = (plain.a1.asarray() - alpha1[None, :]).sum(1)
+    lost = X[np.ix_(low_i, low_j)].sum(1)
+    assert np.all(off[low_i][lost > 0] > want[low_i][lost > 0] + 0.5)          # the exact ratios keep those counts
+    for k in PARAMS + ('pi_d', 'pi_s'):
+        e = relerr(getattr(m, k).asarray(), ref[k])
+        assert e < tol, (k, e)
+    assert relerr(m.p_s.asarray(), ref['p_s']) < 20 * tol

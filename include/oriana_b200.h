@@ -55,6 +55,12 @@ extern "C" {
                                  accumulation chunks at their nominal length even when the slab is too small to fill the
                                  machine, so that its sums are chained -- and rounded -- like the resident matrix's          */
 
+#define ORI_F_DETERMINISTIC 256u /* tensor path, dense models: every sum that the plain kernels form with floating-point atomics is
+                                 formed in a fixed order instead -- the chunk items of a row block / gene block add their partial
+                                 sums one after the other (a ticket per block), per-item ELBO terms and per-block factor sums go
+                                 through scratch arrays that are summed in index order -- so two runs of the same problem on the
+                                 same device agree bit for bit.  Needs det_ws.                                              */
+
 /* modes of ori_mstep */
 #define ORI_M_STEP 0          /* regular end of iteration t+1: finalise ELBO(t), pi(t); M-step; next lp   */
 #define ORI_M_INIT 1          /* after ori_init_expectations: M-step on the initial expectations          */
@@ -142,6 +148,10 @@ typedef struct ori_problem {
      * (sparse_zigap.py:109): same rule. */
     float* thrU;           /* [2 x n_rows], per generation like eU */
     float* thrV;           /* [p]                                  */
+
+    /* ORI_F_DETERMINISTIC: scratch of ori_det_workspace_doubles(n_rows, p, KP) doubles (NULL otherwise) */
+    double* det_ws;
+    int64_t det_ws_doubles;
 } ori_problem_t;
 
 /* ---- library ---------------------------------------------------------------------------------- */
@@ -165,6 +175,8 @@ int ori_gamma_expect_f32(const float* a1, const float* a2, float* E, float* Elog
 /* ---- the CAVI iteration, device-resident state -------------------------------------------------- */
 /* Scratch floats the tensor path needs for a rank owning n_rows cells of p genes at padded latent dimension KP. */
 int64_t ori_tc_workspace_floats(int64_t n_rows, int32_t p, int32_t KP);
+/* Size of ori_problem_t::det_ws in doubles (ORI_F_DETERMINISTIC). */
+int64_t ori_det_workspace_doubles(int64_t n_rows, int32_t p, int32_t KP);
 /* 1 when the calls below will take the tensor path for this problem, 0 for the CUDA-core kernels. */
 int ori_uses_tensor_path(const ori_problem_t* P);
 /* Validate a problem description (shapes, alignment, null pointers). */

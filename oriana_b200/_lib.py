@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get('ORIANA_B200_LIB') or os.path.join(_HERE, 'lib', 'libo
 
 ORI_F_DROPOUT, ORI_F_QUIRK, ORI_F_ELBO, ORI_F_NO_TENSOR, ORI_F_SPARSE, ORI_F_DEVICE_ITER, ORI_F_PRECISE = 1, 2, 4, 8, 16, 32, 64
 ORI_F_FIXED_CHAIN = 128
+ORI_F_DETERMINISTIC = 256
 ORI_M_STEP, ORI_M_INIT, ORI_M_INIT_KEEP, ORI_M_FINALIZE, ORI_M_REFRESH = 0, 1, 2, 3, 4
 R64_NSLOTS = 8
 SCAL_SLOTS = 16
@@ -36,7 +37,7 @@ class OriProblem(C.Structure):
         ('tc_ws', C.c_void_p), ('tc_ws_floats', C.c_int64),
         ('p_s', C.c_void_p), ('logV', C.c_void_p), ('eVd', C.c_void_p), ('eVz', C.c_void_p), ('Vh_old', C.c_void_p),
         ('eUl', C.c_void_p * 2), ('pi_s', C.c_void_p), ('tau', C.c_double),
-        ('xrow', C.c_void_p), ('xcol', C.c_void_p), ('thrU', C.c_void_p), ('thrV', C.c_void_p),
+        ('xrow', C.c_void_p), ('xcol', C.c_void_p), ('thrU', C.c_void_p), ('thrV', C.c_void_p), ('det_ws', C.c_void_p), ('det_ws_doubles', C.c_int64),
     ]
 
 
@@ -49,6 +50,7 @@ _SIGNATURES = {
     'ori_special_f64': ([C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p], C.c_int),
     'ori_gamma_expect_f32': ([C.c_void_p] * 5 + [C.c_int64, C.c_void_p], C.c_int),
     'ori_tc_workspace_floats': ([C.c_int64, C.c_int32, C.c_int32], C.c_int64),
+    'ori_det_workspace_doubles': ([C.c_int64, C.c_int32, C.c_int32], C.c_int64),
     'ori_uses_tensor_path': ([_PP], C.c_int),
     'ori_problem_check': ([_PP], C.c_int),
     'ori_count_stats': ([_PP, C.c_void_p], C.c_int),

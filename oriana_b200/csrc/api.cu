@@ -151,6 +151,12 @@ int ori_problem_check(const ori_problem_t* P) {
         return set_error(ORI_EINVAL, "KP=%d must be 8, 16, 32 or 64 and >= K=%d", P->KP, P->K);
     if (P->tc_ws && (((uintptr_t)P->tc_ws & 127) || P->tc_ws_floats < tc_workspace_floats(P->n_rows, P->p, P->KP)))
         return set_error(ORI_EINVAL, "tc_ws must be 128-byte aligned and hold ori_tc_workspace_floats() floats");
+    if (P->flags & ORI_F_DETERMINISTIC) {
+        if (P->flags & ORI_F_SPARSE) return set_error(ORI_EUNSUPPORTED, "ORI_F_DETERMINISTIC is not available for the sparse model");
+        if (!P->tc_ws) return set_error(ORI_EUNSUPPORTED, "ORI_F_DETERMINISTIC needs the tensor path (tc_ws)");
+        if (!P->det_ws || P->det_ws_doubles < det_workspace_doubles(P->n_rows, P->p, P->KP))
+            return set_error(ORI_EINVAL, "ORI_F_DETERMINISTIC needs det_ws of ori_det_workspace_doubles() doubles");
+    }
     if (P->ldx < P->p || (P->ldx & 3)) return set_error(ORI_EINVAL, "ldx=%lld must be >= p and a multiple of 4", (long long)P->ldx);
     if (P->n_total < P->n_rows || P->n_total <= 0) return set_error(ORI_EINVAL, "n_total=%lld < n_rows", (long long)P->n_total);
     if ((P->flags & ORI_F_QUIRK) && P->p < P->K) return set_error(ORI_EINVAL, "quirk mode needs p >= K (zigap.py:94 reads D_hat[i, k])");
@@ -216,6 +222,7 @@ static int pass_genes_any(const ori_problem_t* P, int gen_old, cudaStream_t st) 
 }
 
 int64_t ori_tc_workspace_floats(int64_t n_rows, int32_t p, int32_t KP) { return tc_workspace_floats(n_rows, p, KP); }
+int64_t ori_det_workspace_doubles(int64_t n_rows, int32_t p, int32_t KP) { return det_workspace_doubles(n_rows, p, KP); }
 
 int ori_uses_tensor_path(const ori_problem_t* P) { return (P && tc_eligible(P)) ? 1 : 0; }
 

@@ -48,6 +48,17 @@ int launch_deviance(const ori_problem_t* P, int gen, const double* pi, const dou
 
 // kernels_tc.cu
 long long tc_workspace_floats(long long n_rows, int p, int KP);
+
+// ORI_F_DETERMINISTIC scratch (ori_problem_t::det_ws), in doubles:
+//   [0, DET_FU_BLOCKS * DET_FU_SLOTS)   per-block partial sums of k_factor_update (sum log E | sum E | entropy | D.uv)
+//   [.., + pad128(p))                    column sums of D_hat of the second column slice of the tensor gene pass
+//   [.., + det_max_items * DET_ITEM_SLOTS)  per-item, per-CTA, per-warp ELBO terms of the tensor gene pass
+//   [.., + tickets)                      one int per own tile of the running tensor pass (chunk order of the accumulator adds)
+constexpr int DET_FU_BLOCKS = 148 * 8;
+constexpr int DET_FU_SLOTS = 2 * 64 + 2;
+constexpr int DET_ITEM_SLOTS = 2 * 8 * 2;          // CTAs of a pair x element-wise warps x (x log den, entropy)
+long long det_max_items(long long n_rows, int p);
+long long det_workspace_doubles(long long n_rows, int p, int KP);
 bool tc_eligible(const ori_problem_t* P);
 int launch_tc_prep_genes(const ori_problem_t* P, cudaStream_t st);
 int launch_tc_prep_rows(const ori_problem_t* P, int gen_old, cudaStream_t st);

@@ -364,9 +364,14 @@ k_factor_update(long long rows, int K, int KP,
                 const float* __restrict__ xsum,
                 double* __restrict__ Slog, double* __restrict__ Shat,
                 double* __restrict__ Hsum, double* __restrict__ PUVsum, int write_state,
-                float* __restrict__ thr_out)
+                float* __restrict__ thr_out, double* __restrict__ blk_part)
 {
+    // blk_part (ORI_F_DETERMINISTIC): no floating-point atomics -- every thread keeps the sums of its own component (a
+    // thread's k is fixed: the grid stride is a multiple of KP), the block adds them in thread order and writes its
+    // partials to blk_part[block][DET_FU_SLOTS]; k_det_sum_blocks adds the blocks in index order.
     __shared__ double sSlog[64], sShat[64], sH, sP;
+    __shared__ double sA[256], sB[256];
+    double dSlog = 0.0, dShat = 0.0;
     __shared__ float smax[8];
     if (threadIdx.x < 64) { sSlog[threadIdx.x] = 0.0; sShat[threadIdx.x] = 0.0; }
     if (threadIdx.x == 0) { sH = 0.0; sP = 0.0; }
@@ -424,8 +429,8 @@ k_factor_update(long long rows, int K, int KP,
             if (eEl_new) eEl_new[idx] = eE != 0.f ? eE * Elog : 0.f;     // sparse_zigap.py:116 operand
         }
         if (!Slog) continue;
-        atomicAdd(&sSlog[k], (double)Elog);
-        atomicAdd(&sShat[k], (double)E);
+        if (blk_part) { dSlog += (double)Elog; dShat += (double)E; }
+        else { atomicAdd(&sSlog[k], (double)Elog); atomicAdd(&sShat[k], (double)E); }
         // entropy of q: a - log b + lgamma(a) + (1 - a) psi(a), with psi(a) taken as Elog + log b from the float32
         // Elog that also enters the prior term (alpha1 - 1) sum Elog: when a ~ 1e-15 (zero NMF factors, base.py:38-40)
         // psi ~ -1e15 and the two terms only cancel if they carry the same rounding
@@ -438,6 +443,24 @@ k_factor_update(long long rows, int K, int KP,
     for (int o = 16; o > 0; o >>= 1) {
         tH += __shfl_xor_sync(0xffffffffu, tH, o);
         tP += __shfl_xor_sync(0xffffffffu, tP, o);
+    }
+    if (blk_part) {
+        double* out = blk_part + (long long)blockIdx.x * DET_FU_SLOTS;
+        sA[threadIdx.x] = dSlog; sB[threadIdx.x] = dShat;
+        __shared__ double sW[2][8];
+        if ((threadIdx.x & 31) == 0) { sW[0][warp] = tH; sW[1][warp] = tP; }
+        __syncthreads();
+        if (threadIdx.x < KP) {
+            double a = 0.0, b = 0.0;
+            for (int r = 0; r < 256 / KP; ++r) { a += sA[r * KP + threadIdx.x]; b += sB[r * KP + threadIdx.x]; }
+            out[threadIdx.x] = a; out[64 + threadIdx.x] = b;
+        }
+        if (threadIdx.x == 0) {
+            double h = 0.0, q = 0.0;
+            for (int w = 0; w < 8; ++w) { h += sW[0][w]; q += sW[1][w]; }
+            out[128] = h; out[129] = q;
+        }
+        return;
     }
     if ((threadIdx.x & 31) == 0) { atomicAdd(&sH, tH); atomicAdd(&sP, tP); }
     __syncthreads();
@@ -1019,6 +1042,21 @@ int launch_pass_genes_simt(const ori_problem_t* P, int g, cudaStream_t st) {
     return set_error(ORI_EINVAL, "KP must be 8, 16, 32 or 64 (got %d)", P->KP);
 }
 
+// ORI_F_DETERMINISTIC: the per-block partials of k_factor_update, added block by block in index order
+__global__ void k_det_sum_blocks(const double* __restrict__ blk_part, int nblocks, int K,
+                                 double* __restrict__ Slog, double* __restrict__ Shat,
+                                 double* __restrict__ Hsum, double* __restrict__ PUVsum)
+{
+    const int t = threadIdx.x;
+    if (t >= DET_FU_SLOTS) return;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += blk_part[(long long)b * DET_FU_SLOTS + t];
+    if (t < 64) { if (Slog && t < K) Slog[t] += s; }
+    else if (t < 128) { if (Slog && t - 64 < K) Shat[t - 64] += s; }
+    else if (t == 128) { if (Slog) *Hsum += s; }
+    else if (PUVsum) *PUVsum += s;
+}
+
 static int update_grid(long long total) {
     long long b = (total + 255) / 256;
     return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
@@ -1033,26 +1071,32 @@ int launch_row_update(const ori_problem_t* P, int g, int write_state, cudaStream
     double* SU = P->red64 + p + KP;
     double* part = P->red64 + p + 2 * KP;
     const bool drop = P->flags & ORI_F_DROPOUT, sparse = P->flags & ORI_F_SPARSE;
+    const bool det = (P->flags & ORI_F_DETERMINISTIC) && P->det_ws;
     const int grid = update_grid(P->n_rows * KP);
     if (write_state >= 2) {
         const bool sums = write_state == 2;
         k_factor_update<true><<<grid, 256, 0, st>>>(P->n_rows, K, KP, nullptr, nullptr, nullptr, nullptr,
             nullptr, nullptr, nullptr, P->a1, P->a2, P->U_hat[g], P->eU[g], sparse ? P->eUl[g] : nullptr, P->xrow,
-            sums ? SlogU : nullptr, SU, part + R64_HROW, nullptr, 1, P->thrU ? P->thrU + (long long)g * P->n_rows : nullptr);
+            sums ? SlogU : nullptr, SU, part + R64_HROW, nullptr, 1, P->thrU ? P->thrU + (long long)g * P->n_rows : nullptr,
+            (det && sums) ? P->det_ws : nullptr);
+        if (det && sums) k_det_sum_blocks<<<1, 256, 0, st>>>(P->det_ws, grid, K, SlogU, SU, part + R64_HROW, nullptr);
     } else {
         // GaP: rate = alpha2 + sum_j V_hat_jk (gap.py:98); the column sums live in gsum[KP..2KP)
         k_factor_update<false><<<grid, 256, 0, st>>>(P->n_rows, K, KP, P->Zi, P->eU[g],
             drop ? P->a2s : nullptr, P->gsum + KP, P->hyper, P->hyper + K, P->U_hat[g],
             P->a1, P->a2, P->U_hat[1 - g], P->eU[1 - g], sparse ? P->eUl[1 - g] : nullptr, P->xrow, SlogU, SU,
-            part + R64_HROW, part + R64_PUV, write_state, P->thrU ? P->thrU + (long long)(1 - g) * P->n_rows : nullptr);
+            part + R64_HROW, part + R64_PUV, write_state, P->thrU ? P->thrU + (long long)(1 - g) * P->n_rows : nullptr,
+            det ? P->det_ws : nullptr);
+        if (det) k_det_sum_blocks<<<1, 256, 0, st>>>(P->det_ws, grid, K, SlogU, SU, part + R64_HROW, part + R64_PUV);
     }
-    return check_launch("k_factor_update(rows)");
+    return check_launch("k_factor_update(rows)", det ? 2 : 1);
 }
 
 int launch_gene_update(const ori_problem_t* P, int write_state, cudaStream_t st) {
     const int p = P->p, K = P->K, KP = P->KP;
     const bool drop = P->flags & ORI_F_DROPOUT;
     double* SlogV = P->gsum; double* SV = P->gsum + KP; double* gpart = P->gsum + 2 * KP;
+    const bool det = (P->flags & ORI_F_DETERMINISTIC) && P->det_ws && !(P->flags & ORI_F_SPARSE);
     const int grid = update_grid((long long)p * KP);
     if (P->flags & ORI_F_SPARSE) {
         const int gs = cdiv(p, 128);
@@ -1062,15 +1106,18 @@ int launch_gene_update(const ori_problem_t* P, int write_state, cudaStream_t st)
     }
     if (write_state == 2) {
         k_factor_update<true><<<grid, 256, 0, st>>>(p, K, KP, nullptr, nullptr, nullptr, nullptr,
-            nullptr, nullptr, nullptr, P->b1, P->b2, P->V_hat, P->eV, nullptr, P->xcol, SlogV, SV, gpart, nullptr, 1, P->thrV);
+            nullptr, nullptr, nullptr, P->b1, P->b2, P->V_hat, P->eV, nullptr, P->xcol, SlogV, SV, gpart, nullptr, 1, P->thrV,
+            det ? P->det_ws : nullptr);
     } else {
         // GaP: rate = beta2 + sum_i U_hat_ik (gap.py:106) with the NEW U_hat: red64[p+KP ..)
         float* Zj = P->red32; float* b2s = P->red32 + (long long)p * KP;
         k_factor_update<false><<<grid, 256, 0, st>>>(p, K, KP, Zj, P->eV, drop ? b2s : nullptr,
             P->red64 + p + KP, P->hyper + 2 * K, P->hyper + 3 * K, nullptr,
-            P->b1, P->b2, P->V_hat, P->eV, nullptr, P->xcol, SlogV, SV, gpart, nullptr, write_state, P->thrV);
+            P->b1, P->b2, P->V_hat, P->eV, nullptr, P->xcol, SlogV, SV, gpart, nullptr, write_state, P->thrV,
+            det ? P->det_ws : nullptr);
     }
-    return check_launch("k_factor_update(genes)");
+    if (det) k_det_sum_blocks<<<1, 256, 0, st>>>(P->det_ws, grid, K, SlogV, SV, gpart, nullptr);
+    return check_launch("k_factor_update(genes)", det ? 2 : 1);
 }
 
 int launch_mstep(const ori_problem_t* P, int mode, cudaStream_t st) {

@@ -181,6 +181,12 @@ struct TcArgs {
     const float* thr_own;            // [own_total]
     const float* thr_sw;             // [sw_total]
     const float* thr_sw_max;         // [1] largest thr_sw
+    // ORI_F_DETERMINISTIC (both NULL otherwise): the chunk items of an own tile add their accumulators in chunk order
+    // -- tickets[tile] counts the element-wise warps that have finished, item by item -- and the ELBO terms of every
+    // (item, CTA, warp) go to their own slot of item_part instead of one atomic target (k_det_sum_items adds them in order)
+    int* tickets;                    // [n_own_tiles], zero before the launch
+    double* item_part;               // [n_items][DET_ITEM_SLOTS]
+    double* colsum2;                 // [genes] column sums of the second column slice: a gene's two warps never share a target
 };
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -261,7 +267,9 @@ struct TileIter {
 
 // UFL: underflow-emulation hooks (TcArgs::thr_*).  A separate instantiation: two more live registers in the element-wise
 // loop cost the plain kernels 7 % (row pass) / 3 % (gene pass) when the hooks were runtime-switched.
-template <bool GENES, bool DROPOUT, bool ELBO, bool PAIR, int KP, bool PRECISE, bool DEVI = false, bool UFL = false>
+// DET: the ORI_F_DETERMINISTIC epilogue (TcArgs::tickets / item_part), a separate instantiation for the same reason (runtime-
+// switched it cost the plain kernels 2.6 % / 3.4 %).
+template <bool GENES, bool DROPOUT, bool ELBO, bool PAIR, int KP, bool PRECISE, bool DEVI = false, bool UFL = false, bool DET = false>
 #if ORI_TC_NEW == 16
 __global__ void __maxnreg__(96)
 #else
@@ -1023,6 +1031,16 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             //      slice 0 drains acc1, slice 1 acc2
             mbar_wait(&bars[B_ACC_READY], li & 1, 32);
             tc_fence_after();
+            const int det_tile = ti.own0 / TC_OWN;
+            if (DET && a.tickets) {          // wait until every warp of the previous chunk item of this own tile has added its sums
+                const int want = (ti.item / a.n_own_units) * NEW;
+                if (lane == 0) {
+                    volatile int* tk = a.tickets + det_tile;
+                    while (*tk < want) __nanosleep(200);
+                }
+                __syncwarp();
+                __threadfence();
+            }
             if (aside == 0 || DROPOUT) {
                 float* out = (aside == 0 ? a.acc1 : a.acc2) + own_idx * KP;
 #pragma unroll
@@ -1040,7 +1058,10 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             __syncwarp();
             if (lane == 0) arrive_leader(&bars[B_ACC_FREE]);
             if (GENES) {
-                if (DROPOUT && own_ok) atomicAdd(a.colsum + own_idx, (double)cs);
+                if (DROPOUT && own_ok) {
+                    static_assert(!DET || SLICES == 2, "deterministic epilogue: two column slices");
+                    atomicAdd(((DET && slice) ? a.colsum2 : a.colsum) + own_idx, (double)cs);
+                }
                 if (ELBO) {
                     if (!own_ok) { acc_xl = 0.0; acc_ent = 0.0; }
 #pragma unroll
@@ -1049,10 +1070,21 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                         acc_ent += __shfl_xor_sync(0xffffffffu, acc_ent, o);
                     }
                     if (lane == 0) {
-                        atomicAdd(a.part64 + R64_XLOGDEN, acc_xl * (double)LN2);
-                        if (DROPOUT) atomicAdd(a.part64 + R64_ENT, acc_ent * (double)LN2);
+                        if (DET && a.item_part) {
+                            double* slot = a.item_part + ((long long)ti.item * DET_ITEM_SLOTS + (rank * NEW + ew) * 2);
+                            slot[0] = acc_xl * (double)LN2;
+                            slot[1] = DROPOUT ? acc_ent * (double)LN2 : 0.0;
+                        } else {
+                            atomicAdd(a.part64 + R64_XLOGDEN, acc_xl * (double)LN2);
+                            if (DROPOUT) atomicAdd(a.part64 + R64_ENT, acc_ent * (double)LN2);
+                        }
                     }
                 }
+            }
+            if (DET && a.tickets) {          // this warp's sums are in: let the next chunk item of the tile proceed
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicAdd(a.tickets + det_tile, 1);
             }
             ++li;
             ti.item += ti.stride;
@@ -1174,8 +1206,54 @@ __global__ void k_tc_prep_dev(const float* __restrict__ lp, const double* __rest
     reinterpret_cast<float4*>(out)[2 * (long long)j + 1] = b;
 }
 
+// ORI_F_DETERMINISTIC: the per-(item, CTA, warp) ELBO terms of the gene pass, added in index order by one block
+__global__ void __launch_bounds__(1024)
+k_det_sum_items(const double* __restrict__ item_part, long long n_slots, double* __restrict__ part64)
+{
+    __shared__ double s0[1024], s1[1024];
+    double a = 0.0, b = 0.0;
+    // thread t owns the contiguous range [t * per, (t + 1) * per): a fixed order whatever the timing
+    const long long per = (n_slots + 1023) / 1024;
+    const long long lo = (long long)threadIdx.x * per, hi = lo + per < n_slots ? lo + per : n_slots;
+    for (long long i = lo; i < hi; ++i) { a += item_part[2 * i]; b += item_part[2 * i + 1]; }
+    s0[threadIdx.x] = a; s1[threadIdx.x] = b;
+    __syncthreads();
+    for (int w = 512; w > 0; w >>= 1) {
+        if (threadIdx.x < w) { s0[threadIdx.x] += s0[threadIdx.x + w]; s1[threadIdx.x] += s1[threadIdx.x + w]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { part64[R64_XLOGDEN] += s0[0]; part64[R64_ENT] += s1[0]; }
+}
+
+__global__ void k_det_add(double* __restrict__ dst, const double* __restrict__ src, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
+// accumulation chunk lengths in sweep entries (see tc_partition)
+#ifndef ORI_TC_CHUNK
+#define ORI_TC_CHUNK 16384
+#endif
+#ifndef ORI_TC_CHUNK_PRECISE
+#define ORI_TC_CHUNK_PRECISE 2048
+#endif
 static long long pad128(long long v) { return (v + 127) / 128 * 128; }
+
+long long det_max_items(long long n_rows, int p) {
+    // items = own units x sweep chunks; the shortest nominal chunk is ORI_TC_CHUNK_PRECISE sweep entries, own units are at
+    // least 128 wide, and the small-problem splitting of tc_partition stops below one item per SM
+    const long long np = pad128(n_rows), pp = pad128(p);
+    const long long a = (np / 128) * (pp / ORI_TC_CHUNK_PRECISE + 1), b = (pp / 128) * (np / ORI_TC_CHUNK_PRECISE + 1);
+    long long m = a > b ? a : b;
+    return m > 2 * 148 ? m : 2 * 148;
+}
+long long det_workspace_doubles(long long n_rows, int p, int KP) {
+    (void)KP;
+    const long long tiles = (pad128(n_rows) + pad128(p)) / 128 + 64;
+    return (long long)DET_FU_BLOCKS * DET_FU_SLOTS + pad128(p) + det_max_items(n_rows, p) * DET_ITEM_SLOTS + (tiles + 1) / 2;
+}
 
 long long tc_workspace_floats(long long n_rows, int p, int KP) {
     const long long np = pad128(n_rows), pp = pad128(p);
@@ -1292,12 +1370,6 @@ static bool use_pair() { static int v = env_int("ORI_TC_PAIR", 1); return v != 0
 // item instead (two accumulator sets in TMEM, the element-wise warps flushing one while the other accumulates) was built
 // and measured: 60.2 / 24.3 / 34.4 ms -- the flush code in the element-wise loop costs more than the drains it saves.
 // Problems too small to give every SM (pair) an item are split further.
-#ifndef ORI_TC_CHUNK
-#define ORI_TC_CHUNK 16384
-#endif
-#ifndef ORI_TC_CHUNK_PRECISE
-#define ORI_TC_CHUNK_PRECISE 2048
-#endif
 static void tc_partition(TcArgs& a, bool genes, int units, int sw, bool precise, bool fixed_chain) {
     // the row pass sweeps the genes: its chaining depends on p only (not on the sharding / slabbing of the cells), so its
     // chunks may be twice as long -- one item per row block up to p = 32768 -- at the same accumulation bias
@@ -1314,9 +1386,9 @@ static void tc_partition(TcArgs& a, bool genes, int units, int sw, bool precise,
     a.n_items = a.n_own_units * a.n_chunks;
 }
 
-template <bool GENES, bool D, bool E, bool PAIR, int KP, bool PRECISE, bool UFL = false>
+template <bool GENES, bool D, bool E, bool PAIR, int KP, bool PRECISE, bool UFL = false, bool DET = false>
 static int launch_tc_variant(const TcMaps& maps, const TcArgs& a, int grid, cudaStream_t st) {
-    auto kern = k_tc_pass<GENES, D, E, PAIR, KP, PRECISE, false, UFL>;
+    auto kern = k_tc_pass<GENES, D, E, PAIR, KP, PRECISE, false, UFL, DET>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<KP, PAIR, PRECISE>::SMEM_BYTES);
@@ -1376,7 +1448,37 @@ static int launch_tc_pass_p(const ori_problem_t* P, int gen_old, cudaStream_t st
     const int units = num_sms() / NCTA;
     tc_partition(a, GENES, units, SW, PRECISE, (P->flags & ORI_F_FIXED_CHAIN) != 0);
     const int grid = NCTA * (a.n_items < units ? a.n_items : units);
+    a.tickets = nullptr; a.item_part = nullptr; a.colsum2 = nullptr;
+    const bool det = (P->flags & ORI_F_DETERMINISTIC) && P->det_ws;
+    if (det) {
+        if (a.n_items > det_max_items(P->n_rows, P->p)) return set_error(ORI_EINVAL, "det_ws too small for %d items", a.n_items);
+        a.colsum2 = P->det_ws + (long long)DET_FU_BLOCKS * DET_FU_SLOTS;
+        a.item_part = a.colsum2 + pad128(P->p);
+        if (GENES && drop) {
+            const cudaError_t e2 = cudaMemsetAsync(a.colsum2, 0, sizeof(double) * (size_t)P->p, st);
+            if (e2 != cudaSuccess) return set_error(ORI_ECUDA, "cudaMemsetAsync(colsum2): %s", cudaGetErrorString(e2));
+        }
+        a.tickets = reinterpret_cast<int*>(a.item_part + det_max_items(P->n_rows, P->p) * DET_ITEM_SLOTS);
+        cudaError_t e_ = cudaMemsetAsync(a.tickets, 0, sizeof(int) * (size_t)(a.n_own_tiles + 2), st);
+        if (e_ != cudaSuccess) return set_error(ORI_ECUDA, "cudaMemsetAsync(tickets): %s", cudaGetErrorString(e_));
+        if (!(GENES && elbo)) a.item_part = nullptr;
+        else {      // slots of the second CTA stay unwritten with the single-CTA kernels
+            e_ = cudaMemsetAsync(a.item_part, 0, sizeof(double) * (size_t)a.n_items * DET_ITEM_SLOTS, st);
+            if (e_ != cudaSuccess) return set_error(ORI_ECUDA, "cudaMemsetAsync(item_part): %s", cudaGetErrorString(e_));
+        }
+    }
     int rc;
+    if (det) {
+        if (ufl) return set_error(ORI_EUNSUPPORTED, "ORI_F_DETERMINISTIC and the underflow thresholds cannot be combined on the tensor path");
+        if constexpr (PAIR) {
+            if (drop && elbo) rc = launch_tc_variant<GENES, true, true, PAIR, KP, PRECISE, false, true>(maps, a, grid, st);
+            else if (drop) rc = launch_tc_variant<GENES, true, false, PAIR, KP, PRECISE, false, true>(maps, a, grid, st);
+            else if (elbo) rc = launch_tc_variant<GENES, false, true, PAIR, KP, PRECISE, false, true>(maps, a, grid, st);
+            else rc = launch_tc_variant<GENES, false, false, PAIR, KP, PRECISE, false, true>(maps, a, grid, st);
+        } else {
+            return set_error(ORI_EUNSUPPORTED, "ORI_F_DETERMINISTIC needs the CTA-pair kernels (ORI_TC_PAIR=1)");
+        }
+    } else
     if (ufl) {
         if constexpr (PAIR) {
             if (drop && elbo) rc = launch_tc_variant<GENES, true, true, PAIR, KP, PRECISE, true>(maps, a, grid, st);
@@ -1392,6 +1494,13 @@ static int launch_tc_pass_p(const ori_problem_t* P, int gen_old, cudaStream_t st
     else if (elbo) rc = launch_tc_variant<GENES, false, true, PAIR, KP, PRECISE>(maps, a, grid, st);
     else rc = launch_tc_variant<GENES, false, false, PAIR, KP, PRECISE>(maps, a, grid, st);
     if (rc != ORI_OK) return rc;
+    int extra = 0;
+    if (det && GENES && drop) { k_det_add<<<cdiv(P->p, 256), 256, 0, st>>>(P->red64, a.colsum2, P->p); ++extra; }
+    if (a.item_part) {
+        k_det_sum_items<<<1, 1024, 0, st>>>(a.item_part, (long long)a.n_items * (DET_ITEM_SLOTS / 2), P->red64 + P->p + 2 * P->KP);
+        ++extra;
+    }
+    if (extra) return check_launch("k_tc_pass + deterministic sums", 1 + extra);
     return check_launch(GENES ? "k_tc_pass(genes)" : "k_tc_pass(rows)");
 }
 

@@ -79,7 +79,7 @@ class FactorModel(metaclass=ABCMeta):
 
     def __init__(self, cmatrix, k=2, use_factors=True, *, state=None, compat_quirk=False, sharded=False,
                  process_group=None, elbo=True, trace_cap=4096, force_simt=False, tensor=None, nmf=None, graphs=False,
-                 keep_hyper=True, precise=False, emulate_underflow=False):
+                 keep_hyper=True, precise=False, emulate_underflow=False, deterministic=False):
         self._dev = _lib.require_cuda()
         self._lib = _lib.load()
         _lib.check(self._lib.ori_device_check(self._dev.index or 0))
@@ -122,6 +122,15 @@ class FactorModel(metaclass=ABCMeta):
         # gap.py:73-76: terms with log_U_hat + log_V_hat <= -103.97 are 0 there; an entry whose terms all are assigns its
         # count to no component).  Off by default, like the quirk: the default keeps the exact ratios.
         self.emulate_underflow = bool(emulate_underflow)
+        # deterministic=True (tensor path, dense models): every floating-point sum is formed in a fixed order (ORI_F_DETERMINISTIC):
+        # two runs from the same state on the same device agree bit for bit
+        self.deterministic = bool(deterministic)
+        if self.deterministic:
+            if self._sparse or not self._tensor:
+                raise ValueError('deterministic=True needs the tensor path (tensor=True or >= 2^21 entries) and a dense model')
+            if self.emulate_underflow:
+                raise ValueError('deterministic=True and emulate_underflow=True cannot be combined')
+            self._flags |= _lib.ORI_F_DETERMINISTIC
         self._graphs = {} if graphs else None
         self.graph_replays = 0
         self._graph_kernels = 0
@@ -234,6 +243,10 @@ class FactorModel(metaclass=ABCMeta):
             P.tc_ws, P.tc_ws_floats = self._tc_ws.data_ptr(), self._tc_ws.numel()
         P.xrow, P.xcol = ptr(self._xrow), ptr(self._xcol)
         P.thrU, P.thrV = ptr(self._thrU), ptr(self._thrV)
+        self._det_ws = None
+        if self.deterministic:
+            self._det_ws = torch.zeros((int(self._lib.ori_det_workspace_doubles(n, p, KP)) + 8,), **f64)
+            P.det_ws, P.det_ws_doubles = self._det_ws.data_ptr(), self._det_ws.numel()
         self._bind_extra(P, rowf, genef, ptr)
         self._P = P
         _lib.check(self._lib.ori_problem_check(ctypes.byref(P)))

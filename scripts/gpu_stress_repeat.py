@@ -1,17 +1,17 @@
 """Run the same CAVI steps several times from one state and report, per step count, the spread between runs: the only
 source of run-to-run variation is the order of the floating-point atomics (the kernels themselves are deterministic), and the
 iteration amplifies it step by step.  An outlier against the trend would mean a race.
-Usage: python scripts/gpu_stress_repeat.py [reps] [n p K] [simt|precise]"""
+Usage: python scripts/gpu_stress_repeat.py [reps] [n p K] [simt|precise|det]  (det: ORI_F_DETERMINISTIC, expected spread 0)"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from oriana.models import ZIGaP
 from oriana.singlecell import synth_counts_device
 
-args = [a for a in sys.argv[1:] if a not in ('simt', 'precise')]
+args = [a for a in sys.argv[1:] if a not in ('simt', 'precise', 'det')]
 reps = int(args[0]) if len(args) > 0 else 6
 n, p, K = (int(a) for a in args[1:4]) if len(args) > 3 else (4000, 1700, 12)
-kw = dict(tensor=('simt' not in sys.argv), precise=('precise' in sys.argv))
+kw = dict(tensor=('simt' not in sys.argv), precise=('precise' in sys.argv), deterministic=('det' in sys.argv))
 X = synth_counts_device(n, p, K, seed=8)
 np.random.seed(5)
 m0 = ZIGaP(X[:, :p], k=K, use_factors=False, **kw)

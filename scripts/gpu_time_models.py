@@ -19,7 +19,7 @@ for (n, p, K) in sizes:
         for elbo in ((True,) if quick else (True, False)):
             np.random.seed(0)
             m = cls(X[:, :p], k=K, use_factors=False, tensor=True, elbo=elbo, precise='precise' in sys.argv,
-                    emulate_underflow='underflow' in sys.argv)
+                    emulate_underflow='underflow' in sys.argv, deterministic='det' in sys.argv)
             for _ in range(2): m.step()
             m.enable_kernel_timing()
             for _ in range(4): m.step()

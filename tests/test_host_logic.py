@@ -209,7 +209,7 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().ori_version() >= 100
     # struct layout agreed between the header and the ctypes mirror
     n_ptr = len(re.findall(r'^\s+(?:const\s+)?(?:float|double)\s*\*', header.split('typedef struct ori_problem')[1].split('} ori_problem_t')[0], flags=re.M))
-    assert ctypes.sizeof(_lib.OriProblem) == 3 * 8 + 6 * 4 + 24 * 8 + 8 + 9 * 8 + 2 * 8 + 2 * 8 and n_ptr >= 20   # + the sparse block + xrow, xcol + thrU, thrV
+    assert ctypes.sizeof(_lib.OriProblem) == 3 * 8 + 6 * 4 + 24 * 8 + 8 + 9 * 8 + 2 * 8 + 2 * 8 + 2 * 8 and n_ptr >= 20   # + the sparse block + xrow, xcol + thrU, thrV + det_ws, det_ws_doubles
 
 
 def test_no_cpu_fallback():

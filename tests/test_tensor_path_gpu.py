@@ -284,3 +284,50 @@ def test_config5_slab_tensor_path_matches_cuda_core_path(cuda_lib):
     et, es = mt.elbo_trace, ms.elbo_trace
     assert np.max(np.abs(et - es) / np.abs(es)) < 1e-4, (et, es)
     assert (np.diff(et) > 0).all()
+
+
+@pytest.mark.parametrize('shape,kw', [((4000, 1700, 12), {}), ((40000, 600, 8), {}), ((6000, 900, 20), dict(precise=True)),
+                                      ((3000, 1000, 40), {})])
+@pytest.mark.parametrize('model', ['zigap', 'gap'])
+def test_deterministic_mode_repeats_bit_for_bit(cuda_lib, model, shape, kw):
+    """ORI_F_DETERMINISTIC: chunk items add their accumulators in chunk order (tickets), ELBO terms and factor sums go through
+    per-item / per-block slots summed in index order.  Three runs from the same state agree in every bit of every
+    parameter after 6 steps (the plain kernels differ between runs by up to 1e-4 in single entries: float atomics), and
+    agree with the plain kernels to the tensor path's tolerance.  Shapes: one chunk per gene block; three chunks (tickets
+    at work); the fp32-grade plan (2048-cell chunks); the K = 64 plan."""
+    from oracle import cavi_numpy as cn
+    from oriana.models import GaP, ZIGaP
+    from oriana.singlecell import CountMatrix
+    n, p, K = shape
+    X = cn.synth_counts(n, p, K, seed=n % 97)
+    s = cn.init_state(X, K, np.random.default_rng(1), model)
+    cls = ZIGaP if model == 'zigap' else GaP
+    names = ('a1', 'a2', 'b1', 'b2', 'alpha1', 'alpha2', 'beta1', 'beta2') + (('pi_d',) if model == 'zigap' else ())
+
+    def run(**extra):
+        m = cls(CountMatrix(X), k=K, use_factors=False, state=s, tensor=True, **kw, **extra)
+        assert m.uses_tensor_path
+        for _ in range(6):
+            m.step()
+        return {k: getattr(m, k).asarray().copy() for k in names}, np.asarray(m.elbo_trace).copy()
+
+    runs = [run(deterministic=True) for _ in range(3)]
+    for got, tr in runs[1:]:
+        for k in names:
+            assert np.array_equal(got[k], runs[0][0][k]), (k, float(np.max(np.abs(got[k] - runs[0][0][k]))))
+        # the trace also carries sum lgamma(X + 1), a constant formed once per model with double-precision atomics
+        np.testing.assert_allclose(tr, runs[0][1], rtol=1e-13)
+    plain, ptr = run()
+    for k in names:
+        assert relerr(plain[k], runs[0][0][k]) < 5e-3, k
+    np.testing.assert_allclose(ptr, runs[0][1], rtol=1e-5)
+
+
+def test_deterministic_mode_needs_the_tensor_path(cuda_lib):
+    from oriana.models import SparseZIGaP, ZIGaP
+    from oriana.singlecell import CountMatrix
+    X = np.ones((64, 32))
+    with pytest.raises(ValueError):
+        ZIGaP(CountMatrix(X), k=2, use_factors=False, deterministic=True)            # CUDA-core kernels at this size
+    with pytest.raises(ValueError):
+        SparseZIGaP(CountMatrix(X), k=2, use_factors=False, tensor=True, deterministic=True)

@@ -55,11 +55,12 @@ extern "C" {
                                  accumulation chunks at their nominal length even when the slab is too small to fill the
                                  machine, so that its sums are chained -- and rounded -- like the resident matrix's          */
 
-#define ORI_F_DETERMINISTIC 256u /* tensor path, dense models: every sum that the plain kernels form with floating-point atomics is
-                                 formed in a fixed order instead -- the chunk items of a row block / gene block add their partial
-                                 sums one after the other (a ticket per block), per-item ELBO terms and per-block factor sums go
-                                 through scratch arrays that are summed in index order -- so two runs of the same problem on the
-                                 same device agree bit for bit.  Needs det_ws.                                              */
+#define ORI_F_DETERMINISTIC 256u /* every sum that the plain kernels form with floating-point atomics is formed in a fixed order
+                                 instead, so two runs of the same problem on the same device agree bit for bit.  Tensor kernels:
+                                 the chunk items of a row block / gene block add their partial sums one after the other (a
+                                 ticket per block); per-item ELBO terms and per-block factor sums go through scratch arrays
+                                 that are summed in index order.  CUDA-core kernels (up to 2^26 matrix entries): one CTA per
+                                 row block, per-CTA / per-row-chunk slots summed in index order.  Needs det_ws.             */
 
 /* modes of ori_mstep */
 #define ORI_M_STEP 0          /* regular end of iteration t+1: finalise ELBO(t), pi(t); M-step; next lp   */

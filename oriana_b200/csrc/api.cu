@@ -152,8 +152,8 @@ int ori_problem_check(const ori_problem_t* P) {
     if (P->tc_ws && (((uintptr_t)P->tc_ws & 127) || P->tc_ws_floats < tc_workspace_floats(P->n_rows, P->p, P->KP)))
         return set_error(ORI_EINVAL, "tc_ws must be 128-byte aligned and hold ori_tc_workspace_floats() floats");
     if (P->flags & ORI_F_DETERMINISTIC) {
-        if (P->flags & ORI_F_SPARSE) return set_error(ORI_EUNSUPPORTED, "ORI_F_DETERMINISTIC is not available for the sparse model");
-        if (!P->tc_ws) return set_error(ORI_EUNSUPPORTED, "ORI_F_DETERMINISTIC needs the tensor path (tc_ws)");
+        if (!P->tc_ws && !det_simt_ok(P->n_rows, P->p))
+            return set_error(ORI_EUNSUPPORTED, "ORI_F_DETERMINISTIC on the CUDA-core kernels is limited to 2^26 matrix entries");
         if (!P->det_ws || P->det_ws_doubles < det_workspace_doubles(P->n_rows, P->p, P->KP))
             return set_error(ORI_EINVAL, "ORI_F_DETERMINISTIC needs det_ws of ori_det_workspace_doubles() doubles");
     }

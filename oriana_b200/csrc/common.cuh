@@ -57,8 +57,15 @@ long long tc_workspace_floats(long long n_rows, int p, int KP);
 constexpr int DET_FU_BLOCKS = 148 * 8;
 constexpr int DET_FU_SLOTS = 2 * 64 + 2;
 constexpr int DET_ITEM_SLOTS = 2 * 8 * 2;          // CTAs of a pair x element-wise warps x (x log den, entropy)
+//   CUDA-core kernels (problems up to DET_SIMT_MAX entries), from det_simt_offset():
+//   [nb x p] column sums per row block | [nb x 2] ELBO terms per row block | [chunks x 3 x p x KP] floats: gene sums per row chunk
+constexpr long long DET_SIMT_MAX = 1ll << 26;
 long long det_max_items(long long n_rows, int p);
 long long det_workspace_doubles(long long n_rows, int p, int KP);
+long long det_simt_offset(long long n_rows, int p);
+inline bool det_simt_ok(long long n_rows, int p) { return n_rows * (long long)p <= DET_SIMT_MAX; }
+// src[n][2] added in index order by one block: *dst0 += sum src[.][0], *dst1 += sum src[.][1]
+int launch_det_sum_pairs(const double* src, long long n, double* dst0, double* dst1, cudaStream_t st);
 bool tc_eligible(const ori_problem_t* P);
 int launch_tc_prep_genes(const ori_problem_t* P, cudaStream_t st);
 int launch_tc_prep_rows(const ori_problem_t* P, int gen_old, cudaStream_t st);

@@ -54,8 +54,11 @@ k_pass_rows(const float* __restrict__ X, long long ldx, long long n_rows, int p,
             const float* __restrict__ lp, const float* __restrict__ pfloor,
             float* __restrict__ Zi, float* __restrict__ a2s,
             double* __restrict__ colsum, double* __restrict__ part64,
-            const float* __restrict__ thrU, const float* __restrict__ thrV)
+            const float* __restrict__ thrU, const float* __restrict__ thrV,
+            double* __restrict__ det_cs, double* __restrict__ det_part)
 {
+    // det_cs / det_part (ORI_F_DETERMINISTIC, launched with gridDim.y == 1): this CTA's column sums and ELBO terms go to
+    // its own slots [blockIdx.x][p] / [blockIdx.x][2] instead of atomic targets; launch_det_sum_* add them in index order
     __shared__ float sX[PR_TR][PR_TG + 1];
     __shared__ float sthr[PR_TG];
     __shared__ __align__(16) float sV[PR_TG][KP];
@@ -186,7 +189,8 @@ k_pass_rows(const float* __restrict__ X, long long ldx, long long n_rows, int p,
                 float tot = 0.f;
 #pragma unroll
                 for (int w = 0; w < PR_TR / 32; ++w) tot += scs[w][tid];
-                atomicAdd(colsum + j0 + tid, (double)tot);
+                if (det_cs) det_cs[(long long)blockIdx.x * p + j0 + tid] = (double)tot;
+                else atomicAdd(colsum + j0 + tid, (double)tot);
             }
         }
     }
@@ -202,7 +206,10 @@ k_pass_rows(const float* __restrict__ X, long long ldx, long long n_rows, int p,
         if (!row_ok) { acc_xl = 0.0; acc_ent = 0.0; }
         const double s1 = block_reduce_sum(acc_xl, sred);
         const double s2 = block_reduce_sum(acc_ent, sred);
-        if (tid == 0) { atomicAdd(part64 + R64_XLOGDEN, s1); atomicAdd(part64 + R64_ENT, s2); }
+        if (tid == 0) {
+            if (det_part) { det_part[2 * blockIdx.x] = s1; det_part[2 * blockIdx.x + 1] = s2; }
+            else { atomicAdd(part64 + R64_XLOGDEN, s1); atomicAdd(part64 + R64_ENT, s2); }
+        }
     }
 }
 
@@ -223,8 +230,11 @@ k_pass_genes(const float* __restrict__ X, long long ldx, long long n_rows, int p
              const float* __restrict__ eV, const float* __restrict__ Vh,
              const float* __restrict__ lp, const float* __restrict__ pfloor,
              float* __restrict__ Zj, float* __restrict__ b2s, float* __restrict__ Zl,
-             const float* __restrict__ thrU, const float* __restrict__ thrV)
+             const float* __restrict__ thrU, const float* __restrict__ thrV,
+             float* __restrict__ det_z, long long det_stride)
 {
+    // det_z (ORI_F_DETERMINISTIC): the sums of row chunk blockIdx.y are stored to det_z[blockIdx.y][Zj | b2s | Zl][p x KP]
+    // instead of added atomically; k_det_sum_chunks adds the chunks in index order
     __shared__ float sthr[PG_TR];
     __shared__ __align__(16) float sUl[SPARSE ? PG_TR : 1][KP];
     __shared__ __align__(16) float sU[PG_TR][KP];
@@ -335,7 +345,16 @@ k_pass_genes(const float* __restrict__ X, long long ldx, long long n_rows, int p
             }
         }
     }
-    if (j_ok) {
+    if (j_ok && det_z) {
+        float* base = det_z + (long long)blockIdx.y * det_stride + (long long)j * KP;
+        const long long pk = (long long)p * KP;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            base[k] = zj[k];
+            if (DROPOUT) base[pk + k] = bs[k];
+            if (SPARSE) base[2 * pk + k] = zl[k];
+        }
+    } else if (j_ok) {
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
             atomicAdd(Zj + (long long)j * KP + k, zj[k]);
@@ -343,6 +362,25 @@ k_pass_genes(const float* __restrict__ X, long long ldx, long long n_rows, int p
             if (SPARSE) atomicAdd(Zl + (long long)j * KP + k, zl[k]);
         }
     }
+}
+
+// ORI_F_DETERMINISTIC helpers of the CUDA-core passes: ordered sums over CTAs / row chunks
+__global__ void k_det_sum_cols(double* __restrict__ colsum, const double* __restrict__ det_cs, int nb, int p)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p) return;
+    double s = 0.0;
+    for (int b = 0; b < nb; ++b) s += det_cs[(long long)b * p + j];
+    colsum[j] += s;
+}
+__global__ void k_det_sum_chunks_strided(float* __restrict__ dst, const float* __restrict__ det_z, int ny, long long total,
+                                         long long stride)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float s = 0.f;
+    for (int y = 0; y < ny; ++y) s += det_z[(long long)y * stride + i];
+    dst[i] += s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -642,13 +680,19 @@ __device__ __forceinline__ double nan_to_num_f64(double x) {
 
 template <bool FROM_PARAMS>
 __global__ void __launch_bounds__(128)
-k_sparse_gene_update(ori_problem_t P)
+k_sparse_gene_update(ori_problem_t P, double* __restrict__ blk_part)
 {
+    // blk_part (ORI_F_DETERMINISTIC): the column sums of E[log V'] and E[V'] are formed without atomics -- a fixed
+    // shuffle tree per warp and component, the block's four warps in order, the blocks in order (k_det_sum_blocks)
     __shared__ double sSlog[64], sShat[64];
+    __shared__ double sW[4][64][2];
     if (threadIdx.x < 64) { sSlog[threadIdx.x] = 0.0; sShat[threadIdx.x] = 0.0; }
     __syncthreads();
     const int p = P.p, K = P.K, KP = P.KP;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    double dL[32], dE[32];               // this gene's contributions (K <= 32), kept for the ordered sums
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { dL[k] = 0.0; dE[k] = 0.0; }
     if (j < p) {
         const float* Zj = P.red32;
         const float* b2s = P.red32 + (long long)p * KP;
@@ -692,8 +736,13 @@ k_sparse_gene_update(ori_problem_t P)
             P.p_s[idx] = Sn; P.logV[idx] = Elog; P.V_hat[idx] = veff;
             P.eVd[idx] = ps > P.tau ? 1.f : 0.f;                              // S_tilde (:134), scaled below
             m = fmaxf(m, Elog);
-            atomicAdd(&sSlog[k], (double)Elog);
-            atomicAdd(&sShat[k], (double)E);
+            if (blk_part) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) if (q == k) { dL[q] = (double)Elog; dE[q] = (double)E; }
+            } else {
+                atomicAdd(&sSlog[k], (double)Elog);
+                atomicAdd(&sShat[k], (double)E);
+            }
             ssum += ps;
         }
         // centred exponentials of this gene (special.cuh) and the masked operands of the next iteration
@@ -705,6 +754,24 @@ k_sparse_gene_update(ori_problem_t P)
         }
         if (P.thrV) P.thrV[j] = underflow_thr_f32(m);
         if (!FROM_PARAMS) P.pi_s[j] = ssum / (double)K;                       // :196
+    }
+    if (blk_part) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            double a = dL[k], b = dE[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+            if (lane == 0) { sW[warp][k][0] = a; sW[warp][k][1] = b; }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            double a = 0.0, b = 0.0;
+            for (int w = 0; w < 4; ++w) { a += sW[w][threadIdx.x][0]; b += sW[w][threadIdx.x][1]; }
+            double* out = blk_part + (long long)blockIdx.x * DET_FU_SLOTS;
+            out[threadIdx.x] = a; out[64 + threadIdx.x] = b;
+        }
+        return;
     }
     __syncthreads();
     if (threadIdx.x < K) {
@@ -957,16 +1024,33 @@ static int pass_rows_kp(const ori_problem_t* P, int g, cudaStream_t st) {
     const int ntiles = cdiv(P->p, PR_TG);
     int gy = 1;  // split the gene sweep until there are several waves of CTAs (3 resident per SM): a 1.8-wave grid idles
     while (bx * gy < 148 * 3 * 6 && gy * 2 <= ntiles) gy *= 2;   // most of the machine during its last wave
-    dim3 grid(bx, gy);
     const bool drop = P->flags & ORI_F_DROPOUT, elbo = P->flags & ORI_F_ELBO;
     double* colsum = P->red64;
     double* part = P->red64 + P->p + 2 * P->KP;
+    // ORI_F_DETERMINISTIC: one CTA per row block (a single add per Zi / a2s element), per-CTA slots for the rest
+    double* det_cs = nullptr; double* det_part = nullptr;
+    if ((P->flags & ORI_F_DETERMINISTIC) && P->det_ws) {
+        if (!det_simt_ok(P->n_rows, P->p)) return set_error(ORI_EUNSUPPORTED, "ORI_F_DETERMINISTIC on the CUDA-core kernels: problem too large");
+        gy = 1;
+        det_cs = P->det_ws + det_simt_offset(P->n_rows, P->p);
+        det_part = det_cs + (long long)bx * P->p;
+    }
+    auto det_sums = [&]() -> int {
+        if (!det_cs) return ORI_OK;
+        int nk = 0;
+        if (drop) { k_det_sum_cols<<<cdiv(P->p, 128), 128, 0, st>>>(colsum, det_cs, bx, P->p); ++nk; }
+        if (elbo) { if (launch_det_sum_pairs(det_part, bx, part + R64_XLOGDEN, part + R64_ENT, st) != ORI_OK) return ORI_ECUDA; }
+        return nk ? check_launch("k_det_sum_cols", nk) : ORI_OK;
+    };
+    dim3 grid(bx, gy);
     if (P->flags & ORI_F_SPARSE) {
         if constexpr (KP <= 32) {
             k_pass_rows<KP, true, false, true><<<grid, PR_TR, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, P->eU[g],
                 P->U_hat[g], P->eVd, P->Vh_old, P->eVz, P->V_hat, P->lp, P->pfloor, P->Zi, P->a2s, colsum, part,
-                (P->thrU && P->thrV) ? P->thrU + (long long)g * P->n_rows : nullptr, P->thrU ? P->thrV : nullptr);
-            return check_launch("k_pass_rows(sparse)");
+                (P->thrU && P->thrV) ? P->thrU + (long long)g * P->n_rows : nullptr, P->thrU ? P->thrV : nullptr,
+                det_cs, det_part);
+            if (check_launch("k_pass_rows(sparse)") != ORI_OK) return ORI_ECUDA;
+            return det_sums();
         } else {
             return set_error(ORI_EUNSUPPORTED, "the sparse model needs K <= 32");
         }
@@ -975,13 +1059,14 @@ static int pass_rows_kp(const ori_problem_t* P, int g, cudaStream_t st) {
     k_pass_rows<KP, D, E, false><<<grid, PR_TR, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, P->eU[g], P->U_hat[g], \
                                                   P->eV, P->V_hat, P->eV, P->V_hat, P->lp, P->pfloor, P->Zi, P->a2s, colsum, part, \
                                                   (P->thrU && P->thrV) ? P->thrU + (long long)g * P->n_rows : nullptr, \
-                                                  P->thrU ? P->thrV : nullptr)
+                                                  P->thrU ? P->thrV : nullptr, det_cs, det_part)
     if (drop && elbo) ORI_LAUNCH_PR(true, true);
     else if (drop) ORI_LAUNCH_PR(true, false);
     else if (elbo) ORI_LAUNCH_PR(false, true);
     else ORI_LAUNCH_PR(false, false);
 #undef ORI_LAUNCH_PR
-    return check_launch("k_pass_rows");
+    if (check_launch("k_pass_rows") != ORI_OK) return ORI_ECUDA;
+    return det_sums();
 }
 
 int launch_pass_rows_simt(const ori_problem_t* P, int g, cudaStream_t st) {
@@ -1002,18 +1087,37 @@ static int pass_genes_kp(const ori_problem_t* P, int g, cudaStream_t st) {
     long long rpc = (P->n_rows + chunks - 1) / chunks;
     rpc = (rpc + PG_TR - 1) / PG_TR * PG_TR;
     if (rpc > 8192) rpc = 8192;  // bound the fp32 running sums
+    const bool sparse_ = (P->flags & ORI_F_SPARSE) != 0;
+    // ORI_F_DETERMINISTIC: nominal chunks only (their number bounds the scratch), every chunk stores to its own slot
+    float* det_z = nullptr;
+    const long long det_stride = (long long)(sparse_ ? 3 : 2) * P->p * P->KP;
+    if ((P->flags & ORI_F_DETERMINISTIC) && P->det_ws) {
+        if (!det_simt_ok(P->n_rows, P->p)) return set_error(ORI_EUNSUPPORTED, "ORI_F_DETERMINISTIC on the CUDA-core kernels: problem too large");
+        rpc = 8192;
+        const long long nb = cdiv(P->n_rows, PR_TR);
+        det_z = reinterpret_cast<float*>(P->det_ws + det_simt_offset(P->n_rows, P->p) + nb * P->p + 2 * nb + 2);
+    }
     const int gy = cdiv(P->n_rows, rpc);
     dim3 grid(bx, gy);
     const bool drop = P->flags & ORI_F_DROPOUT, quirk = (P->flags & ORI_F_QUIRK) != 0;
     float* Zj = P->red32;
     float* b2s = P->red32 + (long long)P->p * P->KP;
+    auto det_sums = [&]() -> int {
+        if (!det_z) return ORI_OK;
+        // blocks of the [Zj | b2s | Zl] scratch that this launch did not write (no dropout) are never read: sum what exists
+        const long long total = drop ? det_stride : (long long)P->p * P->KP;
+        k_det_sum_chunks_strided<<<cdiv(total, 256), 256, 0, st>>>(P->red32, det_z, gy, total, det_stride);
+        return check_launch("k_det_sum_chunks");
+    };
     if (P->flags & ORI_F_SPARSE) {
         if constexpr (KP <= 32) {
             k_pass_genes<KP, true, false, true><<<grid, PG_TG, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, (int)rpc,
                 P->eU[g], nullptr, P->U_hat[g], P->U_hat[1 - g], P->eUl[g], P->eVd, P->Vh_old, P->lp, P->pfloor,
                 Zj, b2s, P->red32 + 2ll * P->p * P->KP,
-                (P->thrU && P->thrV) ? P->thrU + (long long)g * P->n_rows : nullptr, P->thrU ? P->thrV : nullptr);
-            return check_launch("k_pass_genes(sparse)");
+                (P->thrU && P->thrV) ? P->thrU + (long long)g * P->n_rows : nullptr, P->thrU ? P->thrV : nullptr,
+                det_z, det_stride);
+            if (check_launch("k_pass_genes(sparse)") != ORI_OK) return ORI_ECUDA;
+            return det_sums();
         } else {
             return set_error(ORI_EUNSUPPORTED, "the sparse model needs K <= 32");
         }
@@ -1023,13 +1127,14 @@ static int pass_genes_kp(const ori_problem_t* P, int g, cudaStream_t st) {
                                                    P->eUw, P->U_hat[g], P->U_hat[1 - g], nullptr, P->eV, P->V_hat, \
                                                    P->lp, P->pfloor, Zj, b2s, nullptr, \
                                                    (P->thrU && P->thrV) ? P->thrU + (long long)g * P->n_rows : nullptr, \
-                                                  P->thrU ? P->thrV : nullptr)
+                                                   P->thrU ? P->thrV : nullptr, det_z, det_stride)
     if (drop && quirk) ORI_LAUNCH_PG(true, true);
     else if (drop) ORI_LAUNCH_PG(true, false);
     else if (quirk) ORI_LAUNCH_PG(false, true);
     else ORI_LAUNCH_PG(false, false);
 #undef ORI_LAUNCH_PG
-    return check_launch("k_pass_genes");
+    if (check_launch("k_pass_genes") != ORI_OK) return ORI_ECUDA;
+    return det_sums();
 }
 
 int launch_pass_genes_simt(const ori_problem_t* P, int g, cudaStream_t st) {
@@ -1053,7 +1158,7 @@ __global__ void k_det_sum_blocks(const double* __restrict__ blk_part, int nblock
     for (int b = 0; b < nblocks; ++b) s += blk_part[(long long)b * DET_FU_SLOTS + t];
     if (t < 64) { if (Slog && t < K) Slog[t] += s; }
     else if (t < 128) { if (Slog && t - 64 < K) Shat[t - 64] += s; }
-    else if (t == 128) { if (Slog) *Hsum += s; }
+    else if (t == 128) { if (Slog && Hsum) *Hsum += s; }
     else if (PUVsum) *PUVsum += s;
 }
 
@@ -1100,9 +1205,13 @@ int launch_gene_update(const ori_problem_t* P, int write_state, cudaStream_t st)
     const int grid = update_grid((long long)p * KP);
     if (P->flags & ORI_F_SPARSE) {
         const int gs = cdiv(p, 128);
-        if (write_state == 2) k_sparse_gene_update<true><<<gs, 128, 0, st>>>(*P);
-        else k_sparse_gene_update<false><<<gs, 128, 0, st>>>(*P);
-        return check_launch("k_sparse_gene_update");
+        const bool sdet = (P->flags & ORI_F_DETERMINISTIC) && P->det_ws;
+        if (sdet && gs > DET_FU_BLOCKS) return set_error(ORI_EUNSUPPORTED, "ORI_F_DETERMINISTIC: too many genes for the sparse update");
+        double* bp = sdet ? P->det_ws : nullptr;
+        if (write_state == 2) k_sparse_gene_update<true><<<gs, 128, 0, st>>>(*P, bp);
+        else k_sparse_gene_update<false><<<gs, 128, 0, st>>>(*P, bp);
+        if (sdet) k_det_sum_blocks<<<1, 256, 0, st>>>(P->det_ws, gs, K, SlogV, SV, nullptr, nullptr);
+        return check_launch("k_sparse_gene_update", sdet ? 2 : 1);
     }
     if (write_state == 2) {
         k_factor_update<true><<<grid, 256, 0, st>>>(p, K, KP, nullptr, nullptr, nullptr, nullptr,

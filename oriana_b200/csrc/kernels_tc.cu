@@ -1208,7 +1208,7 @@ __global__ void k_tc_prep_dev(const float* __restrict__ lp, const double* __rest
 
 // ORI_F_DETERMINISTIC: the per-(item, CTA, warp) ELBO terms of the gene pass, added in index order by one block
 __global__ void __launch_bounds__(1024)
-k_det_sum_items(const double* __restrict__ item_part, long long n_slots, double* __restrict__ part64)
+k_det_sum_items(const double* __restrict__ item_part, long long n_slots, double* __restrict__ dst0, double* __restrict__ dst1)
 {
     __shared__ double s0[1024], s1[1024];
     double a = 0.0, b = 0.0;
@@ -1222,7 +1222,7 @@ k_det_sum_items(const double* __restrict__ item_part, long long n_slots, double*
         if (threadIdx.x < w) { s0[threadIdx.x] += s0[threadIdx.x + w]; s1[threadIdx.x] += s1[threadIdx.x + w]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { part64[R64_XLOGDEN] += s0[0]; part64[R64_ENT] += s1[0]; }
+    if (threadIdx.x == 0) { *dst0 += s0[0]; *dst1 += s1[0]; }
 }
 
 __global__ void k_det_add(double* __restrict__ dst, const double* __restrict__ src, int n)
@@ -1249,10 +1249,22 @@ long long det_max_items(long long n_rows, int p) {
     long long m = a > b ? a : b;
     return m > 2 * 148 ? m : 2 * 148;
 }
+long long det_simt_offset(long long n_rows, int p) {
+    const long long tiles = (pad128(n_rows) + pad128(p)) / 128 + 64;
+    return (long long)DET_FU_BLOCKS * DET_FU_SLOTS + pad128(p) + det_max_items(n_rows, p) * DET_ITEM_SLOTS + (tiles + 1) / 2 + 2;
+}
 long long det_workspace_doubles(long long n_rows, int p, int KP) {
     (void)KP;
-    const long long tiles = (pad128(n_rows) + pad128(p)) / 128 + 64;
-    return (long long)DET_FU_BLOCKS * DET_FU_SLOTS + pad128(p) + det_max_items(n_rows, p) * DET_ITEM_SLOTS + (tiles + 1) / 2;
+    long long simt = 0;
+    if (det_simt_ok(n_rows, p)) {
+        const long long nb = (n_rows + 127) / 128, chunks = (n_rows + 8191) / 8192;
+        simt = nb * p + 2 * nb + 2 + (chunks * 3 * p * 64 + 1) / 2 + 8;
+    }
+    return det_simt_offset(n_rows, p) + simt;
+}
+int launch_det_sum_pairs(const double* src, long long n, double* dst0, double* dst1, cudaStream_t st) {
+    k_det_sum_items<<<1, 1024, 0, st>>>(src, n, dst0, dst1);
+    return check_launch("k_det_sum_items");
 }
 
 long long tc_workspace_floats(long long n_rows, int p, int KP) {
@@ -1497,7 +1509,8 @@ static int launch_tc_pass_p(const ori_problem_t* P, int gen_old, cudaStream_t st
     int extra = 0;
     if (det && GENES && drop) { k_det_add<<<cdiv(P->p, 256), 256, 0, st>>>(P->red64, a.colsum2, P->p); ++extra; }
     if (a.item_part) {
-        k_det_sum_items<<<1, 1024, 0, st>>>(a.item_part, (long long)a.n_items * (DET_ITEM_SLOTS / 2), P->red64 + P->p + 2 * P->KP);
+        double* part = P->red64 + P->p + 2 * P->KP;
+        k_det_sum_items<<<1, 1024, 0, st>>>(a.item_part, (long long)a.n_items * (DET_ITEM_SLOTS / 2), part + R64_XLOGDEN, part + R64_ENT);
         ++extra;
     }
     if (extra) return check_launch("k_tc_pass + deterministic sums", 1 + extra);

@@ -122,12 +122,12 @@ class FactorModel(metaclass=ABCMeta):
         # gap.py:73-76: terms with log_U_hat + log_V_hat <= -103.97 are 0 there; an entry whose terms all are assigns its
         # count to no component).  Off by default, like the quirk: the default keeps the exact ratios.
         self.emulate_underflow = bool(emulate_underflow)
-        # deterministic=True (tensor path, dense models): every floating-point sum is formed in a fixed order (ORI_F_DETERMINISTIC):
-        # two runs from the same state on the same device agree bit for bit
+        # deterministic=True: every floating-point sum is formed in a fixed order (ORI_F_DETERMINISTIC): two runs from the same
+        # state on the same device agree bit for bit
         self.deterministic = bool(deterministic)
         if self.deterministic:
-            if self._sparse or not self._tensor:
-                raise ValueError('deterministic=True needs the tensor path (tensor=True or >= 2^21 entries) and a dense model')
+            if not self._tensor and self.n * self.p > (1 << 26):
+                raise ValueError('deterministic=True on the CUDA-core kernels is limited to 2^26 matrix entries')
             if self.emulate_underflow:
                 raise ValueError('deterministic=True and emulate_underflow=True cannot be combined')
             self._flags |= _lib.ORI_F_DETERMINISTIC

@@ -323,11 +323,49 @@ def test_deterministic_mode_repeats_bit_for_bit(cuda_lib, model, shape, kw):
     np.testing.assert_allclose(ptr, runs[0][1], rtol=1e-5)
 
 
-def test_deterministic_mode_needs_the_tensor_path(cuda_lib):
-    from oriana.models import SparseZIGaP, ZIGaP
+@pytest.mark.parametrize('case', ['cuda_core_zigap', 'cuda_core_gap_chunks', 'sparse_cuda_core', 'sparse_tensor'])
+def test_deterministic_mode_on_the_other_kernel_families(cuda_lib, case):
+    """The same switch on the CUDA-core kernels (one CTA per row block, per-CTA / per-row-chunk slots summed in order) and
+    on the sparse model (its gene update sums by a fixed shuffle tree): bit-identical repeats."""
+    from oracle import cavi_numpy as cn, sparse_numpy as sn
+    from oriana.models import GaP, SparseZIGaP, ZIGaP
     from oriana.singlecell import CountMatrix
-    X = np.ones((64, 32))
+    if case == 'cuda_core_zigap':
+        n, p, K, cls, kw = 700, 450, 6, ZIGaP, dict(tensor=False)
+    elif case == 'cuda_core_gap_chunks':
+        n, p, K, cls, kw = 20000, 60, 9, GaP, dict(tensor=False)          # three row chunks in the gene pass
+    elif case == 'sparse_cuda_core':
+        n, p, K, cls, kw = 500, 300, 5, SparseZIGaP, dict(tensor=False)
+    else:
+        n, p, K, cls, kw = 4000, 1700, 12, SparseZIGaP, dict(tensor=True)
+    X = cn.synth_counts(n, p, K, seed=n % 89)
+    sparse = cls is SparseZIGaP
+    s = sn.init_state(X, K, np.random.default_rng(2)) if sparse else \
+        cn.init_state(X, K, np.random.default_rng(2), 'gap' if cls is GaP else 'zigap')
+    names = ('a1', 'a2', 'b1', 'b2', 'alpha1', 'alpha2', 'beta1', 'beta2') + (() if cls is GaP else ('pi_d',)) \
+        + (('p_s', 'pi_s') if sparse else ())
+
+    def run(**extra):
+        m = cls(CountMatrix(X), k=K, use_factors=False, state=s, **kw, **extra)
+        assert m.uses_tensor_path == kw['tensor']
+        for _ in range(5):
+            m.step()
+        return {k: getattr(m, k).asarray().copy() for k in names}
+
+    runs = [run(deterministic=True) for _ in range(3)]
+    for got in runs[1:]:
+        for k in names:
+            assert np.array_equal(got[k], runs[0][k]), (case, k, float(np.max(np.abs(got[k] - runs[0][k]))))
+    plain = run()
+    for k in names:
+        # the sparse model's S-step (a sigmoid of a difference of large sums) amplifies the plain kernels' own run-to-run
+        # spread to ~1e-2 after five steps
+        assert relerr(plain[k], runs[0][k]) < (3e-2 if sparse else 1e-4), (case, k)
+
+
+def test_deterministic_mode_size_limit_of_the_cuda_core_kernels(cuda_lib):
+    from oriana.models import ZIGaP
+    from oriana.singlecell import CountMatrix
+    X = np.zeros((70000, 1000), dtype=np.uint8)                                   # 7e7 entries > 2^26
     with pytest.raises(ValueError):
-        ZIGaP(CountMatrix(X), k=2, use_factors=False, deterministic=True)            # CUDA-core kernels at this size
-    with pytest.raises(ValueError):
-        SparseZIGaP(CountMatrix(X), k=2, use_factors=False, tensor=True, deterministic=True)
+        ZIGaP(CountMatrix(X), k=2, use_factors=False, tensor=False, deterministic=True)

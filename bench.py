@@ -264,8 +264,9 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-extra', action='store_true', help='skip the secondary measurements (operator seam, config 5 at 8 GPUs)')
     ap.add_argument('--e2e-steps', type=int, default=0)
-    ap.add_argument('--e2e-x', default='u8esc', choices=['u8esc', 'u16', 'f32'],
-                    help='how the host holds X for the e2e leg: saturating uint8 + escapes (default), uint16, float32')
+    ap.add_argument('--e2e-x', default='auto', choices=['auto', 'sparse', 'u8esc', 'u16', 'f32'],
+                    help='how the host holds X for the e2e leg: bitmap + non-zero bytes (sparse), saturating uint8 + escapes '
+                         '(u8esc), uint16, float32; auto (default) = sparse when that is the smaller of the two lossless byte forms')
     args = ap.parse_args()
     n, p, K = CONFIGS[args.config]
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -410,15 +411,22 @@ def main():
         del model
         # counts are small integers: by default the host keeps them as saturating uint8 + an escape list for the
         # counts >= 255 (lossless, oriana_b200.host_step.CompactCounts): one byte per entry crosses PCIe per step
-        from oriana_b200.host_step import CompactCounts, bind_host_thread_to_gpu
+        from oriana_b200.host_step import CompactCounts, SparseCounts, bind_host_thread_to_gpu
         # pinned host buffers next to this rank's GPU: allocate them from the cores NVML calls local to it
         all_cores = os.sched_getaffinity(0)
         numa_cores = bind_host_thread_to_gpu(local)
-        if args.e2e_x == 'u8esc':
+        e2e_x = args.e2e_x
+        if e2e_x == 'auto':
+            e2e_x = 'sparse' if SparseCounts.smaller_than_bytes(X[:, :p]) else 'u8esc'
+        if e2e_x == 'sparse':
+            Xh = SparseCounts.from_tensor(X[:, :p])
+            xdesc = ('bitmap (1 bit per entry) + %d non-zero bytes (%.3f bytes per entry in all) + %d escapes (counts >= 255)'
+                     % (Xh.nz.numel(), Xh.nbytes / float(rows * p), Xh.row.numel()))
+        elif e2e_x == 'u8esc':
             Xh = CompactCounts.from_tensor(X[:, :p])
             xdesc = 'uint8 + %d escapes (counts >= 255)' % Xh.row.numel()
         else:
-            xdt = torch.uint16 if (args.e2e_x == 'u16' and float(X.max()) < 65536) else torch.float32
+            xdt = torch.uint16 if (e2e_x == 'u16' and float(X.max()) < 65536) else torch.float32
             Xh = torch.empty((rows, p), dtype=xdt, pin_memory=True)
             for r in range(0, rows, 1 << 16):
                 Xh[r:r + (1 << 16)].copy_(X[r:r + (1 << 16), :p].to(xdt))

@@ -282,6 +282,15 @@ int ori_synth_counts_f32(float* X, int64_t ldx, int64_t row0, int64_t n_rows, in
 int ori_widen_counts_f32(const void* src, int elem_bytes, int64_t lds, float* dst, int64_t ldd,
                          int64_t rows, int32_t p, void* stream);
 
+/* Sparse ingest: dst[r, 32 w + l] = bit l of bitmap[r, w] ? (float)nz[rowoff[r] - base + rank of that bit in row r] : 0
+ * (device pointers; bitmap rows of words_per_row >= ceil(p / 32) uint32 words, pad bits zero; nz = the non-zero counts
+ * of the rows in gene order as saturating bytes, 255 = see ori_scatter_counts_f32; rowoff[r] = position of row r's
+ * first byte in the caller's whole stream, base = position of nz[0]).  p / 8 + nnz bytes per cell cross PCIe instead
+ * of p: the sparse form of cmatrix.py:100-104 (as_sparse_matrix) as the streaming format of the host-facing step. */
+int ori_expand_bitmap_counts_f32(const uint32_t* bitmap, int64_t words_per_row, const uint8_t* nz,
+                                 const int64_t* rowoff, int64_t base, float* dst, int64_t ldd, int64_t rows,
+                                 int32_t p, void* stream);
+
 /* Escapes of the saturating uint8 encoding: X[row[e] - row0, col[e]] = val[e] (device pointers; row = global
  * cell index, row0 = first cell of the slab held in X).  Entries outside the slab are ignored. */
 int ori_scatter_counts_f32(float* X, int64_t ldx, int64_t row0, int64_t rows, int32_t p, const int32_t* row,

@@ -77,6 +77,8 @@ _SIGNATURES = {
     'ori_zigap_compute_Z_q_expectations_ctx': ([C.c_void_p] * 8 + [C.c_int64] * 3 + [C.c_int], C.c_int),
     'ori_gap_compute_Z_q_expectations_ctx': ([C.c_void_p] * 6 + [C.c_int64] * 3, C.c_int),
     'ori_widen_counts_f32': ([C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p], C.c_int),
+    'ori_expand_bitmap_counts_f32': ([C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+                                      C.c_int32, C.c_void_p], C.c_int),
     'ori_scatter_counts_f32': ([C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int64, C.c_void_p], C.c_int),
     'ori_synth_counts_f32': ([C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_uint64,

@@ -70,6 +70,20 @@ using namespace tc;
 #ifndef ORI_KO_MATH
 #define ORI_KO_MATH 0      // no element-wise math at all: den / uv go back as they came
 #endif
+#ifndef ORI_TC_SKEW
+#define ORI_TC_SKEW 0      // cycles by which the second column-slice warps start every item late (experiment)
+#endif
+#ifndef ORI_TC_PROF
+#define ORI_TC_PROF 0      // 1: phase timers (clock()) in the element-wise warps and the MMA issuer of CTA 0 / 1, printed at the end
+                           //    of every launch (scripts/gpu_time_models.py quick; never in the product build)
+#endif
+#if ORI_TC_PROF
+#define PF_CLK(v) const uint32_t v = (uint32_t)clock()
+#define PF_ADD(acc, t1, t0) acc += (t1) - (t0)
+#else
+#define PF_CLK(v)
+#define PF_ADD(acc, t1, t0)
+#endif
 #ifndef ORI_TC_BF16X
 #define ORI_TC_BF16X 1     // 1: the two cross terms hi.lo + lo.hi of every 3xTF32 contraction run as ONE bf16 chain over
                            //    [hi | lo] . [lo | hi] (error 2^-9 of a 2^-12 term): 4 instead of 6 MMA chains per tile
@@ -435,11 +449,18 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             constexpr uint32_t idescS16 = make_idesc_bf16(TC_OWN * NCTA, SW);
             (void)idescS16; (void)mma16;
             auto commit = [&](uint64_t* bar) { if (PAIR) tc_commit_pair(bar); else tc_commit(bar); };
+#if ORI_TC_PROF
+            uint32_t pm_pready = 0, pm_tfull = 0, pm_issP = 0, pm_kfull = 0, pm_issS = 0;
+            const uint32_t pm_begin = (uint32_t)clock();
+#endif
             auto issue_P = [&](uint32_t it, bool first, bool last, int li) {
                 const uint32_t s = it % NS, ts = it % TST;
+                PF_CLK(pq0);
                 mbar_wait(&bars[B_PREADY + s], (it / NS) & 1, 20);
+                PF_CLK(pq1); PF_ADD(pm_pready, pq1, pq0);
                 mbar_wait(&bars[B_TFULL + ts], (it / TST) & 1, 24);
                 if (first) mbar_wait(&bars[B_ACC_FREE], (li & 1) ^ 1, 21);
+                PF_CLK(pq2); PF_ADD(pm_tfull, pq2, pq1);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t td = tdesc0 + (uint64_t)((ts * T_STAGE) >> 4);
@@ -475,6 +496,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     if (last) commit(&bars[B_ACC_READY]);
                 }
                 __syncwarp();
+                PF_CLK(pq3); PF_ADD(pm_issP, pq3, pq2);
             };
             // S runs NS - 1 tiles ahead of P: S(it) overwrites the TMEM stage P(it - NS) has read (the tensor pipe executes in
             // issue order), so each loop iteration issues S(it) and then P(it - (NS - 1)); `tp` trails `ti` for the latter
@@ -494,8 +516,10 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             while (ti.valid(a)) {
                 const uint32_t s = it % NS, ks_ = it % KST;
                 const bool first = ti.first(), last = ti.last();
+                PF_CLK(pr0);
                 mbar_wait(&bars[B_KFULL + ks_], (it / KST) & 1, 23);
                 if (first) mbar_wait(&bars[B_A_READY], li & 1, 22);
+                PF_CLK(pr1); PF_ADD(pm_kfull, pr1, pr0);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t kd = kdesc0 + (uint64_t)((ks_ * K_STAGE) >> 4);
@@ -539,12 +563,18 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     commit(&bars[B_KEMPTY + ks_]);
                 }
                 __syncwarp();
+                PF_CLK(pr2); PF_ADD(pm_issS, pr2, pr1);
                 if (it >= (uint32_t)(NS - 1)) trail_P();
                 if (last) ++li;
                 ++it;
                 ti.next(a);
             }
             while (itp < it) trail_P();
+#if ORI_TC_PROF
+            if (blockIdx.x < 2 && lane == 0 && !DEVI)
+                printf("PROF mma genes=%d cta=%d tiles=%u total=%u kfull=%u issS=%u pready=%u tfull=%u issP=%u\n", (int)GENES, (int)blockIdx.x,
+                       it, (uint32_t)clock() - pm_begin, pm_kfull, pm_issS, pm_pready, pm_tfull, pm_issP);
+#endif
         }
     } else {
         // ======================================= element-wise stage + epilogue =================================
@@ -615,6 +645,10 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
         ti.init(a, NCTA, rank);
         uint32_t it = 0;                              // tiles of this CTA so far: TMEM stage it & 1, X stage it % XST
         int li = 0;
+#if ORI_TC_PROF
+        uint32_t pf_wait = 0, pf_ld = 0, pf_math = 0, pf_st = 0, pf_ho = 0, pf_epi = 0;
+        const uint32_t pf_begin = (uint32_t)clock();
+#endif
         if (ti.valid(a)) a_load_store(ti.own0);
         while (ti.valid(a)) {
             const long long own_idx = (long long)ti.own0 + lrow;
@@ -937,7 +971,14 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 for (int t = ti.t_begin; t < t_end; ++t, ++it) {
                     const bool last = (t == t_end - 1);
                     const Tile c = tile_of(it, t);
+                    PF_CLK(pc0);
                     wait_tile(it);
+#if ORI_TC_SKEW
+                    // experiment: the two warps of a sub-partition leave lock-step (slice 1 starts every item late), so that
+                    // one computes while the other sits in its tile-boundary latencies
+                    if (t == ti.t_begin && slice == 1) { const uint32_t s0 = (uint32_t)clock(); while ((uint32_t)clock() - s0 < ORI_TC_SKEW) {} }
+#endif
+                    PF_CLK(pc1); PF_ADD(pf_wait, pc1, pc0);
                     if (last && has_next) a_load_store(next_own0);   // every S of this item has completed: A can be replaced
                     if (!c.slow) ld_group(c, 0, 0);
                     load_x(c, 0, 0);
@@ -949,6 +990,9 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                         if (g + 1 < G) load_x(c, g + 1, b ^ 1);
                         if (!c.slow) {
                             tmem_wait_ld();
+#if ORI_TC_PROF
+                            if (g == 0) { PF_CLK(pc2); PF_ADD(pf_ld, pc2, pc1); PF_ADD(pf_math, 0u, pc2); }
+#endif
                             if (g + 1 < G) ld_group(c, g + 1, b ^ 1);
                             float g_cs = 0.f, g_xl = 0.f, g_ent = 0.f;
                             const float dmin = fast_group(c, g, b, g_cs, g_xl, g_ent);
@@ -959,8 +1003,11 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                         st_group(c, g, b);
                     }
                     if (GENES && ELBO) { kahan_add(xl_s, xl_c, t_xl); if (DROPOUT) kahan_add(ent_s, ent_c, t_ent); }
+                    PF_CLK(pc3); PF_ADD(pf_math, pc3, 0u);
                     tmem_wait_st();
+                    PF_CLK(pc4); PF_ADD(pf_st, pc4, pc3);
                     hand_off(c);
+                    PF_CLK(pc5); PF_ADD(pf_ho, pc5, pc4);
                 }
             } else {
                 // ---- deep plan (one 16-column group per warp and tile, S three tiles ahead): while tile t is computed the
@@ -1027,6 +1074,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 continue;
             }
             double acc_xl = (double)xl_s - (double)xl_c, acc_ent = (double)ent_s - (double)ent_c;
+            PF_CLK(pe0);
             // ---- epilogue of the work item: accumulators -> global (atomics: the sweep of one own tile is split);
             //      slice 0 drains acc1, slice 1 acc2
             mbar_wait(&bars[B_ACC_READY], li & 1, 32);
@@ -1089,7 +1137,13 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             ++li;
             ti.item += ti.stride;
             ti.load(a);
+            PF_CLK(pe1); PF_ADD(pf_epi, pe1, pe0);
         }
+#if ORI_TC_PROF
+        if (blockIdx.x < 2 && lane == 0 && !DEVI)
+            printf("PROF ew genes=%d cta=%d warp=%d tiles=%u total=%u wait=%u ld=%u math=%u st=%u handoff=%u epi=%u\n", (int)GENES,
+                   (int)blockIdx.x, ew, it, (uint32_t)clock() - pf_begin, pf_wait, pf_ld, pf_math, pf_st, pf_ho, pf_epi);
+#endif
     }
     tc_fence_before();
     __syncthreads();

@@ -136,6 +136,81 @@ extern "C" int ori_widen_counts_f32(const void* src, int elem_bytes, int64_t lds
     return check_launch("k_widen_counts");
 }
 
+// ---- bitmap + non-zero bytes -> float32 (sparse count-matrix ingest) ---------------------------------------------
+// Single-cell count matrices are mostly zeros (cmatrix.py:100-104 as_sparse_matrix): a host that keeps, per cell, one
+// bit per gene plus the non-zero counts as saturating bytes in gene order streams p / 8 + nnz bytes per cell per step
+// instead of p.  Bit l of word w of a row = gene 32 w + l; rowoff[r] - base = position of row r's first non-zero byte.
+// One CTA per row: (1) popcount prefix over the row's words, (2) lane l of a warp expands bit l of one word at a time,
+// so every store is one coalesced 128-byte line and the bytes a word needs are consecutive.
+constexpr int XB_WORDS = 1024;       // bitmap words per block of a row (256 threads x 4 words)
+__global__ void __launch_bounds__(256)
+k_expand_bitmap(const uint32_t* __restrict__ bm, long long wpr, const uint8_t* __restrict__ nz,
+                const long long* __restrict__ rowoff, long long base, float* __restrict__ dst, long long ldd,
+                long long rows, int p)
+{
+    __shared__ uint32_t s_word[XB_WORDS];
+    __shared__ uint32_t s_off[XB_WORDS];
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = (p + 31) >> 5;
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+        const uint8_t* src = nz + (rowoff[r] - base);
+        const uint32_t* brow = bm + r * wpr;
+        float* drow = dst + r * ldd;
+        uint32_t carry = 0;
+        for (int w0 = 0; w0 < W; w0 += XB_WORDS) {
+            uint32_t wv[4], pre[4], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int w = w0 + 4 * tid + i;
+                wv[i] = w < W ? brow[w] : 0u;
+                pre[i] = sum;
+                sum += __popc(wv[i]);
+            }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (lane == 31) s_warp[warp] = inc;
+            __syncthreads();
+            uint32_t wbase = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) if (q < warp) wbase += s_warp[q];
+            if (tid == 255) s_total = wbase + inc;
+            const uint32_t excl = carry + wbase + inc - sum;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { s_word[4 * tid + i] = wv[i]; s_off[4 * tid + i] = excl + pre[i]; }
+            __syncthreads();
+            const int nw = min(XB_WORDS, W - w0);
+            for (int j = warp; j < nw; j += 8) {
+                const uint32_t word = s_word[j];
+                const int col = (w0 + j) * 32 + lane;
+                const bool bit = (word >> lane) & 1u;
+                float v = 0.f;
+                if (bit) v = (float)src[s_off[j] + __popc(word & ((1u << lane) - 1u))];
+                if (col < p) drow[col] = v;
+            }
+            carry += s_total;
+            __syncthreads();
+        }
+    }
+}
+
+extern "C" int ori_expand_bitmap_counts_f32(const uint32_t* bitmap, int64_t words_per_row, const uint8_t* nz,
+                                            const int64_t* rowoff, int64_t base, float* dst, int64_t ldd,
+                                            int64_t rows, int32_t p, void* stream)
+{
+    if (!bitmap || !rowoff || !dst || p <= 0 || rows < 0 || ldd < p || words_per_row < (p + 31) / 32)
+        return set_error(ORI_EINVAL, "ori_expand_bitmap_counts_f32: bad argument");
+    if (rows == 0) return ORI_OK;
+    const int grid = (int)(rows < 148 * 64 ? rows : 148 * 64);
+    k_expand_bitmap<<<grid, 256, 0, (cudaStream_t)stream>>>(bitmap, words_per_row, nz, (const long long*)rowoff, base, dst, ldd, rows, p);
+    return check_launch("k_expand_bitmap");
+}
+
 // Escapes of the saturating uint8 encoding: X[row[e] - row0, col[e]] = val[e] for the entries whose count does not
 // fit a byte (stored as 255 in the compact matrix).  row is the GLOBAL cell index, row0 the first cell of the slab.
 __global__ void __launch_bounds__(256)

@@ -358,6 +358,55 @@ def test_host_streamed_step_with_compact_counts(cuda_lib):
             assert np.array_equal(dst.cpu().numpy()[:, :p], a[:, :p].astype(np.float32))
 
 
+def test_host_streamed_step_with_sparse_counts(cuda_lib):
+    """X kept on the host as bitmap + non-zero bytes (SparseCounts; cmatrix.py:100-104's sparse view as a streaming
+    format): the device expansion is exact (ragged widths, rows without a non-zero, rows longer than one block of bitmap
+    words, counts >= 255 through the escape list) and the host-streamed step gives the float32-host results for fewer bytes."""
+    import ctypes
+    import torch
+    from oriana_b200.host_step import HostStreamedCAVI, SparseCounts
+    rng = np.random.default_rng(5)
+    st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for rows, p, keep in ((7, 13, 0.5), (33, 130, 0.3), (5, 64, 1.0), (3, 1, 0.5), (4, 40000, 0.2), (300, 977, 0.05)):
+        X = (rng.poisson(9., size=(rows, p)) * (rng.random((rows, p)) < keep)).astype(np.float32)
+        X[rows // 2] = 0                                           # a cell without a single count
+        X[0, p - 1] = 255; X[rows - 1, 0] = 70000
+        sp = SparseCounts.from_tensor(torch.as_tensor(X), chunk_rows=5, pin=False)
+        assert np.array_equal(sp.dense().numpy(), X)
+        ldd = (p + 3) // 4 * 4
+        dst = torch.full((rows, ldd), -1., dtype=torch.float32, device='cuda')
+        bm, nz, off = sp.bitmap.cuda(), sp.nz.cuda(), sp.rowoff.cuda()
+        # a slab in the middle of the stream: rows [r0, rows), base = position of its first byte
+        for r0 in (0, rows // 3):
+            lo, hi = sp.byte_range(r0, rows)
+            rc = cuda_lib.ori_expand_bitmap_counts_f32(bm[r0:].data_ptr(), bm.shape[1], nz[lo:].data_ptr() if hi > lo else nz.data_ptr(),
+                                                       off[r0:].data_ptr(), lo, dst[r0:].data_ptr(), ldd, rows - r0, p, st())
+            assert rc == 0
+            a, b, c = sp.escapes(r0, rows), None, None
+            cnt = a[1] - a[0]
+            if cnt:
+                er, ec, ev = sp.row[a[0]:a[1]].cuda(), sp.col[a[0]:a[1]].cuda(), sp.val[a[0]:a[1]].cuda()
+                assert cuda_lib.ori_scatter_counts_f32(dst[r0:].data_ptr(), ldd, r0, rows - r0, p, er.data_ptr(), ec.data_ptr(),
+                                                       ev.data_ptr(), cnt, st()) == 0
+            assert np.array_equal(dst.cpu().numpy()[r0:, :p], X[r0:]), (rows, p, r0)
+    g = load_golden('zigap_ragged')
+    s = dict(golden_state(g, 0))
+    X2 = s['X'].copy(); X2[3, 7] = 255; X2[100, 330] = 70000; X2[64] = 0; s['X'] = X2
+    K = s['a1'].shape[1]
+    X2f = torch.as_tensor(X2.astype(np.float32))
+    sp = SparseCounts.from_tensor(X2f, chunk_rows=50)
+    assert sp.row.numel() == 2 and torch.equal(sp.dense(), X2f)
+    ref = HostStreamedCAVI(X2f.pin_memory(), K, s, dropout=True, slab_rows=64)
+    h = HostStreamedCAVI(sp, K, s, dropout=True, slab_rows=64)
+    for _ in range(3):
+        e_ref, e = ref.step(), h.step()
+    for k in PARAMS:
+        assert relerr(h.state_dict()[k], ref.state_dict()[k]) < 5e-6, ('sparse', k)
+    assert abs(e - e_ref) < 1e-6 * abs(e_ref)
+    zeros = float((X2 == 0).mean())
+    assert h.h2d_bytes < ref.h2d_bytes * (0.25 * (0.125 + 1 - zeros) + 0.1)
+
+
 def test_count_matrix_to_device_narrow_upload(cuda_lib):
     """CountMatrix.to_device: uint8 / uint16 / float32 uploads give the same float32 matrix in HBM, with the 16-byte
     row pitch the kernels need (ragged p), uploaded in several slabs."""

@@ -163,6 +163,30 @@ def test_count_matrix_ingest_helpers():
     assert cc.row.numel() == 1
 
 
+def test_sparse_counts_round_trip():
+    """SparseCounts (bitmap + non-zero bytes + escapes, the streaming format of the host-facing step) is lossless: ragged
+    widths, all-zero rows and matrices, chunk boundaries inside the matrix, counts at and beyond the byte range."""
+    import torch
+    from oriana_b200.host_step import SparseCounts
+    rng = np.random.default_rng(0)
+    for n, p in ((7, 33), (50, 100), (33, 64), (5, 1), (64, 2049)):
+        X = (rng.poisson(20, (n, p)) * (rng.random((n, p)) < 0.5)).astype(np.float32)
+        X[rng.integers(0, n), rng.integers(0, p)] = 300.
+        X[0, p - 1] = 255.; X[n - 1, 0] = 1000.; X[n // 2] = 0.
+        sp = SparseCounts.from_tensor(torch.from_numpy(X), chunk_rows=3, pin=False)
+        assert np.array_equal(sp.dense().numpy(), X), (n, p)
+        assert sp.bitmap.shape == (n, (p + 31) // 32) and int(sp.rowoff[-1]) == int((X != 0).sum())
+        lo, hi = sp.byte_range(n // 2, n // 2 + 1)
+        assert lo == hi                                            # the empty row owns no bytes
+        # bit l of word w = gene 32 w + l
+        w = sp.bitmap.numpy().view(np.uint32)
+        j = p - 1
+        assert ((w[0, j // 32] >> np.uint32(j % 32)) & 1) == 1
+    sp = SparseCounts.from_tensor(torch.zeros((4, 40)), pin=False)
+    assert sp.nz.numel() == 0 and not sp.dense().any()
+    assert SparseCounts.smaller_than_bytes(torch.zeros((4, 40))) and not SparseCounts.smaller_than_bytes(torch.ones((4, 40)))
+
+
 def test_reference_driver_imports_resolve():
     """Every `from oriana... import ...` line of the reference's drivers and tests (main.py:5-6,
     experiments/clustering.py:5-6, test/test.py:5-7) resolves against the alias package."""

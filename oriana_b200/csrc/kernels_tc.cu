@@ -70,8 +70,10 @@ using namespace tc;
 #ifndef ORI_KO_MATH
 #define ORI_KO_MATH 0      // no element-wise math at all: den / uv go back as they came
 #endif
-#ifndef ORI_TC_SKEW
-#define ORI_TC_SKEW 0      // cycles by which the second column-slice warps start every item late (experiment)
+#ifndef ORI_TC_SPLIT
+#define ORI_TC_SPLIT 0     // 1 (with ORI_TC_NEW=16): the 16 element-wise warps form two groups of 8; group g takes the tiles of
+                           //    parity g (= TMEM stage g), 32 columns per warp, single register buffer.  While one group waits
+                           //    for its next S (behind its own P), the other group's tile keeps the sub-partition busy.
 #endif
 #ifndef ORI_TC_PROF
 #define ORI_TC_PROF 0      // 1: phase timers (clock()) in the element-wise warps and the MMA issuer of CTA 0 / 1, printed at the end
@@ -104,6 +106,9 @@ constexpr int ASUBS = SLICES / 2;     // warps sharing one own-side array / one 
 constexpr int NISS = ORI_TC_ISSUERS;
 constexpr int ISS2_WARP = 2 + NEW;    // the second issuer sits after the element-wise warps (quarter = warp & 3 stays valid)
 constexpr int TC_THREADS = 64 + 32 * NEW + (NISS == 2 ? 32 : 0);
+constexpr bool SPLIT = ORI_TC_SPLIT != 0;
+static_assert(!SPLIT || NEW == 16, "ORI_TC_SPLIT needs ORI_TC_NEW=16");
+constexpr int NEWT = SPLIT ? NEW / 2 : NEW;   // element-wise warps that work on one tile
 
 // Plan of one kernel variant.  KP: padded latent dimension (32 or 64).  PAIR: the CTA-pair variant (cta_group::2,
 // M = 256 over two SMs): each CTA stages only half of every streamed operand tile (the pair's MMA reads both
@@ -284,8 +289,11 @@ struct TileIter {
 // DET: the ORI_F_DETERMINISTIC epilogue (TcArgs::tickets / item_part), a separate instantiation for the same reason (runtime-
 // switched it cost the plain kernels 2.6 % / 3.4 %).
 template <bool GENES, bool DROPOUT, bool ELBO, bool PAIR, int KP, bool PRECISE, bool DEVI = false, bool UFL = false, bool DET = false>
+#ifndef ORI_TC_MAXNREG
+#define ORI_TC_MAXNREG 96
+#endif
 #if ORI_TC_NEW == 16
-__global__ void __maxnreg__(96)
+__global__ void __maxnreg__(ORI_TC_MAXNREG)
 #else
 __global__ void __launch_bounds__(TC_THREADS, 1)
 #endif
@@ -302,7 +310,7 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
     constexpr int B_KFULL = C::B_KFULL, B_KEMPTY = C::B_KEMPTY, B_TFULL = C::B_TFULL, B_TEMPTY = C::B_TEMPTY,
                   B_XFULL = C::B_XFULL, B_XEMPTY = C::B_XEMPTY, B_SREADY = C::B_SREADY, B_PREADY = C::B_PREADY,
                   B_ACC_READY = C::B_ACC_READY, B_ACC_FREE = C::B_ACC_FREE, B_A_READY = C::B_A_READY, NBARS = C::NBARS;
-    constexpr int CW = SW / SLICES;           // tile columns per element-wise warp: 32 or 16
+    constexpr int CW = SW / (SPLIT ? SLICES / 2 : SLICES);   // tile columns per element-wise warp: 32 or 16
     constexpr int G = CW / 16;                // groups of 16 columns per tile for one warp
     constexpr int NQ = DROPOUT ? 4 : 2;       // K-major operand arrays in use
     constexpr int NT = DROPOUT ? 2 : 1;       // transposed operand arrays in use
@@ -318,8 +326,8 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
         constexpr int NI = (NISS == 2 && DROPOUT) ? 2 : 1;      // issuers at work: each commits once per stage
         for (int s = 0; s < KST; ++s) { mbar_init(&bars[B_KFULL + s], 1); mbar_init(&bars[B_KEMPTY + s], NI); }
         for (int s = 0; s < TST; ++s) { mbar_init(&bars[B_TFULL + s], 1); mbar_init(&bars[B_TEMPTY + s], NI); }
-        for (int s = 0; s < XST; ++s) { mbar_init(&bars[B_XFULL + s], 1); mbar_init(&bars[B_XEMPTY + s], NEW); }
-        for (int s = 0; s < NS; ++s) { mbar_init(&bars[B_SREADY + s], NI); mbar_init(&bars[B_PREADY + s], NEW * NCTA); }
+        for (int s = 0; s < XST; ++s) { mbar_init(&bars[B_XFULL + s], 1); mbar_init(&bars[B_XEMPTY + s], NEWT); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&bars[B_SREADY + s], NI); mbar_init(&bars[B_PREADY + s], NEWT * NCTA); }
         mbar_init(&bars[B_ACC_READY], NI);
         mbar_init(&bars[B_ACC_FREE], NEW * NCTA);
         mbar_init(&bars[B_A_READY], NEW * NCTA);
@@ -582,7 +590,8 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
         const int slice = ew >> 2;                    // which half of the tile's columns / of the own-side arrays
         const int lrow = quarter * 32 + lane;         // own index inside the tile = TMEM lane
-        const int colbase = slice * CW;
+        const int colbase = (SPLIT ? (slice & 1) : slice) * CW;
+        const int group = slice >> 1;                 // SPLIT: parity of the tiles this warp works on
         const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
         const uint32_t sbase = smem_u32(smem);
         const bool any_floor = DROPOUT && (*a.any_floor != 0);
@@ -880,6 +889,13 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
             };
             long long dv0 = 0, dv1 = 0, dv2 = 0;      // deviance pass: truncated log-likelihood sums of this thread and item
             if constexpr (DEVI) {
+                // components of this cell's U_hat that are not exactly zero (bit k & 31): see k_tc_prep_dev
+                uint32_t mU = 0;
+                if (own_ok) {
+                    const float* uh = a.own_E + own_idx * KP;
+#pragma unroll 8
+                    for (int k = 0; k < KP; ++k) if (__ldg(uh + k) != 0.f) mU |= 1u << (k & 31);
+                }
                 // ---- deviance pass (base.py:58-82, sparse_zigap.py:44-51): "den" = the rate L = U_hat . V_hat^T, "uv" = the
                 //      contraction that generates D_hat (log2 units).  Per entry, like k_deviance's integer mode:
                 //        zero, round(D_hat) = 0 (uv >= logit pi):  l_uv = 0
@@ -937,6 +953,17 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                                 const float4 ga = lds128(ca), gb = lds128(ca + 16);
                                 const float xe = xs_[e], uvp = us_[e];
                                 const bool nz = xe != 0.f, kept = uvp < ga.x;
+                                // every product U_hat_ik V_hat_jk is exactly zero (a masked gene of the sparse model, mostly): the
+                                // float64 rate is 0 and the term of the observed count -inf, which the reference's int64 buffer
+                                // holds as INT64_MIN (trunc64 below gives the same); the other two sums as on the fast path
+                                if (nz && (mU & __float_as_uint(gb.w)) == 0u) {
+                                    const float g1 = fmaf(xe, lg2_approx(xe) * LN2, ga.w - xe), g2 = fmaf(xe, gb.y, ga.w - gb.x);
+                                    if (fmaxf(fabsf(g1), fabsf(g2)) < 8e6f) {
+                                        dv0 = (long long)((unsigned long long)dv0 + 0x8000000000000000ull);
+                                        dv1 += (int)g1; dv2 += (int)g2;
+                                        continue;
+                                    }
+                                }
                                 double Ld = 0.0;
                                 const float* uh = a.own_E + own_idx * KP;
                                 for (int k = 0; k < KP; ++k) {
@@ -970,14 +997,19 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                 //      the tile is handed to the MMA warp as soon as its last group is stored
                 for (int t = ti.t_begin; t < t_end; ++t, ++it) {
                     const bool last = (t == t_end - 1);
+                    if (SPLIT && (int)(it & 1) != group) {
+                        // the other group's tile.  The item's last tile still carries this warp's share of the next item's
+                        // own-side operands: wait until its S (hence every S of the item) has completed
+                        if (last && has_next) {
+                            mbar_wait(&bars[B_SREADY + it % NS], (it / NS) & 1, 33);
+                            tc_fence_after();
+                            a_load_store(next_own0);
+                        }
+                        continue;
+                    }
                     const Tile c = tile_of(it, t);
                     PF_CLK(pc0);
                     wait_tile(it);
-#if ORI_TC_SKEW
-                    // experiment: the two warps of a sub-partition leave lock-step (slice 1 starts every item late), so that
-                    // one computes while the other sits in its tile-boundary latencies
-                    if (t == ti.t_begin && slice == 1) { const uint32_t s0 = (uint32_t)clock(); while ((uint32_t)clock() - s0 < ORI_TC_SKEW) {} }
-#endif
                     PF_CLK(pc1); PF_ADD(pf_wait, pc1, pc0);
                     if (last && has_next) a_load_store(next_own0);   // every S of this item has completed: A can be replaced
                     if (!c.slow) ld_group(c, 0, 0);
@@ -985,15 +1017,16 @@ k_tc_pass(const __grid_constant__ TcMaps maps, const TcArgs a)
                     float t_xl = 0.f, t_ent = 0.f;
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
-                        const int b = g & 1;
+                        const int b = SPLIT ? 0 : (g & 1);       // SPLIT: one register buffer, no prefetch inside the tile
                         bool redo = c.slow;
-                        if (g + 1 < G) load_x(c, g + 1, b ^ 1);
+                        if (!SPLIT && g + 1 < G) load_x(c, g + 1, b ^ 1);
+                        if (SPLIT && g > 0) { if (!c.slow) ld_group(c, g, 0); load_x(c, g, 0); }
                         if (!c.slow) {
                             tmem_wait_ld();
 #if ORI_TC_PROF
                             if (g == 0) { PF_CLK(pc2); PF_ADD(pf_ld, pc2, pc1); PF_ADD(pf_math, 0u, pc2); }
 #endif
-                            if (g + 1 < G) ld_group(c, g + 1, b ^ 1);
+                            if (!SPLIT && g + 1 < G) ld_group(c, g + 1, b ^ 1);
                             float g_cs = 0.f, g_xl = 0.f, g_ent = 0.f;
                             const float dmin = fast_group(c, g, b, g_cs, g_xl, g_ent);
                             redo = __any_sync(0xffffffffu, dmin <= den_lim) != 0;
@@ -1241,10 +1274,15 @@ __global__ void k_tc_thr_max(const float* __restrict__ thr, long long n, int* __
 }
 
 // deviance pass: 8 constants per gene, tile-major [tile][SW][8]:
-//   logit(pi_gen) * log2(e) | pi | 1 - pi | log pi | mean | log mean | trunc(log(pi e^-mean + 1 - pi)) | 0
-// pi = the finalised Bernoulli prior, pi_gen (through lp) the one that generated D_hat, mean = column mean of X
+//   logit(pi_gen) * log2(e) | pi | 1 - pi | log pi | mean | log mean | trunc(log(pi e^-mean + 1 - pi)) | mask
+// pi = the finalised Bernoulli prior, pi_gen (through lp) the one that generated D_hat, mean = column mean of X;
+// mask (bit pattern in a float slot): bit k & 31 set when component k of the gene's effective V_hat = b1 / b2 (* S_hat) is
+// not exactly zero in float64 -- with the matching mask of the cell's U_hat an empty intersection means the rate is
+// EXACTLY zero (masked genes of the sparse model, sparse_zigap.py:103), which the element-wise warps then know without
+// the float64 redo
 __global__ void k_tc_prep_dev(const float* __restrict__ lp, const double* __restrict__ pi, const double* __restrict__ cmean,
-                              float* __restrict__ out, int p, int pad)
+                              float* __restrict__ out, int p, int pad, const float* __restrict__ b1,
+                              const float* __restrict__ b2, const float* __restrict__ ps, int KP)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= pad) return;
@@ -1255,6 +1293,12 @@ __global__ void k_tc_prep_dev(const float* __restrict__ lp, const double* __rest
         b.x = (float)mj; b.y = (float)log(mj);
         const float lm = logf(fmaf((float)pj, (float)exp(-mj), (float)(1.0 - pj)));     // as k_deviance's integer mode
         b.z = (float)(int)lm;
+        uint32_t mask = 0;
+        for (int k = 0; k < KP; ++k) {
+            const long long gk = (long long)j * KP + k;
+            if (b2[gk] != 0.f && b1[gk] != 0.f && (!ps || ps[gk] != 0.f)) mask |= 1u << (k & 31);
+        }
+        b.w = __uint_as_float(mask);
     }
     reinterpret_cast<float4*>(out)[2 * (long long)j] = a;
     reinterpret_cast<float4*>(out)[2 * (long long)j + 1] = b;
@@ -1536,7 +1580,7 @@ static int launch_tc_pass_p(const ori_problem_t* P, int gen_old, cudaStream_t st
     int rc;
     if (det) {
         if (ufl) return set_error(ORI_EUNSUPPORTED, "ORI_F_DETERMINISTIC and the underflow thresholds cannot be combined on the tensor path");
-        if constexpr (PAIR) {
+        if constexpr (PAIR && NEW == 8) {
             if (drop && elbo) rc = launch_tc_variant<GENES, true, true, PAIR, KP, PRECISE, false, true>(maps, a, grid, st);
             else if (drop) rc = launch_tc_variant<GENES, true, false, PAIR, KP, PRECISE, false, true>(maps, a, grid, st);
             else if (elbo) rc = launch_tc_variant<GENES, false, true, PAIR, KP, PRECISE, false, true>(maps, a, grid, st);
@@ -1601,7 +1645,7 @@ static int launch_deviance_tc_kp(const ori_problem_t* P, int g, const double* pi
     // gene-side K-major operands: [hi | lo] of the effective V_hat (rate) and of the V_hat that generates D_hat (log2 units)
     k_tc_prep_K<<<cdiv(w.pp * KP, 256), 256, 0, st>>>(P->V_hat, sparse ? P->Vh_old : P->V_hat, LOG2E, w.geneK, P->p, w.pp, KP);
     float* devlp = w.geneT;                 // the transposed-operand area is free here (no accumulating contraction)
-    k_tc_prep_dev<<<cdiv(w.pp, 256), 256, 0, st>>>(P->lp, pi, cmean, devlp, P->p, (int)w.pp);
+    k_tc_prep_dev<<<cdiv(w.pp, 256), 256, 0, st>>>(P->lp, pi, cmean, devlp, P->p, (int)w.pp, P->b1, P->b2, sparse ? P->p_s : nullptr, KP);
     {
         const cudaError_t e_ = cudaMemsetAsync(w.flags, 0, 32 * sizeof(int), st);
         if (e_ != cudaSuccess) return set_error(ORI_ECUDA, "cudaMemsetAsync(tc flags): %s", cudaGetErrorString(e_));

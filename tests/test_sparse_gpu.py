@@ -158,3 +158,38 @@ def test_sparse_tensor_paths_track_the_cuda_core_path(cuda_lib):
     assert np.median(np.abs(b1t - b1s)[same] / (np.abs(b1s)[same] + 1e-12)) < 1e-3
     ds, dt = ms.reconstruction_deviance(int_quirk=False), mt.reconstruction_deviance(int_quirk=False)
     assert abs(dt - ds) <= 5e-3 * abs(ds) or not np.isfinite(ds)
+
+
+def test_deviance_counts_exactly_zero_rates_like_the_cuda_core_kernel(cuda_lib):
+    """Genes whose every component is masked out (S_hat = 0) have an EXACTLY zero rate: an observed count there is log 0
+    = -inf, INT64_MIN in the reference's integer buffer (sparse_zigap.py:45).  The tensor deviance pass recognises them
+    from the zero patterns of U_hat and V_hat (no float64 redo) and must wrap its first sum exactly like the CUDA-core
+    kernel: an odd number of such entries leaves the sign bit set, the rest of the sum agrees."""
+    from oriana.models import SparseZIGaP
+    from oriana.singlecell import synth_counts_device
+    n, p, K = 20_000, 3_000, 8
+    X = synth_counts_device(n, p, K, seed=11)
+    np.random.seed(5)
+    m0 = SparseZIGaP(X[:, :p], k=K, use_factors=False, tensor=False)
+    m0.step()
+    st = m0.state_dict()
+    masked = np.array([3, 64, 65, 1500, 2999])
+    st['p_s'][masked] = 0.                               # S_hat = 0 on every component of these genes
+    st['X'] = X[:, :p]
+    ms = SparseZIGaP(X[:, :p], k=K, use_factors=False, state=st, tensor=False)
+    mt = SparseZIGaP(X[:, :p], k=K, use_factors=False, state=st)
+    assert mt.uses_tensor_path and not ms.uses_tensor_path
+    li_s, li_t = ms._loglikelihood_sums(want_f64=False)[0], mt._loglikelihood_sums(want_f64=False)[0]
+    n_inf = int((X[:, :p][:, torch_idx(masked)] != 0).sum())
+    assert n_inf > 0
+    top = lambda v: (int(v) >> 63) & 1                   # sign bit = parity of the INT64_MIN terms (plus the ordinary sum's sign)
+    rest = lambda v: int(v) & ((1 << 63) - 1)
+    assert top(li_s[0]) == top(li_t[0])
+    assert abs(rest(li_s[0]) - rest(li_t[0])) <= 1e-4 * abs(int(li_s[1]))
+    assert abs(int(li_s[1]) - int(li_t[1])) <= 1e-4 * abs(int(li_s[1]))
+    assert abs(int(li_s[2]) - int(li_t[2])) <= 1e-4 * abs(int(li_s[2]))
+
+
+def torch_idx(a):
+    import torch
+    return torch.as_tensor(a, device='cuda')

@@ -42,7 +42,7 @@ extern "C" {
 #define ORI_F_ELBO 4u         /* accumulate the ELBO terms inside the row pass                            */
 #define ORI_F_NO_TENSOR 8u    /* force the CUDA-core kernels (tests); default picks tcgen05 when it can   */
 #define ORI_F_SPARSE 16u      /* SparseZIGaP: spike-and-slab layer S on V (sparse_zigap.py:100-204); needs
-                                 ORI_F_DROPOUT, the `sparse` block below, K <= 32; CUDA-core kernels, no ELBO */
+                                 ORI_F_DROPOUT, the `sparse` block below, K <= 64 (tensor kernels: K <= 32), no ELBO */
 #define ORI_F_DEVICE_ITER 32u /* the iteration count (index into elbo_trace) is read from scal[5] on the device
                                  instead of ori_problem_t::iter, so that one captured CUDA graph of a whole
                                  step can be replayed for every iteration                                   */

@@ -173,7 +173,6 @@ int ori_problem_check(const ori_problem_t* P) {
     if (P->flags & ORI_F_SPARSE) {
         if (!(P->flags & ORI_F_DROPOUT) || (P->flags & (ORI_F_QUIRK | ORI_F_ELBO)))
             return set_error(ORI_EINVAL, "ORI_F_SPARSE needs ORI_F_DROPOUT and excludes ORI_F_QUIRK / ORI_F_ELBO");
-        if (P->KP > 32) return set_error(ORI_EUNSUPPORTED, "the sparse model needs K <= 32 (got %d)", P->K);
         if (!P->p_s || !P->logV || !P->eVd || !P->eVz || !P->Vh_old || !P->eUl[0] || !P->eUl[1] || !P->pi_s)
             return set_error(ORI_EINVAL, "sparse buffers missing");
         if (((uintptr_t)P->eVd & 15) || ((uintptr_t)P->eVz & 15) || ((uintptr_t)P->Vh_old & 15))

@@ -45,7 +45,8 @@ constexpr int PR_TG = 32;
 // SPARSE (sparse_zigap.py:100-116, :140-142, :166): the denominator operand eV carries the mask S_tilde, the row
 // sums contract with eVz = eV * S_hat, D_hat is rebuilt from Vh = the PREVIOUS effective V_hat and the rate sums
 // contract with Vc = the current one.  Otherwise eVz == eV and Vc == Vh (not read).
-template <int KP, bool DROPOUT, bool ELBO, bool SPARSE>
+// TG: genes per tile (32; 16 for the sparse model at KP = 64, whose four gene-side operand tiles would not fit 48 KB)
+template <int KP, bool DROPOUT, bool ELBO, bool SPARSE, int TG = PR_TG>
 __global__ void __launch_bounds__(PR_TR)
 k_pass_rows(const float* __restrict__ X, long long ldx, long long n_rows, int p,
             const float* __restrict__ eU, const float* __restrict__ Uh,
@@ -59,14 +60,14 @@ k_pass_rows(const float* __restrict__ X, long long ldx, long long n_rows, int p,
 {
     // det_cs / det_part (ORI_F_DETERMINISTIC, launched with gridDim.y == 1): this CTA's column sums and ELBO terms go to
     // its own slots [blockIdx.x][p] / [blockIdx.x][2] instead of atomic targets; launch_det_sum_* add them in index order
-    __shared__ float sX[PR_TR][PR_TG + 1];
-    __shared__ float sthr[PR_TG];
-    __shared__ __align__(16) float sV[PR_TG][KP];
-    __shared__ __align__(16) float sVh[DROPOUT ? PR_TG : 1][KP];
-    __shared__ __align__(16) float sVz[SPARSE ? PR_TG : 1][KP];
-    __shared__ __align__(16) float sVc[SPARSE ? PR_TG : 1][KP];
-    __shared__ float slp[PR_TG], sfl[PR_TG];
-    __shared__ float scs[PR_TR / 32][PR_TG];
+    __shared__ float sX[PR_TR][TG + 1];
+    __shared__ float sthr[TG];
+    __shared__ __align__(16) float sV[TG][KP];
+    __shared__ __align__(16) float sVh[DROPOUT ? TG : 1][KP];
+    __shared__ __align__(16) float sVz[SPARSE ? TG : 1][KP];
+    __shared__ __align__(16) float sVc[SPARSE ? TG : 1][KP];
+    __shared__ float slp[TG], sfl[TG];
+    __shared__ float scs[PR_TR / 32][TG];
     __shared__ double sred[PR_TR / 32];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -84,23 +85,23 @@ k_pass_rows(const float* __restrict__ X, long long ldx, long long n_rows, int p,
     double acc_xl = 0.0, acc_ent = 0.0;
     const float tu = (thrU && row_ok) ? thrU[row] : 0.f;         // underflow emulation (special.cuh); 0: never triggers
 
-    const int ntiles = (p + PR_TG - 1) / PR_TG;
+    const int ntiles = (p + TG - 1) / TG;
     for (int t = blockIdx.y; t < ntiles; t += gridDim.y) {
-        const int j0 = t * PR_TG;
-        const int gcount = min(PR_TG, p - j0);
+        const int j0 = t * TG;
+        const int gcount = min(TG, p - j0);
         __syncthreads();  // previous tile fully consumed
         // X tile: warp w loads rows w, w+4, ...; a row segment is 32 consecutive floats
         for (int rr = warp; rr < PR_TR; rr += PR_TR / 32) {
             const long long r = row0 + rr;
             float v = 0.f;
             if (r < n_rows && lane < gcount) v = __ldg(X + r * ldx + j0 + lane);
-            sX[rr][lane] = v;
+            if (lane < TG) sX[rr][lane] = v;
         }
         float* sVf = &sV[0][0];
         float* sVhf = &sVh[0][0];
         float* sVzf = &sVz[0][0];
         float* sVcf = &sVc[0][0];
-        for (int idx = tid; idx < PR_TG * KP; idx += PR_TR) {
+        for (int idx = tid; idx < TG * KP; idx += PR_TR) {
             const int g = idx / KP;
             const bool ok = g < gcount;
             sVf[idx] = ok ? eV[(long long)j0 * KP + idx] : 0.f;
@@ -110,11 +111,11 @@ k_pass_rows(const float* __restrict__ X, long long ldx, long long n_rows, int p,
                 sVcf[idx] = ok ? Vc[(long long)j0 * KP + idx] : 0.f;
             }
         }
-        if (DROPOUT && tid < PR_TG) {
+        if (DROPOUT && tid < TG) {
             slp[tid] = tid < gcount ? lp[j0 + tid] : 0.f;
             sfl[tid] = tid < gcount ? pfloor[j0 + tid] : 0.f;
         }
-        if (tid < PR_TG) sthr[tid] = (thrV && tid < gcount) ? thrV[j0 + tid] : 0.f;
+        if (tid < TG) sthr[tid] = (thrV && tid < gcount) ? thrV[j0 + tid] : 0.f;
         __syncthreads();
 
         float t_xl = 0.f, t_ent = 0.f;
@@ -183,7 +184,7 @@ k_pass_rows(const float* __restrict__ X, long long ldx, long long n_rows, int p,
 #pragma unroll 8
                 for (int rr = 0; rr < 32; ++rr) cs += sX[warp * 32 + rr][lane];
             }
-            scs[warp][lane] = cs;
+            if (lane < TG) scs[warp][lane] = cs;
             __syncthreads();
             if (tid < gcount) {
                 float tot = 0.f;
@@ -1021,7 +1022,8 @@ k_deviance(const float* __restrict__ X, long long ldx, long long n_rows, int p,
 template <int KP>
 static int pass_rows_kp(const ori_problem_t* P, int g, cudaStream_t st) {
     const int bx = cdiv(P->n_rows, PR_TR);
-    const int ntiles = cdiv(P->p, PR_TG);
+    constexpr int TGS = KP <= 32 ? PR_TG : 16;         // tile width of the sparse variant
+    const int ntiles = cdiv(P->p, (P->flags & ORI_F_SPARSE) ? TGS : PR_TG);
     int gy = 1;  // split the gene sweep until there are several waves of CTAs (3 resident per SM): a 1.8-wave grid idles
     while (bx * gy < 148 * 3 * 6 && gy * 2 <= ntiles) gy *= 2;   // most of the machine during its last wave
     const bool drop = P->flags & ORI_F_DROPOUT, elbo = P->flags & ORI_F_ELBO;
@@ -1044,16 +1046,12 @@ static int pass_rows_kp(const ori_problem_t* P, int g, cudaStream_t st) {
     };
     dim3 grid(bx, gy);
     if (P->flags & ORI_F_SPARSE) {
-        if constexpr (KP <= 32) {
-            k_pass_rows<KP, true, false, true><<<grid, PR_TR, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, P->eU[g],
-                P->U_hat[g], P->eVd, P->Vh_old, P->eVz, P->V_hat, P->lp, P->pfloor, P->Zi, P->a2s, colsum, part,
-                (P->thrU && P->thrV) ? P->thrU + (long long)g * P->n_rows : nullptr, P->thrU ? P->thrV : nullptr,
-                det_cs, det_part);
-            if (check_launch("k_pass_rows(sparse)") != ORI_OK) return ORI_ECUDA;
-            return det_sums();
-        } else {
-            return set_error(ORI_EUNSUPPORTED, "the sparse model needs K <= 32");
-        }
+        k_pass_rows<KP, true, false, true, TGS><<<grid, PR_TR, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, P->eU[g],
+            P->U_hat[g], P->eVd, P->Vh_old, P->eVz, P->V_hat, P->lp, P->pfloor, P->Zi, P->a2s, colsum, part,
+            (P->thrU && P->thrV) ? P->thrU + (long long)g * P->n_rows : nullptr, P->thrU ? P->thrV : nullptr,
+            det_cs, det_part);
+        if (check_launch("k_pass_rows(sparse)") != ORI_OK) return ORI_ECUDA;
+        return det_sums();
     }
 #define ORI_LAUNCH_PR(D, E)                                                                              \
     k_pass_rows<KP, D, E, false><<<grid, PR_TR, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, P->eU[g], P->U_hat[g], \
@@ -1110,17 +1108,13 @@ static int pass_genes_kp(const ori_problem_t* P, int g, cudaStream_t st) {
         return check_launch("k_det_sum_chunks");
     };
     if (P->flags & ORI_F_SPARSE) {
-        if constexpr (KP <= 32) {
-            k_pass_genes<KP, true, false, true><<<grid, PG_TG, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, (int)rpc,
-                P->eU[g], nullptr, P->U_hat[g], P->U_hat[1 - g], P->eUl[g], P->eVd, P->Vh_old, P->lp, P->pfloor,
-                Zj, b2s, P->red32 + 2ll * P->p * P->KP,
-                (P->thrU && P->thrV) ? P->thrU + (long long)g * P->n_rows : nullptr, P->thrU ? P->thrV : nullptr,
-                det_z, det_stride);
-            if (check_launch("k_pass_genes(sparse)") != ORI_OK) return ORI_ECUDA;
-            return det_sums();
-        } else {
-            return set_error(ORI_EUNSUPPORTED, "the sparse model needs K <= 32");
-        }
+        k_pass_genes<KP, true, false, true><<<grid, PG_TG, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, (int)rpc,
+            P->eU[g], nullptr, P->U_hat[g], P->U_hat[1 - g], P->eUl[g], P->eVd, P->Vh_old, P->lp, P->pfloor,
+            Zj, b2s, P->red32 + 2ll * P->p * P->KP,
+            (P->thrU && P->thrV) ? P->thrU + (long long)g * P->n_rows : nullptr, P->thrU ? P->thrV : nullptr,
+            det_z, det_stride);
+        if (check_launch("k_pass_genes(sparse)") != ORI_OK) return ORI_ECUDA;
+        return det_sums();
     }
 #define ORI_LAUNCH_PG(D, Q)                                                                             \
     k_pass_genes<KP, D, Q, false><<<grid, PG_TG, 0, st>>>(P->X, P->ldx, P->n_rows, P->p, (int)rpc, P->eU[g], \

@@ -8,7 +8,7 @@ One CAVI iteration is the ZIGaP iteration with three changes (sparse_zigap.py:11
   * the gene side updates V' AND S (:144-163) and the M-step also refreshes pi_s (:196);
   * the dropout posterior multiplies the NEW U_hat with the effective V_hat = S_hat * V'_hat of the iteration's START
     (:140, :166) -- so the kernels that rebuild D_hat on the fly keep one older generation of it (`Vh_old`).
-K <= 32; no ELBO (the reference's convergence trace for this model is the deviance, `reconstruction_deviance()` /
+K <= 64 (tensor kernels: K <= 32); no ELBO (the reference's convergence trace for this model is the deviance, `reconstruction_deviance()` /
 `explained_deviance()`, base.py:58-82, evaluated on the device).
 
 Kernel family.  The S update is a sigmoid of the difference of two large gene-side sums (:157-160), so p_s amplifies
@@ -36,8 +36,13 @@ class SparseZIGaP(ZIGaP):
     def __init__(self, *args, tau=0.5, **kwargs):
         if kwargs.get('compat_quirk'):
             raise ValueError('compat_quirk is a ZIGaP switch (zigap.py:94); sparse_zigap.py:115 has the correct index')
-        if kwargs.get('k', args[1] if len(args) > 1 else 2) > 32:
-            raise ValueError('SparseZIGaP supports k <= 32')
+        k = kwargs.get('k', args[1] if len(args) > 1 else 2)
+        if k > 64:
+            raise ValueError('SparseZIGaP supports k <= 64')
+        if k > 32:                                                # the tensor plans of this model exist for k <= 32
+            if kwargs.get('tensor'):
+                raise ValueError('SparseZIGaP: the tensor path needs k <= 32 (32 < k <= 64 runs on the CUDA-core kernels)')
+            kwargs['tensor'] = False
         kwargs['elbo'] = False
         kwargs.setdefault('precise', True)                        # fp32-grade sums (see the module docstring)
         self._col_mean = None

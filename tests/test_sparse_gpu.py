@@ -67,7 +67,7 @@ def test_sparse_trajectory_and_deviance_match_reference(cuda_lib, name, path):
             assert abs(m.explained_deviance() - expl_ref) <= 1e-4 * abs(expl_ref), (name, t)
 
 
-@pytest.mark.parametrize('shape', [(700, 450, 6), (257, 1031, 20), (1500, 90, 32)])
+@pytest.mark.parametrize('shape', [(700, 450, 6), (257, 1031, 20), (1500, 90, 32), (300, 210, 40), (129, 77, 64)])
 def test_sparse_fresh_problem_matches_oracle(cuda_lib, shape):
     from oracle import cavi_numpy as cn, sparse_numpy as sn
     n, p, K = shape
@@ -112,7 +112,13 @@ def test_sparse_constructor_path_and_snapshot(cuda_lib):
     for k in KEYS:
         assert relerr(getattr(m2, k).asarray(), getattr(m, k).asarray()) < 1e-5, k
     with pytest.raises(ValueError):
-        SparseZIGaP(CountMatrix(X), k=40, use_factors=False)
+        SparseZIGaP(CountMatrix(X), k=65, use_factors=False)
+    with pytest.raises(ValueError):
+        SparseZIGaP(CountMatrix(X), k=40, use_factors=False, tensor=True)     # tensor plans of this model: k <= 32
+    m40 = SparseZIGaP(CountMatrix(X), k=40, use_factors=False)                # 32 < k <= 64: CUDA-core kernels
+    assert not m40.uses_tensor_path
+    m40.step()
+    assert np.isfinite(m40.b1.asarray()).all() and np.isfinite(m40.reconstruction_deviance())
 
 
 def test_sparse_tensor_paths_track_the_cuda_core_path(cuda_lib):

@@ -403,6 +403,20 @@ def main():
                 'frac': dom['achieved'] / peak, 'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': alg_bytes, 'kernels': kernels,
                 'step_frac': (8.0 * rows * p / (ms_step * 1e-3) / 1e9) / peak}
+    # second roofline of the same kernels (profiles/r2_xu_mio_bound.md): a MUFU costs 8 cycles per warp instruction and SM
+    # sub-partition (16 lanes / clk / SM, measured); the row pass issues 2 per entry (ex2 + rcp), the gene pass 3 (+ lg2 of
+    # the ELBO).  Floor = entries x MUFU / (SMs x 16 x the median SM clock sampled during the timed region).
+    if uses_tc and clocks.get('sm_mhz'):
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        per = {'pass_rows': 2, 'pass_genes': 3}
+        xu = []
+        for k in kernels:
+            floor_ms = rows * p * per[k['kernel']] / (sms * 16.0 * clocks['sm_mhz'] * 1e6) * 1e3
+            xu.append({'kernel': k['kernel'], 'mufu_per_entry': per[k['kernel']], 'floor_ms': floor_ms, 'frac': floor_ms / k['ms']})
+        step_floor = sum(x['floor_ms'] for x in xu)
+        roofline['xu'] = {'bound': 'special-function (MUFU) issue, not a contract field: explains the HBM fraction', 'sm_mhz': clocks['sm_mhz'],
+                          'kernels': xu, 'step_floor_ms': step_floor, 'step_frac': step_floor / ms_step,
+                          'hbm_step_floor_ms': 8.0 * rows * p / (peak * 1e9) * 1e3}
 
     # ---- end to end through host buffers
     e2e = None

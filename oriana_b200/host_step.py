@@ -299,6 +299,7 @@ class HostStreamedCAVI:
             s['stage'] = torch.zeros((2, S, K), **f32)     # unpadded a1|a2 as they travel
             self._slabs.append(s)
         self._streams = [torch.cuda.Stream(device=dev) for _ in self._slabs]
+        self._copy_stream = torch.cuda.Stream(device=dev)
         self._Pg = self._problem(None, 0)
         self._keep_hyper = keep_hyper
         self._init_pass()
@@ -362,58 +363,86 @@ class HostStreamedCAVI:
         g['scal'].copy_(self.scal, non_blocking=True)
         self.h2d_bytes += 2 * self.p * K * 4 + 4 * K * 8 + self.p * 8 + _lib.SCAL_SLOTS * 8
 
-    def _upload_slab(self, s, r0, rows):
+    def _copy_slab(self, s, r0, rows):
+        """Host -> device copies of one slab (current stream = the copy stream): X in the form the host holds it, the escape
+        list, the row parameters.  Returns what `_finish_upload` needs."""
         K, p = self.k, self.p
+        info = dict(lo=0, cnt=0)
         xbytes_sent = rows * p * self._xbytes
         if self._xbytes == 4:
             s['X'][:rows, :p].copy_(self.X[r0:r0 + rows], non_blocking=True)
+        elif self._sparse is not None:
+            sp = self._sparse
+            lo, hi = sp.byte_range(r0, r0 + rows)
+            s['bm'][:rows].copy_(sp.bitmap[r0:r0 + rows], non_blocking=True)
+            if hi > lo:
+                s['nz'][:hi - lo].copy_(sp.nz[lo:hi], non_blocking=True)
+            s['off'][:rows + 1].copy_(sp.rowoff[r0:r0 + rows + 1], non_blocking=True)
+            info['lo'] = lo
+            xbytes_sent = rows * s['bm'].shape[1] * 4 + (hi - lo) + (rows + 1) * 8
         else:
-            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-            if self._sparse is not None:
-                sp = self._sparse
-                lo, hi = sp.byte_range(r0, r0 + rows)
-                s['bm'][:rows].copy_(sp.bitmap[r0:r0 + rows], non_blocking=True)
-                if hi > lo:
-                    s['nz'][:hi - lo].copy_(sp.nz[lo:hi], non_blocking=True)
-                s['off'][:rows + 1].copy_(sp.rowoff[r0:r0 + rows + 1], non_blocking=True)
-                _lib.check(self._lib.ori_expand_bitmap_counts_f32(s['bm'].data_ptr(), s['bm'].shape[1], s['nz'].data_ptr(),
-                                                                  s['off'].data_ptr(), lo, s['X'].data_ptr(), self._ldx, rows, p, st))
-                xbytes_sent = rows * s['bm'].shape[1] * 4 + (hi - lo) + (rows + 1) * 8
-            else:
-                s['Xq'][:rows].copy_(self.X[r0:r0 + rows], non_blocking=True)
-                _lib.check(self._lib.ori_widen_counts_f32(s['Xq'].data_ptr(), self._xbytes, p, s['X'].data_ptr(), self._ldx,
-                                                          rows, p, st))
-            if self._compact is not None:
-                lo, hi = self._compact.escapes(r0, r0 + rows)
-                cnt = hi - lo
-                if cnt:
-                    if cnt > s['esc'][0].numel():          # a slab with unusually many large counts: grow its buffers
-                        s['esc'] = [torch.zeros((2 * cnt,), dtype=t.dtype, device=t.device) for t in s['esc']]
-                    for dst, src in zip(s['esc'], (self._compact.row, self._compact.col, self._compact.val)):
-                        dst[:cnt].copy_(src[lo:hi], non_blocking=True)
-                    _lib.check(self._lib.ori_scatter_counts_f32(s['X'].data_ptr(), self._ldx, r0, rows, p, s['esc'][0].data_ptr(),
-                                                                s['esc'][1].data_ptr(), s['esc'][2].data_ptr(), cnt, st))
-                    self.h2d_bytes += 12 * cnt
-        # row sums of the slab (ELBO scale term, include/oriana_b200.h xrow): X is in HBM anyway
-        _lib.check(self._lib.ori_row_sums_f32(s['X'].data_ptr(), self._ldx, rows, p, s['xrow'].data_ptr(),
-                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            s['Xq'][:rows].copy_(self.X[r0:r0 + rows], non_blocking=True)
+        if self._compact is not None:
+            lo, hi = self._compact.escapes(r0, r0 + rows)
+            cnt = info['cnt'] = hi - lo
+            if cnt:
+                if cnt > s['esc'][0].numel():          # a slab with unusually many large counts: grow its buffers
+                    s['esc'] = [torch.zeros((2 * cnt,), dtype=t.dtype, device=t.device) for t in s['esc']]
+                for dst, src in zip(s['esc'], (self._compact.row, self._compact.col, self._compact.val)):
+                    dst[:cnt].copy_(src[lo:hi], non_blocking=True)
+                self.h2d_bytes += 12 * cnt
         s['stage'][0, :rows].copy_(self.a1[r0:r0 + rows], non_blocking=True)
         s['stage'][1, :rows].copy_(self.a2[r0:r0 + rows], non_blocking=True)
-        s['a1'][:rows, :K] = s['stage'][0, :rows]; s['a2'][:rows, :K] = s['stage'][1, :rows]
         self.h2d_bytes += xbytes_sent + 2 * rows * K * 4
+        return info
+
+    def _finish_upload(self, s, r0, rows, info):
+        """Device side of the upload (current stream = the slab's compute stream): compact counts -> float32 X, escapes, row
+        sums, padded row parameters."""
+        K, p = self.k, self.p
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if self._sparse is not None:
+            _lib.check(self._lib.ori_expand_bitmap_counts_f32(s['bm'].data_ptr(), s['bm'].shape[1], s['nz'].data_ptr(),
+                                                              s['off'].data_ptr(), info['lo'], s['X'].data_ptr(), self._ldx,
+                                                              rows, p, st))
+        elif self._xbytes != 4:
+            _lib.check(self._lib.ori_widen_counts_f32(s['Xq'].data_ptr(), self._xbytes, p, s['X'].data_ptr(), self._ldx,
+                                                      rows, p, st))
+        if info['cnt']:
+            _lib.check(self._lib.ori_scatter_counts_f32(s['X'].data_ptr(), self._ldx, r0, rows, p, s['esc'][0].data_ptr(),
+                                                        s['esc'][1].data_ptr(), s['esc'][2].data_ptr(), info['cnt'], st))
+        # row sums of the slab (ELBO scale term, include/oriana_b200.h xrow): X is in HBM anyway
+        _lib.check(self._lib.ori_row_sums_f32(s['X'].data_ptr(), self._ldx, rows, p, s['xrow'].data_ptr(), st))
+        s['a1'][:rows, :K] = s['stage'][0, :rows]; s['a2'][:rows, :K] = s['stage'][1, :rows]
 
     def _slab_loop(self, body):
+        """Slabs in order.  ALL host -> device copies go through one copy stream, so they run one after the other at the
+        full PCIe rate while the previous slab's kernels run on its compute stream (issued from two compute streams, the
+        copies of two slabs shared the link and both slabs then computed with the link idle: 10 instead of 7.5 ms per
+        slab, scripts/gpu_e2e_timeline.py).  A slab's buffers are refilled once its previous occupant's kernels and
+        device -> host copies are done."""
         main = torch.cuda.current_stream()
         ready = torch.cuda.Event(); ready.record(main)
+        copy_st = self._copy_stream
+        copy_st.wait_event(ready)
+        done = [None] * len(self._slabs)
         for i, r0 in enumerate(range(0, self.n, self.slab)):
             b = i % len(self._slabs)
-            st = self._streams[b]
+            st, s = self._streams[b], self._slabs[b]
             if i < len(self._slabs):
                 st.wait_event(ready)
             rows = min(self.slab, self.n - r0)
+            if done[b] is not None:
+                copy_st.wait_event(done[b])
+            with torch.cuda.stream(copy_st):
+                info = self._copy_slab(s, r0, rows)
+                arrived = torch.cuda.Event(); arrived.record(copy_st)
+            st.wait_event(arrived)
             with torch.cuda.stream(st):
-                self._upload_slab(self._slabs[b], r0, rows)
-                body(self._slabs[b], self._problem(self._slabs[b], rows), r0, rows, st)
+                self._finish_upload(s, r0, rows, info)
+                body(s, self._problem(s, rows), r0, rows, st)
+                done[b] = torch.cuda.Event(); done[b].record(st)
+        main.wait_stream(copy_st)
         for st in self._streams:
             main.wait_stream(st)
 

@@ -346,11 +346,71 @@ int ori_deviance_sums(const ori_problem_t* P, int gen, const double* pi, const d
 // tensor-path workspaces -- and keeps it between calls: after the first call of a given shape no cudaMalloc, no stream
 // or event is created (ori_ctx_stats counts them).  The *_host entry points without a context argument use one
 // process-wide default context behind a mutex.
+#include <condition_variable>
 #include <mutex>
+#include <thread>
+
+// Host arrays of the reference are pageable numpy memory: a plain cudaMemcpy from them runs at ~11 GB/s (one driver thread
+// staging through its own small pinned buffer).  CopyPool + the context's ring of pinned staging chunks do the same
+// staging with several threads, so that the DMA of chunk i overlaps the memcpy of chunk i+1 (operator seam, bench.py
+// `operator_seam`).
+struct CopyPool {
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    const char* src = nullptr; char* dst = nullptr; size_t bytes = 0;
+    unsigned long long gen = 0;
+    int pending = 0;
+    bool stop = false;
+    void start(int n) {
+        for (int i = 0; i < n; ++i) th.emplace_back([this, i, n] { run(i, n); });
+    }
+    void run(int i, int n) {
+        unsigned long long seen = 0;
+        for (;;) {
+            const char* s_; char* d_; size_t b_;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_go.wait(lk, [&] { return stop || gen != seen; });
+                if (stop) return;
+                seen = gen; s_ = src; d_ = dst; b_ = bytes;
+            }
+            const size_t per = ((b_ + n - 1) / n + 63) & ~(size_t)63;
+            const size_t lo = per * i < b_ ? per * i : b_, hi = lo + per < b_ ? lo + per : b_;
+            if (hi > lo) memcpy(d_ + lo, s_ + lo, hi - lo);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (--pending == 0) cv_done.notify_one();
+            }
+        }
+    }
+    void copy(void* d, const void* s, size_t b) {
+        if (th.empty() || b < (1u << 20)) { memcpy(d, s, b); return; }
+        std::unique_lock<std::mutex> lk(mu);
+        src = (const char*)s; dst = (char*)d; bytes = b; pending = (int)th.size(); ++gen;
+        cv_go.notify_all();
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+    void shutdown() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv_go.notify_all();
+        for (auto& t : th) t.join();
+        th.clear();
+    }
+};
 
 struct ori_ctx {
     cudaStream_t st[2] = {nullptr, nullptr};
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    // pinned staging ring for pageable host inputs
+    static constexpr int NSTG = 4;
+    static constexpr size_t STG_BYTES = 32u << 20;
+    void* stg[NSTG] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t stg_ev[NSTG] = {nullptr, nullptr, nullptr, nullptr};
+    bool stg_busy[NSTG] = {false, false, false, false};
+    int stg_next = 0;
+    CopyPool pool;
+    unsigned long long staged_bytes = 0;
     struct Buf { void* p = nullptr; size_t cap = 0; };
     enum { X0, X1, D0, D1, LUS0, LUS1, EU0, EU1, EUW0, EUW1, EUL0, EUL1, ZI0, ZI1, OI0, OI1, WS0, WS1, THRU0, THRU1,
            LVRAW, EV, ZJ, ZJ3A, ZJ3B, OUTJ, D64, THRV, NBUF };
@@ -370,7 +430,52 @@ struct ori_ctx {
         }
         return ORI_OK;
     }
+    // rows of `width` bytes, contiguous on the host, to a pitched device buffer on stream s.  Pinned (or registered) host
+    // memory is copied directly; pageable memory goes through the staging ring.
+    int h2d_rows(void* dst, size_t dpitch, const void* src, size_t width, int64_t rows, cudaStream_t s) {
+        if (rows <= 0 || width == 0) return ORI_OK;
+        cudaPointerAttributes at;
+        const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (pinned || (size_t)rows * width < (4u << 20)) {
+            const cudaError_t e = cudaMemcpy2DAsync(dst, dpitch, src, width, width, rows, cudaMemcpyHostToDevice, s);
+            return e == cudaSuccess ? ORI_OK : set_error(ORI_ECUDA, "cudaMemcpy2DAsync: %s", cudaGetErrorString(e));
+        }
+        if (!stg[0]) {
+            for (int i = 0; i < NSTG; ++i) {
+                cudaError_t e = cudaHostAlloc(&stg[i], STG_BYTES, cudaHostAllocDefault);
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&stg_ev[i], cudaEventDisableTiming);
+                if (e != cudaSuccess) return set_error(ORI_ECUDA, "pinned staging: %s", cudaGetErrorString(e));
+            }
+            unsigned hc = std::thread::hardware_concurrency();
+            pool.start((int)(hc >= 16 ? 8 : (hc >= 4 ? hc / 2 : 1)));
+            ++allocs;
+        }
+        int64_t per = (int64_t)(STG_BYTES / width);
+        if (per < 1) {     // a single row longer than a staging chunk: let the driver stage it
+            const cudaError_t e = cudaMemcpy2DAsync(dst, dpitch, src, width, width, rows, cudaMemcpyHostToDevice, s);
+            return e == cudaSuccess ? ORI_OK : set_error(ORI_ECUDA, "cudaMemcpy2DAsync: %s", cudaGetErrorString(e));
+        }
+        for (int64_t r = 0; r < rows; r += per) {
+            const int64_t nr = rows - r < per ? rows - r : per;
+            const int i = stg_next; stg_next = (stg_next + 1) % NSTG;
+            if (stg_busy[i]) { cudaEventSynchronize(stg_ev[i]); stg_busy[i] = false; }
+            pool.copy(stg[i], (const char*)src + (size_t)r * width, (size_t)nr * width);
+            cudaError_t e = cudaMemcpy2DAsync((char*)dst + (size_t)r * dpitch, dpitch, stg[i], width, width, nr, cudaMemcpyHostToDevice, s);
+            if (e == cudaSuccess) e = cudaEventRecord(stg_ev[i], s);
+            if (e != cudaSuccess) return set_error(ORI_ECUDA, "staged copy: %s", cudaGetErrorString(e));
+            stg_busy[i] = true;
+            staged_bytes += (size_t)nr * width;
+        }
+        return ORI_OK;
+    }
     void release() {
+        pool.shutdown();
+        for (int i = 0; i < NSTG; ++i) {
+            if (stg_ev[i]) { cudaEventDestroy(stg_ev[i]); stg_ev[i] = nullptr; }
+            if (stg[i]) { cudaFreeHost(stg[i]); stg[i] = nullptr; }
+            stg_busy[i] = false;
+        }
         for (auto& b : buf) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
         for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
         for (auto& s : st) { if (s) cudaStreamDestroy(s); s = nullptr; }
@@ -482,8 +587,8 @@ static int z_operator_ctx(ori_ctx* C, float* Zi_out, float* Zj_out, float* Z3_ou
         float* dlUs = C->as<float>(B::LUS0 + b);
         float* deU = C->as<float>(B::EU0 + b); float* deUw = C->as<float>(B::EUW0 + b); float* deUl = C->as<float>(B::EUL0 + b);
         float* dZi = C->as<float>(B::ZI0 + b); float* dOutI = C->as<float>(B::OI0 + b);
-        ORI_CUDA(cudaMemcpy2DAsync(x, sizeof(float) * ldx, X + r0 * p, sizeof(float) * p, sizeof(float) * p, nr, cudaMemcpyHostToDevice, s));
-        if (D) ORI_CUDA(cudaMemcpy2DAsync(dD, sizeof(float) * ldx, D + r0 * p, sizeof(float) * p, sizeof(float) * p, nr, cudaMemcpyHostToDevice, s));
+        ORI_TRY(C->h2d_rows(x, sizeof(float) * ldx, X + r0 * p, sizeof(float) * p, nr, s));
+        if (D) ORI_TRY(C->h2d_rows(dD, sizeof(float) * ldx, D + r0 * p, sizeof(float) * p, nr, s));
         ORI_CUDA(cudaMemcpyAsync(dlUs, logU + r0 * K, sizeof(float) * nr * K, cudaMemcpyHostToDevice, s));
         k_exp_pad<<<cdiv(nr * KP, 256), 256, 0, s>>>(dlUs, nullptr, 0, 0, deU, nr, (int)K, KP, C->as<float>(B::THRU0 + b));
         if (D && quirk)   // zigap.py:94: weight of cell i for latent k is D_hat[i, k]

@@ -178,3 +178,10 @@ class CountMatrix:
         from ..host_step import CompactCounts
         a = self._data if isinstance(self._data, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(self._data))
         return CompactCounts.from_tensor(a, pin=pin)
+
+    def to_sparse_counts(self, pin=True):
+        """Bitmap + non-zero bytes + escape list (`oriana_b200.host_step.SparseCounts`): the streaming form of
+        `as_sparse_matrix()` (cmatrix.py:100-104) for host-streamed CAVI, p / 8 + nnz bytes per cell."""
+        from ..host_step import SparseCounts
+        a = self._data if isinstance(self._data, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(self._data))
+        return SparseCounts.from_tensor(a, pin=pin)

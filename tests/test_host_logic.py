@@ -161,6 +161,9 @@ def test_count_matrix_ingest_helpers():
     cc = CountMatrix(np.minimum(Y, 1000)).to_compact(pin=False)
     np.testing.assert_array_equal(cc.dense().numpy(), np.minimum(Y, 1000))
     assert cc.row.numel() == 1
+    sc = CountMatrix(np.minimum(Y, 1000)).to_sparse_counts(pin=False)
+    np.testing.assert_array_equal(sc.dense().numpy(), np.minimum(Y, 1000))
+    assert sc.row.numel() == 1 and sc.nz.numel() == int((Y != 0).sum())
 
 
 def test_sparse_counts_round_trip():

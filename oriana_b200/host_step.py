@@ -2,8 +2,9 @@
 
 The reference keeps X and every parameter in host numpy arrays and its `step()` (base.py:54-56) reads and
 writes them in place.  `HostStreamedCAVI.step()` is the same contract on the B200: every step, the count
-matrix and the row-side parameters are streamed from (pinned) host memory in row slabs, the three per-slab
-kernels (row pass -> U update -> gene pass) run while the next slab is in flight on a second stream, the
+matrix and the row-side parameters are streamed from (pinned) host memory in row slabs -- every host -> device
+copy on one copy stream, so the slabs follow each other at the PCIe line rate -- the three per-slab kernels
+(row pass -> U update -> gene pass) run on the slab's own compute stream while the next slab is in flight, the
 updated row parameters stream back, and the gene-side update + M-step run once at the end.  Because the row
 side of the iteration never needs another row (SURVEY.md section 8e iii), a slab is needed on the device
 only while it is processed: the device footprint is two slabs, independent of n (out-of-core in HBM).

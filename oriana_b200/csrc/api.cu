@@ -441,14 +441,16 @@ struct ori_ctx {
             const cudaError_t e = cudaMemcpy2DAsync(dst, dpitch, src, width, width, rows, cudaMemcpyHostToDevice, s);
             return e == cudaSuccess ? ORI_OK : set_error(ORI_ECUDA, "cudaMemcpy2DAsync: %s", cudaGetErrorString(e));
         }
-        if (!stg[0]) {
+        if (!stg[NSTG - 1] || !stg_ev[NSTG - 1]) {
             for (int i = 0; i < NSTG; ++i) {
-                cudaError_t e = cudaHostAlloc(&stg[i], STG_BYTES, cudaHostAllocDefault);
-                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&stg_ev[i], cudaEventDisableTiming);
-                if (e != cudaSuccess) return set_error(ORI_ECUDA, "pinned staging: %s", cudaGetErrorString(e));
+                cudaError_t e = stg[i] ? cudaSuccess : cudaHostAlloc(&stg[i], STG_BYTES, cudaHostAllocDefault);
+                if (e == cudaSuccess && !stg_ev[i]) e = cudaEventCreateWithFlags(&stg_ev[i], cudaEventDisableTiming);
+                if (e != cudaSuccess) return set_error(ORI_ECUDA, "pinned staging: %s", cudaGetErrorString(e));   // retried by the next call
             }
-            unsigned hc = std::thread::hardware_concurrency();
-            pool.start((int)(hc >= 16 ? 8 : (hc >= 4 ? hc / 2 : 1)));
+            if (pool.th.empty()) {
+                unsigned hc = std::thread::hardware_concurrency();
+                pool.start((int)(hc >= 16 ? 8 : (hc >= 4 ? hc / 2 : 1)));
+            }
             ++allocs;
         }
         int64_t per = (int64_t)(STG_BYTES / width);

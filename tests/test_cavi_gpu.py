@@ -382,7 +382,7 @@ def test_host_streamed_step_with_sparse_counts(cuda_lib):
             rc = cuda_lib.ori_expand_bitmap_counts_f32(bm[r0:].data_ptr(), bm.shape[1], nz[lo:].data_ptr() if hi > lo else nz.data_ptr(),
                                                        off[r0:].data_ptr(), lo, dst[r0:].data_ptr(), ldd, rows - r0, p, st())
             assert rc == 0
-            a, b, c = sp.escapes(r0, rows), None, None
+            a = sp.escapes(r0, rows)
             cnt = a[1] - a[0]
             if cnt:
                 er, ec, ev = sp.row[a[0]:a[1]].cuda(), sp.col[a[0]:a[1]].cuda(), sp.val[a[0]:a[1]].cuda()
